@@ -1,0 +1,176 @@
+/*
+ * ultrare_b200 -- C ABI of the B200-native UltraRE sharded-retraining hot path.
+ *
+ * The reference (ZhangYizhao/UltraRE) has no FFI layer: its seam is the Python
+ * call surface of method/utils.py, method/scratch.py, method/sisa.py, group.py
+ * (SURVEY.md §8b).  Each entry point below replaces the arithmetic of one of
+ * those Python functions; the reference-side binding is a ctypes stub
+ * (INTEGRATION.md).  Conventions:
+ *   - every pointer is a raw DEVICE address unless its name starts with h_;
+ *     the caller (PyTorch) owns all memory, the library allocates nothing that
+ *     outlives a call;
+ *   - every launch is asynchronous on the caller's `stream` (a cudaStream_t cast
+ *     to void*); the library never synchronises;
+ *   - every function returns 0 on success, a positive cudaError_t or a negative
+ *     URE_E* code otherwise; ure_last_error() gives the thread-local message;
+ *   - indices are int32 on device; interactions are packed 16-byte records.
+ */
+#ifndef ULTRARE_B200_H
+#define ULTRARE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define URE_ABI_VERSION 1
+#define URE_MAX_SHARDS 256        /* shard models batched in one launch           */
+#define URE_TOP_K 10              /* baseTest(top_k=10), method/utils.py:115      */
+
+#define URE_EINVAL (-1)           /* bad argument                                  */
+#define URE_EUNSUPPORTED (-2)     /* shape outside what the kernels are built for  */
+#define URE_ECOOP (-3)            /* cooperative launch cannot be made resident    */
+
+/* One rating: what RatingData.__getitem__ yields (read.py:118-124) --
+ * (user int, item int, rating fp32 = float32(float64(rating)/max_rating)). */
+typedef struct {
+  int32_t user;
+  int32_t item;
+  float rating;
+  int32_t pad;
+} ure_inter_t;
+
+/* One shard model + its training data: the state Scratch.train builds
+ * (method/scratch.py:59,65-69): MF tables (method/utils.py:30-43), SGD momentum
+ * buffers, dense gradient scratch, and the shard's DataLoader contents. */
+typedef struct {
+  const ure_inter_t* inter; /* [n] the shard's training interactions                      */
+  const int32_t* perm;      /* [n_epochs_total][n] explicit visiting orders, or NULL for   */
+                            /* the keyed Feistel permutation (csrc/feistel.cuh)             */
+  float* P;                 /* [n_user, d] user table                                      */
+  float* Q;                 /* [n_item, d] item table                                      */
+  float* bufP;              /* [n_user, d] momentum buffer (zero before the first step)    */
+  float* bufQ;              /* [n_item, d]                                                 */
+  float* gP;                /* [n_user, d] gradient scratch (zero on entry, zero on exit)  */
+  float* gQ;                /* [n_item, d]                                                 */
+  double* sse;              /* [n_epochs_total] per-epoch sum of squared errors (+=)       */
+  int32_t* lastP;           /* lazy mode only: [n_user] step index each row is current to  */
+  int32_t* lastQ;           /* lazy mode only: [n_item]                                    */
+  int32_t n;                /* interactions in the shard                                   */
+  int32_t n_user;           /* rows of P                                                   */
+  int32_t n_item;           /* rows of Q                                                   */
+  int32_t shard_id;         /* Feistel key component                                       */
+  uint32_t perm_seed;       /* Feistel key component                                       */
+  int32_t reserved;
+} ure_mf_shard_t;
+
+typedef struct {
+  int32_t d;            /* embedding dimension k (config.py:19): 8,16,32,64 or 128          */
+  int32_t batch;        /* config.py:26                                                      */
+  float lr0;            /* config.py:27                                                      */
+  float lr_decay;       /* config.py:28, StepLR gamma (scratch.py:69)                        */
+  int32_t lr_step;      /* StepLR step_size = 50 epochs (scratch.py:69)                      */
+  float weight_decay;   /* config.py:20 lam                                                  */
+  float momentum;       /* config.py:29                                                      */
+  int32_t lazy;         /* 0: dense sweep every step (reference arithmetic, bit-faithful     */
+                        /*    order); 1: closed-form catch-up of untouched rows  */
+} ure_mf_hparams_t;
+
+const char* ure_last_error(void);
+int ure_abi_version(void);
+
+/* Bytes of device scratch ure_mf_train needs (grid barrier + step tables). */
+int64_t ure_mf_train_workspace_bytes(void);
+
+/* baseTrain (method/utils.py:46-111) for ALL shards of `d_shards` at once, for
+ * global steps [step_begin, step_end).  Shard s runs batch (t mod spe_s) of its
+ * epoch (t div spe_s), spe_s = ceil(n_s/batch), and is idle once it has done
+ * `epochs` epochs.  One persistent cooperative launch.  `d_workspace` must be
+ * zero-filled before the first call of a training and reused afterwards. */
+int ure_mf_train(const ure_mf_shard_t* d_shards, int n_shards, const ure_mf_hparams_t* h_hp,
+                 int epochs, int64_t step_begin, int64_t step_end, void* d_workspace, void* stream);
+
+/* Lazy mode: bring every row of every shard up to date (end of training / before export). */
+int ure_mf_flush(const ure_mf_shard_t* d_shards, int n_shards, const ure_mf_hparams_t* h_hp,
+                 int epochs, int64_t step_now, void* stream);
+
+/* Ensemble score of baseTest (method/utils.py:141-148):
+ * score[j] = (sum_k P_k[u_j].Q_k[i_j]) / denom;  *sse += sum_j (score[j]-r_j)^2.
+ * denom = K gives torch.stack(preds).mean(0); denom = 1 gives the partial sum a rank
+ * contributes before the cross-GPU all-reduce (then ure_score_finalize).
+ * d_P / d_Q are device arrays of K table pointers.  d_score and d_sse may be NULL. */
+int ure_ensemble_score(const float* const* d_P, const float* const* d_Q, int n_models, int d,
+                       const ure_inter_t* d_inter, int64_t n, float denom, float* d_score,
+                       double* d_sse, void* stream);
+
+/* score[j] = sum[j] / denom (in place allowed); *sse += sum_j (score[j]-r_j)^2. */
+int ure_score_finalize(const float* d_sum, const ure_inter_t* d_inter, int64_t n, float denom,
+                       float* d_score, double* d_sse, void* stream);
+
+/* HR@10 / NDCG@10 of baseTest (method/utils.py:166-184) over user segments.
+ * Segment s covers rows d_order[d_seg[s] .. d_seg[s+1]) (d_order NULL = identity).
+ * d_out[0] += sum_u ndcg_u ; d_out[1] += sum_u hr_u ; d_out[2] += #users.
+ * Tie rule: descending value, later index first (np.argsort(kind='stable')[::-1]). */
+int ure_rank_metrics(const ure_inter_t* d_inter, const float* d_score, const int32_t* d_order,
+                     const int64_t* d_seg, int64_t n_seg, double* d_out, void* stream);
+
+/* Affected-shard routing (method/sisa.py:76-81): flags[owner[u]] = 1 for u in del. */
+int ure_route_deletions(const int32_t* d_owner, int32_t n_user, const int32_t* d_del, int32_t n_del,
+                        int32_t* d_flags, int32_t n_shards, void* stream);
+
+/* Merge of owner rows (method/sisa.py:52-58 learn, 107-113 unlearn):
+ * row u of d_merged <- P_{owner[u]}[row_of[u]] when owner[u] >= 0 and
+ * (d_retrain == NULL or d_retrain[owner[u]] != 0); rows with owner[u] < 0 are
+ * zeroed when zero_unowned != 0 (learn), else left as they are (unlearn).
+ * d_row_of NULL = the shard table is indexed by global user id. */
+int ure_merge_user_rows(const float* const* d_P, const int32_t* d_owner, const int32_t* d_row_of,
+                        const int32_t* d_retrain, float* d_merged, int32_t n_user, int d,
+                        int zero_unowned, void* stream);
+
+/* Squared-euclidean cost matrix of ot_cluster (method/utils.py:637), transposed to
+ * [n, kpad] row major: M[i,j] = ||x_i||^2 + ||c_j||^2 - 2 x_i.c_j, the contraction on
+ * tcgen05 (kind::tf32, 3-term hi/lo split = fp32-accurate).  Columns j >= k are
+ * filled with +inf.  d multiple of 8, d <= 128; kpad multiple of 16, <= 256.
+ * d_inertia (may be NULL): += sum_i min_j M[i,j] (utils.py:638). */
+int ure_cost_matrix(const float* d_X, int64_t n, int d, const float* d_C, int k, int kpad,
+                    float* d_M, double* d_inertia, void* stream);
+
+/* Same contraction on CUDA cores (fp32 FMA): the check for the tcgen05 kernel. */
+int ure_cost_matrix_simt(const float* d_X, int64_t n, int d, const float* d_C, int k, int kpad,
+                         float* d_M, double* d_inertia, void* stream);
+
+/* One Sinkhorn column pass (replaces the ot.emd call, utils.py:641-644):
+ * for every row i: P_ij = a_i * softmax_j((g_j - M_ij)/eps);  d_colsum[j] += sum_i P_ij.
+ * a_i = 1/n_total.  d_colsum is double [kpad], zero on entry. */
+int ure_sinkhorn_colsum(const float* d_M, int64_t n, int k, int kpad, const float* d_g, float eps,
+                        double n_total, double* d_colsum, void* stream);
+
+/* g_j += eps * (log(1/k) - log(colsum_j)); re-zeroes d_colsum. */
+int ure_sinkhorn_update_g(float* d_g, double* d_colsum, int k, float eps, void* stream);
+
+/* Whole single-GPU Sinkhorn in one persistent cooperative launch:
+ * h_eps[s], h_iters[s] for s < n_stages (epsilon scaling).  d_workspace:
+ * ure_sinkhorn_workspace_bytes() bytes, zero-filled. */
+int64_t ure_sinkhorn_workspace_bytes(void);
+int ure_sinkhorn(const float* d_M, int64_t n, int k, int kpad, float* d_g, const float* h_eps,
+                 const int32_t* h_iters, int n_stages, void* d_workspace, void* stream);
+
+/* Row-normalised plan for given g: P[i,j] = (1/n_total) softmax_j((g_j - M_ij)/eps), [n,k] fp32. */
+int ure_sinkhorn_plan(const float* d_M, int64_t n, int k, int kpad, const float* d_g, float eps,
+                      double n_total, float* d_plan, void* stream);
+
+/* label_i = argmax_j plan[i,j], first maximum wins (utils.py:647). plan fp64 or fp32, ld = row stride. */
+int ure_assign_plan_f64(const double* d_plan, int64_t n, int k, int64_t ld, int32_t* d_label, void* stream);
+int ure_assign_plan_f32(const float* d_plan, int64_t n, int k, int64_t ld, int32_t* d_label, void* stream);
+
+/* label_i = argmax_j (g_j - M_ij) (== argmax of the Sinkhorn plan row), and the
+ * centroid accumulators of utils.py:648: d_sum[j,:] += x_i, d_cnt[j] += 1 (double / int64). */
+int ure_assign_centroids(const float* d_M, int64_t n, int k, int kpad, const float* d_g,
+                         const float* d_X, int d, int32_t* d_label, double* d_sum, int64_t* d_cnt,
+                         void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ULTRARE_B200_H */

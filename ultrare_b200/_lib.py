@@ -1,0 +1,89 @@
+"""ctypes binding of libultrare_b200.so (include/ultrare_b200.h).
+
+There is NO fallback: if the shared library is missing and cannot be built, or a
+call fails, a RuntimeError is raised.  Nothing here imports the CPU oracle.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libultrare_b200.so")
+
+URE_MAX_SHARDS = 256
+URE_TOP_K = 10
+
+_p = C.c_void_p
+_i32, _i64, _f32, _f64 = C.c_int32, C.c_int64, C.c_float, C.c_double
+
+
+class MFShard(C.Structure):
+    """ure_mf_shard_t"""
+    _fields_ = [("inter", _p), ("perm", _p), ("P", _p), ("Q", _p), ("bufP", _p), ("bufQ", _p),
+                ("gP", _p), ("gQ", _p), ("sse", _p), ("lastP", _p), ("lastQ", _p),
+                ("n", _i32), ("n_user", _i32), ("n_item", _i32), ("shard_id", _i32),
+                ("perm_seed", C.c_uint32), ("reserved", _i32)]
+
+
+class MFHParams(C.Structure):
+    """ure_mf_hparams_t"""
+    _fields_ = [("d", _i32), ("batch", _i32), ("lr0", _f32), ("lr_decay", _f32), ("lr_step", _i32),
+                ("weight_decay", _f32), ("momentum", _f32), ("lazy", _i32)]
+
+
+assert C.sizeof(MFShard) == 112 and C.sizeof(MFHParams) == 32
+
+# name -> (restype, argtypes); every symbol include/ultrare_b200.h declares
+SIGNATURES = {
+    "ure_last_error": (C.c_char_p, []),
+    "ure_abi_version": (C.c_int, []),
+    "ure_mf_train_workspace_bytes": (_i64, []),
+    "ure_mf_train": (C.c_int, [_p, C.c_int, C.POINTER(MFHParams), C.c_int, _i64, _i64, _p, _p]),
+    "ure_mf_flush": (C.c_int, [_p, C.c_int, C.POINTER(MFHParams), C.c_int, _i64, _p]),
+    "ure_ensemble_score": (C.c_int, [_p, _p, C.c_int, C.c_int, _p, _i64, _f32, _p, _p, _p]),
+    "ure_score_finalize": (C.c_int, [_p, _p, _i64, _f32, _p, _p, _p]),
+    "ure_rank_metrics": (C.c_int, [_p, _p, _p, _p, _i64, _p, _p]),
+    "ure_route_deletions": (C.c_int, [_p, _i32, _p, _i32, _p, _i32, _p]),
+    "ure_merge_user_rows": (C.c_int, [_p, _p, _p, _p, _p, _i32, C.c_int, C.c_int, _p]),
+    "ure_cost_matrix": (C.c_int, [_p, _i64, C.c_int, _p, C.c_int, C.c_int, _p, _p, _p]),
+    "ure_cost_matrix_simt": (C.c_int, [_p, _i64, C.c_int, _p, C.c_int, C.c_int, _p, _p, _p]),
+    "ure_sinkhorn_colsum": (C.c_int, [_p, _i64, C.c_int, C.c_int, _p, _f32, _f64, _p, _p]),
+    "ure_sinkhorn_update_g": (C.c_int, [_p, _p, C.c_int, _f32, _p]),
+    "ure_sinkhorn_workspace_bytes": (_i64, []),
+    "ure_sinkhorn": (C.c_int, [_p, _i64, C.c_int, C.c_int, _p, C.POINTER(_f32), C.POINTER(_i32), C.c_int, _p, _p]),
+    "ure_sinkhorn_plan": (C.c_int, [_p, _i64, C.c_int, C.c_int, _p, _f32, _f64, _p, _p]),
+    "ure_assign_plan_f64": (C.c_int, [_p, _i64, C.c_int, _i64, _p, _p]),
+    "ure_assign_plan_f32": (C.c_int, [_p, _i64, C.c_int, _i64, _p, _p]),
+    "ure_assign_centroids": (C.c_int, [_p, _i64, C.c_int, C.c_int, _p, _p, C.c_int, _p, _p, _p, _p]),
+}
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load (building first if the .so is absent and nvcc is present) -- or raise."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        from . import build as _build
+        _build.build()
+    try:
+        handle = C.CDLL(LIB_PATH)
+    except OSError as e:
+        raise RuntimeError(f"ultrare_b200: cannot load {LIB_PATH}: {e}. There is no CPU fallback; "
+                           "run `python -m ultrare_b200.build`.") from e
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(handle, name)           # AttributeError if the .so lacks a declared symbol
+        fn.restype, fn.argtypes = res, args
+    if handle.ure_abi_version() != 1:
+        raise RuntimeError("ultrare_b200: ABI version mismatch; rebuild the shared library")
+    _lib = handle
+    return handle
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = lib().ure_last_error().decode(errors="replace")
+        raise RuntimeError(f"ultrare_b200 {what} failed (code {rc}): {msg}")

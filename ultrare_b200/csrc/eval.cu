@@ -1,0 +1,224 @@
+// Ensemble scoring and ranking metrics: the arithmetic of baseTest
+// (reference method/utils.py:115-187) and computeNDCG/computeDCG (utils.py:190-210).
+#include "common.cuh"
+
+namespace ure {
+namespace {
+
+// ---------------------------------------------------------------------------
+// score[j] = mean_k P_k[u].Q_k[i]   (utils.py:141-145);  sse += (score - r)^2 (utils.py:148)
+// A group of D/4 lanes owns one test interaction and walks the K models; when
+// consecutive models share the user table (after the SISA merge all do,
+// sisa.py:57-58) the user row stays in registers.
+// ---------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(256)
+ensemble_score_kernel(const float* const* __restrict__ Pk, const float* const* __restrict__ Qk, int K,
+                      const ure_inter_t* __restrict__ inter, long long n, float denom,
+                      float* __restrict__ score, double* __restrict__ sse) {
+  constexpr int G = D / 4;
+  const int lane = threadIdx.x & 31;
+  const int gl = lane % G;
+  const long long n_groups = ((long long)gridDim.x * blockDim.x) / G;
+  const long long gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
+  // trip count must be uniform across the warp: round n up to the groups of one warp
+  constexpr int GPW = 32 / G;
+  const long long n_round = (n + GPW - 1) / GPW * GPW;
+  double acc = 0.0;
+  for (long long j = gid; j < n_round; j += n_groups) {
+    const bool valid = j < n;
+    int u = 0, it = 0;
+    float r = 0.f;
+    if (valid) {
+      const int4 rec = ld_stream_i4(inter + j);
+      u = rec.x; it = rec.y; r = __int_as_float(rec.z);
+    }
+    float sum = 0.f;
+    const float* lastP = nullptr;
+    float4 pu = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < K; ++k) {
+      const float* P = Pk[k];
+      const float* Q = Qk[k];
+      float dot = 0.f;
+      if (valid) {
+        if (P != lastP) { pu = __ldg(reinterpret_cast<const float4*>(P + (size_t)u * D) + gl); lastP = P; }
+        const float4 qi = __ldg(reinterpret_cast<const float4*>(Q + (size_t)it * D) + gl);
+        dot = pu.x * qi.x;
+        dot = fmaf(pu.y, qi.y, dot);
+        dot = fmaf(pu.z, qi.z, dot);
+        dot = fmaf(pu.w, qi.w, dot);
+      }
+#pragma unroll
+      for (int o = G / 2; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o, G);
+      sum += dot;
+    }
+    if (valid && gl == 0) {
+      const float sc = sum / denom;             // torch.stack(preds).mean(0): sum then divide
+      if (score) score[j] = sc;
+      const float e = sc - r;
+      acc += (double)e * (double)e;
+    }
+  }
+  acc = warp_sum(acc);
+  __shared__ double part[8];
+  if (lane == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0 && sse) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += part[w];
+    if (t != 0.0) atomicAdd(sse, t);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// HR@10 / NDCG@10 per user segment, one warp per user (utils.py:166-181).
+//   rank_v(e) = #{e' : v(e') > v(e) or (v(e') == v(e) and e' > e)}   ("later index first")
+//   top_pred[p] / top_rating[p] = element of rank p  (p < 10)
+//   relevance[p] = r[top_pred[p]] ; hit = relevance >= 4/5 ; HR = #hit / 10
+//   common[p] = top_rating[p] in set(top_pred)        (positional, utils.py:179)
+//   NDCG = (sum_p relevance[p]*hit[p]*common[p] * w_p) / sum_p w_p,  w_0 = 1, w_p = 1/log2(p+1)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+rank_metrics_kernel(const ure_inter_t* __restrict__ inter, const float* __restrict__ score,
+                    const int32_t* __restrict__ order, const long long* __restrict__ seg, long long n_seg,
+                    double* __restrict__ out) {
+  __shared__ int top_pred[8][URE_TOP_K];
+  __shared__ int top_rating[8][URE_TOP_K];
+  const int lane = threadIdx.x & 31;
+  const int w = threadIdx.x >> 5;
+  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  double ndcg_sum = 0.0, hr_sum = 0.0, users = 0.0;
+  for (long long sgm = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; sgm < n_seg; sgm += n_warps) {
+    const long long b = seg[sgm];
+    const int L = (int)(seg[sgm + 1] - b);
+    if (L <= 0) continue;
+    if (lane < URE_TOP_K) { top_pred[w][lane] = -1; top_rating[w][lane] = -1; }
+    __syncwarp();
+    for (int e = lane; e < L; e += 32) {
+      const long long re = order ? order[b + e] : b + e;
+      const float ve = score[re];
+      const float te = inter[re].rating;
+      int rp = 0, rr = 0;
+      for (int f = 0; f < L; ++f) {
+        const long long rf = order ? order[b + f] : b + f;
+        const float vf = score[rf];
+        const float tf = inter[rf].rating;
+        rp += (vf > ve) || (vf == ve && f > e);
+        rr += (tf > te) || (tf == te && f > e);
+      }
+      if (rp < URE_TOP_K) top_pred[w][rp] = e;
+      if (rr < URE_TOP_K) top_rating[w][rr] = e;
+    }
+    __syncwarp();
+    double rel = 0.0, hit = 0.0;
+    if (lane < URE_TOP_K && lane < L) {
+      const int ep = top_pred[w][lane];
+      const long long rpos = order ? order[b + ep] : b + ep;
+      const double relevance = (double)inter[rpos].rating;
+      const bool h = relevance >= (4.0 / 5.0);
+      const int tr = top_rating[w][lane];
+      bool common = false;
+#pragma unroll
+      for (int q = 0; q < URE_TOP_K; ++q) common |= (top_pred[w][q] == tr);
+      hit = h ? 1.0 : 0.0;
+      const double wgt = lane == 0 ? 1.0 : 1.0 / log2((double)(lane + 1));
+      rel = (h && common) ? relevance * wgt : 0.0;
+    }
+    rel = warp_sum(rel);
+    hit = warp_sum(hit);
+    if (lane == 0) {
+      double idcg = 1.0;
+      for (int p = 1; p < URE_TOP_K; ++p) idcg += 1.0 / log2((double)(p + 1));
+      ndcg_sum += rel / idcg;
+      hr_sum += hit / (double)URE_TOP_K;
+      users += 1.0;
+    }
+    __syncwarp();
+  }
+  if (lane == 0 && users > 0.0) {
+    atomicAdd(out + 0, ndcg_sum);
+    atomicAdd(out + 1, hr_sum);
+    atomicAdd(out + 2, users);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+score_finalize_kernel(const float* __restrict__ sum, const ure_inter_t* __restrict__ inter, long long n, float denom,
+                      float* __restrict__ score, double* __restrict__ sse) {
+  double acc = 0.0;
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (long long)gridDim.x * blockDim.x) {
+    const float sc = sum[j] / denom;
+    score[j] = sc;
+    const float e = sc - inter[j].rating;
+    acc += (double)e * (double)e;
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0 && sse && acc != 0.0) atomicAdd(sse, acc);
+}
+
+template <int D>
+int launch_score(const float* const* P, const float* const* Q, int K, const ure_inter_t* inter, long long n,
+                 float denom, float* score, double* sse, cudaStream_t st) {
+  constexpr int G = D / 4;
+  const long long groups_per_block = 256 / G;
+  long long blocks = (n + groups_per_block - 1) / groups_per_block;
+  const long long cap = (long long)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  ensemble_score_kernel<D><<<(unsigned)blocks, 256, 0, st>>>(P, Q, K, inter, n, denom, score, sse);
+  URE_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+}  // namespace ure
+
+extern "C" int ure_ensemble_score(const float* const* d_P, const float* const* d_Q, int n_models, int d,
+                                  const ure_inter_t* d_inter, int64_t n, float denom, float* d_score,
+                                  double* d_sse, void* stream) {
+  using namespace ure;
+  URE_REQUIRE(d_P && d_Q && (d_inter || n == 0), URE_EINVAL, "ure_ensemble_score: null argument");
+  URE_REQUIRE(n_models >= 1 && denom > 0.f, URE_EINVAL, "ure_ensemble_score: n_models=%d denom=%g", n_models, (double)denom);
+  if (n <= 0) return 0;
+  auto st = static_cast<cudaStream_t>(stream);
+  switch (d) {
+    case 8: return launch_score<8>(d_P, d_Q, n_models, d_inter, n, denom, d_score, d_sse, st);
+    case 16: return launch_score<16>(d_P, d_Q, n_models, d_inter, n, denom, d_score, d_sse, st);
+    case 32: return launch_score<32>(d_P, d_Q, n_models, d_inter, n, denom, d_score, d_sse, st);
+    case 64: return launch_score<64>(d_P, d_Q, n_models, d_inter, n, denom, d_score, d_sse, st);
+    case 128: return launch_score<128>(d_P, d_Q, n_models, d_inter, n, denom, d_score, d_sse, st);
+    default:
+      set_error("ure_ensemble_score: d=%d not in {8,16,32,64,128}", d);
+      return URE_EUNSUPPORTED;
+  }
+}
+
+extern "C" int ure_score_finalize(const float* d_sum, const ure_inter_t* d_inter, int64_t n, float denom,
+                                  float* d_score, double* d_sse, void* stream) {
+  using namespace ure;
+  URE_REQUIRE(n == 0 || (d_sum && d_inter && d_score), URE_EINVAL, "ure_score_finalize: null argument");
+  URE_REQUIRE(denom > 0.f, URE_EINVAL, "ure_score_finalize: denom=%g", (double)denom);
+  if (n <= 0) return 0;
+  long long blocks = (n + 255) / 256;
+  const long long cap = (long long)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  score_finalize_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_sum, d_inter, n, denom,
+                                                                                     d_score, d_sse);
+  URE_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int ure_rank_metrics(const ure_inter_t* d_inter, const float* d_score, const int32_t* d_order,
+                                const int64_t* d_seg, int64_t n_seg, double* d_out, void* stream) {
+  using namespace ure;
+  URE_REQUIRE(d_out && (n_seg == 0 || (d_inter && d_score && d_seg)), URE_EINVAL,
+              "ure_rank_metrics: null argument");
+  if (n_seg <= 0) return 0;
+  long long blocks = (n_seg + 7) / 8;
+  const long long cap = (long long)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  rank_metrics_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      d_inter, d_score, d_order, reinterpret_cast<const long long*>(d_seg), n_seg, d_out);
+  URE_CUDA(cudaGetLastError());
+  return 0;
+}

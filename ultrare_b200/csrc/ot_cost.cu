@@ -1,0 +1,384 @@
+// User-to-centroid squared-euclidean cost matrix on the 5th-gen tensor cores.
+//
+// Replaces  dist = ((X - centroid[:, None])**2).sum(axis=2)   (reference
+// method/utils.py:637, a NumPy broadcast that materialises [k,n,d]) by
+//     M[i,j] = ||x_i||^2 + ||c_j||^2 - 2 * (X C^T)[i,j]
+// with the contraction X C^T issued as tcgen05.mma kind::tf32 on 128-row tiles and
+// fp32 accumulators in TMEM.  Plain TF32 (10-bit mantissa) would destroy the 1e-5
+// relative cost tolerance the Sinkhorn plan needs, so both operands
+// are split x = hi + lo with hi = x & 0xFFFFE000 (exactly representable in tf32) and
+// three MMAs hi*hi + hi*lo + lo*hi are accumulated: error ~2^-21 relative.
+//
+// Pipeline per CTA (persistent over row tiles, 128 threads):
+//   bulk-TMA (cp.async.bulk, 1-D) stages the raw fp32 tile [128, d] into shared memory
+//   under an mbarrier; all threads split it into the K-major no-swizzle UMMA core-matrix
+//   layout ([d/4 chunks][128 rows][16 B]) and reduce the row norms; one thread issues
+//   3*d/8 MMAs and commits to an mbarrier; the four warps read their 32 TMEM lanes back
+//   with tcgen05.ld, apply the norm epilogue and store the rows of M.
+// The problem is bound by reading X (4*n*d bytes), not by the tensor pipe (Appendix D).
+#include "common.cuh"
+
+namespace ure {
+namespace {
+
+constexpr int kTileRows = 128;
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* holder_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(holder_smem)), "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+//   [0,14) start>>4 | [16,30) LBO>>4 (stride between the two 16-byte K chunks of one MMA)
+//   [32,46) SBO>>4 (stride between 8-row groups) | [46,48) version = 1 | [61,64) layout = 0
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+// cute::UMMA::InstrDescriptor for kind::tf32, fp32 accumulate, both operands K-major, M = 128
+__device__ __forceinline__ uint32_t make_idesc_tf32(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileRows >> 4) << 24);
+}
+
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+struct CostSmemLayout {
+  uint32_t raw_off, raw_stage_bytes, stages;
+  uint32_t a_hi, a_lo, lbo_a;
+  uint32_t b_hi, b_lo, lbo_b;
+  uint32_t xnorm, cnorm, bars, holder, total;
+};
+
+__host__ __device__ inline CostSmemLayout cost_layout(int D, int NB, int stages) {
+  CostSmemLayout L;
+  const uint32_t chunks = D / 4;
+  L.lbo_a = kTileRows * 16 + (chunks >= 8 ? 16 : 32);
+  L.lbo_b = NB * 16 + (chunks >= 8 ? 16 : 32);
+  uint32_t o = 0;
+  L.stages = stages;
+  L.raw_stage_bytes = kTileRows * D * 4;
+  L.raw_off = o; o += L.raw_stage_bytes * stages;
+  L.a_hi = o; o += L.lbo_a * chunks;
+  L.a_lo = o; o += L.lbo_a * chunks;
+  L.b_hi = o; o += L.lbo_b * chunks;
+  L.b_lo = o; o += L.lbo_b * chunks;
+  L.xnorm = o; o += kTileRows * 4;
+  L.cnorm = o; o += NB * 4;
+  L.bars = o; o += 8 * 4;       // full[2], mma
+  L.holder = o; o += 16;
+  L.total = o;
+  return L;
+}
+
+template <int D>
+__global__ void __launch_bounds__(kTileRows)
+cost_tc_kernel(const float* __restrict__ X, long long n, const float* __restrict__ C, int k, int kpad, int NB,
+               int stages, uint32_t tmem_cols, float* __restrict__ M, double* __restrict__ inertia) {
+  constexpr int CH = D / 4;                    // 16-byte K chunks per row
+  extern __shared__ __align__(128) unsigned char sm[];
+  const CostSmemLayout L = cost_layout(D, NB, stages);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sm + L.bars);
+  uint64_t* mma_bar = full + 2;
+  uint32_t* holder = reinterpret_cast<uint32_t*>(sm + L.holder);
+  float* xnorm = reinterpret_cast<float*>(sm + L.xnorm);
+  float* cnorm = reinterpret_cast<float*>(sm + L.cnorm);
+  const int col0 = blockIdx.y * NB;            // first centroid column of this CTA
+
+  if (tid == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    mbar_init(mma_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(holder, tmem_cols);
+
+  // ---- centroid block -> B_hi / B_lo (K-major core-matrix layout) + ||c||^2
+  for (int idx = tid; idx < NB * CH; idx += kTileRows) {
+    const int j = idx / CH, c = idx % CH;
+    const int col = col0 + j;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (col < k) v = __ldg(reinterpret_cast<const float4*>(C + (size_t)col * D) + c);
+    float4 hi = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+    float4 lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
+    *reinterpret_cast<float4*>(sm + L.b_hi + c * L.lbo_b + j * 16) = hi;
+    *reinterpret_cast<float4*>(sm + L.b_lo + c * L.lbo_b + j * 16) = lo;
+    float s = (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+#pragma unroll
+    for (int o = CH / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o, CH);
+    if (c == 0) cnorm[j] = col < k ? s : INFINITY;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *holder;
+  const uint32_t idesc = make_idesc_tf32(NB);
+  const uint32_t a_hi_addr = smem_u32(sm + L.a_hi), a_lo_addr = smem_u32(sm + L.a_lo);
+  const uint32_t b_hi_addr = smem_u32(sm + L.b_hi), b_lo_addr = smem_u32(sm + L.b_lo);
+
+  const long long n_tiles = (n + kTileRows - 1) / kTileRows;
+  auto tile_bytes = [&](long long tile) -> uint32_t {
+    const long long rows = (n - tile * kTileRows) < kTileRows ? (n - tile * kTileRows) : kTileRows;
+    return (uint32_t)(rows * D * 4);
+  };
+  auto issue_load = [&](long long tile, int stage) {
+    const uint32_t bytes = tile_bytes(tile);
+    mbar_expect_tx(&full[stage], bytes);
+    bulk_g2s(sm + L.raw_off + (size_t)stage * L.raw_stage_bytes, X + tile * kTileRows * (long long)D, bytes, &full[stage]);
+  };
+
+  long long tile = blockIdx.x;
+  if (tid == 0 && tile < n_tiles) issue_load(tile, 0);
+  double inertia_acc = 0.0;
+  for (int it = 0; tile < n_tiles; ++it, tile += gridDim.x) {
+    const int stage = stages == 2 ? (it & 1) : 0;
+    const uint32_t full_parity = stages == 2 ? ((it >> 1) & 1) : (it & 1);
+    const long long next = tile + gridDim.x;
+    if (stages == 2 && tid == 0 && next < n_tiles) issue_load(next, stage ^ 1);
+    mbar_wait(&full[stage], full_parity);
+
+    // ---- split the raw tile into hi / lo operand tiles, reduce row norms
+    const float* raw = reinterpret_cast<const float*>(sm + L.raw_off + (size_t)stage * L.raw_stage_bytes);
+#pragma unroll 4
+    for (int m = 0; m < CH; ++m) {
+      const int idx = tid + m * kTileRows;
+      const int r = idx / CH, c = idx % CH;
+      const float4 v = *reinterpret_cast<const float4*>(raw + r * D + c * 4);
+      const float4 hi = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+      const float4 lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
+      *reinterpret_cast<float4*>(sm + L.a_hi + c * L.lbo_a + r * 16) = hi;
+      *reinterpret_cast<float4*>(sm + L.a_lo + c * L.lbo_a + r * 16) = lo;
+      float s = (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+#pragma unroll
+      for (int o = CH / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o, CH);
+      if (c == 0) xnorm[r] = s;
+    }
+    fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+    __syncthreads();
+
+    if (tid == 0) {
+      if (stages == 1 && next < n_tiles) issue_load(next, 0);     // raw tile fully consumed
+      tc_fence_after();
+#pragma unroll
+      for (int kk = 0; kk < D / 8; ++kk) {
+        const uint64_t ah = make_desc(a_hi_addr + kk * 2 * L.lbo_a, L.lbo_a, 128);
+        const uint64_t al = make_desc(a_lo_addr + kk * 2 * L.lbo_a, L.lbo_a, 128);
+        const uint64_t bh = make_desc(b_hi_addr + kk * 2 * L.lbo_b, L.lbo_b, 128);
+        const uint64_t bl = make_desc(b_lo_addr + kk * 2 * L.lbo_b, L.lbo_b, 128);
+        umma_tf32(tmem_base, ah, bh, idesc, kk > 0);
+        umma_tf32(tmem_base, ah, bl, idesc, 1);
+        umma_tf32(tmem_base, al, bh, idesc, 1);
+      }
+      umma_commit(mma_bar);       // implies tcgen05.fence::before_thread_sync
+    }
+    mbar_wait(mma_bar, it & 1);
+    tc_fence_after();
+
+    // ---- epilogue: thread = row = TMEM lane
+    const long long row = tile * kTileRows + tid;
+    const float xn = xnorm[tid];
+    float rmin = INFINITY;
+    for (int c0 = 0; c0 < NB; c0 += 16) {
+      float acc[16];
+      tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, acc);
+      if (row < n) {
+        float out[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          out[j] = fmaf(-2.f, acc[j], xn + cnorm[c0 + j]);
+          rmin = fminf(rmin, out[j]);
+        }
+        float4* dst = reinterpret_cast<float4*>(M + row * kpad + col0 + c0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) dst[q] = make_float4(out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]);
+      }
+    }
+    if (inertia && row < n) inertia_acc += (double)rmin;
+    tc_fence_before();
+    __syncthreads();              // TMEM accumulator and A tiles may be overwritten now
+  }
+  if (inertia) {
+    inertia_acc = warp_sum(inertia_acc);
+    if (lane == 0 && inertia_acc != 0.0) atomicAdd(inertia, inertia_acc);
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// ------------------------------------------------------------------ CUDA-core check kernel
+// Direct fp32 sum_t (x-c)^2 (the reference expression): one thread per (row, column).
+__global__ void cost_simt_kernel(const float* __restrict__ X, long long n, int d, const float* __restrict__ C, int k,
+                                 int kpad, float* __restrict__ M) {
+  const long long x = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= n * kpad) return;
+  const long long i = x / kpad;
+  const int j = (int)(x % kpad);
+  float s = INFINITY;
+  if (j < k) {
+    s = 0.f;
+    for (int t = 0; t < d; ++t) {
+      const float df = __ldg(X + i * d + t) - __ldg(C + (size_t)j * d + t);
+      s = fmaf(df, df, s);
+    }
+  }
+  M[x] = s;
+}
+
+__global__ void rowmin_sum_kernel(const float* __restrict__ M, long long n, int k, int kpad, double* __restrict__ out) {
+  double acc = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float m = INFINITY;
+    for (int j = 0; j < k; ++j) m = fminf(m, M[i * kpad + j]);
+    acc += (double)m;
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0 && acc != 0.0) atomicAdd(out, acc);
+}
+
+int launch_rowmin(const float* M, long long n, int k, int kpad, double* inertia, cudaStream_t st) {
+  long long blocks = (n + 255) / 256;
+  const long long cap = (long long)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  rowmin_sum_kernel<<<(unsigned)blocks, 256, 0, st>>>(M, n, k, kpad, inertia);
+  URE_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <int D>
+int launch_cost_tc(const float* X, long long n, const float* C, int k, int kpad, float* M, double* inertia,
+                   cudaStream_t st) {
+  // choose the column block NB (multiple of 16) and the number of raw stages that fit in shared memory
+  const uint32_t budget = 220 * 1024;
+  int NB = kpad, stages = 2;
+  while (true) {
+    if (cost_layout(D, NB, stages).total <= budget) break;
+    if (stages == 2 && cost_layout(D, NB, 1).total <= budget) { stages = 1; break; }
+    if (NB <= 16) { set_error("ure_cost_matrix: d=%d does not fit shared memory", D); return URE_EUNSUPPORTED; }
+    NB = ((NB / 2 + 15) / 16) * 16;
+    stages = 2;
+  }
+  const int col_blocks = (kpad + NB - 1) / NB;
+  URE_REQUIRE(col_blocks * NB == kpad, URE_EUNSUPPORTED, "ure_cost_matrix: kpad=%d not divisible into %d-column blocks",
+              kpad, NB);
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < NB) tmem_cols <<= 1;
+  const CostSmemLayout L = cost_layout(D, NB, stages);
+  auto kern = cost_tc_kernel<D>;
+  URE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+  int occ = 0;
+  URE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kTileRows, L.total));
+  URE_REQUIRE(occ >= 1, URE_EUNSUPPORTED, "ure_cost_matrix: kernel cannot be resident (smem %u)", L.total);
+  const int max_by_tmem = 512 / (int)tmem_cols;
+  if (occ > max_by_tmem) occ = max_by_tmem;
+  if (occ > 8) occ = 8;
+  const long long n_tiles = (n + kTileRows - 1) / kTileRows;
+  long long gx = (long long)num_sms() * occ / col_blocks;
+  if (gx < 1) gx = 1;
+  if (gx > n_tiles) gx = n_tiles;
+  double* fused_inertia = (col_blocks == 1) ? inertia : nullptr;
+  kern<<<dim3((unsigned)gx, (unsigned)col_blocks), kTileRows, L.total, st>>>(X, n, C, k, kpad, NB, stages, tmem_cols, M,
+                                                                            fused_inertia);
+  URE_CUDA(cudaGetLastError());
+  if (inertia && !fused_inertia) return launch_rowmin(M, n, k, kpad, inertia, st);
+  return 0;
+}
+
+int check_cost_args(const float* X, long long n, int d, const float* C, int k, int kpad, float* M, const char* who) {
+  URE_REQUIRE(X && C && M, URE_EINVAL, "%s: null argument", who);
+  URE_REQUIRE(n > 0 && k >= 1 && k <= kpad && kpad % 16 == 0 && kpad <= 256, URE_EINVAL,
+              "%s: bad shape n=%lld k=%d kpad=%d (kpad multiple of 16, <= 256)", who, n, k, kpad);
+  URE_REQUIRE(d >= 1, URE_EINVAL, "%s: d=%d", who, d);
+  return 0;
+}
+
+}  // namespace
+}  // namespace ure
+
+extern "C" int ure_cost_matrix(const float* d_X, int64_t n, int d, const float* d_C, int k, int kpad, float* d_M,
+                               double* d_inertia, void* stream) {
+  using namespace ure;
+  if (int rc = check_cost_args(d_X, n, d, d_C, k, kpad, d_M, "ure_cost_matrix")) return rc;
+  auto st = static_cast<cudaStream_t>(stream);
+  switch (d) {
+    case 8: return launch_cost_tc<8>(d_X, n, d_C, k, kpad, d_M, d_inertia, st);
+    case 16: return launch_cost_tc<16>(d_X, n, d_C, k, kpad, d_M, d_inertia, st);
+    case 32: return launch_cost_tc<32>(d_X, n, d_C, k, kpad, d_M, d_inertia, st);
+    case 64: return launch_cost_tc<64>(d_X, n, d_C, k, kpad, d_M, d_inertia, st);
+    case 128: return launch_cost_tc<128>(d_X, n, d_C, k, kpad, d_M, d_inertia, st);
+    default:
+      set_error("ure_cost_matrix: d=%d not in {8,16,32,64,128}", d);
+      return URE_EUNSUPPORTED;
+  }
+}
+
+extern "C" int ure_cost_matrix_simt(const float* d_X, int64_t n, int d, const float* d_C, int k, int kpad,
+                                    float* d_M, double* d_inertia, void* stream) {
+  using namespace ure;
+  if (int rc = check_cost_args(d_X, n, d, d_C, k, kpad, d_M, "ure_cost_matrix_simt")) return rc;
+  auto st = static_cast<cudaStream_t>(stream);
+  const long long total = n * kpad;
+  cost_simt_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_X, n, d, d_C, k, kpad, d_M);
+  URE_CUDA(cudaGetLastError());
+  if (d_inertia) return launch_rowmin(d_M, n, k, kpad, d_inertia, st);
+  return 0;
+}

@@ -1,0 +1,464 @@
+// Balanced-OT user grouping: Sinkhorn scaling, plan, assignment and centroid sums.
+//
+// Replaces the ot.emd call and the label/centroid lines of ot_cluster (reference
+// method/utils.py:641-648).  The reference's comment says "compute sinkhorn distance"
+// but the code calls the exact network simplex; north_star mandates
+// Sinkhorn on the GPU, whose eps -> 0 limit is that exact plan.
+//
+// With uniform row marginals a_i = 1/n the row potential is a function of the column
+// potentials g alone, so one Sinkhorn iteration is ONE streaming pass over the cost
+// matrix M [n, kpad] (row major, columns >= k hold +inf):
+//     t_ij = (g_j - M_ij)/eps ;  P_ij = a_i * softmax_j(t_ij) ;  colsum_j = sum_i P_ij
+//     g_j += eps * (log b_j - log colsum_j),  b_j = 1/k
+// P_ij <= a_i, so colsum needs no max-shift.  Row work is a warp-shuffle reduction over
+// kpad/4 lanes; column sums go registers -> shuffle -> shared -> one fp64 atomic per
+// column per CTA.
+#include "common.cuh"
+
+namespace ure {
+namespace {
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr int kMaxStages = 16;
+constexpr int kSkThreads = 512;
+
+template <int KPAD>
+struct RowMap {
+  static constexpr int LPR = (KPAD / 4 < 32) ? KPAD / 4 : 32;   // lanes per row
+  static constexpr int VEC = KPAD / 4 / LPR;                     // float4 per lane
+  static constexpr int RPW = 32 / LPR;                           // rows per warp pass
+};
+
+// softmax numerators of one row fragment; returns 1/sum over the row (group reduction)
+template <int KPAD>
+__device__ __forceinline__ float row_softmax(const float4 (&m)[RowMap<KPAD>::VEC], const float4 (&g)[RowMap<KPAD>::VEC],
+                                             float scale, float4 (&p)[RowMap<KPAD>::VEC], float& row_max_t) {
+  using RM = RowMap<KPAD>;
+  float mx = -INFINITY;
+#pragma unroll
+  for (int v = 0; v < RM::VEC; ++v) {
+    p[v].x = (g[v].x - m[v].x) * scale; p[v].y = (g[v].y - m[v].y) * scale;
+    p[v].z = (g[v].z - m[v].z) * scale; p[v].w = (g[v].w - m[v].w) * scale;
+    mx = fmaxf(mx, fmaxf(fmaxf(p[v].x, p[v].y), fmaxf(p[v].z, p[v].w)));
+  }
+#pragma unroll
+  for (int o = RM::LPR / 2; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o, RM::LPR));
+  float s = 0.f;
+#pragma unroll
+  for (int v = 0; v < RM::VEC; ++v) {
+    p[v].x = exp2f(p[v].x - mx); p[v].y = exp2f(p[v].y - mx);
+    p[v].z = exp2f(p[v].z - mx); p[v].w = exp2f(p[v].w - mx);
+    s += (p[v].x + p[v].y) + (p[v].z + p[v].w);
+  }
+#pragma unroll
+  for (int o = RM::LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o, RM::LPR);
+  row_max_t = mx;
+  return 1.0f / s;
+}
+
+template <int KPAD>
+__device__ __forceinline__ void load_g(const float* g, int k, int gl, float4 (&out)[RowMap<KPAD>::VEC]) {
+  using RM = RowMap<KPAD>;
+#pragma unroll
+  for (int v = 0; v < RM::VEC; ++v) {
+    const int c = (v * RM::LPR + gl) * 4;
+    out[v].x = c + 0 < k ? g[c + 0] : 0.f; out[v].y = c + 1 < k ? g[c + 1] : 0.f;
+    out[v].z = c + 2 < k ? g[c + 2] : 0.f; out[v].w = c + 3 < k ? g[c + 3] : 0.f;
+  }
+}
+
+// Accumulate the column sums of rows [r0,r1) handled by this CTA into csum_sh[KPAD] (shared, fp32).
+// MSRC: row-major matrix base (global or shared) whose row 0 is row `base_row`.
+template <int KPAD>
+__device__ __forceinline__ void colsum_rows(const float* Msrc, long long base_row, long long r0, long long r1,
+                                            const float* g_sh, int k, float scale, float a, float* csum_sh) {
+  using RM = RowMap<KPAD>;
+  const int lane = threadIdx.x & 31;
+  const int gl = lane % RM::LPR;
+  const int rw = lane / RM::LPR;
+  const int warp = threadIdx.x >> 5;
+  const int n_warps = blockDim.x >> 5;
+  float4 g[RM::VEC], acc[RM::VEC];
+  load_g<KPAD>(g_sh, k, gl, g);
+#pragma unroll
+  for (int v = 0; v < RM::VEC; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long row0 = r0 + (long long)warp * RM::RPW; row0 < r1; row0 += (long long)n_warps * RM::RPW) {
+    const long long row = row0 + rw;
+    const bool valid = row < r1;
+    float4 m[RM::VEC], p[RM::VEC];
+#pragma unroll
+    for (int v = 0; v < RM::VEC; ++v) {
+      m[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (valid) m[v] = *(reinterpret_cast<const float4*>(Msrc + (row - base_row) * KPAD) + v * RM::LPR + gl);
+    }
+    float mx;
+    const float inv = row_softmax<KPAD>(m, g, scale, p, mx);
+    const float w = valid ? a * inv : 0.f;
+#pragma unroll
+    for (int v = 0; v < RM::VEC; ++v) {
+      acc[v].x = fmaf(p[v].x, w, acc[v].x); acc[v].y = fmaf(p[v].y, w, acc[v].y);
+      acc[v].z = fmaf(p[v].z, w, acc[v].z); acc[v].w = fmaf(p[v].w, w, acc[v].w);
+    }
+  }
+  // lanes with equal gl hold the same columns: fold the RPW row slots of the warp
+#pragma unroll
+  for (int v = 0; v < RM::VEC; ++v) {
+#pragma unroll
+    for (int o = RM::LPR; o < 32; o <<= 1) {
+      acc[v].x += __shfl_xor_sync(0xffffffffu, acc[v].x, o); acc[v].y += __shfl_xor_sync(0xffffffffu, acc[v].y, o);
+      acc[v].z += __shfl_xor_sync(0xffffffffu, acc[v].z, o); acc[v].w += __shfl_xor_sync(0xffffffffu, acc[v].w, o);
+    }
+    if (rw == 0) {
+      const int c = (v * RM::LPR + gl) * 4;
+      atomicAdd(&csum_sh[c + 0], acc[v].x); atomicAdd(&csum_sh[c + 1], acc[v].y);
+      atomicAdd(&csum_sh[c + 2], acc[v].z); atomicAdd(&csum_sh[c + 3], acc[v].w);
+    }
+  }
+}
+
+// --------------------------------------------------------------------------- split-phase kernels
+template <int KPAD>
+__global__ void __launch_bounds__(kSkThreads)
+colsum_kernel(const float* __restrict__ M, long long n, int k, const float* __restrict__ g, float scale, float a,
+              double* __restrict__ colsum) {
+  __shared__ float g_sh[KPAD];
+  __shared__ float csum_sh[KPAD];
+  for (int j = threadIdx.x; j < KPAD; j += blockDim.x) { g_sh[j] = j < k ? g[j] : 0.f; csum_sh[j] = 0.f; }
+  __syncthreads();
+  const long long per = (n + gridDim.x - 1) / gridDim.x;
+  const long long r0 = per * blockIdx.x;
+  const long long r1 = r0 + per < n ? r0 + per : n;
+  if (r0 < r1) colsum_rows<KPAD>(M, 0, r0, r1, g_sh, k, scale, a, csum_sh);
+  __syncthreads();
+  for (int j = threadIdx.x; j < k; j += blockDim.x)
+    if (csum_sh[j] != 0.f) atomicAdd(colsum + j, (double)csum_sh[j]);
+}
+
+__global__ void update_g_kernel(float* g, double* colsum, int k, float eps) {
+  const int j = threadIdx.x;
+  if (j < k) {
+    const double c = colsum[j];
+    g[j] = (float)((double)g[j] + (double)eps * (-log((double)k) - log(c)));
+    colsum[j] = 0.0;
+  }
+}
+
+// --------------------------------------------------------------------------- persistent Sinkhorn
+struct SkStages {
+  float eps[kMaxStages];
+  int iters[kMaxStages];
+  int n;
+};
+struct SkWorkspace {
+  unsigned barrier;
+  unsigned pad[31];
+  double colsum[3][256];
+  double col_err;       // max_j |colsum_j - 1/k| seen at the last iteration
+  long long iters_done;
+};
+
+template <int KPAD, bool CACHED>
+__global__ void __launch_bounds__(kSkThreads, 1)
+sinkhorn_kernel(const float* __restrict__ M, long long n, int k, float* __restrict__ g_io, SkStages stages,
+                SkWorkspace* ws) {
+  extern __shared__ __align__(16) float m_sh[];     // CACHED: this CTA's rows of M
+  __shared__ float g_sh[KPAD];
+  __shared__ float csum_sh[KPAD];
+  const int tid = threadIdx.x;
+  const long long per = (n + gridDim.x - 1) / gridDim.x;
+  const long long r0 = per * blockIdx.x < n ? per * blockIdx.x : n;
+  const long long r1 = r0 + per < n ? r0 + per : n;
+  for (int j = tid; j < KPAD; j += blockDim.x) { g_sh[j] = j < k ? g_io[j] : 0.f; csum_sh[j] = 0.f; }
+  if (CACHED) {
+    const long long cnt4 = (r1 - r0) * (KPAD / 4);
+    const float4* src = reinterpret_cast<const float4*>(M + r0 * KPAD);
+    for (long long x = tid; x < cnt4; x += blockDim.x) reinterpret_cast<float4*>(m_sh)[x] = __ldg(src + x);
+  }
+  __syncthreads();
+  const float a = (float)(1.0 / (double)n);
+  const double logb = -log((double)k);
+  unsigned bar_target = 0;
+  long long it_global = 0;
+  for (int s = 0; s < stages.n; ++s) {
+    const float eps = stages.eps[s];
+    const float scale = kLog2e / eps;
+    for (int it = 0; it < stages.iters[s]; ++it, ++it_global) {
+      double* cs = ws->colsum[it_global % 3];
+      if (r0 < r1) colsum_rows<KPAD>(CACHED ? m_sh : M, CACHED ? r0 : 0, r0, r1, g_sh, k, scale, a, csum_sh);
+      __syncthreads();
+      for (int j = tid; j < k; j += blockDim.x) {
+        if (csum_sh[j] != 0.f) atomicAdd(cs + j, (double)csum_sh[j]);
+        csum_sh[j] = 0.f;
+      }
+      grid_barrier(&ws->barrier, bar_target);
+      // every CTA applies the identical update to its private copy of g
+      double err = 0.0;
+      for (int j = tid; j < k; j += blockDim.x) {
+        const double c = __ldcg(cs + j);
+        g_sh[j] = (float)((double)g_sh[j] + (double)eps * (logb - log(c)));
+        if (blockIdx.x == 0) {
+          ws->colsum[(it_global + 2) % 3][j] = 0.0;
+          err = fmax(err, fabs(c - 1.0 / (double)k));
+        }
+      }
+      if (blockIdx.x == 0) {                      // diagnostics only
+        __shared__ double err_sh;
+        if (tid == 0) err_sh = 0.0;
+        __syncthreads();
+        if (err > 0.0) atomicMax(reinterpret_cast<unsigned long long*>(&err_sh), (unsigned long long)__double_as_longlong(err));
+        __syncthreads();
+        if (tid == 0) { ws->col_err = err_sh; ws->iters_done = it_global + 1; }
+      }
+      __syncthreads();
+    }
+  }
+  if (blockIdx.x == 0)
+    for (int j = tid; j < k; j += blockDim.x) g_io[j] = g_sh[j];
+}
+
+// --------------------------------------------------------------------------- plan / assignment
+template <int KPAD>
+__global__ void __launch_bounds__(256)
+plan_kernel(const float* __restrict__ M, long long n, int k, const float* __restrict__ g, float scale, float a,
+            float* __restrict__ plan) {
+  using RM = RowMap<KPAD>;
+  __shared__ float g_sh[KPAD];
+  for (int j = threadIdx.x; j < KPAD; j += blockDim.x) g_sh[j] = j < k ? g[j] : 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, gl = lane % RM::LPR, rw = lane / RM::LPR;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  float4 gv[RM::VEC];
+  load_g<KPAD>(g_sh, k, gl, gv);
+  for (long long row0 = warp * RM::RPW; row0 < n; row0 += n_warps * RM::RPW) {
+    const long long row = row0 + rw;
+    const bool valid = row < n;
+    float4 m[RM::VEC], p[RM::VEC];
+#pragma unroll
+    for (int v = 0; v < RM::VEC; ++v) {
+      m[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (valid) m[v] = __ldg(reinterpret_cast<const float4*>(M + row * KPAD) + v * RM::LPR + gl);
+    }
+    float mx;
+    const float w = a * row_softmax<KPAD>(m, gv, scale, p, mx);
+    if (valid) {
+#pragma unroll
+      for (int v = 0; v < RM::VEC; ++v) {
+        const int c = (v * RM::LPR + gl) * 4;
+        float* dst = plan + row * k;
+        if (c + 0 < k) dst[c + 0] = p[v].x * w;
+        if (c + 1 < k) dst[c + 1] = p[v].y * w;
+        if (c + 2 < k) dst[c + 2] = p[v].z * w;
+        if (c + 3 < k) dst[c + 3] = p[v].w * w;
+      }
+    }
+  }
+}
+
+template <typename T>
+__global__ void assign_plan_kernel(const T* __restrict__ plan, long long n, int k, long long ld,
+                                   int32_t* __restrict__ label) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const T* row = plan + i * ld;
+  T best = row[0];
+  int arg = 0;
+  for (int j = 1; j < k; ++j) {
+    const T v = row[j];
+    if (v > best) { best = v; arg = j; }         // strict '>' keeps the first maximum (np.argmax)
+  }
+  label[i] = arg;
+}
+
+// label_i = argmax_j (g_j - M_ij), first max wins; centroid sums via shared-memory atomics.
+// One warp per row for the X read (coalesced d floats); acc_sh [k][d] fp32, flushed to fp64 global.
+__global__ void __launch_bounds__(256)
+assign_centroid_kernel(const float* __restrict__ M, long long n, int k, int kpad, const float* __restrict__ g,
+                       const float* __restrict__ X, int d, int32_t* __restrict__ label, double* __restrict__ sum,
+                       long long* __restrict__ cnt, int flush_rows) {
+  extern __shared__ __align__(16) float acc_sh[];   // [k*d] then cnt_sh[k] (as int)
+  int* cnt_sh = reinterpret_cast<int*>(acc_sh + (size_t)k * d);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n_warps = blockDim.x >> 5;
+  for (int x = tid; x < k * d; x += blockDim.x) acc_sh[x] = 0.f;
+  for (int x = tid; x < k; x += blockDim.x) cnt_sh[x] = 0;
+  __syncthreads();
+  const long long per = (n + gridDim.x - 1) / gridDim.x;
+  const long long r0 = per * blockIdx.x < n ? per * blockIdx.x : n;
+  const long long r1 = r0 + per < n ? r0 + per : n;
+  for (long long c0 = r0; c0 < r1; c0 += flush_rows) {
+    const long long c1 = c0 + flush_rows < r1 ? c0 + flush_rows : r1;
+    for (long long row = c0 + warp; row < c1; row += n_warps) {
+      float best = -INFINITY;
+      int arg = 0x7fffffff;
+      for (int j = lane; j < k; j += 32) {
+        const float v = __ldg(g + j) - __ldg(M + row * kpad + j);
+        if (v > best) { best = v; arg = j; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+        if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+      }
+      if (lane == 0) { label[row] = arg; atomicAdd(&cnt_sh[arg], 1); }
+      if (X) {
+        const float* xr = X + row * d;
+        float* ar = acc_sh + (size_t)arg * d;
+        for (int t = lane; t < d; t += 32) atomicAdd(&ar[t], __ldg(xr + t));
+      }
+    }
+    __syncthreads();
+    if (X)
+      for (int x = tid; x < k * d; x += blockDim.x) {
+        const float v = acc_sh[x];
+        if (v != 0.f) { atomicAdd(sum + x, (double)v); acc_sh[x] = 0.f; }
+      }
+    for (int x = tid; x < k; x += blockDim.x) {
+      const int v = cnt_sh[x];
+      if (v) { atomicAdd(reinterpret_cast<unsigned long long*>(cnt + x), (unsigned long long)v); cnt_sh[x] = 0; }
+    }
+    __syncthreads();
+  }
+}
+
+#define URE_KPAD_SWITCH(kpad, CALL)                    \
+  switch (kpad) {                                      \
+    case 16: { constexpr int KP = 16; CALL; } break;   \
+    case 32: { constexpr int KP = 32; CALL; } break;   \
+    case 64: { constexpr int KP = 64; CALL; } break;   \
+    case 128: { constexpr int KP = 128; CALL; } break; \
+    case 256: { constexpr int KP = 256; CALL; } break; \
+    default:                                           \
+      set_error("kpad=%d not in {16,32,64,128,256}", kpad); \
+      return URE_EUNSUPPORTED;                         \
+  }
+
+int check_mk(const void* M, long long n, int k, int kpad, const char* who) {
+  URE_REQUIRE(M != nullptr, URE_EINVAL, "%s: null cost matrix", who);
+  URE_REQUIRE(n > 0 && k >= 1 && k <= kpad, URE_EINVAL, "%s: bad shape n=%lld k=%d kpad=%d", who, n, k, kpad);
+  return 0;
+}
+
+template <int KPAD, bool CACHED>
+int launch_sinkhorn(const float* M, long long n, int k, float* g, const SkStages& st, SkWorkspace* ws, int grid,
+                    size_t smem, cudaStream_t stream) {
+  auto kern = sinkhorn_kernel<KPAD, CACHED>;
+  URE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 0;
+  URE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kSkThreads, smem));
+  URE_REQUIRE(occ >= 1, URE_ECOOP, "sinkhorn_kernel<%d> cannot be resident (smem %zu)", KPAD, smem);
+  void* args[] = {(void*)&M, (void*)&n, (void*)&k, (void*)&g, (void*)&st, (void*)&ws};
+  URE_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(kSkThreads), args, smem, stream));
+  return 0;
+}
+
+}  // namespace
+}  // namespace ure
+
+extern "C" int ure_sinkhorn_colsum(const float* d_M, int64_t n, int k, int kpad, const float* d_g, float eps,
+                                   double n_total, double* d_colsum, void* stream) {
+  using namespace ure;
+  if (int rc = check_mk(d_M, n, k, kpad, "ure_sinkhorn_colsum")) return rc;
+  URE_REQUIRE(d_g && d_colsum && eps > 0.f && n_total >= 1.0, URE_EINVAL, "ure_sinkhorn_colsum: bad argument");
+  const float scale = kLog2e / eps, a = (float)(1.0 / n_total);
+  long long blocks = (n + 2047) / 2048;
+  const long long cap = (long long)num_sms() * 4;
+  if (blocks > cap) blocks = cap;
+  auto st = static_cast<cudaStream_t>(stream);
+  URE_KPAD_SWITCH(kpad, (colsum_kernel<KP><<<(unsigned)blocks, kSkThreads, 0, st>>>(d_M, n, k, d_g, scale, a, d_colsum)));
+  URE_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int ure_sinkhorn_update_g(float* d_g, double* d_colsum, int k, float eps, void* stream) {
+  using namespace ure;
+  URE_REQUIRE(d_g && d_colsum && k >= 1 && k <= 256 && eps > 0.f, URE_EINVAL, "ure_sinkhorn_update_g: bad argument");
+  update_g_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_g, d_colsum, k, eps);
+  URE_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int64_t ure_sinkhorn_workspace_bytes(void) { return (int64_t)sizeof(ure::SkWorkspace); }
+
+extern "C" int ure_sinkhorn(const float* d_M, int64_t n, int k, int kpad, float* d_g, const float* h_eps,
+                            const int32_t* h_iters, int n_stages, void* d_workspace, void* stream) {
+  using namespace ure;
+  if (int rc = check_mk(d_M, n, k, kpad, "ure_sinkhorn")) return rc;
+  URE_REQUIRE(d_g && h_eps && h_iters && d_workspace, URE_EINVAL, "ure_sinkhorn: null argument");
+  URE_REQUIRE(n_stages >= 1 && n_stages <= kMaxStages, URE_EINVAL, "ure_sinkhorn: n_stages=%d outside [1,%d]",
+              n_stages, kMaxStages);
+  SkStages stg;
+  stg.n = n_stages;
+  for (int s = 0; s < n_stages; ++s) {
+    URE_REQUIRE(h_eps[s] > 0.f && h_iters[s] >= 0, URE_EINVAL, "ure_sinkhorn: stage %d eps/iters invalid", s);
+    stg.eps[s] = h_eps[s];
+    stg.iters[s] = h_iters[s];
+  }
+  auto st = static_cast<cudaStream_t>(stream);
+  auto* ws = static_cast<SkWorkspace*>(d_workspace);
+  URE_CUDA(cudaMemsetAsync(ws, 0, sizeof(SkWorkspace), st));
+  const int grid = num_sms();
+  const long long per = (n + grid - 1) / grid;
+  const size_t need = (size_t)per * kpad * sizeof(float);
+  const bool cached = need <= 200 * 1024;
+  const size_t smem = cached ? need : 0;
+  if (cached) {
+    URE_KPAD_SWITCH(kpad, return (launch_sinkhorn<KP, true>(d_M, n, k, d_g, stg, ws, grid, smem, st)));
+  } else {
+    URE_KPAD_SWITCH(kpad, return (launch_sinkhorn<KP, false>(d_M, n, k, d_g, stg, ws, grid, smem, st)));
+  }
+  return 0;
+}
+
+extern "C" int ure_sinkhorn_plan(const float* d_M, int64_t n, int k, int kpad, const float* d_g, float eps,
+                                 double n_total, float* d_plan, void* stream) {
+  using namespace ure;
+  if (int rc = check_mk(d_M, n, k, kpad, "ure_sinkhorn_plan")) return rc;
+  URE_REQUIRE(d_g && d_plan && eps > 0.f && n_total >= 1.0, URE_EINVAL, "ure_sinkhorn_plan: bad argument");
+  const float scale = kLog2e / eps, a = (float)(1.0 / n_total);
+  long long blocks = (n + 255) / 256;
+  const long long cap = (long long)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  auto st = static_cast<cudaStream_t>(stream);
+  URE_KPAD_SWITCH(kpad, (plan_kernel<KP><<<(unsigned)blocks, 256, 0, st>>>(d_M, n, k, d_g, scale, a, d_plan)));
+  URE_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int ure_assign_plan_f64(const double* d_plan, int64_t n, int k, int64_t ld, int32_t* d_label,
+                                   void* stream) {
+  using namespace ure;
+  URE_REQUIRE(d_plan && d_label && n > 0 && k >= 1 && ld >= k, URE_EINVAL, "ure_assign_plan_f64: bad argument");
+  assign_plan_kernel<double><<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      d_plan, n, k, ld, d_label);
+  URE_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int ure_assign_plan_f32(const float* d_plan, int64_t n, int k, int64_t ld, int32_t* d_label,
+                                   void* stream) {
+  using namespace ure;
+  URE_REQUIRE(d_plan && d_label && n > 0 && k >= 1 && ld >= k, URE_EINVAL, "ure_assign_plan_f32: bad argument");
+  assign_plan_kernel<float><<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      d_plan, n, k, ld, d_label);
+  URE_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int ure_assign_centroids(const float* d_M, int64_t n, int k, int kpad, const float* d_g,
+                                    const float* d_X, int d, int32_t* d_label, double* d_sum, int64_t* d_cnt,
+                                    void* stream) {
+  using namespace ure;
+  if (int rc = check_mk(d_M, n, k, kpad, "ure_assign_centroids")) return rc;
+  URE_REQUIRE(d_g && d_label && d_cnt && (!d_X || (d_sum && d > 0)), URE_EINVAL, "ure_assign_centroids: bad argument");
+  const size_t smem = ((size_t)k * (d_X ? d : 0) + k) * sizeof(float);
+  URE_REQUIRE(smem <= 200 * 1024, URE_EUNSUPPORTED, "ure_assign_centroids: k*d=%d too large for shared memory", k * d);
+  URE_CUDA(cudaFuncSetAttribute(assign_centroid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  long long blocks = (n + 1023) / 1024;
+  const long long cap = (long long)num_sms() * 2;
+  if (blocks > cap) blocks = cap;
+  assign_centroid_kernel<<<(unsigned)blocks, 256, smem, static_cast<cudaStream_t>(stream)>>>(
+      d_M, n, k, kpad, d_g, d_X, d_X ? d : 0, d_label, d_sum, reinterpret_cast<long long*>(d_cnt), 4096);
+  URE_CUDA(cudaGetLastError());
+  return 0;
+}

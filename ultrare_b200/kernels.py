@@ -1,0 +1,283 @@
+"""Tensor-level wrappers over the C ABI (include/ultrare_b200.h).
+
+PyTorch is used for device memory and streams only; every arithmetic step on the
+hot path is a hand-written sm_100a kernel inside libultrare_b200.so.  All calls are
+asynchronous on the current CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import MFHParams, MFShard, check
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("ultrare_b200: tensors must live on a CUDA device (no CPU path exists)")
+
+
+# ------------------------------------------------------------------------------ interactions
+def pack_interactions(users, items, ratings, device) -> torch.Tensor:
+    """(uid, iid, rating) columns -> int32 [n,4] ure_inter_t records on `device`.
+
+    rating is cast the way RatingData does (reference read.py:113,124): float32(float64).
+    """
+    n = len(users)
+    rec = np.zeros((n, 4), dtype=np.int32)
+    rec[:, 0] = np.asarray(users).astype(np.int64)
+    rec[:, 1] = np.asarray(items).astype(np.int64)
+    rec[:, 2] = np.asarray(ratings, dtype=np.float64).astype(np.float32).view(np.int32)
+    t = torch.from_numpy(rec)
+    if torch.device(device).type == "cuda":
+        t = t.pin_memory().to(device, non_blocking=True)
+    return t
+
+
+def pointer_table(tensors: Sequence[torch.Tensor], device) -> torch.Tensor:
+    return torch.tensor([t.data_ptr() for t in tensors], dtype=torch.int64, device=device)
+
+
+# ------------------------------------------------------------------------------ MF training
+class ShardState:
+    """Device state of one shard model: what Scratch.train builds (scratch.py:59,65-69)."""
+
+    def __init__(self, inter: torch.Tensor, P: torch.Tensor, Q: torch.Tensor, epochs: int,
+                 shard_id: int = 0, perm_seed: int = 42, perm: Optional[torch.Tensor] = None):
+        _need_cuda(inter, P, Q, perm)
+        assert inter.dtype == torch.int32 and inter.dim() == 2 and inter.shape[1] == 4
+        assert P.dtype == torch.float32 and Q.dtype == torch.float32 and P.shape[1] == Q.shape[1]
+        self.inter, self.P, self.Q = inter.contiguous(), P, Q
+        assert P.is_contiguous() and Q.is_contiguous()
+        self.bufP, self.bufQ = torch.zeros_like(P), torch.zeros_like(Q)
+        self.gP, self.gQ = torch.zeros_like(P), torch.zeros_like(Q)
+        self.sse = torch.zeros(max(1, epochs), dtype=torch.float64, device=P.device)
+        self.perm = None
+        if perm is not None:
+            assert perm.dtype == torch.int32 and perm.shape == (epochs, inter.shape[0])
+            self.perm = perm.contiguous()
+        self.n = int(inter.shape[0])
+        self.shard_id, self.perm_seed, self.epochs = int(shard_id), int(perm_seed) & 0xFFFFFFFF, int(epochs)
+
+    def descriptor(self) -> MFShard:
+        d = MFShard()
+        d.inter, d.perm = self.inter.data_ptr(), (self.perm.data_ptr() if self.perm is not None else None)
+        d.P, d.Q = self.P.data_ptr(), self.Q.data_ptr()
+        d.bufP, d.bufQ = self.bufP.data_ptr(), self.bufQ.data_ptr()
+        d.gP, d.gQ, d.sse = self.gP.data_ptr(), self.gQ.data_ptr(), self.sse.data_ptr()
+        d.lastP = d.lastQ = None
+        d.n, d.n_user, d.n_item = self.n, self.P.shape[0], self.Q.shape[0]
+        d.shard_id, d.perm_seed, d.reserved = self.shard_id, self.perm_seed, 0
+        return d
+
+    def steps_per_epoch(self, batch: int) -> int:
+        return -(-self.n // batch)
+
+
+class ShardBatch:
+    """All shard models a GPU owns, trained together by one persistent launch."""
+
+    def __init__(self, shards: List[ShardState], d: int, batch: int, lr: float = 1e-3, lr_decay: float = 0.95,
+                 lr_step: int = 50, weight_decay: float = 0.1, momentum: float = 0.9):
+        if not 1 <= len(shards) <= _lib.URE_MAX_SHARDS:
+            raise ValueError(f"1..{_lib.URE_MAX_SHARDS} shards per launch")
+        self.shards = shards
+        self.device = shards[0].P.device
+        self.epochs = shards[0].epochs
+        assert all(s.epochs == self.epochs for s in shards)
+        self.hp = MFHParams(d=d, batch=batch, lr0=lr, lr_decay=lr_decay, lr_step=lr_step,
+                            weight_decay=weight_decay, momentum=momentum, lazy=0)
+        arr = (MFShard * len(shards))(*[s.descriptor() for s in shards])
+        host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+        self.table = host.to(self.device)
+        self.ws = torch.zeros(int(_lib.lib().ure_mf_train_workspace_bytes()), dtype=torch.uint8, device=self.device)
+        self.total_steps = max(s.steps_per_epoch(batch) for s in shards) * self.epochs
+        self.step = 0
+
+    def train(self, step_end: Optional[int] = None) -> None:
+        """Advance every shard to global step `step_end` (default: the end of training)."""
+        step_end = self.total_steps if step_end is None else min(int(step_end), self.total_steps)
+        if step_end <= self.step:
+            return
+        with torch.cuda.device(self.device):
+            check(_lib.lib().ure_mf_train(_ptr(self.table), len(self.shards), C.byref(self.hp), self.epochs,
+                                          self.step, step_end, _ptr(self.ws), _stream()), "ure_mf_train")
+        self.step = step_end
+
+    def interactions_trained(self) -> int:
+        return sum(s.n for s in self.shards) * self.epochs
+
+    def train_losses(self) -> List[np.ndarray]:
+        """Per shard: sqrt(sse_epoch / n) for every epoch (utils.py:108).  Synchronises."""
+        return [np.sqrt(s.sse.cpu().numpy() / max(1, s.n)) for s in self.shards]
+
+
+# ------------------------------------------------------------------------------ evaluation
+def ensemble_score(P_list, Q_list, inter, denom: Optional[float] = None, want_score: bool = True):
+    """(score fp32 [n] or None, sse fp64 [1]) for the K models (P_k, Q_k)."""
+    _need_cuda(inter, *P_list, *Q_list)
+    dev = inter.device
+    K, d, n = len(P_list), P_list[0].shape[1], inter.shape[0]
+    score = torch.empty(n, dtype=torch.float32, device=dev) if want_score else None
+    sse = torch.zeros(1, dtype=torch.float64, device=dev)
+    pt, qt = pointer_table(P_list, dev), pointer_table(Q_list, dev)
+    with torch.cuda.device(dev):
+        check(_lib.lib().ure_ensemble_score(_ptr(pt), _ptr(qt), K, d, _ptr(inter), n,
+                                            float(K if denom is None else denom), _ptr(score), _ptr(sse),
+                                            _stream()), "ure_ensemble_score")
+    return score, sse
+
+
+def score_finalize(sum_t, inter, denom: float):
+    _need_cuda(sum_t, inter)
+    sse = torch.zeros(1, dtype=torch.float64, device=inter.device)
+    score = torch.empty_like(sum_t)
+    with torch.cuda.device(inter.device):
+        check(_lib.lib().ure_score_finalize(_ptr(sum_t), _ptr(inter), inter.shape[0], float(denom), _ptr(score),
+                                            _ptr(sse), _stream()), "ure_score_finalize")
+    return score, sse
+
+
+def user_segments(users: np.ndarray):
+    """(order or None, seg int64 [n_seg+1]) grouping test rows by user id in order of first
+    appearance with rows kept in file order (host dict of utils.py:151-161)."""
+    users = np.asarray(users)
+    n = len(users)
+    if n == 0:
+        return None, np.zeros(1, dtype=np.int64)
+    change = np.flatnonzero(users[1:] != users[:-1]) + 1
+    starts = np.concatenate([[0], change])
+    if len(np.unique(users[starts])) == len(starts):        # every user is one contiguous run
+        return None, np.concatenate([starts, [n]]).astype(np.int64)
+    order = np.argsort(users, kind="stable")
+    us = users[order]
+    starts = np.concatenate([[0], np.flatnonzero(us[1:] != us[:-1]) + 1])
+    return order.astype(np.int32), np.concatenate([starts, [n]]).astype(np.int64)
+
+
+def rank_metrics(inter, score, seg, order=None) -> torch.Tensor:
+    """fp64 [3] = (sum ndcg, sum hr, #users)."""
+    _need_cuda(inter, score, seg, order)
+    out = torch.zeros(3, dtype=torch.float64, device=inter.device)
+    with torch.cuda.device(inter.device):
+        check(_lib.lib().ure_rank_metrics(_ptr(inter), _ptr(score), _ptr(order), _ptr(seg), seg.shape[0] - 1,
+                                          _ptr(out), _stream()), "ure_rank_metrics")
+    return out
+
+
+# ------------------------------------------------------------------------------ SISA bookkeeping
+def route_deletions(owner: torch.Tensor, del_ids: torch.Tensor, n_shards: int) -> torch.Tensor:
+    _need_cuda(owner, del_ids)
+    flags = torch.zeros(n_shards, dtype=torch.int32, device=owner.device)
+    with torch.cuda.device(owner.device):
+        check(_lib.lib().ure_route_deletions(_ptr(owner), owner.shape[0], _ptr(del_ids), del_ids.shape[0],
+                                             _ptr(flags), n_shards, _stream()), "ure_route_deletions")
+    return flags
+
+
+def merge_user_rows(P_list, owner, merged, row_of=None, retrain=None, zero_unowned=False) -> None:
+    _need_cuda(owner, merged, row_of, retrain, *P_list)
+    pt = pointer_table(P_list, merged.device)
+    with torch.cuda.device(merged.device):
+        check(_lib.lib().ure_merge_user_rows(_ptr(pt), _ptr(owner), _ptr(row_of), _ptr(retrain), _ptr(merged),
+                                             merged.shape[0], merged.shape[1], int(zero_unowned), _stream()),
+              "ure_merge_user_rows")
+
+
+# ------------------------------------------------------------------------------ OT grouping
+def kpad_for(k: int) -> int:
+    for kp in (16, 32, 64, 128, 256):
+        if k <= kp:
+            return kp
+    raise ValueError("k > 256 centroids is not supported")
+
+
+def cost_matrix(X, Cc, want_inertia=False, simt=False):
+    """M [n,kpad] fp32 (columns >= k are +inf) and optionally the fp64 inertia scalar tensor."""
+    _need_cuda(X, Cc)
+    n, d = X.shape
+    k = Cc.shape[0]
+    kp = kpad_for(k)
+    M = torch.empty((n, kp), dtype=torch.float32, device=X.device)
+    inertia = torch.zeros(1, dtype=torch.float64, device=X.device) if want_inertia else None
+    fn = _lib.lib().ure_cost_matrix_simt if simt else _lib.lib().ure_cost_matrix
+    with torch.cuda.device(X.device):
+        check(fn(_ptr(X.contiguous()), n, d, _ptr(Cc.contiguous()), k, kp, _ptr(M), _ptr(inertia), _stream()),
+              "ure_cost_matrix")
+    return (M, inertia) if want_inertia else M
+
+
+def sinkhorn(M, k, eps_schedule, g=None) -> torch.Tensor:
+    """Single-GPU persistent Sinkhorn; eps_schedule = [(eps, iters), ...]. Returns g fp32 [k]."""
+    _need_cuda(M, g)
+    n, kp = M.shape
+    g = torch.zeros(k, dtype=torch.float32, device=M.device) if g is None else g.clone()
+    S = len(eps_schedule)
+    eps = (C.c_float * S)(*[float(e) for e, _ in eps_schedule])
+    its = (C.c_int32 * S)(*[int(i) for _, i in eps_schedule])
+    ws = torch.zeros(int(_lib.lib().ure_sinkhorn_workspace_bytes()), dtype=torch.uint8, device=M.device)
+    with torch.cuda.device(M.device):
+        check(_lib.lib().ure_sinkhorn(_ptr(M), n, k, kp, _ptr(g), eps, its, S, _ptr(ws), _stream()), "ure_sinkhorn")
+    return g
+
+
+def sinkhorn_colsum(M, k, g, eps, n_total, colsum) -> None:
+    with torch.cuda.device(M.device):
+        check(_lib.lib().ure_sinkhorn_colsum(_ptr(M), M.shape[0], k, M.shape[1], _ptr(g), float(eps),
+                                             float(n_total), _ptr(colsum), _stream()), "ure_sinkhorn_colsum")
+
+
+def sinkhorn_update_g(g, colsum, k, eps) -> None:
+    with torch.cuda.device(g.device):
+        check(_lib.lib().ure_sinkhorn_update_g(_ptr(g), _ptr(colsum), k, float(eps), _stream()),
+              "ure_sinkhorn_update_g")
+
+
+def sinkhorn_plan(M, k, g, eps, n_total=None) -> torch.Tensor:
+    n, kp = M.shape
+    plan = torch.empty((n, k), dtype=torch.float32, device=M.device)
+    with torch.cuda.device(M.device):
+        check(_lib.lib().ure_sinkhorn_plan(_ptr(M), n, k, kp, _ptr(g), float(eps),
+                                           float(n if n_total is None else n_total), _ptr(plan), _stream()),
+              "ure_sinkhorn_plan")
+    return plan
+
+
+def assign_plan(plan: torch.Tensor) -> torch.Tensor:
+    """label = argmax_j plan[i,j], first maximum wins (utils.py:647)."""
+    _need_cuda(plan)
+    plan = plan.contiguous()
+    n, k = plan.shape
+    label = torch.empty(n, dtype=torch.int32, device=plan.device)
+    fn = {torch.float64: _lib.lib().ure_assign_plan_f64, torch.float32: _lib.lib().ure_assign_plan_f32}[plan.dtype]
+    with torch.cuda.device(plan.device):
+        check(fn(_ptr(plan), n, k, k, _ptr(label), _stream()), "ure_assign_plan")
+    return label
+
+
+def assign_centroids(M, k, g, X=None):
+    """(label int32 [n], sums fp64 [k,d] or None, counts int64 [k])."""
+    n, kp = M.shape
+    dev = M.device
+    label = torch.empty(n, dtype=torch.int32, device=dev)
+    cnt = torch.zeros(k, dtype=torch.int64, device=dev)
+    d = 0 if X is None else X.shape[1]
+    sums = None if X is None else torch.zeros((k, d), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.lib().ure_assign_centroids(_ptr(M), n, k, kp, _ptr(g), _ptr(X), d, _ptr(label), _ptr(sums),
+                                              _ptr(cnt), _stream()), "ure_assign_centroids")
+    return label, sums, cnt

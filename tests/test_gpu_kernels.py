@@ -1,0 +1,305 @@
+"""GPU parity: every kernel of libultrare_b200.so, called through the C ABI, against the
+CPU oracle and against the fixtures the reference itself produced (tests/golden/)."""
+import numpy as np
+import pytest
+
+from conftest import init_weights, load_gold
+from oracle import evalm, mf as omf, ot as oot, sisa as osisa
+
+pytestmark = pytest.mark.gpu
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _shard(K, toy, dev, epochs, batch, explicit_perm, seeds, shard_ids=None, data=None):
+    torch = _torch()
+    from ultrare_b200 import kernels as kn
+    shards, host = [], []
+    for s in range(K):
+        u, i, r = data[s] if data is not None else toy["train"]
+        r32 = (np.asarray(r, dtype=np.float64) / 5.0).astype(np.float32) if data is None else r
+        P0, Q0 = init_weights(seeds[s], toy["n_user"], toy["n_item"], toy["k"])
+        sid = s if shard_ids is None else shard_ids[s]
+        perms = [omf.feistel_perm(len(u), omf.perm_key(42, sid, ep)) for ep in range(epochs)]
+        inter = kn.pack_interactions(u, i, r32.astype(np.float64), dev)
+        perm_t = torch.tensor(np.stack(perms).astype(np.int32), device=dev) if explicit_perm else None
+        shards.append(kn.ShardState(inter, torch.tensor(P0, device=dev), torch.tensor(Q0, device=dev), epochs,
+                                    shard_id=sid, perm_seed=42, perm=perm_t))
+        host.append((u, i, r32, P0, Q0, perms))
+    return shards, host
+
+
+@pytest.mark.parametrize("explicit_perm", [True, False])
+def test_mf_train_vs_reference_golden(toy, cuda_dev, explicit_perm):
+    """ure_mf_train == reference baseTrain (+SGD/StepLR): losses 1e-3 rel, weights 1e-4 abs (Appendix E)."""
+    torch = _torch()
+    from ultrare_b200 import kernels as kn
+    z = load_gold("toy_train.npz")
+    epochs, batch = int(z["epochs"]), int(z["batch"])
+    shards, _ = _shard(1, toy, cuda_dev, epochs, batch, explicit_perm, [int(z["weight_seed"])])
+    sb = kn.ShardBatch(shards, toy["k"], batch)
+    sb.train()
+    torch.cuda.synchronize()
+    losses = sb.train_losses()[0]
+    np.testing.assert_allclose(losses, z["losses"], rtol=1e-3)
+    assert np.abs(losses - z["losses"]).max() / z["losses"].max() < 1e-5
+    assert np.abs(shards[0].P.cpu().numpy() - z["P_final"]).max() < 1e-4
+    assert np.abs(shards[0].Q.cpu().numpy() - z["Q_final"]).max() < 1e-4
+    assert float(shards[0].gP.abs().max()) == 0.0 and float(shards[0].gQ.abs().max()) == 0.0
+
+
+def test_mf_train_epoch_by_epoch_equals_single_launch(toy, cuda_dev):
+    torch = _torch()
+    from ultrare_b200 import kernels as kn
+    a, _ = _shard(1, toy, cuda_dev, 2, 3000, False, [7])
+    b, _ = _shard(1, toy, cuda_dev, 2, 3000, False, [7])
+    sa, sb = kn.ShardBatch(a, 16, 3000), kn.ShardBatch(b, 16, 3000)
+    sa.train()
+    spe = b[0].steps_per_epoch(3000)
+    for t in range(1, 2 * spe + 1):
+        sb.train(t)
+    torch.cuda.synchronize()
+    # identical schedule; only the order of fp32 atomics differs
+    assert np.abs(a[0].P.cpu().numpy() - b[0].P.cpu().numpy()).max() < 2e-5
+    np.testing.assert_allclose(sa.train_losses()[0], sb.train_losses()[0], rtol=1e-6)
+
+
+def test_mf_train_k_shards_batched_vs_oracle(toy, cuda_dev):
+    """K ragged shards in ONE launch (different sizes => different steps/epoch) == K oracle trainings."""
+    torch = _torch()
+    from ultrare_b200 import kernels as kn
+    u, i, r = toy["train"]
+    r32 = (r / 5.0).astype(np.float32)
+    K, epochs, batch = 3, 2, 3000
+    groups = osisa.uniform_groups(toy["n_user"], K)
+    data = []
+    for s, g in enumerate(groups):
+        loc = np.isin(u, g if s else g[: len(g) // 2])        # shard 0 much smaller: ragged schedules
+        data.append((u[loc], i[loc], r32[loc]))
+    shards, host = _shard(K, toy, cuda_dev, epochs, batch, False, [11, 12, 13], data=data)
+    assert len({sh.steps_per_epoch(batch) for sh in shards}) > 1
+    sb = kn.ShardBatch(shards, toy["k"], batch)
+    sb.train()
+    torch.cuda.synchronize()
+    losses = sb.train_losses()
+    for s in range(K):
+        uu, ii, rr, P0, Q0, perms = host[s]
+        P, Q, _, _, ls = omf.mf_train(P0, Q0, uu, ii, rr, perms, batch, epochs)
+        np.testing.assert_allclose(losses[s], ls, rtol=1e-5)
+        assert np.abs(shards[s].P.cpu().numpy() - P).max() < 1e-4
+        assert np.abs(shards[s].Q.cpu().numpy() - Q).max() < 1e-4
+
+
+@pytest.mark.parametrize("d", [8, 32, 64, 128])
+def test_mf_train_other_dims_vs_oracle(cuda_dev, d):
+    torch = _torch()
+    from ultrare_b200 import kernels as kn
+    rng = np.random.default_rng(d)
+    U, I, n, batch, epochs = 300, 200, 5000, 1024, 2
+    u, i = rng.integers(0, U, n), rng.integers(0, I, n)
+    r = rng.integers(1, 6, n).astype(np.float32) / 5
+    P0 = rng.standard_normal((U, d), dtype=np.float32) * 0.3
+    Q0 = rng.standard_normal((I, d), dtype=np.float32) * 0.3
+    perms = [omf.feistel_perm(n, omf.perm_key(9, 0, ep)) for ep in range(epochs)]
+    sh = kn.ShardState(kn.pack_interactions(u, i, r, cuda_dev), torch.tensor(P0, device=cuda_dev),
+                       torch.tensor(Q0, device=cuda_dev), epochs, 0, 9)
+    sb = kn.ShardBatch([sh], d, batch)
+    sb.train()
+    P, Q, _, _, ls = omf.mf_train(P0, Q0, u, i, r, perms, batch, epochs)
+    np.testing.assert_allclose(sb.train_losses()[0], ls, rtol=1e-5)
+    assert np.abs(sh.P.cpu().numpy() - P).max() < 1e-4 and np.abs(sh.Q.cpu().numpy() - Q).max() < 1e-4
+
+
+def test_ensemble_score_and_metrics_vs_reference_golden(toy, cuda_dev):
+    """Scores 1e-5 abs, RMSE/HR 1e-3 rel vs the reference's baseTest; NDCG vs the stable-rule oracle."""
+    torch = _torch()
+    from ultrare_b200 import kernels as kn
+    z = load_gold("toy_train.npz")
+    u, i, r = toy["test"]
+    r32 = (r / 5.0).astype(np.float32)
+    inter = kn.pack_interactions(u, i, r / 5.0, cuda_dev)
+    P, Q = torch.tensor(z["P_final"], device=cuda_dev), torch.tensor(z["Q_final"], device=cuda_dev)
+    score, sse = kn.ensemble_score([P], [Q], inter)
+    assert np.abs(score.cpu().numpy() - z["test_score"]).max() < 1e-5
+    rmse = float(np.sqrt(sse.item() / len(u)))
+    assert abs(rmse - float(z["test_rmse"])) / float(z["test_rmse"]) < 1e-5
+    order, seg = kn.user_segments(u)
+    assert order is None
+    out = kn.rank_metrics(inter, score, torch.tensor(seg, device=cuda_dev)).cpu().numpy()
+    n_users = len(np.unique(u))
+    assert out[2] == n_users
+    nd_o, hr_o = evalm.rank_metrics(u, r32, score.cpu().numpy(), kind="stable")
+    assert abs(out[1] / n_users - float(z["test_hr"])) / float(z["test_hr"]) < 1e-3
+    assert abs(out[1] / n_users - hr_o) < 1e-12
+    assert abs(out[0] / n_users - nd_o) < 1e-9
+    # GPU scores through the reference's own host ranking (default argsort on this box): H7
+    nd_ref_rule, _ = evalm.rank_metrics(u, r32, score.cpu().numpy(), kind=None)
+    assert abs(nd_ref_rule - float(z["test_ndcg_ref"])) / float(z["test_ndcg_ref"]) < 1e-3
+
+
+def test_ensemble_k_models_and_unsorted_users(cuda_dev):
+    torch = _torch()
+    from ultrare_b200 import kernels as kn
+    rng = np.random.default_rng(0)
+    U, I, d, n, K = 50, 40, 16, 3000, 5
+    u, i = rng.integers(0, U, n), rng.integers(0, I, n)      # users NOT contiguous -> order indirection
+    r = rng.integers(1, 11, n).astype(np.float32) / 10
+    Ps = [rng.standard_normal((U, d), dtype=np.float32) for _ in range(K)]
+    Qs = [rng.standard_normal((I, d), dtype=np.float32) for _ in range(K)]
+    inter = kn.pack_interactions(u, i, r, cuda_dev)
+    tP = [torch.tensor(p, device=cuda_dev) for p in Ps]
+    tQ = [torch.tensor(q, device=cuda_dev) for q in Qs]
+    score, sse = kn.ensemble_score(tP, tQ, inter)
+    ref = evalm.ensemble_score(Ps, Qs, u, i)
+    assert np.abs(score.cpu().numpy() - ref).max() < 2e-5
+    assert abs(sse.item() - evalm.sse(ref, r)) / evalm.sse(ref, r) < 1e-5
+    # partial sums + finalize == one call (the multi-GPU evaluation path)
+    s1, _ = kn.ensemble_score(tP[:2], tQ[:2], inter, denom=1.0)
+    s2, _ = kn.ensemble_score(tP[2:], tQ[2:], inter, denom=1.0)
+    fin, sse2 = kn.score_finalize(s1 + s2, inter, float(K))
+    assert np.abs(fin.cpu().numpy() - ref).max() < 2e-5 and abs(sse2.item() - sse.item()) / sse.item() < 1e-5
+    order, seg = kn.user_segments(u)
+    assert order is not None
+    out = kn.rank_metrics(inter, score, torch.tensor(seg, device=cuda_dev), torch.tensor(order, device=cuda_dev))
+    nd, hr = evalm.rank_metrics(u, r, score.cpu().numpy(), kind="stable")
+    out = out.cpu().numpy()
+    assert out[2] == len(np.unique(u))
+    assert abs(out[0] / out[2] - nd) < 1e-9 and abs(out[1] / out[2] - hr) < 1e-12
+
+
+def test_rank_metrics_edge_cases(cuda_dev):
+    """Users with 1 item, < 10 items (zero padding), all-tied ratings and tied scores."""
+    torch = _torch()
+    from ultrare_b200 import kernels as kn
+    u = np.array([0] + [1] * 3 + [2] * 10 + [3] * 25 + [4] * 12)
+    n = len(u)
+    rng = np.random.default_rng(1)
+    r = (rng.integers(1, 6, n) / 5).astype(np.float32)
+    r[u == 4] = 0.8
+    s = rng.standard_normal(n).astype(np.float32)
+    s[u == 3] = np.round(s[u == 3])                        # many tied scores
+    inter = kn.pack_interactions(u, np.zeros(n, dtype=np.int64), r, cuda_dev)
+    _, seg = kn.user_segments(u)
+    out = kn.rank_metrics(inter, torch.tensor(s, device=cuda_dev), torch.tensor(seg, device=cuda_dev)).cpu().numpy()
+    nd, hr = evalm.rank_metrics(u, r, s, kind="stable")
+    assert out[2] == 5 and abs(out[0] / 5 - nd) < 1e-12 and abs(out[1] / 5 - hr) < 1e-12
+    empty = kn.rank_metrics(inter[:0], torch.zeros(0, device=cuda_dev), torch.zeros(1, dtype=torch.int64, device=cuda_dev))
+    assert empty.cpu().numpy().tolist() == [0.0, 0.0, 0.0]
+
+
+def test_routing_and_merge_vs_reference_golden(cuda_dev):
+    """retrain_gid and merged tables bit-exact (Appendix E)."""
+    torch = _torch()
+    from ultrare_b200 import kernels as kn
+    z = load_gold("toy_sisa.npz")
+    K, U = int(z["K"]), 1508
+    groups = [z[f"group{s}"] for s in range(K)]
+    owner = np.full(U, -1, dtype=np.int32)
+    for s, g in enumerate(groups):
+        owner[g] = s
+    t_owner = torch.tensor(owner, device=cuda_dev)
+    flags = kn.route_deletions(t_owner, torch.tensor(z["del_user"].astype(np.int32), device=cuda_dev), K)
+    assert np.flatnonzero(flags.cpu().numpy()).tolist() == z["retrain_gid"].tolist()
+    assert set(np.flatnonzero(flags.cpu().numpy())) == osisa.route_deletions(groups, z["del_user"])
+    # merge: learn (zero + owner rows) then unlearn (clone + retrained owners)
+    rng = np.random.default_rng(2)
+    Ps = [rng.standard_normal((U, 16), dtype=np.float32) for _ in range(K)]
+    tP = [torch.tensor(p, device=cuda_dev) for p in Ps]
+    merged = torch.full((U, 16), 7.0, device=cuda_dev)
+    kn.merge_user_rows(tP, t_owner, merged, zero_unowned=True)
+    assert np.array_equal(merged.cpu().numpy(), osisa.merge_learn(Ps, groups))
+    P2 = [rng.standard_normal((U, 16), dtype=np.float32) for _ in range(K)]
+    before = merged.cpu().numpy().copy()
+    kn.merge_user_rows([torch.tensor(p, device=cuda_dev) for p in P2], t_owner, merged, retrain=flags)
+    assert np.array_equal(merged.cpu().numpy(), osisa.merge_unlearn(before, P2, groups, z["retrain_gid"].tolist()))
+
+
+@pytest.mark.parametrize("n,d,k", [(6040, 16, 5), (1000, 8, 3), (5000, 64, 32), (3001, 32, 8), (2048, 128, 16),
+                                   (4096, 64, 128), (700, 64, 200)])
+def test_cost_matrix_tcgen05_vs_float64(cuda_dev, n, d, k):
+    """tcgen05 3xTF32 cost == float64 sum (x-c)^2 within 1e-5 relative (Appendix E); also vs the SIMT kernel."""
+    torch = _torch()
+    from ultrare_b200 import kernels as kn
+    rng = np.random.default_rng(n + d + k)
+    X = rng.standard_normal((n, d), dtype=np.float32)
+    Cc = X[rng.choice(n, k, replace=False)] + 0.1 * rng.standard_normal((k, d), dtype=np.float32)
+    tX, tC = torch.tensor(X, device=cuda_dev), torch.tensor(Cc, device=cuda_dev)
+    M, inertia = kn.cost_matrix(tX, tC, want_inertia=True)
+    Ms, inertia_s = kn.cost_matrix(tX, tC, want_inertia=True, simt=True)
+    ref = oot.cost_matrix(X, Cc)
+    M, Ms = M.cpu().numpy(), Ms.cpu().numpy()
+    assert np.isinf(M[:, k:]).all() and np.isinf(Ms[:, k:]).all()
+    scale = ref.max()
+    assert np.abs(Ms[:, :k] - ref).max() / scale < 1e-5
+    assert np.abs(M[:, :k] - ref).max() / scale < 1e-5
+    ref_in = ref.min(axis=1).sum()
+    assert abs(inertia.item() - ref_in) / ref_in < 1e-5 and abs(inertia_s.item() - ref_in) / ref_in < 1e-5
+
+
+@pytest.mark.parametrize("n,k", [(6040, 5), (999, 3), (20000, 32), (4000, 128), (3000, 200)])
+def test_sinkhorn_plan_vs_float64_oracle(cuda_dev, n, k):
+    """Persistent Sinkhorn: n*P within 1e-4 of the float64 oracle at the same eps schedule (Appendix E);
+    the split-phase kernels (multi-GPU path) give the same potentials; labels == argmax of the oracle plan."""
+    torch = _torch()
+    from ultrare_b200 import kernels as kn
+    rng = np.random.default_rng(n + k)
+    d = 16
+    X = rng.standard_normal((n, d), dtype=np.float32)
+    Cc = X[rng.choice(n, k, replace=False)]
+    M = kn.cost_matrix(torch.tensor(X, device=cuda_dev), torch.tensor(Cc, device=cuda_dev))
+    Mh = M.cpu().numpy()[:, :k].astype(np.float64)
+    mean = float(Mh.mean())
+    sched = [(mean * 0.5, 20), (mean * 0.1, 40), (mean * 0.03, 60)]
+    g = kn.sinkhorn(M, k, sched)
+    P_o, _, g_o, _ = oot.sinkhorn_log(Mh, sched)
+    assert np.abs(g.cpu().numpy() - g_o).max() < 1e-3 * mean
+    plan = kn.sinkhorn_plan(M, k, g, sched[-1][0]).cpu().numpy()
+    assert np.abs(n * plan - n * P_o).max() < 1e-4
+    np.testing.assert_allclose(plan.sum(1), 1.0 / n, rtol=1e-5)
+    # split phase (what the multi-GPU driver runs, with an all-reduce between the two kernels)
+    g2 = torch.zeros(k, dtype=torch.float32, device=cuda_dev)
+    colsum = torch.zeros(M.shape[1], dtype=torch.float64, device=cuda_dev)
+    for eps, iters in sched:
+        for _ in range(iters):
+            kn.sinkhorn_colsum(M, k, g2, eps, n, colsum)
+            kn.sinkhorn_update_g(g2, colsum, k, eps)
+    assert (g2 - g).abs().max().item() < 1e-4 * mean
+    # assignment: bit-exact given the same plan (oracle plan in fp64 through our extraction kernel) ...
+    lab_o = oot.assign(P_o)
+    lab = kn.assign_plan(torch.tensor(P_o, device=cuda_dev)).cpu().numpy()
+    assert np.array_equal(lab, lab_o)
+    # ... and the fused potentials->label kernel agrees with argmax of our own plan
+    label, sums, cnt = kn.assign_centroids(M, k, g, torch.tensor(X, device=cuda_dev))
+    label = label.cpu().numpy()
+    assert np.array_equal(label, np.argmax(g.cpu().numpy()[None, :] - M.cpu().numpy()[:, :k], axis=1))
+    assert (label == lab_o).mean() > 0.999
+    assert np.array_equal(cnt.cpu().numpy(), np.bincount(label, minlength=k))
+    ref_sum = np.stack([X[label == j].astype(np.float64).sum(0) for j in range(k)])
+    assert np.abs(sums.cpu().numpy() - ref_sum).max() < 1e-3
+
+
+def test_assign_plan_first_max_wins_on_emd_plan(cuda_dev):
+    """The reference's plan (exact EMD vertex) through the extraction kernel: bit-exact labels, ties -> first."""
+    torch = _torch()
+    from ultrare_b200 import kernels as kn
+    rng = np.random.default_rng(5)
+    n, k = 600, 4
+    M = rng.random((n, k))
+    G = oot.emd_lp(np.ones(n) / n, np.ones(k) / k, M)
+    G[:7] = 0.0                                             # all-tied rows -> label 0 like np.argmax
+    lab = kn.assign_plan(torch.tensor(G, device=cuda_dev)).cpu().numpy()
+    assert np.array_equal(lab, np.argmax(G, axis=1))
+    lab32 = kn.assign_plan(torch.tensor(G.astype(np.float32), device=cuda_dev)).cpu().numpy()
+    assert np.array_equal(lab32, np.argmax(G.astype(np.float32), axis=1))
+
+
+def test_errors_are_loud(cuda_dev):
+    torch = _torch()
+    from ultrare_b200 import kernels as kn
+    with pytest.raises(RuntimeError):
+        kn.cost_matrix(torch.zeros((10, 12), device=cuda_dev), torch.zeros((2, 12), device=cuda_dev))   # d=12
+    with pytest.raises(RuntimeError):
+        kn.ensemble_score([torch.zeros((4, 16))], [torch.zeros((4, 16))], torch.zeros((1, 4), dtype=torch.int32))

@@ -1,0 +1,300 @@
+"""B200 mirror of the reference's SISA learner (method/sisa.py:7-118).
+
+Same class, constructor and ``learn`` / ``unlearn`` / ``test`` signatures, same artefacts
+(``model{i}.pth``, ``user_mat{i}.npy``, ``item_mat{i}.npy``, ``log{i}.npy``, ``log0.npy``).
+What changes underneath:
+  * the K shard trainings of sisa.py:33-36 / 86-89 (a sequential Python loop) become ONE
+    persistent launch that trains every shard this GPU owns at once (kernels.ShardBatch);
+  * deleted users are routed to their shards by an owner-map kernel (sisa.py:76-81 is a
+    triple nested Python loop);
+  * the owner-row merge (sisa.py:52-58, 107-113) is a gather kernel;
+  * with torch.distributed initialised, shard s lives on rank s mod world and only the
+    merged user table and the evaluation scores cross GPUs (ultrare_b200/dist.py).
+
+``epoch_eval`` selects how much of the reference's per-epoch in-training evaluation
+(scratch.py:83-128) is reproduced:
+  'faithful'  every epoch of every shard is evaluated exactly as the reference does,
+              including its quirk of ensembling the in-training model with
+              ``self.model_list`` (scratch.py:83-86) -- from device snapshots taken at
+              epoch boundaries, after the batched training.  Shard models keep the
+              reference's full [n_user, k] user tables (the quirk reads non-owner rows).
+  'final'     test_* of the last epoch of each shard only (earlier entries and total_* NaN);
+  'none'      train_loss only.
+In 'final' / 'none' mode each shard model stores only its owners' user rows (compact
+table): rows a shard does not own never receive a gradient and are dropped by the merge, so
+the merged table, the item tables and every final metric are unchanged.
+"""
+from __future__ import annotations
+
+import os
+import time
+import types
+import warnings
+
+import numpy as np
+import torch
+from torch import nn
+
+from .. import dist as udist
+from .. import kernels as kn
+from .scratch import Scratch
+from .utils import baseTest
+
+
+class _Table:
+    """Evaluation view of one model: just the two weight tensors."""
+
+    def __init__(self, P, Q):
+        self.user_mat = types.SimpleNamespace(weight=P)
+        self.item_mat = types.SimpleNamespace(weight=Q)
+
+
+class _RemoteModel:
+    """Placeholder in model_list for a shard another GPU owns: the shared merged user table only."""
+
+    def __init__(self, merged_param):
+        self.user_mat = types.SimpleNamespace(weight=merged_param)
+        self.item_mat = None
+
+
+def _local(models):
+    return [m for m in models if m is not None and getattr(m, 'item_mat', None) is not None]
+
+
+class Sisa(Scratch):
+    def __init__(self, param={}, model_type='mf', n_group=5, group_index=[]):
+        super(Sisa, self).__init__(param, model_type)
+        self.n_group = n_group
+        self.group_index = group_index
+        self.model_list = []
+        self.epoch_eval = os.environ.get('ULTRARE_EPOCH_EVAL', 'faithful')
+        self.dist = udist.get()
+        owner = np.full(self.n_user, -1, dtype=np.int32)
+        row_of = np.zeros(self.n_user, dtype=np.int32)
+        for g in range(len(group_index) - 1, -1, -1):          # a user belongs to the FIRST group listing it
+            ids = np.asarray(group_index[g], dtype=np.int64)
+            owner[ids] = g
+            row_of[ids] = np.arange(len(ids), dtype=np.int32)
+        self._owner_np, self._row_of_np = owner, row_of
+        self._owner = torch.from_numpy(owner).to(self.device)
+        self._row_of = torch.from_numpy(row_of).to(self.device)
+        self._group_rows = {}
+        self.retrain_gid = set()
+        self.timing = {}
+
+    def _mode(self):
+        if self.dist.world > 1 and self.epoch_eval == 'faithful':
+            return 'final'          # the quirk needs every other shard's model on this GPU
+        return self.epoch_eval
+
+    def _rows(self, g):
+        if g not in self._group_rows:
+            self._group_rows[g] = torch.as_tensor(np.asarray(self.group_index[g], dtype=np.int64), device=self.device)
+        return self._group_rows[g]
+
+    # ------------------------------------------------------------------ evaluation
+    def test(self, test_data, verbose, save_dir):
+        """reference sisa.py:18-23."""
+        rmse, ndcg, hr = self._ensemble_test(test_data, verbose)
+        log = {'total_rmse': rmse, 'total_ndcg': ndcg, 'total_hr': hr}
+        if len(save_dir) > 0 and self.dist.rank == 0:
+            np.save(save_dir + '/log0', log)
+        self.final_log = log
+        return log
+
+    def _ensemble_test(self, test_data, verbose):
+        if self.dist.world == 1:
+            return baseTest(test_data, self.model_list, self.loss_fn, self.device, verbose)
+        # every rank scores against its own shards' item tables; partial sums are all-reduced
+        mine = _local(self.model_list)
+        ds = test_data.dataset
+        inter = ds.records(self.device)
+        if mine:
+            part, _ = kn.ensemble_score([m.user_mat.weight.data for m in mine],
+                                        [m.item_mat.weight.data for m in mine], inter, denom=1.0)
+        else:
+            part = torch.zeros(len(ds), dtype=torch.float32, device=self.device)
+        self.dist.all_reduce(part)
+        score, sse = kn.score_finalize(part, inter, float(self.n_group))
+        order, seg = ds.segments(self.device)
+        out = kn.rank_metrics(inter, score, seg, order)
+        vals = torch.cat([sse, out]).cpu().numpy()
+        users = max(vals[3], 1.0)
+        return float(np.sqrt(vals[0] / len(ds))), float(vals[1] / users), float(vals[2] / users)
+
+    # ------------------------------------------------------------------ batched shard training
+    def _train_shards(self, ids, train_dlist, test_dlist, test_data, verbose, prior):
+        """Train shards `ids` (ascending) together; returns ({shard: model}, {shard: unmerged P},
+        {shard: index of its last-epoch log entry}).
+
+        prior(i, new) -> list of models the reference would have in self.model_list while shard
+        i trains, `new` being the {shard: model} dict of this call (epoch_eval='faithful' only).
+        """
+        mine = self.dist.my_shards(list(ids))
+        mode = self._mode()
+        compact = mode != 'faithful'
+        E = self.epochs
+        t0 = time.time()
+        models, states, snaps, losses = {}, [], {}, []
+        if mine:
+            for i in mine:
+                ld = train_dlist[i]
+                if compact:
+                    models[i] = self._new_model(i + 1, user_rows=self._rows(i))
+                    rec = ld.dataset.records_mapped(self.device, self._row_of_np, 'sisa_local')
+                else:
+                    models[i] = self._new_model(i + 1)
+                    rec = ld.dataset.records(self.device)
+                states.append(kn.ShardState(rec, models[i].user_mat.weight.data, models[i].item_mat.weight.data, E,
+                                            shard_id=i + 1, perm_seed=self.seed, perm=ld.explicit_perm(self.device, E)))
+            batch = train_dlist[mine[0]].batch_size
+            sb = kn.ShardBatch(states, self.k, batch, self.lr, self.lr_decay, 50, self.lam, self.momentum)
+            if mode == 'faithful':
+                need = sum((s.P.numel() + s.Q.numel()) * 4 for s in states) * E
+                if need > 8 << 30:
+                    warnings.warn("epoch_eval='faithful' needs %.1f GB of snapshots; evaluating the last epoch only"
+                                  % (need / 2**30))
+                    mode = 'faithful-last'
+            if mode == 'faithful':
+                ends = {}
+                for j, s in enumerate(states):
+                    spe = s.steps_per_epoch(batch)
+                    for e in range(E):
+                        ends.setdefault((e + 1) * spe, []).append((j, e))
+                for boundary in sorted(ends):
+                    sb.train(boundary)
+                    for j, e in ends[boundary]:
+                        snaps[(mine[j], e)] = (states[j].P.clone(), states[j].Q.clone())
+            else:
+                sb.train()
+            self._last_batch = sb
+            losses = sb.train_losses()                       # the one sync of the whole training
+        self.timing['train_s'] = time.time() - t0
+
+        # ---- logs, in the reference's order: shard after shard, epoch after epoch (Appendix A14)
+        nan = float('nan')
+        last_idx = {}
+        stamp = time.strftime('%H:%M:%S', time.gmtime(self.timing['train_s'] / max(1, E * max(1, len(mine)))))
+        for j, i in enumerate(mine):
+            pri = prior(i, models) if mode.startswith('faithful') else None
+            for e in range(E):
+                self.log['train_loss'].append(float(losses[j][e]))
+                tr = to = (nan, nan, nan)
+                if mode == 'faithful' or (mode == 'faithful-last' and e == E - 1):
+                    P, Q = snaps[(i, e)] if mode == 'faithful' else (states[j].P, states[j].Q)
+                    ms = pri + [_Table(P, Q)]
+                    tr = baseTest(test_dlist[i], ms, self.loss_fn, self.device, 0)
+                    to = baseTest(test_data, ms, self.loss_fn, self.device, 0)
+                for key, v in zip(('test_rmse', 'test_ndcg', 'test_hr'), tr):
+                    self.log[key].append(v)
+                for key, v in zip(('total_rmse', 'total_ndcg', 'total_hr'), to):
+                    self.log[key].append(v)
+                self.log['time'].append(stamp)
+                if verbose == 1:
+                    print(f'[shard {i+1}] Epoch: [{e+1:>2d}/{E:>2d}] train loss: {losses[j][e]:>.9f},'
+                          f' test RMSE: {tr[0]:>.4f}, total RMSE: {to[0]:>.4f}')
+            last_idx[i] = len(self.log['test_rmse']) - 1
+        unmerged = {i: models[i].user_mat.weight.data for i in mine}
+        return models, unmerged, last_idx, compact
+
+    def _finish(self, new, unmerged, last_idx, compact, merged, test_dlist, save_dir):
+        """After the merge: 'final'-mode last-epoch test metrics, then the per-shard artefacts."""
+        full_merged = nn.Parameter(merged, requires_grad=False)
+        for i, m in new.items():
+            m.user_mat = nn.Embedding(merged.shape[0], self.k, _weight=merged)
+            m.user_mat.weight = full_merged
+        if self._mode() == 'final' and self.dist.world == 1:
+            for i, m in new.items():       # own shard's test users are all owned by shard i: merged rows == its rows
+                tr = baseTest(test_dlist[i], [m], self.loss_fn, self.device, 0)
+                for key, v in zip(('test_rmse', 'test_ndcg', 'test_hr'), tr):
+                    self.log[key][last_idx[i]] = v
+        if len(save_dir) > 0:
+            for i, m in new.items():
+                P = unmerged[i]
+                if compact:                # artefact keeps the reference's [n_user, k] shape; non-owner rows zero
+                    full = torch.zeros((self.n_user, self.k), dtype=torch.float32, device=self.device)
+                    full[self._rows(i)] = P
+                    P = full
+                torch.save({'user_mat.weight': P.cpu(), 'item_mat.weight': m.item_mat.weight.data.cpu()},
+                           save_dir + '/model' + str(i + 1) + '.pth')
+                np.save(save_dir + '/user_mat' + str(i + 1), P.cpu().numpy())
+                np.save(save_dir + '/item_mat' + str(i + 1), m.item_mat.weight.data.cpu().numpy())
+                np.save(save_dir + '/log' + str(i + 1), self.log)
+
+    # ------------------------------------------------------------------ merge
+    def _merged_from(self, base, unmerged, compact, retrain_flags):
+        """Owner rows of the freshly trained shards gathered over `base` (or zeros): sisa.py:52-58,107-113."""
+        dev, K = self.device, self.n_group
+        filler = next(iter(unmerged.values())) if unmerged else base
+        tables = [unmerged.get(s, filler) for s in range(K)]
+        row_of = self._row_of if compact else None
+        if self.dist.world == 1:
+            merged = torch.zeros((self.n_user, self.k), dtype=torch.float32, device=dev) if base is None else base.clone()
+            kn.merge_user_rows(tables, self._owner, merged, row_of=row_of, retrain=retrain_flags,
+                               zero_unowned=base is None)
+            return merged
+        # multi-GPU: each rank contributes the rows of the shards it trained; rows are disjoint
+        mine_flags = torch.zeros(K, dtype=torch.int32, device=dev)
+        for s in unmerged:
+            mine_flags[s] = 1
+        contrib = torch.zeros((self.n_user, self.k), dtype=torch.float32, device=dev)
+        if unmerged:
+            kn.merge_user_rows(tables, self._owner, contrib, row_of=row_of, retrain=mine_flags, zero_unowned=True)
+        self.dist.all_reduce(contrib)
+        if base is None:
+            return contrib
+        rows = (self._owner >= 0) & (retrain_flags[self._owner.clamp(min=0).long()] != 0)
+        merged = base.clone()
+        merged[rows] = contrib[rows]
+        return merged
+
+    # ------------------------------------------------------------------ learn / unlearn
+    def learn(self, train_dlist, test_dlist, test_data, verbose, save_dir):
+        """reference sisa.py:25-63."""
+        assert len(train_dlist) == self.n_group
+        assert len(test_dlist) == self.n_group
+        new, unmerged, last_idx, compact = self._train_shards(
+            range(self.n_group), train_dlist, test_dlist, test_data, verbose,
+            lambda i, new: [new[j] for j in range(i)])
+        merged = self._merged_from(None, unmerged, compact, None)
+        self._finish(new, unmerged, last_idx, compact, merged, test_dlist, save_dir)
+        shared = next(iter(new.values())).user_mat.weight if new else nn.Parameter(merged, requires_grad=False)
+        self.model_list = [new[i] if i in new else _RemoteModel(shared) for i in range(self.n_group)]
+        self.test(test_data, verbose, save_dir)
+        return self.model_list
+
+    def route(self, del_user):
+        """retrain flags of sisa.py:76-81, by the owner-map kernel (int32 [n_group] on device)."""
+        d = torch.as_tensor(np.asarray(list(del_user), dtype=np.int32), device=self.device)
+        return kn.route_deletions(self._owner, d, self.n_group)
+
+    def unlearn(self, model_list, train_dlist, test_dlist, test_data, del_user, verbose, save_dir):
+        """reference sisa.py:66-118."""
+        self.model_list = list(model_list)
+        assert len(train_dlist) == self.n_group
+        assert len(test_dlist) == self.n_group
+
+        flags = self.route(del_user)
+        self.retrain_gid = set(int(s) for s in np.flatnonzero(flags.cpu().numpy()))
+        order = sorted(self.retrain_gid)
+        model_before_unlearn = self.model_list[0]                               # sisa.py:84
+        base = model_before_unlearn.user_mat.weight.data
+        old = list(self.model_list)
+
+        def prior(i, new):
+            # self.model_list as the reference sees it while retraining shard i: the old models, with
+            # the shards retrained before i (ascending set order) already replaced (sisa.py:86-89)
+            cur = [(new[j] if (j in new and j in order and order.index(j) < order.index(i)) else old[j])
+                   for j in range(self.n_group)]
+            return _local(cur)
+
+        new, unmerged, last_idx, compact = self._train_shards(order, train_dlist, test_dlist, test_data, verbose, prior)
+        merged = self._merged_from(base, unmerged, compact, flags)
+        self._finish(new, unmerged, last_idx, compact, merged, test_dlist, save_dir)
+        for i, m in new.items():
+            self.model_list[i] = m
+        shared = next(iter(new.values())).user_mat.weight if new else nn.Parameter(merged, requires_grad=False)
+        for m in self.model_list:
+            m.user_mat.weight = shared
+        self.test(test_data, verbose, save_dir)
+        return self.model_list

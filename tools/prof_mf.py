@@ -1,0 +1,56 @@
+"""Profiling driver: one ml1m-shaped K=5 batched MF training (the dominant kernel), nothing else.
+    python tools/prof_mf.py [--epochs E] [--d D] [--reps R]
+Prints the kernel time measured with CUDA events (never under a profiler)."""
+import argparse
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from ultrare_b200 import kernels as kn, synth  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--epochs", type=int, default=10)
+ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--batch", type=int, default=30000)
+ap.add_argument("--k", type=int, default=5)
+args = ap.parse_args()
+
+dev = torch.device("cuda:0")
+train, _ = synth.ml_like()
+u, i, r = train
+U, I, d, K = 6040, 3416, 16, args.k
+rs = np.random.RandomState(0)
+perm_u = rs.permutation(U)
+groups = np.array_split(perm_u, K)
+row_of = np.zeros(U, dtype=np.int64)
+owner = np.zeros(U, dtype=np.int64)
+for g, ids in enumerate(groups):
+    row_of[ids] = np.arange(len(ids))
+    owner[ids] = g
+shards = []
+gen = torch.Generator(device=dev).manual_seed(1)
+for g, ids in enumerate(groups):
+    loc = owner[u] == g
+    inter = kn.pack_interactions(row_of[u[loc]], i[loc], r[loc] / 5.0, dev)
+    P = torch.empty((len(ids), d), device=dev).normal_(generator=gen)
+    Q = torch.empty((I, d), device=dev).normal_(generator=gen)
+    shards.append(kn.ShardState(inter, P, Q, args.epochs, shard_id=g + 1, perm_seed=42))
+sb = kn.ShardBatch(shards, d, args.batch)
+n_inter = sum(s.n for s in shards) * args.epochs
+for rep in range(args.reps):
+    for s in shards:
+        s.bufP.zero_(); s.bufQ.zero_(); s.sse.zero_()
+    sb.step = 0
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    sb.train()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    print(f"rep {rep}: {ms:.3f} ms for {sb.total_steps} steps ({ms * 1e3 / sb.total_steps:.2f} us/step), "
+          f"{n_inter / ms / 1e6:.2f} G inter/s, {n_inter * 268 / ms / 1e6:.1f} GB/s algorithmic")
+print("losses", [float(x[-1]) for x in sb.train_losses()])

@@ -30,49 +30,9 @@ struct Workspace {
   unsigned pad[63];
 };
 
-// dynamic shared memory layout, K = number of shards
-struct Smem {
-  int K;
-  // pointers / constants, loaded once
-  const ure_inter_t** inter;
-  const int32_t** perm;
-  float** P; float** Q; float** bufP; float** bufQ; float** gP; float** gQ;
-  double** sse;
-  int* n; int* n_user; int* n_item; int* spe;
-  uint32_t* seed; int* shard_id;
-  // per-step
-  int* item_prefix;        // [K+1] flattened batch positions
-  long long* row_prefix;   // [2K+1] flattened float4 elements of the dense sweep
-  int* epoch; int* start; float* lr;
-  Feistel* fe;
-  float* sse_acc;          // [K]
-
-  __device__ void carve(unsigned char* base, int K_) {
-    K = K_;
-    size_t o = 0;
-    auto take = [&](size_t bytes) { unsigned char* p = base + o; o += (bytes + 15) & ~size_t(15); return p; };
-    inter = (const ure_inter_t**)take(sizeof(void*) * K);
-    perm = (const int32_t**)take(sizeof(void*) * K);
-    P = (float**)take(sizeof(void*) * K);
-    Q = (float**)take(sizeof(void*) * K);
-    bufP = (float**)take(sizeof(void*) * K);
-    bufQ = (float**)take(sizeof(void*) * K);
-    gP = (float**)take(sizeof(void*) * K);
-    gQ = (float**)take(sizeof(void*) * K);
-    sse = (double**)take(sizeof(void*) * K);
-    row_prefix = (long long*)take(sizeof(long long) * (2 * K + 1));
-    n = (int*)take(4 * K); n_user = (int*)take(4 * K); n_item = (int*)take(4 * K); spe = (int*)take(4 * K);
-    seed = (uint32_t*)take(4 * K); shard_id = (int*)take(4 * K);
-    item_prefix = (int*)take(4 * (K + 1));
-    epoch = (int*)take(4 * K); start = (int*)take(4 * K); lr = (float*)take(4 * K);
-    fe = (Feistel*)take(sizeof(Feistel) * K);
-    sse_acc = (float*)take(4 * K);
-  }
-  static size_t bytes(int K) {
-    auto r = [](size_t b) { return (b + 15) & ~size_t(15); };
-    return 9 * r(sizeof(void*) * K) + r(sizeof(long long) * (2 * K + 1)) + 6 * r(4 * K) + r(4 * (K + 1)) +
-           3 * r(4 * K) + r(sizeof(Feistel) * K) + r(4 * K);
-  }
+// Per-CTA shard tables (static shared memory, URE_MAX_SHARDS entries): direct LDS addressing.
+struct ShardPtrs {      // 32 bytes: fetched with two LDS.128
+  float* P; float* Q; float* gP; float* gQ;
 };
 
 // largest s with prefix[s] <= x  (prefix[0] = 0, prefix[K] = total > x)
@@ -86,28 +46,87 @@ __device__ __forceinline__ int find_segment(const T* prefix, int nseg, T x) {
   return lo;
 }
 
+// Gradient work of one 32-interaction warp chunk.  Lane l fetched interaction l (u, it, r, shard s);
+// a group of G = D/4 lanes processes its G interactions SUB at a time (2*SUB 16-byte gathers in flight).
+// UNIFORM: the whole chunk lies in shard tables `tp`; otherwise each interaction looks its shard up.
+template <int D, bool UNIFORM>
+__device__ __forceinline__ float chunk_gradients(int u, int it, float r, int s, const ShardPtrs& tp,
+                                                  const ShardPtrs* s_ptr, int gl) {
+  constexpr int G = D / 4;
+  constexpr int SUB = (G < 4) ? G : 4;
+  float my_e = 0.f;
+#pragma unroll
+  for (int q0 = 0; q0 < G; q0 += SUB) {
+    float4 pu[SUB], qi[SUB];
+    int uq[SUB], iq[SUB], sq[SUB];
+    float rq[SUB];
+#pragma unroll
+    for (int q = 0; q < SUB; ++q) {
+      uq[q] = __shfl_sync(0xffffffffu, u, q0 + q, G);
+      iq[q] = __shfl_sync(0xffffffffu, it, q0 + q, G);
+      rq[q] = __shfl_sync(0xffffffffu, r, q0 + q, G);
+      sq[q] = __shfl_sync(0xffffffffu, s, q0 + q, G);
+      pu[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+      qi[q] = pu[q];
+      if (sq[q] >= 0) {
+        const float* Pb = UNIFORM ? tp.P : s_ptr[sq[q]].P;
+        const float* Qb = UNIFORM ? tp.Q : s_ptr[sq[q]].Q;
+        pu[q] = ld_cg_f4(Pb + (size_t)uq[q] * D + 4 * gl);
+        qi[q] = ld_cg_f4(Qb + (size_t)iq[q] * D + 4 * gl);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < SUB; ++q) {
+      float dot = pu[q].x * qi[q].x;
+      dot = fmaf(pu[q].y, qi[q].y, dot);
+      dot = fmaf(pu[q].z, qi[q].z, dot);
+      dot = fmaf(pu[q].w, qi[q].w, dot);
+#pragma unroll
+      for (int o = G / 2; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o, G);
+      const float e = dot - rq[q];
+      if (gl == q0 + q) my_e = e;
+      if (sq[q] >= 0) {
+        float* gPb = UNIFORM ? tp.gP : s_ptr[sq[q]].gP;
+        float* gQb = UNIFORM ? tp.gQ : s_ptr[sq[q]].gQ;
+        const float ge = 2.f * e;
+        red_add_f4(gPb + (size_t)uq[q] * D + 4 * gl, ge * qi[q].x, ge * qi[q].y, ge * qi[q].z, ge * qi[q].w);
+        red_add_f4(gQb + (size_t)iq[q] * D + 4 * gl, ge * pu[q].x, ge * pu[q].y, ge * pu[q].z, ge * pu[q].w);
+      }
+    }
+  }
+  return my_e;
+}
+
 template <int D>
 __global__ void __launch_bounds__(kThreads, 1)
 mf_train_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams_t hp, int epochs,
                 long long step_begin, long long step_end, Workspace* ws) {
   constexpr int G = D / 4;                 // lanes per interaction
-  constexpr int SUB = (G < 4) ? G : 4;     // interactions whose gathers are in flight together
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ Smem sm;
+  constexpr int KM = URE_MAX_SHARDS;
+  __shared__ ShardPtrs s_ptr[KM];
+  __shared__ const ure_inter_t* s_inter[KM];
+  __shared__ const int32_t* s_perm[KM];
+  __shared__ float* s_buf[2 * KM];         // bufP, bufQ
+  __shared__ double* s_sse[KM];
+  __shared__ long long s_row_prefix[2 * KM + 1];
+  __shared__ int s_n[KM], s_nuser[KM], s_nitem[KM], s_spe[KM], s_shard_id[KM];
+  __shared__ uint32_t s_seed[KM];
+  __shared__ int s_item_prefix[KM + 1], s_epoch[KM], s_start[KM];
+  __shared__ float s_lr[KM], s_sse_acc[KM];
+  __shared__ Feistel s_fe[KM];
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int gl = lane % G;
-  if (tid == 0) sm.carve(smem_raw, K);
-  __syncthreads();
   for (int s = tid; s < K; s += kThreads) {
     const ure_mf_shard_t sh = shards[s];
-    sm.inter[s] = sh.inter; sm.perm[s] = sh.perm;
-    sm.P[s] = sh.P; sm.Q[s] = sh.Q; sm.bufP[s] = sh.bufP; sm.bufQ[s] = sh.bufQ;
-    sm.gP[s] = sh.gP; sm.gQ[s] = sh.gQ; sm.sse[s] = sh.sse;
-    sm.n[s] = sh.n; sm.n_user[s] = sh.n_user; sm.n_item[s] = sh.n_item;
-    sm.spe[s] = (sh.n + hp.batch - 1) / hp.batch;
-    sm.seed[s] = sh.perm_seed; sm.shard_id[s] = sh.shard_id;
-    sm.sse_acc[s] = 0.f;
+    s_ptr[s] = ShardPtrs{sh.P, sh.Q, sh.gP, sh.gQ};
+    s_inter[s] = sh.inter; s_perm[s] = sh.perm;
+    s_buf[2 * s] = sh.bufP; s_buf[2 * s + 1] = sh.bufQ;
+    s_sse[s] = sh.sse;
+    s_n[s] = sh.n; s_nuser[s] = sh.n_user; s_nitem[s] = sh.n_item;
+    s_spe[s] = (sh.n + hp.batch - 1) / hp.batch;
+    s_seed[s] = sh.perm_seed; s_shard_id[s] = sh.shard_id;
+    s_sse_acc[s] = 0.f;
   }
   unsigned bar_target = 0;
   const long long n_threads = (long long)gridDim.x * kThreads;
@@ -119,134 +138,110 @@ mf_train_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
   for (long long t = step_begin; t < step_end; ++t) {
     // ---------------------------------------------------------------- per-step tables
     for (int s = tid; s < K; s += kThreads) {
-      const int spe = sm.spe[s];
+      const int spe = s_spe[s];
       const bool active = spe > 0 && t < (long long)spe * epochs;
       int ep = 0, cnt = 0, st = 0;
       if (active) {
         ep = (int)(t / spe);
         st = (int)(t % spe) * hp.batch;
-        cnt = min(hp.batch, sm.n[s] - st);
-        sm.fe[s].init((uint32_t)sm.n[s], perm_key(sm.seed[s], (uint32_t)sm.shard_id[s], (uint32_t)ep));
-        sm.lr[s] = (float)((double)hp.lr0 * pow((double)hp.lr_decay, (double)(ep / hp.lr_step)));
+        cnt = min(hp.batch, s_n[s] - st);
+        s_fe[s].init((uint32_t)s_n[s], perm_key(s_seed[s], (uint32_t)s_shard_id[s], (uint32_t)ep));
+        double lr = (double)hp.lr0;
+        for (int q = ep / hp.lr_step; q > 0; --q) lr *= (double)hp.lr_decay;
+        s_lr[s] = (float)lr;
       }
-      sm.epoch[s] = active ? ep : -1;
-      sm.start[s] = st;
-      sm.item_prefix[s + 1] = cnt;                               // counts, scanned below
-      sm.row_prefix[2 * s + 1] = active ? (long long)sm.n_user[s] * G : 0;
-      sm.row_prefix[2 * s + 2] = active ? (long long)sm.n_item[s] * G : 0;
+      s_epoch[s] = active ? ep : -1;
+      s_start[s] = st;
+      s_item_prefix[s + 1] = cnt;                               // counts, scanned below
+      s_row_prefix[2 * s + 1] = active ? (long long)s_nuser[s] * G : 0;
+      s_row_prefix[2 * s + 2] = active ? (long long)s_nitem[s] * G : 0;
     }
     __syncthreads();
     if (tid < 32) {                                              // warp 0: inclusive scans
       int carry = 0;
       for (int base = 0; base < K; base += 32) {
         int idx = base + lane;
-        int v = idx < K ? sm.item_prefix[idx + 1] : 0;
+        int v = idx < K ? s_item_prefix[idx + 1] : 0;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { int u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
-        if (idx < K) sm.item_prefix[idx + 1] = v + carry;
+        if (idx < K) s_item_prefix[idx + 1] = v + carry;
         carry += __shfl_sync(0xffffffffu, v, 31);
       }
       long long carry2 = 0;
       for (int base = 0; base < 2 * K; base += 32) {
         int idx = base + lane;
-        long long v = idx < 2 * K ? sm.row_prefix[idx + 1] : 0;
+        long long v = idx < 2 * K ? s_row_prefix[idx + 1] : 0;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { long long u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
-        if (idx < 2 * K) sm.row_prefix[idx + 1] = v + carry2;
+        if (idx < 2 * K) s_row_prefix[idx + 1] = v + carry2;
         carry2 += __shfl_sync(0xffffffffu, v, 31);
       }
-      if (lane == 0) { sm.item_prefix[0] = 0; sm.row_prefix[0] = 0; }
+      if (lane == 0) { s_item_prefix[0] = 0; s_row_prefix[0] = 0; }
     }
     __syncthreads();
 
     // ---------------------------------------------------------------- phase A: gradients
-    const int total = sm.item_prefix[K];
-    float acc = 0.f;
+    const int total = s_item_prefix[K];
+    float acc = 0.f;          // sum of e^2 of this lane's own interactions, all in shard acc_s
     int acc_s = -1;
     for (int wc = gwarp; wc * 32 < total; wc += n_warps) {
       const int item = wc * 32 + lane;
       const bool valid = item < total;
-      int s = 0;
+      int s = -1;
       int u = 0, it = 0;
       float r = 0.f;
       if (valid) {
-        s = find_segment(sm.item_prefix, K, item);
-        const int j = sm.start[s] + (item - sm.item_prefix[s]);
-        const int32_t* pm = sm.perm[s];
-        const uint32_t idx = pm ? (uint32_t)__ldg(pm + (long long)sm.epoch[s] * sm.n[s] + j)
-                                : sm.fe[s]((uint32_t)j);
-        const int4 rec = ld_stream_i4(sm.inter[s] + idx);
+        s = find_segment(s_item_prefix, K, item);
+        const int j = s_start[s] + (item - s_item_prefix[s]);
+        const int32_t* pm = s_perm[s];
+        const uint32_t idx = pm ? (uint32_t)__ldg(pm + (long long)s_epoch[s] * s_n[s] + j)
+                                : s_fe[s]((uint32_t)j);
+        const int4 rec = ld_stream_i4(s_inter[s] + idx);
         u = rec.x; it = rec.y; r = __int_as_float(rec.z);
       }
-      float my_e = 0.f;
-#pragma unroll
-      for (int q0 = 0; q0 < G; q0 += SUB) {
-        float4 pu[SUB], qi[SUB];
-        int uq[SUB], iq[SUB], sq[SUB];
-        float rq[SUB];
-        bool vq[SUB];
-#pragma unroll
-        for (int q = 0; q < SUB; ++q) {
-          uq[q] = __shfl_sync(0xffffffffu, u, q0 + q, G);
-          iq[q] = __shfl_sync(0xffffffffu, it, q0 + q, G);
-          rq[q] = __shfl_sync(0xffffffffu, r, q0 + q, G);
-          sq[q] = __shfl_sync(0xffffffffu, s, q0 + q, G);
-          vq[q] = __shfl_sync(0xffffffffu, (int)valid, q0 + q, G) != 0;
-          pu[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-          qi[q] = pu[q];
-          if (vq[q]) {
-            pu[q] = ld_cg_f4(sm.P[sq[q]] + (size_t)uq[q] * D + 4 * gl);
-            qi[q] = ld_cg_f4(sm.Q[sq[q]] + (size_t)iq[q] * D + 4 * gl);
-          }
-        }
-#pragma unroll
-        for (int q = 0; q < SUB; ++q) {
-          float dot = pu[q].x * qi[q].x;
-          dot = fmaf(pu[q].y, qi[q].y, dot);
-          dot = fmaf(pu[q].z, qi[q].z, dot);
-          dot = fmaf(pu[q].w, qi[q].w, dot);
-#pragma unroll
-          for (int o = G / 2; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o, G);
-          const float e = dot - rq[q];
-          if (gl == q0 + q) my_e = e;
-          if (vq[q]) {
-            const float ge = 2.f * e;
-            red_add_f4(sm.gP[sq[q]] + (size_t)uq[q] * D + 4 * gl, ge * qi[q].x, ge * qi[q].y, ge * qi[q].z, ge * qi[q].w);
-            red_add_f4(sm.gQ[sq[q]] + (size_t)iq[q] * D + 4 * gl, ge * pu[q].x, ge * pu[q].y, ge * pu[q].z, ge * pu[q].w);
-          }
-        }
-      }
-      if (valid) {
-        if (s != acc_s) {
-          if (acc_s >= 0) atomicAdd(&sm.sse_acc[acc_s], acc);
+      // the common case: the whole 32-interaction chunk lies in one shard -> table pointers once per warp
+      const int s0 = __shfl_sync(0xffffffffu, s, 0);
+      const bool uniform = __all_sync(0xffffffffu, s == s0 || !valid);
+      const ShardPtrs tp = s_ptr[s0];
+      const float my_e = uniform ? chunk_gradients<D, true>(u, it, r, s, tp, s_ptr, gl)
+                                 : chunk_gradients<D, false>(u, it, r, s, tp, s_ptr, gl);
+      // loss: warp-reduce when the chunk is single-shard (one shared atomic per warp, not per lane)
+      const float e2 = valid ? my_e * my_e : 0.f;
+      if (uniform) {
+        const float w = warp_sum(e2);
+        if (s0 != acc_s) {
+          if (acc_s >= 0 && lane == 0) atomicAdd(&s_sse_acc[acc_s], acc);
           acc = 0.f;
-          acc_s = s;
+          acc_s = s0;
         }
-        acc = fmaf(my_e, my_e, acc);
+        acc += w;                                   // every lane carries the warp total; lane 0 publishes
+      } else if (valid) {
+        atomicAdd(&s_sse_acc[s], e2);
       }
     }
-    if (acc_s >= 0) atomicAdd(&sm.sse_acc[acc_s], acc);
+    if (acc_s >= 0 && lane == 0) atomicAdd(&s_sse_acc[acc_s], acc);
     __syncthreads();
     for (int s = tid; s < K; s += kThreads) {
-      const float v = sm.sse_acc[s];
+      const float v = s_sse_acc[s];
       if (v != 0.f) {
-        atomicAdd(sm.sse[s] + sm.epoch[s], (double)v);
-        sm.sse_acc[s] = 0.f;
+        atomicAdd(s_sse[s] + s_epoch[s], (double)v);
+        s_sse_acc[s] = 0.f;
       }
     }
     grid_barrier(&ws->barrier, bar_target);
 
     // ---------------------------------------------------------------- phase B: dense SGD sweep
-    const long long total4 = sm.row_prefix[2 * K];
+    const long long total4 = s_row_prefix[2 * K];
     const float wd = hp.weight_decay, mu = hp.momentum;
     for (long long x = gtid; x < total4; x += n_threads) {
-      const int seg = find_segment(sm.row_prefix, 2 * K, x);
-      const size_t off = (size_t)(x - sm.row_prefix[seg]) * 4;
+      const int seg = find_segment(s_row_prefix, 2 * K, x);
+      const size_t off = (size_t)(x - s_row_prefix[seg]) * 4;
       const int s = seg >> 1;
-      float* W = (seg & 1) ? sm.Q[s] : sm.P[s];
-      float* Bf = (seg & 1) ? sm.bufQ[s] : sm.bufP[s];
-      float* Gr = (seg & 1) ? sm.gQ[s] : sm.gP[s];
-      const float nlr = -sm.lr[s];
+      const ShardPtrs tp = s_ptr[s];
+      float* W = (seg & 1) ? tp.Q : tp.P;
+      float* Gr = (seg & 1) ? tp.gQ : tp.gP;
+      float* Bf = s_buf[seg];
+      const float nlr = -s_lr[s];
       float4 g = ld_cg_f4(Gr + off), w = ld_cg_f4(W + off), b = ld_cg_f4(Bf + off);
       // torch SGD: d_p = g + wd*w (fma); buf = buf*mu + d_p; w = w + (-lr)*buf (fma)
       g.x = fmaf(wd, w.x, g.x); g.y = fmaf(wd, w.y, g.y); g.z = fmaf(wd, w.z, g.z); g.w = fmaf(wd, w.w, g.w);
@@ -265,8 +260,7 @@ template <int D>
 int launch(const ure_mf_shard_t* d_shards, int K, const ure_mf_hparams_t& hp, int epochs, long long s0,
            long long s1, Workspace* ws, cudaStream_t st) {
   auto kern = mf_train_kernel<D>;
-  const size_t smem = Smem::bytes(K);
-  URE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const size_t smem = 0;
   int occ = 0;
   URE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem));
   URE_REQUIRE(occ >= 1, URE_ECOOP, "mf_train_kernel<%d> cannot be resident (smem %zu)", D, smem);

@@ -91,6 +91,14 @@ int64_t ure_mf_train_workspace_bytes(void);
 int ure_mf_train(const ure_mf_shard_t* d_shards, int n_shards, const ure_mf_hparams_t* h_hp,
                  int epochs, int64_t step_begin, int64_t step_end, void* d_workspace, void* stream);
 
+/* Diagnostics (tracing): record six SM-clock stamps per CTA and step -- step start, tables ready,
+ * gradients issued, barrier 1 passed, sweep issued, barrier 2 passed -- for the first `steps` steps of
+ * the following ure_mf_train calls into d_trace [steps][ure_mf_grid_size()][6] int64; NULL = off. */
+int ure_mf_train_trace(void* d_workspace, int64_t* d_trace, int steps, void* stream);
+int ure_mf_grid_size(void);
+/* Diagnostics: bit 0 skips the gradient scatter, bit 1 uses the identity visiting order (timing experiments). */
+int ure_mf_debug_flags(void* d_workspace, unsigned flags, void* stream);
+
 /* Lazy mode: bring every row of every shard up to date (end of training / before export). */
 int ure_mf_flush(const ure_mf_shard_t* d_shards, int n_shards, const ure_mf_hparams_t* h_hp,
                  int epochs, int64_t step_now, void* stream);

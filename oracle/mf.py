@@ -44,29 +44,40 @@ def perm_key(seed: int, shard: int, epoch: int) -> int:
     return k
 
 
-def feistel_half_bits(n: int) -> int:
-    bits = max(2, int(n - 1).bit_length())
-    return (bits + 1) // 2
+FEISTEL_ROUNDS = 6
+
+
+def feistel_domain(n: int):
+    """(a, b): a = ceil(sqrt(n)), b = ceil(n/a) -- the mixed-radix domain [0,a) x [0,b) >= n."""
+    import math
+    a = max(1, math.isqrt(n - 1) + 1) if n > 1 else 1
+    b = max(1, -(-n // a))
+    return a, b
 
 
 def feistel_perm(n: int, key: int) -> np.ndarray:
-    """perm[j] for j in [0,n): the position-j element of the epoch's shuffled order."""
+    """perm[j] for j in [0,n): the position-j element of the epoch's shuffled order.
+
+    6-round alternating Feistel over x = L*b + R, cycle-walked into [0,n)
+    (ultrare_b200/csrc/feistel.cuh)."""
     if n <= 1:
         return np.zeros(n, dtype=np.int64)
-    half = feistel_half_bits(n)
-    mask = (1 << half) - 1
-    rk = [int(mix32((key + r * 0x9E3779B9) & 0xFFFFFFFF)) for r in range(4)]
+    a, b = feistel_domain(n)
+    rk = [int(mix32((key + r * 0x9E3779B9) & 0xFFFFFFFF)) for r in range(FEISTEL_ROUNDS)]
     x = np.arange(n, dtype=np.uint64)
     out = np.empty(n, dtype=np.int64)
     todo = np.arange(n)
     while todo.size:
-        L = x >> half
-        R = x & mask
-        for r in range(4):
-            t = L ^ (mix32(R ^ rk[r]) & mask)
-            L = R
-            R = t
-        x = (L << half) | R
+        L = x // b
+        R = x - L * b
+        for r in range(FEISTEL_ROUNDS):
+            if r % 2 == 0:
+                L = L + ((mix32(R ^ rk[r]) * a) >> 32)
+                L = np.where(L >= a, L - a, L)
+            else:
+                R = R + ((mix32(L ^ rk[r]) * b) >> 32)
+                R = np.where(R >= b, R - b, R)
+        x = L * b + R
         done = x < n
         out[todo[done]] = x[done].astype(np.int64)
         todo = todo[~done]

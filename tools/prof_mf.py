@@ -54,3 +54,33 @@ for rep in range(args.reps):
     print(f"rep {rep}: {ms:.3f} ms for {sb.total_steps} steps ({ms * 1e3 / sb.total_steps:.2f} us/step), "
           f"{n_inter / ms / 1e6:.2f} G inter/s, {n_inter * 268 / ms / 1e6:.1f} GB/s algorithmic")
 print("losses", [float(x[-1]) for x in sb.train_losses()])
+
+ap2 = None
+def run_trace(flags, label):
+    print("====", label)
+    L = _lib.lib()
+    grid, nst = L.ure_mf_grid_size(), 40
+    trace = torch.zeros((nst, grid, 6), dtype=torch.int64, device=dev)
+    _lib.check(L.ure_mf_train_trace(C.c_void_p(sb.ws.data_ptr()), C.c_void_p(trace.data_ptr()), nst, None))
+    for s in shards:
+        s.bufP.zero_(); s.bufQ.zero_(); s.sse.zero_()
+    sb.step = 0
+    _lib.check(L.ure_mf_debug_flags(C.c_void_p(sb.ws.data_ptr()), flags, None))
+    sb.train()
+    torch.cuda.synchronize()
+    _lib.check(L.ure_mf_train_trace(C.c_void_p(sb.ws.data_ptr()), None, 0, None))
+    _lib.check(L.ure_mf_debug_flags(C.c_void_p(sb.ws.data_ptr()), 0, None))
+    tr = trace.cpu().numpy().astype(np.float64)[5:]          # skip cold steps
+    d = np.diff(tr, axis=2)                                   # [steps, grid, 5]
+    names = ["gradients", "overlap1", "wait1", "sweep", "arr2+fetch+wait2"]
+    print("per-phase SM cycles (median over CTAs and steps / p95 / max):")
+    for k, nm in enumerate(names):
+        x = d[:, :, k].ravel()
+        print(f"  {nm:18s} {np.median(x):8.0f} {np.percentile(x, 95):8.0f} {x.max():8.0f}")
+    step_cyc = tr[1:, :, 0] - tr[:-1, :, 0]
+    print("step cycles median", np.median(step_cyc), "=> us at 1.965 GHz:", np.median(step_cyc) / 1965)
+
+import ctypes as C
+from ultrare_b200 import _lib
+for flags, label in ((0, "baseline"), (1, "no REDs"), (2, "identity order"), (3, "no REDs + identity order")):
+    run_trace(flags, label)

@@ -51,6 +51,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dig:
         return LIB
     os.makedirs(OBJ, exist_ok=True)
+    if os.path.exists(stamp):
+        os.unlink(stamp)
     objs, logs = [], []
     with cf.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
         for src, obj, rc, out in ex.map(_compile, sources()):
@@ -62,6 +64,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         f.write("\n".join(logs))
     if verbose:
         print("\n".join(logs))
+    if os.path.exists(LIB):
+        os.unlink(LIB)              # never leave a stale library behind a failed link
     r = subprocess.run([NVCC, "-shared", "-o", LIB, *objs, "-lcudart"], capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stdout + r.stderr)

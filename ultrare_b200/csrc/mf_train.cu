@@ -7,16 +7,23 @@
 // on every row of both tables, for every shard (the K sequential Scratch.train calls
 // of method/sisa.py:33-36,86-89 become one launch).
 //
-// Structure per global step t (cooperative launch, one CTA per SM):
-//   phase A  all shards' batches, flattened and split evenly over the grid; a group of
-//            d/4 lanes owns one interaction: 16-byte gathers of P[u], Q[i], shuffle
-//            dot product, red.global.add.v4.f32 scatter of both gradient rows;
-//   barrier
-//   phase B  dense sweep over all rows of all active shards: g += wd*w; buf = mu*buf+g;
-//            w -= lr*buf; g = 0   (in place);
-//   barrier
-// The visiting order is either an explicit permutation (parity runs against the
-// reference) or the inline Feistel permutation (feistel.cuh).
+// One cooperative launch, one CTA per SM, all steps inside.  The batch-synchronous semantics
+// need two grid-wide barriers per step; on this 148-SM part a barrier costs ~2 us of pure
+// latency, so each barrier is split into ARRIVE and WAIT and everything that does not depend
+// on the other CTAs is issued in between:
+//
+//   gradients(t)   gather P[u], Q[i] (16-byte L2 loads), shuffle dot product, loss,
+//                  red.global.add.v4.f32 scatter of both gradient rows
+//   ARRIVE 1       -- overlap: load this thread's sweep operands w, buf (unchanged by the
+//                     gradient phase); warp 1 builds the step tables of t+1
+//   WAIT 1
+//   sweep(t)       dense SGD on every row of every active shard: g += wd*w; buf = mu*buf+g;
+//                  w -= lr*buf; g = 0   (in place)
+//   ARRIVE 2       -- overlap: permutation index + record fetch of this warp's chunk of t+1
+//   WAIT 2
+//
+// The visiting order is either an explicit permutation (parity runs against the reference) or
+// the inline Feistel permutation (feistel.cuh).
 #include "common.cuh"
 #include "feistel.cuh"
 
@@ -24,18 +31,33 @@ namespace ure {
 namespace {
 
 constexpr int kThreads = 1024;
+constexpr int KM = URE_MAX_SHARDS;
 
 struct Workspace {
   unsigned barrier;
-  unsigned pad[63];
+  unsigned pad0;
+  long long* trace;        // optional [steps][gridDim.x][6] SM-clock stamps (ure_mf_train_trace), else NULL
+  int trace_steps;
+  unsigned debug_flags;    // diagnostics only: 1 = skip gradient REDs, 2 = identity visiting order
+  unsigned pad[58];
 };
+static_assert(sizeof(Workspace) == 256, "workspace layout");
 
-// Per-CTA shard tables (static shared memory, URE_MAX_SHARDS entries): direct LDS addressing.
-struct ShardPtrs {      // 32 bytes: fetched with two LDS.128
+struct ShardPtrs {         // 32 bytes: fetched with two LDS.128
   float* P; float* Q; float* gP; float* gQ;
 };
 
-// largest s with prefix[s] <= x  (prefix[0] = 0, prefix[K] = total > x)
+// Step tables, double buffered (built for t+1 while step t is still running).
+struct StepTables {
+  int item_prefix[KM + 1];           // flattened batch positions of the active shards
+  long long row_prefix[2 * KM + 1];  // flattened float4 elements of the dense sweep
+  int epoch[KM];                     // -1: shard finished
+  int start[KM];                     // first position of the batch inside the epoch
+  float lr[KM];
+  FeistelKeys keys[KM];
+};
+
+// largest s with prefix[s] <= x  (prefix[0] = 0, prefix[nseg] = total > x)
 template <typename T>
 __device__ __forceinline__ int find_segment(const T* prefix, int nseg, T x) {
   int lo = 0, hi = nseg;
@@ -46,12 +68,29 @@ __device__ __forceinline__ int find_segment(const T* prefix, int nseg, T x) {
   return lo;
 }
 
-// Gradient work of one 32-interaction warp chunk.  Lane l fetched interaction l (u, it, r, shard s);
+// ---- split grid barrier (monotonic counter; cooperative launch guarantees co-residency)
+__device__ __forceinline__ void barrier_arrive(unsigned* counter) {
+  __syncthreads();                        // every warp of the CTA has issued its writes / REDs
+  if (threadIdx.x == 0) {
+    __threadfence();                      // cumulative: orders the CTA's prior writes before the arrival
+    atomicAdd(counter, 1u);
+  }
+}
+__device__ __forceinline__ void barrier_wait(unsigned* counter, unsigned target) {
+  if (threadIdx.x == 0) {
+    while (*reinterpret_cast<volatile unsigned*>(counter) < target) {
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// Gradient work of one 32-interaction warp chunk.  Lane l fetched interaction l (u, it, r, shard s or -1);
 // a group of G = D/4 lanes processes its G interactions SUB at a time (2*SUB 16-byte gathers in flight).
 // UNIFORM: the whole chunk lies in shard tables `tp`; otherwise each interaction looks its shard up.
 template <int D, bool UNIFORM>
 __device__ __forceinline__ float chunk_gradients(int u, int it, float r, int s, const ShardPtrs& tp,
-                                                  const ShardPtrs* s_ptr, int gl) {
+                                                  const ShardPtrs* s_ptr, int gl, unsigned dbg) {
   constexpr int G = D / 4;
   constexpr int SUB = (G < 4) ? G : 4;
   float my_e = 0.f;
@@ -85,7 +124,7 @@ __device__ __forceinline__ float chunk_gradients(int u, int it, float r, int s, 
       for (int o = G / 2; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o, G);
       const float e = dot - rq[q];
       if (gl == q0 + q) my_e = e;
-      if (sq[q] >= 0) {
+      if (sq[q] >= 0 && !(dbg & 1u)) {
         float* gPb = UNIFORM ? tp.gP : s_ptr[sq[q]].gP;
         float* gQb = UNIFORM ? tp.gQ : s_ptr[sq[q]].gQ;
         const float ge = 2.f * e;
@@ -102,20 +141,24 @@ __global__ void __launch_bounds__(kThreads, 1)
 mf_train_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams_t hp, int epochs,
                 long long step_begin, long long step_end, Workspace* ws) {
   constexpr int G = D / 4;                 // lanes per interaction
-  constexpr int KM = URE_MAX_SHARDS;
+  // ---- per-CTA shard tables (static shared memory): constant for the whole launch
   __shared__ ShardPtrs s_ptr[KM];
   __shared__ const ure_inter_t* s_inter[KM];
   __shared__ const int32_t* s_perm[KM];
   __shared__ float* s_buf[2 * KM];         // bufP, bufQ
   __shared__ double* s_sse[KM];
-  __shared__ long long s_row_prefix[2 * KM + 1];
   __shared__ int s_n[KM], s_nuser[KM], s_nitem[KM], s_spe[KM], s_shard_id[KM];
   __shared__ uint32_t s_seed[KM];
-  __shared__ int s_item_prefix[KM + 1], s_epoch[KM], s_start[KM];
-  __shared__ float s_lr[KM], s_sse_acc[KM];
-  __shared__ Feistel s_fe[KM];
+  __shared__ FeistelDomain s_dom[KM];
+  // ---- per-shard schedule cursor (advanced by the table builder) and the double-buffered step tables
+  __shared__ int s_cur_epoch[KM], s_cur_batch[KM];
+  extern __shared__ __align__(16) unsigned char dyn_smem[];     // StepTables[2] (static limit is 48 KB)
+  StepTables* const s_tab = reinterpret_cast<StepTables*>(dyn_smem);
+  __shared__ float s_sse_acc[KM];
+
   const int tid = threadIdx.x;
   const int lane = tid & 31;
+  const int warp = tid >> 5;
   const int gl = lane % G;
   for (int s = tid; s < K; s += kThreads) {
     const ure_mf_shard_t sh = shards[s];
@@ -124,87 +167,121 @@ mf_train_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
     s_buf[2 * s] = sh.bufP; s_buf[2 * s + 1] = sh.bufQ;
     s_sse[s] = sh.sse;
     s_n[s] = sh.n; s_nuser[s] = sh.n_user; s_nitem[s] = sh.n_item;
-    s_spe[s] = (sh.n + hp.batch - 1) / hp.batch;
+    const int spe = (sh.n + hp.batch - 1) / hp.batch;
+    s_spe[s] = spe;
     s_seed[s] = sh.perm_seed; s_shard_id[s] = sh.shard_id;
+    s_dom[s].init((uint32_t)sh.n);
+    s_cur_epoch[s] = spe > 0 ? (int)(step_begin / spe) : epochs;     // the only divisions of the launch
+    s_cur_batch[s] = spe > 0 ? (int)(step_begin % spe) : 0;
     s_sse_acc[s] = 0.f;
   }
-  unsigned bar_target = 0;
+  const unsigned dbg = ws->debug_flags;
+  long long* const trace = ws->trace;
+  const int trace_steps = ws->trace_steps;
   const long long n_threads = (long long)gridDim.x * kThreads;
   const long long gtid = (long long)blockIdx.x * kThreads + tid;
   const int n_warps = (int)(n_threads >> 5);
   const int gwarp = (int)(gtid >> 5);
+  unsigned bar_target = 0;
   __syncthreads();
 
-  for (long long t = step_begin; t < step_end; ++t) {
-    // ---------------------------------------------------------------- per-step tables
-    for (int s = tid; s < K; s += kThreads) {
-      const int spe = s_spe[s];
-      const bool active = spe > 0 && t < (long long)spe * epochs;
-      int ep = 0, cnt = 0, st = 0;
-      if (active) {
-        ep = (int)(t / spe);
-        st = (int)(t % spe) * hp.batch;
-        cnt = min(hp.batch, s_n[s] - st);
-        s_fe[s].init((uint32_t)s_n[s], perm_key(s_seed[s], (uint32_t)s_shard_id[s], (uint32_t)ep));
-        double lr = (double)hp.lr0;
-        for (int q = ep / hp.lr_step; q > 0; --q) lr *= (double)hp.lr_decay;
-        s_lr[s] = (float)lr;
+  // Step tables for the step the cursors point at, then advance the cursors.  Executed by ONE warp
+  // (lanes = shards, 32 at a time, prefix carried): no block-wide synchronisation inside.
+  auto build_tables = [&](StepTables& tb) {
+    int carry = 0;
+    long long carry2 = 0;
+    for (int base = 0; base < K; base += 32) {
+      const int s = base + lane;
+      int cnt = 0, ep = -1, st = 0;
+      long long rows_u = 0, rows_i = 0;
+      if (s < K) {
+        const int spe = s_spe[s];
+        ep = s_cur_epoch[s];
+        const int bi = s_cur_batch[s];
+        if (spe > 0 && ep < epochs) {
+          st = bi * hp.batch;
+          cnt = min(hp.batch, s_n[s] - st);
+          rows_u = (long long)s_nuser[s] * G;
+          rows_i = (long long)s_nitem[s] * G;
+          double lr = (double)hp.lr0;
+          for (int q = ep / hp.lr_step; q > 0; --q) lr *= (double)hp.lr_decay;
+          tb.lr[s] = (float)lr;
+          tb.keys[s].init(perm_key(s_seed[s], (uint32_t)s_shard_id[s], (uint32_t)ep));
+          if (bi + 1 == spe) { s_cur_epoch[s] = ep + 1; s_cur_batch[s] = 0; }
+          else s_cur_batch[s] = bi + 1;
+        } else {
+          ep = -1;
+        }
+        tb.epoch[s] = ep;
+        tb.start[s] = st;
       }
-      s_epoch[s] = active ? ep : -1;
-      s_start[s] = st;
-      s_item_prefix[s + 1] = cnt;                               // counts, scanned below
-      s_row_prefix[2 * s + 1] = active ? (long long)s_nuser[s] * G : 0;
-      s_row_prefix[2 * s + 2] = active ? (long long)s_nitem[s] * G : 0;
-    }
-    __syncthreads();
-    if (tid < 32) {                                              // warp 0: inclusive scans
-      int carry = 0;
-      for (int base = 0; base < K; base += 32) {
-        int idx = base + lane;
-        int v = idx < K ? s_item_prefix[idx + 1] : 0;
+      int v = cnt;
+      long long v2 = rows_u + rows_i;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { int u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
-        if (idx < K) s_item_prefix[idx + 1] = v + carry;
-        carry += __shfl_sync(0xffffffffu, v, 31);
+      for (int o = 1; o < 32; o <<= 1) {
+        const int a = __shfl_up_sync(0xffffffffu, v, o);
+        const long long b = __shfl_up_sync(0xffffffffu, v2, o);
+        if (lane >= o) { v += a; v2 += b; }
       }
-      long long carry2 = 0;
-      for (int base = 0; base < 2 * K; base += 32) {
-        int idx = base + lane;
-        long long v = idx < 2 * K ? s_row_prefix[idx + 1] : 0;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { long long u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
-        if (idx < 2 * K) s_row_prefix[idx + 1] = v + carry2;
-        carry2 += __shfl_sync(0xffffffffu, v, 31);
+      if (s < K) {
+        tb.item_prefix[s + 1] = v + carry;
+        tb.row_prefix[2 * s + 1] = v2 + carry2 - rows_i;
+        tb.row_prefix[2 * s + 2] = v2 + carry2;
       }
-      if (lane == 0) { s_item_prefix[0] = 0; s_row_prefix[0] = 0; }
+      carry += __shfl_sync(0xffffffffu, v, 31);
+      carry2 += __shfl_sync(0xffffffffu, v2, 31);
     }
-    __syncthreads();
+    if (lane == 0) { tb.item_prefix[0] = 0; tb.row_prefix[0] = 0; }
+  };
 
-    // ---------------------------------------------------------------- phase A: gradients
-    const int total = s_item_prefix[K];
-    float acc = 0.f;          // sum of e^2 of this lane's own interactions, all in shard acc_s
+  // Visiting-order index + record of this lane's interaction in warp chunk `wc` of the step in `tb`.
+  auto fetch = [&](const StepTables& tb, int wc, int& s, int& u, int& it, float& r) {
+    const int item = wc * 32 + lane;
+    s = -1; u = 0; it = 0; r = 0.f;
+    if (item < tb.item_prefix[K]) {
+      s = find_segment(tb.item_prefix, K, item);
+      const int j = tb.start[s] + (item - tb.item_prefix[s]);
+      const int32_t* pm = s_perm[s];
+      uint32_t idx;
+      if (pm) idx = (uint32_t)__ldg(pm + (long long)tb.epoch[s] * s_n[s] + j);
+      else if (dbg & 2u) idx = (uint32_t)j;
+      else idx = feistel(s_dom[s], tb.keys[s], (uint32_t)j);
+      const int4 rec = ld_stream_i4(s_inter[s] + idx);
+      u = rec.x; it = rec.y; r = __int_as_float(rec.z);
+    }
+  };
+
+#define URE_STAMP(PH)                                                                                  \
+  if (trace && tid == 0 && (t - step_begin) < trace_steps)                                             \
+    trace[((t - step_begin) * gridDim.x + blockIdx.x) * 6 + (PH)] = clock64();
+
+  // ---- prologue: tables and first-chunk records of the first step
+  if (warp == 0) build_tables(s_tab[0]);
+  __syncthreads();
+  int ps, pu_, pi_;
+  float pr_;
+  fetch(s_tab[0], gwarp, ps, pu_, pi_, pr_);
+
+  int cur = 0;
+  for (long long t = step_begin; t < step_end; ++t, cur ^= 1) {
+    const StepTables& tb = s_tab[cur];
+    URE_STAMP(0)
+    // ---------------------------------------------------------------- gradients
+    const int total = tb.item_prefix[K];
+    float acc = 0.f;          // sum of e^2 of the chunks this warp processed, all in shard acc_s
     int acc_s = -1;
     for (int wc = gwarp; wc * 32 < total; wc += n_warps) {
-      const int item = wc * 32 + lane;
-      const bool valid = item < total;
-      int s = -1;
-      int u = 0, it = 0;
-      float r = 0.f;
-      if (valid) {
-        s = find_segment(s_item_prefix, K, item);
-        const int j = s_start[s] + (item - s_item_prefix[s]);
-        const int32_t* pm = s_perm[s];
-        const uint32_t idx = pm ? (uint32_t)__ldg(pm + (long long)s_epoch[s] * s_n[s] + j)
-                                : s_fe[s]((uint32_t)j);
-        const int4 rec = ld_stream_i4(s_inter[s] + idx);
-        u = rec.x; it = rec.y; r = __int_as_float(rec.z);
-      }
+      int s, u, it;
+      float r;
+      if (wc == gwarp) { s = ps; u = pu_; it = pi_; r = pr_; }      // prefetched during WAIT 2 of step t-1
+      else fetch(tb, wc, s, u, it, r);
+      const bool valid = s >= 0;
       // the common case: the whole 32-interaction chunk lies in one shard -> table pointers once per warp
       const int s0 = __shfl_sync(0xffffffffu, s, 0);
       const bool uniform = __all_sync(0xffffffffu, s == s0 || !valid);
       const ShardPtrs tp = s_ptr[s0];
-      const float my_e = uniform ? chunk_gradients<D, true>(u, it, r, s, tp, s_ptr, gl)
-                                 : chunk_gradients<D, false>(u, it, r, s, tp, s_ptr, gl);
+      const float my_e = uniform ? chunk_gradients<D, true>(u, it, r, s, tp, s_ptr, gl, dbg)
+                                 : chunk_gradients<D, false>(u, it, r, s, tp, s_ptr, gl, dbg);
       // loss: warp-reduce when the chunk is single-shard (one shared atomic per warp, not per lane)
       const float e2 = valid ? my_e * my_e : 0.f;
       if (uniform) {
@@ -220,29 +297,54 @@ mf_train_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
       }
     }
     if (acc_s >= 0 && lane == 0) atomicAdd(&s_sse_acc[acc_s], acc);
-    __syncthreads();
+    URE_STAMP(1)
+    barrier_arrive(&ws->barrier);                   // ---------------- ARRIVE 1
+    bar_target += gridDim.x;
+    // overlap: publish the loss, preload the sweep operands that the gradient phase did not touch,
+    // build the tables of step t+1
     for (int s = tid; s < K; s += kThreads) {
       const float v = s_sse_acc[s];
       if (v != 0.f) {
-        atomicAdd(s_sse[s] + s_epoch[s], (double)v);
+        atomicAdd(s_sse[s] + tb.epoch[s], (double)v);
         s_sse_acc[s] = 0.f;
       }
     }
-    grid_barrier(&ws->barrier, bar_target);
+    const long long total4 = tb.row_prefix[2 * K];
+    int seg0 = 0;
+    size_t off0 = 0;
+    float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f), b0 = w0;
+    if (gtid < total4) {
+      seg0 = find_segment(tb.row_prefix, 2 * K, gtid);
+      off0 = (size_t)(gtid - tb.row_prefix[seg0]) * 4;
+      const ShardPtrs tp = s_ptr[seg0 >> 1];
+      w0 = ld_cg_f4(((seg0 & 1) ? tp.Q : tp.P) + off0);
+      b0 = ld_cg_f4(s_buf[seg0] + off0);
+    }
+    if (warp == 1 && t + 1 < step_end) build_tables(s_tab[cur ^ 1]);
+    URE_STAMP(2)
+    barrier_wait(&ws->barrier, bar_target);         // ---------------- WAIT 1
+    URE_STAMP(3)
 
-    // ---------------------------------------------------------------- phase B: dense SGD sweep
-    const long long total4 = s_row_prefix[2 * K];
+    // ---------------------------------------------------------------- dense SGD sweep
     const float wd = hp.weight_decay, mu = hp.momentum;
     for (long long x = gtid; x < total4; x += n_threads) {
-      const int seg = find_segment(s_row_prefix, 2 * K, x);
-      const size_t off = (size_t)(x - s_row_prefix[seg]) * 4;
-      const int s = seg >> 1;
-      const ShardPtrs tp = s_ptr[s];
+      int seg;
+      size_t off;
+      float4 w, b;
+      if (x == gtid) { seg = seg0; off = off0; w = w0; b = b0; }
+      else {
+        seg = find_segment(tb.row_prefix, 2 * K, x);
+        off = (size_t)(x - tb.row_prefix[seg]) * 4;
+        const ShardPtrs tq = s_ptr[seg >> 1];
+        w = ld_cg_f4(((seg & 1) ? tq.Q : tq.P) + off);
+        b = ld_cg_f4(s_buf[seg] + off);
+      }
+      const ShardPtrs tp = s_ptr[seg >> 1];
       float* W = (seg & 1) ? tp.Q : tp.P;
       float* Gr = (seg & 1) ? tp.gQ : tp.gP;
       float* Bf = s_buf[seg];
-      const float nlr = -s_lr[s];
-      float4 g = ld_cg_f4(Gr + off), w = ld_cg_f4(W + off), b = ld_cg_f4(Bf + off);
+      const float nlr = -tb.lr[seg >> 1];
+      float4 g = ld_cg_f4(Gr + off);
       // torch SGD: d_p = g + wd*w (fma); buf = buf*mu + d_p; w = w + (-lr)*buf (fma)
       g.x = fmaf(wd, w.x, g.x); g.y = fmaf(wd, w.y, g.y); g.z = fmaf(wd, w.z, g.z); g.w = fmaf(wd, w.w, g.w);
       b.x = __fadd_rn(__fmul_rn(b.x, mu), g.x); b.y = __fadd_rn(__fmul_rn(b.y, mu), g.y);
@@ -252,18 +354,27 @@ mf_train_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
       st_cg_f4(Bf + off, b);
       st_cg_f4(Gr + off, make_float4(0.f, 0.f, 0.f, 0.f));
     }
-    grid_barrier(&ws->barrier, bar_target);
+    URE_STAMP(4)
+    barrier_arrive(&ws->barrier);                   // ---------------- ARRIVE 2
+    bar_target += gridDim.x;
+    // overlap: visiting-order index + record of this warp's first chunk of step t+1 (static data);
+    // the tables of t+1 were written by warp 1 before WAIT 1's __syncthreads
+    if (t + 1 < step_end) fetch(s_tab[cur ^ 1], gwarp, ps, pu_, pi_, pr_);
+    barrier_wait(&ws->barrier, bar_target);         // ---------------- WAIT 2
+    URE_STAMP(5)
   }
+#undef URE_STAMP
 }
 
 template <int D>
 int launch(const ure_mf_shard_t* d_shards, int K, const ure_mf_hparams_t& hp, int epochs, long long s0,
            long long s1, Workspace* ws, cudaStream_t st) {
   auto kern = mf_train_kernel<D>;
-  const size_t smem = 0;
+  const size_t smem = 2 * sizeof(StepTables);
+  URE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0;
   URE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem));
-  URE_REQUIRE(occ >= 1, URE_ECOOP, "mf_train_kernel<%d> cannot be resident (smem %zu)", D, smem);
+  URE_REQUIRE(occ >= 1, URE_ECOOP, "mf_train_kernel<%d> cannot be resident", D);
   const int grid = num_sms();
   URE_CUDA(cudaMemsetAsync(&ws->barrier, 0, sizeof(unsigned), st));
   void* args[] = {(void*)&d_shards, (void*)&K, (void*)&hp, (void*)&epochs, (void*)&s0, (void*)&s1, (void*)&ws};
@@ -300,6 +411,33 @@ extern "C" int ure_mf_train(const ure_mf_shard_t* d_shards, int n_shards, const 
       return URE_EUNSUPPORTED;
   }
 }
+
+// Diagnostics: the next ure_mf_train calls on this workspace record, for their first `steps` steps, six
+// SM-clock stamps per CTA (step start, gradients issued, arrive-1 overlap done, barrier 1 passed, sweep
+// issued, barrier 2 passed) into d_trace [steps][grid][6] int64.  d_trace = NULL switches tracing off.
+extern "C" int ure_mf_train_trace(void* d_workspace, int64_t* d_trace, int steps, void* stream) {
+  using namespace ure;
+  URE_REQUIRE(d_workspace, URE_EINVAL, "ure_mf_train_trace: null workspace");
+  auto* ws = static_cast<Workspace*>(d_workspace);
+  long long* p = reinterpret_cast<long long*>(d_trace);
+  URE_CUDA(cudaMemcpyAsync(&ws->trace, &p, sizeof(p), cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream)));
+  URE_CUDA(cudaMemcpyAsync(&ws->trace_steps, &steps, sizeof(int), cudaMemcpyHostToDevice,
+                           static_cast<cudaStream_t>(stream)));
+  URE_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+extern "C" int ure_mf_debug_flags(void* d_workspace, unsigned flags, void* stream) {
+  using namespace ure;
+  URE_REQUIRE(d_workspace, URE_EINVAL, "ure_mf_debug_flags: null workspace");
+  auto* ws = static_cast<Workspace*>(d_workspace);
+  URE_CUDA(cudaMemcpyAsync(&ws->debug_flags, &flags, sizeof(flags), cudaMemcpyHostToDevice,
+                           static_cast<cudaStream_t>(stream)));
+  URE_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+extern "C" int ure_mf_grid_size(void) { return ure::num_sms(); }
 
 extern "C" int ure_mf_flush(const ure_mf_shard_t*, int, const ure_mf_hparams_t* h_hp, int, int64_t, void*) {
   if (h_hp && h_hp->lazy == 0) return 0;   // dense mode: every row is always current

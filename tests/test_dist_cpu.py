@@ -1,0 +1,126 @@
+"""CPU, world_size 2 over gloo: the host-side logic of the multi-GPU decomposition (ultrare_b200/dist.py,
+SURVEY.md §8e).  The device kernels are stood in for by the oracle's NumPy arithmetic -- what is under test
+is the placement, the partial-sum / all-reduce structure and that it reproduces the single-process result."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, fn, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from ultrare_b200 import dist as udist
+    d = udist.init_from_env(backend="gloo")
+    try:
+        ret[rank] = fn(d)
+    finally:
+        d.td.destroy_process_group()
+
+
+def _run(fn, world=2):
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, fn, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    return [ret[r] for r in range(world)]
+
+
+def _placement(d):
+    mine = d.my_shards(range(5))
+    lo, hi = d.row_block(6041)
+    return dict(rank=d.rank, world=d.world, mine=mine, block=(lo, hi), total=d.sum_int(hi - lo),
+                mx=d.max_float(float(d.rank) + 0.5))
+
+
+def test_placement_and_scalar_collectives():
+    out = _run(_placement)
+    assert [o["mine"] for o in out] == [[0, 2, 4], [1, 3]]
+    assert out[0]["block"] == (0, 3021) and out[1]["block"] == (3021, 6041)
+    assert all(o["total"] == 6041 and o["mx"] == 1.5 and o["world"] == 2 for o in out)
+
+
+def _sinkhorn_sharded(d):
+    """Row-sharded Sinkhorn: local column sums + all-reduce of k marginals per iteration (§8e)."""
+    from oracle import ot as oot
+    rng = np.random.default_rng(0)
+    n, k = 2001, 6
+    M = rng.random((n, k)) * 20
+    sched = [(4.0, 15), (1.0, 25)]
+    lo, hi = d.row_block(n)
+    Ml = M[lo:hi]
+    g = np.zeros(k)
+    for eps, iters in sched:
+        for _ in range(iters):
+            T = (g[None, :] - Ml) / eps
+            mx = T.max(1, keepdims=True)
+            lse = mx[:, 0] + np.log(np.exp(T - mx).sum(1))
+            col = torch.from_numpy(np.exp(T - lse[:, None] - np.log(n)).sum(0))
+            d.all_reduce(col)
+            g = g + eps * (-np.log(k) - np.log(col.numpy()))
+    _, _, g_ref, _ = oot.sinkhorn_log(M, sched)
+    # labels + centroid sums: local assignment, all-reduce of [k,d] sums and [k] counts
+    lab = np.argmax(g[None, :] - Ml, axis=1)
+    cnt = torch.from_numpy(np.bincount(lab, minlength=k).astype(np.int64))
+    d.all_reduce(cnt)
+    lab_ref = np.argmax(g_ref[None, :] - M, axis=1)
+    return dict(err=float(np.abs(g - g_ref).max()), cnt=cnt.numpy().tolist(),
+                cnt_ref=np.bincount(lab_ref, minlength=k).tolist())
+
+
+def test_row_sharded_sinkhorn_equals_single_process():
+    out = _run(_sinkhorn_sharded)
+    for o in out:
+        assert o["err"] < 1e-9 and o["cnt"] == o["cnt_ref"]
+
+
+def _ensemble_sharded(d):
+    """Shard s on rank s mod world: partial ensemble sums all-reduced == single-process ensemble; the merge of
+    owner rows as a sum of zero-filled contributions is bit-exact (rows are disjoint)."""
+    from oracle import evalm, sisa as osisa
+    rng = np.random.default_rng(1)
+    K, U, I, dd, n = 5, 60, 40, 16, 500
+    groups = osisa.uniform_groups(U, K)
+    Ps = [rng.standard_normal((U, dd), dtype=np.float32) for _ in range(K)]
+    Qs = [rng.standard_normal((I, dd), dtype=np.float32) for _ in range(K)]
+    u, i = rng.integers(0, U, n), rng.integers(0, I, n)
+    merged_ref = osisa.merge_learn(Ps, groups)
+    contrib = np.zeros_like(merged_ref)
+    for s in d.my_shards(range(K)):
+        g = np.asarray(groups[s])
+        contrib[g] = Ps[s][g]
+    t = torch.from_numpy(contrib)
+    d.all_reduce(t)
+    merged = t.numpy()
+    part = np.zeros(n, dtype=np.float32)
+    for s in d.my_shards(range(K)):
+        part += evalm.mf_score(merged, Qs[s], u, i)
+    tp = torch.from_numpy(part)
+    d.all_reduce(tp)
+    score = tp.numpy() / np.float32(K)
+    ref = evalm.ensemble_score([merged_ref] * K, Qs, u, i)
+    return dict(merge_exact=bool(np.array_equal(merged, merged_ref)), err=float(np.abs(score - ref).max()))
+
+
+def test_sharded_merge_and_ensemble_equal_single_process():
+    out = _run(_ensemble_sharded)
+    for o in out:
+        assert o["merge_exact"] and o["err"] < 1e-5

@@ -32,20 +32,62 @@ def _need_cuda(*ts):
 
 
 # ------------------------------------------------------------------------------ interactions
+_PACK_THREADS = 4
+_POOL = []
+
+
+def _pack_pool():
+    if not _POOL:
+        from concurrent.futures import ThreadPoolExecutor
+        _POOL.append(ThreadPoolExecutor(max_workers=_PACK_THREADS))
+    return _POOL[0]
+
+
+_PINNED = {}   # rows -> list of pinned int32 [rows,4] staging buffers (reused: cudaHostAlloc is slow)
+
+
+def _staging(n: int) -> torch.Tensor:
+    cap = 1 << max(10, int(n - 1).bit_length())
+    pool = _PINNED.setdefault(cap, [])
+    for buf, ev in pool:
+        if ev is None or ev.query():
+            pool.remove((buf, ev))
+            return buf
+    return torch.empty((cap, 4), dtype=torch.int32, pin_memory=True)
+
+
 def pack_interactions(users, items, ratings, device) -> torch.Tensor:
     """(uid, iid, rating) columns -> int32 [n,4] ure_inter_t records on `device`.
 
-    rating is cast the way RatingData does (reference read.py:113,124): float32(float64).
+    rating is cast the way RatingData does (reference read.py:113,124): float32(float64).  On a CUDA
+    device the records are written straight into a pinned staging buffer and copied asynchronously.
     """
     n = len(users)
-    rec = np.zeros((n, 4), dtype=np.int32)
-    rec[:, 0] = np.asarray(users).astype(np.int64)
-    rec[:, 1] = np.asarray(items).astype(np.int64)
-    rec[:, 2] = np.asarray(ratings, dtype=np.float64).astype(np.float32).view(np.int32)
-    t = torch.from_numpy(rec)
-    if torch.device(device).type == "cuda":
-        t = t.pin_memory().to(device, non_blocking=True)
-    return t
+    cuda = torch.device(device).type == "cuda"
+    stage = _staging(n) if cuda and n > 0 else torch.empty((max(n, 1), 4), dtype=torch.int32)
+    rec = stage.numpy()[:n]
+    users, items, ratings = np.asarray(users), np.asarray(items), np.asarray(ratings, dtype=np.float64)
+
+    def fill(lo, hi):                                   # NumPy converts int64 / float64 -> int32 on assignment
+        rec[lo:hi, 0] = users[lo:hi]
+        rec[lo:hi, 1] = items[lo:hi]
+        rec[lo:hi, 2].view(np.float32)[...] = ratings[lo:hi]
+        rec[lo:hi, 3] = 0
+
+    if n >= (1 << 17):                                  # the casts release the GIL: pack in parallel
+        step = -(-n // _PACK_THREADS)
+        list(_pack_pool().map(lambda lo: fill(lo, min(n, lo + step)), range(0, n, step)))
+    else:
+        fill(0, n)
+    if not cuda:
+        return stage[:n].clone()
+    out = torch.empty((n, 4), dtype=torch.int32, device=device)
+    if n > 0:
+        out.copy_(stage[:n], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        _PINNED[stage.shape[0]].append((stage, ev))      # reusable once the copy has completed
+    return out
 
 
 def pointer_table(tensors: Sequence[torch.Tensor], device) -> torch.Tensor:
@@ -57,15 +99,19 @@ class ShardState:
     """Device state of one shard model: what Scratch.train builds (scratch.py:59,65-69)."""
 
     def __init__(self, inter: torch.Tensor, P: torch.Tensor, Q: torch.Tensor, epochs: int,
-                 shard_id: int = 0, perm_seed: int = 42, perm: Optional[torch.Tensor] = None):
+                 shard_id: int = 0, perm_seed: int = 42, perm: Optional[torch.Tensor] = None, scratch=None):
+        """scratch: optional (bufP, bufQ, gP, gQ, sse) zero-filled views of a batch allocation."""
         _need_cuda(inter, P, Q, perm)
         assert inter.dtype == torch.int32 and inter.dim() == 2 and inter.shape[1] == 4
         assert P.dtype == torch.float32 and Q.dtype == torch.float32 and P.shape[1] == Q.shape[1]
         self.inter, self.P, self.Q = inter.contiguous(), P, Q
         assert P.is_contiguous() and Q.is_contiguous()
-        self.bufP, self.bufQ = torch.zeros_like(P), torch.zeros_like(Q)
-        self.gP, self.gQ = torch.zeros_like(P), torch.zeros_like(Q)
-        self.sse = torch.zeros(max(1, epochs), dtype=torch.float64, device=P.device)
+        if scratch is None:
+            self.bufP, self.bufQ = torch.zeros_like(P), torch.zeros_like(Q)
+            self.gP, self.gQ = torch.zeros_like(P), torch.zeros_like(Q)
+            self.sse = torch.zeros(max(1, epochs), dtype=torch.float64, device=P.device)
+        else:
+            self.bufP, self.bufQ, self.gP, self.gQ, self.sse = scratch
         self.perm = None
         if perm is not None:
             assert perm.dtype == torch.int32 and perm.shape == (epochs, inter.shape[0])
@@ -122,8 +168,26 @@ class ShardBatch:
         return sum(s.n for s in self.shards) * self.epochs
 
     def train_losses(self) -> List[np.ndarray]:
-        """Per shard: sqrt(sse_epoch / n) for every epoch (utils.py:108).  Synchronises."""
-        return [np.sqrt(s.sse.cpu().numpy() / max(1, s.n)) for s in self.shards]
+        """Per shard: sqrt(sse_epoch / n) for every epoch (utils.py:108).  Synchronises (one D2H)."""
+        sse = torch.stack([s.sse for s in self.shards]).cpu().numpy()
+        return [np.sqrt(sse[j] / max(1, s.n)) for j, s in enumerate(self.shards)]
+
+
+def alloc_shard_batch(rows_P: Sequence[int], n_item: int, d: int, epochs: int, device, generator=None, std=1.0):
+    """One allocation for all shard models of a launch: N(0,std) tables (reference utils.py:38-40) plus the
+    zero-filled momentum / gradient / loss scratch.  Returns per-shard (P, Q, scratch) views."""
+    K = len(rows_P)
+    tot_p = int(sum(rows_P))
+    W = torch.empty((tot_p + K * n_item, d), dtype=torch.float32, device=device).normal_(0.0, std, generator=generator)
+    Z = torch.zeros((2, tot_p + K * n_item, d), dtype=torch.float32, device=device)
+    sse = torch.zeros((K, max(1, epochs)), dtype=torch.float64, device=device)
+    out, o = [], 0
+    for j, r in enumerate(rows_P):
+        qo = tot_p + j * n_item
+        out.append((W[o:o + r], W[qo:qo + n_item],
+                    (Z[0, o:o + r], Z[0, qo:qo + n_item], Z[1, o:o + r], Z[1, qo:qo + n_item], sse[j])))
+        o += r
+    return out
 
 
 # ------------------------------------------------------------------------------ evaluation

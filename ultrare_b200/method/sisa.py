@@ -137,16 +137,28 @@ class Sisa(Scratch):
         t0 = time.time()
         models, states, snaps, losses = {}, [], {}, []
         if mine:
-            for i in mine:
+            # default init: ONE allocation + one normal_() for every shard of the launch (device RNG);
+            # an overridden _new_model (parity runs inject weights) or host-seeded init goes shard by shard
+            batched = self.init_on_device and type(self)._new_model is Scratch._new_model
+            if batched:
+                from .scratch import model_generator
+                from .utils import MF
+                rows = [len(self.group_index[i]) if compact else self.n_user for i in mine]
+                views = kn.alloc_shard_batch(rows, self.n_item, self.k, E, self.device,
+                                             model_generator(self.seed, mine[0] + 1, self.device))
+            for j, i in enumerate(mine):
                 ld = train_dlist[i]
-                if compact:
-                    models[i] = self._new_model(i + 1, user_rows=self._rows(i))
-                    rec = ld.dataset.records_mapped(self.device, self._row_of_np, 'sisa_local')
+                rec = (ld.dataset.records_mapped(self.device, self._row_of_np, 'sisa_local') if compact
+                       else ld.dataset.records(self.device))
+                scratch = None
+                if batched:
+                    P, Q, scratch = views[j]
+                    models[i] = MF.wrap(P, Q)
                 else:
-                    models[i] = self._new_model(i + 1)
-                    rec = ld.dataset.records(self.device)
+                    models[i] = self._new_model(i + 1, user_rows=self._rows(i)) if compact else self._new_model(i + 1)
                 states.append(kn.ShardState(rec, models[i].user_mat.weight.data, models[i].item_mat.weight.data, E,
-                                            shard_id=i + 1, perm_seed=self.seed, perm=ld.explicit_perm(self.device, E)))
+                                            shard_id=i + 1, perm_seed=self.seed, perm=ld.explicit_perm(self.device, E),
+                                            scratch=scratch))
             batch = train_dlist[mine[0]].batch_size
             sb = kn.ShardBatch(states, self.k, batch, self.lr, self.lr_decay, 50, self.lam, self.momentum)
             if mode == 'faithful':
@@ -166,7 +178,9 @@ class Sisa(Scratch):
                     for j, e in ends[boundary]:
                         snaps[(mine[j], e)] = (states[j].P.clone(), states[j].Q.clone())
             else:
+                self.timing['setup_ms'] = (time.time() - t0) * 1e3
                 sb.train()
+                self.timing['launch_ms'] = (time.time() - t0) * 1e3 - self.timing['setup_ms']
             self._last_batch = sb
             losses = sb.train_losses()                       # the one sync of the whole training
         self.timing['train_s'] = time.time() - t0
@@ -274,8 +288,10 @@ class Sisa(Scratch):
         assert len(train_dlist) == self.n_group
         assert len(test_dlist) == self.n_group
 
+        t_begin = time.perf_counter()
         flags = self.route(del_user)
         self.retrain_gid = set(int(s) for s in np.flatnonzero(flags.cpu().numpy()))
+        self.timing['route_ms'] = (time.perf_counter() - t_begin) * 1e3
         order = sorted(self.retrain_gid)
         model_before_unlearn = self.model_list[0]                               # sisa.py:84
         base = model_before_unlearn.user_mat.weight.data
@@ -289,6 +305,7 @@ class Sisa(Scratch):
             return _local(cur)
 
         new, unmerged, last_idx, compact = self._train_shards(order, train_dlist, test_dlist, test_data, verbose, prior)
+        t_m = time.perf_counter()
         merged = self._merged_from(base, unmerged, compact, flags)
         self._finish(new, unmerged, last_idx, compact, merged, test_dlist, save_dir)
         for i, m in new.items():
@@ -296,5 +313,9 @@ class Sisa(Scratch):
         shared = next(iter(new.values())).user_mat.weight if new else nn.Parameter(merged, requires_grad=False)
         for m in self.model_list:
             m.user_mat.weight = shared
+        t_t = time.perf_counter()
         self.test(test_data, verbose, save_dir)
+        self.timing['merge_ms'] = (t_t - t_m) * 1e3
+        self.timing['test_ms'] = (time.perf_counter() - t_t) * 1e3
+        self.timing['total_ms'] = (time.perf_counter() - t_begin) * 1e3
         return self.model_list

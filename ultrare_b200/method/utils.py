@@ -77,6 +77,18 @@ class MF(nn.Module):
         self.item_mat.weight.requires_grad_(False)
         return self
 
+    @classmethod
+    def wrap(cls, P, Q):
+        """Model over existing device tensors (no copy): views into a batch allocation."""
+        self = cls.__new__(cls)
+        nn.Module.__init__(self)
+        self.k = P.shape[1]
+        self.user_mat = nn.Embedding(P.shape[0], self.k, _weight=P)
+        self.item_mat = nn.Embedding(Q.shape[0], self.k, _weight=Q)
+        self.user_mat.weight.requires_grad_(False)
+        self.item_mat.weight.requires_grad_(False)
+        return self
+
     @staticmethod
     def _normal(shape, dev, generator):
         """N(0, STD) (reference utils.py:38-40).  A host generator gives device-independent values;

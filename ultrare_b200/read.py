@@ -76,14 +76,23 @@ class RatingData:
     """reference read.py:108-124: users/items int, ratings float (already / max_rating)."""
 
     def __init__(self, rating_array):
-        self.users = np.asarray(rating_array[0]).astype(int)
-        self.items = np.asarray(rating_array[1]).astype(int)
-        self.ratings = np.asarray(rating_array[2]).astype(float)
+        self._raw = rating_array              # [3, n]: uid, iid, rating / max_rating (float64, read.py:64-68)
+        self._n = int(np.shape(rating_array[0])[0])
+        self._cols = {}
         self._records = {}
         self._segments = {}
 
+    def _col(self, j, dtype):
+        if j not in self._cols:               # the reference's eager casts (read.py:111-113), done on demand
+            self._cols[j] = np.asarray(self._raw[j]).astype(dtype)
+        return self._cols[j]
+
+    users = property(lambda self: self._col(0, int))
+    items = property(lambda self: self._col(1, int))
+    ratings = property(lambda self: self._col(2, float))
+
     def __len__(self):
-        return len(self.users)
+        return self._n
 
     def __getitem__(self, idx):
         return (torch.tensor(self.users[idx], dtype=torch.long),
@@ -94,14 +103,14 @@ class RatingData:
         """int32 [n,4] ure_inter_t records resident on `device` (uploaded once)."""
         key = str(device)
         if key not in self._records:
-            self._records[key] = kn.pack_interactions(self.users, self.items, self.ratings, device)
+            self._records[key] = kn.pack_interactions(self._raw[0], self._raw[1], self._raw[2], device)
         return self._records[key]
 
     def records_mapped(self, device, row_of: np.ndarray, tag: str) -> torch.Tensor:
         """Records whose user field is row_of[user] (the row inside a compact per-shard user table)."""
         key = (str(device), tag)
         if key not in self._records:
-            self._records[key] = kn.pack_interactions(row_of[self.users], self.items, self.ratings, device)
+            self._records[key] = kn.pack_interactions(row_of[self.users], self._raw[1], self._raw[2], device)
         return self._records[key]
 
     def segments(self, device):

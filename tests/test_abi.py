@@ -1,0 +1,81 @@
+"""CPU: the C-ABI library builds for sm_100a, loads, and exports every symbol include/ultrare_b200.h declares
+(no compute calls: there is no GPU here); the product never imports the oracle."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_header_symbols_are_exported_and_bound():
+    from ultrare_b200 import _lib, build
+    path = build.build()
+    header = open(os.path.join(ROOT, "include", "ultrare_b200.h")).read()
+    declared = set(re.findall(r"\b(ure_[a-z0-9_]+)\s*\(", header))
+    handle = ctypes.CDLL(path)
+    for name in declared:
+        assert hasattr(handle, name), f"{name} declared in the header but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert handle.ure_abi_version() == 1
+    handle.ure_last_error.restype = ctypes.c_char_p
+    assert isinstance(handle.ure_last_error(), bytes)
+
+
+def test_struct_layouts_match_the_header():
+    from ultrare_b200 import _lib
+    assert ctypes.sizeof(_lib.MFShard) == 112 and ctypes.sizeof(_lib.MFHParams) == 32
+    assert _lib.MFShard.n.offset == 88 and _lib.MFShard.perm_seed.offset == 104
+
+
+def test_sass_has_blackwell_tensor_and_bulk_copy_instructions():
+    """tcgen05.mma -> UTC*MMA, tcgen05.ld -> LDTM, cp.async.bulk -> UBLKCP, red.v4.f32 -> REDG...F32x4."""
+    so = os.path.join(ROOT, "ultrare_b200", "libultrare_b200.so")
+    sass = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
+    assert re.search(r"UTC[A-Z]*MMA", sass), "no tcgen05 MMA in SASS"
+    assert "LDTM" in sass and "UBLKCP" in sass
+    assert re.search(r"RED[G]?\.E\.ADD\.F32x4", sass)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "ultrare_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), os.path.join(dp, f)
+
+
+def test_cuda_required_loudly():
+    import torch
+    if torch.cuda.is_available():
+        return
+    import pytest
+    from ultrare_b200.method.utils import MF
+    from ultrare_b200 import kernels as kn
+    with pytest.raises(RuntimeError):
+        MF(10, 10, 16)
+    with pytest.raises(RuntimeError):
+        kn.ensemble_score([torch.zeros(4, 16)], [torch.zeros(4, 16)], torch.zeros((1, 4), dtype=torch.int32))
+
+
+def test_host_read_rating_matches_oracle():
+    """ultrare_b200.read.readRating (owner-map single pass) == oracle restatement of read.py:9-70."""
+    import numpy as np
+    import pandas as pd
+    from oracle import sisa as osisa
+    from ultrare_b200.read import readRating
+    rng = np.random.default_rng(0)
+    n_user, n = 200, 5000
+    u = np.sort(rng.integers(0, n_user, n))
+    i = rng.integers(0, 300, n)
+    r = rng.integers(1, 6, n).astype(float)
+    groups = osisa.uniform_groups(n_user, 4)
+    dels = rng.choice(n_user, 15, replace=False)
+    for sort in ("a", "r"):
+        got, gidx = readRating(pd.DataFrame({0: u, 1: i, 2: r}), n_user, 5, list(dels), [], 4, groups, sort)
+        ref, ridx = osisa.read_rating(u, i, r, n_user, 5, dels, 4, groups, sort)
+        assert [list(a) for a in gidx] == [list(a) for a in ridx]
+        for a, b in zip(got, ref):
+            assert a.shape == b.shape and np.array_equal(a, b)

@@ -96,7 +96,8 @@ int ure_mf_train(const ure_mf_shard_t* d_shards, int n_shards, const ure_mf_hpar
  * the following ure_mf_train calls into d_trace [steps][ure_mf_grid_size()][6] int64; NULL = off. */
 int ure_mf_train_trace(void* d_workspace, int64_t* d_trace, int steps, void* stream);
 int ure_mf_grid_size(void);
-/* Diagnostics: bit 0 skips the gradient scatter, bit 1 uses the identity visiting order (timing experiments). */
+/* Diagnostics: bit 0 skips the gradient scatter, bit 1 uses the identity visiting order, bit 2 runs the
+ * shards as two interleaved pipelines (timing experiments only). */
 int ure_mf_debug_flags(void* d_workspace, unsigned flags, void* stream);
 
 /* Lazy mode: bring every row of every shard up to date (end of training / before export). */

@@ -72,15 +72,24 @@ def run_trace(flags, label):
     _lib.check(L.ure_mf_debug_flags(C.c_void_p(sb.ws.data_ptr()), 0, None))
     tr = trace.cpu().numpy().astype(np.float64)[5:]          # skip cold steps
     d = np.diff(tr, axis=2)                                   # [steps, grid, 5]
-    names = ["gradients", "overlap1", "wait1", "sweep", "arr2+fetch+wait2"]
+    names = ["stamp0-1", "stamp1-2", "stamp2-3", "stamp3-4", "stamp4-5"]
     print("per-phase SM cycles (median over CTAs and steps / p95 / max):")
     for k, nm in enumerate(names):
         x = d[:, :, k].ravel()
         print(f"  {nm:18s} {np.median(x):8.0f} {np.percentile(x, 95):8.0f} {x.max():8.0f}")
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for s_ in shards:
+        s_.bufP.zero_(); s_.bufQ.zero_(); s_.sse.zero_()
+    sb.step = 0
+    _lib.check(L.ure_mf_debug_flags(C.c_void_p(sb.ws.data_ptr()), flags, None))
+    e0.record(); sb.train(); e1.record(); torch.cuda.synchronize()
+    _lib.check(L.ure_mf_debug_flags(C.c_void_p(sb.ws.data_ptr()), 0, None))
+    ms = e0.elapsed_time(e1)
+    print(f"  whole launch {ms:.3f} ms = {ms * 1e3 / sb.total_steps:.2f} us/step, {n_inter * 268 / ms / 1e6:.0f} GB/s algorithmic")
     step_cyc = tr[1:, :, 0] - tr[:-1, :, 0]
     print("step cycles median", np.median(step_cyc), "=> us at 1.965 GHz:", np.median(step_cyc) / 1965)
 
 import ctypes as C
 from ultrare_b200 import _lib
-for flags, label in ((0, "baseline"), (1, "no REDs"), (2, "identity order"), (3, "no REDs + identity order")):
+for flags, label in ((0, "single pipeline"), (4, "two pipelines (experimental)"), (1, "single pipeline, no REDs")):
     run_trace(flags, label)

@@ -158,12 +158,14 @@ int ure_sinkhorn_colsum(const float* d_M, int64_t n, int k, int kpad, const floa
 /* g_j += eps * (log(1/k) - log(colsum_j)); re-zeroes d_colsum. */
 int ure_sinkhorn_update_g(float* d_g, double* d_colsum, int k, float eps, void* stream);
 
-/* Whole single-GPU Sinkhorn in one persistent cooperative launch:
- * h_eps[s], h_iters[s] for s < n_stages (epsilon scaling).  d_workspace:
- * ure_sinkhorn_workspace_bytes() bytes, zero-filled. */
+/* Whole single-GPU Sinkhorn: h_eps[s], h_iters[s] for s < n_stages (epsilon scaling), starting from the
+ * potentials in d_g (zeros = cold start).  Small problems (a CTA's rows of M fit in shared memory) run as ONE
+ * persistent cooperative launch with a grid barrier per iteration and, when tol > 0, leave a stage early once
+ * max_j |colsum_j - 1/k| * k < tol; large problems run the split-phase kernels for every scheduled iteration.
+ * d_workspace: ure_sinkhorn_workspace_bytes() bytes. */
 int64_t ure_sinkhorn_workspace_bytes(void);
 int ure_sinkhorn(const float* d_M, int64_t n, int k, int kpad, float* d_g, const float* h_eps,
-                 const int32_t* h_iters, int n_stages, void* d_workspace, void* stream);
+                 const int32_t* h_iters, int n_stages, float tol, void* d_workspace, void* stream);
 
 /* Row-normalised plan for given g: P[i,j] = (1/n_total) softmax_j((g_j - M_ij)/eps), [n,k] fp32. */
 int ure_sinkhorn_plan(const float* d_M, int64_t n, int k, int kpad, const float* d_g, float eps,

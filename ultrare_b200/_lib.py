@@ -54,7 +54,7 @@ SIGNATURES = {
     "ure_sinkhorn_colsum": (C.c_int, [_p, _i64, C.c_int, C.c_int, _p, _f32, _f64, _p, _p]),
     "ure_sinkhorn_update_g": (C.c_int, [_p, _p, C.c_int, _f32, _p]),
     "ure_sinkhorn_workspace_bytes": (_i64, []),
-    "ure_sinkhorn": (C.c_int, [_p, _i64, C.c_int, C.c_int, _p, C.POINTER(_f32), C.POINTER(_i32), C.c_int, _p, _p]),
+    "ure_sinkhorn": (C.c_int, [_p, _i64, C.c_int, C.c_int, _p, C.POINTER(_f32), C.POINTER(_i32), C.c_int, _f32, _p, _p]),
     "ure_sinkhorn_plan": (C.c_int, [_p, _i64, C.c_int, C.c_int, _p, _f32, _f64, _p, _p]),
     "ure_assign_plan_f64": (C.c_int, [_p, _i64, C.c_int, _i64, _p, _p]),
     "ure_assign_plan_f32": (C.c_int, [_p, _i64, C.c_int, _i64, _p, _p]),

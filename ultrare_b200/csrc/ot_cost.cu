@@ -22,6 +22,7 @@ namespace ure {
 namespace {
 
 constexpr int kTileRows = 128;
+constexpr int kCostThreads = 512;      // 16 warps: transform + epilogue are instruction bound with fewer
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -106,7 +107,7 @@ struct CostSmemLayout {
   uint32_t raw_off, raw_stage_bytes, stages;
   uint32_t a_hi, a_lo, lbo_a;
   uint32_t b_hi, b_lo, lbo_b;
-  uint32_t xnorm, cnorm, bars, holder, total;
+  uint32_t xnorm, rowmin, cnorm, bars, holder, total;
 };
 
 __host__ __device__ inline CostSmemLayout cost_layout(int D, int NB, int stages) {
@@ -123,6 +124,7 @@ __host__ __device__ inline CostSmemLayout cost_layout(int D, int NB, int stages)
   L.b_hi = o; o += L.lbo_b * chunks;
   L.b_lo = o; o += L.lbo_b * chunks;
   L.xnorm = o; o += kTileRows * 4;
+  L.rowmin = o; o += kTileRows * 4;
   L.cnorm = o; o += NB * 4;
   L.bars = o; o += 8 * 4;       // full[2], mma
   L.holder = o; o += 16;
@@ -131,7 +133,7 @@ __host__ __device__ inline CostSmemLayout cost_layout(int D, int NB, int stages)
 }
 
 template <int D>
-__global__ void __launch_bounds__(kTileRows)
+__global__ void __launch_bounds__(kCostThreads)
 cost_tc_kernel(const float* __restrict__ X, long long n, const float* __restrict__ C, int k, int kpad, int NB,
                int stages, uint32_t tmem_cols, float* __restrict__ M, double* __restrict__ inertia) {
   constexpr int CH = D / 4;                    // 16-byte K chunks per row
@@ -142,6 +144,7 @@ cost_tc_kernel(const float* __restrict__ X, long long n, const float* __restrict
   uint64_t* mma_bar = full + 2;
   uint32_t* holder = reinterpret_cast<uint32_t*>(sm + L.holder);
   float* xnorm = reinterpret_cast<float*>(sm + L.xnorm);
+  int* rowmin = reinterpret_cast<int*>(sm + L.rowmin);     // float bits (costs are >= 0: int order == float order)
   float* cnorm = reinterpret_cast<float*>(sm + L.cnorm);
   const int col0 = blockIdx.y * NB;            // first centroid column of this CTA
 
@@ -154,7 +157,7 @@ cost_tc_kernel(const float* __restrict__ X, long long n, const float* __restrict
   if (warp == 0) tmem_alloc(holder, tmem_cols);
 
   // ---- centroid block -> B_hi / B_lo (K-major core-matrix layout) + ||c||^2
-  for (int idx = tid; idx < NB * CH; idx += kTileRows) {
+  for (int idx = tid; idx < NB * CH; idx += kCostThreads) {
     const int j = idx / CH, c = idx % CH;
     const int col = col0 + j;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -199,9 +202,9 @@ cost_tc_kernel(const float* __restrict__ X, long long n, const float* __restrict
 
     // ---- split the raw tile into hi / lo operand tiles, reduce row norms
     const float* raw = reinterpret_cast<const float*>(sm + L.raw_off + (size_t)stage * L.raw_stage_bytes);
+    if (tid < kTileRows) rowmin[tid] = 0x7f800000;          // +inf
 #pragma unroll 4
-    for (int m = 0; m < CH; ++m) {
-      const int idx = tid + m * kTileRows;
+    for (int idx = tid; idx < kTileRows * CH; idx += kCostThreads) {
       const int r = idx / CH, c = idx % CH;
       const float4 v = *reinterpret_cast<const float4*>(raw + r * D + c * 4);
       const float4 hi = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
@@ -234,13 +237,15 @@ cost_tc_kernel(const float* __restrict__ X, long long n, const float* __restrict
     mbar_wait(mma_bar, it & 1);
     tc_fence_after();
 
-    // ---- epilogue: thread = row = TMEM lane
-    const long long row = tile * kTileRows + tid;
-    const float xn = xnorm[tid];
+    // ---- epilogue: warp w reads TMEM lanes 32*(w%4).. (its row quarter) and every 4th 16-column chunk
+    const int rq = warp & 3, cg = warp >> 2;
+    const int trow = rq * 32 + lane;
+    const long long row = tile * kTileRows + trow;
+    const float xn = xnorm[trow];
     float rmin = INFINITY;
-    for (int c0 = 0; c0 < NB; c0 += 16) {
+    for (int c0 = cg * 16; c0 < NB; c0 += 16 * (kCostThreads / 128)) {
       float acc[16];
-      tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, acc);
+      tmem_ld16(tmem_base + ((uint32_t)(rq * 32) << 16) + (uint32_t)c0, acc);
       if (row < n) {
         float out[16];
 #pragma unroll
@@ -253,9 +258,11 @@ cost_tc_kernel(const float* __restrict__ X, long long n, const float* __restrict
         for (int q = 0; q < 4; ++q) dst[q] = make_float4(out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]);
       }
     }
-    if (inertia && row < n) inertia_acc += (double)rmin;
+    if (inertia && row < n && rmin < INFINITY) atomicMin(&rowmin[trow], __float_as_int(fmaxf(rmin, 0.f)));
     tc_fence_before();
     __syncthreads();              // TMEM accumulator and A tiles may be overwritten now
+    if (inertia && tid < kTileRows && tile * kTileRows + tid < n) inertia_acc += (double)__int_as_float(rowmin[tid]);
+    __syncthreads();              // rowmin is re-initialised by the next tile
   }
   if (inertia) {
     inertia_acc = warp_sum(inertia_acc);
@@ -326,7 +333,7 @@ int launch_cost_tc(const float* X, long long n, const float* C, int k, int kpad,
   auto kern = cost_tc_kernel<D>;
   URE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
   int occ = 0;
-  URE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kTileRows, L.total));
+  URE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kCostThreads, L.total));
   URE_REQUIRE(occ >= 1, URE_EUNSUPPORTED, "ure_cost_matrix: kernel cannot be resident (smem %u)", L.total);
   const int max_by_tmem = 512 / (int)tmem_cols;
   if (occ > max_by_tmem) occ = max_by_tmem;
@@ -336,7 +343,7 @@ int launch_cost_tc(const float* X, long long n, const float* C, int k, int kpad,
   if (gx < 1) gx = 1;
   if (gx > n_tiles) gx = n_tiles;
   double* fused_inertia = (col_blocks == 1) ? inertia : nullptr;
-  kern<<<dim3((unsigned)gx, (unsigned)col_blocks), kTileRows, L.total, st>>>(X, n, C, k, kpad, NB, stages, tmem_cols, M,
+  kern<<<dim3((unsigned)gx, (unsigned)col_blocks), kCostThreads, L.total, st>>>(X, n, C, k, kpad, NB, stages, tmem_cols, M,
                                                                             fused_inertia);
   URE_CUDA(cudaGetLastError());
   if (inertia && !fused_inertia) return launch_rowmin(M, n, k, kpad, inertia, st);

@@ -148,12 +148,13 @@ struct SkStages {
   float eps[kMaxStages];
   int iters[kMaxStages];
   int n;
+  float tol;   // a stage ends early once max_j |colsum_j - 1/k| * k < tol (0: always run all iterations)
 };
 struct SkWorkspace {
   unsigned barrier;
   unsigned pad[31];
   double colsum[3][256];
-  double col_err;       // max_j |colsum_j - 1/k| seen at the last iteration
+  double col_err;       // max_j |colsum_j - 1/k| * k seen at the last iteration
   long long iters_done;
 };
 
@@ -191,25 +192,23 @@ sinkhorn_kernel(const float* __restrict__ M, long long n, int k, float* __restri
         csum_sh[j] = 0.f;
       }
       grid_barrier(&ws->barrier, bar_target);
-      // every CTA applies the identical update to its private copy of g
-      double err = 0.0;
+      // every CTA applies the identical update to its private copy of g (and takes the identical
+      // early-exit decision: all read the same column sums)
+      __shared__ float err_sh;
+      if (tid == 0) err_sh = 0.f;
+      __syncthreads();
       for (int j = tid; j < k; j += blockDim.x) {
         const double c = __ldcg(cs + j);
         g_sh[j] = (float)((double)g_sh[j] + (double)eps * (logb - log(c)));
-        if (blockIdx.x == 0) {
-          ws->colsum[(it_global + 2) % 3][j] = 0.0;
-          err = fmax(err, fabs(c - 1.0 / (double)k));
-        }
-      }
-      if (blockIdx.x == 0) {                      // diagnostics only
-        __shared__ double err_sh;
-        if (tid == 0) err_sh = 0.0;
-        __syncthreads();
-        if (err > 0.0) atomicMax(reinterpret_cast<unsigned long long*>(&err_sh), (unsigned long long)__double_as_longlong(err));
-        __syncthreads();
-        if (tid == 0) { ws->col_err = err_sh; ws->iters_done = it_global + 1; }
+        if (blockIdx.x == 0) ws->colsum[(it_global + 2) % 3][j] = 0.0;
+        const float e = (float)(fabs(c * (double)k - 1.0));
+        atomicMax(reinterpret_cast<int*>(&err_sh), __float_as_int(e));       // e >= 0: int order == float order
       }
       __syncthreads();
+      const float err = err_sh;
+      if (blockIdx.x == 0 && tid == 0) { ws->col_err = (double)err; ws->iters_done = it_global + 1; }
+      __syncthreads();
+      if (stages.tol > 0.f && err < stages.tol) { ++it_global; break; }
     }
   }
   if (blockIdx.x == 0)
@@ -270,28 +269,73 @@ __global__ void assign_plan_kernel(const T* __restrict__ plan, long long n, int 
   label[i] = arg;
 }
 
-// label_i = argmax_j (g_j - M_ij), first max wins; centroid sums via shared-memory atomics.
-// One warp per row for the X read (coalesced d floats); acc_sh [k][d] fp32, flushed to fp64 global.
+// label_i = argmax_j (g_j - M_ij), first max wins; centroid sums in shared memory.
+// One warp per row (coalesced d-float read of X).  The accumulators [k][d] are replicated `copies` times;
+// with one copy per warp (copies == warps) a warp owns its copy and adds without atomics, otherwise warps
+// sharing a copy use shared-memory atomics.  Copies are folded into the fp64 global sums every flush_rows.
 __global__ void __launch_bounds__(256)
 assign_centroid_kernel(const float* __restrict__ M, long long n, int k, int kpad, const float* __restrict__ g,
                        const float* __restrict__ X, int d, int32_t* __restrict__ label, double* __restrict__ sum,
-                       long long* __restrict__ cnt, int flush_rows) {
-  extern __shared__ __align__(16) float acc_sh[];   // [k*d] then cnt_sh[k] (as int)
-  int* cnt_sh = reinterpret_cast<int*>(acc_sh + (size_t)k * d);
+                       long long* __restrict__ cnt, int flush_rows, int copies) {
+  extern __shared__ __align__(16) float acc_sh[];   // [copies][k*d], then cnt_sh [copies][k] (int)
+  const int kd = k * d;
+  int* cnt_sh = reinterpret_cast<int*>(acc_sh + (size_t)copies * kd);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n_warps = blockDim.x >> 5;
-  for (int x = tid; x < k * d; x += blockDim.x) acc_sh[x] = 0.f;
-  for (int x = tid; x < k; x += blockDim.x) cnt_sh[x] = 0;
+  const bool exclusive = copies == n_warps;
+  float* my_acc = acc_sh + (size_t)(warp % copies) * kd;
+  int* my_cnt = cnt_sh + (warp % copies) * k;
+  __shared__ float g_sh[256];
+  for (int x = tid; x < k; x += blockDim.x) g_sh[x] = g[x];
+  for (int x = tid; x < copies * kd; x += blockDim.x) acc_sh[x] = 0.f;
+  for (int x = tid; x < copies * k; x += blockDim.x) cnt_sh[x] = 0;
   __syncthreads();
   const long long per = (n + gridDim.x - 1) / gridDim.x;
   const long long r0 = per * blockIdx.x < n ? per * blockIdx.x : n;
   const long long r1 = r0 + per < n ? r0 + per : n;
   for (long long c0 = r0; c0 < r1; c0 += flush_rows) {
     const long long c1 = c0 + flush_rows < r1 ? c0 + flush_rows : r1;
+    if (k <= 32) {
+      // small k: a THREAD finds its row's label (k compares over its own kpad floats), then the warp walks
+      // its 32 rows and adds each 4*d-byte row of X into the label's accumulator with coalesced loads
+      for (long long row0 = c0 + (long long)warp * 32; row0 < c1; row0 += (long long)n_warps * 32) {
+        const long long row = row0 + lane;
+        const bool valid = row < c1;
+        int arg = 0;
+        if (valid) {
+          float best = -INFINITY;
+          const float4* mr = reinterpret_cast<const float4*>(M + row * kpad);
+          for (int j4 = 0; j4 * 4 < k; ++j4) {
+            const float4 m = __ldg(mr + j4);
+            const float v[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int j = j4 * 4 + q;
+              if (j < k) {
+                const float t = g_sh[j] - v[q];
+                if (t > best) { best = t; arg = j; }      // strict '>' keeps the first maximum
+              }
+            }
+          }
+          label[row] = arg;
+        }
+        const int n_valid = (int)((c1 - row0) < 32 ? (c1 - row0) : 32);
+        for (int r = 0; r < n_valid; ++r) {
+          const int lab = __shfl_sync(0xffffffffu, arg, r);
+          if (lane == 0) { if (exclusive) my_cnt[lab] += 1; else atomicAdd(&my_cnt[lab], 1); }
+          if (X) {
+            const float* xr = X + (row0 + r) * d;
+            float* ar = my_acc + (size_t)lab * d;
+            if (exclusive) for (int t = lane; t < d; t += 32) ar[t] += __ldg(xr + t);
+            else for (int t = lane; t < d; t += 32) atomicAdd(&ar[t], __ldg(xr + t));
+          }
+        }
+      }
+    } else
     for (long long row = c0 + warp; row < c1; row += n_warps) {
       float best = -INFINITY;
       int arg = 0x7fffffff;
       for (int j = lane; j < k; j += 32) {
-        const float v = __ldg(g + j) - __ldg(M + row * kpad + j);
+        const float v = g_sh[j] - __ldg(M + row * kpad + j);
         if (v > best) { best = v; arg = j; }
       }
 #pragma unroll
@@ -300,22 +344,28 @@ assign_centroid_kernel(const float* __restrict__ M, long long n, int k, int kpad
         const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
         if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
       }
-      if (lane == 0) { label[row] = arg; atomicAdd(&cnt_sh[arg], 1); }
+      if (lane == 0) {
+        label[row] = arg;
+        if (exclusive) my_cnt[arg] += 1; else atomicAdd(&my_cnt[arg], 1);
+      }
       if (X) {
         const float* xr = X + row * d;
-        float* ar = acc_sh + (size_t)arg * d;
-        for (int t = lane; t < d; t += 32) atomicAdd(&ar[t], __ldg(xr + t));
+        float* ar = my_acc + (size_t)arg * d;
+        if (exclusive) for (int t = lane; t < d; t += 32) ar[t] += __ldg(xr + t);
+        else for (int t = lane; t < d; t += 32) atomicAdd(&ar[t], __ldg(xr + t));
       }
     }
     __syncthreads();
     if (X)
-      for (int x = tid; x < k * d; x += blockDim.x) {
-        const float v = acc_sh[x];
-        if (v != 0.f) { atomicAdd(sum + x, (double)v); acc_sh[x] = 0.f; }
+      for (int x = tid; x < kd; x += blockDim.x) {
+        float v = 0.f;
+        for (int c = 0; c < copies; ++c) { v += acc_sh[(size_t)c * kd + x]; acc_sh[(size_t)c * kd + x] = 0.f; }
+        if (v != 0.f) atomicAdd(sum + x, (double)v);
       }
     for (int x = tid; x < k; x += blockDim.x) {
-      const int v = cnt_sh[x];
-      if (v) { atomicAdd(reinterpret_cast<unsigned long long*>(cnt + x), (unsigned long long)v); cnt_sh[x] = 0; }
+      int v = 0;
+      for (int c = 0; c < copies; ++c) { v += cnt_sh[c * k + x]; cnt_sh[c * k + x] = 0; }
+      if (v) atomicAdd(reinterpret_cast<unsigned long long*>(cnt + x), (unsigned long long)v);
     }
     __syncthreads();
   }
@@ -381,7 +431,7 @@ extern "C" int ure_sinkhorn_update_g(float* d_g, double* d_colsum, int k, float 
 extern "C" int64_t ure_sinkhorn_workspace_bytes(void) { return (int64_t)sizeof(ure::SkWorkspace); }
 
 extern "C" int ure_sinkhorn(const float* d_M, int64_t n, int k, int kpad, float* d_g, const float* h_eps,
-                            const int32_t* h_iters, int n_stages, void* d_workspace, void* stream) {
+                            const int32_t* h_iters, int n_stages, float tol, void* d_workspace, void* stream) {
   using namespace ure;
   if (int rc = check_mk(d_M, n, k, kpad, "ure_sinkhorn")) return rc;
   URE_REQUIRE(d_g && h_eps && h_iters && d_workspace, URE_EINVAL, "ure_sinkhorn: null argument");
@@ -389,6 +439,7 @@ extern "C" int ure_sinkhorn(const float* d_M, int64_t n, int k, int kpad, float*
               n_stages, kMaxStages);
   SkStages stg;
   stg.n = n_stages;
+  stg.tol = tol;
   for (int s = 0; s < n_stages; ++s) {
     URE_REQUIRE(h_eps[s] > 0.f && h_iters[s] >= 0, URE_EINVAL, "ure_sinkhorn: stage %d eps/iters invalid", s);
     stg.eps[s] = h_eps[s];
@@ -400,13 +451,17 @@ extern "C" int ure_sinkhorn(const float* d_M, int64_t n, int k, int kpad, float*
   const int grid = num_sms();
   const long long per = (n + grid - 1) / grid;
   const size_t need = (size_t)per * kpad * sizeof(float);
-  const bool cached = need <= 200 * 1024;
-  const size_t smem = cached ? need : 0;
-  if (cached) {
-    URE_KPAD_SWITCH(kpad, return (launch_sinkhorn<KP, true>(d_M, n, k, d_g, stg, ws, grid, smem, st)));
-  } else {
-    URE_KPAD_SWITCH(kpad, return (launch_sinkhorn<KP, false>(d_M, n, k, d_g, stg, ws, grid, smem, st)));
+  if (need <= 200 * 1024) {
+    // small problem: everything is latency -- one persistent launch, a CTA's rows cached in shared memory
+    URE_KPAD_SWITCH(kpad, return (launch_sinkhorn<KP, true>(d_M, n, k, d_g, stg, ws, grid, need, st)));
   }
+  // large problem: one streaming pass per iteration at full occupancy (split-phase kernels, no host sync;
+  // the early exit needs the column sums on the host, so every scheduled iteration runs)
+  for (int s = 0; s < n_stages; ++s)
+    for (int it = 0; it < h_iters[s]; ++it) {
+      if (int rc = ure_sinkhorn_colsum(d_M, n, k, kpad, d_g, h_eps[s], (double)n, ws->colsum[0], stream)) return rc;
+      if (int rc = ure_sinkhorn_update_g(d_g, ws->colsum[0], k, h_eps[s], stream)) return rc;
+    }
   return 0;
 }
 
@@ -451,14 +506,20 @@ extern "C" int ure_assign_centroids(const float* d_M, int64_t n, int k, int kpad
   using namespace ure;
   if (int rc = check_mk(d_M, n, k, kpad, "ure_assign_centroids")) return rc;
   URE_REQUIRE(d_g && d_label && d_cnt && (!d_X || (d_sum && d > 0)), URE_EINVAL, "ure_assign_centroids: bad argument");
-  const size_t smem = ((size_t)k * (d_X ? d : 0) + k) * sizeof(float);
-  URE_REQUIRE(smem <= 200 * 1024, URE_EUNSUPPORTED, "ure_assign_centroids: k*d=%d too large for shared memory", k * d);
+  const int dd = d_X ? d : 0;
+  const size_t one = ((size_t)k * dd + k) * sizeof(float);
+  URE_REQUIRE(one <= 200 * 1024, URE_EUNSUPPORTED, "ure_assign_centroids: k*d=%d too large for shared memory", k * d);
+  int copies = (int)((96 * 1024) / one);            // <= 96 KB: two CTAs per SM stay resident
+  if (copies > 8) copies = 8;                        // 8 warps per CTA
+  if (copies < 1) copies = 1;
+  while (copies > 1 && (8 % copies) != 0) --copies;  // warps map evenly onto copies
+  const size_t smem = one * copies;
   URE_CUDA(cudaFuncSetAttribute(assign_centroid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   long long blocks = (n + 1023) / 1024;
   const long long cap = (long long)num_sms() * 2;
   if (blocks > cap) blocks = cap;
   assign_centroid_kernel<<<(unsigned)blocks, 256, smem, static_cast<cudaStream_t>(stream)>>>(
-      d_M, n, k, kpad, d_g, d_X, d_X ? d : 0, d_label, d_sum, reinterpret_cast<long long*>(d_cnt), 4096);
+      d_M, n, k, kpad, d_g, d_X, dd, d_label, d_sum, reinterpret_cast<long long*>(d_cnt), 4096, copies);
   URE_CUDA(cudaGetLastError());
   return 0;
 }

@@ -285,8 +285,9 @@ def cost_matrix(X, Cc, want_inertia=False, simt=False):
     return (M, inertia) if want_inertia else M
 
 
-def sinkhorn(M, k, eps_schedule, g=None) -> torch.Tensor:
-    """Single-GPU persistent Sinkhorn; eps_schedule = [(eps, iters), ...]. Returns g fp32 [k]."""
+def sinkhorn(M, k, eps_schedule, g=None, tol: float = 0.0) -> torch.Tensor:
+    """Single-GPU Sinkhorn; eps_schedule = [(eps, iters), ...], g = warm-start potentials (None: zeros),
+    tol > 0 = early exit on the relative column-marginal error.  Returns g fp32 [k]."""
     _need_cuda(M, g)
     n, kp = M.shape
     g = torch.zeros(k, dtype=torch.float32, device=M.device) if g is None else g.clone()
@@ -295,7 +296,8 @@ def sinkhorn(M, k, eps_schedule, g=None) -> torch.Tensor:
     its = (C.c_int32 * S)(*[int(i) for _, i in eps_schedule])
     ws = torch.zeros(int(_lib.lib().ure_sinkhorn_workspace_bytes()), dtype=torch.uint8, device=M.device)
     with torch.cuda.device(M.device):
-        check(_lib.lib().ure_sinkhorn(_ptr(M), n, k, kp, _ptr(g), eps, its, S, _ptr(ws), _stream()), "ure_sinkhorn")
+        check(_lib.lib().ure_sinkhorn(_ptr(M), n, k, kp, _ptr(g), eps, its, S, float(tol), _ptr(ws), _stream()),
+              "ure_sinkhorn")
     return g
 
 

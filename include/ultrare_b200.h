@@ -62,7 +62,7 @@ typedef struct {
   int32_t n_item;           /* rows of Q                                                   */
   int32_t shard_id;         /* Feistel key component                                       */
   uint32_t perm_seed;       /* Feistel key component                                       */
-  int32_t reserved;
+  int32_t group;            /* warp group (0 or 1) that trains this shard, see ure_mf_train        */
 } ure_mf_shard_t;
 
 typedef struct {
@@ -83,21 +83,25 @@ int ure_abi_version(void);
 /* Bytes of device scratch ure_mf_train needs (grid barrier + step tables). */
 int64_t ure_mf_train_workspace_bytes(void);
 
-/* baseTrain (method/utils.py:46-111) for ALL shards of `d_shards` at once, for
- * global steps [step_begin, step_end).  Shard s runs batch (t mod spe_s) of its
- * epoch (t div spe_s), spe_s = ceil(n_s/batch), and is idle once it has done
- * `epochs` epochs.  One persistent cooperative launch.  `d_workspace` must be
- * zero-filled before the first call of a training and reused afterwards. */
+/* baseTrain (method/utils.py:46-111) for ALL shards of `d_shards` at once, for global steps
+ * [step_begin, step_end).  Shard s runs batch (t mod spe_s) of its epoch (t div spe_s),
+ * spe_s = ceil(n_s/batch), and is idle once it has done `epochs` epochs.  One persistent cooperative
+ * launch, one 32-warp CTA per SM.  Shards are independent, so the warps of every CTA are split into two
+ * groups: the first `warps_group0` warps train the shards with group == 0, the others those with
+ * group == 1, each group with its own grid barrier, so one group's barrier latency is covered by the
+ * other's work.  warps_group0 = 32 runs everything as one group (required when there is one shard).
+ * Balance: warps_group0 / 32 ~ the share of the interactions that group 0's shards hold. */
 int ure_mf_train(const ure_mf_shard_t* d_shards, int n_shards, const ure_mf_hparams_t* h_hp,
-                 int epochs, int64_t step_begin, int64_t step_end, void* d_workspace, void* stream);
+                 int epochs, int64_t step_begin, int64_t step_end, int warps_group0,
+                 void* d_workspace, void* stream);
 
 /* Diagnostics (tracing): record six SM-clock stamps per CTA and step -- step start, tables ready,
  * gradients issued, barrier 1 passed, sweep issued, barrier 2 passed -- for the first `steps` steps of
  * the following ure_mf_train calls into d_trace [steps][ure_mf_grid_size()][6] int64; NULL = off. */
 int ure_mf_train_trace(void* d_workspace, int64_t* d_trace, int steps, void* stream);
 int ure_mf_grid_size(void);
-/* Diagnostics: bit 0 skips the gradient scatter, bit 1 uses the identity visiting order, bit 2 runs the
- * shards as two interleaved pipelines (timing experiments only). */
+/* Diagnostics: bit 0 skips the gradient scatter, bit 1 uses the identity visiting order, bits 8..13 force
+ * warps_group0 (timing experiments only). */
 int ure_mf_debug_flags(void* d_workspace, unsigned flags, void* stream);
 
 /* Lazy mode: bring every row of every shard up to date (end of training / before export). */

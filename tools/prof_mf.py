@@ -91,5 +91,5 @@ def run_trace(flags, label):
 
 import ctypes as C
 from ultrare_b200 import _lib
-for flags, label in ((0, "single pipeline"), (4, "two pipelines (experimental)"), (1, "single pipeline, no REDs")):
+for flags, label in ((0, "two warp groups (default split %d)" % sb.warps_group0), (32 << 8, "one group of 32 warps"), (16 << 8, "forced 16/16"), (20 << 8, "forced 20/12")):
     run_trace(flags, label)

@@ -23,7 +23,7 @@ class MFShard(C.Structure):
     _fields_ = [("inter", _p), ("perm", _p), ("P", _p), ("Q", _p), ("bufP", _p), ("bufQ", _p),
                 ("gP", _p), ("gQ", _p), ("sse", _p), ("lastP", _p), ("lastQ", _p),
                 ("n", _i32), ("n_user", _i32), ("n_item", _i32), ("shard_id", _i32),
-                ("perm_seed", C.c_uint32), ("reserved", _i32)]
+                ("perm_seed", C.c_uint32), ("group", _i32)]
 
 
 class MFHParams(C.Structure):
@@ -39,7 +39,7 @@ SIGNATURES = {
     "ure_last_error": (C.c_char_p, []),
     "ure_abi_version": (C.c_int, []),
     "ure_mf_train_workspace_bytes": (_i64, []),
-    "ure_mf_train": (C.c_int, [_p, C.c_int, C.POINTER(MFHParams), C.c_int, _i64, _i64, _p, _p]),
+    "ure_mf_train": (C.c_int, [_p, C.c_int, C.POINTER(MFHParams), C.c_int, _i64, _i64, C.c_int, _p, _p]),
     "ure_mf_train_trace": (C.c_int, [_p, _p, C.c_int, _p]),
     "ure_mf_grid_size": (C.c_int, []),
     "ure_mf_debug_flags": (C.c_int, [_p, C.c_uint32, _p]),

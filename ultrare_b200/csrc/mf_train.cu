@@ -34,7 +34,7 @@ constexpr int kThreads = 1024;
 constexpr int KM = URE_MAX_SHARDS;
 
 struct Workspace {
-  unsigned barrier[2];     // one monotonic counter per shard group
+  unsigned barrier[2];     // one monotonic counter per warp group
   long long* trace;        // optional [steps][gridDim.x][6] SM-clock stamps (ure_mf_train_trace), else NULL
   int trace_steps;
   unsigned debug_flags;    // diagnostics only: 1 = skip gradient REDs, 2 = identity visiting order
@@ -67,21 +67,28 @@ __device__ __forceinline__ int find_segment(const T* prefix, int nseg, T x) {
   return lo;
 }
 
-// ---- split grid barrier (monotonic counter; cooperative launch guarantees co-residency)
-__device__ __forceinline__ void barrier_arrive(unsigned* counter) {
-  __syncthreads();                        // every warp of the CTA has issued its writes / REDs
-  if (threadIdx.x == 0) {
-    __threadfence();                      // cumulative: orders the CTA's prior writes before the arrival
+// ---- split grid barrier (monotonic counter; cooperative launch guarantees co-residency).
+// A CTA hosts up to two independent warp groups; each group synchronises on its own named barrier
+// (bar.sync id, count) and its own global counter, so a group waiting at a grid barrier leaves the SM to
+// the other group's warps.
+__device__ __forceinline__ void group_sync(int bar_id, int n_threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(n_threads) : "memory");
+}
+__device__ __forceinline__ void barrier_arrive(unsigned* counter, int bar_id, int n_threads, bool leader) {
+  group_sync(bar_id, n_threads);          // every warp of the group has issued its writes / REDs
+  if (leader) {
+    __threadfence();                      // cumulative: orders the group's prior writes before the arrival
     atomicAdd(counter, 1u);
   }
 }
-__device__ __forceinline__ void barrier_wait(unsigned* counter, unsigned target) {
-  if (threadIdx.x == 0) {
+__device__ __forceinline__ void barrier_wait(unsigned* counter, unsigned target, int bar_id, int n_threads,
+                                             bool leader) {
+  if (leader) {
     while (*reinterpret_cast<volatile unsigned*>(counter) < target) {
     }
     __threadfence();
   }
-  __syncthreads();
+  group_sync(bar_id, n_threads);
 }
 
 // Gradient work of one 32-interaction warp chunk.  Lane l fetched interaction l (u, it, r, shard s or -1);
@@ -135,24 +142,13 @@ __device__ __forceinline__ float chunk_gradients(int u, int it, float r, int s, 
   return my_e;
 }
 
-// Per-group pipeline state kept in registers.
-struct GroupCtx {
-  int ps, pu, pi;          // prefetched record of this lane's interaction in the warp's first chunk
-  float pr;
-  int seg0;                // preloaded operands of this thread's first sweep element
-  size_t off0;
-  float4 w0, b0;
-  unsigned target;         // running barrier target of the group's counter
-  int cur;                 // which of the group's two step tables is current
-};
-
-// NG = number of independent shard groups (shard s belongs to group s % NG).  Shards never interact, so
-// with NG = 2 the two groups run as two interleaved pipelines: every barrier WAIT of one group is covered
-// by gradient / sweep work of the other.
-template <int D, int NG>
+// Shards never interact, so the CTA's 32 warps are split into (up to) two warp GROUPS, each running the
+// whole step pipeline for its own subset of the shards (ure_mf_shard_t::group) with its own named barrier
+// and its own grid-barrier counter: while one group sits in a barrier, the SM executes the other's warps.
+template <int D>
 __global__ void __launch_bounds__(kThreads, 1)
 mf_train_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams_t hp, int epochs,
-                long long step_begin, long long step_end, Workspace* ws) {
+                long long step_begin, long long step_end, Workspace* ws, int warps_g0) {
   constexpr int G = D / 4;                 // lanes per interaction
   // ---- per-CTA shard tables (static shared memory): constant for the whole launch
   __shared__ ShardPtrs s_ptr[KM];
@@ -161,19 +157,18 @@ mf_train_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
   __shared__ float* s_buf[2 * KM];         // bufP, bufQ
   __shared__ double* s_sse[KM];
   __shared__ int s_n[KM], s_nuser[KM], s_nitem[KM], s_spe[KM], s_shard_id[KM];
+  __shared__ unsigned char s_group[KM];
   __shared__ uint32_t s_seed[KM];
   __shared__ FeistelDomain s_dom[KM];
   // ---- per-shard schedule cursor (advanced by the table builder) and the double-buffered step tables
   __shared__ int s_cur_epoch[KM], s_cur_batch[KM];
-  extern __shared__ __align__(16) unsigned char dyn_smem[];     // StepTables[NG][2] (static limit is 48 KB)
-  StepTables* const s_tab = reinterpret_cast<StepTables*>(dyn_smem);
+  extern __shared__ __align__(16) unsigned char dyn_smem[];     // StepTables[2 groups][2] (static limit is 48 KB)
+  StepTables* const s_tab_all = reinterpret_cast<StepTables*>(dyn_smem);
   __shared__ float s_sse_acc[KM];
 
-  const int tid = threadIdx.x;
-  const int lane = tid & 31;
-  const int warp = tid >> 5;
+  const int lane = threadIdx.x & 31;
   const int gl = lane % G;
-  for (int s = tid; s < K; s += kThreads) {
+  for (int s = threadIdx.x; s < K; s += kThreads) {
     const ure_mf_shard_t sh = shards[s];
     s_ptr[s] = ShardPtrs{sh.P, sh.Q, sh.gP, sh.gQ};
     s_inter[s] = sh.inter; s_perm[s] = sh.perm;
@@ -183,35 +178,48 @@ mf_train_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
     const int spe = (sh.n + hp.batch - 1) / hp.batch;
     s_spe[s] = spe;
     s_seed[s] = sh.perm_seed; s_shard_id[s] = sh.shard_id;
+    s_group[s] = (unsigned char)((warps_g0 < kThreads / 32) ? (sh.group & 1) : 0);
     s_dom[s].init((uint32_t)sh.n);
     s_cur_epoch[s] = spe > 0 ? (int)(step_begin / spe) : epochs;     // the only divisions of the launch
     s_cur_batch[s] = spe > 0 ? (int)(step_begin % spe) : 0;
     s_sse_acc[s] = 0.f;
   }
+  __syncthreads();
+
+  // ---- this thread's warp group
+  const int grp = (int)(threadIdx.x >> 5) < warps_g0 ? 0 : 1;
+  const int g_warps = grp == 0 ? warps_g0 : kThreads / 32 - warps_g0;     // warps of the group in this CTA
+  const int g_threads = g_warps * 32;
+  const int tid = threadIdx.x - (grp == 0 ? 0 : warps_g0 * 32);          // thread index inside the group
+  const int warp = tid >> 5;
+  const int bar_id = grp + 1;                                             // named barrier of the group
+  const bool leader = tid == 0;
+  unsigned* const counter = &ws->barrier[grp];
+  StepTables* const s_tab = s_tab_all + 2 * grp;
   const unsigned dbg = ws->debug_flags;
   long long* const trace = ws->trace;
   const int trace_steps = ws->trace_steps;
-  const long long n_threads = (long long)gridDim.x * kThreads;
-  const long long gtid = (long long)blockIdx.x * kThreads + tid;
+  const long long n_threads = (long long)gridDim.x * g_threads;          // the group's threads grid-wide
+  const long long gtid = (long long)blockIdx.x * g_threads + tid;
   const int n_warps = (int)(n_threads >> 5);
   const int gwarp = (int)(gtid >> 5);
   const float wd = hp.weight_decay, mu = hp.momentum;
-  __syncthreads();
+  unsigned bar_target = 0;
 
-  // Step tables of group g for the step its shards' cursors point at, then advance the cursors.  Executed
+  // Step tables of the group for the step its shards' cursors point at, then advance the cursors.  Executed
   // by ONE warp (lanes = shards, 32 at a time, prefix carried): no block-wide synchronisation inside.
-  auto build_tables = [&](StepTables& tb, int g) {
+  auto build_tables = [&](StepTables& tb) {
     int carry = 0;
     long long carry2 = 0;
     for (int base = 0; base < K; base += 32) {
       const int s = base + lane;
       int cnt = 0, ep = -1, st = 0;
       long long rows_u = 0, rows_i = 0;
-      if (s < K) {
+      if (s < K && s_group[s] == grp) {
         const int spe = s_spe[s];
         ep = s_cur_epoch[s];
         const int bi = s_cur_batch[s];
-        if ((s % NG) == g && spe > 0 && ep < epochs) {
+        if (spe > 0 && ep < epochs) {
           st = bi * hp.batch;
           cnt = min(hp.batch, s_n[s] - st);
           rows_u = (long long)s_nuser[s] * G;
@@ -225,6 +233,8 @@ mf_train_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
         } else {
           ep = -1;
         }
+      }
+      if (s < K) {
         tb.epoch[s] = ep;
         tb.start[s] = st;
       }
@@ -264,16 +274,30 @@ mf_train_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
     }
   };
 
-  // ---------------------------------------------------------------- gradients of group g
-  auto gradients = [&](GroupCtx& c, int g) {
-    const StepTables& tb = s_tab[2 * g + c.cur];
+#define URE_STAMP(PH)                                                                                  \
+  if (trace && leader && grp == 0 && (t - step_begin) < trace_steps)                                   \
+    trace[((t - step_begin) * gridDim.x + blockIdx.x) * 6 + (PH)] = clock64();
+
+  // ---- prologue: tables and first-chunk records of the group's first step
+  if (warp == 0) build_tables(s_tab[0]);
+  group_sync(bar_id, g_threads);
+  int ps, pu_, pi_;
+  float pr_;
+  fetch(s_tab[0], gwarp, ps, pu_, pi_, pr_);
+
+  int cur = 0;
+  for (long long t = step_begin; t < step_end; ++t, cur ^= 1) {
+    const StepTables& tb = s_tab[cur];
+    const bool more = t + 1 < step_end;
+    URE_STAMP(0)
+    // ---------------------------------------------------------------- gradients
     const int total = tb.item_prefix[K];
     float acc = 0.f;          // sum of e^2 of the chunks this warp processed, all in shard acc_s
     int acc_s = -1;
     for (int wc = gwarp; wc * 32 < total; wc += n_warps) {
       int s, u, it;
       float r;
-      if (wc == gwarp) { s = c.ps; u = c.pu; it = c.pi; r = c.pr; }      // prefetched behind a barrier
+      if (wc == gwarp) { s = ps; u = pu_; it = pi_; r = pr_; }      // prefetched behind WAIT 2 of step t-1
       else fetch(tb, wc, s, u, it, r);
       const bool valid = s >= 0;
       // the common case: the whole 32-interaction chunk lies in one shard -> table pointers once per warp
@@ -297,47 +321,41 @@ mf_train_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
       }
     }
     if (acc_s >= 0 && lane == 0) atomicAdd(&s_sse_acc[acc_s], acc);
-  };
-
-  auto arrive = [&](GroupCtx& c, int g) {
-    barrier_arrive(&ws->barrier[g]);
-    c.target += gridDim.x;
-  };
-  auto wait = [&](GroupCtx& c, int g) { barrier_wait(&ws->barrier[g], c.target); };
-
-  // Work that only needs the CTA's own gradient phase: publish the loss, preload the sweep operands the
-  // gradient phase did not touch, build the group's tables of the next step (warp 1).
-  auto after_gradients = [&](GroupCtx& c, int g, bool more) {
-    const StepTables& tb = s_tab[2 * g + c.cur];
-    for (int s = tid; s < K; s += kThreads) {
-      if ((s % NG) != g) continue;
+    URE_STAMP(1)
+    barrier_arrive(counter, bar_id, g_threads, leader);     // ---------------- ARRIVE 1
+    bar_target += gridDim.x;
+    // overlap: publish the loss, preload the sweep operands that the gradient phase did not touch,
+    // build the tables of step t+1
+    for (int s = tid; s < K; s += g_threads) {
+      if (s_group[s] != grp) continue;
       const float v = s_sse_acc[s];
       if (v != 0.f) {
         atomicAdd(s_sse[s] + tb.epoch[s], (double)v);
         s_sse_acc[s] = 0.f;
       }
     }
-    c.seg0 = 0; c.off0 = 0;
-    c.w0 = make_float4(0.f, 0.f, 0.f, 0.f); c.b0 = c.w0;
-    if (gtid < tb.row_prefix[2 * K]) {
-      c.seg0 = find_segment(tb.row_prefix, 2 * K, gtid);
-      c.off0 = (size_t)(gtid - tb.row_prefix[c.seg0]) * 4;
-      const ShardPtrs tp = s_ptr[c.seg0 >> 1];
-      c.w0 = ld_cg_f4(((c.seg0 & 1) ? tp.Q : tp.P) + c.off0);
-      c.b0 = ld_cg_f4(s_buf[c.seg0] + c.off0);
-    }
-    if (warp == 1 && more) build_tables(s_tab[2 * g + (c.cur ^ 1)], g);
-  };
-
-  // ---------------------------------------------------------------- dense SGD sweep of group g
-  auto sweep = [&](GroupCtx& c, int g) {
-    const StepTables& tb = s_tab[2 * g + c.cur];
     const long long total4 = tb.row_prefix[2 * K];
+    int seg0 = 0;
+    size_t off0 = 0;
+    float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f), b0 = w0;
+    if (gtid < total4) {
+      seg0 = find_segment(tb.row_prefix, 2 * K, gtid);
+      off0 = (size_t)(gtid - tb.row_prefix[seg0]) * 4;
+      const ShardPtrs tp = s_ptr[seg0 >> 1];
+      w0 = ld_cg_f4(((seg0 & 1) ? tp.Q : tp.P) + off0);
+      b0 = ld_cg_f4(s_buf[seg0] + off0);
+    }
+    if (warp == (g_warps > 1 ? 1 : 0) && more) build_tables(s_tab[cur ^ 1]);
+    URE_STAMP(2)
+    barrier_wait(counter, bar_target, bar_id, g_threads, leader);   // -------- WAIT 1
+    URE_STAMP(3)
+
+    // ---------------------------------------------------------------- dense SGD sweep
     for (long long x = gtid; x < total4; x += n_threads) {
       int seg;
       size_t off;
       float4 w, b;
-      if (x == gtid) { seg = c.seg0; off = c.off0; w = c.w0; b = c.b0; }
+      if (x == gtid) { seg = seg0; off = off0; w = w0; b = b0; }
       else {
         seg = find_segment(tb.row_prefix, 2 * K, x);
         off = (size_t)(x - tb.row_prefix[seg]) * 4;
@@ -350,115 +368,46 @@ mf_train_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
       float* Gr = (seg & 1) ? tp.gQ : tp.gP;
       float* Bf = s_buf[seg];
       const float nlr = -tb.lr[seg >> 1];
-      float4 gr = ld_cg_f4(Gr + off);
+      float4 g = ld_cg_f4(Gr + off);
       // torch SGD: d_p = g + wd*w (fma); buf = buf*mu + d_p; w = w + (-lr)*buf (fma)
-      gr.x = fmaf(wd, w.x, gr.x); gr.y = fmaf(wd, w.y, gr.y); gr.z = fmaf(wd, w.z, gr.z); gr.w = fmaf(wd, w.w, gr.w);
-      b.x = __fadd_rn(__fmul_rn(b.x, mu), gr.x); b.y = __fadd_rn(__fmul_rn(b.y, mu), gr.y);
-      b.z = __fadd_rn(__fmul_rn(b.z, mu), gr.z); b.w = __fadd_rn(__fmul_rn(b.w, mu), gr.w);
+      g.x = fmaf(wd, w.x, g.x); g.y = fmaf(wd, w.y, g.y); g.z = fmaf(wd, w.z, g.z); g.w = fmaf(wd, w.w, g.w);
+      b.x = __fadd_rn(__fmul_rn(b.x, mu), g.x); b.y = __fadd_rn(__fmul_rn(b.y, mu), g.y);
+      b.z = __fadd_rn(__fmul_rn(b.z, mu), g.z); b.w = __fadd_rn(__fmul_rn(b.w, mu), g.w);
       w.x = fmaf(nlr, b.x, w.x); w.y = fmaf(nlr, b.y, w.y); w.z = fmaf(nlr, b.z, w.z); w.w = fmaf(nlr, b.w, w.w);
       st_cg_f4(W + off, w);
       st_cg_f4(Bf + off, b);
       st_cg_f4(Gr + off, make_float4(0.f, 0.f, 0.f, 0.f));
     }
-  };
-
-  // visiting-order index + record of this warp's first chunk of the group's next step (static data)
-  auto prefetch_next = [&](GroupCtx& c, int g, bool more) {
-    if (more) fetch(s_tab[2 * g + (c.cur ^ 1)], gwarp, c.ps, c.pu, c.pi, c.pr);
-  };
-
-#define URE_STAMP(PH)                                                                                  \
-  if (trace && tid == 0 && (t - step_begin) < trace_steps)                                             \
-    trace[((t - step_begin) * gridDim.x + blockIdx.x) * 6 + (PH)] = clock64();
-
-  // ---- prologue: tables and first-chunk records of the first step of every group
-  GroupCtx c[NG];
-  if (warp == 0) {
-#pragma unroll
-    for (int g = 0; g < NG; ++g) build_tables(s_tab[2 * g], g);
+    URE_STAMP(4)
+    barrier_arrive(counter, bar_id, g_threads, leader);     // ---------------- ARRIVE 2
+    bar_target += gridDim.x;
+    // overlap: visiting-order index + record of this warp's first chunk of step t+1 (static data);
+    // the tables of t+1 were written before WAIT 1's group barrier
+    if (more) fetch(s_tab[cur ^ 1], gwarp, ps, pu_, pi_, pr_);
+    barrier_wait(counter, bar_target, bar_id, g_threads, leader);   // -------- WAIT 2
+    URE_STAMP(5)
   }
-  __syncthreads();
-#pragma unroll
-  for (int g = 0; g < NG; ++g) {
-    c[g].cur = 0;
-    c[g].target = 0;
-    fetch(s_tab[2 * g], gwarp, c[g].ps, c[g].pu, c[g].pi, c[g].pr);
-  }
-
-  for (long long t = step_begin; t < step_end; ++t) {
-    const bool more = t + 1 < step_end;
-    URE_STAMP(0)
-    if (NG == 1) {
-      gradients(c[0], 0);
-      URE_STAMP(1)
-      arrive(c[0], 0);                     // ARRIVE 1
-      after_gradients(c[0], 0, more);
-      URE_STAMP(2)
-      wait(c[0], 0);                       // WAIT 1
-      URE_STAMP(3)
-      sweep(c[0], 0);
-      URE_STAMP(4)
-      arrive(c[0], 0);                     // ARRIVE 2
-      prefetch_next(c[0], 0, more);
-      wait(c[0], 0);                       // WAIT 2
-      URE_STAMP(5)
-    } else {
-      // two interleaved pipelines; group 1 runs half a step behind group 0
-      gradients(c[0], 0);
-      arrive(c[0], 0);                     // A: ARRIVE 1
-      after_gradients(c[0], 0, more);
-      URE_STAMP(1)
-      if (t > step_begin) wait(c[NG - 1], NG - 1);          // B: WAIT 2 of step t-1
-      gradients(c[NG - 1], NG - 1);
-      arrive(c[NG - 1], NG - 1);           // B: ARRIVE 1
-      after_gradients(c[NG - 1], NG - 1, more);
-      URE_STAMP(2)
-      wait(c[0], 0);                       // A: WAIT 1
-      sweep(c[0], 0);
-      arrive(c[0], 0);                     // A: ARRIVE 2
-      prefetch_next(c[0], 0, more);
-      URE_STAMP(3)
-      wait(c[NG - 1], NG - 1);             // B: WAIT 1
-      sweep(c[NG - 1], NG - 1);
-      arrive(c[NG - 1], NG - 1);           // B: ARRIVE 2
-      prefetch_next(c[NG - 1], NG - 1, more);
-      URE_STAMP(4)
-      wait(c[0], 0);                       // A: WAIT 2
-      URE_STAMP(5)
-    }
-#pragma unroll
-    for (int g = 0; g < NG; ++g) c[g].cur ^= 1;
-  }
-  if (NG == 2 && step_end > step_begin) wait(c[NG - 1], NG - 1);   // B: WAIT 2 of the last step
 #undef URE_STAMP
 }
 
-bool g_two_pipelines = false;   // diagnostics (ure_mf_debug_flags bit 2)
+int g_force_warps_g0 = -1;   // diagnostics (ure_mf_debug_flags bits 8..13): force the warp split, 32 = one group
 
-template <int D, int NG>
-int launch_ng(const ure_mf_shard_t* d_shards, int K, const ure_mf_hparams_t& hp, int epochs, long long s0,
-              long long s1, Workspace* ws, cudaStream_t st) {
-  auto kern = mf_train_kernel<D, NG>;
-  const size_t smem = 2 * NG * sizeof(StepTables);
+template <int D>
+int launch(const ure_mf_shard_t* d_shards, int K, const ure_mf_hparams_t& hp, int epochs, long long s0,
+           long long s1, Workspace* ws, int warps_g0, cudaStream_t st) {
+  auto kern = mf_train_kernel<D>;
+  const size_t smem = 4 * sizeof(StepTables);
   URE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0;
   URE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem));
   URE_REQUIRE(occ >= 1, URE_ECOOP, "mf_train_kernel<%d> cannot be resident", D);
   const int grid = num_sms();
+  if (g_force_warps_g0 >= 1 && g_force_warps_g0 <= 32) warps_g0 = g_force_warps_g0;
   URE_CUDA(cudaMemsetAsync(ws->barrier, 0, 2 * sizeof(unsigned), st));
-  void* args[] = {(void*)&d_shards, (void*)&K, (void*)&hp, (void*)&epochs, (void*)&s0, (void*)&s1, (void*)&ws};
+  void* args[] = {(void*)&d_shards, (void*)&K,  (void*)&hp, (void*)&epochs,
+                  (void*)&s0,       (void*)&s1, (void*)&ws, (void*)&warps_g0};
   URE_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(kThreads), args, smem, st));
   return 0;
-}
-
-// Default: a single pipeline over all shards.  The two-pipeline variant (debug flag 4) is kept for
-// experiments: measured 2x SLOWER on B200 (profiles/r1_notes.md) because every ARRIVE's fence and every
-// WAIT still stop the whole CTA at a __syncthreads -- it needs a dedicated barrier warp to pay off.
-template <int D>
-int launch(const ure_mf_shard_t* d_shards, int K, const ure_mf_hparams_t& hp, int epochs, long long s0,
-           long long s1, Workspace* ws, cudaStream_t st) {
-  if (K >= 2 && g_two_pipelines) return launch_ng<D, 2>(d_shards, K, hp, epochs, s0, s1, ws, st);
-  return launch_ng<D, 1>(d_shards, K, hp, epochs, s0, s1, ws, st);
 }
 
 }  // namespace
@@ -467,8 +416,8 @@ int launch(const ure_mf_shard_t* d_shards, int K, const ure_mf_hparams_t& hp, in
 extern "C" int64_t ure_mf_train_workspace_bytes(void) { return (int64_t)sizeof(ure::Workspace); }
 
 extern "C" int ure_mf_train(const ure_mf_shard_t* d_shards, int n_shards, const ure_mf_hparams_t* h_hp,
-                            int epochs, int64_t step_begin, int64_t step_end, void* d_workspace,
-                            void* stream) {
+                            int epochs, int64_t step_begin, int64_t step_end, int warps_group0,
+                            void* d_workspace, void* stream) {
   using namespace ure;
   URE_REQUIRE(d_shards && h_hp && d_workspace, URE_EINVAL, "ure_mf_train: null argument");
   URE_REQUIRE(n_shards >= 1 && n_shards <= URE_MAX_SHARDS, URE_EINVAL,
@@ -476,15 +425,17 @@ extern "C" int ure_mf_train(const ure_mf_shard_t* d_shards, int n_shards, const 
   URE_REQUIRE(h_hp->batch > 0 && h_hp->lr_step > 0 && epochs > 0, URE_EINVAL,
               "ure_mf_train: batch/lr_step/epochs must be positive");
   URE_REQUIRE(h_hp->lazy == 0, URE_EUNSUPPORTED, "ure_mf_train: lazy mode not built in this version");
+  URE_REQUIRE(warps_group0 >= 1 && warps_group0 <= kThreads / 32, URE_EINVAL,
+              "ure_mf_train: warps_group0=%d outside [1,%d]", warps_group0, kThreads / 32);
   if (step_end <= step_begin) return 0;
   auto* ws = static_cast<Workspace*>(d_workspace);
   auto st = static_cast<cudaStream_t>(stream);
   switch (h_hp->d) {
-    case 8: return launch<8>(d_shards, n_shards, *h_hp, epochs, step_begin, step_end, ws, st);
-    case 16: return launch<16>(d_shards, n_shards, *h_hp, epochs, step_begin, step_end, ws, st);
-    case 32: return launch<32>(d_shards, n_shards, *h_hp, epochs, step_begin, step_end, ws, st);
-    case 64: return launch<64>(d_shards, n_shards, *h_hp, epochs, step_begin, step_end, ws, st);
-    case 128: return launch<128>(d_shards, n_shards, *h_hp, epochs, step_begin, step_end, ws, st);
+    case 8: return launch<8>(d_shards, n_shards, *h_hp, epochs, step_begin, step_end, ws, warps_group0, st);
+    case 16: return launch<16>(d_shards, n_shards, *h_hp, epochs, step_begin, step_end, ws, warps_group0, st);
+    case 32: return launch<32>(d_shards, n_shards, *h_hp, epochs, step_begin, step_end, ws, warps_group0, st);
+    case 64: return launch<64>(d_shards, n_shards, *h_hp, epochs, step_begin, step_end, ws, warps_group0, st);
+    case 128: return launch<128>(d_shards, n_shards, *h_hp, epochs, step_begin, step_end, ws, warps_group0, st);
     default:
       set_error("ure_mf_train: d=%d not in {8,16,32,64,128}", h_hp->d);
       return URE_EUNSUPPORTED;
@@ -510,7 +461,7 @@ extern "C" int ure_mf_debug_flags(void* d_workspace, unsigned flags, void* strea
   using namespace ure;
   URE_REQUIRE(d_workspace, URE_EINVAL, "ure_mf_debug_flags: null workspace");
   auto* ws = static_cast<Workspace*>(d_workspace);
-  g_two_pipelines = (flags & 4u) != 0;
+  g_force_warps_g0 = (int)((flags >> 8) & 63u) ? (int)((flags >> 8) & 63u) : -1;
   URE_CUDA(cudaMemcpyAsync(&ws->debug_flags, &flags, sizeof(flags), cudaMemcpyHostToDevice,
                            static_cast<cudaStream_t>(stream)));
   URE_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));

@@ -118,6 +118,7 @@ class ShardState:
             self.perm = perm.contiguous()
         self.n = int(inter.shape[0])
         self.shard_id, self.perm_seed, self.epochs = int(shard_id), int(perm_seed) & 0xFFFFFFFF, int(epochs)
+        self.group = 0
 
     def descriptor(self) -> MFShard:
         d = MFShard()
@@ -127,7 +128,7 @@ class ShardState:
         d.gP, d.gQ, d.sse = self.gP.data_ptr(), self.gQ.data_ptr(), self.sse.data_ptr()
         d.lastP = d.lastQ = None
         d.n, d.n_user, d.n_item = self.n, self.P.shape[0], self.Q.shape[0]
-        d.shard_id, d.perm_seed, d.reserved = self.shard_id, self.perm_seed, 0
+        d.shard_id, d.perm_seed, d.group = self.shard_id, self.perm_seed, self.group
         return d
 
     def steps_per_epoch(self, batch: int) -> int:
@@ -147,12 +148,29 @@ class ShardBatch:
         assert all(s.epochs == self.epochs for s in shards)
         self.hp = MFHParams(d=d, batch=batch, lr0=lr, lr_decay=lr_decay, lr_step=lr_step,
                             weight_decay=weight_decay, momentum=momentum, lazy=0)
+        self.warps_group0 = self._split_groups(shards)
         arr = (MFShard * len(shards))(*[s.descriptor() for s in shards])
         host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
         self.table = host.to(self.device)
         self.ws = torch.zeros(int(_lib.lib().ure_mf_train_workspace_bytes()), dtype=torch.uint8, device=self.device)
         self.total_steps = max(s.steps_per_epoch(batch) for s in shards) * self.epochs
         self.step = 0
+
+    @staticmethod
+    def _split_groups(shards, total_warps: int = 32, min_warps: int = 6) -> int:
+        """Greedy split of the shards into two warp groups of near-equal interaction count; returns the
+        number of warps of group 0 (32 = a single group)."""
+        if len(shards) < 2:
+            for s in shards:
+                s.group = 0
+            return total_warps
+        load = [0, 0]
+        for s in sorted(shards, key=lambda s: -s.n):
+            g = 0 if load[0] <= load[1] else 1
+            s.group = g
+            load[g] += s.n
+        w0 = int(round(total_warps * load[0] / max(1, load[0] + load[1])))
+        return min(total_warps - min_warps, max(min_warps, w0))
 
     def train(self, step_end: Optional[int] = None) -> None:
         """Advance every shard to global step `step_end` (default: the end of training)."""
@@ -161,7 +179,8 @@ class ShardBatch:
             return
         with torch.cuda.device(self.device):
             check(_lib.lib().ure_mf_train(_ptr(self.table), len(self.shards), C.byref(self.hp), self.epochs,
-                                          self.step, step_end, _ptr(self.ws), _stream()), "ure_mf_train")
+                                          self.step, step_end, self.warps_group0, _ptr(self.ws), _stream()),
+                  "ure_mf_train")
         self.step = step_end
 
     def interactions_trained(self) -> int:

@@ -55,8 +55,9 @@ typedef struct {
   float* gP;                /* [n_user, d] gradient scratch (zero on entry, zero on exit)  */
   float* gQ;                /* [n_item, d]                                                 */
   double* sse;              /* [n_epochs_total] per-epoch sum of squared errors (+=)       */
-  int32_t* lastP;           /* lazy mode only: [n_user] step index each row is current to  */
+  int32_t* lastP;           /* lazy mode only: [n_user] steps applied to each row (bit 31: touched flag) */
   int32_t* lastQ;           /* lazy mode only: [n_item]                                    */
+  int32_t* touched;         /* lazy mode only: [2][2][1 + batch] per step parity and table: count, row list */
   int32_t n;                /* interactions in the shard                                   */
   int32_t n_user;           /* rows of P                                                   */
   int32_t n_item;           /* rows of Q                                                   */
@@ -75,6 +76,10 @@ typedef struct {
   float momentum;       /* config.py:29                                                      */
   int32_t lazy;         /* 0: dense sweep every step (reference arithmetic, bit-faithful     */
                         /*    order); 1: closed-form catch-up of untouched rows  */
+  const float* decay;   /* lazy: DEVICE table [decay_len][4] of M^n = (a11,a12,a21,a22), the */
+                        /*    n-step gradient-free update [w;buf] <- M^n [w;buf]; else NULL   */
+  int32_t decay_len;    /* lazy: number of table entries (>= total steps + 1)                */
+  int32_t reserved;
 } ure_mf_hparams_t;
 
 const char* ure_last_error(void);
@@ -104,8 +109,10 @@ int ure_mf_grid_size(void);
  * warps_group0 (timing experiments only). */
 int ure_mf_debug_flags(void* d_workspace, unsigned flags, void* stream);
 
-/* Lazy mode: bring every row of every shard up to date (end of training / before export). */
-int ure_mf_flush(const ure_mf_shard_t* d_shards, int n_shards, const ure_mf_hparams_t* h_hp,
+/* Lazy mode: bring every row of every shard up to date (before the tables are read by anything else):
+ * rows whose step count is below the shard's own (min(step_now, spe_s*epochs)) are advanced with M^n.
+ * h_shards is the HOST copy of the descriptor table.  No-op in dense mode. */
+int ure_mf_flush(const ure_mf_shard_t* h_shards, int n_shards, const ure_mf_hparams_t* h_hp,
                  int epochs, int64_t step_now, void* stream);
 
 /* Ensemble score of baseTest (method/utils.py:141-148):

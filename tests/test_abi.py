@@ -25,8 +25,8 @@ def test_header_symbols_are_exported_and_bound():
 
 def test_struct_layouts_match_the_header():
     from ultrare_b200 import _lib
-    assert ctypes.sizeof(_lib.MFShard) == 112 and ctypes.sizeof(_lib.MFHParams) == 32
-    assert _lib.MFShard.n.offset == 88 and _lib.MFShard.perm_seed.offset == 104
+    assert ctypes.sizeof(_lib.MFShard) == 120 and ctypes.sizeof(_lib.MFHParams) == 48
+    assert _lib.MFShard.n.offset == 96 and _lib.MFShard.perm_seed.offset == 112 and _lib.MFHParams.decay.offset == 32
 
 
 def test_sass_has_blackwell_tensor_and_bulk_copy_instructions():

@@ -303,3 +303,41 @@ def test_errors_are_loud(cuda_dev):
         kn.cost_matrix(torch.zeros((10, 12), device=cuda_dev), torch.zeros((2, 12), device=cuda_dev))   # d=12
     with pytest.raises(RuntimeError):
         kn.ensemble_score([torch.zeros((4, 16))], [torch.zeros((4, 16))], torch.zeros((1, 4), dtype=torch.int32))
+
+
+@pytest.mark.parametrize("d,K", [(16, 1), (64, 3), (128, 2)])
+def test_mf_train_lazy_equals_dense_reference_arithmetic(cuda_dev, d, K):
+    """Lazy mode (closed-form catch-up of untouched rows, M^n table) == the reference's dense optimiser:
+    tables far larger than a batch, so most rows are untouched most steps; compared with the dense NumPy
+    oracle after ure_mf_flush (weights 1e-4 abs, losses 1e-5 rel), ragged shards included."""
+    torch = _torch()
+    from ultrare_b200 import kernels as kn
+    rng = np.random.default_rng(100 + d)
+    U, I, batch, epochs = 3000, 2500, 512, 3
+    shards, host = [], []
+    for s in range(K):
+        n = 6000 + 1700 * s
+        u, i = rng.integers(0, U, n), rng.integers(0, I, n)
+        r = rng.integers(1, 6, n).astype(np.float32) / 5
+        P0 = rng.standard_normal((U, d), dtype=np.float32) * 0.3
+        Q0 = rng.standard_normal((I, d), dtype=np.float32) * 0.3
+        perms = [omf.feistel_perm(n, omf.perm_key(9, s, ep)) for ep in range(epochs)]
+        shards.append(kn.ShardState(kn.pack_interactions(u, i, r, cuda_dev), torch.tensor(P0, device=cuda_dev),
+                                    torch.tensor(Q0, device=cuda_dev), epochs, s, 9))
+        host.append((u, i, r, P0, Q0, perms))
+    sb = kn.ShardBatch(shards, d, batch, lazy=True)
+    sb.train()
+    sb.flush()
+    torch.cuda.synchronize()
+    losses = sb.train_losses()
+    for s in range(K):
+        u, i, r, P0, Q0, perms = host[s]
+        P, Q, bP, bQ, ls = omf.mf_train(P0, Q0, u, i, r, perms, batch, epochs)
+        np.testing.assert_allclose(losses[s], ls, rtol=1e-5)
+        assert np.abs(shards[s].P.cpu().numpy() - P).max() < 1e-4
+        assert np.abs(shards[s].Q.cpu().numpy() - Q).max() < 1e-4
+        assert np.abs(shards[s].bufP.cpu().numpy() - bP).max() < 1e-3
+        assert float(shards[s].gP.abs().max()) == 0.0 and float(shards[s].gQ.abs().max()) == 0.0
+        untouched = np.setdiff1d(np.arange(U), u)
+        assert len(untouched) > 0                      # rows that only ever decayed are exact too
+        assert np.abs(shards[s].P.cpu().numpy()[untouched] - P[untouched]).max() < 1e-5

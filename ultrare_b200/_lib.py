@@ -21,7 +21,7 @@ _i32, _i64, _f32, _f64 = C.c_int32, C.c_int64, C.c_float, C.c_double
 class MFShard(C.Structure):
     """ure_mf_shard_t"""
     _fields_ = [("inter", _p), ("perm", _p), ("P", _p), ("Q", _p), ("bufP", _p), ("bufQ", _p),
-                ("gP", _p), ("gQ", _p), ("sse", _p), ("lastP", _p), ("lastQ", _p),
+                ("gP", _p), ("gQ", _p), ("sse", _p), ("lastP", _p), ("lastQ", _p), ("touched", _p),
                 ("n", _i32), ("n_user", _i32), ("n_item", _i32), ("shard_id", _i32),
                 ("perm_seed", C.c_uint32), ("group", _i32)]
 
@@ -29,10 +29,11 @@ class MFShard(C.Structure):
 class MFHParams(C.Structure):
     """ure_mf_hparams_t"""
     _fields_ = [("d", _i32), ("batch", _i32), ("lr0", _f32), ("lr_decay", _f32), ("lr_step", _i32),
-                ("weight_decay", _f32), ("momentum", _f32), ("lazy", _i32)]
+                ("weight_decay", _f32), ("momentum", _f32), ("lazy", _i32), ("decay", _p), ("decay_len", _i32),
+                ("reserved", _i32)]
 
 
-assert C.sizeof(MFShard) == 112 and C.sizeof(MFHParams) == 32
+assert C.sizeof(MFShard) == 120 and C.sizeof(MFHParams) == 48
 
 # name -> (restype, argtypes); every symbol include/ultrare_b200.h declares
 SIGNATURES = {
@@ -43,7 +44,7 @@ SIGNATURES = {
     "ure_mf_train_trace": (C.c_int, [_p, _p, C.c_int, _p]),
     "ure_mf_grid_size": (C.c_int, []),
     "ure_mf_debug_flags": (C.c_int, [_p, C.c_uint32, _p]),
-    "ure_mf_flush": (C.c_int, [_p, C.c_int, C.POINTER(MFHParams), C.c_int, _i64, _p]),
+    "ure_mf_flush": (C.c_int, [C.POINTER(MFShard), C.c_int, C.POINTER(MFHParams), C.c_int, _i64, _p]),
     "ure_ensemble_score": (C.c_int, [_p, _p, C.c_int, C.c_int, _p, _i64, _f32, _p, _p, _p]),
     "ure_score_finalize": (C.c_int, [_p, _p, _i64, _f32, _p, _p, _p]),
     "ure_rank_metrics": (C.c_int, [_p, _p, _p, _p, _i64, _p, _p]),

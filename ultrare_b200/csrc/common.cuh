@@ -14,6 +14,12 @@ void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
 int num_sms();
 
+// lazy variant of the MF training step (mf_train_lazy.cu)
+int mf_train_lazy(const ure_mf_shard_t* d_shards, int n_shards, const ure_mf_hparams_t* hp, int epochs,
+                  long long step_begin, long long step_end, void* d_workspace, cudaStream_t st);
+int mf_flush_lazy(const ure_mf_shard_t* h_shards, int n_shards, const ure_mf_hparams_t* hp, int epochs,
+                  long long step_now, cudaStream_t st);
+
 #define URE_CUDA(call)                                      \
   do {                                                      \
     cudaError_t e__ = (call);                               \

@@ -424,7 +424,9 @@ extern "C" int ure_mf_train(const ure_mf_shard_t* d_shards, int n_shards, const 
               "ure_mf_train: n_shards=%d outside [1,%d]", n_shards, URE_MAX_SHARDS);
   URE_REQUIRE(h_hp->batch > 0 && h_hp->lr_step > 0 && epochs > 0, URE_EINVAL,
               "ure_mf_train: batch/lr_step/epochs must be positive");
-  URE_REQUIRE(h_hp->lazy == 0, URE_EUNSUPPORTED, "ure_mf_train: lazy mode not built in this version");
+  if (h_hp->lazy)
+    return mf_train_lazy(d_shards, n_shards, h_hp, epochs, step_begin, step_end, d_workspace,
+                         static_cast<cudaStream_t>(stream));
   URE_REQUIRE(warps_group0 >= 1 && warps_group0 <= kThreads / 32, URE_EINVAL,
               "ure_mf_train: warps_group0=%d outside [1,%d]", warps_group0, kThreads / 32);
   if (step_end <= step_begin) return 0;
@@ -470,8 +472,10 @@ extern "C" int ure_mf_debug_flags(void* d_workspace, unsigned flags, void* strea
 
 extern "C" int ure_mf_grid_size(void) { return ure::num_sms(); }
 
-extern "C" int ure_mf_flush(const ure_mf_shard_t*, int, const ure_mf_hparams_t* h_hp, int, int64_t, void*) {
-  if (h_hp && h_hp->lazy == 0) return 0;   // dense mode: every row is always current
-  ure::set_error("ure_mf_flush: lazy mode not built in this version");
-  return URE_EUNSUPPORTED;
+extern "C" int ure_mf_flush(const ure_mf_shard_t* h_shards, int n_shards, const ure_mf_hparams_t* h_hp, int epochs,
+                            int64_t step_now, void* stream) {
+  using namespace ure;
+  URE_REQUIRE(h_hp, URE_EINVAL, "ure_mf_flush: null hparams");
+  if (h_hp->lazy == 0) return 0;           // dense mode: every row is always current
+  return mf_flush_lazy(h_shards, n_shards, h_hp, epochs, step_now, static_cast<cudaStream_t>(stream));
 }

@@ -119,6 +119,7 @@ class ShardState:
         self.n = int(inter.shape[0])
         self.shard_id, self.perm_seed, self.epochs = int(shard_id), int(perm_seed) & 0xFFFFFFFF, int(epochs)
         self.group = 0
+        self.lastP = self.lastQ = self.touched = None          # lazy mode state (ShardBatch(lazy=True))
 
     def descriptor(self) -> MFShard:
         d = MFShard()
@@ -126,7 +127,9 @@ class ShardState:
         d.P, d.Q = self.P.data_ptr(), self.Q.data_ptr()
         d.bufP, d.bufQ = self.bufP.data_ptr(), self.bufQ.data_ptr()
         d.gP, d.gQ, d.sse = self.gP.data_ptr(), self.gQ.data_ptr(), self.sse.data_ptr()
-        d.lastP = d.lastQ = None
+        d.lastP = self.lastP.data_ptr() if self.lastP is not None else None
+        d.lastQ = self.lastQ.data_ptr() if self.lastQ is not None else None
+        d.touched = self.touched.data_ptr() if self.touched is not None else None
         d.n, d.n_user, d.n_item = self.n, self.P.shape[0], self.Q.shape[0]
         d.shard_id, d.perm_seed, d.group = self.shard_id, self.perm_seed, self.group
         return d
@@ -139,21 +142,39 @@ class ShardBatch:
     """All shard models a GPU owns, trained together by one persistent launch."""
 
     def __init__(self, shards: List[ShardState], d: int, batch: int, lr: float = 1e-3, lr_decay: float = 0.95,
-                 lr_step: int = 50, weight_decay: float = 0.1, momentum: float = 0.9):
+                 lr_step: int = 50, weight_decay: float = 0.1, momentum: float = 0.9, lazy: bool = False):
         if not 1 <= len(shards) <= _lib.URE_MAX_SHARDS:
             raise ValueError(f"1..{_lib.URE_MAX_SHARDS} shards per launch")
         self.shards = shards
         self.device = shards[0].P.device
         self.epochs = shards[0].epochs
         assert all(s.epochs == self.epochs for s in shards)
+        self.total_steps = max(s.steps_per_epoch(batch) for s in shards) * self.epochs
+        self.lazy = bool(lazy)
+        self.decay = None
+        if self.lazy:
+            # M^n for n = 0..total_steps (float64 on the host): the n-step gradient-free SGD update
+            # [w;buf] <- M^n [w;buf], M = [[1-lr*wd, -lr*mu],[wd, mu]]  (csrc/mf_train_lazy.cu)
+            M = np.array([[1.0 - lr * weight_decay, -lr * momentum], [weight_decay, momentum]])
+            T = np.empty((self.total_steps + 2, 2, 2))
+            T[0] = np.eye(2)
+            for n in range(1, len(T)):
+                T[n] = M @ T[n - 1]
+            self.decay = torch.from_numpy(T.reshape(-1, 4).astype(np.float32)).to(self.device)
+            for s in shards:
+                s.lastP = torch.zeros(s.P.shape[0], dtype=torch.int32, device=self.device)
+                s.lastQ = torch.zeros(s.Q.shape[0], dtype=torch.int32, device=self.device)
+                s.touched = torch.zeros(4 * (1 + batch), dtype=torch.int32, device=self.device)
         self.hp = MFHParams(d=d, batch=batch, lr0=lr, lr_decay=lr_decay, lr_step=lr_step,
-                            weight_decay=weight_decay, momentum=momentum, lazy=0)
+                            weight_decay=weight_decay, momentum=momentum, lazy=int(self.lazy),
+                            decay=self.decay.data_ptr() if self.lazy else None,
+                            decay_len=len(self.decay) if self.lazy else 0, reserved=0)
         self.warps_group0 = self._split_groups(shards)
         arr = (MFShard * len(shards))(*[s.descriptor() for s in shards])
+        self.host_table = arr
         host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
         self.table = host.to(self.device)
         self.ws = torch.zeros(int(_lib.lib().ure_mf_train_workspace_bytes()), dtype=torch.uint8, device=self.device)
-        self.total_steps = max(s.steps_per_epoch(batch) for s in shards) * self.epochs
         self.step = 0
 
     @staticmethod
@@ -182,6 +203,13 @@ class ShardBatch:
                                           self.step, step_end, self.warps_group0, _ptr(self.ws), _stream()),
                   "ure_mf_train")
         self.step = step_end
+
+    def flush(self) -> None:
+        """Lazy mode: advance every row to the current step (call before reading P / Q)."""
+        if self.lazy:
+            with torch.cuda.device(self.device):
+                check(_lib.lib().ure_mf_flush(self.host_table, len(self.shards), C.byref(self.hp), self.epochs,
+                                              self.step, _stream()), "ure_mf_flush")
 
     def interactions_trained(self) -> int:
         return sum(s.n for s in self.shards) * self.epochs

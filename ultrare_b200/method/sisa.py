@@ -57,6 +57,29 @@ class _RemoteModel:
         self.item_mat = None
 
 
+_OWNER_CACHE = {}
+
+
+def _owner_maps(group_index, n_user, device):
+    """owner[u] = group of user u (-1: none), row_of[u] = its row in the group's compact table; numpy + device
+    copies, cached per group_index object (learn / unlearn / repeated requests reuse the same grouping)."""
+    key = (id(group_index), n_user, str(device))
+    hit = _OWNER_CACHE.get(key)
+    if hit is not None and hit[0] is group_index:
+        return hit[1:]
+    owner = np.full(n_user, -1, dtype=np.int32)
+    row_of = np.zeros(n_user, dtype=np.int32)
+    for g in range(len(group_index) - 1, -1, -1):              # a user belongs to the FIRST group listing it
+        ids = np.asarray(group_index[g], dtype=np.int64)
+        owner[ids] = g
+        row_of[ids] = np.arange(len(ids), dtype=np.int32)
+    out = (owner, row_of, torch.from_numpy(owner).to(device), torch.from_numpy(row_of).to(device))
+    if len(_OWNER_CACHE) > 8:
+        _OWNER_CACHE.clear()
+    _OWNER_CACHE[key] = (group_index,) + out
+    return out
+
+
 def _local(models):
     return [m for m in models if m is not None and getattr(m, 'item_mat', None) is not None]
 
@@ -69,15 +92,7 @@ class Sisa(Scratch):
         self.model_list = []
         self.epoch_eval = os.environ.get('ULTRARE_EPOCH_EVAL', 'faithful')
         self.dist = udist.get()
-        owner = np.full(self.n_user, -1, dtype=np.int32)
-        row_of = np.zeros(self.n_user, dtype=np.int32)
-        for g in range(len(group_index) - 1, -1, -1):          # a user belongs to the FIRST group listing it
-            ids = np.asarray(group_index[g], dtype=np.int64)
-            owner[ids] = g
-            row_of[ids] = np.arange(len(ids), dtype=np.int32)
-        self._owner_np, self._row_of_np = owner, row_of
-        self._owner = torch.from_numpy(owner).to(self.device)
-        self._row_of = torch.from_numpy(row_of).to(self.device)
+        self._owner_np, self._row_of_np, self._owner, self._row_of = _owner_maps(group_index, self.n_user, self.device)
         self._group_rows = {}
         self.retrain_gid = set()
         self.timing = {}

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define URE_ABI_VERSION 1
+#define URE_ABI_VERSION 2
 #define URE_MAX_SHARDS 256        /* shard models batched in one launch           */
 #define URE_TOP_K 10              /* baseTest(top_k=10), method/utils.py:115      */
 
@@ -58,6 +58,12 @@ typedef struct {
   int32_t* lastP;           /* lazy mode only: [n_user] steps applied to each row (bit 31: touched flag) */
   int32_t* lastQ;           /* lazy mode only: [n_item]                                    */
   int32_t* touched;         /* lazy mode only: [2][2][1 + batch] per step parity and table: count, row list */
+  ure_inter_t* inter_u;     /* owner mode only: [n] records sorted by user, pad = index in `inter`          */
+  ure_inter_t* inter_i;     /* owner mode only: [n] records sorted by item, pad = index in `inter`          */
+  int32_t* off_u;           /* owner mode only: [n_user + 2] row offsets into inter_u (zero on entry of     */
+                            /*    ure_mf_owner_prepare; entries 0..n_user valid afterwards)                 */
+  int32_t* off_i;           /* owner mode only: [n_item + 2]                                                */
+  int32_t* perm_inv;        /* owner mode with explicit `perm`: [n_epochs_total][n] inverse visiting orders */
   int32_t n;                /* interactions in the shard                                   */
   int32_t n_user;           /* rows of P                                                   */
   int32_t n_item;           /* rows of Q                                                   */
@@ -74,13 +80,25 @@ typedef struct {
   int32_t lr_step;      /* StepLR step_size = 50 epochs (scratch.py:69)                      */
   float weight_decay;   /* config.py:20 lam                                                  */
   float momentum;       /* config.py:29                                                      */
-  int32_t lazy;         /* 0: dense sweep every step (reference arithmetic, bit-faithful     */
-                        /*    order); 1: closed-form catch-up of untouched rows  */
+  int32_t mode;         /* URE_MF_DENSE / URE_MF_LAZY / URE_MF_OWNER (below)                 */
   const float* decay;   /* lazy: DEVICE table [decay_len][4] of M^n = (a11,a12,a21,a22), the */
                         /*    n-step gradient-free update [w;buf] <- M^n [w;buf]; else NULL   */
   int32_t decay_len;    /* lazy: number of table entries (>= total steps + 1)                */
-  int32_t reserved;
+  int32_t owner_smem;   /* OWNER: dynamic shared-memory bytes planned by ure_mf_owner_prepare */
 } ure_mf_hparams_t;
+
+/* ure_mf_hparams_t::mode -- three schedules of the SAME arithmetic (baseTrain + dense optim.SGD):
+ *   DENSE  gradients scattered with L2 vector atomics, then a dense sweep; two grid barriers per step.
+ *   LAZY   closed-form catch-up of untouched rows (M^n table) instead of the dense sweep.
+ *   OWNER  owner-computes: every CTA owns a slice of user rows and a slice of item rows of ONE shard
+ *          (weights + momentum resident in shared memory), walks its own interactions of the batch from
+ *          the user-sorted and the item-sorted copy of the records, accumulates row gradients in
+ *          registers (no atomics, no gradient arrays) and applies the SGD update in the same pass;
+ *          weights are published double-buffered (P/Q and gP/gQ alternate) so one barrier per step
+ *          among the shard's CTAs suffices.  Needs ure_mf_owner_prepare and n_shards <= #SMs. */
+#define URE_MF_DENSE 0
+#define URE_MF_LAZY 1
+#define URE_MF_OWNER 2
 
 const char* ure_last_error(void);
 int ure_abi_version(void);
@@ -99,6 +117,15 @@ int64_t ure_mf_train_workspace_bytes(void);
 int ure_mf_train(const ure_mf_shard_t* d_shards, int n_shards, const ure_mf_hparams_t* h_hp,
                  int epochs, int64_t step_begin, int64_t step_end, int warps_group0,
                  void* d_workspace, void* stream);
+
+/* Owner mode set-up, once per shard table (asynchronous, no host sync): builds inter_u / inter_i /
+ * off_u / off_i (counting sort of the records by user and by item) and perm_inv for shards with an
+ * explicit perm, then plans the CTA ownership and writes into the first 16 bytes of d_workspace
+ * int32 {shared-memory bytes the busiest CTA needs, bytes available, max rows per CTA, max
+ * interactions per CTA}: the caller reads them back once and must not start mode OWNER when
+ * need > available (ure_mf_train refuses it loudly on the next call as well). */
+int ure_mf_owner_prepare(const ure_mf_shard_t* d_shards, int n_shards, const ure_mf_hparams_t* h_hp,
+                         int epochs, void* d_workspace, void* stream);
 
 /* Diagnostics (tracing): record six SM-clock stamps per CTA and step -- step start, tables ready,
  * gradients issued, barrier 1 passed, sweep issued, barrier 2 passed -- for the first `steps` steps of

@@ -32,15 +32,20 @@ def _shard(K, toy, dev, epochs, batch, explicit_perm, seeds, shard_ids=None, dat
     return shards, host
 
 
+MODES = ["dense", "owner"]
+
+
+@pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("explicit_perm", [True, False])
-def test_mf_train_vs_reference_golden(toy, cuda_dev, explicit_perm):
+def test_mf_train_vs_reference_golden(toy, cuda_dev, explicit_perm, mode):
     """ure_mf_train == reference baseTrain (+SGD/StepLR): losses 1e-3 rel, weights 1e-4 abs (Appendix E)."""
     torch = _torch()
     from ultrare_b200 import kernels as kn
     z = load_gold("toy_train.npz")
     epochs, batch = int(z["epochs"]), int(z["batch"])
     shards, _ = _shard(1, toy, cuda_dev, epochs, batch, explicit_perm, [int(z["weight_seed"])])
-    sb = kn.ShardBatch(shards, toy["k"], batch)
+    sb = kn.ShardBatch(shards, toy["k"], batch, mode=mode)
+    assert sb.mode == mode
     sb.train()
     torch.cuda.synchronize()
     losses = sb.train_losses()[0]
@@ -51,12 +56,13 @@ def test_mf_train_vs_reference_golden(toy, cuda_dev, explicit_perm):
     assert float(shards[0].gP.abs().max()) == 0.0 and float(shards[0].gQ.abs().max()) == 0.0
 
 
-def test_mf_train_epoch_by_epoch_equals_single_launch(toy, cuda_dev):
+@pytest.mark.parametrize("mode", MODES)
+def test_mf_train_epoch_by_epoch_equals_single_launch(toy, cuda_dev, mode):
     torch = _torch()
     from ultrare_b200 import kernels as kn
     a, _ = _shard(1, toy, cuda_dev, 2, 3000, False, [7])
     b, _ = _shard(1, toy, cuda_dev, 2, 3000, False, [7])
-    sa, sb = kn.ShardBatch(a, 16, 3000), kn.ShardBatch(b, 16, 3000)
+    sa, sb = kn.ShardBatch(a, 16, 3000, mode=mode), kn.ShardBatch(b, 16, 3000, mode=mode)
     sa.train()
     spe = b[0].steps_per_epoch(3000)
     for t in range(1, 2 * spe + 1):
@@ -67,7 +73,8 @@ def test_mf_train_epoch_by_epoch_equals_single_launch(toy, cuda_dev):
     np.testing.assert_allclose(sa.train_losses()[0], sb.train_losses()[0], rtol=1e-6)
 
 
-def test_mf_train_k_shards_batched_vs_oracle(toy, cuda_dev):
+@pytest.mark.parametrize("mode", MODES)
+def test_mf_train_k_shards_batched_vs_oracle(toy, cuda_dev, mode):
     """K ragged shards in ONE launch (different sizes => different steps/epoch) == K oracle trainings."""
     torch = _torch()
     from ultrare_b200 import kernels as kn
@@ -81,7 +88,7 @@ def test_mf_train_k_shards_batched_vs_oracle(toy, cuda_dev):
         data.append((u[loc], i[loc], r32[loc]))
     shards, host = _shard(K, toy, cuda_dev, epochs, batch, False, [11, 12, 13], data=data)
     assert len({sh.steps_per_epoch(batch) for sh in shards}) > 1
-    sb = kn.ShardBatch(shards, toy["k"], batch)
+    sb = kn.ShardBatch(shards, toy["k"], batch, mode=mode)
     sb.train()
     torch.cuda.synchronize()
     losses = sb.train_losses()
@@ -93,8 +100,9 @@ def test_mf_train_k_shards_batched_vs_oracle(toy, cuda_dev):
         assert np.abs(shards[s].Q.cpu().numpy() - Q).max() < 1e-4
 
 
+@pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("d", [8, 32, 64, 128])
-def test_mf_train_other_dims_vs_oracle(cuda_dev, d):
+def test_mf_train_other_dims_vs_oracle(cuda_dev, d, mode):
     torch = _torch()
     from ultrare_b200 import kernels as kn
     rng = np.random.default_rng(d)
@@ -106,7 +114,7 @@ def test_mf_train_other_dims_vs_oracle(cuda_dev, d):
     perms = [omf.feistel_perm(n, omf.perm_key(9, 0, ep)) for ep in range(epochs)]
     sh = kn.ShardState(kn.pack_interactions(u, i, r, cuda_dev), torch.tensor(P0, device=cuda_dev),
                        torch.tensor(Q0, device=cuda_dev), epochs, 0, 9)
-    sb = kn.ShardBatch([sh], d, batch)
+    sb = kn.ShardBatch([sh], d, batch, mode=mode)
     sb.train()
     P, Q, _, _, ls = omf.mf_train(P0, Q0, u, i, r, perms, batch, epochs)
     np.testing.assert_allclose(sb.train_losses()[0], ls, rtol=1e-5)
@@ -341,3 +349,71 @@ def test_mf_train_lazy_equals_dense_reference_arithmetic(cuda_dev, d, K):
         untouched = np.setdiff1d(np.arange(U), u)
         assert len(untouched) > 0                      # rows that only ever decayed are exact too
         assert np.abs(shards[s].P.cpu().numpy()[untouched] - P[untouched]).max() < 1e-5
+
+
+def test_mf_owner_prepare_sorts_and_inverts(cuda_dev):
+    """ure_mf_owner_prepare: the user-sorted / item-sorted record copies are permutations of the shard's records
+    grouped by row (pad = original index), the offsets are the row histograms' prefix sums, perm_inv inverts perm."""
+    torch = _torch()
+    from ultrare_b200 import kernels as kn
+    rng = np.random.default_rng(5)
+    U, I, n, epochs = 70, 90, 4000, 2
+    u, i = rng.integers(0, U, n), rng.integers(0, I - 7, n)        # items I-7.. never occur: empty trailing rows
+    r = rng.integers(1, 6, n).astype(np.float32) / 5
+    perm = np.stack([rng.permutation(n) for _ in range(epochs)]).astype(np.int32)
+    st = kn.ShardState(kn.pack_interactions(u, i, r, cuda_dev), torch.zeros((U, 16), device=cuda_dev),
+                       torch.zeros((I, 16), device=cuda_dev), epochs, perm=torch.tensor(perm, device=cuda_dev))
+    sb = kn.ShardBatch([st], 16, 512, mode="owner")
+    torch.cuda.synchronize()
+    for rec, off, key, rows in ((st.inter_u, st.off_u, u, U), (st.inter_i, st.off_i, i, I)):
+        rec, off = rec.cpu().numpy(), off.cpu().numpy()
+        assert np.array_equal(off[:rows + 1], np.concatenate([[0], np.cumsum(np.bincount(key, minlength=rows))]))
+        assert np.array_equal(np.sort(rec[:, 3]), np.arange(n))
+        j = rec[:, 3]
+        assert np.array_equal(rec[:, 0], u[j]) and np.array_equal(rec[:, 1], i[j])
+        assert np.array_equal(rec[:, 2].view(np.float32), r[j])
+        col = rec[:, 0] if key is u else rec[:, 1]
+        assert np.all(np.diff(col) >= 0)
+    inv = st.perm_inv.cpu().numpy()
+    for e in range(epochs):
+        assert np.array_equal(inv[e][perm[e]], np.arange(n))
+    assert sb.owner_plan["smem_need"] <= sb.owner_plan["smem_avail"]
+
+
+def test_mf_owner_skewed_rows_many_shards_vs_oracle(cuda_dev):
+    """Owner schedule on ragged shards with heavy rows (one user / one item holding a large share of a shard, rows
+    split over many chunks and CTAs with no rows at all), more steps per epoch than a chunk window, empty shard."""
+    torch = _torch()
+    from ultrare_b200 import kernels as kn
+    rng = np.random.default_rng(77)
+    d, batch, epochs, K = 16, 257, 2, 7
+    shards, host = [], []
+    for s in range(K):
+        U, I = 40 + 13 * s, 55 + 9 * s
+        n = 0 if s == 3 else 3000 + 2500 * s
+        u, i = rng.integers(0, U, n), rng.integers(0, I, n)
+        if n:
+            u[rng.random(n) < 0.4] = 3                  # a user with 40 % of the shard
+            i[rng.random(n) < 0.3] = 5
+        r = rng.integers(1, 6, n).astype(np.float32) / 5
+        P0 = rng.standard_normal((U, d), dtype=np.float32) * 0.3
+        Q0 = rng.standard_normal((I, d), dtype=np.float32) * 0.3
+        perms = [omf.feistel_perm(n, omf.perm_key(9, s, ep)) for ep in range(epochs)] if n else []
+        shards.append(kn.ShardState(kn.pack_interactions(u, i, r, cuda_dev), torch.tensor(P0, device=cuda_dev),
+                                    torch.tensor(Q0, device=cuda_dev), epochs, s, 9))
+        host.append((u, i, r, P0, Q0, perms))
+    sb = kn.ShardBatch(shards, d, batch, mode="owner")
+    sb.train()
+    torch.cuda.synchronize()
+    losses = sb.train_losses()
+    for s in range(K):
+        u, i, r, P0, Q0, perms = host[s]
+        if len(u) == 0:
+            assert np.array_equal(shards[s].P.cpu().numpy(), P0)
+            continue
+        P, Q, bP, bQ, ls = omf.mf_train(P0, Q0, u, i, r, perms, batch, epochs)
+        np.testing.assert_allclose(losses[s], ls, rtol=1e-5)
+        assert np.abs(shards[s].P.cpu().numpy() - P).max() < 1e-4
+        assert np.abs(shards[s].Q.cpu().numpy() - Q).max() < 1e-4
+        assert np.abs(shards[s].bufQ.cpu().numpy() - bQ).max() < 1e-3
+        assert float(shards[s].gP.abs().max()) == 0.0 and float(shards[s].gQ.abs().max()) == 0.0

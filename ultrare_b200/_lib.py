@@ -22,6 +22,7 @@ class MFShard(C.Structure):
     """ure_mf_shard_t"""
     _fields_ = [("inter", _p), ("perm", _p), ("P", _p), ("Q", _p), ("bufP", _p), ("bufQ", _p),
                 ("gP", _p), ("gQ", _p), ("sse", _p), ("lastP", _p), ("lastQ", _p), ("touched", _p),
+                ("inter_u", _p), ("inter_i", _p), ("off_u", _p), ("off_i", _p), ("perm_inv", _p),
                 ("n", _i32), ("n_user", _i32), ("n_item", _i32), ("shard_id", _i32),
                 ("perm_seed", C.c_uint32), ("group", _i32)]
 
@@ -29,11 +30,13 @@ class MFShard(C.Structure):
 class MFHParams(C.Structure):
     """ure_mf_hparams_t"""
     _fields_ = [("d", _i32), ("batch", _i32), ("lr0", _f32), ("lr_decay", _f32), ("lr_step", _i32),
-                ("weight_decay", _f32), ("momentum", _f32), ("lazy", _i32), ("decay", _p), ("decay_len", _i32),
-                ("reserved", _i32)]
+                ("weight_decay", _f32), ("momentum", _f32), ("mode", _i32), ("decay", _p), ("decay_len", _i32),
+                ("owner_smem", _i32)]
 
 
-assert C.sizeof(MFShard) == 120 and C.sizeof(MFHParams) == 48
+MF_DENSE, MF_LAZY, MF_OWNER = 0, 1, 2
+
+assert C.sizeof(MFShard) == 160 and C.sizeof(MFHParams) == 48
 
 # name -> (restype, argtypes); every symbol include/ultrare_b200.h declares
 SIGNATURES = {
@@ -41,6 +44,7 @@ SIGNATURES = {
     "ure_abi_version": (C.c_int, []),
     "ure_mf_train_workspace_bytes": (_i64, []),
     "ure_mf_train": (C.c_int, [_p, C.c_int, C.POINTER(MFHParams), C.c_int, _i64, _i64, C.c_int, _p, _p]),
+    "ure_mf_owner_prepare": (C.c_int, [_p, C.c_int, C.POINTER(MFHParams), C.c_int, _p, _p]),
     "ure_mf_train_trace": (C.c_int, [_p, _p, C.c_int, _p]),
     "ure_mf_grid_size": (C.c_int, []),
     "ure_mf_debug_flags": (C.c_int, [_p, C.c_uint32, _p]),
@@ -81,7 +85,7 @@ def lib() -> C.CDLL:
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(handle, name)           # AttributeError if the .so lacks a declared symbol
         fn.restype, fn.argtypes = res, args
-    if handle.ure_abi_version() != 1:
+    if handle.ure_abi_version() != 2:
         raise RuntimeError("ultrare_b200: ABI version mismatch; rebuild the shared library")
     _lib = handle
     return handle

@@ -20,6 +20,12 @@ int mf_train_lazy(const ure_mf_shard_t* d_shards, int n_shards, const ure_mf_hpa
 int mf_flush_lazy(const ure_mf_shard_t* h_shards, int n_shards, const ure_mf_hparams_t* hp, int epochs,
                   long long step_now, cudaStream_t st);
 
+// owner-computes variant (mf_train_owner.cu)
+int mf_train_owner(const ure_mf_shard_t* d_shards, int n_shards, const ure_mf_hparams_t* hp, int epochs,
+                   long long step_begin, long long step_end, void* d_workspace, cudaStream_t st);
+int64_t mf_owner_workspace_bytes();
+void mf_owner_debug(unsigned flags);
+
 #define URE_CUDA(call)                                      \
   do {                                                      \
     cudaError_t e__ = (call);                               \

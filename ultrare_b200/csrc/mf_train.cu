@@ -413,7 +413,10 @@ int launch(const ure_mf_shard_t* d_shards, int K, const ure_mf_hparams_t& hp, in
 }  // namespace
 }  // namespace ure
 
-extern "C" int64_t ure_mf_train_workspace_bytes(void) { return (int64_t)sizeof(ure::Workspace); }
+extern "C" int64_t ure_mf_train_workspace_bytes(void) {
+  const int64_t a = (int64_t)sizeof(ure::Workspace), b = ure::mf_owner_workspace_bytes();
+  return a > b ? a : b;
+}
 
 extern "C" int ure_mf_train(const ure_mf_shard_t* d_shards, int n_shards, const ure_mf_hparams_t* h_hp,
                             int epochs, int64_t step_begin, int64_t step_end, int warps_group0,
@@ -424,7 +427,12 @@ extern "C" int ure_mf_train(const ure_mf_shard_t* d_shards, int n_shards, const 
               "ure_mf_train: n_shards=%d outside [1,%d]", n_shards, URE_MAX_SHARDS);
   URE_REQUIRE(h_hp->batch > 0 && h_hp->lr_step > 0 && epochs > 0, URE_EINVAL,
               "ure_mf_train: batch/lr_step/epochs must be positive");
-  if (h_hp->lazy)
+  URE_REQUIRE(h_hp->mode >= URE_MF_DENSE && h_hp->mode <= URE_MF_OWNER, URE_EINVAL, "ure_mf_train: mode=%d unknown",
+              h_hp->mode);
+  if (h_hp->mode == URE_MF_OWNER)
+    return mf_train_owner(d_shards, n_shards, h_hp, epochs, step_begin, step_end, d_workspace,
+                          static_cast<cudaStream_t>(stream));
+  if (h_hp->mode == URE_MF_LAZY)
     return mf_train_lazy(d_shards, n_shards, h_hp, epochs, step_begin, step_end, d_workspace,
                          static_cast<cudaStream_t>(stream));
   URE_REQUIRE(warps_group0 >= 1 && warps_group0 <= kThreads / 32, URE_EINVAL,
@@ -464,6 +472,7 @@ extern "C" int ure_mf_debug_flags(void* d_workspace, unsigned flags, void* strea
   URE_REQUIRE(d_workspace, URE_EINVAL, "ure_mf_debug_flags: null workspace");
   auto* ws = static_cast<Workspace*>(d_workspace);
   g_force_warps_g0 = (int)((flags >> 8) & 63u) ? (int)((flags >> 8) & 63u) : -1;
+  mf_owner_debug(flags);
   URE_CUDA(cudaMemcpyAsync(&ws->debug_flags, &flags, sizeof(flags), cudaMemcpyHostToDevice,
                            static_cast<cudaStream_t>(stream)));
   URE_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
@@ -476,6 +485,6 @@ extern "C" int ure_mf_flush(const ure_mf_shard_t* h_shards, int n_shards, const 
                             int64_t step_now, void* stream) {
   using namespace ure;
   URE_REQUIRE(h_hp, URE_EINVAL, "ure_mf_flush: null hparams");
-  if (h_hp->lazy == 0) return 0;           // dense mode: every row is always current
+  if (h_hp->mode != URE_MF_LAZY) return 0;   // dense / owner schedules: every row is always current
   return mf_flush_lazy(h_shards, n_shards, h_hp, epochs, step_now, static_cast<cudaStream_t>(stream));
 }

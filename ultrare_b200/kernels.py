@@ -95,6 +95,9 @@ def pointer_table(tensors: Sequence[torch.Tensor], device) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------------ MF training
+DEFAULT_MF_MODE = "auto"       # schedule ShardBatch picks when the caller does not say (see ShardBatch)
+
+
 class ShardState:
     """Device state of one shard model: what Scratch.train builds (scratch.py:59,65-69)."""
 
@@ -119,7 +122,8 @@ class ShardState:
         self.n = int(inter.shape[0])
         self.shard_id, self.perm_seed, self.epochs = int(shard_id), int(perm_seed) & 0xFFFFFFFF, int(epochs)
         self.group = 0
-        self.lastP = self.lastQ = self.touched = None          # lazy mode state (ShardBatch(lazy=True))
+        self.lastP = self.lastQ = self.touched = None          # lazy mode state (ShardBatch(mode="lazy"))
+        self.inter_u = self.inter_i = self.off_u = self.off_i = self.perm_inv = None   # owner mode state
 
     def descriptor(self) -> MFShard:
         d = MFShard()
@@ -130,6 +134,9 @@ class ShardState:
         d.lastP = self.lastP.data_ptr() if self.lastP is not None else None
         d.lastQ = self.lastQ.data_ptr() if self.lastQ is not None else None
         d.touched = self.touched.data_ptr() if self.touched is not None else None
+        for name in ("inter_u", "inter_i", "off_u", "off_i", "perm_inv"):
+            t = getattr(self, name)
+            setattr(d, name, t.data_ptr() if t is not None else None)
         d.n, d.n_user, d.n_item = self.n, self.P.shape[0], self.Q.shape[0]
         d.shard_id, d.perm_seed, d.group = self.shard_id, self.perm_seed, self.group
         return d
@@ -139,18 +146,34 @@ class ShardState:
 
 
 class ShardBatch:
-    """All shard models a GPU owns, trained together by one persistent launch."""
+    """All shard models a GPU owns, trained together by one persistent launch.
+
+    mode: "dense" (L2-atomic scatter + dense sweep), "lazy" (closed-form catch-up of untouched rows),
+    "owner" (owner-computes, weights resident in shared memory: small tables only) or "auto" = owner when
+    its plan fits the shared memory of the SMs, else dense.  The three schedules compute the same update."""
 
     def __init__(self, shards: List[ShardState], d: int, batch: int, lr: float = 1e-3, lr_decay: float = 0.95,
-                 lr_step: int = 50, weight_decay: float = 0.1, momentum: float = 0.9, lazy: bool = False):
+                 lr_step: int = 50, weight_decay: float = 0.1, momentum: float = 0.9, lazy: bool = False,
+                 mode: Optional[str] = None):
         if not 1 <= len(shards) <= _lib.URE_MAX_SHARDS:
             raise ValueError(f"1..{_lib.URE_MAX_SHARDS} shards per launch")
+        mode = ("lazy" if lazy else DEFAULT_MF_MODE) if mode is None else mode
+        if mode not in ("dense", "lazy", "owner", "auto"):
+            raise ValueError(f"mode {mode!r}")
         self.shards = shards
         self.device = shards[0].P.device
         self.epochs = shards[0].epochs
         assert all(s.epochs == self.epochs for s in shards)
         self.total_steps = max(s.steps_per_epoch(batch) for s in shards) * self.epochs
-        self.lazy = bool(lazy)
+        self.ws = torch.zeros(int(_lib.lib().ure_mf_train_workspace_bytes()), dtype=torch.uint8, device=self.device)
+        self.hp = MFHParams(d=d, batch=batch, lr0=lr, lr_decay=lr_decay, lr_step=lr_step,
+                            weight_decay=weight_decay, momentum=momentum, mode=_lib.MF_DENSE,
+                            decay=None, decay_len=0, owner_smem=0)
+        self.owner_plan = None
+        if mode in ("owner", "auto"):
+            mode = self._prepare_owner(mode == "owner")
+        self.mode = mode
+        self.lazy = mode == "lazy"
         self.decay = None
         if self.lazy:
             # M^n for n = 0..total_steps (float64 on the host): the n-step gradient-free SGD update
@@ -165,17 +188,54 @@ class ShardBatch:
                 s.lastP = torch.zeros(s.P.shape[0], dtype=torch.int32, device=self.device)
                 s.lastQ = torch.zeros(s.Q.shape[0], dtype=torch.int32, device=self.device)
                 s.touched = torch.zeros(4 * (1 + batch), dtype=torch.int32, device=self.device)
-        self.hp = MFHParams(d=d, batch=batch, lr0=lr, lr_decay=lr_decay, lr_step=lr_step,
-                            weight_decay=weight_decay, momentum=momentum, lazy=int(self.lazy),
-                            decay=self.decay.data_ptr() if self.lazy else None,
-                            decay_len=len(self.decay) if self.lazy else 0, reserved=0)
+            self.hp.mode, self.hp.decay, self.hp.decay_len = _lib.MF_LAZY, self.decay.data_ptr(), len(self.decay)
         self.warps_group0 = self._split_groups(shards)
-        arr = (MFShard * len(shards))(*[s.descriptor() for s in shards])
-        self.host_table = arr
-        host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
-        self.table = host.to(self.device)
-        self.ws = torch.zeros(int(_lib.lib().ure_mf_train_workspace_bytes()), dtype=torch.uint8, device=self.device)
+        self._upload_table()
         self.step = 0
+
+    def _upload_table(self):
+        arr = (MFShard * len(self.shards))(*[s.descriptor() for s in self.shards])
+        self.host_table = arr
+        self.table = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(self.device)
+
+    def _prepare_owner(self, required: bool) -> str:
+        """Owner-mode set-up: one allocation for the sorted record copies + row offsets of every shard,
+        ure_mf_owner_prepare (counting sorts + CTA plan), one 16-byte read-back of the plan."""
+        L = _lib.lib()
+        shards, dev = self.shards, self.device
+        if len(shards) > int(L.ure_mf_grid_size()):
+            if required:
+                raise RuntimeError("owner mode needs at most one shard per SM")
+            return "dense"
+        n_tot = sum(s.n for s in shards)
+        rec = torch.empty((2, max(1, n_tot), 4), dtype=torch.int32, device=dev)
+        n_off = sum(s.P.shape[0] + s.Q.shape[0] + 4 for s in shards)
+        off = torch.zeros(n_off, dtype=torch.int32, device=dev)
+        o = r = 0
+        for s in shards:
+            s.inter_u, s.inter_i = rec[0, r:r + s.n], rec[1, r:r + s.n]
+            r += s.n
+            nu, ni = s.P.shape[0] + 2, s.Q.shape[0] + 2
+            s.off_u, s.off_i = off[o:o + nu], off[o + nu:o + nu + ni]
+            o += nu + ni
+            s.perm_inv = torch.empty_like(s.perm) if s.perm is not None else None
+        self._owner_keep = (rec, off)
+        self._upload_table()
+        with torch.cuda.device(dev):
+            check(L.ure_mf_owner_prepare(_ptr(self.table), len(shards), C.byref(self.hp), self.epochs, _ptr(self.ws),
+                                         _stream()), "ure_mf_owner_prepare")
+        need, avail, max_rows, max_slots = self.ws[:16].view(torch.int32).tolist()      # the one sync of the set-up
+        self.owner_plan = {"smem_need": need, "smem_avail": avail, "max_rows_per_cta": max_rows,
+                           "max_slots_per_cta": max_slots}
+        if need > avail:
+            if required:
+                raise RuntimeError(f"owner mode: the busiest CTA needs {need} B of shared memory, {avail} B available")
+            for s in shards:
+                s.inter_u = s.inter_i = s.off_u = s.off_i = s.perm_inv = None
+            self._owner_keep = None
+            return "dense"
+        self.hp.mode, self.hp.owner_smem = _lib.MF_OWNER, need
+        return "owner"
 
     @staticmethod
     def _split_groups(shards, total_warps: int = 32, min_warps: int = 6) -> int:

@@ -44,7 +44,16 @@ def perm_key(seed: int, shard: int, epoch: int) -> int:
     return k
 
 
-FEISTEL_ROUNDS = 6
+FEISTEL_ROUNDS = 4
+
+
+def round_hash(x):
+    """Round function of the Feistel network (csrc/feistel.cuh round_hash): two multiplies, one xor-shift."""
+    x = np.asarray(x, dtype=np.uint64) & 0xFFFFFFFF
+    x = (x * 0x9E3779B1) & 0xFFFFFFFF
+    x ^= x >> 15
+    x = (x * 0x85EBCA6B) & 0xFFFFFFFF
+    return x
 
 
 def feistel_domain(n: int):
@@ -58,7 +67,7 @@ def feistel_domain(n: int):
 def feistel_perm(n: int, key: int) -> np.ndarray:
     """perm[j] for j in [0,n): the position-j element of the epoch's shuffled order.
 
-    6-round alternating Feistel over x = L*b + R, cycle-walked into [0,n)
+    4-round alternating Feistel over x = L*b + R, cycle-walked into [0,n)
     (ultrare_b200/csrc/feistel.cuh)."""
     if n <= 1:
         return np.zeros(n, dtype=np.int64)
@@ -72,10 +81,10 @@ def feistel_perm(n: int, key: int) -> np.ndarray:
         R = x - L * b
         for r in range(FEISTEL_ROUNDS):
             if r % 2 == 0:
-                L = L + ((mix32(R ^ rk[r]) * a) >> 32)
+                L = L + ((round_hash(R ^ rk[r]) * a) >> 32)
                 L = np.where(L >= a, L - a, L)
             else:
-                R = R + ((mix32(L ^ rk[r]) * b) >> 32)
+                R = R + ((round_hash(L ^ rk[r]) * b) >> 32)
                 R = np.where(R >= b, R - b, R)
         x = L * b + R
         done = x < n

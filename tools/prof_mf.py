@@ -16,6 +16,8 @@ ap.add_argument("--epochs", type=int, default=10)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--batch", type=int, default=30000)
 ap.add_argument("--k", type=int, default=5)
+ap.add_argument("--mode", default="owner", choices=["dense", "owner"])
+ap.add_argument("--trace", action="store_true", help="dense schedule only: per-phase SM-clock stamps")
 args = ap.parse_args()
 
 dev = torch.device("cuda:0")
@@ -38,7 +40,8 @@ for g, ids in enumerate(groups):
     P = torch.empty((len(ids), d), device=dev).normal_(generator=gen)
     Q = torch.empty((I, d), device=dev).normal_(generator=gen)
     shards.append(kn.ShardState(inter, P, Q, args.epochs, shard_id=g + 1, perm_seed=42))
-sb = kn.ShardBatch(shards, d, args.batch)
+sb = kn.ShardBatch(shards, d, args.batch, mode=args.mode)
+print("mode", sb.mode, "plan", sb.owner_plan)
 n_inter = sum(s.n for s in shards) * args.epochs
 for rep in range(args.reps):
     for s in shards:
@@ -55,7 +58,10 @@ for rep in range(args.reps):
           f"{n_inter / ms / 1e6:.2f} G inter/s, {n_inter * 268 / ms / 1e6:.1f} GB/s algorithmic")
 print("losses", [float(x[-1]) for x in sb.train_losses()])
 
-ap2 = None
+if not args.trace:
+    sys.exit(0)
+
+
 def run_trace(flags, label):
     print("====", label)
     L = _lib.lib()
@@ -72,7 +78,8 @@ def run_trace(flags, label):
     _lib.check(L.ure_mf_debug_flags(C.c_void_p(sb.ws.data_ptr()), 0, None))
     tr = trace.cpu().numpy().astype(np.float64)[5:]          # skip cold steps
     d = np.diff(tr, axis=2)                                   # [steps, grid, 5]
-    names = ["stamp0-1", "stamp1-2", "stamp2-3", "stamp3-4", "stamp4-5"]
+    names = (["scan + waves (warp 1)", "other warps", "boundary + sweep", "arrive + step_of slice", "barrier wait"] if args.mode == "owner" else
+             ["gradients", "overlap1", "wait1", "sweep", "arr2+fetch+wait2"])
     print("per-phase SM cycles (median over CTAs and steps / p95 / max):")
     for k, nm in enumerate(names):
         x = d[:, :, k].ravel()
@@ -91,5 +98,9 @@ def run_trace(flags, label):
 
 import ctypes as C
 from ultrare_b200 import _lib
-for flags, label in ((0, "two warp groups (default split %d)" % sb.warps_group0), (32 << 8, "one group of 32 warps"), (16 << 8, "forced 16/16"), (20 << 8, "forced 20/12")):
+if args.mode == "owner":
+    cases = ((0, "owner"),)
+else:
+    cases = ((0, "two warp groups (default split %d)" % sb.warps_group0), (32 << 8, "one group of 32 warps"))
+for flags, label in cases:
     run_trace(flags, label)

@@ -463,8 +463,8 @@ extern "C" int ure_mf_train_trace(void* d_workspace, int64_t* d_trace, int steps
   URE_CUDA(cudaMemcpyAsync(&ws->trace, &p, sizeof(p), cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream)));
   URE_CUDA(cudaMemcpyAsync(&ws->trace_steps, &steps, sizeof(int), cudaMemcpyHostToDevice,
                            static_cast<cudaStream_t>(stream)));
-  URE_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
-  return 0;
+  // the owner schedule keeps its own (disjoint) trace fields in the same workspace
+  return mf_owner_trace(d_workspace, p, steps, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int ure_mf_debug_flags(void* d_workspace, unsigned flags, void* stream) {

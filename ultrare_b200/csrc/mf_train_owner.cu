@@ -10,11 +10,15 @@
 //     shard (the per-epoch visiting order); which batch a slot belongs to in epoch e is
 //     step_of(slot) = inverse_permutation_e(record index) / batch, evaluated once per epoch into a
 //     shared-memory uint16 array -- for the NEXT epoch, slice by slice, in the shadow of the barrier.
-//   * A step walks every owned row (in chunks of slots, handed out dynamically to groups of d/4 lanes):
-//     the slots of the current batch gather the OTHER table's row (16-byte L2 loads), the error is
-//     re-computed on both sides, the row gradient accumulates in registers, and the SGD update of the
-//     row is applied right away (rows split over several chunks combine through shared memory).
-//     No global atomics, no gradient arrays, no separate dense sweep.
+//   * A step (1) compacts the CTA's slots of the current batch into a sorted list (ballot/popc, order
+//     preserving), (2) walks the list in waves -- a group of d/4 lanes per interaction: the OTHER table's row
+//     is gathered with 16-byte L2 loads, the error is re-computed on both sides, the contributions of
+//     consecutive interactions of the same row are summed in registers (in the group, then across the
+//     warp's groups by a segmented shuffle reduction) and the run totals go to a shared-memory gradient
+//     row, (3) sweeps the owned rows: SGD update in shared memory + publication of the new weights.
+//     No global atomics, no global gradient arrays, no separate dense sweep over HBM/L2.
+//   * When they fit, the slots' (other index, rating, own row) are cached in shared memory as well, so the
+//     only L2 traffic of a step is the gather of the other table's rows.
 //   * Updated rows are published to the buffer the NEXT step reads: P/Q and gP/gQ alternate
 //     (reads of step j come from buffer j&1), so gradients always see pre-step weights (batch-synchronous
 //     semantics of the reference) with ONE barrier per step -- and only among the CTAs of the shard.
@@ -34,7 +38,10 @@ struct OwnerWs {
   int max_slots;          // max interactions (user side + item side) per CTA
   int planned_grid;       // grid size the plan was made for
   int planned_K;
-  int pad[26];
+  int trace_steps;        // diagnostics (ure_mf_train_trace): stamps of the first trace_steps steps of a launch
+  int pad0;
+  long long* trace;       // [trace_steps][grid][6] SM-clock stamps, or NULL
+  int pad[22];
   unsigned bar[KMAX][32]; // one barrier counter per shard, one 128-byte line each
 };
 
@@ -116,22 +123,34 @@ __device__ void make_plan(const ure_mf_shard_t* shards, int K, int cta, int n_ct
   __syncthreads();
 }
 
-__host__ __device__ inline int owner_smem_need(int rows, int slots, int d) {
-  // w, buf, gacc [rows][d] fp32 | rowslot [rows+1], cpref [rows+1], done [rows] int | step_of [2][slots] u16
-  long long b = (long long)rows * d * 12 + (long long)(rows + 1) * 8 + (long long)rows * 4 + 64;
-  b += 2ll * 2 * ((slots + 7) & ~7);
-  return b > 0x7fffffff ? 0x7fffffff : (int)b;
+constexpr int kRing = 256;                // per-warp queue of batch slots (entries, power of two)
+
+// Dynamic shared memory of a CTA with `rows` owned rows and `slots` owned interactions (both sides):
+//   w, buf, g [rows][d] fp32 | boundary rows [2*warps][d] fp32 | rowslot [rows+1] int | queues [warps][kRing] u16
+//   | step_of [2][slots] u8 (u16 when steps/epoch > 255)                    -- the minimum, plus, when it fits,
+//   other [slots] int | rating [slots] fp32 | own row [slots] u16           -- the record cache.
+__host__ __device__ inline long long owner_smem_fixed(int rows, int slots, int d, int spe) {
+  const long long m_pad = (slots + 15) & ~15;
+  return (long long)rows * d * 12 + 64ll * d * 4 + (long long)(rows + 4) * 4 + 32ll * kRing * 2 +
+         2 * m_pad * (spe > 255 ? 2 : 1) + 64;
+}
+__host__ __device__ inline long long owner_smem_cache(int slots) {
+  const long long m_pad = (slots + 15) & ~15;
+  return m_pad * 10;
 }
 
-__global__ void plan_kernel(const ure_mf_shard_t* shards, int K, int d, OwnerWs* ws) {
+__global__ void plan_kernel(const ure_mf_shard_t* shards, int K, int d, int batch, OwnerWs* ws) {
   __shared__ PlanScratch ps;
   __shared__ Plan pl;
   make_plan(shards, K, blockIdx.x, gridDim.x, pl, ps);
   if (threadIdx.x == 0) {
-    const int rows = (pl.ru1 - pl.ru0) + (pl.ri1 - pl.ri0);
-    atomicMax(&ws->need_smem, owner_smem_need(rows, pl.mU + pl.mI, d));
+    const int rows = (pl.ru1 - pl.ru0) + (pl.ri1 - pl.ri0), m = pl.mU + pl.mI;
+    const int spe = (shards[pl.shard].n + batch - 1) / batch;
+    const long long need = owner_smem_fixed(rows, m, d, spe);
+    atomicMax(&ws->need_smem, (int)min(need, 0x7fffffffll));
     atomicMax(&ws->max_rows, rows);
-    atomicMax(&ws->max_slots, pl.mU + pl.mI);
+    atomicMax(&ws->max_slots, m);
+    if (m > 65535 * 32 || rows > 65535 || spe > 65535) atomicMax(&ws->need_smem, 0x7fffffff);
   }
 }
 
@@ -206,49 +225,27 @@ __global__ void perm_inverse_kernel(const ure_mf_shard_t* shards, int epochs) {
   }
 }
 
-// ---------------------------------------------------------------- the inverse visiting order
-__device__ __forceinline__ uint32_t feistel_inverse(const FeistelDomain& dm, const FeistelKeys& ks, uint32_t y) {
-  if (dm.n <= 1) return 0;
-  uint32_t x = y;
-  do {
-    uint32_t L = x / dm.b, R = x - L * dm.b;
-#pragma unroll
-    for (int r = kFeistelRounds - 1; r >= 0; --r) {
-      if ((r & 1) == 0) {
-        const uint32_t f = mulhi32(mix32(R ^ ks.rk[r]), dm.a);
-        L = L >= f ? L - f : L + dm.a - f;
-      } else {
-        const uint32_t f = mulhi32(mix32(L ^ ks.rk[r]), dm.b);
-        R = R >= f ? R - f : R + dm.b - f;
-      }
-    }
-    x = L * dm.b + R;
-  } while (x >= dm.n);
-  return x;
-}
-
 // ---------------------------------------------------------------- the training kernel
 template <int D>
 __global__ void __launch_bounds__(kOwnThreads, 1)
 mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams_t hp, int epochs,
-                long long step_begin, long long step_end, OwnerWs* ws, unsigned dbg) {
+                long long step_begin, long long step_end, OwnerWs* ws, unsigned dbg, int smem_bytes) {
   constexpr int G = D / 4;                 // lanes per row / interaction
-  extern __shared__ __align__(16) unsigned char dyn[];
-  constexpr int GPW = 32 / G;              // groups per warp
+  constexpr int GPW = 32 / G;              // lane groups per warp
+  constexpr int QB = 4;                    // interactions a group handles per wave (gathers in flight per lane)
+  constexpr int WAVE = GPW * QB;           // interactions per warp and wave
+  constexpr int NW = kOwnThreads / 32;
   constexpr unsigned FULL = 0xffffffffu;
+  extern __shared__ __align__(16) unsigned char dyn[];
   __shared__ PlanScratch s_ps;
   __shared__ Plan s_pl;
   __shared__ ure_mf_shard_t s_sh;
-  __shared__ int s_next;
-  __shared__ float s_sse;
+  __shared__ float s_wsse[NW];
+  __shared__ int s_bkey[2 * NW];           // row of every boundary record (-1: unused)
 
-  const int tid = threadIdx.x, lane = tid & 31, gl = lane % G, gw = lane / G;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gl = lane % G, gw = lane / G;
   make_plan(shards, K, blockIdx.x, gridDim.x, s_pl, s_ps);
-  if (tid == 0) {
-    s_sh = shards[s_pl.shard];
-    s_next = 0;
-    s_sse = 0.f;
-  }
+  if (tid == 0) s_sh = shards[s_pl.shard];
   __syncthreads();
   const Plan pl = s_pl;
   const ure_mf_shard_t& sh = s_sh;
@@ -261,80 +258,115 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
   if (t_end <= step_begin) return;         // the whole shard (all of its CTAs) has nothing to do
 
   // ---- shared-memory carve-up
+  const int m_pad = (m + 15) & ~15;
+  const bool wide = spe > 255;             // step_of entries: u8, or u16 for long epochs
   float* const s_w = reinterpret_cast<float*>(dyn);
   float* const s_b = s_w + (size_t)rows * D;
   float* const s_g = s_b + (size_t)rows * D;
-  int* const s_rowslot = reinterpret_cast<int*>(s_g + (size_t)rows * D);   // [rows+1] CTA-local first slot
-  int* const s_cpref = s_rowslot + rows + 1;                                // [rows+1] chunk prefix
-  int* const s_done = s_cpref + rows + 1;                                   // [rows]
-  const int m_pad = (m + 7) & ~7;
-  unsigned short* const s_step = reinterpret_cast<unsigned short*>(
-      (reinterpret_cast<uintptr_t>(s_done + rows) + 15) & ~uintptr_t(15));  // [2][m_pad]
+  float* const s_bnd = s_g + (size_t)rows * D;                              // [2*NW][D] boundary-row partial sums
+  int* const s_rowslot = reinterpret_cast<int*>(s_bnd + (size_t)2 * NW * D);   // [rows+1] CTA-local first slot
+  unsigned short* const s_ring = reinterpret_cast<unsigned short*>(s_rowslot + rows + 4) + warp * kRing;
+  unsigned char* const s_step8 = reinterpret_cast<unsigned char*>(
+      (reinterpret_cast<uintptr_t>(s_ring - warp * kRing + NW * kRing) + 15) & ~uintptr_t(15));
+  unsigned short* const s_step16 = reinterpret_cast<unsigned short*>(s_step8);
+  unsigned char* carve = s_step8 + (size_t)2 * m_pad * (wide ? 2 : 1);
+  carve = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(carve) + 15) & ~uintptr_t(15));
+  const bool cached = owner_smem_fixed(rows, m, D, spe) + owner_smem_cache(m) <= (long long)smem_bytes;
+  int* s_other = nullptr;
+  float* s_rating = nullptr;
+  unsigned short* s_row = nullptr;
+  if (cached) {
+    s_other = reinterpret_cast<int*>(carve);
+    s_rating = reinterpret_cast<float*>(s_other + m_pad);
+    s_row = reinterpret_cast<unsigned short*>(s_rating + m_pad);
+  }
 
-  // chunk length: a multiple of the 64-slot scan window, longer when batches are a small part of the epoch
-  const int CL = 64 * max(1, min(8, (spe + 7) / 8));
+  const int4* const recU = reinterpret_cast<const int4*>(sh.inter_u + pl.su0);           // slot sl < mU
+  const int4* const recI = reinterpret_cast<const int4*>(sh.inter_i + pl.si0) - pl.mU;   // slot sl >= mU
+  auto row_of_rec = [&](const int4& rec, bool it) { return it ? rec.y - pl.ri0 + rowsU : rec.x - pl.ru0; };
 
-  // ---- prologue: owned rows -> shared memory, slot offsets, chunk prefix
+  // this warp's slots [w0, w1): a contiguous, row-sorted range; only its first and last row can be shared with
+  // other warps -- their partial sums go to the warp's two boundary records, everything else straight to s_g
+  const int per = (((m + NW - 1) / NW) + 3) & ~3;
+  const int w0 = min(warp * per, m), w1 = min(w0 + per, m);
+  int rowF = -1, rowL = -1;
+  if (w0 < w1) {
+    rowF = row_of_rec(__ldg((w0 >= pl.mU ? recI : recU) + w0), w0 >= pl.mU);
+    rowL = row_of_rec(__ldg((w1 - 1 >= pl.mU ? recI : recU) + (w1 - 1)), w1 - 1 >= pl.mU);
+  }
+  float* const bndF = s_bnd + (size_t)(2 * warp) * D;
+  float* const bndL = bndF + D;
+
+  // ---- prologue: owned rows -> shared memory, slot offsets, record cache
   for (int x = tid; x < rows * G; x += kOwnThreads) {
     const int r = x / G, c = x % G;
     const bool it = r >= rowsU;
     const size_t go = (size_t)(it ? pl.ri0 + (r - rowsU) : pl.ru0 + r) * D + 4 * c;
-    const float4 w = ld_cg_f4((it ? sh.Q : sh.P) + go);
-    const float4 b = ld_cg_f4((it ? sh.bufQ : sh.bufP) + go);
-    *reinterpret_cast<float4*>(s_w + (size_t)r * D + 4 * c) = w;
-    *reinterpret_cast<float4*>(s_b + (size_t)r * D + 4 * c) = b;
+    *reinterpret_cast<float4*>(s_w + (size_t)r * D + 4 * c) = ld_cg_f4((it ? sh.Q : sh.P) + go);
+    *reinterpret_cast<float4*>(s_b + (size_t)r * D + 4 * c) = ld_cg_f4((it ? sh.bufQ : sh.bufP) + go);
     *reinterpret_cast<float4*>(s_g + (size_t)r * D + 4 * c) = make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  for (int r = tid; r <= rows; r += kOwnThreads) {
+  for (int x = tid; x < 2 * NW * G; x += kOwnThreads)
+    *reinterpret_cast<float4*>(s_bnd + 4 * (size_t)x) = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int r = tid; r <= rows; r += kOwnThreads)
     s_rowslot[r] = r <= rowsU ? sh.off_u[pl.ru0 + r] - pl.su0
                               : pl.mU + sh.off_i[pl.ri0 + (r - rowsU)] - pl.si0;
-    if (r < rows) s_done[r] = 0;
-  }
-  __syncthreads();
-  if (tid < 32) {                          // chunk prefix: an empty row still gets one chunk (it must decay)
-    int carry = 0;
-    for (int base = 0; base < rows; base += 32) {
-      const int r = base + lane;
-      int v = 0;
-      if (r < rows) v = max(1, (s_rowslot[r + 1] - s_rowslot[r] + CL - 1) / CL);
-      int inc = v;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int a = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += a;
-      }
-      if (r < rows) s_cpref[r] = carry + inc - v;
-      carry += __shfl_sync(0xffffffffu, inc, 31);
+  if (lane == 0) { s_bkey[2 * warp] = rowF; s_bkey[2 * warp + 1] = rowL; s_wsse[warp] = 0.f; }
+  if (cached) {
+    for (int sl = tid; sl < m; sl += kOwnThreads) {
+      const bool it = sl >= pl.mU;
+      const int4 rec = __ldg((it ? recI : recU) + sl);
+      s_other[sl] = it ? rec.x : rec.y;
+      s_rating[sl] = __int_as_float(rec.z);
+      s_row[sl] = (unsigned short)row_of_rec(rec, it);
     }
-    if (lane == 0) s_cpref[rows] = carry;
   }
-  __syncthreads();
-  const int total_chunks = s_cpref[rows];
+  // the pad of both step_of buffers never matches a step number
+  for (int x = m + tid; x < m_pad; x += kOwnThreads) {
+    if (wide) { s_step16[x] = 0xffffu; s_step16[m_pad + x] = 0xffffu; }
+    else { s_step8[x] = 0xffu; s_step8[m_pad + x] = 0xffu; }
+  }
 
   // ---- visiting order -> step_of
   FeistelDomain dom;
   dom.init((uint32_t)n);
   const uint32_t magic = (uint32_t)(0x100000000ull / (uint32_t)B);     // floor(2^32/B): quotient low by <= 1
-  auto fill_step_of = [&](int epoch, long long lo, long long hi) {
-    unsigned short* out = s_step + (size_t)(epoch & 1) * m_pad;
+  auto fill_step_of = [&](int epoch, int lo, int hi) {
+    constexpr int NI = 3;
+    const size_t ob = (size_t)(epoch & 1) * m_pad;
     FeistelKeys ks;
     ks.init(perm_key(sh.perm_seed, (uint32_t)sh.shard_id, (uint32_t)epoch));
     const int32_t* pinv = sh.perm_inv ? sh.perm_inv + (long long)epoch * n : nullptr;
-    for (long long sl = lo + tid; sl < hi; sl += kOwnThreads) {
-      const ure_inter_t* rec = sl < pl.mU ? sh.inter_u + pl.su0 + sl : sh.inter_i + pl.si0 + (sl - pl.mU);
-      const uint32_t j = (uint32_t)__ldg(&rec->pad);
-      uint32_t pos;
-      if (pinv) pos = (uint32_t)__ldg(pinv + j);
-      else if (dbg & 2u) pos = j;
-      else pos = feistel_inverse(dom, ks, j);
-      uint32_t q = B == 1 ? pos : mulhi32(pos, magic);
-      if ((q + 1) * (uint32_t)B <= pos) ++q;
-      out[sl] = (unsigned short)q;
+    for (int s0 = lo + tid; s0 < hi; s0 += NI * kOwnThreads) {
+      uint32_t x[NI];
+      bool live[NI];
+#pragma unroll
+      for (int u = 0; u < NI; ++u) {
+        const int sl = s0 + u * kOwnThreads;
+        live[u] = sl < hi;
+        x[u] = 0;
+        if (live[u]) x[u] = (uint32_t)__ldg(&((sl >= pl.mU ? recI : recU) + sl)->w);
+      }
+      if (pinv) {
+#pragma unroll
+        for (int u = 0; u < NI; ++u)
+          if (live[u]) x[u] = (uint32_t)__ldg(pinv + x[u]);
+      } else if (!(dbg & 2u)) {
+        feistel_inverse_n<NI>(dom, ks, x, live);
+      }
+#pragma unroll
+      for (int u = 0; u < NI; ++u) {
+        if (!live[u]) continue;
+        uint32_t q = B == 1 ? x[u] : mulhi32(x[u], magic);
+        if ((q + 1) * (uint32_t)B <= x[u]) ++q;
+        const int sl = s0 + u * kOwnThreads;
+        if (wide) s_step16[ob + sl] = (unsigned short)q; else s_step8[ob + sl] = (unsigned char)q;
+      }
     }
   };
   int e = (int)(step_begin / spe), k = (int)(step_begin % spe);
   fill_step_of(e, 0, m);
-  if (k > 0 && e + 1 < epochs) fill_step_of(e + 1, 0, (long long)k * m / spe);
+  if (k > 0 && e + 1 < epochs) fill_step_of(e + 1, 0, (int)((long long)k * m / spe));
   __syncthreads();
 
   auto lr_of = [&](int epoch) {
@@ -347,6 +379,22 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
   unsigned* const counter = &ws->bar[pl.shard][0];
   unsigned bar_target = 0;
   double epoch_sse = 0.0;                  // thread 0 only
+  long long* const trace = ws->trace;
+  const int trace_steps = ws->trace_steps;
+#define URE_STAMP(PH)                                                               \
+  if (trace && tid == 32 && (t - step_begin) < trace_steps)                        \
+    trace[((t - step_begin) * gridDim.x + blockIdx.x) * 6 + (PH)] = clock64();
+
+  // run total -> the row's gradient accumulator.  Plain read-modify-write: within the warp flushes of one row
+  // are at different program points (a __syncwarp between them), across warps only rowF / rowL can collide.
+  auto flush = [&](int row, const float4& a) {
+    if (row >= 0) {
+      float4* gp = reinterpret_cast<float4*>((row == rowF ? bndF : row == rowL ? bndL : s_g + (size_t)row * D) + 4 * gl);
+      float4 v = *gp;
+      v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+      *gp = v;
+    }
+  };
 
   for (long long t = step_begin; t < t_end; ++t) {
     const int rd = (int)((t - step_begin) & 1);
@@ -354,148 +402,188 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
     const float* const Qr = rd ? sh.gQ : sh.Q;
     float* const Pw = rd ? sh.P : sh.gP;
     float* const Qw = rd ? sh.Q : sh.gQ;
-    const unsigned short* const stp = s_step + (size_t)(e & 1) * m_pad;
+    const size_t sb = (size_t)(e & 1) * m_pad;
     float sse_l = 0.f;
+    URE_STAMP(0)
 
-    // ------------------------------------------------------------ owned rows, chunk by chunk
-    // A warp takes GPW consecutive chunks from the CTA's queue, one per lane group; control flow is
-    // warp-uniform (groups with fewer slots of this batch idle under predication).
+    // -------------------------------------------------------------- (1)+(2) the warp streams its own slots:
+    // slots of this batch are queued in slot order (= row order) and consumed a wave at a time
+    int scan = w0;                         // next slot to look at (multiple of 4)
+    unsigned q_rd = 0, q_wr = 0;           // queue counters (warp-uniform)
     for (;;) {
-      int x0 = 0;
-      if (lane == 0) x0 = atomicAdd(&s_next, GPW);
-      x0 = __shfl_sync(FULL, x0, 0);
-      if (x0 >= total_chunks) break;
-      const int x = x0 + gw;
-      const bool have = x < total_chunks;
-      int row = 0, nch = 1, sl0 = 0, sl1 = 0;
-      if (have) {
-        int lo = 0, hi = rows;             // largest row with cpref[row] <= x
-        while (hi - lo > 1) {
-          const int mid = (lo + hi) >> 1;
-          if (s_cpref[mid] <= x) lo = mid; else hi = mid;
+      while ((int)(q_wr - q_rd) < WAVE && scan < w1) {
+        const int sl = scan + 4 * lane;    // this lane's 4 slots of the 128-slot window
+        unsigned hits = 0;
+        if (sl < w1) {
+          if (wide) {
+            const uint2 v = *reinterpret_cast<const uint2*>(s_step16 + sb + sl);
+            hits = ((v.x & 0xffffu) == (unsigned)k) | (((v.x >> 16) == (unsigned)k) << 1) |
+                   (((v.y & 0xffffu) == (unsigned)k) << 2) | (((v.y >> 16) == (unsigned)k) << 3);
+          } else {
+            const unsigned v = *reinterpret_cast<const unsigned*>(s_step8 + sb + sl);
+            hits = ((v & 0xffu) == (unsigned)k) | ((((v >> 8) & 0xffu) == (unsigned)k) << 1) |
+                   ((((v >> 16) & 0xffu) == (unsigned)k) << 2) | (((v >> 24) == (unsigned)k) << 3);
+          }
+          if (sl + 4 > w1) hits &= (1u << (w1 - sl)) - 1u;     // slots of the next warp / the pad
         }
-        row = lo;
-        nch = s_cpref[row + 1] - s_cpref[row];
-        sl0 = s_rowslot[row] + (x - s_cpref[row]) * CL;
-        sl1 = min(sl0 + CL, s_rowslot[row + 1]);
-      }
-      const bool it = row >= rowsU;
-      const int4* const recs = reinterpret_cast<const int4*>(it ? sh.inter_i + pl.si0 - pl.mU : sh.inter_u + pl.su0);
-      const float* const other = it ? Pr : Qr;
-      const float4 wown = *reinterpret_cast<const float4*>(s_w + (size_t)row * D + 4 * gl);
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-
-      for (int w0 = sl0;; w0 += 64) {
-        const bool act = have && w0 < sl1;
-        if (!__any_sync(FULL, act)) break;
-        unsigned long long mask = 0;
-        if (act) {
+        const int c = __popc(hits);
+        int incl = c;
 #pragma unroll
-          for (int i = 0; i < 64 / G; ++i) {
-            const int sl = w0 + gl + G * i;
-            if (sl < sl1 && stp[sl] == (unsigned short)k) mask |= 1ull << (gl + G * i);
-          }
+        for (int o = 1; o < 32; o <<= 1) {
+          const int a = __shfl_up_sync(FULL, incl, o);
+          if (lane >= o) incl += a;
         }
+        unsigned pos = q_wr + (unsigned)(incl - c);
 #pragma unroll
-        for (int o = G / 2; o > 0; o >>= 1) mask |= __shfl_xor_sync(FULL, mask, o);
-        while (__any_sync(FULL, mask != 0)) {
-          int4 rec[4];
-          float4 o4[4];
-          bool ok[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            ok[q] = mask != 0;
-            rec[q] = make_int4(0, 0, 0, 0);
-            if (ok[q]) {
-              const int b = __ffsll((long long)mask) - 1;
-              mask &= mask - 1;
-              rec[q] = __ldg(recs + w0 + b);
-            }
-          }
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            o4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (ok[q]) o4[q] = ld_cg_f4(other + (size_t)(it ? rec[q].x : rec[q].y) * D + 4 * gl);
-          }
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float dot = wown.x * o4[q].x;
-            dot = fmaf(wown.y, o4[q].y, dot);
-            dot = fmaf(wown.z, o4[q].z, dot);
-            dot = fmaf(wown.w, o4[q].w, dot);
-#pragma unroll
-            for (int o = G / 2; o > 0; o >>= 1) dot += __shfl_xor_sync(FULL, dot, o);
-            const float err = ok[q] ? dot - __int_as_float(rec[q].z) : 0.f;
-            const float ge = 2.f * err;
-            acc.x = fmaf(ge, o4[q].x, acc.x); acc.y = fmaf(ge, o4[q].y, acc.y);
-            acc.z = fmaf(ge, o4[q].z, acc.z); acc.w = fmaf(ge, o4[q].w, acc.w);
-            if (!it && gl == 0) sse_l = fmaf(err, err, sse_l);
-          }
-        }
+        for (int i = 0; i < 4; ++i)
+          if (hits & (1u << i)) s_ring[(pos++) & (kRing - 1)] = (unsigned short)(sl + i - w0);
+        q_wr += (unsigned)__shfl_sync(FULL, incl, 31);
+        scan += 128;
       }
-
-      // ---------------------------------------------------------- the row's SGD update (whoever completes it)
-      const bool multi = have && nch > 1;
-      float* const gp = s_g + (size_t)row * D + 4 * gl;
-      if (multi) {
-        atomicAdd(gp + 0, acc.x); atomicAdd(gp + 1, acc.y); atomicAdd(gp + 2, acc.z); atomicAdd(gp + 3, acc.w);
-      }
-      __threadfence_block();
       __syncwarp();
-      int old = 0;
-      if (multi && gl == 0) old = atomicAdd(&s_done[row], 1);
-      old = __shfl_sync(FULL, old, lane - gl);
-      const bool finish = have && (!multi || old == nch - 1);
-      if (multi && finish) {
-        __threadfence_block();
-        volatile float* vg = gp;
-        acc = make_float4(vg[0], vg[1], vg[2], vg[3]);
-        *reinterpret_cast<float4*>(gp) = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (gl == 0) s_done[row] = 0;
-      }
-      if (finish) {
-        float* wp = s_w + (size_t)row * D + 4 * gl;
-        float* bp = s_b + (size_t)row * D + 4 * gl;
-        float4 w = *reinterpret_cast<float4*>(wp);
-        float4 b = *reinterpret_cast<float4*>(bp);
-        // torch SGD: d_p = g + wd*w (fma); buf = buf*mu + d_p; w = w + (-lr)*buf (fma)
-        acc.x = fmaf(wd, w.x, acc.x); acc.y = fmaf(wd, w.y, acc.y);
-        acc.z = fmaf(wd, w.z, acc.z); acc.w = fmaf(wd, w.w, acc.w);
-        b.x = __fadd_rn(__fmul_rn(b.x, mu), acc.x); b.y = __fadd_rn(__fmul_rn(b.y, mu), acc.y);
-        b.z = __fadd_rn(__fmul_rn(b.z, mu), acc.z); b.w = __fadd_rn(__fmul_rn(b.w, mu), acc.w);
-        w.x = fmaf(nlr, b.x, w.x); w.y = fmaf(nlr, b.y, w.y); w.z = fmaf(nlr, b.z, w.z); w.w = fmaf(nlr, b.w, w.w);
-        *reinterpret_cast<float4*>(wp) = w;
-        *reinterpret_cast<float4*>(bp) = b;
-        const size_t go = (size_t)(it ? pl.ri0 + (row - rowsU) : pl.ru0 + row) * D + 4 * gl;
-        st_cg_f4((it ? Qw : Pw) + go, w);
-      }
-    }
+      const int nent = min((int)(q_wr - q_rd), WAVE);
+      if (nent == 0) break;
 
-    // ------------------------------------------------------------ loss, barrier among the shard's CTAs
+      // ------------------------------------------------------------ one wave: QB consecutive entries per group
+      int row[QB], oth[QB];
+      float rat[QB];
+      float4 o4[QB];
+#pragma unroll
+      for (int q = 0; q < QB; ++q) {
+        row[q] = -1; oth[q] = 0; rat[q] = 0.f;
+        if (gw * QB + q < nent) {
+          const int sl = w0 + s_ring[(q_rd + gw * QB + q) & (kRing - 1)];
+          if (cached) {
+            row[q] = s_row[sl]; oth[q] = s_other[sl]; rat[q] = s_rating[sl];
+          } else {
+            const bool it = sl >= pl.mU;
+            const int4 rec = __ldg((it ? recI : recU) + sl);
+            row[q] = row_of_rec(rec, it);
+            oth[q] = it ? rec.x : rec.y;
+            rat[q] = __int_as_float(rec.z);
+          }
+        }
+      }
+      q_rd += (unsigned)nent;
+#pragma unroll
+      for (int q = 0; q < QB; ++q) {
+        o4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row[q] >= 0) o4[q] = ld_cg_f4((row[q] >= rowsU ? Pr : Qr) + (size_t)oth[q] * D + 4 * gl);
+      }
+      int key = -1;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int q = 0; q < QB; ++q) {
+        float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row[q] >= 0) w = *reinterpret_cast<const float4*>(s_w + (size_t)row[q] * D + 4 * gl);
+        float dot = w.x * o4[q].x;
+        dot = fmaf(w.y, o4[q].y, dot);
+        dot = fmaf(w.z, o4[q].z, dot);
+        dot = fmaf(w.w, o4[q].w, dot);
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) dot += __shfl_xor_sync(FULL, dot, o);
+        const float err = row[q] >= 0 ? dot - rat[q] : 0.f;
+        const float ge = 2.f * err;
+        if (row[q] >= 0 && row[q] < rowsU && gl == 0) sse_l = fmaf(err, err, sse_l);
+        if (q > 0 && row[q] != key) {      // the row changes inside the group: the finished run goes out
+          flush(key, acc);
+          acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        key = row[q];
+        acc.x = fmaf(ge, o4[q].x, acc.x); acc.y = fmaf(ge, o4[q].y, acc.y);
+        acc.z = fmaf(ge, o4[q].z, acc.z); acc.w = fmaf(ge, o4[q].w, acc.w);
+      }
+      // segmented reduction of the groups' trailing runs (the queue is sorted, equal rows are adjacent)
+#pragma unroll
+      for (int o = 1; o < GPW; o <<= 1) {
+        const int k2 = __shfl_down_sync(FULL, key, o * G);
+        float4 a2;
+        a2.x = __shfl_down_sync(FULL, acc.x, o * G); a2.y = __shfl_down_sync(FULL, acc.y, o * G);
+        a2.z = __shfl_down_sync(FULL, acc.z, o * G); a2.w = __shfl_down_sync(FULL, acc.w, o * G);
+        if (gw + o < GPW && k2 == key) { acc.x += a2.x; acc.y += a2.y; acc.z += a2.z; acc.w += a2.w; }
+      }
+      const int kprev = __shfl_up_sync(FULL, key, G);
+      __syncwarp();                        // the in-group flushes above are visible to the head flushes below
+      if (gw == 0 || kprev != key) flush(key, acc);
+      __syncwarp();
+    }
     sse_l = warp_sum(sse_l);
-    if (lane == 0 && sse_l != 0.f) atomicAdd(&s_sse, sse_l);
+    if (lane == 0) s_wsse[warp] = sse_l;
+    URE_STAMP(1)
+    __syncthreads();
+    URE_STAMP(2)
+
+    // ------------------------------------------------------------ boundary rows: first record of a row adds
+    // up every record of that row (they are adjacent: records are in slot order) into s_g
+    for (int i = tid / G; i < 2 * NW; i += kOwnThreads / G) {
+      const int key = s_bkey[i];
+      if (key < 0) continue;
+      int j = i - 1;
+      while (j >= 0 && s_bkey[j] < 0) --j;
+      if (j >= 0 && s_bkey[j] == key) continue;          // not the head
+      float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (j = i; j < 2 * NW && (s_bkey[j] < 0 || s_bkey[j] == key); ++j) {
+        if (s_bkey[j] < 0) continue;
+        float4* bp = reinterpret_cast<float4*>(s_bnd + (size_t)j * D + 4 * gl);
+        const float4 v = *bp;
+        sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+        *bp = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      float4* gp = reinterpret_cast<float4*>(s_g + (size_t)key * D + 4 * gl);
+      float4 v = *gp;
+      v.x += sum.x; v.y += sum.y; v.z += sum.z; v.w += sum.w;
+      *gp = v;
+    }
+    __syncthreads();
+
+    // ------------------------------------------------------------ (3) SGD update of every owned row, publication
+    for (int x = tid; x < rows * G; x += kOwnThreads) {
+      const int r = x / G, c = x % G;
+      float* gp = s_g + (size_t)r * D + 4 * c;
+      float* wp = s_w + (size_t)r * D + 4 * c;
+      float* bp = s_b + (size_t)r * D + 4 * c;
+      float4 g = *reinterpret_cast<float4*>(gp);
+      float4 w = *reinterpret_cast<float4*>(wp);
+      float4 b = *reinterpret_cast<float4*>(bp);
+      // torch SGD: d_p = g + wd*w (fma); buf = buf*mu + d_p; w = w + (-lr)*buf (fma)
+      g.x = fmaf(wd, w.x, g.x); g.y = fmaf(wd, w.y, g.y); g.z = fmaf(wd, w.z, g.z); g.w = fmaf(wd, w.w, g.w);
+      b.x = __fadd_rn(__fmul_rn(b.x, mu), g.x); b.y = __fadd_rn(__fmul_rn(b.y, mu), g.y);
+      b.z = __fadd_rn(__fmul_rn(b.z, mu), g.z); b.w = __fadd_rn(__fmul_rn(b.w, mu), g.w);
+      w.x = fmaf(nlr, b.x, w.x); w.y = fmaf(nlr, b.y, w.y); w.z = fmaf(nlr, b.z, w.z); w.w = fmaf(nlr, b.w, w.w);
+      *reinterpret_cast<float4*>(wp) = w;
+      *reinterpret_cast<float4*>(bp) = b;
+      *reinterpret_cast<float4*>(gp) = make_float4(0.f, 0.f, 0.f, 0.f);
+      const bool it = r >= rowsU;
+      st_cg_f4((it ? Qw : Pw) + (size_t)(it ? pl.ri0 + (r - rowsU) : pl.ru0 + r) * D + 4 * c, w);
+    }
     __syncthreads();                       // every row of this CTA is updated and published
-    if (tid == 0)
-      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+    URE_STAMP(3)
+
+    // ------------------------------------------------------------ barrier among the shard's CTAs
+    if (tid == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+    __syncwarp();
     bar_target += (unsigned)pl.c;
     const bool last_of_epoch = k + 1 == spe;
     // in the barrier's shadow: this step's slice of the NEXT epoch's step_of
-    if (e + 1 < epochs) fill_step_of(e + 1, (long long)k * m / spe, (long long)(k + 1) * m / spe);
+    if (e + 1 < epochs) fill_step_of(e + 1, (int)((long long)k * m / spe), (int)((long long)(k + 1) * m / spe));
+    URE_STAMP(4)
     if (tid == 0) {
-      epoch_sse += (double)s_sse;
-      s_sse = 0.f;
+      float v = 0.f;
+      for (int w = 0; w < NW; ++w) v += s_wsse[w];
+      epoch_sse += (double)v;
       if (last_of_epoch || t + 1 == t_end) {
         if (epoch_sse != 0.0) atomicAdd(sh.sse + e, epoch_sse);
         epoch_sse = 0.0;
       }
-      s_next = 0;
       while (ld_acquire_u32(counter) < bar_target) {
       }
     }
     __syncthreads();
+    URE_STAMP(5)
     if (last_of_epoch) { ++e; k = 0; nlr = -lr_of(e); }
     else ++k;
   }
+#undef URE_STAMP
 
   // ---- epilogue: the owned rows go back to P/Q (whatever the parity), momentum to bufP/bufQ, and the
   // alternate weight buffer gP/gQ is returned zeroed (the DENSE schedule's contract for its gradient scratch)
@@ -513,7 +601,7 @@ int max_dyn_smem(int* out) {
   int dev = 0, v = 0;
   URE_CUDA(cudaGetDevice(&dev));
   URE_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  *out = v - 8 * 1024;                     // the kernel's static shared memory (plan scratch, descriptor)
+  *out = v - 8 * 1024;                     // minus the kernel's static shared memory (plan scratch, descriptor)
   return 0;
 }
 
@@ -523,8 +611,8 @@ int launch_owner(const ure_mf_shard_t* d_shards, int K, const ure_mf_hparams_t& 
   auto kern = mf_owner_kernel<D>;
   URE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   URE_CUDA(cudaMemsetAsync(ws->bar, 0, sizeof(ws->bar), st));
-  void* args[] = {(void*)&d_shards, (void*)&K,  (void*)&hp, (void*)&epochs,
-                  (void*)&s0,       (void*)&s1, (void*)&ws, (void*)&dbg};
+  void* args[] = {(void*)&d_shards, (void*)&K,  (void*)&hp,  (void*)&epochs, (void*)&s0,
+                  (void*)&s1,       (void*)&ws, (void*)&dbg, (void*)&smem};
   URE_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(num_sms()), dim3(kOwnThreads), args, (size_t)smem, st));
   return 0;
 }
@@ -534,6 +622,13 @@ unsigned g_owner_dbg = 0;
 }  // namespace
 
 int64_t mf_owner_workspace_bytes() { return (int64_t)sizeof(OwnerWs); }
+int mf_owner_trace(void* d_workspace, long long* d_trace, int steps, cudaStream_t st) {
+  auto* ws = static_cast<OwnerWs*>(d_workspace);
+  URE_CUDA(cudaMemcpyAsync(&ws->trace, &d_trace, sizeof(d_trace), cudaMemcpyHostToDevice, st));
+  URE_CUDA(cudaMemcpyAsync(&ws->trace_steps, &steps, sizeof(int), cudaMemcpyHostToDevice, st));
+  URE_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
 void mf_owner_debug(unsigned flags) { g_owner_dbg = flags; }
 
 // called by ure_mf_train when hparams.mode == URE_MF_OWNER.  h_need / h_avail: what ure_mf_owner_prepare
@@ -552,7 +647,7 @@ int mf_train_owner(const ure_mf_shard_t* d_shards, int n_shards, const ure_mf_hp
               "dense or lazy schedule for this problem size", hp->owner_smem, avail);
   if (step_end <= step_begin) return 0;
   auto* ws = static_cast<OwnerWs*>(d_workspace);
-  const int smem = hp->owner_smem;
+  const int smem = avail;                  // everything: what the plan does not need caches records / lengthens the list
   switch (hp->d) {
     case 8: return launch_owner<8>(d_shards, n_shards, *hp, epochs, step_begin, step_end, ws, smem, g_owner_dbg, st);
     case 16: return launch_owner<16>(d_shards, n_shards, *hp, epochs, step_begin, step_end, ws, smem, g_owner_dbg, st);
@@ -582,9 +677,9 @@ extern "C" int ure_mf_owner_prepare(const ure_mf_shard_t* d_shards, int n_shards
   perm_inverse_kernel<<<dim3(blocks, n_shards), 256, 0, st>>>(d_shards, epochs);
   int avail = 0;
   if (int rc = max_dyn_smem(&avail)) return rc;
-  const int head[6] = {0, avail, 0, 0, num_sms(), n_shards};
+  const int head[8] = {0, avail, 0, 0, num_sms(), n_shards, 0, 0};
   URE_CUDA(cudaMemcpyAsync(ws, head, sizeof(head), cudaMemcpyHostToDevice, st));
-  plan_kernel<<<num_sms(), 32, 0, st>>>(d_shards, n_shards, h_hp->d, ws);
+  plan_kernel<<<num_sms(), 32, 0, st>>>(d_shards, n_shards, h_hp->d, h_hp->batch, ws);
   URE_CUDA(cudaGetLastError());
   return 0;
 }

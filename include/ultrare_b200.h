@@ -84,7 +84,9 @@ typedef struct {
   const float* decay;   /* lazy: DEVICE table [decay_len][4] of M^n = (a11,a12,a21,a22), the */
                         /*    n-step gradient-free update [w;buf] <- M^n [w;buf]; else NULL   */
   int32_t decay_len;    /* lazy: number of table entries (>= total steps + 1)                */
-  int32_t owner_smem;   /* OWNER: dynamic shared-memory bytes planned by ure_mf_owner_prepare */
+  int32_t owner_smem;   /* OWNER: dynamic shared-memory bytes to launch with (from ure_mf_owner_prepare) */
+  int32_t owner_cached; /* OWNER: 1 = owner_smem includes the shared-memory record cache          */
+  int32_t reserved;
 } ure_mf_hparams_t;
 
 /* ure_mf_hparams_t::mode -- three schedules of the SAME arithmetic (baseTrain + dense optim.SGD):
@@ -120,10 +122,11 @@ int ure_mf_train(const ure_mf_shard_t* d_shards, int n_shards, const ure_mf_hpar
 
 /* Owner mode set-up, once per shard table (asynchronous, no host sync): builds inter_u / inter_i /
  * off_u / off_i (counting sort of the records by user and by item) and perm_inv for shards with an
- * explicit perm, then plans the CTA ownership and writes into the first 16 bytes of d_workspace
+ * explicit perm, then plans the CTA ownership and writes into the first 20 bytes of d_workspace
  * int32 {shared-memory bytes the busiest CTA needs, bytes available, max rows per CTA, max
- * interactions per CTA}: the caller reads them back once and must not start mode OWNER when
- * need > available (ure_mf_train refuses it loudly on the next call as well). */
+ * interactions per CTA, bytes needed with the record cache}: the caller reads them back once, sets
+ * hparams.owner_smem / owner_cached accordingly and must not start mode OWNER when need > available
+ * (ure_mf_train refuses it loudly as well). */
 int ure_mf_owner_prepare(const ure_mf_shard_t* d_shards, int n_shards, const ure_mf_hparams_t* h_hp,
                          int epochs, void* d_workspace, void* stream);
 
@@ -161,6 +164,13 @@ int ure_score_finalize(const float* d_sum, const ure_inter_t* d_inter, int64_t n
  * Tie rule: descending value, later index first (np.argsort(kind='stable')[::-1]). */
 int ure_rank_metrics(const ure_inter_t* d_inter, const float* d_score, const int32_t* d_order,
                      const int64_t* d_seg, int64_t n_seg, double* d_out, void* stream);
+
+/* Data ingest (what RatingData.__init__ + __getitem__ do on the host, read.py:111-113,118-124): the float64
+ * [3, n] array readRating hands over (rows: user id, item id, rating / max_rating; row stride ld elements),
+ * already on the device, becomes packed records: user = int(u) -- or d_row_of[int(u)], the row inside a
+ * compact per-shard user table, when d_row_of != NULL -- item = int(i), rating = float32(r). */
+int ure_pack_interactions_f64(const double* d_cols, int64_t n, int64_t ld, const int32_t* d_row_of,
+                              int32_t n_map, ure_inter_t* d_out, void* stream);
 
 /* Affected-shard routing (method/sisa.py:76-81): flags[owner[u]] = 1 for u in del. */
 int ure_route_deletions(const int32_t* d_owner, int32_t n_user, const int32_t* d_del, int32_t n_del,

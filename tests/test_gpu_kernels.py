@@ -380,7 +380,8 @@ def test_mf_owner_prepare_sorts_and_inverts(cuda_dev):
     assert sb.owner_plan["smem_need"] <= sb.owner_plan["smem_avail"]
 
 
-def test_mf_owner_skewed_rows_many_shards_vs_oracle(cuda_dev):
+@pytest.mark.parametrize("cache", [True, False])
+def test_mf_owner_skewed_rows_many_shards_vs_oracle(cuda_dev, cache):
     """Owner schedule on ragged shards with heavy rows (one user / one item holding a large share of a shard, rows
     split over many chunks and CTAs with no rows at all), more steps per epoch than a chunk window, empty shard."""
     torch = _torch()
@@ -402,7 +403,8 @@ def test_mf_owner_skewed_rows_many_shards_vs_oracle(cuda_dev):
         shards.append(kn.ShardState(kn.pack_interactions(u, i, r, cuda_dev), torch.tensor(P0, device=cuda_dev),
                                     torch.tensor(Q0, device=cuda_dev), epochs, s, 9))
         host.append((u, i, r, P0, Q0, perms))
-    sb = kn.ShardBatch(shards, d, batch, mode="owner")
+    sb = kn.ShardBatch(shards, d, batch, mode="owner", owner_cache=cache)
+    assert sb.owner_plan["cached"] == cache
     sb.train()
     torch.cuda.synchronize()
     losses = sb.train_losses()
@@ -417,3 +419,22 @@ def test_mf_owner_skewed_rows_many_shards_vs_oracle(cuda_dev):
         assert np.abs(shards[s].Q.cpu().numpy() - Q).max() < 1e-4
         assert np.abs(shards[s].bufQ.cpu().numpy() - bQ).max() < 1e-3
         assert float(shards[s].gP.abs().max()) == 0.0 and float(shards[s].gQ.abs().max()) == 0.0
+
+
+def test_pack_interactions_on_device_equals_host_casts(cuda_dev):
+    """ure_pack_interactions_f64 == RatingData's host casts (read.py:111-113,124): int(uid), int(iid),
+    float32(float64 rating), bit for bit, with and without the compact-row mapping; empty input."""
+    torch = _torch()
+    from ultrare_b200 import kernels as kn
+    rng = np.random.default_rng(3)
+    n, U = 200_003, 5000
+    raw = np.vstack([rng.integers(0, U, n).astype(np.float64), rng.integers(0, 3000, n).astype(np.float64),
+                     rng.integers(1, 11, n) / 2.0 / 5.0])
+    row_of = rng.permutation(U).astype(np.int32)
+    got = kn.upload_interactions(raw, cuda_dev).cpu().numpy()
+    assert np.array_equal(got[:, 0], raw[0].astype(int)) and np.array_equal(got[:, 1], raw[1].astype(int))
+    assert np.array_equal(got[:, 2].view(np.float32), raw[2].astype(np.float32)) and not got[:, 3].any()
+    got = kn.upload_interactions(raw, cuda_dev, torch.tensor(row_of, device=cuda_dev)).cpu().numpy()
+    assert np.array_equal(got[:, 0], row_of[raw[0].astype(int)])
+    assert np.array_equal(got, kn.pack_interactions(row_of[raw[0].astype(int)], raw[1], raw[2], cuda_dev).cpu().numpy())
+    assert kn.upload_interactions(np.zeros((3, 0)), cuda_dev).shape == (0, 4)

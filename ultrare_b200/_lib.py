@@ -31,12 +31,12 @@ class MFHParams(C.Structure):
     """ure_mf_hparams_t"""
     _fields_ = [("d", _i32), ("batch", _i32), ("lr0", _f32), ("lr_decay", _f32), ("lr_step", _i32),
                 ("weight_decay", _f32), ("momentum", _f32), ("mode", _i32), ("decay", _p), ("decay_len", _i32),
-                ("owner_smem", _i32)]
+                ("owner_smem", _i32), ("owner_cached", _i32), ("reserved", _i32)]
 
 
 MF_DENSE, MF_LAZY, MF_OWNER = 0, 1, 2
 
-assert C.sizeof(MFShard) == 160 and C.sizeof(MFHParams) == 48
+assert C.sizeof(MFShard) == 160 and C.sizeof(MFHParams) == 56
 
 # name -> (restype, argtypes); every symbol include/ultrare_b200.h declares
 SIGNATURES = {
@@ -52,6 +52,7 @@ SIGNATURES = {
     "ure_ensemble_score": (C.c_int, [_p, _p, C.c_int, C.c_int, _p, _i64, _f32, _p, _p, _p]),
     "ure_score_finalize": (C.c_int, [_p, _p, _i64, _f32, _p, _p, _p]),
     "ure_rank_metrics": (C.c_int, [_p, _p, _p, _p, _i64, _p, _p]),
+    "ure_pack_interactions_f64": (C.c_int, [_p, _i64, _i64, _p, _i32, _p, _p]),
     "ure_route_deletions": (C.c_int, [_p, _i32, _p, _i32, _p, _i32, _p]),
     "ure_merge_user_rows": (C.c_int, [_p, _p, _p, _p, _p, _i32, C.c_int, C.c_int, _p]),
     "ure_cost_matrix": (C.c_int, [_p, _i64, C.c_int, _p, C.c_int, C.c_int, _p, _p, _p]),

@@ -36,7 +36,7 @@ struct OwnerWs {
   int avail_smem;         // what the launch can give
   int max_rows;           // max rows (user + item) per CTA
   int max_slots;          // max interactions (user side + item side) per CTA
-  int planned_grid;       // grid size the plan was made for
+  int need_cached;        // written by plan_kernel: the same with the record cache
   int planned_K;
   int trace_steps;        // diagnostics (ure_mf_train_trace): stamps of the first trace_steps steps of a launch
   int pad0;
@@ -124,19 +124,19 @@ __device__ void make_plan(const ure_mf_shard_t* shards, int K, int cta, int n_ct
 }
 
 constexpr int kRing = 256;                // per-warp queue of batch slots (entries, power of two)
+constexpr int kOtherBits = 20;            // record cache: other-table row in the low 20 bits, own row above
 
 // Dynamic shared memory of a CTA with `rows` owned rows and `slots` owned interactions (both sides):
-//   w, buf, g [rows][d] fp32 | boundary rows [2*warps][d] fp32 | rowslot [rows+1] int | queues [warps][kRing] u16
+//   w, buf, g [rows][d] fp32 | boundary rows [2*warps][d] fp32 | queues [warps][kRing] u16
 //   | step_of [2][slots] u8 (u16 when steps/epoch > 255)                    -- the minimum, plus, when it fits,
-//   other [slots] int | rating [slots] fp32 | own row [slots] u16           -- the record cache.
+//   {other | own row << 20, rating} [slots] 8 B                              -- the record cache.
 __host__ __device__ inline long long owner_smem_fixed(int rows, int slots, int d, int spe) {
   const long long m_pad = (slots + 15) & ~15;
-  return (long long)rows * d * 12 + 64ll * d * 4 + (long long)(rows + 4) * 4 + 32ll * kRing * 2 +
-         2 * m_pad * (spe > 255 ? 2 : 1) + 64;
+  return (long long)rows * d * 12 + 64ll * d * 4 + 32ll * kRing * 2 + 2 * m_pad * (spe > 255 ? 2 : 1) + 64;
 }
 __host__ __device__ inline long long owner_smem_cache(int slots) {
   const long long m_pad = (slots + 15) & ~15;
-  return m_pad * 10;
+  return m_pad * 8;
 }
 
 __global__ void plan_kernel(const ure_mf_shard_t* shards, int K, int d, int batch, OwnerWs* ws) {
@@ -148,9 +148,13 @@ __global__ void plan_kernel(const ure_mf_shard_t* shards, int K, int d, int batc
     const int spe = (shards[pl.shard].n + batch - 1) / batch;
     const long long need = owner_smem_fixed(rows, m, d, spe);
     atomicMax(&ws->need_smem, (int)min(need, 0x7fffffffll));
+    atomicMax(&ws->need_cached, (int)min(need + owner_smem_cache(m), 0x7fffffffll));
     atomicMax(&ws->max_rows, rows);
     atomicMax(&ws->max_slots, m);
-    if (m > 65535 * 32 || rows > 65535 || spe > 65535) atomicMax(&ws->need_smem, 0x7fffffff);
+    const ure_mf_shard_t& sh = shards[pl.shard];
+    if (m > 65535 * 32 || spe > 65535) atomicMax(&ws->need_smem, 0x7fffffff);
+    if (rows >= (1 << (32 - kOtherBits)) || sh.n_user > (1 << kOtherBits) || sh.n_item > (1 << kOtherBits))
+      atomicMax(&ws->need_cached, 0x7fffffff);
   }
 }
 
@@ -226,10 +230,12 @@ __global__ void perm_inverse_kernel(const ure_mf_shard_t* shards, int epochs) {
 }
 
 // ---------------------------------------------------------------- the training kernel
-template <int D>
+// The loop below is issue-bound (ncu: ~60 % issue-slot utilisation, profiles/): 32-bit shared-memory indexing,
+// packed cache records and compile-time CACHED keep its instruction count down.
+template <int D, bool CACHED>
 __global__ void __launch_bounds__(kOwnThreads, 1)
 mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams_t hp, int epochs,
-                long long step_begin, long long step_end, OwnerWs* ws, unsigned dbg, int smem_bytes) {
+                long long step_begin, long long step_end, OwnerWs* ws, unsigned dbg) {
   constexpr int G = D / 4;                 // lanes per row / interaction
   constexpr int GPW = 32 / G;              // lane groups per warp
   constexpr int QB = 4;                    // interactions a group handles per wave (gathers in flight per lane)
@@ -247,43 +253,37 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
   make_plan(shards, K, blockIdx.x, gridDim.x, s_pl, s_ps);
   if (tid == 0) s_sh = shards[s_pl.shard];
   __syncthreads();
-  const Plan pl = s_pl;
   const ure_mf_shard_t& sh = s_sh;
-  const int rowsU = pl.ru1 - pl.ru0, rowsI = pl.ri1 - pl.ri0, rows = rowsU + rowsI;
-  const int m = pl.mU + pl.mI;
+  const int ru0 = s_pl.ru0, ri0 = s_pl.ri0, mU = s_pl.mU;
+  const int rowsU = s_pl.ru1 - ru0, rows = rowsU + (s_pl.ri1 - ri0);
+  const int m = mU + s_pl.mI;
   const int B = hp.batch;
   const int n = sh.n;
   const int spe = (n + B - 1) / B;
   const long long t_end = spe > 0 ? min(step_end, (long long)spe * epochs) : step_begin;
   if (t_end <= step_begin) return;         // the whole shard (all of its CTAs) has nothing to do
 
-  // ---- shared-memory carve-up
+  // ---- shared-memory carve-up (all indices are 32-bit element offsets)
   const int m_pad = (m + 15) & ~15;
   const bool wide = spe > 255;             // step_of entries: u8, or u16 for long epochs
-  float* const s_w = reinterpret_cast<float*>(dyn);
-  float* const s_b = s_w + (size_t)rows * D;
-  float* const s_g = s_b + (size_t)rows * D;
-  float* const s_bnd = s_g + (size_t)rows * D;                              // [2*NW][D] boundary-row partial sums
-  int* const s_rowslot = reinterpret_cast<int*>(s_bnd + (size_t)2 * NW * D);   // [rows+1] CTA-local first slot
-  unsigned short* const s_ring = reinterpret_cast<unsigned short*>(s_rowslot + rows + 4) + warp * kRing;
-  unsigned char* const s_step8 = reinterpret_cast<unsigned char*>(
-      (reinterpret_cast<uintptr_t>(s_ring - warp * kRing + NW * kRing) + 15) & ~uintptr_t(15));
+  // fixed-size arrays first (compile-time offsets), then one interleaved record per owned row
+  constexpr int RS = 3 * D;                // row stride in floats: [w | buf | g]
+  float* const s_bnd = reinterpret_cast<float*>(dyn);                       // [2*NW][D] boundary-row partial sums
+  unsigned short* const s_rings = reinterpret_cast<unsigned short*>(s_bnd + 2 * NW * D);
+  unsigned short* const s_ring = s_rings + warp * kRing;
+  float* const s_w = reinterpret_cast<float*>(s_rings + NW * kRing);        // row r: s_w + r*RS
+  float* const s_b = s_w + D;
+  float* const s_g = s_w + 2 * D;
+  unsigned char* const s_step8 = reinterpret_cast<unsigned char*>(s_w + rows * RS);        // 16-byte aligned
   unsigned short* const s_step16 = reinterpret_cast<unsigned short*>(s_step8);
-  unsigned char* carve = s_step8 + (size_t)2 * m_pad * (wide ? 2 : 1);
-  carve = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(carve) + 15) & ~uintptr_t(15));
-  const bool cached = owner_smem_fixed(rows, m, D, spe) + owner_smem_cache(m) <= (long long)smem_bytes;
-  int* s_other = nullptr;
-  float* s_rating = nullptr;
-  unsigned short* s_row = nullptr;
-  if (cached) {
-    s_other = reinterpret_cast<int*>(carve);
-    s_rating = reinterpret_cast<float*>(s_other + m_pad);
-    s_row = reinterpret_cast<unsigned short*>(s_rating + m_pad);
-  }
+  uint2* const s_rec = reinterpret_cast<uint2*>(s_step8 + 2 * m_pad * (wide ? 2 : 1));     // CACHED only
 
-  const int4* const recU = reinterpret_cast<const int4*>(sh.inter_u + pl.su0);           // slot sl < mU
-  const int4* const recI = reinterpret_cast<const int4*>(sh.inter_i + pl.si0) - pl.mU;   // slot sl >= mU
-  auto row_of_rec = [&](const int4& rec, bool it) { return it ? rec.y - pl.ri0 + rowsU : rec.x - pl.ru0; };
+  const int4* const recU = reinterpret_cast<const int4*>(sh.inter_u + s_pl.su0);           // slot sl < mU
+  const int4* const recI = reinterpret_cast<const int4*>(sh.inter_i + s_pl.si0) - mU;      // slot sl >= mU
+  auto pack_rec = [&](const int4& rec, bool it) {       // {other | own row << kOtherBits, rating}
+    const unsigned row = (unsigned)(it ? rec.y - ri0 + rowsU : rec.x - ru0);
+    return make_uint2((unsigned)(it ? rec.x : rec.y) | (row << kOtherBits), (unsigned)rec.z);
+  };
 
   // this warp's slots [w0, w1): a contiguous, row-sorted range; only its first and last row can be shared with
   // other warps -- their partial sums go to the warp's two boundary records, everything else straight to s_g
@@ -291,36 +291,25 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
   const int w0 = min(warp * per, m), w1 = min(w0 + per, m);
   int rowF = -1, rowL = -1;
   if (w0 < w1) {
-    rowF = row_of_rec(__ldg((w0 >= pl.mU ? recI : recU) + w0), w0 >= pl.mU);
-    rowL = row_of_rec(__ldg((w1 - 1 >= pl.mU ? recI : recU) + (w1 - 1)), w1 - 1 >= pl.mU);
+    rowF = (int)(pack_rec(__ldg((w0 >= mU ? recI : recU) + w0), w0 >= mU).x >> kOtherBits);
+    rowL = (int)(pack_rec(__ldg((w1 - 1 >= mU ? recI : recU) + (w1 - 1)), w1 - 1 >= mU).x >> kOtherBits);
   }
-  float* const bndF = s_bnd + (size_t)(2 * warp) * D;
-  float* const bndL = bndF + D;
+  const int offF = (int)(s_bnd - s_g) + 2 * warp * D, offL = offF + D;      // float offsets relative to s_g
 
-  // ---- prologue: owned rows -> shared memory, slot offsets, record cache
+  // ---- prologue: owned rows -> shared memory, record cache
   for (int x = tid; x < rows * G; x += kOwnThreads) {
     const int r = x / G, c = x % G;
     const bool it = r >= rowsU;
-    const size_t go = (size_t)(it ? pl.ri0 + (r - rowsU) : pl.ru0 + r) * D + 4 * c;
-    *reinterpret_cast<float4*>(s_w + (size_t)r * D + 4 * c) = ld_cg_f4((it ? sh.Q : sh.P) + go);
-    *reinterpret_cast<float4*>(s_b + (size_t)r * D + 4 * c) = ld_cg_f4((it ? sh.bufQ : sh.bufP) + go);
-    *reinterpret_cast<float4*>(s_g + (size_t)r * D + 4 * c) = make_float4(0.f, 0.f, 0.f, 0.f);
+    const size_t go = (size_t)(it ? ri0 + (r - rowsU) : ru0 + r) * D + 4 * c;
+    *reinterpret_cast<float4*>(s_w + r * RS + 4 * c) = ld_cg_f4((it ? sh.Q : sh.P) + go);
+    *reinterpret_cast<float4*>(s_b + r * RS + 4 * c) = ld_cg_f4((it ? sh.bufQ : sh.bufP) + go);
+    *reinterpret_cast<float4*>(s_g + r * RS + 4 * c) = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   for (int x = tid; x < 2 * NW * G; x += kOwnThreads)
-    *reinterpret_cast<float4*>(s_bnd + 4 * (size_t)x) = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int r = tid; r <= rows; r += kOwnThreads)
-    s_rowslot[r] = r <= rowsU ? sh.off_u[pl.ru0 + r] - pl.su0
-                              : pl.mU + sh.off_i[pl.ri0 + (r - rowsU)] - pl.si0;
+    *reinterpret_cast<float4*>(s_bnd + 4 * x) = make_float4(0.f, 0.f, 0.f, 0.f);
   if (lane == 0) { s_bkey[2 * warp] = rowF; s_bkey[2 * warp + 1] = rowL; s_wsse[warp] = 0.f; }
-  if (cached) {
-    for (int sl = tid; sl < m; sl += kOwnThreads) {
-      const bool it = sl >= pl.mU;
-      const int4 rec = __ldg((it ? recI : recU) + sl);
-      s_other[sl] = it ? rec.x : rec.y;
-      s_rating[sl] = __int_as_float(rec.z);
-      s_row[sl] = (unsigned short)row_of_rec(rec, it);
-    }
-  }
+  if (CACHED)
+    for (int sl = tid; sl < m; sl += kOwnThreads) s_rec[sl] = pack_rec(__ldg((sl >= mU ? recI : recU) + sl), sl >= mU);
   // the pad of both step_of buffers never matches a step number
   for (int x = m + tid; x < m_pad; x += kOwnThreads) {
     if (wide) { s_step16[x] = 0xffffu; s_step16[m_pad + x] = 0xffffu; }
@@ -333,7 +322,7 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
   const uint32_t magic = (uint32_t)(0x100000000ull / (uint32_t)B);     // floor(2^32/B): quotient low by <= 1
   auto fill_step_of = [&](int epoch, int lo, int hi) {
     constexpr int NI = 3;
-    const size_t ob = (size_t)(epoch & 1) * m_pad;
+    const int ob = (epoch & 1) * m_pad;
     FeistelKeys ks;
     ks.init(perm_key(sh.perm_seed, (uint32_t)sh.shard_id, (uint32_t)epoch));
     const int32_t* pinv = sh.perm_inv ? sh.perm_inv + (long long)epoch * n : nullptr;
@@ -345,7 +334,7 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
         const int sl = s0 + u * kOwnThreads;
         live[u] = sl < hi;
         x[u] = 0;
-        if (live[u]) x[u] = (uint32_t)__ldg(&((sl >= pl.mU ? recI : recU) + sl)->w);
+        if (live[u]) x[u] = (uint32_t)__ldg(&((sl >= mU ? recI : recU) + sl)->w);
       }
       if (pinv) {
 #pragma unroll
@@ -376,7 +365,8 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
   };
   float nlr = -lr_of(e);
   const float wd = hp.weight_decay, mu = hp.momentum;
-  unsigned* const counter = &ws->bar[pl.shard][0];
+  unsigned* const counter = &ws->bar[s_pl.shard][0];
+  const unsigned n_cta = (unsigned)s_pl.c;
   unsigned bar_target = 0;
   double epoch_sse = 0.0;                  // thread 0 only
   long long* const trace = ws->trace;
@@ -389,7 +379,7 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
   // are at different program points (a __syncwarp between them), across warps only rowF / rowL can collide.
   auto flush = [&](int row, const float4& a) {
     if (row >= 0) {
-      float4* gp = reinterpret_cast<float4*>((row == rowF ? bndF : row == rowL ? bndL : s_g + (size_t)row * D) + 4 * gl);
+      float4* gp = reinterpret_cast<float4*>(s_g + (row == rowF ? offF : row == rowL ? offL : row * RS) + 4 * gl);
       float4 v = *gp;
       v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
       *gp = v;
@@ -397,12 +387,11 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
   };
 
   for (long long t = step_begin; t < t_end; ++t) {
-    const int rd = (int)((t - step_begin) & 1);
+    const bool rd = (t - step_begin) & 1;
     const float* const Pr = rd ? sh.gP : sh.P;
     const float* const Qr = rd ? sh.gQ : sh.Q;
-    float* const Pw = rd ? sh.P : sh.gP;
-    float* const Qw = rd ? sh.Q : sh.gQ;
-    const size_t sb = (size_t)(e & 1) * m_pad;
+    const int sb = (e & 1) * m_pad;
+    const unsigned k4 = (unsigned)k * (wide ? 0x00010001u : 0x01010101u);
     float sse_l = 0.f;
     URE_STAMP(0)
 
@@ -413,16 +402,15 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
     for (;;) {
       while ((int)(q_wr - q_rd) < WAVE && scan < w1) {
         const int sl = scan + 4 * lane;    // this lane's 4 slots of the 128-slot window
-        unsigned hits = 0;
+        unsigned hits = 0;                 // bit i: slot sl+i belongs to this batch
         if (sl < w1) {
           if (wide) {
             const uint2 v = *reinterpret_cast<const uint2*>(s_step16 + sb + sl);
-            hits = ((v.x & 0xffffu) == (unsigned)k) | (((v.x >> 16) == (unsigned)k) << 1) |
-                   (((v.y & 0xffffu) == (unsigned)k) << 2) | (((v.y >> 16) == (unsigned)k) << 3);
+            const unsigned a = __vcmpeq2(v.x, k4), b = __vcmpeq2(v.y, k4);
+            hits = (a & 1u) | ((a >> 15) & 2u) | ((b & 1u) << 2) | ((b >> 13) & 8u);
           } else {
-            const unsigned v = *reinterpret_cast<const unsigned*>(s_step8 + sb + sl);
-            hits = ((v & 0xffu) == (unsigned)k) | ((((v >> 8) & 0xffu) == (unsigned)k) << 1) |
-                   ((((v >> 16) & 0xffu) == (unsigned)k) << 2) | (((v >> 24) == (unsigned)k) << 3);
+            const unsigned a = __vcmpeq4(*reinterpret_cast<const unsigned*>(s_step8 + sb + sl), k4);
+            hits = (a & 1u) | ((a >> 7) & 2u) | ((a >> 14) & 4u) | ((a >> 21) & 8u);
           }
           if (sl + 4 > w1) hits &= (1u << (w1 - sl)) - 1u;     // slots of the next warp / the pad
         }
@@ -434,9 +422,10 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
           if (lane >= o) incl += a;
         }
         unsigned pos = q_wr + (unsigned)(incl - c);
+        const int rel = sl - w0;
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-          if (hits & (1u << i)) s_ring[(pos++) & (kRing - 1)] = (unsigned short)(sl + i - w0);
+          if (hits & (1u << i)) s_ring[(pos++) & (kRing - 1)] = (unsigned short)(rel + i);
         q_wr += (unsigned)__shfl_sync(FULL, incl, 31);
         scan += 128;
       }
@@ -445,46 +434,38 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
       if (nent == 0) break;
 
       // ------------------------------------------------------------ one wave: QB consecutive entries per group
-      int row[QB], oth[QB];
+      int row[QB];
       float rat[QB];
       float4 o4[QB];
 #pragma unroll
       for (int q = 0; q < QB; ++q) {
-        row[q] = -1; oth[q] = 0; rat[q] = 0.f;
+        row[q] = -1; rat[q] = 0.f;
+        o4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (gw * QB + q < nent) {
           const int sl = w0 + s_ring[(q_rd + gw * QB + q) & (kRing - 1)];
-          if (cached) {
-            row[q] = s_row[sl]; oth[q] = s_other[sl]; rat[q] = s_rating[sl];
-          } else {
-            const bool it = sl >= pl.mU;
-            const int4 rec = __ldg((it ? recI : recU) + sl);
-            row[q] = row_of_rec(rec, it);
-            oth[q] = it ? rec.x : rec.y;
-            rat[q] = __int_as_float(rec.z);
-          }
+          uint2 rec;
+          if (CACHED) rec = s_rec[sl];
+          else rec = pack_rec(__ldg((sl >= mU ? recI : recU) + sl), sl >= mU);
+          row[q] = (int)(rec.x >> kOtherBits);
+          rat[q] = __uint_as_float(rec.y);
+          o4[q] = ld_cg_f4((row[q] >= rowsU ? Pr : Qr) + (size_t)(rec.x & ((1u << kOtherBits) - 1u)) * D + 4 * gl);
         }
       }
       q_rd += (unsigned)nent;
-#pragma unroll
-      for (int q = 0; q < QB; ++q) {
-        o4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row[q] >= 0) o4[q] = ld_cg_f4((row[q] >= rowsU ? Pr : Qr) + (size_t)oth[q] * D + 4 * gl);
-      }
       int key = -1;
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int q = 0; q < QB; ++q) {
-        float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row[q] >= 0) w = *reinterpret_cast<const float4*>(s_w + (size_t)row[q] * D + 4 * gl);
+        const float4 w = *reinterpret_cast<const float4*>(s_w + max(row[q], 0) * RS + 4 * gl);   // invalid: o4 = 0
         float dot = w.x * o4[q].x;
         dot = fmaf(w.y, o4[q].y, dot);
         dot = fmaf(w.z, o4[q].z, dot);
         dot = fmaf(w.w, o4[q].w, dot);
 #pragma unroll
         for (int o = G / 2; o > 0; o >>= 1) dot += __shfl_xor_sync(FULL, dot, o);
-        const float err = row[q] >= 0 ? dot - rat[q] : 0.f;
+        const float err = dot - rat[q];    // invalid entry: 0 - 0
         const float ge = 2.f * err;
-        if (row[q] >= 0 && row[q] < rowsU && gl == 0) sse_l = fmaf(err, err, sse_l);
+        if (row[q] < rowsU) sse_l = fmaf(err, err, sse_l);      // every lane of the group: divided by G below
         if (q > 0 && row[q] != key) {      // the row changes inside the group: the finished run goes out
           flush(key, acc);
           acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -508,7 +489,7 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
       __syncwarp();
     }
     sse_l = warp_sum(sse_l);
-    if (lane == 0) s_wsse[warp] = sse_l;
+    if (lane == 0) s_wsse[warp] = sse_l * (1.f / G);
     URE_STAMP(1)
     __syncthreads();
     URE_STAMP(2)
@@ -524,12 +505,12 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
       float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
       for (j = i; j < 2 * NW && (s_bkey[j] < 0 || s_bkey[j] == key); ++j) {
         if (s_bkey[j] < 0) continue;
-        float4* bp = reinterpret_cast<float4*>(s_bnd + (size_t)j * D + 4 * gl);
+        float4* bp = reinterpret_cast<float4*>(s_bnd + j * D + 4 * gl);
         const float4 v = *bp;
         sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
         *bp = make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      float4* gp = reinterpret_cast<float4*>(s_g + (size_t)key * D + 4 * gl);
+      float4* gp = reinterpret_cast<float4*>(s_g + key * RS + 4 * gl);
       float4 v = *gp;
       v.x += sum.x; v.y += sum.y; v.z += sum.z; v.w += sum.w;
       *gp = v;
@@ -537,24 +518,26 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
     __syncthreads();
 
     // ------------------------------------------------------------ (3) SGD update of every owned row, publication
-    for (int x = tid; x < rows * G; x += kOwnThreads) {
-      const int r = x / G, c = x % G;
-      float* gp = s_g + (size_t)r * D + 4 * c;
-      float* wp = s_w + (size_t)r * D + 4 * c;
-      float* bp = s_b + (size_t)r * D + 4 * c;
-      float4 g = *reinterpret_cast<float4*>(gp);
-      float4 w = *reinterpret_cast<float4*>(wp);
-      float4 b = *reinterpret_cast<float4*>(bp);
-      // torch SGD: d_p = g + wd*w (fma); buf = buf*mu + d_p; w = w + (-lr)*buf (fma)
-      g.x = fmaf(wd, w.x, g.x); g.y = fmaf(wd, w.y, g.y); g.z = fmaf(wd, w.z, g.z); g.w = fmaf(wd, w.w, g.w);
-      b.x = __fadd_rn(__fmul_rn(b.x, mu), g.x); b.y = __fadd_rn(__fmul_rn(b.y, mu), g.y);
-      b.z = __fadd_rn(__fmul_rn(b.z, mu), g.z); b.w = __fadd_rn(__fmul_rn(b.w, mu), g.w);
-      w.x = fmaf(nlr, b.x, w.x); w.y = fmaf(nlr, b.y, w.y); w.z = fmaf(nlr, b.z, w.z); w.w = fmaf(nlr, b.w, w.w);
-      *reinterpret_cast<float4*>(wp) = w;
-      *reinterpret_cast<float4*>(bp) = b;
-      *reinterpret_cast<float4*>(gp) = make_float4(0.f, 0.f, 0.f, 0.f);
-      const bool it = r >= rowsU;
-      st_cg_f4((it ? Qw : Pw) + (size_t)(it ? pl.ri0 + (r - rowsU) : pl.ru0 + r) * D + 4 * c, w);
+    {
+      float* const Pw = rd ? sh.P : sh.gP;
+      float* const Qw = rd ? sh.Q : sh.gQ;
+      for (int x = tid; x < rows * G; x += kOwnThreads) {
+        const int r = x / G, c = x % G;
+        float4* wp = reinterpret_cast<float4*>(s_w + r * RS + 4 * c);
+        float4* bp = wp + D / 4;
+        float4* gp = wp + D / 2;
+        float4 g = *gp, w = *wp, b = *bp;
+        // torch SGD: d_p = g + wd*w (fma); buf = buf*mu + d_p; w = w + (-lr)*buf (fma)
+        g.x = fmaf(wd, w.x, g.x); g.y = fmaf(wd, w.y, g.y); g.z = fmaf(wd, w.z, g.z); g.w = fmaf(wd, w.w, g.w);
+        b.x = __fadd_rn(__fmul_rn(b.x, mu), g.x); b.y = __fadd_rn(__fmul_rn(b.y, mu), g.y);
+        b.z = __fadd_rn(__fmul_rn(b.z, mu), g.z); b.w = __fadd_rn(__fmul_rn(b.w, mu), g.w);
+        w.x = fmaf(nlr, b.x, w.x); w.y = fmaf(nlr, b.y, w.y); w.z = fmaf(nlr, b.z, w.z); w.w = fmaf(nlr, b.w, w.w);
+        *wp = w;
+        *bp = b;
+        *gp = make_float4(0.f, 0.f, 0.f, 0.f);
+        const bool it = r >= rowsU;
+        st_cg_f4((it ? Qw : Pw) + (size_t)(it ? ri0 + (r - rowsU) : ru0 + r) * D + 4 * c, w);
+      }
     }
     __syncthreads();                       // every row of this CTA is updated and published
     URE_STAMP(3)
@@ -562,7 +545,7 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
     // ------------------------------------------------------------ barrier among the shard's CTAs
     if (tid == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
     __syncwarp();
-    bar_target += (unsigned)pl.c;
+    bar_target += n_cta;
     const bool last_of_epoch = k + 1 == spe;
     // in the barrier's shadow: this step's slice of the NEXT epoch's step_of
     if (e + 1 < epochs) fill_step_of(e + 1, (int)((long long)k * m / spe), (int)((long long)(k + 1) * m / spe));
@@ -590,9 +573,9 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
   for (int x = tid; x < rows * G; x += kOwnThreads) {
     const int r = x / G, c = x % G;
     const bool it = r >= rowsU;
-    const size_t go = (size_t)(it ? pl.ri0 + (r - rowsU) : pl.ru0 + r) * D + 4 * c;
-    st_cg_f4((it ? sh.Q : sh.P) + go, *reinterpret_cast<const float4*>(s_w + (size_t)r * D + 4 * c));
-    st_cg_f4((it ? sh.bufQ : sh.bufP) + go, *reinterpret_cast<const float4*>(s_b + (size_t)r * D + 4 * c));
+    const size_t go = (size_t)(it ? ri0 + (r - rowsU) : ru0 + r) * D + 4 * c;
+    st_cg_f4((it ? sh.Q : sh.P) + go, *reinterpret_cast<const float4*>(s_w + r * RS + 4 * c));
+    st_cg_f4((it ? sh.bufQ : sh.bufP) + go, *reinterpret_cast<const float4*>(s_b + r * RS + 4 * c));
     st_cg_f4((it ? sh.gQ : sh.gP) + go, make_float4(0.f, 0.f, 0.f, 0.f));
   }
 }
@@ -607,12 +590,12 @@ int max_dyn_smem(int* out) {
 
 template <int D>
 int launch_owner(const ure_mf_shard_t* d_shards, int K, const ure_mf_hparams_t& hp, int epochs, long long s0,
-                 long long s1, OwnerWs* ws, int smem, unsigned dbg, cudaStream_t st) {
-  auto kern = mf_owner_kernel<D>;
+                 long long s1, OwnerWs* ws, int smem, bool cached, unsigned dbg, cudaStream_t st) {
+  auto kern = cached ? mf_owner_kernel<D, true> : mf_owner_kernel<D, false>;
   URE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   URE_CUDA(cudaMemsetAsync(ws->bar, 0, sizeof(ws->bar), st));
-  void* args[] = {(void*)&d_shards, (void*)&K,  (void*)&hp,  (void*)&epochs, (void*)&s0,
-                  (void*)&s1,       (void*)&ws, (void*)&dbg, (void*)&smem};
+  void* args[] = {(void*)&d_shards, (void*)&K,  (void*)&hp, (void*)&epochs,
+                  (void*)&s0,       (void*)&s1, (void*)&ws, (void*)&dbg};
   URE_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(num_sms()), dim3(kOwnThreads), args, (size_t)smem, st));
   return 0;
 }
@@ -647,13 +630,14 @@ int mf_train_owner(const ure_mf_shard_t* d_shards, int n_shards, const ure_mf_hp
               "dense or lazy schedule for this problem size", hp->owner_smem, avail);
   if (step_end <= step_begin) return 0;
   auto* ws = static_cast<OwnerWs*>(d_workspace);
-  const int smem = avail;                  // everything: what the plan does not need caches records / lengthens the list
+  const int smem = hp->owner_smem;
+  const bool cached = hp->owner_cached != 0;
   switch (hp->d) {
-    case 8: return launch_owner<8>(d_shards, n_shards, *hp, epochs, step_begin, step_end, ws, smem, g_owner_dbg, st);
-    case 16: return launch_owner<16>(d_shards, n_shards, *hp, epochs, step_begin, step_end, ws, smem, g_owner_dbg, st);
-    case 32: return launch_owner<32>(d_shards, n_shards, *hp, epochs, step_begin, step_end, ws, smem, g_owner_dbg, st);
-    case 64: return launch_owner<64>(d_shards, n_shards, *hp, epochs, step_begin, step_end, ws, smem, g_owner_dbg, st);
-    case 128: return launch_owner<128>(d_shards, n_shards, *hp, epochs, step_begin, step_end, ws, smem, g_owner_dbg, st);
+    case 8: return launch_owner<8>(d_shards, n_shards, *hp, epochs, step_begin, step_end, ws, smem, cached, g_owner_dbg, st);
+    case 16: return launch_owner<16>(d_shards, n_shards, *hp, epochs, step_begin, step_end, ws, smem, cached, g_owner_dbg, st);
+    case 32: return launch_owner<32>(d_shards, n_shards, *hp, epochs, step_begin, step_end, ws, smem, cached, g_owner_dbg, st);
+    case 64: return launch_owner<64>(d_shards, n_shards, *hp, epochs, step_begin, step_end, ws, smem, cached, g_owner_dbg, st);
+    case 128: return launch_owner<128>(d_shards, n_shards, *hp, epochs, step_begin, step_end, ws, smem, cached, g_owner_dbg, st);
     default:
       set_error("ure_mf_train(owner): d=%d not in {8,16,32,64,128}", hp->d);
       return URE_EUNSUPPORTED;
@@ -677,7 +661,7 @@ extern "C" int ure_mf_owner_prepare(const ure_mf_shard_t* d_shards, int n_shards
   perm_inverse_kernel<<<dim3(blocks, n_shards), 256, 0, st>>>(d_shards, epochs);
   int avail = 0;
   if (int rc = max_dyn_smem(&avail)) return rc;
-  const int head[8] = {0, avail, 0, 0, num_sms(), n_shards, 0, 0};
+  const int head[8] = {0, avail, 0, 0, 0, n_shards, 0, 0};
   URE_CUDA(cudaMemcpyAsync(ws, head, sizeof(head), cudaMemcpyHostToDevice, st));
   plan_kernel<<<num_sms(), 32, 0, st>>>(d_shards, n_shards, h_hp->d, h_hp->batch, ws);
   URE_CUDA(cudaGetLastError());

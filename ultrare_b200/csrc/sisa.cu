@@ -36,8 +36,32 @@ __global__ void merge_kernel(const float* const* __restrict__ Pk, const int32_t*
   *dst = __ldg(reinterpret_cast<const float4*>(Pk[s]) + row * d4 + c);
 }
 
+__global__ void pack_f64_kernel(const double* __restrict__ cols, long long n, long long ld,
+                                const int32_t* __restrict__ row_of, int n_map, int4* __restrict__ out) {
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (long long)gridDim.x * blockDim.x) {
+    int u = (int)cols[j];
+    const int it = (int)cols[ld + j];
+    const float r = (float)cols[2 * ld + j];                // float32(float64): round to nearest even, as NumPy
+    if (row_of) u = (u >= 0 && u < n_map) ? row_of[u] : -1;
+    out[j] = make_int4(u, it, __float_as_int(r), 0);
+  }
+}
+
 }  // namespace
 }  // namespace ure
+
+extern "C" int ure_pack_interactions_f64(const double* d_cols, int64_t n, int64_t ld, const int32_t* d_row_of,
+                                         int32_t n_map, ure_inter_t* d_out, void* stream) {
+  using namespace ure;
+  URE_REQUIRE((d_cols && d_out) || n == 0, URE_EINVAL, "ure_pack_interactions_f64: null argument");
+  URE_REQUIRE(ld >= n, URE_EINVAL, "ure_pack_interactions_f64: ld < n");
+  if (n <= 0) return 0;
+  const int blocks = (int)((n + 255) / 256 < (long long)(8 * num_sms()) ? (n + 255) / 256 : 8 * num_sms());
+  pack_f64_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_cols, n, ld, d_row_of, n_map,
+                                                                          reinterpret_cast<int4*>(d_out));
+  URE_CUDA(cudaGetLastError());
+  return 0;
+}
 
 extern "C" int ure_route_deletions(const int32_t* d_owner, int32_t n_user, const int32_t* d_del, int32_t n_del,
                                    int32_t* d_flags, int32_t n_shards, void* stream) {

@@ -32,7 +32,7 @@ def _need_cuda(*ts):
 
 
 # ------------------------------------------------------------------------------ interactions
-_PACK_THREADS = 4
+_PACK_THREADS = 8
 _POOL = []
 
 
@@ -88,6 +88,71 @@ def pack_interactions(users, items, ratings, device) -> torch.Tensor:
         ev.record()
         _PINNED[stage.shape[0]].append((stage, ev))      # reusable once the copy has completed
     return out
+
+
+_PINNED_BYTES = {}   # capacity -> list of (pinned uint8 buffer, event): staging for raw float64 uploads
+
+
+def _staging_bytes(nbytes: int) -> torch.Tensor:
+    cap = 1 << max(16, int(nbytes - 1).bit_length())
+    pool = _PINNED_BYTES.setdefault(cap, [])
+    for item in pool:
+        if item[1] is None or item[1].query():
+            pool.remove(item)
+            return item[0]
+    return torch.empty(cap, dtype=torch.uint8, pin_memory=True)
+
+
+def upload_interactions_many(raws, device, row_of: Optional[torch.Tensor] = None) -> List[torch.Tensor]:
+    """float64 [3, n] arrays (uid, iid, rating/max_rating: what readRating returns, reference read.py:64-68) ->
+    int32 [n,4] ure_inter_t records on `device`, packed ON the device (ure_pack_interactions_f64).
+
+    The host only moves bytes: every array is copied into pinned staging memory (one thread per array, NumPy
+    releases the GIL) and uploaded asynchronously; the casts of RatingData (read.py:111-113,124) and the optional
+    user -> compact-row mapping (`row_of`, int32 device tensor) run in the pack kernel."""
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError("ultrare_b200: interactions are packed on a CUDA device (no CPU path exists)")
+    arrs, stages = [], []
+    for raw in raws:
+        raw = np.asarray(raw)
+        if raw.ndim != 2 or raw.dtype != np.float64 or raw.shape[0] != 3:
+            raw = np.ascontiguousarray(np.asarray(raw).reshape(3, -1)[:3], dtype=np.float64)
+        arrs.append(raw)
+        stages.append(_staging_bytes(24 * raw.shape[1]) if raw.shape[1] else None)
+
+    def fill(j):
+        n = arrs[j].shape[1]
+        np.copyto(stages[j].numpy()[:24 * n].view(np.float64).reshape(3, n), arrs[j])
+
+    todo = [j for j, a in enumerate(arrs) if a.shape[1]]
+    if len(todo) > 1 and sum(arrs[j].shape[1] for j in todo) >= (1 << 16):
+        list(_pack_pool().map(fill, todo))
+    else:
+        for j in todo:
+            fill(j)
+    outs = []
+    with torch.cuda.device(dev):
+        for j, raw in enumerate(arrs):
+            n = raw.shape[1]
+            out = torch.empty((n, 4), dtype=torch.int32, device=dev)
+            outs.append(out)
+            if n == 0:
+                continue
+            cols = torch.empty((3, n), dtype=torch.float64, device=dev)
+            cols.copy_(stages[j][:24 * n].view(torch.float64).view(3, n), non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            _PINNED_BYTES[stages[j].shape[0]].append((stages[j], ev))
+            check(_lib.lib().ure_pack_interactions_f64(_ptr(cols), n, n, _ptr(row_of),
+                                                       0 if row_of is None else int(row_of.shape[0]), _ptr(out),
+                                                       _stream()), "ure_pack_interactions_f64")
+    return outs
+
+
+def upload_interactions(raw, device, row_of: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """One array through upload_interactions_many."""
+    return upload_interactions_many([raw], device, row_of)[0]
 
 
 def pointer_table(tensors: Sequence[torch.Tensor], device) -> torch.Tensor:
@@ -154,7 +219,7 @@ class ShardBatch:
 
     def __init__(self, shards: List[ShardState], d: int, batch: int, lr: float = 1e-3, lr_decay: float = 0.95,
                  lr_step: int = 50, weight_decay: float = 0.1, momentum: float = 0.9, lazy: bool = False,
-                 mode: Optional[str] = None):
+                 mode: Optional[str] = None, owner_cache: bool = True):
         if not 1 <= len(shards) <= _lib.URE_MAX_SHARDS:
             raise ValueError(f"1..{_lib.URE_MAX_SHARDS} shards per launch")
         mode = ("lazy" if lazy else DEFAULT_MF_MODE) if mode is None else mode
@@ -168,8 +233,9 @@ class ShardBatch:
         self.ws = torch.zeros(int(_lib.lib().ure_mf_train_workspace_bytes()), dtype=torch.uint8, device=self.device)
         self.hp = MFHParams(d=d, batch=batch, lr0=lr, lr_decay=lr_decay, lr_step=lr_step,
                             weight_decay=weight_decay, momentum=momentum, mode=_lib.MF_DENSE,
-                            decay=None, decay_len=0, owner_smem=0)
+                            decay=None, decay_len=0, owner_smem=0, owner_cached=0, reserved=0)
         self.owner_plan = None
+        self._owner_cache = bool(owner_cache)       # False: keep the records in L2 (tests of the uncached variant)
         if mode in ("owner", "auto"):
             mode = self._prepare_owner(mode == "owner")
         self.mode = mode
@@ -224,9 +290,9 @@ class ShardBatch:
         with torch.cuda.device(dev):
             check(L.ure_mf_owner_prepare(_ptr(self.table), len(shards), C.byref(self.hp), self.epochs, _ptr(self.ws),
                                          _stream()), "ure_mf_owner_prepare")
-        need, avail, max_rows, max_slots = self.ws[:16].view(torch.int32).tolist()      # the one sync of the set-up
+        need, avail, max_rows, max_slots, need_c = self.ws[:20].view(torch.int32).tolist()   # the one sync of the set-up
         self.owner_plan = {"smem_need": need, "smem_avail": avail, "max_rows_per_cta": max_rows,
-                           "max_slots_per_cta": max_slots}
+                           "max_slots_per_cta": max_slots, "smem_need_cached": need_c, "cached": need_c <= avail}
         if need > avail:
             if required:
                 raise RuntimeError(f"owner mode: the busiest CTA needs {need} B of shared memory, {avail} B available")
@@ -234,7 +300,11 @@ class ShardBatch:
                 s.inter_u = s.inter_i = s.off_u = s.off_i = s.perm_inv = None
             self._owner_keep = None
             return "dense"
-        self.hp.mode, self.hp.owner_smem = _lib.MF_OWNER, need
+        self.hp.mode = _lib.MF_OWNER
+        cached = need_c <= avail and self._owner_cache
+        self.owner_plan["cached"] = cached
+        self.hp.owner_cached = int(cached)
+        self.hp.owner_smem = need_c if cached else need
         return "owner"
 
     @staticmethod

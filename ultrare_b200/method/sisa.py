@@ -161,9 +161,12 @@ class Sisa(Scratch):
                 rows = [len(self.group_index[i]) if compact else self.n_user for i in mine]
                 views = kn.alloc_shard_batch(rows, self.n_item, self.k, E, self.device,
                                              model_generator(self.seed, mine[0] + 1, self.device))
+            from ..read import RatingData
+            RatingData.upload_many([train_dlist[i].dataset for i in mine], self.device,
+                                   self._row_of if compact else None, 'sisa_local' if compact else None)
             for j, i in enumerate(mine):
                 ld = train_dlist[i]
-                rec = (ld.dataset.records_mapped(self.device, self._row_of_np, 'sisa_local') if compact
+                rec = (ld.dataset.records_mapped(self.device, self._row_of, 'sisa_local') if compact
                        else ld.dataset.records(self.device))
                 scratch = None
                 if batched:
@@ -196,6 +199,14 @@ class Sisa(Scratch):
                 self.timing['setup_ms'] = (time.time() - t0) * 1e3
                 sb.train()
                 self.timing['launch_ms'] = (time.time() - t0) * 1e3 - self.timing['setup_ms']
+                # while the GPU trains: stage what the final evaluation needs (upload + user segments are cached
+                # on the RatingData objects), so self.test() after the merge finds them resident
+                for ld in ([test_data] if test_data is not None else []) + \
+                        ([test_dlist[i] for i in mine] if mode == 'final' and self.dist.world == 1 else []):
+                    ds = getattr(ld, 'dataset', None)
+                    if ds is not None and len(ds) > 0:
+                        ds.records(self.device)
+                        ds.segments(self.device)
             self._last_batch = sb
             losses = sb.train_losses()                       # the one sync of the whole training
         self.timing['train_s'] = time.time() - t0

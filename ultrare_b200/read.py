@@ -103,15 +103,24 @@ class RatingData:
         """int32 [n,4] ure_inter_t records resident on `device` (uploaded once)."""
         key = str(device)
         if key not in self._records:
-            self._records[key] = kn.pack_interactions(self._raw[0], self._raw[1], self._raw[2], device)
+            self._records[key] = kn.upload_interactions(self._raw, device)
         return self._records[key]
 
-    def records_mapped(self, device, row_of: np.ndarray, tag: str) -> torch.Tensor:
-        """Records whose user field is row_of[user] (the row inside a compact per-shard user table)."""
+    def records_mapped(self, device, row_of: torch.Tensor, tag: str) -> torch.Tensor:
+        """Records whose user field is row_of[user] (the row inside a compact per-shard user table);
+        row_of: int32 tensor on `device`, applied by the pack kernel."""
         key = (str(device), tag)
         if key not in self._records:
-            self._records[key] = kn.pack_interactions(row_of[self.users], self._raw[1], self._raw[2], device)
+            self._records[key] = kn.upload_interactions(self._raw, device, row_of)
         return self._records[key]
+
+    @staticmethod
+    def upload_many(datasets, device, row_of=None, tag=None):
+        """records()/records_mapped() of several datasets at once: their host copies run in parallel."""
+        key = str(device) if tag is None else (str(device), tag)
+        todo = [ds for ds in datasets if key not in ds._records]
+        for ds, rec in zip(todo, kn.upload_interactions_many([ds._raw for ds in todo], device, row_of)):
+            ds._records[key] = rec
 
     def segments(self, device):
         """(order or None, seg) device tensors of the per-user test segments (utils.py:151-161)."""

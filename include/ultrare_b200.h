@@ -84,9 +84,10 @@ typedef struct {
   const float* decay;   /* lazy: DEVICE table [decay_len][4] of M^n = (a11,a12,a21,a22), the */
                         /*    n-step gradient-free update [w;buf] <- M^n [w;buf]; else NULL   */
   int32_t decay_len;    /* lazy: number of table entries (>= total steps + 1)                */
-  int32_t owner_smem;   /* OWNER: dynamic shared-memory bytes to launch with (from ure_mf_owner_prepare) */
-  int32_t owner_cached; /* OWNER: 1 = owner_smem includes the shared-memory record cache          */
-  int32_t reserved;
+  int32_t owner_cap_rows;  /* OWNER: max owned rows of a CTA, from ure_mf_owner_prepare's plan      */
+  int32_t owner_cap_slots; /* OWNER: max owned interactions of a CTA, rounded up to a multiple of 16 */
+  int32_t owner_flags;     /* OWNER: bit 0 = keep the record cache in shared memory, bit 1 = some   */
+                           /*        shard has more than 255 steps per epoch (16-bit step numbers)  */
 } ure_mf_hparams_t;
 
 /* ure_mf_hparams_t::mode -- three schedules of the SAME arithmetic (baseTrain + dense optim.SGD):
@@ -122,13 +123,16 @@ int ure_mf_train(const ure_mf_shard_t* d_shards, int n_shards, const ure_mf_hpar
 
 /* Owner mode set-up, once per shard table (asynchronous, no host sync): builds inter_u / inter_i /
  * off_u / off_i (counting sort of the records by user and by item) and perm_inv for shards with an
- * explicit perm, then plans the CTA ownership and writes into the first 20 bytes of d_workspace
- * int32 {shared-memory bytes the busiest CTA needs, bytes available, max rows per CTA, max
- * interactions per CTA, bytes needed with the record cache}: the caller reads them back once, sets
- * hparams.owner_smem / owner_cached accordingly and must not start mode OWNER when need > available
- * (ure_mf_train refuses it loudly as well). */
+ * explicit perm, then plans the CTA ownership and writes into the first 16 bytes of d_workspace
+ * int32 {max owned rows of a CTA, max owned interactions of a CTA, max steps per epoch of a shard,
+ * dynamic shared-memory bytes available}: the caller reads them back once, fills hparams.owner_cap_rows /
+ * owner_cap_slots / owner_flags and must not start mode OWNER when ure_mf_owner_smem_bytes exceeds what is
+ * available (ure_mf_train refuses it loudly as well). */
 int ure_mf_owner_prepare(const ure_mf_shard_t* d_shards, int n_shards, const ure_mf_hparams_t* h_hp,
                          int epochs, void* d_workspace, void* stream);
+
+/* Dynamic shared memory per CTA of the OWNER schedule for these capacities. */
+int64_t ure_mf_owner_smem_bytes(int d, int cap_rows, int cap_slots, int wide, int cached);
 
 /* Diagnostics (tracing): record six SM-clock stamps per CTA and step -- step start, tables ready,
  * gradients issued, barrier 1 passed, sweep issued, barrier 2 passed -- for the first `steps` steps of

@@ -31,7 +31,7 @@ class MFHParams(C.Structure):
     """ure_mf_hparams_t"""
     _fields_ = [("d", _i32), ("batch", _i32), ("lr0", _f32), ("lr_decay", _f32), ("lr_step", _i32),
                 ("weight_decay", _f32), ("momentum", _f32), ("mode", _i32), ("decay", _p), ("decay_len", _i32),
-                ("owner_smem", _i32), ("owner_cached", _i32), ("reserved", _i32)]
+                ("owner_cap_rows", _i32), ("owner_cap_slots", _i32), ("owner_flags", _i32)]
 
 
 MF_DENSE, MF_LAZY, MF_OWNER = 0, 1, 2
@@ -45,6 +45,7 @@ SIGNATURES = {
     "ure_mf_train_workspace_bytes": (_i64, []),
     "ure_mf_train": (C.c_int, [_p, C.c_int, C.POINTER(MFHParams), C.c_int, _i64, _i64, C.c_int, _p, _p]),
     "ure_mf_owner_prepare": (C.c_int, [_p, C.c_int, C.POINTER(MFHParams), C.c_int, _p, _p]),
+    "ure_mf_owner_smem_bytes": (_i64, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "ure_mf_train_trace": (C.c_int, [_p, _p, C.c_int, _p]),
     "ure_mf_grid_size": (C.c_int, []),
     "ure_mf_debug_flags": (C.c_int, [_p, C.c_uint32, _p]),

@@ -24,6 +24,7 @@
 //     semantics of the reference) with ONE barrier per step -- and only among the CTAs of the shard.
 #include "common.cuh"
 #include "feistel.cuh"
+#include <type_traits>
 
 namespace ure {
 namespace {
@@ -32,14 +33,13 @@ constexpr int kOwnThreads = 1024;
 constexpr int KMAX = URE_MAX_SHARDS;
 
 struct OwnerWs {
-  int need_smem;          // written by plan_kernel: dynamic shared memory the busiest CTA needs
-  int avail_smem;         // what the launch can give
-  int max_rows;           // max rows (user + item) per CTA
-  int max_slots;          // max interactions (user side + item side) per CTA
-  int need_cached;        // written by plan_kernel: the same with the record cache
-  int planned_K;
+  int max_rows;           // written by plan_kernel: max owned rows (user + item) of a CTA
+  int max_slots;          // max owned interactions (user side + item side) of a CTA
+  int max_spe;            // max steps per epoch of a shard
+  int avail_smem;         // dynamic shared memory a launch can get
+  int pad0[2];
   int trace_steps;        // diagnostics (ure_mf_train_trace): stamps of the first trace_steps steps of a launch
-  int pad0;
+  int pad1;
   long long* trace;       // [trace_steps][grid][6] SM-clock stamps, or NULL
   int pad[22];
   unsigned bar[KMAX][32]; // one barrier counter per shard, one 128-byte line each
@@ -123,38 +123,26 @@ __device__ void make_plan(const ure_mf_shard_t* shards, int K, int cta, int n_ct
   __syncthreads();
 }
 
-constexpr int kRing = 256;                // per-warp queue of batch slots (entries, power of two)
 constexpr int kOtherBits = 20;            // record cache: other-table row in the low 20 bits, own row above
+constexpr int kOwnWarps = kOwnThreads / 32;
 
-// Dynamic shared memory of a CTA with `rows` owned rows and `slots` owned interactions (both sides):
-//   w, buf, g [rows][d] fp32 | boundary rows [2*warps][d] fp32 | queues [warps][kRing] u16
-//   | step_of [2][slots] u8 (u16 when steps/epoch > 255)                    -- the minimum, plus, when it fits,
-//   {other | own row << 20, rating} [slots] 8 B                              -- the record cache.
-__host__ __device__ inline long long owner_smem_fixed(int rows, int slots, int d, int spe) {
-  const long long m_pad = (slots + 15) & ~15;
-  return (long long)rows * d * 12 + 64ll * d * 4 + 32ll * kRing * 2 + 2 * m_pad * (spe > 255 ? 2 : 1) + 64;
-}
-__host__ __device__ inline long long owner_smem_cache(int slots) {
-  const long long m_pad = (slots + 15) & ~15;
-  return m_pad * 8;
+// Dynamic shared memory of the training kernel.  The layout depends on LAUNCH-uniform capacities only
+// (cap_rows, cap_slots: the plan's maxima over the CTAs), so every array base is a uniform value:
+//   boundary rows [2*warps][d] fp32 | batch list [cap_slots] u16 | record cache [cap_slots] 8 B (optional)
+//   | step_of [2][cap_slots] u8 (u16 when steps/epoch > 255) | owned rows [cap_rows][3d] fp32 (w | buf | g)
+__host__ __device__ inline long long owner_smem_bytes(int d, int cap_rows, int cap_slots, bool wide, bool cached) {
+  return 2ll * kOwnWarps * d * 4 + 2ll * cap_slots + (cached ? 8ll * cap_slots : 0) +
+         2ll * cap_slots * (wide ? 2 : 1) + 12ll * cap_rows * d;
 }
 
-__global__ void plan_kernel(const ure_mf_shard_t* shards, int K, int d, int batch, OwnerWs* ws) {
+__global__ void plan_kernel(const ure_mf_shard_t* shards, int K, int batch, OwnerWs* ws) {
   __shared__ PlanScratch ps;
   __shared__ Plan pl;
   make_plan(shards, K, blockIdx.x, gridDim.x, pl, ps);
   if (threadIdx.x == 0) {
-    const int rows = (pl.ru1 - pl.ru0) + (pl.ri1 - pl.ri0), m = pl.mU + pl.mI;
-    const int spe = (shards[pl.shard].n + batch - 1) / batch;
-    const long long need = owner_smem_fixed(rows, m, d, spe);
-    atomicMax(&ws->need_smem, (int)min(need, 0x7fffffffll));
-    atomicMax(&ws->need_cached, (int)min(need + owner_smem_cache(m), 0x7fffffffll));
-    atomicMax(&ws->max_rows, rows);
-    atomicMax(&ws->max_slots, m);
-    const ure_mf_shard_t& sh = shards[pl.shard];
-    if (m > 65535 * 32 || spe > 65535) atomicMax(&ws->need_smem, 0x7fffffff);
-    if (rows >= (1 << (32 - kOtherBits)) || sh.n_user > (1 << kOtherBits) || sh.n_item > (1 << kOtherBits))
-      atomicMax(&ws->need_cached, 0x7fffffff);
+    atomicMax(&ws->max_rows, (pl.ru1 - pl.ru0) + (pl.ri1 - pl.ri0));
+    atomicMax(&ws->max_slots, pl.mU + pl.mI);
+    atomicMax(&ws->max_spe, (shards[pl.shard].n + batch - 1) / batch);
   }
 }
 
@@ -230,9 +218,9 @@ __global__ void perm_inverse_kernel(const ure_mf_shard_t* shards, int epochs) {
 }
 
 // ---------------------------------------------------------------- the training kernel
-// The loop below is issue-bound (ncu: ~60 % issue-slot utilisation, profiles/): 32-bit shared-memory indexing,
-// packed cache records and compile-time CACHED keep its instruction count down.
-template <int D, bool CACHED>
+// The loop below is issue-bound (ncu: ~60 % issue-slot utilisation, profiles/): launch-uniform array bases,
+// 32-bit shared-memory indexing, packed cache records and compile-time CACHED keep its instruction count down.
+template <int D, bool CACHED, bool WIDE>
 __global__ void __launch_bounds__(kOwnThreads, 1)
 mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams_t hp, int epochs,
                 long long step_begin, long long step_end, OwnerWs* ws, unsigned dbg) {
@@ -240,14 +228,17 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
   constexpr int GPW = 32 / G;              // lane groups per warp
   constexpr int QB = 4;                    // interactions a group handles per wave (gathers in flight per lane)
   constexpr int WAVE = GPW * QB;           // interactions per warp and wave
-  constexpr int NW = kOwnThreads / 32;
+  constexpr int NW = kOwnWarps;
+  constexpr int RS = 3 * D;                // row stride in floats: [w | buf | g]
   constexpr unsigned FULL = 0xffffffffu;
   extern __shared__ __align__(16) unsigned char dyn[];
   __shared__ PlanScratch s_ps;
   __shared__ Plan s_pl;
   __shared__ ure_mf_shard_t s_sh;
   __shared__ float s_wsse[NW];
+  __shared__ int s_wcnt[NW];
   __shared__ int s_bkey[2 * NW];           // row of every boundary record (-1: unused)
+  __shared__ FeistelKeys s_keys;           // of the epoch whose step_of is being filled
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gl = lane % G, gw = lane / G;
   make_plan(shards, K, blockIdx.x, gridDim.x, s_pl, s_ps);
@@ -263,20 +254,16 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
   const long long t_end = spe > 0 ? min(step_end, (long long)spe * epochs) : step_begin;
   if (t_end <= step_begin) return;         // the whole shard (all of its CTAs) has nothing to do
 
-  // ---- shared-memory carve-up (all indices are 32-bit element offsets)
-  const int m_pad = (m + 15) & ~15;
-  const bool wide = spe > 255;             // step_of entries: u8, or u16 for long epochs
-  // fixed-size arrays first (compile-time offsets), then one interleaved record per owned row
-  constexpr int RS = 3 * D;                // row stride in floats: [w | buf | g]
+  // ---- shared-memory carve-up: bases depend on kernel parameters only
+  const int cap = hp.owner_cap_slots;      // multiple of 16, >= m
+  using step_t = typename std::conditional<WIDE, unsigned short, unsigned char>::type;   // u16 for long epochs
   float* const s_bnd = reinterpret_cast<float*>(dyn);                       // [2*NW][D] boundary-row partial sums
-  unsigned short* const s_rings = reinterpret_cast<unsigned short*>(s_bnd + 2 * NW * D);
-  unsigned short* const s_ring = s_rings + warp * kRing;
-  float* const s_w = reinterpret_cast<float*>(s_rings + NW * kRing);        // row r: s_w + r*RS
+  unsigned short* const s_list = reinterpret_cast<unsigned short*>(s_bnd + 2 * NW * D);   // [cap] slots of the batch
+  uint2* const s_rec = reinterpret_cast<uint2*>(s_list + cap);              // [cap], CACHED only
+  step_t* const s_step = reinterpret_cast<step_t*>(s_rec + (CACHED ? cap : 0));   // [2][cap]
+  float* const s_w = reinterpret_cast<float*>(s_step + 2 * cap);            // row r: s_w + r*RS
   float* const s_b = s_w + D;
   float* const s_g = s_w + 2 * D;
-  unsigned char* const s_step8 = reinterpret_cast<unsigned char*>(s_w + rows * RS);        // 16-byte aligned
-  unsigned short* const s_step16 = reinterpret_cast<unsigned short*>(s_step8);
-  uint2* const s_rec = reinterpret_cast<uint2*>(s_step8 + 2 * m_pad * (wide ? 2 : 1));     // CACHED only
 
   const int4* const recU = reinterpret_cast<const int4*>(sh.inter_u + s_pl.su0);           // slot sl < mU
   const int4* const recI = reinterpret_cast<const int4*>(sh.inter_i + s_pl.si0) - mU;      // slot sl >= mU
@@ -284,16 +271,14 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
     const unsigned row = (unsigned)(it ? rec.y - ri0 + rowsU : rec.x - ru0);
     return make_uint2((unsigned)(it ? rec.x : rec.y) | (row << kOtherBits), (unsigned)rec.z);
   };
+  auto rec_of = [&](int sl) {
+    if (CACHED) return s_rec[sl];
+    return pack_rec(__ldg((sl >= mU ? recI : recU) + sl), sl >= mU);
+  };
 
-  // this warp's slots [w0, w1): a contiguous, row-sorted range; only its first and last row can be shared with
-  // other warps -- their partial sums go to the warp's two boundary records, everything else straight to s_g
-  const int per = (((m + NW - 1) / NW) + 3) & ~3;
+  // this warp's slots [w0, w1) of the per-step batch scan
+  const int per = (((m + NW - 1) / NW) + 15) & ~15;       // 16-byte aligned chunks of step_of
   const int w0 = min(warp * per, m), w1 = min(w0 + per, m);
-  int rowF = -1, rowL = -1;
-  if (w0 < w1) {
-    rowF = (int)(pack_rec(__ldg((w0 >= mU ? recI : recU) + w0), w0 >= mU).x >> kOtherBits);
-    rowL = (int)(pack_rec(__ldg((w1 - 1 >= mU ? recI : recU) + (w1 - 1)), w1 - 1 >= mU).x >> kOtherBits);
-  }
   const int offF = (int)(s_bnd - s_g) + 2 * warp * D, offL = offF + D;      // float offsets relative to s_g
 
   // ---- prologue: owned rows -> shared memory, record cache
@@ -307,24 +292,22 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
   }
   for (int x = tid; x < 2 * NW * G; x += kOwnThreads)
     *reinterpret_cast<float4*>(s_bnd + 4 * x) = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (lane == 0) { s_bkey[2 * warp] = rowF; s_bkey[2 * warp + 1] = rowL; s_wsse[warp] = 0.f; }
   if (CACHED)
     for (int sl = tid; sl < m; sl += kOwnThreads) s_rec[sl] = pack_rec(__ldg((sl >= mU ? recI : recU) + sl), sl >= mU);
-  // the pad of both step_of buffers never matches a step number
-  for (int x = m + tid; x < m_pad; x += kOwnThreads) {
-    if (wide) { s_step16[x] = 0xffffu; s_step16[m_pad + x] = 0xffffu; }
-    else { s_step8[x] = 0xffu; s_step8[m_pad + x] = 0xffu; }
-  }
+  // slots beyond m never match a step number
+  for (int x = m + tid; x < cap; x += kOwnThreads) s_step[x] = s_step[cap + x] = (step_t)~0u;
 
   // ---- visiting order -> step_of
   FeistelDomain dom;
   dom.init((uint32_t)n);
   const uint32_t magic = (uint32_t)(0x100000000ull / (uint32_t)B);     // floor(2^32/B): quotient low by <= 1
+  auto set_keys = [&](int epoch) {         // by one thread, a block barrier before the next fill
+    if (tid == 0) s_keys.init(perm_key(sh.perm_seed, (uint32_t)sh.shard_id, (uint32_t)epoch));
+  };
   auto fill_step_of = [&](int epoch, int lo, int hi) {
-    constexpr int NI = 3;
-    const int ob = (epoch & 1) * m_pad;
-    FeistelKeys ks;
-    ks.init(perm_key(sh.perm_seed, (uint32_t)sh.shard_id, (uint32_t)epoch));
+    constexpr int NI = 2;
+    const int ob = (epoch & 1) * cap;
+    const FeistelKeys ks = s_keys;
     const int32_t* pinv = sh.perm_inv ? sh.perm_inv + (long long)epoch * n : nullptr;
     for (int s0 = lo + tid; s0 < hi; s0 += NI * kOwnThreads) {
       uint32_t x[NI];
@@ -349,12 +332,17 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
         uint32_t q = B == 1 ? x[u] : mulhi32(x[u], magic);
         if ((q + 1) * (uint32_t)B <= x[u]) ++q;
         const int sl = s0 + u * kOwnThreads;
-        if (wide) s_step16[ob + sl] = (unsigned short)q; else s_step8[ob + sl] = (unsigned char)q;
+        s_step[ob + sl] = (step_t)q;
       }
     }
   };
   int e = (int)(step_begin / spe), k = (int)(step_begin % spe);
+  set_keys(e);
+  __syncthreads();
   fill_step_of(e, 0, m);
+  __syncthreads();
+  set_keys(e + 1);
+  __syncthreads();
   if (k > 0 && e + 1 < epochs) fill_step_of(e + 1, 0, (int)((long long)k * m / spe));
   __syncthreads();
 
@@ -375,95 +363,153 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
   if (trace && tid == 32 && (t - step_begin) < trace_steps)                        \
     trace[((t - step_begin) * gridDim.x + blockIdx.x) * 6 + (PH)] = clock64();
 
-  // run total -> the row's gradient accumulator.  Plain read-modify-write: within the warp flushes of one row
-  // are at different program points (a __syncwarp between them), across warps only rowF / rowL can collide.
-  auto flush = [&](int row, const float4& a) {
-    if (row >= 0) {
-      float4* gp = reinterpret_cast<float4*>(s_g + (row == rowF ? offF : row == rowL ? offL : row * RS) + 4 * gl);
-      float4 v = *gp;
-      v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
-      *gp = v;
-    }
-  };
-
   for (long long t = step_begin; t < t_end; ++t) {
     const bool rd = (t - step_begin) & 1;
     const float* const Pr = rd ? sh.gP : sh.P;
     const float* const Qr = rd ? sh.gQ : sh.Q;
-    const int sb = (e & 1) * m_pad;
-    const unsigned k4 = (unsigned)k * (wide ? 0x00010001u : 0x01010101u);
     float sse_l = 0.f;
     URE_STAMP(0)
 
-    // -------------------------------------------------------------- (1)+(2) the warp streams its own slots:
-    // slots of this batch are queued in slot order (= row order) and consumed a wave at a time
-    int scan = w0;                         // next slot to look at (multiple of 4)
-    unsigned q_rd = 0, q_wr = 0;           // queue counters (warp-uniform)
-    for (;;) {
-      while ((int)(q_wr - q_rd) < WAVE && scan < w1) {
-        const int sl = scan + 4 * lane;    // this lane's 4 slots of the 128-slot window
-        unsigned hits = 0;                 // bit i: slot sl+i belongs to this batch
+    // -------------------------------------------------------------- (1) the batch, as a sorted list of slots
+    // Every lane looks at 16 CONSECUTIVE slots of the warp's range per chunk (one 16-byte load), keeps their
+    // hit mask in a register, and after one block-wide prefix writes its hits: lane-major = slot-major order.
+    const step_t* const stp = s_step + (e & 1) * cap;
+    constexpr int MAXCH = 4;               // chunks of 512 slots kept in registers; longer ranges re-scan
+    unsigned hm[MAXCH];
+    int cnt = 0;
+    {
+      const unsigned k4 = (unsigned)k * (WIDE ? 0x00010001u : 0x01010101u);
+#pragma unroll
+      for (int c = 0; c < MAXCH; ++c) {
+        const int sl = w0 + 512 * c + 16 * lane;
+        unsigned mask = 0;
         if (sl < w1) {
-          if (wide) {
-            const uint2 v = *reinterpret_cast<const uint2*>(s_step16 + sb + sl);
-            const unsigned a = __vcmpeq2(v.x, k4), b = __vcmpeq2(v.y, k4);
-            hits = (a & 1u) | ((a >> 15) & 2u) | ((b & 1u) << 2) | ((b >> 13) & 8u);
+          if (WIDE) {
+            const uint4 v0 = *reinterpret_cast<const uint4*>(stp + sl), v1 = *reinterpret_cast<const uint4*>(stp + sl + 8);
+            const unsigned w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const unsigned a = __vcmpeq2(w[j], k4);
+              mask |= ((a & 1u) | ((a >> 15) & 2u)) << (2 * j);
+            }
           } else {
-            const unsigned a = __vcmpeq4(*reinterpret_cast<const unsigned*>(s_step8 + sb + sl), k4);
-            hits = (a & 1u) | ((a >> 7) & 2u) | ((a >> 14) & 4u) | ((a >> 21) & 8u);
+            const uint4 v = *reinterpret_cast<const uint4*>(stp + sl);
+            const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const unsigned a = __vcmpeq4(w[j], k4) & 0x01010101u;
+              mask |= ((a | (a >> 7) | (a >> 14) | (a >> 21)) & 0xfu) << (4 * j);
+            }
           }
-          if (sl + 4 > w1) hits &= (1u << (w1 - sl)) - 1u;     // slots of the next warp / the pad
+          if (sl + 16 > w1) mask &= (1u << (w1 - sl)) - 1u;    // slots of the next warp / the pad
         }
-        const int c = __popc(hits);
-        int incl = c;
+        hm[c] = mask;
+        cnt += __popc(mask);
+      }
+      for (int sl = w0 + 512 * MAXCH + lane; sl < w1; sl += 32) cnt += (int)stp[sl] == k;   // rare: long ranges
+    }
+    // exclusive prefix of the lanes' counts inside the warp, then of the warps inside the CTA
+    int lincl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int a = __shfl_up_sync(FULL, lincl, o);
+      if (lane >= o) lincl += a;
+    }
+    if (lane == 31) s_wcnt[warp] = lincl;
+    __syncthreads();
+    int incl = s_wcnt[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int a = __shfl_up_sync(FULL, incl, o);
+      if (lane >= o) incl += a;
+    }
+    const int total = __shfl_sync(FULL, incl, 31);
+    {
+      const int wbase = __shfl_sync(FULL, incl, warp) - __shfl_sync(FULL, lincl, 31);   // first position of the warp
+      int pos = wbase;
+      // chunk-major, lane-major inside a chunk: positions of chunk c start after all hits of chunks < c
+#pragma unroll
+      for (int c = 0; c < MAXCH; ++c) {
+        const int hc = __popc(hm[c]);
+        int ci = hc;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-          const int a = __shfl_up_sync(FULL, incl, o);
-          if (lane >= o) incl += a;
+          const int a = __shfl_up_sync(FULL, ci, o);
+          if (lane >= o) ci += a;
         }
-        unsigned pos = q_wr + (unsigned)(incl - c);
-        const int rel = sl - w0;
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if (hits & (1u << i)) s_ring[(pos++) & (kRing - 1)] = (unsigned short)(rel + i);
-        q_wr += (unsigned)__shfl_sync(FULL, incl, 31);
-        scan += 128;
+        int p = pos + ci - hc;
+        unsigned mk = hm[c];
+        const int sl = w0 + 512 * c + 16 * lane;
+        while (mk) {
+          const int bpos = __ffs(mk) - 1;
+          mk &= mk - 1;
+          s_list[p++] = (unsigned short)(sl + bpos);
+        }
+        pos += __shfl_sync(FULL, ci, 31);
+        if (w0 + 512 * (c + 1) >= w1) break;            // warp-uniform
       }
-      __syncwarp();
-      const int nent = min((int)(q_wr - q_rd), WAVE);
-      if (nent == 0) break;
+      for (int s0 = w0 + 512 * MAXCH; s0 < w1; s0 += 32) {     // rare: long ranges, one slot per lane
+        const int sl = s0 + lane;
+        const bool hit = ((int)stp[min(sl, w1 - 1)] == k) & (sl < w1);
+        const unsigned bal = __ballot_sync(FULL, hit);
+        if (hit) s_list[pos + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)sl;
+        pos += __popc(bal);
+      }
+    }
+    __syncthreads();
+    URE_STAMP(1)
 
-      // ------------------------------------------------------------ one wave: QB consecutive entries per group
+    // -------------------------------------------------------------- (2) waves: this warp's contiguous share
+    // Only the first and the last row of the share can be shared with other warps: their partial sums go to the
+    // warp's two boundary records, everything else straight to the row's accumulator (plain read-modify-write:
+    // within the warp, flushes of one row are at different program points with a __syncwarp between them).
+    const int n_waves = (total + WAVE - 1) / WAVE;
+    const int wv0 = warp * (n_waves / NW) + min(warp, n_waves % NW);
+    const int wv1 = wv0 + n_waves / NW + (warp < n_waves % NW ? 1 : 0);
+    const int ent1 = min(total, wv1 * WAVE);
+    int rowF = -1, rowL = -1;
+    if (wv0 < wv1) {
+      rowF = (int)(rec_of(s_list[wv0 * WAVE]).x >> kOtherBits);
+      rowL = (int)(rec_of(s_list[ent1 - 1]).x >> kOtherBits);
+    }
+    if (lane == 0) { s_bkey[2 * warp] = rowF; s_bkey[2 * warp + 1] = rowL; }
+    auto flush = [&](int row, const float4& a) {
+      if (row >= 0) {
+        float4* gp = reinterpret_cast<float4*>(s_g + (row == rowF ? offF : row == rowL ? offL : row * RS) + 4 * gl);
+        float4 v = *gp;
+        v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+        *gp = v;
+      }
+    };
+    for (int wv = wv0; wv < wv1; ++wv) {
+      const int ent0 = wv * WAVE + gw * QB;
       int row[QB];
       float rat[QB];
       float4 o4[QB];
 #pragma unroll
-      for (int q = 0; q < QB; ++q) {
-        row[q] = -1; rat[q] = 0.f;
-        o4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (gw * QB + q < nent) {
-          const int sl = w0 + s_ring[(q_rd + gw * QB + q) & (kRing - 1)];
-          uint2 rec;
-          if (CACHED) rec = s_rec[sl];
-          else rec = pack_rec(__ldg((sl >= mU ? recI : recU) + sl), sl >= mU);
-          row[q] = (int)(rec.x >> kOtherBits);
-          rat[q] = __uint_as_float(rec.y);
-          o4[q] = ld_cg_f4((row[q] >= rowsU ? Pr : Qr) + (size_t)(rec.x & ((1u << kOtherBits) - 1u)) * D + 4 * gl);
-        }
+      for (int q = 0; q < QB; ++q) {       // branch-free: entries past the end re-read the last one, weight 0
+        const uint2 rec = rec_of(s_list[min(ent0 + q, ent1 - 1)]);
+        const bool ok = ent0 + q < ent1;
+        const int r = (int)(rec.x >> kOtherBits);
+        row[q] = ok ? r : -1;
+        rat[q] = __uint_as_float(rec.y);
+        // L1-allocating load: a CTA re-reads popular rows within a step; the acquire load that ends every
+        // barrier invalidates L1 (CCTL.IVALL), so no line survives into the step that rewrites its buffer
+        o4[q] = __ldca(reinterpret_cast<const float4*>((r >= rowsU ? Pr : Qr) +
+                                                       (size_t)(rec.x & ((1u << kOtherBits) - 1u)) * D + 4 * gl));
       }
-      q_rd += (unsigned)nent;
       int key = -1;
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int q = 0; q < QB; ++q) {
-        const float4 w = *reinterpret_cast<const float4*>(s_w + max(row[q], 0) * RS + 4 * gl);   // invalid: o4 = 0
+        const float4 w = *reinterpret_cast<const float4*>(s_w + max(row[q], 0) * RS + 4 * gl);
         float dot = w.x * o4[q].x;
         dot = fmaf(w.y, o4[q].y, dot);
         dot = fmaf(w.z, o4[q].z, dot);
         dot = fmaf(w.w, o4[q].w, dot);
 #pragma unroll
         for (int o = G / 2; o > 0; o >>= 1) dot += __shfl_xor_sync(FULL, dot, o);
-        const float err = dot - rat[q];    // invalid entry: 0 - 0
+        const float err = row[q] >= 0 ? dot - rat[q] : 0.f;
         const float ge = 2.f * err;
         if (row[q] < rowsU) sse_l = fmaf(err, err, sse_l);      // every lane of the group: divided by G below
         if (q > 0 && row[q] != key) {      // the row changes inside the group: the finished run goes out
@@ -474,7 +520,7 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
         acc.x = fmaf(ge, o4[q].x, acc.x); acc.y = fmaf(ge, o4[q].y, acc.y);
         acc.z = fmaf(ge, o4[q].z, acc.z); acc.w = fmaf(ge, o4[q].w, acc.w);
       }
-      // segmented reduction of the groups' trailing runs (the queue is sorted, equal rows are adjacent)
+      // segmented reduction of the groups' trailing runs (the list is sorted, equal rows are adjacent)
 #pragma unroll
       for (int o = 1; o < GPW; o <<= 1) {
         const int k2 = __shfl_down_sync(FULL, key, o * G);
@@ -490,12 +536,11 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
     }
     sse_l = warp_sum(sse_l);
     if (lane == 0) s_wsse[warp] = sse_l * (1.f / G);
-    URE_STAMP(1)
     __syncthreads();
     URE_STAMP(2)
 
     // ------------------------------------------------------------ boundary rows: first record of a row adds
-    // up every record of that row (they are adjacent: records are in slot order) into s_g
+    // up every record of that row (they are adjacent: records are in list order) into its accumulator
     for (int i = tid / G; i < 2 * NW; i += kOwnThreads / G) {
       const int key = s_bkey[i];
       if (key < 0) continue;
@@ -563,8 +608,12 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
     }
     __syncthreads();
     URE_STAMP(5)
-    if (last_of_epoch) { ++e; k = 0; nlr = -lr_of(e); }
-    else ++k;
+    if (last_of_epoch) {
+      ++e; k = 0; nlr = -lr_of(e);
+      set_keys(e + 1);                     // read by the fill after this step's block barriers
+    } else {
+      ++k;
+    }
   }
 #undef URE_STAMP
 
@@ -591,7 +640,9 @@ int max_dyn_smem(int* out) {
 template <int D>
 int launch_owner(const ure_mf_shard_t* d_shards, int K, const ure_mf_hparams_t& hp, int epochs, long long s0,
                  long long s1, OwnerWs* ws, int smem, bool cached, unsigned dbg, cudaStream_t st) {
-  auto kern = cached ? mf_owner_kernel<D, true> : mf_owner_kernel<D, false>;
+  const bool wide = (hp.owner_flags & 2) != 0;
+  auto kern = cached ? (wide ? mf_owner_kernel<D, true, true> : mf_owner_kernel<D, true, false>)
+                     : (wide ? mf_owner_kernel<D, false, true> : mf_owner_kernel<D, false, false>);
   URE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   URE_CUDA(cudaMemsetAsync(ws->bar, 0, sizeof(ws->bar), st));
   void* args[] = {(void*)&d_shards, (void*)&K,  (void*)&hp, (void*)&epochs,
@@ -614,24 +665,28 @@ int mf_owner_trace(void* d_workspace, long long* d_trace, int steps, cudaStream_
 }
 void mf_owner_debug(unsigned flags) { g_owner_dbg = flags; }
 
-// called by ure_mf_train when hparams.mode == URE_MF_OWNER.  h_need / h_avail: what ure_mf_owner_prepare
-// planned, read back by the caller (the library never synchronises).
+// called by ure_mf_train when hparams.mode == URE_MF_OWNER; the capacities in hparams are the plan's maxima the
+// caller read back after ure_mf_owner_prepare (the library never synchronises)
 int mf_train_owner(const ure_mf_shard_t* d_shards, int n_shards, const ure_mf_hparams_t* hp, int epochs,
                    long long step_begin, long long step_end, void* d_workspace, cudaStream_t st) {
   URE_REQUIRE(n_shards <= num_sms(), URE_EUNSUPPORTED,
               "ure_mf_train(owner): %d shards need at least as many SMs (%d)", n_shards, num_sms());
-  URE_REQUIRE(hp->owner_smem > 0, URE_EINVAL,
-              "ure_mf_train(owner): hparams.owner_smem must carry the shared-memory bytes planned by "
-              "ure_mf_owner_prepare (read back from the workspace)");
+  URE_REQUIRE(hp->owner_cap_rows > 0 && hp->owner_cap_slots >= 0 && hp->owner_cap_slots % 16 == 0, URE_EINVAL,
+              "ure_mf_train(owner): hparams.owner_cap_rows / owner_cap_slots must carry the plan of "
+              "ure_mf_owner_prepare (slots rounded up to a multiple of 16)");
+  URE_REQUIRE(hp->owner_cap_slots <= 65520 && hp->owner_cap_rows < (1 << (32 - kOtherBits)), URE_EUNSUPPORTED,
+              "ure_mf_train(owner): %d interactions / %d rows per CTA exceed the 16-bit slot / 12-bit row fields",
+              hp->owner_cap_slots, hp->owner_cap_rows);
+  const bool cached = (hp->owner_flags & 1) != 0, wide = (hp->owner_flags & 2) != 0;
+  const long long need = owner_smem_bytes(hp->d, hp->owner_cap_rows, hp->owner_cap_slots, wide, cached);
   int avail = 0;
   if (int rc = max_dyn_smem(&avail)) return rc;
-  URE_REQUIRE(hp->owner_smem <= avail, URE_EUNSUPPORTED,
-              "ure_mf_train(owner): the busiest CTA needs %d bytes of shared memory, %d available -- use the "
-              "dense or lazy schedule for this problem size", hp->owner_smem, avail);
+  URE_REQUIRE(need <= avail, URE_EUNSUPPORTED,
+              "ure_mf_train(owner): the plan needs %lld bytes of shared memory per CTA, %d available -- use the "
+              "dense or lazy schedule for this problem size", need, avail);
   if (step_end <= step_begin) return 0;
   auto* ws = static_cast<OwnerWs*>(d_workspace);
-  const int smem = hp->owner_smem;
-  const bool cached = hp->owner_cached != 0;
+  const int smem = (int)need;
   switch (hp->d) {
     case 8: return launch_owner<8>(d_shards, n_shards, *hp, epochs, step_begin, step_end, ws, smem, cached, g_owner_dbg, st);
     case 16: return launch_owner<16>(d_shards, n_shards, *hp, epochs, step_begin, step_end, ws, smem, cached, g_owner_dbg, st);
@@ -645,6 +700,10 @@ int mf_train_owner(const ure_mf_shard_t* d_shards, int n_shards, const ure_mf_hp
 }
 
 }  // namespace ure
+
+extern "C" int64_t ure_mf_owner_smem_bytes(int d, int cap_rows, int cap_slots, int wide, int cached) {
+  return ure::owner_smem_bytes(d, cap_rows, cap_slots, wide != 0, cached != 0);
+}
 
 extern "C" int ure_mf_owner_prepare(const ure_mf_shard_t* d_shards, int n_shards, const ure_mf_hparams_t* h_hp,
                                     int epochs, void* d_workspace, void* stream) {
@@ -661,9 +720,9 @@ extern "C" int ure_mf_owner_prepare(const ure_mf_shard_t* d_shards, int n_shards
   perm_inverse_kernel<<<dim3(blocks, n_shards), 256, 0, st>>>(d_shards, epochs);
   int avail = 0;
   if (int rc = max_dyn_smem(&avail)) return rc;
-  const int head[8] = {0, avail, 0, 0, 0, n_shards, 0, 0};
+  const int head[8] = {0, 0, 0, avail, 0, 0, 0, 0};
   URE_CUDA(cudaMemcpyAsync(ws, head, sizeof(head), cudaMemcpyHostToDevice, st));
-  plan_kernel<<<num_sms(), 32, 0, st>>>(d_shards, n_shards, h_hp->d, h_hp->batch, ws);
+  plan_kernel<<<num_sms(), 32, 0, st>>>(d_shards, n_shards, h_hp->batch, ws);
   URE_CUDA(cudaGetLastError());
   return 0;
 }

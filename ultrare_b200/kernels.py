@@ -233,7 +233,7 @@ class ShardBatch:
         self.ws = torch.zeros(int(_lib.lib().ure_mf_train_workspace_bytes()), dtype=torch.uint8, device=self.device)
         self.hp = MFHParams(d=d, batch=batch, lr0=lr, lr_decay=lr_decay, lr_step=lr_step,
                             weight_decay=weight_decay, momentum=momentum, mode=_lib.MF_DENSE,
-                            decay=None, decay_len=0, owner_smem=0, owner_cached=0, reserved=0)
+                            decay=None, decay_len=0, owner_cap_rows=0, owner_cap_slots=0, owner_flags=0)
         self.owner_plan = None
         self._owner_cache = bool(owner_cache)       # False: keep the records in L2 (tests of the uncached variant)
         if mode in ("owner", "auto"):
@@ -290,21 +290,25 @@ class ShardBatch:
         with torch.cuda.device(dev):
             check(L.ure_mf_owner_prepare(_ptr(self.table), len(shards), C.byref(self.hp), self.epochs, _ptr(self.ws),
                                          _stream()), "ure_mf_owner_prepare")
-        need, avail, max_rows, max_slots, need_c = self.ws[:20].view(torch.int32).tolist()   # the one sync of the set-up
-        self.owner_plan = {"smem_need": need, "smem_avail": avail, "max_rows_per_cta": max_rows,
-                           "max_slots_per_cta": max_slots, "smem_need_cached": need_c, "cached": need_c <= avail}
-        if need > avail:
+        max_rows, max_slots, max_spe, avail = self.ws[:16].view(torch.int32).tolist()   # the one sync of the set-up
+        cap_rows, cap_slots, wide = max(1, max_rows), -(-max_slots // 16) * 16, int(max_spe > 255)
+        need = int(L.ure_mf_owner_smem_bytes(self.hp.d, cap_rows, cap_slots, wide, 0))
+        need_c = int(L.ure_mf_owner_smem_bytes(self.hp.d, cap_rows, cap_slots, wide, 1))
+        fits = need <= avail and cap_slots <= 65520 and cap_rows < 4096 and max_spe <= 65535
+        cached = fits and need_c <= avail and self._owner_cache and \
+            max(max(s.P.shape[0], s.Q.shape[0]) for s in shards) <= (1 << 20)
+        self.owner_plan = {"smem_need": need, "smem_need_cached": need_c, "smem_avail": avail, "cached": cached,
+                           "max_rows_per_cta": max_rows, "max_slots_per_cta": max_slots, "max_steps_per_epoch": max_spe}
+        if not fits:
             if required:
-                raise RuntimeError(f"owner mode: the busiest CTA needs {need} B of shared memory, {avail} B available")
+                raise RuntimeError(f"owner mode does not fit this problem: {self.owner_plan}")
             for s in shards:
                 s.inter_u = s.inter_i = s.off_u = s.off_i = s.perm_inv = None
             self._owner_keep = None
             return "dense"
         self.hp.mode = _lib.MF_OWNER
-        cached = need_c <= avail and self._owner_cache
-        self.owner_plan["cached"] = cached
-        self.hp.owner_cached = int(cached)
-        self.hp.owner_smem = need_c if cached else need
+        self.hp.owner_cap_rows, self.hp.owner_cap_slots = cap_rows, cap_slots
+        self.hp.owner_flags = int(cached) | (wide << 1)
         return "owner"
 
     @staticmethod

@@ -57,23 +57,33 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index=0):
-        self.gpu, self.proc, self.path = gpu_index, None, None
+        self.gpu, self.proc, self.path, self.skip = gpu_index, None, None, 0
 
     def start(self):
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=open(self.path, "w"),
+                                          "-lms", "20", "-i", str(self.gpu)], stdout=open(self.path, "w"),
                                          stderr=subprocess.DEVNULL)
+            t0 = time.time()                 # nvidia-smi needs ~0.1 s to come up: wait for its first line
+            while time.time() - t0 < 2.0 and os.path.getsize(self.path) == 0:
+                time.sleep(0.01)
         except Exception:
             self.proc = None
+
+    def mark(self):
+        """Samples taken before this call (warm-up) are dropped by stop()."""
+        try:
+            self.skip = sum(1 for _ in open(self.path))
+        except Exception:
+            self.skip = 0
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.proc is None:
             return out
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -82,7 +92,7 @@ class ClockSampler:
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         try:
-            for line in open(self.path):
+            for line in list(open(self.path))[self.skip:]:
                 f = [x.strip() for x in line.split(",")]
                 if len(f) < 9:
                     continue
@@ -223,9 +233,11 @@ def run_ours(args):
     step_ms = []
     launches = 0
     total_steps = args.warmup + args.steps
+    if rank == 0:
+        sampler.start()
     for it in range(total_steps):
         if it == args.warmup and rank == 0:
-            sampler.start()
+            sampler.mark()
         flush.fill_(it & 0xFF)                                               # L2 flush between steps
         un = new_sisa()
         d.barrier()
@@ -238,7 +250,6 @@ def run_ours(args):
         ms = e0.elapsed_time(e1)
         if it >= args.warmup:
             step_ms.append(d.max_float(ms))
-    clocks = sampler.stop() if rank == 0 else None
     n_retrained = len(un.retrain_gid)
     # kernels of ours launched per step: route(1) + train(1) + merge(1) + score(1 or 2) + rank(1)
     launches = (1 + 1 + 1 + (2 if world > 1 else 1) + 1) * args.steps
@@ -263,13 +274,15 @@ def run_ours(args):
         torch.cuda.synchronize()
         k_ms.append(e0.elapsed_time(e1))
     kern_ms = float(np.median(k_ms))
+    clocks = sampler.stop() if rank == 0 else None       # sampled over the timed steps + the kernel-alone repeats
     peak, peak_src = measured_peaks()
     alg_bytes = n_inter_local * E * A_MF(D_EMB)
     achieved = alg_bytes / (kern_ms / 1e3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "mf_train_traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        traffic = json.load(open(tpath)).get("mf_owner_kernel<16>" if sb.mode == "owner" else "mf_train_kernel<16>",
+                                             {}).get("dram_bytes_per_launch")
 
     # ---- end to end from host buffers through the public API
     h2d = 16 * (sum(a.shape[1] for a in sp["unlearn_train"]) + test_np.shape[1]) + 4 * len(del_user)
@@ -310,7 +323,8 @@ def run_ours(args):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": float(np.mean(e2e_ms)), "retrain_after_delete_s": float(np.mean(e2e_ms)) / 1e3},
-        "roofline": {"bound": "hbm", "kernel": "mf_train_kernel<16>", "achieved": achieved, "peak": peak,
+        "roofline": {"bound": "hbm", "kernel": ("mf_owner_kernel<16>" if sb.mode == "owner" else "mf_train_kernel<16>"),
+                     "schedule": sb.mode, "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": int(alg_bytes),
                      "share_of_step": kern_ms / ms_per_step},

@@ -21,7 +21,11 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_membar_per_issue_active.ratio",
-        "lts__t_sectors_op_red.sum", "lts__t_sectors_op_read.sum", "lts__t_sectors_op_write.sum"]
+        "lts__t_sectors_op_red.sum", "lts__t_sectors_op_read.sum", "lts__t_sectors_op_write.sum",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "l1tex__t_sector_hit_rate.pct",
+        "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio"]
 
 
 def raw_summary(rep, out_name, title):
@@ -70,6 +74,8 @@ if __name__ == "__main__":
     g = os.path.join(ROOT, "gpurun_out")
     tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
     for rep, out, title in ((f"{g}/prof_mf_{tag}c.ncu-rep", f"{tag}_mf_train_ncu.txt", "mf_train_kernel<16>, ml1m shape K=5, 10 epochs"),
+                            (f"{g}/prof_owner_v5c.ncu-rep", f"{tag}_mf_owner_ncu.txt",
+                             "mf_owner_kernel<16,cached,u8>, ml1m shape K=5, 10 epochs (70 steps)"),
                             (f"{g}/prof_ot_{tag}a.ncu-rep", f"{tag}_ot_ncu.txt", "OT grouping kernels, n=1M k=32 d=64")):
         if os.path.exists(rep):
             raw_summary(rep, out, title)

@@ -309,7 +309,8 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
     const int ob = (epoch & 1) * cap;
     const FeistelKeys ks = s_keys;
     const int32_t* pinv = sh.perm_inv ? sh.perm_inv + (long long)epoch * n : nullptr;
-    for (int s0 = lo + tid; s0 < hi; s0 += NI * kOwnThreads) {
+    // slots are dealt from the LAST thread down: a short extra round lands on warp 31, not on the warp that polls
+    for (int s0 = lo + (kOwnThreads - 1 - tid); s0 < hi; s0 += NI * kOwnThreads) {
       uint32_t x[NI];
       bool live[NI];
 #pragma unroll

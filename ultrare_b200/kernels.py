@@ -160,7 +160,7 @@ def pointer_table(tensors: Sequence[torch.Tensor], device) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------------ MF training
-DEFAULT_MF_MODE = "dense"      # schedule ShardBatch picks when the caller does not say (see ShardBatch)
+DEFAULT_MF_MODE = "auto"       # schedule ShardBatch picks when the caller does not say (see ShardBatch)
 
 
 class ShardState:

@@ -130,9 +130,10 @@ constexpr int kOwnWarps = kOwnThreads / 32;
 // (cap_rows, cap_slots: the plan's maxima over the CTAs), so every array base is a uniform value:
 //   boundary rows [2*warps][d] fp32 | batch list [cap_slots] u16 | record cache [cap_slots] 8 B (optional)
 //   | step_of [2][cap_slots] u8 (u16 when steps/epoch > 255) | owned rows [cap_rows][3d] fp32 (w | buf | g)
+//   | first boundary record of every row [cap_rows] int
 __host__ __device__ inline long long owner_smem_bytes(int d, int cap_rows, int cap_slots, bool wide, bool cached) {
   return 2ll * kOwnWarps * d * 4 + 2ll * cap_slots + (cached ? 8ll * cap_slots : 0) +
-         2ll * cap_slots * (wide ? 2 : 1) + 12ll * cap_rows * d;
+         2ll * cap_slots * (wide ? 2 : 1) + 12ll * cap_rows * d + 4ll * cap_rows;
 }
 
 __global__ void plan_kernel(const ure_mf_shard_t* shards, int K, int batch, OwnerWs* ws) {
@@ -264,6 +265,7 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
   float* const s_w = reinterpret_cast<float*>(s_step + 2 * cap);            // row r: s_w + r*RS
   float* const s_b = s_w + D;
   float* const s_g = s_w + 2 * D;
+  int* const s_bidx = reinterpret_cast<int*>(s_w + hp.owner_cap_rows * RS);   // [rows] first boundary record, or INT_MAX
 
   const int4* const recU = reinterpret_cast<const int4*>(sh.inter_u + s_pl.su0);           // slot sl < mU
   const int4* const recI = reinterpret_cast<const int4*>(sh.inter_i + s_pl.si0) - mU;      // slot sl >= mU
@@ -292,6 +294,7 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
   }
   for (int x = tid; x < 2 * NW * G; x += kOwnThreads)
     *reinterpret_cast<float4*>(s_bnd + 4 * x) = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int r = tid; r < rows; r += kOwnThreads) s_bidx[r] = 0x7fffffff;
   if (CACHED)
     for (int sl = tid; sl < m; sl += kOwnThreads) s_rec[sl] = pack_rec(__ldg((sl >= mU ? recI : recU) + sl), sl >= mU);
   // slots beyond m never match a step number
@@ -364,6 +367,49 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
   if (trace && tid == 32 && (t - step_begin) < trace_steps)                        \
     trace[((t - step_begin) * gridDim.x + blockIdx.x) * 6 + (PH)] = clock64();
 
+  // Batch scan of one step: every lane looks at 16 CONSECUTIVE slots of the warp's range per chunk (one 16-byte
+  // load) and keeps their hit mask in a register; the warp's total goes to s_wcnt.  Runs in the barrier's shadow
+  // of the step before (the prologue for the first step); the list itself is written at the top of the step.
+  constexpr int MAXCH = 4;                 // chunks of 512 slots kept in registers; longer ranges re-scan
+  unsigned hm[MAXCH];
+  auto scan_batch = [&](int ep, int kk) {
+    const step_t* const stp = s_step + (ep & 1) * cap;
+    const unsigned k4 = (unsigned)kk * (WIDE ? 0x00010001u : 0x01010101u);
+    int cnt = 0;
+#pragma unroll
+    for (int c = 0; c < MAXCH; ++c) {
+      const int sl = w0 + 512 * c + 16 * lane;
+      unsigned mask = 0;
+      if (sl < w1) {
+        if (WIDE) {
+          const uint4 v0 = *reinterpret_cast<const uint4*>(stp + sl), v1 = *reinterpret_cast<const uint4*>(stp + sl + 8);
+          const unsigned w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const unsigned a = __vcmpeq2(w[j], k4);
+            mask |= ((a & 1u) | ((a >> 15) & 2u)) << (2 * j);
+          }
+        } else {
+          const uint4 v = *reinterpret_cast<const uint4*>(stp + sl);
+          const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const unsigned a = __vcmpeq4(w[j], k4) & 0x01010101u;
+            mask |= ((a | (a >> 7) | (a >> 14) | (a >> 21)) & 0xfu) << (4 * j);
+          }
+        }
+        if (sl + 16 > w1) mask &= (1u << (w1 - sl)) - 1u;    // slots of the next warp / the pad
+      }
+      hm[c] = mask;
+      cnt += __popc(mask);
+    }
+    for (int sl = w0 + 512 * MAXCH + lane; sl < w1; sl += 32) cnt += (int)stp[sl] == kk;   // rare: long ranges
+    cnt = (int)warp_sum((float)cnt);       // exact: counts are far below 2^24
+    if (lane == 0) s_wcnt[warp] = cnt;
+  };
+  scan_batch(e, k);
+  __syncthreads();
+
   for (long long t = step_begin; t < t_end; ++t) {
     const bool rd = (t - step_begin) & 1;
     const float* const Pr = rd ? sh.gP : sh.P;
@@ -372,52 +418,9 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
     URE_STAMP(0)
 
     // -------------------------------------------------------------- (1) the batch, as a sorted list of slots
-    // Every lane looks at 16 CONSECUTIVE slots of the warp's range per chunk (one 16-byte load), keeps their
-    // hit mask in a register, and after one block-wide prefix writes its hits: lane-major = slot-major order.
+    // (hit masks hm[] and the warp totals s_wcnt were prepared in the previous step's barrier shadow)
     const step_t* const stp = s_step + (e & 1) * cap;
-    constexpr int MAXCH = 4;               // chunks of 512 slots kept in registers; longer ranges re-scan
-    unsigned hm[MAXCH];
-    int cnt = 0;
-    {
-      const unsigned k4 = (unsigned)k * (WIDE ? 0x00010001u : 0x01010101u);
-#pragma unroll
-      for (int c = 0; c < MAXCH; ++c) {
-        const int sl = w0 + 512 * c + 16 * lane;
-        unsigned mask = 0;
-        if (sl < w1) {
-          if (WIDE) {
-            const uint4 v0 = *reinterpret_cast<const uint4*>(stp + sl), v1 = *reinterpret_cast<const uint4*>(stp + sl + 8);
-            const unsigned w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const unsigned a = __vcmpeq2(w[j], k4);
-              mask |= ((a & 1u) | ((a >> 15) & 2u)) << (2 * j);
-            }
-          } else {
-            const uint4 v = *reinterpret_cast<const uint4*>(stp + sl);
-            const unsigned w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const unsigned a = __vcmpeq4(w[j], k4) & 0x01010101u;
-              mask |= ((a | (a >> 7) | (a >> 14) | (a >> 21)) & 0xfu) << (4 * j);
-            }
-          }
-          if (sl + 16 > w1) mask &= (1u << (w1 - sl)) - 1u;    // slots of the next warp / the pad
-        }
-        hm[c] = mask;
-        cnt += __popc(mask);
-      }
-      for (int sl = w0 + 512 * MAXCH + lane; sl < w1; sl += 32) cnt += (int)stp[sl] == k;   // rare: long ranges
-    }
-    // exclusive prefix of the lanes' counts inside the warp, then of the warps inside the CTA
-    int lincl = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int a = __shfl_up_sync(FULL, lincl, o);
-      if (lane >= o) lincl += a;
-    }
-    if (lane == 31) s_wcnt[warp] = lincl;
-    __syncthreads();
+    // exclusive prefix of the warps' totals inside the CTA
     int incl = s_wcnt[lane];
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -426,7 +429,7 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
     }
     const int total = __shfl_sync(FULL, incl, 31);
     {
-      const int wbase = __shfl_sync(FULL, incl, warp) - __shfl_sync(FULL, lincl, 31);   // first position of the warp
+      const int wbase = __shfl_sync(FULL, incl, warp) - s_wcnt[warp];   // first position of the warp
       int pos = wbase;
       // chunk-major, lane-major inside a chunk: positions of chunk c start after all hits of chunks < c
 #pragma unroll
@@ -473,7 +476,10 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
       rowF = (int)(rec_of(s_list[wv0 * WAVE]).x >> kOtherBits);
       rowL = (int)(rec_of(s_list[ent1 - 1]).x >> kOtherBits);
     }
-    if (lane == 0) { s_bkey[2 * warp] = rowF; s_bkey[2 * warp + 1] = rowL; }
+    if (lane == 0) {
+      s_bkey[2 * warp] = rowF; s_bkey[2 * warp + 1] = rowL;
+      if (rowF >= 0) { atomicMin(&s_bidx[rowF], 2 * warp); atomicMin(&s_bidx[rowL], 2 * warp + 1); }
+    }
     auto flush = [&](int row, const float4& a) {
       if (row >= 0) {
         float4* gp = reinterpret_cast<float4*>(s_g + (row == rowF ? offF : row == rowL ? offL : row * RS) + 4 * gl);
@@ -540,29 +546,6 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
     __syncthreads();
     URE_STAMP(2)
 
-    // ------------------------------------------------------------ boundary rows: first record of a row adds
-    // up every record of that row (they are adjacent: records are in list order) into its accumulator
-    for (int i = tid / G; i < 2 * NW; i += kOwnThreads / G) {
-      const int key = s_bkey[i];
-      if (key < 0) continue;
-      int j = i - 1;
-      while (j >= 0 && s_bkey[j] < 0) --j;
-      if (j >= 0 && s_bkey[j] == key) continue;          // not the head
-      float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (j = i; j < 2 * NW && (s_bkey[j] < 0 || s_bkey[j] == key); ++j) {
-        if (s_bkey[j] < 0) continue;
-        float4* bp = reinterpret_cast<float4*>(s_bnd + j * D + 4 * gl);
-        const float4 v = *bp;
-        sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
-        *bp = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      float4* gp = reinterpret_cast<float4*>(s_g + key * RS + 4 * gl);
-      float4 v = *gp;
-      v.x += sum.x; v.y += sum.y; v.z += sum.z; v.w += sum.w;
-      *gp = v;
-    }
-    __syncthreads();
-
     // ------------------------------------------------------------ (3) SGD update of every owned row, publication
     {
       float* const Pw = rd ? sh.P : sh.gP;
@@ -573,6 +556,19 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
         float4* bp = wp + D / 4;
         float4* gp = wp + D / 2;
         float4 g = *gp, w = *wp, b = *bp;
+        // boundary rows: the partial sums of the warps that shared the row (adjacent records, in list order)
+        const int bi = s_bidx[r];
+        if (bi != 0x7fffffff) {
+          for (int j = bi; j < 2 * NW && (s_bkey[j] < 0 || s_bkey[j] == r); ++j) {
+            if (s_bkey[j] < 0) continue;
+            float4* rp = reinterpret_cast<float4*>(s_bnd + j * D + 4 * c);
+            const float4 v = *rp;
+            g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w;
+            *rp = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          __syncwarp(__activemask());
+          if (c == 0) s_bidx[r] = 0x7fffffff;
+        }
         // torch SGD: d_p = g + wd*w (fma); buf = buf*mu + d_p; w = w + (-lr)*buf (fma)
         g.x = fmaf(wd, w.x, g.x); g.y = fmaf(wd, w.y, g.y); g.z = fmaf(wd, w.z, g.z); g.w = fmaf(wd, w.w, g.w);
         b.x = __fadd_rn(__fmul_rn(b.x, mu), g.x); b.y = __fadd_rn(__fmul_rn(b.y, mu), g.y);
@@ -595,6 +591,10 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
     const bool last_of_epoch = k + 1 == spe;
     // in the barrier's shadow: this step's slice of the NEXT epoch's step_of
     if (e + 1 < epochs) fill_step_of(e + 1, (int)((long long)k * m / spe), (int)((long long)(k + 1) * m / spe));
+    if (t + 1 < t_end) {                   // ... and the batch scan of the NEXT step
+      if (last_of_epoch) __syncthreads();  // its step_of buffer was completed by the fill just above
+      scan_batch(last_of_epoch ? e + 1 : e, last_of_epoch ? 0 : k + 1);
+    }
     URE_STAMP(4)
     if (tid == 0) {
       float v = 0.f;

@@ -86,8 +86,13 @@ typedef struct {
   int32_t decay_len;    /* lazy: number of table entries (>= total steps + 1)                */
   int32_t owner_cap_rows;  /* OWNER: max owned rows of a CTA, from ure_mf_owner_prepare's plan      */
   int32_t owner_cap_slots; /* OWNER: max owned interactions of a CTA, rounded up to a multiple of 16 */
-  int32_t owner_flags;     /* OWNER: bit 0 = keep the record cache in shared memory, bit 1 = some   */
-                           /*        shard has more than 255 steps per epoch (16-bit step numbers)  */
+  int32_t owner_flags;     /* OWNER: bit 0 = keep the record cache in shared memory                 */
+  int32_t owner_spe_cap;   /* OWNER: max steps per epoch of a shard (plan)                           */
+  int32_t owner_sched_rows;/* OWNER: epochs per shard the schedule tables hold                       */
+  uint16_t* owner_sched;   /* OWNER: DEVICE [owner_sched_rows][owner_sched_stride] batch lists       */
+  int32_t* owner_sched_off;/* OWNER: DEVICE [owner_sched_rows][#SMs][owner_spe_cap + 1] list offsets */
+  int64_t owner_sched_step0;  /* OWNER: global step the schedule window starts at                    */
+  int64_t owner_sched_stride; /* OWNER: slots of one schedule row = sum over the shards of 2 n       */
 } ure_mf_hparams_t;
 
 /* ure_mf_hparams_t::mode -- three schedules of the SAME arithmetic (baseTrain + dense optim.SGD):
@@ -126,13 +131,24 @@ int ure_mf_train(const ure_mf_shard_t* d_shards, int n_shards, const ure_mf_hpar
  * explicit perm, then plans the CTA ownership and writes into the first 16 bytes of d_workspace
  * int32 {max owned rows of a CTA, max owned interactions of a CTA, max steps per epoch of a shard,
  * dynamic shared-memory bytes available}: the caller reads them back once, fills hparams.owner_cap_rows /
- * owner_cap_slots / owner_flags and must not start mode OWNER when ure_mf_owner_smem_bytes exceeds what is
- * available (ure_mf_train refuses it loudly as well). */
+ * owner_cap_slots / owner_spe_cap / owner_flags, allocates the schedule tables, and must not start mode OWNER
+ * when ure_mf_owner_smem_bytes exceeds what is available (ure_mf_train refuses it loudly as well). */
 int ure_mf_owner_prepare(const ure_mf_shard_t* d_shards, int n_shards, const ure_mf_hparams_t* h_hp,
                          int epochs, void* d_workspace, void* stream);
 
-/* Dynamic shared memory per CTA of the OWNER schedule for these capacities. */
-int64_t ure_mf_owner_smem_bytes(int d, int cap_rows, int cap_slots, int wide, int cached);
+/* Dynamic shared memory per CTA the OWNER schedule needs for these capacities (training kernel and
+ * schedule pre-pass, whichever is larger). */
+int64_t ure_mf_owner_smem_bytes(int d, int cap_rows, int cap_slots, int spe_cap, int cached);
+
+/* OWNER mode, before ure_mf_train: fill the schedule tables for the window of owner_sched_rows epochs per
+ * shard that starts at global step `step0` (epoch step0 / spe_s of shard s): for every training CTA, epoch
+ * and step, the sorted list of the CTA's interactions in that step's batch -- the inverse of the epoch's
+ * visiting order (keyed Feistel permutation or perm_inv), evaluated in one embarrassingly parallel pass.
+ * ure_mf_train may then run any steps [a, b) with step0 <= a whose epochs lie inside the window
+ * (hparams.owner_sched_step0 = step0); a step outside it stops the shard and raises the workspace's error
+ * word (int32 at byte 16). */
+int ure_mf_owner_schedule(const ure_mf_shard_t* d_shards, int n_shards, const ure_mf_hparams_t* h_hp,
+                          int epochs, int64_t step0, void* stream);
 
 /* Diagnostics (tracing): record six SM-clock stamps per CTA and step -- step start, tables ready,
  * gradients issued, barrier 1 passed, sweep issued, barrier 2 passed -- for the first `steps` steps of

@@ -57,6 +57,18 @@ for rep in range(args.reps):
     print(f"rep {rep}: {ms:.3f} ms for {sb.total_steps} steps ({ms * 1e3 / sb.total_steps:.2f} us/step), "
           f"{n_inter / ms / 1e6:.2f} G inter/s, {n_inter * 268 / ms / 1e6:.1f} GB/s algorithmic")
 print("losses", [float(x[-1]) for x in sb.train_losses()])
+if sb.mode == "owner":
+    import ctypes as C
+    from ultrare_b200 import _lib
+    for rep in range(3):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.check(_lib.lib().ure_mf_owner_schedule(C.c_void_p(sb.table.data_ptr()), len(sb.shards), C.byref(sb.hp),
+                                                    sb.epochs, 0, None))
+        e1.record()
+        torch.cuda.synchronize()
+        print(f"schedule pre-pass ({sb.hp.owner_sched_rows} rows): {e0.elapsed_time(e1):.3f} ms")
 
 if not args.trace:
     sys.exit(0)

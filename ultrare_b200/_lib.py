@@ -31,12 +31,14 @@ class MFHParams(C.Structure):
     """ure_mf_hparams_t"""
     _fields_ = [("d", _i32), ("batch", _i32), ("lr0", _f32), ("lr_decay", _f32), ("lr_step", _i32),
                 ("weight_decay", _f32), ("momentum", _f32), ("mode", _i32), ("decay", _p), ("decay_len", _i32),
-                ("owner_cap_rows", _i32), ("owner_cap_slots", _i32), ("owner_flags", _i32)]
+                ("owner_cap_rows", _i32), ("owner_cap_slots", _i32), ("owner_flags", _i32),
+                ("owner_spe_cap", _i32), ("owner_sched_rows", _i32), ("owner_sched", _p), ("owner_sched_off", _p),
+                ("owner_sched_step0", _i64), ("owner_sched_stride", _i64)]
 
 
 MF_DENSE, MF_LAZY, MF_OWNER = 0, 1, 2
 
-assert C.sizeof(MFShard) == 160 and C.sizeof(MFHParams) == 56
+assert C.sizeof(MFShard) == 160 and C.sizeof(MFHParams) == 96
 
 # name -> (restype, argtypes); every symbol include/ultrare_b200.h declares
 SIGNATURES = {
@@ -46,6 +48,7 @@ SIGNATURES = {
     "ure_mf_train": (C.c_int, [_p, C.c_int, C.POINTER(MFHParams), C.c_int, _i64, _i64, C.c_int, _p, _p]),
     "ure_mf_owner_prepare": (C.c_int, [_p, C.c_int, C.POINTER(MFHParams), C.c_int, _p, _p]),
     "ure_mf_owner_smem_bytes": (_i64, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "ure_mf_owner_schedule": (C.c_int, [_p, C.c_int, C.POINTER(MFHParams), C.c_int, _i64, _p]),
     "ure_mf_train_trace": (C.c_int, [_p, _p, C.c_int, _p]),
     "ure_mf_grid_size": (C.c_int, []),
     "ure_mf_debug_flags": (C.c_int, [_p, C.c_uint32, _p]),

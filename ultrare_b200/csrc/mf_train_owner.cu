@@ -8,14 +8,15 @@
 //   * The shard's records exist twice, sorted by user and sorted by item (ure_mf_owner_prepare), so the
 //     interactions of an owned row are one contiguous run of slots.  A batch is a random subset of the
 //     shard (the per-epoch visiting order); which batch a slot belongs to in epoch e is
-//     step_of(slot) = inverse_permutation_e(record index) / batch, evaluated once per epoch into a
-//     shared-memory uint16 array -- for the NEXT epoch, slice by slice, in the shadow of the barrier.
-//   * A step (1) compacts the CTA's slots of the current batch into a sorted list (ballot/popc, order
-//     preserving), (2) walks the list in waves -- a group of d/4 lanes per interaction: the OTHER table's row
-//     is gathered with 16-byte L2 loads, the error is re-computed on both sides, the contributions of
-//     consecutive interactions of the same row are summed in registers (in the group, then across the
-//     warp's groups by a segmented shuffle reduction) and the run totals go to a shared-memory gradient
-//     row, (3) sweeps the owned rows: SGD update in shared memory + publication of the new weights.
+//     step_of(slot) = inverse_permutation_e(record index) / batch.  ure_mf_owner_schedule evaluates it for a
+//     window of epochs in an embarrassingly parallel pre-pass and leaves, for every CTA, epoch and step, the
+//     SORTED list of the CTA's slots in that batch (16-bit slot numbers in L2 / HBM): the training loop only
+//     copies its next list into shared memory in the shadow of the barrier.
+//   * A step walks the list in waves -- a group of d/4 lanes per interaction: the OTHER table's row is
+//     gathered with 16-byte loads, the error is re-computed on both sides, the contributions of consecutive
+//     interactions of the same row are summed in registers (in the group, then across the warp's groups by
+//     a segmented shuffle reduction) and the run totals go to the row's shared-memory gradient; then every
+//     owned row gets its SGD update in shared memory and its new weights are published.
 //     No global atomics, no global gradient arrays, no separate dense sweep over HBM/L2.
 //   * When they fit, the slots' (other index, rating, own row) are cached in shared memory as well, so the
 //     only L2 traffic of a step is the gather of the other table's rows.
@@ -37,11 +38,13 @@ struct OwnerWs {
   int max_slots;          // max owned interactions (user side + item side) of a CTA
   int max_spe;            // max steps per epoch of a shard
   int avail_smem;         // dynamic shared memory a launch can get
-  int pad0[2];
+  int error;              // set by the training kernel: 1 = a step outside the scheduled window was requested
+  int pad0;
   int trace_steps;        // diagnostics (ure_mf_train_trace): stamps of the first trace_steps steps of a launch
   int pad1;
   long long* trace;       // [trace_steps][grid][6] SM-clock stamps, or NULL
-  int pad[22];
+  long long tot_slots;    // written by plan_kernel: sum over the shards of 2 n (slots of one schedule row)
+  int pad[20];
   unsigned bar[KMAX][32]; // one barrier counter per shard, one 128-byte line each
 };
 
@@ -49,6 +52,7 @@ struct Plan {
   int shard, q, c;        // my shard, my index among its c CTAs
   int ru0, ru1, ri0, ri1; // owned user rows / item rows
   int su0, mU, si0, mI;   // first slot and slot count in inter_u / inter_i
+  long long slot_base;    // first of the CTA's slots in a schedule row: 2 n of the shards before + su0 + si0
 };
 
 // first r in [0, n_rows] with off[r] >= target, moved down by one when that boundary is nearer
@@ -95,6 +99,9 @@ __device__ void make_plan(const ure_mf_shard_t* shards, int K, int cta, int n_ct
     int s = 0, base = 0;
     while (s < K - 1 && cta >= base + ps.c[s]) base += ps.c[s++];
     pl.shard = s; pl.q = cta - base; pl.c = ps.c[s];
+    long long sb = 0;
+    for (int x = 0; x < s; ++x) sb += 2ll * shards[x].n;
+    pl.slot_base = sb;
   }
   __syncthreads();
   const ure_mf_shard_t& sh = shards[pl.shard];
@@ -119,23 +126,23 @@ __device__ void make_plan(const ure_mf_shard_t* shards, int K, int cta, int n_ct
     pl.ri0 = i0; pl.ri1 = i1;
     pl.su0 = sh.off_u[pl.ru0]; pl.mU = sh.off_u[pl.ru1] - pl.su0;
     pl.si0 = sh.off_i[pl.ri0]; pl.mI = sh.off_i[pl.ri1] - pl.si0;
+    pl.slot_base += (long long)pl.su0 + pl.si0;
   }
   __syncthreads();
 }
 
 constexpr int kOtherBits = 20;            // record cache: other-table row in the low 20 bits, own row above
 constexpr int kOwnWarps = kOwnThreads / 32;
+constexpr int kMaxSpe = 8192;             // steps per epoch the schedule pre-pass handles (histogram in shared memory)
 
 // Dynamic shared memory of the training kernel.  The layout depends on LAUNCH-uniform capacities only
 // (cap_rows, cap_slots: the plan's maxima over the CTAs), so every array base is a uniform value:
 //   boundary rows [2*warps][d] fp32 | batch list [cap_slots] u16 | record cache [cap_slots] 8 B (optional)
-//   | step_of [2][cap_slots] u8 (u16 when steps/epoch > 255) | owned rows [cap_rows][3d] fp32 (w | buf | g)
-//   | first boundary record of every row [cap_rows] int
-__host__ __device__ inline long long owner_smem_bytes(int d, int cap_rows, int cap_slots, bool wide, bool cached) {
-  return 2ll * kOwnWarps * d * 4 + 2ll * cap_slots + (cached ? 8ll * cap_slots : 0) +
-         2ll * cap_slots * (wide ? 2 : 1) + 12ll * cap_rows * d + 4ll * cap_rows;
+//   | owned rows [cap_rows][3d] fp32 (w | buf | g) | first boundary record of every row [cap_rows] int
+__host__ __device__ inline long long owner_smem_bytes(int d, int cap_rows, int cap_slots, bool cached) {
+  return 2ll * kOwnWarps * d * 4 + 2ll * cap_slots + (cached ? 8ll * cap_slots : 0) + 12ll * cap_rows * d +
+         4ll * cap_rows;
 }
-
 __global__ void plan_kernel(const ure_mf_shard_t* shards, int K, int batch, OwnerWs* ws) {
   __shared__ PlanScratch ps;
   __shared__ Plan pl;
@@ -144,6 +151,11 @@ __global__ void plan_kernel(const ure_mf_shard_t* shards, int K, int batch, Owne
     atomicMax(&ws->max_rows, (pl.ru1 - pl.ru0) + (pl.ri1 - pl.ri0));
     atomicMax(&ws->max_slots, pl.mU + pl.mI);
     atomicMax(&ws->max_spe, (shards[pl.shard].n + batch - 1) / batch);
+    if (blockIdx.x == 0) {
+      long long tot = 0;
+      for (int s = 0; s < K; ++s) tot += 2ll * shards[s].n;
+      ws->tot_slots = tot;
+    }
   }
 }
 
@@ -218,10 +230,241 @@ __global__ void perm_inverse_kernel(const ure_mf_shard_t* shards, int epochs) {
   }
 }
 
+// ---------------------------------------------------------------- the schedule pre-pass
+// Block (cta, y): for the training CTA `cta` and the rows r = y, y + gridDim.y, ... of the window that starts at
+// global step step0 (row r = epoch step0 / spe + r of the CTA's shard): the CTA's slots, stably sorted by the step
+// whose batch they are in.
+//   sched [rows][stride] u16 : row r, positions slot_base .. slot_base + m
+//   off   [rows][grid][spe_cap + 1] int : start of every step's run inside the CTA's m entries (off[spe] = m)
+constexpr int kSchedThreads = 512;
+constexpr int kSchedWarps = kSchedThreads / 32;
+
+__host__ __device__ inline long long schedule_smem_bytes(int cap_slots, int spe_cap) {
+  // record index of every slot [cap] int | step of every slot [cap] u16 | histogram [spe_cap + 1] int
+  // | per-warp bin counters [warps][64] int
+  return 6ll * cap_slots + 4ll * (spe_cap + 1) + 4ll * kSchedWarps * 64 + 16;
+}
+
+__global__ void __launch_bounds__(kSchedThreads, 2)
+owner_schedule_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams_t hp, int epochs,
+                      long long step0) {
+  constexpr int NW = kSchedWarps;
+  constexpr unsigned FULL = 0xffffffffu;
+  extern __shared__ __align__(16) unsigned char dyn[];
+  __shared__ PlanScratch s_ps;
+  __shared__ Plan s_pl;
+  __shared__ int s_warp_tot[NW];
+  __shared__ int s_carry;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  make_plan(shards, K, blockIdx.x, gridDim.x, s_pl, s_ps);
+  const ure_mf_shard_t& sh = shards[s_pl.shard];
+  const int mU = s_pl.mU, m = mU + s_pl.mI;
+  const int B = hp.batch, n = sh.n;
+  const int spe = (n + B - 1) / B;
+  if (spe == 0) return;
+  const int cap = hp.owner_cap_slots, spe_cap = hp.owner_spe_cap;
+  int* const s_j = reinterpret_cast<int*>(dyn);                            // [cap] record index of the slot
+  unsigned short* const s_stepof = reinterpret_cast<unsigned short*>(s_j + cap);
+  int* const s_hist = reinterpret_cast<int*>(s_stepof + cap);              // [spe_cap + 1]
+  int* const s_wh = s_hist + spe_cap + 1;                                  // [NW][64]
+  {
+    const int4* const recU = reinterpret_cast<const int4*>(sh.inter_u + s_pl.su0);
+    const int4* const recI = reinterpret_cast<const int4*>(sh.inter_i + s_pl.si0) - mU;
+    for (int sl = tid; sl < m; sl += kSchedThreads) s_j[sl] = __ldg(&((sl >= mU ? recI : recU) + sl)->w);
+  }
+  FeistelDomain dom;
+  dom.init((uint32_t)n);
+  const uint32_t magic = (uint32_t)(0x100000000ull / (uint32_t)B);         // floor(2^32/B): quotient low by <= 1
+  const int per = (m + NW - 1) / NW;                                       // every warp owns a contiguous range
+  const int w0 = min(warp * per, m), w1 = min(w0 + per, m);
+  const unsigned lt = (1u << lane) - 1u;
+
+  for (int r = blockIdx.y; r < hp.owner_sched_rows; r += gridDim.y) {
+    const int epoch = (int)(step0 / spe) + r;
+    if (epoch >= epochs) break;
+    unsigned short* const out = hp.owner_sched + (long long)r * hp.owner_sched_stride + s_pl.slot_base;
+    int* const off = hp.owner_sched_off + ((long long)r * gridDim.x + blockIdx.x) * (spe_cap + 1);
+    FeistelKeys ks;
+    ks.init(perm_key(sh.perm_seed, (uint32_t)sh.shard_id, (uint32_t)epoch));
+    const int32_t* pinv = sh.perm_inv ? sh.perm_inv + (long long)epoch * n : nullptr;
+    constexpr int NI = 4;
+    // step of NI x 32 consecutive slots of this warp's range (lane = slot inside a 32-block)
+    auto steps_of = [&](int base, uint32_t (&q)[NI], bool (&live)[NI]) {
+      uint32_t x[NI];
+#pragma unroll
+      for (int u = 0; u < NI; ++u) {
+        const int sl = base + 32 * u + lane;
+        live[u] = sl < w1;
+        x[u] = live[u] ? (uint32_t)s_j[sl] : 0u;
+      }
+      if (pinv) {
+#pragma unroll
+        for (int u = 0; u < NI; ++u)
+          if (live[u]) x[u] = (uint32_t)__ldg(pinv + x[u]);
+      } else {
+        feistel_inverse_n<NI>(dom, ks, x, live);
+      }
+#pragma unroll
+      for (int u = 0; u < NI; ++u) {
+        q[u] = B == 1 ? x[u] : mulhi32(x[u], magic);
+        if ((q[u] + 1) * (uint32_t)B <= x[u]) ++q[u];
+      }
+    };
+    if (spe <= 64) {
+      // ---- short epochs (the common case): ONE pass computes the steps and the per-warp bin counts, two warps
+      // turn them into cursors, one pass scatters
+      for (int x = tid; x < NW * 64; x += kSchedThreads) s_wh[x] = 0;
+      __syncthreads();                     // also: s_j complete, the previous row's scatter done
+      for (int base = w0; base < w1; base += 32 * NI) {
+        uint32_t q[NI];
+        bool live[NI];
+        steps_of(base, q, live);
+#pragma unroll
+        for (int u = 0; u < NI; ++u) {
+          const unsigned act = __ballot_sync(FULL, live[u]);
+          if (live[u]) {
+            s_stepof[base + 32 * u + lane] = (unsigned short)q[u];
+            const unsigned same = __match_any_sync(act, q[u]);
+            if (lane == __ffs(same) - 1) s_wh[warp * 64 + q[u]] += __popc(same);   // the warp's own counters
+          }
+          __syncwarp();
+        }
+      }
+      __syncthreads();
+      if (tid < 64) {                      // bin totals -> bin starts (two warps) -> per-warp cursors
+        int tot = 0;
+        for (int w = 0; w < NW; ++w) tot += s_wh[w * 64 + tid];
+        int inc = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int a = __shfl_up_sync(FULL, inc, o);
+          if (lane >= o) inc += a;
+        }
+        if (tid == 31) s_carry = inc;
+        asm volatile("bar.sync 1, 64;" ::: "memory");
+        int run = inc - tot + (tid >= 32 ? s_carry : 0);
+        if (tid <= spe) off[tid] = tid < spe ? run : m;
+        if (tid == 63 && spe == 64) off[64] = m;
+        for (int w = 0; w < NW; ++w) {
+          const int t = s_wh[w * 64 + tid];
+          s_wh[w * 64 + tid] = run;
+          run += t;
+        }
+      }
+      __syncthreads();
+      for (int s0 = w0; s0 < w1; s0 += 32) {
+        const int sl = s0 + lane;
+        const bool in = sl < w1;
+        const int bq = in ? (int)s_stepof[sl] : 0;
+        const unsigned act = __ballot_sync(FULL, in);
+        if (in) {
+          const unsigned same = __match_any_sync(act, bq);
+          out[s_wh[warp * 64 + bq] + __popc(same & lt)] = (unsigned short)sl;
+          __syncwarp(act);
+          if (lane == __ffs(same) - 1) s_wh[warp * 64 + bq] += __popc(same);
+        }
+        __syncwarp();
+      }
+      __syncthreads();
+      continue;
+    }
+    // ---- long epochs: histogram over all steps, then the scatter in groups of 64 steps
+    for (int b = tid; b <= spe; b += kSchedThreads) s_hist[b] = 0;
+    __syncthreads();                       // also: s_j complete, the previous row's scatter done
+    for (int base = w0; base < w1; base += 32 * NI) {
+      uint32_t q[NI];
+      bool live[NI];
+      steps_of(base, q, live);
+#pragma unroll
+      for (int u = 0; u < NI; ++u) {
+        const unsigned act = __ballot_sync(FULL, live[u]);
+        if (live[u]) {
+          s_stepof[base + 32 * u + lane] = (unsigned short)q[u];
+          const unsigned same = __match_any_sync(act, q[u]);
+          if (lane == __ffs(same) - 1) atomicAdd(&s_hist[q[u]], __popc(same));
+        }
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    // ---- exclusive scan of the histogram (spe + 1 entries, the last becomes m)
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base <= spe; base += kSchedThreads) {
+      const int x = base + tid;
+      const int v = x <= spe ? s_hist[x] : 0;
+      int inc = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int a = __shfl_up_sync(FULL, inc, o);
+        if (lane >= o) inc += a;
+      }
+      if (lane == 31) s_warp_tot[warp] = inc;
+      __syncthreads();
+      if (warp == 0) {
+        int w = lane < NW ? s_warp_tot[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int a = __shfl_up_sync(FULL, w, o);
+          if (lane >= o) w += a;
+        }
+        if (lane < NW) s_warp_tot[lane] = w;
+      }
+      __syncthreads();
+      const int excl = s_carry + (warp > 0 ? s_warp_tot[warp - 1] : 0) + inc - v;
+      if (x <= spe) { s_hist[x] = excl; off[x] = excl; }
+      __syncthreads();
+      if (tid == 0) s_carry += s_warp_tot[NW - 1];
+      __syncthreads();
+    }
+    // ---- stable scatter, 64 steps at a time: per-warp bin counts -> per-warp bin cursors; inside a warp
+    // __match_any ranks the lanes of one bin in lane (= slot) order
+    for (int g0 = 0; g0 < spe; g0 += 64) {
+      for (int x = tid; x < NW * 64; x += kSchedThreads) s_wh[x] = 0;
+      __syncthreads();
+      for (int s0 = w0; s0 < w1; s0 += 32) {
+        const int sl = s0 + lane;
+        const int b = sl < w1 ? (int)s_stepof[sl] - g0 : -1;
+        const bool in = b >= 0 && b < 64;
+        const unsigned act = __ballot_sync(FULL, in);
+        if (in) {
+          const unsigned same = __match_any_sync(act, b);
+          if (lane == __ffs(same) - 1) s_wh[warp * 64 + b] += __popc(same);     // the warp's own counters
+        }
+        __syncwarp();
+      }
+      __syncthreads();
+      if (tid < 64 && g0 + tid < spe) {
+        int run = s_hist[g0 + tid];
+        for (int w = 0; w < NW; ++w) {
+          const int t = s_wh[w * 64 + tid];
+          s_wh[w * 64 + tid] = run;
+          run += t;
+        }
+      }
+      __syncthreads();
+      for (int s0 = w0; s0 < w1; s0 += 32) {
+        const int sl = s0 + lane;
+        const int b = sl < w1 ? (int)s_stepof[sl] - g0 : -1;
+        const bool in = b >= 0 && b < 64;
+        const unsigned act = __ballot_sync(FULL, in);
+        if (in) {
+          const unsigned same = __match_any_sync(act, b);
+          out[s_wh[warp * 64 + b] + __popc(same & lt)] = (unsigned short)sl;
+          __syncwarp(act);
+          if (lane == __ffs(same) - 1) s_wh[warp * 64 + b] += __popc(same);
+        }
+        __syncwarp();
+      }
+      __syncthreads();
+    }
+  }
+}
+
 // ---------------------------------------------------------------- the training kernel
-// The loop below is issue-bound (ncu: ~60 % issue-slot utilisation, profiles/): launch-uniform array bases,
+// The loop below is issue-bound (ncu: ~50 % issue-slot utilisation, profiles/): launch-uniform array bases,
 // 32-bit shared-memory indexing, packed cache records and compile-time CACHED keep its instruction count down.
-template <int D, bool CACHED, bool WIDE>
+template <int D, bool CACHED>
 __global__ void __launch_bounds__(kOwnThreads, 1)
 mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams_t hp, int epochs,
                 long long step_begin, long long step_end, OwnerWs* ws, unsigned dbg) {
@@ -237,9 +480,8 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
   __shared__ Plan s_pl;
   __shared__ ure_mf_shard_t s_sh;
   __shared__ float s_wsse[NW];
-  __shared__ int s_wcnt[NW];
   __shared__ int s_bkey[2 * NW];           // row of every boundary record (-1: unused)
-  __shared__ FeistelKeys s_keys;           // of the epoch whose step_of is being filled
+  __shared__ int s_total;                  // entries of the batch list in s_list
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gl = lane % G, gw = lane / G;
   make_plan(shards, K, blockIdx.x, gridDim.x, s_pl, s_ps);
@@ -257,12 +499,10 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
 
   // ---- shared-memory carve-up: bases depend on kernel parameters only
   const int cap = hp.owner_cap_slots;      // multiple of 16, >= m
-  using step_t = typename std::conditional<WIDE, unsigned short, unsigned char>::type;   // u16 for long epochs
   float* const s_bnd = reinterpret_cast<float*>(dyn);                       // [2*NW][D] boundary-row partial sums
   unsigned short* const s_list = reinterpret_cast<unsigned short*>(s_bnd + 2 * NW * D);   // [cap] slots of the batch
   uint2* const s_rec = reinterpret_cast<uint2*>(s_list + cap);              // [cap], CACHED only
-  step_t* const s_step = reinterpret_cast<step_t*>(s_rec + (CACHED ? cap : 0));   // [2][cap]
-  float* const s_w = reinterpret_cast<float*>(s_step + 2 * cap);            // row r: s_w + r*RS
+  float* const s_w = reinterpret_cast<float*>(s_rec + (CACHED ? cap : 0));  // row r: s_w + r*RS
   float* const s_b = s_w + D;
   float* const s_g = s_w + 2 * D;
   int* const s_bidx = reinterpret_cast<int*>(s_w + hp.owner_cap_rows * RS);   // [rows] first boundary record, or INT_MAX
@@ -277,13 +517,26 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
     if (CACHED) return s_rec[sl];
     return pack_rec(__ldg((sl >= mU ? recI : recU) + sl), sl >= mU);
   };
-
-  // this warp's slots [w0, w1) of the per-step batch scan
-  const int per = (((m + NW - 1) / NW) + 15) & ~15;       // 16-byte aligned chunks of step_of
-  const int w0 = min(warp * per, m), w1 = min(w0 + per, m);
   const int offF = (int)(s_bnd - s_g) + 2 * warp * D, offL = offF + D;      // float offsets relative to s_g
 
-  // ---- prologue: owned rows -> shared memory, record cache
+  // the CTA's part of the schedule (ure_mf_owner_schedule): row of the shard's epoch, run of the step
+  const int sched_e0 = (int)(hp.owner_sched_step0 / spe);
+  const unsigned short* const sched = hp.owner_sched + s_pl.slot_base;
+  const int* const sched_off = hp.owner_sched_off + (long long)blockIdx.x * (hp.owner_spe_cap + 1);
+  const long long off_row = (long long)gridDim.x * (hp.owner_spe_cap + 1);
+  // batch list of (epoch ep, step kk) -> s_list, its length -> s_total; false: outside the scheduled window
+  auto load_list = [&](int ep, int kk) {
+    const int row = ep - sched_e0;
+    if (row < 0 || row >= hp.owner_sched_rows) return false;
+    const int* o = sched_off + row * off_row + kk;
+    const int a = __ldg(o), b = __ldg(o + 1);
+    const unsigned short* src = sched + row * hp.owner_sched_stride + a;
+    for (int x = tid; x < b - a; x += kOwnThreads) s_list[x] = __ldg(src + x);
+    if (tid == 0) s_total = b - a;
+    return true;
+  };
+
+  // ---- prologue: owned rows -> shared memory, record cache, first batch list
   for (int x = tid; x < rows * G; x += kOwnThreads) {
     const int r = x / G, c = x % G;
     const bool it = r >= rowsU;
@@ -297,57 +550,8 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
   for (int r = tid; r < rows; r += kOwnThreads) s_bidx[r] = 0x7fffffff;
   if (CACHED)
     for (int sl = tid; sl < m; sl += kOwnThreads) s_rec[sl] = pack_rec(__ldg((sl >= mU ? recI : recU) + sl), sl >= mU);
-  // slots beyond m never match a step number
-  for (int x = m + tid; x < cap; x += kOwnThreads) s_step[x] = s_step[cap + x] = (step_t)~0u;
-
-  // ---- visiting order -> step_of
-  FeistelDomain dom;
-  dom.init((uint32_t)n);
-  const uint32_t magic = (uint32_t)(0x100000000ull / (uint32_t)B);     // floor(2^32/B): quotient low by <= 1
-  auto set_keys = [&](int epoch) {         // by one thread, a block barrier before the next fill
-    if (tid == 0) s_keys.init(perm_key(sh.perm_seed, (uint32_t)sh.shard_id, (uint32_t)epoch));
-  };
-  auto fill_step_of = [&](int epoch, int lo, int hi) {
-    constexpr int NI = 2;
-    const int ob = (epoch & 1) * cap;
-    const FeistelKeys ks = s_keys;
-    const int32_t* pinv = sh.perm_inv ? sh.perm_inv + (long long)epoch * n : nullptr;
-    // slots are dealt from the LAST thread down: a short extra round lands on warp 31, not on the warp that polls
-    for (int s0 = lo + (kOwnThreads - 1 - tid); s0 < hi; s0 += NI * kOwnThreads) {
-      uint32_t x[NI];
-      bool live[NI];
-#pragma unroll
-      for (int u = 0; u < NI; ++u) {
-        const int sl = s0 + u * kOwnThreads;
-        live[u] = sl < hi;
-        x[u] = 0;
-        if (live[u]) x[u] = (uint32_t)__ldg(&((sl >= mU ? recI : recU) + sl)->w);
-      }
-      if (pinv) {
-#pragma unroll
-        for (int u = 0; u < NI; ++u)
-          if (live[u]) x[u] = (uint32_t)__ldg(pinv + x[u]);
-      } else if (!(dbg & 2u)) {
-        feistel_inverse_n<NI>(dom, ks, x, live);
-      }
-#pragma unroll
-      for (int u = 0; u < NI; ++u) {
-        if (!live[u]) continue;
-        uint32_t q = B == 1 ? x[u] : mulhi32(x[u], magic);
-        if ((q + 1) * (uint32_t)B <= x[u]) ++q;
-        const int sl = s0 + u * kOwnThreads;
-        s_step[ob + sl] = (step_t)q;
-      }
-    }
-  };
   int e = (int)(step_begin / spe), k = (int)(step_begin % spe);
-  set_keys(e);
-  __syncthreads();
-  fill_step_of(e, 0, m);
-  __syncthreads();
-  set_keys(e + 1);
-  __syncthreads();
-  if (k > 0 && e + 1 < epochs) fill_step_of(e + 1, 0, (int)((long long)k * m / spe));
+  bool in_window = load_list(e, k);
   __syncthreads();
 
   auto lr_of = [&](int epoch) {
@@ -367,106 +571,23 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
   if (trace && tid == 32 && (t - step_begin) < trace_steps)                        \
     trace[((t - step_begin) * gridDim.x + blockIdx.x) * 6 + (PH)] = clock64();
 
-  // Batch scan of one step: every lane looks at 16 CONSECUTIVE slots of the warp's range per chunk (one 16-byte
-  // load) and keeps their hit mask in a register; the warp's total goes to s_wcnt.  Runs in the barrier's shadow
-  // of the step before (the prologue for the first step); the list itself is written at the top of the step.
-  constexpr int MAXCH = 4;                 // chunks of 512 slots kept in registers; longer ranges re-scan
-  unsigned hm[MAXCH];
-  auto scan_batch = [&](int ep, int kk) {
-    const step_t* const stp = s_step + (ep & 1) * cap;
-    const unsigned k4 = (unsigned)kk * (WIDE ? 0x00010001u : 0x01010101u);
-    int cnt = 0;
-#pragma unroll
-    for (int c = 0; c < MAXCH; ++c) {
-      const int sl = w0 + 512 * c + 16 * lane;
-      unsigned mask = 0;
-      if (sl < w1) {
-        if (WIDE) {
-          const uint4 v0 = *reinterpret_cast<const uint4*>(stp + sl), v1 = *reinterpret_cast<const uint4*>(stp + sl + 8);
-          const unsigned w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const unsigned a = __vcmpeq2(w[j], k4);
-            mask |= ((a & 1u) | ((a >> 15) & 2u)) << (2 * j);
-          }
-        } else {
-          const uint4 v = *reinterpret_cast<const uint4*>(stp + sl);
-          const unsigned w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const unsigned a = __vcmpeq4(w[j], k4) & 0x01010101u;
-            mask |= ((a | (a >> 7) | (a >> 14) | (a >> 21)) & 0xfu) << (4 * j);
-          }
-        }
-        if (sl + 16 > w1) mask &= (1u << (w1 - sl)) - 1u;    // slots of the next warp / the pad
-      }
-      hm[c] = mask;
-      cnt += __popc(mask);
-    }
-    for (int sl = w0 + 512 * MAXCH + lane; sl < w1; sl += 32) cnt += (int)stp[sl] == kk;   // rare: long ranges
-    cnt = (int)warp_sum((float)cnt);       // exact: counts are far below 2^24
-    if (lane == 0) s_wcnt[warp] = cnt;
-  };
-  scan_batch(e, k);
-  __syncthreads();
-
   for (long long t = step_begin; t < t_end; ++t) {
+    if (!in_window) {                      // uniform over the shard's CTAs: all of them stop at the same step
+      if (tid == 0) ws->error = 1;
+      break;
+    }
     const bool rd = (t - step_begin) & 1;
     const float* const Pr = rd ? sh.gP : sh.P;
     const float* const Qr = rd ? sh.gQ : sh.Q;
     float sse_l = 0.f;
+    const int total = s_total;
     URE_STAMP(0)
 
-    // -------------------------------------------------------------- (1) the batch, as a sorted list of slots
-    // (hit masks hm[] and the warp totals s_wcnt were prepared in the previous step's barrier shadow)
-    const step_t* const stp = s_step + (e & 1) * cap;
-    // exclusive prefix of the warps' totals inside the CTA
-    int incl = s_wcnt[lane];
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int a = __shfl_up_sync(FULL, incl, o);
-      if (lane >= o) incl += a;
-    }
-    const int total = __shfl_sync(FULL, incl, 31);
-    {
-      const int wbase = __shfl_sync(FULL, incl, warp) - s_wcnt[warp];   // first position of the warp
-      int pos = wbase;
-      // chunk-major, lane-major inside a chunk: positions of chunk c start after all hits of chunks < c
-#pragma unroll
-      for (int c = 0; c < MAXCH; ++c) {
-        const int hc = __popc(hm[c]);
-        int ci = hc;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int a = __shfl_up_sync(FULL, ci, o);
-          if (lane >= o) ci += a;
-        }
-        int p = pos + ci - hc;
-        unsigned mk = hm[c];
-        const int sl = w0 + 512 * c + 16 * lane;
-        while (mk) {
-          const int bpos = __ffs(mk) - 1;
-          mk &= mk - 1;
-          s_list[p++] = (unsigned short)(sl + bpos);
-        }
-        pos += __shfl_sync(FULL, ci, 31);
-        if (w0 + 512 * (c + 1) >= w1) break;            // warp-uniform
-      }
-      for (int s0 = w0 + 512 * MAXCH; s0 < w1; s0 += 32) {     // rare: long ranges, one slot per lane
-        const int sl = s0 + lane;
-        const bool hit = ((int)stp[min(sl, w1 - 1)] == k) & (sl < w1);
-        const unsigned bal = __ballot_sync(FULL, hit);
-        if (hit) s_list[pos + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)sl;
-        pos += __popc(bal);
-      }
-    }
-    __syncthreads();
-    URE_STAMP(1)
-
-    // -------------------------------------------------------------- (2) waves: this warp's contiguous share
-    // Only the first and the last row of the share can be shared with other warps: their partial sums go to the
-    // warp's two boundary records, everything else straight to the row's accumulator (plain read-modify-write:
-    // within the warp, flushes of one row are at different program points with a __syncwarp between them).
+    // -------------------------------------------------------------- waves: this warp's contiguous share of the
+    // sorted batch list.  Only the first and the last row of the share can be shared with other warps: their
+    // partial sums go to the warp's two boundary records, everything else straight to the row's accumulator
+    // (plain read-modify-write: within the warp, flushes of one row are at different program points with a
+    // __syncwarp between them).
     const int n_waves = (total + WAVE - 1) / WAVE;
     const int wv0 = warp * (n_waves / NW) + min(warp, n_waves % NW);
     const int wv1 = wv0 + n_waves / NW + (warp < n_waves % NW ? 1 : 0);
@@ -543,10 +664,11 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
     }
     sse_l = warp_sum(sse_l);
     if (lane == 0) s_wsse[warp] = sse_l * (1.f / G);
+    URE_STAMP(1)
     __syncthreads();
     URE_STAMP(2)
 
-    // ------------------------------------------------------------ (3) SGD update of every owned row, publication
+    // ------------------------------------------------------------ SGD update of every owned row, publication
     {
       float* const Pw = rd ? sh.P : sh.gP;
       float* const Qw = rd ? sh.Q : sh.gQ;
@@ -589,18 +711,14 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
     __syncwarp();
     bar_target += n_cta;
     const bool last_of_epoch = k + 1 == spe;
-    // in the barrier's shadow: this step's slice of the NEXT epoch's step_of
-    if (e + 1 < epochs) fill_step_of(e + 1, (int)((long long)k * m / spe), (int)((long long)(k + 1) * m / spe));
-    if (t + 1 < t_end) {                   // ... and the batch scan of the NEXT step
-      if (last_of_epoch) __syncthreads();  // its step_of buffer was completed by the fill just above
-      scan_batch(last_of_epoch ? e + 1 : e, last_of_epoch ? 0 : k + 1);
-    }
+    // in the barrier's shadow: the batch list of the NEXT step
+    if (t + 1 < t_end) in_window = load_list(last_of_epoch ? e + 1 : e, last_of_epoch ? 0 : k + 1);
     URE_STAMP(4)
     if (tid == 0) {
       float v = 0.f;
       for (int w = 0; w < NW; ++w) v += s_wsse[w];
       epoch_sse += (double)v;
-      if (last_of_epoch || t + 1 == t_end) {
+      if (last_of_epoch || t + 1 == t_end || !in_window) {
         if (epoch_sse != 0.0) atomicAdd(sh.sse + e, epoch_sse);
         epoch_sse = 0.0;
       }
@@ -609,12 +727,8 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
     }
     __syncthreads();
     URE_STAMP(5)
-    if (last_of_epoch) {
-      ++e; k = 0; nlr = -lr_of(e);
-      set_keys(e + 1);                     // read by the fill after this step's block barriers
-    } else {
-      ++k;
-    }
+    if (last_of_epoch) { ++e; k = 0; nlr = -lr_of(e); }
+    else ++k;
   }
 #undef URE_STAMP
 
@@ -641,9 +755,7 @@ int max_dyn_smem(int* out) {
 template <int D>
 int launch_owner(const ure_mf_shard_t* d_shards, int K, const ure_mf_hparams_t& hp, int epochs, long long s0,
                  long long s1, OwnerWs* ws, int smem, bool cached, unsigned dbg, cudaStream_t st) {
-  const bool wide = (hp.owner_flags & 2) != 0;
-  auto kern = cached ? (wide ? mf_owner_kernel<D, true, true> : mf_owner_kernel<D, true, false>)
-                     : (wide ? mf_owner_kernel<D, false, true> : mf_owner_kernel<D, false, false>);
+  auto kern = cached ? mf_owner_kernel<D, true> : mf_owner_kernel<D, false>;
   URE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   URE_CUDA(cudaMemsetAsync(ws->bar, 0, sizeof(ws->bar), st));
   void* args[] = {(void*)&d_shards, (void*)&K,  (void*)&hp, (void*)&epochs,
@@ -678,8 +790,10 @@ int mf_train_owner(const ure_mf_shard_t* d_shards, int n_shards, const ure_mf_hp
   URE_REQUIRE(hp->owner_cap_slots <= 65520 && hp->owner_cap_rows < (1 << (32 - kOtherBits)), URE_EUNSUPPORTED,
               "ure_mf_train(owner): %d interactions / %d rows per CTA exceed the 16-bit slot / 12-bit row fields",
               hp->owner_cap_slots, hp->owner_cap_rows);
-  const bool cached = (hp->owner_flags & 1) != 0, wide = (hp->owner_flags & 2) != 0;
-  const long long need = owner_smem_bytes(hp->d, hp->owner_cap_rows, hp->owner_cap_slots, wide, cached);
+  URE_REQUIRE(hp->owner_sched && hp->owner_sched_off && hp->owner_sched_rows > 0 && hp->owner_sched_step0 <= step_begin,
+              URE_EINVAL, "ure_mf_train(owner): no schedule for step %lld (ure_mf_owner_schedule first)", step_begin);
+  const bool cached = (hp->owner_flags & 1) != 0;
+  const long long need = owner_smem_bytes(hp->d, hp->owner_cap_rows, hp->owner_cap_slots, cached);
   int avail = 0;
   if (int rc = max_dyn_smem(&avail)) return rc;
   URE_REQUIRE(need <= avail, URE_EUNSUPPORTED,
@@ -702,8 +816,34 @@ int mf_train_owner(const ure_mf_shard_t* d_shards, int n_shards, const ure_mf_hp
 
 }  // namespace ure
 
-extern "C" int64_t ure_mf_owner_smem_bytes(int d, int cap_rows, int cap_slots, int wide, int cached) {
-  return ure::owner_smem_bytes(d, cap_rows, cap_slots, wide != 0, cached != 0);
+extern "C" int64_t ure_mf_owner_smem_bytes(int d, int cap_rows, int cap_slots, int spe_cap, int cached) {
+  const long long a = ure::owner_smem_bytes(d, cap_rows, cap_slots, cached != 0);
+  const long long b = ure::schedule_smem_bytes(cap_slots, spe_cap);
+  return a > b ? a : b;
+}
+
+extern "C" int ure_mf_owner_schedule(const ure_mf_shard_t* d_shards, int n_shards, const ure_mf_hparams_t* h_hp,
+                                     int epochs, int64_t step0, void* stream) {
+  using namespace ure;
+  URE_REQUIRE(d_shards && h_hp && h_hp->owner_sched && h_hp->owner_sched_off, URE_EINVAL,
+              "ure_mf_owner_schedule: null argument");
+  URE_REQUIRE(h_hp->owner_sched_rows >= 1 && h_hp->owner_spe_cap >= 1 && h_hp->owner_spe_cap <= kMaxSpe &&
+                  h_hp->owner_cap_slots % 16 == 0 && h_hp->owner_cap_slots <= 65520,
+              URE_EUNSUPPORTED, "ure_mf_owner_schedule: rows=%d spe_cap=%d cap_slots=%d outside the supported range",
+              h_hp->owner_sched_rows, h_hp->owner_spe_cap, h_hp->owner_cap_slots);
+  const long long need = schedule_smem_bytes(h_hp->owner_cap_slots, h_hp->owner_spe_cap);
+  int avail = 0;
+  if (int rc = max_dyn_smem(&avail)) return rc;
+  URE_REQUIRE(need <= avail, URE_EUNSUPPORTED, "ure_mf_owner_schedule: %lld bytes of shared memory needed, %d available",
+              need, avail);
+  ure_mf_hparams_t hp = *h_hp;
+  hp.owner_sched_step0 = step0;
+  URE_CUDA(cudaFuncSetAttribute(owner_schedule_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+  const int ny = h_hp->owner_sched_rows < 4 ? h_hp->owner_sched_rows : 4;    // 2 blocks per SM, 2 rounds
+  owner_schedule_kernel<<<dim3(num_sms(), ny), kSchedThreads, (size_t)need, static_cast<cudaStream_t>(stream)>>>(
+      d_shards, n_shards, hp, epochs, step0);
+  URE_CUDA(cudaGetLastError());
+  return 0;
 }
 
 extern "C" int ure_mf_owner_prepare(const ure_mf_shard_t* d_shards, int n_shards, const ure_mf_hparams_t* h_hp,
@@ -721,7 +861,7 @@ extern "C" int ure_mf_owner_prepare(const ure_mf_shard_t* d_shards, int n_shards
   perm_inverse_kernel<<<dim3(blocks, n_shards), 256, 0, st>>>(d_shards, epochs);
   int avail = 0;
   if (int rc = max_dyn_smem(&avail)) return rc;
-  const int head[8] = {0, 0, 0, avail, 0, 0, 0, 0};
+  const int head[6] = {0, 0, 0, avail, 0, 0};
   URE_CUDA(cudaMemcpyAsync(ws, head, sizeof(head), cudaMemcpyHostToDevice, st));
   plan_kernel<<<num_sms(), 32, 0, st>>>(d_shards, n_shards, h_hp->batch, ws);
   URE_CUDA(cudaGetLastError());

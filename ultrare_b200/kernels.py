@@ -160,6 +160,7 @@ def pointer_table(tensors: Sequence[torch.Tensor], device) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------------ MF training
+OWNER_SCHED_BYTES = 512 << 20  # device memory one ShardBatch may spend on owner-mode schedule tables
 DEFAULT_MF_MODE = "auto"       # schedule ShardBatch picks when the caller does not say (see ShardBatch)
 
 
@@ -233,7 +234,9 @@ class ShardBatch:
         self.ws = torch.zeros(int(_lib.lib().ure_mf_train_workspace_bytes()), dtype=torch.uint8, device=self.device)
         self.hp = MFHParams(d=d, batch=batch, lr0=lr, lr_decay=lr_decay, lr_step=lr_step,
                             weight_decay=weight_decay, momentum=momentum, mode=_lib.MF_DENSE,
-                            decay=None, decay_len=0, owner_cap_rows=0, owner_cap_slots=0, owner_flags=0)
+                            decay=None, decay_len=0, owner_cap_rows=0, owner_cap_slots=0, owner_flags=0,
+                            owner_spe_cap=0, owner_sched_rows=0, owner_sched=None, owner_sched_off=None,
+                            owner_sched_step0=0, owner_sched_stride=0)
         self.owner_plan = None
         self._owner_cache = bool(owner_cache)       # False: keep the records in L2 (tests of the uncached variant)
         if mode in ("owner", "auto"):
@@ -291,10 +294,10 @@ class ShardBatch:
             check(L.ure_mf_owner_prepare(_ptr(self.table), len(shards), C.byref(self.hp), self.epochs, _ptr(self.ws),
                                          _stream()), "ure_mf_owner_prepare")
         max_rows, max_slots, max_spe, avail = self.ws[:16].view(torch.int32).tolist()   # the one sync of the set-up
-        cap_rows, cap_slots, wide = max(1, max_rows), -(-max_slots // 16) * 16, int(max_spe > 255)
-        need = int(L.ure_mf_owner_smem_bytes(self.hp.d, cap_rows, cap_slots, wide, 0))
-        need_c = int(L.ure_mf_owner_smem_bytes(self.hp.d, cap_rows, cap_slots, wide, 1))
-        fits = need <= avail and cap_slots <= 65520 and cap_rows < 4096 and max_spe <= 65535
+        cap_rows, cap_slots, spe_cap = max(1, max_rows), -(-max_slots // 16) * 16, max(1, max_spe)
+        need = int(L.ure_mf_owner_smem_bytes(self.hp.d, cap_rows, cap_slots, spe_cap, 0))
+        need_c = int(L.ure_mf_owner_smem_bytes(self.hp.d, cap_rows, cap_slots, spe_cap, 1))
+        fits = need <= avail and cap_slots <= 65520 and cap_rows < 4096 and max_spe <= 8192
         cached = fits and need_c <= avail and self._owner_cache and \
             max(max(s.P.shape[0], s.Q.shape[0]) for s in shards) <= (1 << 20)
         self.owner_plan = {"smem_need": need, "smem_need_cached": need_c, "smem_avail": avail, "cached": cached,
@@ -306,9 +309,21 @@ class ShardBatch:
                 s.inter_u = s.inter_i = s.off_u = s.off_i = s.perm_inv = None
             self._owner_keep = None
             return "dense"
+        # schedule tables (ure_mf_owner_schedule): as many epochs per shard as OWNER_SCHED_BYTES allows, >= 2
+        grid = int(L.ure_mf_grid_size())
+        stride = max(1, 2 * n_tot)
+        row_bytes = 2 * stride + 4 * grid * (spe_cap + 1)
+        n_rows = int(min(self.epochs + 1, max(2, OWNER_SCHED_BYTES // row_bytes)))
+        self._sched = torch.empty((n_rows, stride), dtype=torch.int16, device=dev)
+        self._sched_off = torch.empty((n_rows, grid, spe_cap + 1), dtype=torch.int32, device=dev)
+        self._sched_cover = (0, 0)                     # global steps [a, b) the tables are valid for
+        self._spes = [s.steps_per_epoch(self.hp.batch) for s in shards if s.n > 0]
+        self.owner_plan["schedule_rows"], self.owner_plan["schedule_bytes"] = n_rows, n_rows * row_bytes
         self.hp.mode = _lib.MF_OWNER
-        self.hp.owner_cap_rows, self.hp.owner_cap_slots = cap_rows, cap_slots
-        self.hp.owner_flags = int(cached) | (wide << 1)
+        self.hp.owner_cap_rows, self.hp.owner_cap_slots, self.hp.owner_spe_cap = cap_rows, cap_slots, spe_cap
+        self.hp.owner_flags = int(cached)
+        self.hp.owner_sched, self.hp.owner_sched_off = self._sched.data_ptr(), self._sched_off.data_ptr()
+        self.hp.owner_sched_rows, self.hp.owner_sched_stride, self.hp.owner_sched_step0 = n_rows, stride, 0
         return "owner"
 
     @staticmethod
@@ -332,11 +347,24 @@ class ShardBatch:
         step_end = self.total_steps if step_end is None else min(int(step_end), self.total_steps)
         if step_end <= self.step:
             return
+        L = _lib.lib()
         with torch.cuda.device(self.device):
-            check(_lib.lib().ure_mf_train(_ptr(self.table), len(self.shards), C.byref(self.hp), self.epochs,
-                                          self.step, step_end, self.warps_group0, _ptr(self.ws), _stream()),
-                  "ure_mf_train")
-        self.step = step_end
+            while self.step < step_end:
+                t1 = step_end
+                if self.mode == "owner":
+                    # the schedule tables hold owner_sched_rows epochs per shard from the window's first step on
+                    a, b = self._sched_cover
+                    if not (a <= self.step < b):
+                        check(L.ure_mf_owner_schedule(_ptr(self.table), len(self.shards), C.byref(self.hp), self.epochs,
+                                                      self.step, _stream()), "ure_mf_owner_schedule")
+                        a = self.step                  # shard s leaves the window at step (a // spe_s + rows) * spe_s
+                        b = min([(a // spe + self.hp.owner_sched_rows) * spe for spe in self._spes
+                                 if a // spe + self.hp.owner_sched_rows < self.epochs] or [self.total_steps])
+                        self._sched_cover, self.hp.owner_sched_step0 = (a, b), a
+                    t1 = min(step_end, b)
+                check(L.ure_mf_train(_ptr(self.table), len(self.shards), C.byref(self.hp), self.epochs,
+                                     self.step, t1, self.warps_group0, _ptr(self.ws), _stream()), "ure_mf_train")
+                self.step = t1
 
     def flush(self) -> None:
         """Lazy mode: advance every row to the current step (call before reading P / Q)."""
@@ -351,6 +379,8 @@ class ShardBatch:
     def train_losses(self) -> List[np.ndarray]:
         """Per shard: sqrt(sse_epoch / n) for every epoch (utils.py:108).  Synchronises (one D2H)."""
         sse = torch.stack([s.sse for s in self.shards]).cpu().numpy()
+        if self.mode == "owner" and int(self.ws[16:20].view(torch.int32).item()) != 0:
+            raise RuntimeError("ultrare_b200: owner schedule asked for a step outside its scheduled window")
         return [np.sqrt(sse[j] / max(1, s.n)) for j, s in enumerate(self.shards)]
 
 

@@ -434,6 +434,12 @@ def main():
         run_reference(args)
     else:
         run_ours(args)
+    try:                                   # clean NCCL shutdown under torchrun (no warning after the JSON line)
+        import torch.distributed as td
+        if td.is_available() and td.is_initialized():
+            td.destroy_process_group()
+    except Exception:
+        pass
 
 
 if __name__ == "__main__":

@@ -275,6 +275,8 @@ def run_ours(args):
         k_ms.append(e0.elapsed_time(e1))
     kern_ms = float(np.median(k_ms))
     clocks = sampler.stop() if rank == 0 else None       # sampled over the timed steps + the kernel-alone repeats
+    if os.environ.get("URE_BENCH_DEBUG"):
+        print(f"[rank {rank}] last device-resident step: {un.timing}", file=sys.stderr)
     peak, peak_src = measured_peaks()
     alg_bytes = n_inter_local * E * A_MF(D_EMB)
     achieved = alg_bytes / (kern_ms / 1e3) / 1e9
@@ -285,7 +287,10 @@ def run_ours(args):
                                              {}).get("dram_bytes_per_launch")
 
     # ---- end to end from host buffers through the public API
-    h2d = 16 * (sum(a.shape[1] for a in sp["unlearn_train"]) + test_np.shape[1]) + 4 * len(del_user)
+    # uploaded per step: the float64 [3, n] arrays of this rank's shards and of the test sets (per-shard sets + the
+    # merged set), the deletion list, the shard descriptor table
+    h2d = 24 * (sum(a.shape[1] for a in sp["unlearn_train"]) + sum(t.shape[1] for t in test_all) + test_np.shape[1]) \
+        + 4 * len(del_user) + 160 * K_SHARDS
     e2e_ms = []
     d2h = 0
     for it in range(max(1, args.warmup // 2) + args.steps):

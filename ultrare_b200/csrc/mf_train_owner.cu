@@ -30,7 +30,7 @@
 namespace ure {
 namespace {
 
-constexpr int kOwnThreads = 1024;
+constexpr int kOwnThreads = 512;
 constexpr int KMAX = URE_MAX_SHARDS;
 
 struct OwnerWs {

@@ -126,27 +126,31 @@ def upload_interactions_many(raws, device, row_of: Optional[torch.Tensor] = None
         np.copyto(stages[j].numpy()[:24 * n].view(np.float64).reshape(3, n), arrs[j])
 
     todo = [j for j, a in enumerate(arrs) if a.shape[1]]
-    if len(todo) > 1 and sum(arrs[j].shape[1] for j in todo) >= (1 << 16):
-        list(_pack_pool().map(fill, todo))
-    else:
-        for j in todo:
-            fill(j)
-    outs = []
+    outs = [torch.empty((a.shape[1], 4), dtype=torch.int32, device=dev) for a in arrs]
+
+    def ship(j):                                            # main thread: async H2D + pack kernel of array j
+        n = arrs[j].shape[1]
+        cols = torch.empty((3, n), dtype=torch.float64, device=dev)
+        cols.copy_(stages[j][:24 * n].view(torch.float64).view(3, n), non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        _PINNED_BYTES[stages[j].shape[0]].append((stages[j], ev))
+        check(_lib.lib().ure_pack_interactions_f64(_ptr(cols), n, n, _ptr(row_of),
+                                                   0 if row_of is None else int(row_of.shape[0]), _ptr(outs[j]),
+                                                   _stream()), "ure_pack_interactions_f64")
+
     with torch.cuda.device(dev):
-        for j, raw in enumerate(arrs):
-            n = raw.shape[1]
-            out = torch.empty((n, 4), dtype=torch.int32, device=dev)
-            outs.append(out)
-            if n == 0:
-                continue
-            cols = torch.empty((3, n), dtype=torch.float64, device=dev)
-            cols.copy_(stages[j][:24 * n].view(torch.float64).view(3, n), non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record()
-            _PINNED_BYTES[stages[j].shape[0]].append((stages[j], ev))
-            check(_lib.lib().ure_pack_interactions_f64(_ptr(cols), n, n, _ptr(row_of),
-                                                       0 if row_of is None else int(row_of.shape[0]), _ptr(out),
-                                                       _stream()), "ure_pack_interactions_f64")
+        if len(todo) > 1 and sum(arrs[j].shape[1] for j in todo) >= (1 << 16):
+            # staging copies on worker threads; every array is shipped as soon as ITS copy is done, so the DMA
+            # engine works while the other arrays are still being copied
+            futs = [_pack_pool().submit(fill, j) for j in todo]
+            for j, f in zip(todo, futs):
+                f.result()
+                ship(j)
+        else:
+            for j in todo:
+                fill(j)
+                ship(j)
     return outs
 
 

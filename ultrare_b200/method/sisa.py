@@ -283,9 +283,10 @@ class Sisa(Scratch):
         self.dist.all_reduce(contrib)
         if base is None:
             return contrib
-        rows = (self._owner >= 0) & (retrain_flags[self._owner.clamp(min=0).long()] != 0)
+        # retrained owners' rows of the reduced table over a copy of the pre-unlearn table: the merge kernel again,
+        # with the reduced table (indexed by global user id) standing in for every shard's table
         merged = base.clone()
-        merged[rows] = contrib[rows]
+        kn.merge_user_rows([contrib] * K, self._owner, merged, row_of=None, retrain=retrain_flags, zero_unowned=False)
         return merged
 
     # ------------------------------------------------------------------ learn / unlearn

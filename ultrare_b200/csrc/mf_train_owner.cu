@@ -240,9 +240,9 @@ constexpr int kSchedThreads = 512;
 constexpr int kSchedWarps = kSchedThreads / 32;
 
 __host__ __device__ inline long long schedule_smem_bytes(int cap_slots, int spe_cap) {
-  // record index of every slot [cap] int | step of every slot [cap] u16 | histogram [spe_cap + 1] int
+  // record index of every slot [cap] int | step, rank of every slot 2 x [cap] u16 | histogram [spe_cap + 1] int
   // | per-warp bin counters [warps][64] int
-  return 6ll * cap_slots + 4ll * (spe_cap + 1) + 4ll * kSchedWarps * 64 + 16;
+  return 8ll * cap_slots + 4ll * (spe_cap + 1) + 4ll * kSchedWarps * 64 + 16;
 }
 
 __global__ void __launch_bounds__(kSchedThreads, 2)
@@ -265,7 +265,8 @@ owner_schedule_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_h
   const int cap = hp.owner_cap_slots, spe_cap = hp.owner_spe_cap;
   int* const s_j = reinterpret_cast<int*>(dyn);                            // [cap] record index of the slot
   unsigned short* const s_stepof = reinterpret_cast<unsigned short*>(s_j + cap);
-  int* const s_hist = reinterpret_cast<int*>(s_stepof + cap);              // [spe_cap + 1]
+  unsigned short* const s_rank = s_stepof + cap;                           // [cap] rank inside (warp, step)
+  int* const s_hist = reinterpret_cast<int*>(s_rank + cap);                // [spe_cap + 1]
   int* const s_wh = s_hist + spe_cap + 1;                                  // [NW][64]
   {
     const int4* const recU = reinterpret_cast<const int4*>(sh.inter_u + s_pl.su0);
@@ -320,18 +321,23 @@ owner_schedule_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_h
         bool live[NI];
         steps_of(base, q, live);
 #pragma unroll
-        for (int u = 0; u < NI; ++u) {
+        for (int u = 0; u < NI; ++u) {     // rank of the slot among the warp's slots of the same step, in slot order
           const unsigned act = __ballot_sync(FULL, live[u]);
+          unsigned same = 0;
+          int old = 0;
           if (live[u]) {
+            same = __match_any_sync(act, q[u]);
+            old = s_wh[warp * 64 + q[u]];                  // the warp's own counters
             s_stepof[base + 32 * u + lane] = (unsigned short)q[u];
-            const unsigned same = __match_any_sync(act, q[u]);
-            if (lane == __ffs(same) - 1) s_wh[warp * 64 + q[u]] += __popc(same);   // the warp's own counters
+            s_rank[base + 32 * u + lane] = (unsigned short)(old + __popc(same & lt));
           }
+          __syncwarp();
+          if (live[u] && lane == __ffs(same) - 1) s_wh[warp * 64 + q[u]] = old + __popc(same);
           __syncwarp();
         }
       }
       __syncthreads();
-      if (tid < 64) {                      // bin totals -> bin starts (two warps) -> per-warp cursors
+      if (tid < 64) {                      // bin totals -> bin starts (two warps) -> per-warp bases
         int tot = 0;
         for (int w = 0; w < NW; ++w) tot += s_wh[w * 64 + tid];
         int inc = tot;
@@ -352,19 +358,8 @@ owner_schedule_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_h
         }
       }
       __syncthreads();
-      for (int s0 = w0; s0 < w1; s0 += 32) {
-        const int sl = s0 + lane;
-        const bool in = sl < w1;
-        const int bq = in ? (int)s_stepof[sl] : 0;
-        const unsigned act = __ballot_sync(FULL, in);
-        if (in) {
-          const unsigned same = __match_any_sync(act, bq);
-          out[s_wh[warp * 64 + bq] + __popc(same & lt)] = (unsigned short)sl;
-          __syncwarp(act);
-          if (lane == __ffs(same) - 1) s_wh[warp * 64 + bq] += __popc(same);
-        }
-        __syncwarp();
-      }
+      for (int sl = w0 + lane; sl < w1; sl += 32)            // position = base of (warp, step) + rank: no order needed
+        out[s_wh[warp * 64 + s_stepof[sl]] + s_rank[sl]] = (unsigned short)sl;
       __syncthreads();
       continue;
     }

@@ -1,0 +1,27 @@
+import sys, time
+sys.path.insert(0, "/root/repo")
+import numpy as np, torch
+from ultrare_b200 import kernels as kn
+from ultrare_b200.method import utils as U
+dev = torch.device("cuda:0")
+rng = np.random.default_rng(7)
+n, d, k = 6040, 16, 5
+X = rng.standard_normal((n, d), dtype=np.float32)
+Xd = torch.tensor(X, device=dev); Cd = torch.tensor(X[:k].copy(), device=dev)
+def t(f, reps=20):
+    f(); torch.cuda.synchronize(); t0 = time.perf_counter()
+    for _ in range(reps): f()
+    torch.cuda.synchronize(); return (time.perf_counter() - t0) / reps * 1e3
+M, inert = kn.cost_matrix(Xd, Cd, want_inertia=True)
+scale = float(inert.item()) / n
+sched = [(e * scale, i) for e, i in U.SINKHORN_SCHEDULE]
+warm = [(e * scale, i) for e, i in U.SINKHORN_SCHEDULE[-U.SINKHORN_WARM_STAGES:]]
+print("schedule", U.SINKHORN_SCHEDULE, "tol", U.SINKHORN_TOL, "warm stages", U.SINKHORN_WARM_STAGES)
+print("cost_matrix ms", t(lambda: kn.cost_matrix(Xd, Cd, want_inertia=True)))
+print("sinkhorn cold ms", t(lambda: kn.sinkhorn(M, k, sched, tol=U.SINKHORN_TOL)))
+g = kn.sinkhorn(M, k, sched, tol=U.SINKHORN_TOL)
+print("sinkhorn warm ms", t(lambda: kn.sinkhorn(M, k, warm, g=g, tol=U.SINKHORN_TOL)))
+print("sinkhorn cold no tol ms", t(lambda: kn.sinkhorn(M, k, sched, tol=0.0)))
+print("assign ms", t(lambda: kn.assign_centroids(M, k, g, Xd)))
+np.random.seed(0); c0 = X[np.random.choice(n, k, replace=False)]
+print("ot_cluster_device ms", t(lambda: U.ot_cluster_device(X, k, centroid0=c0, device=dev), reps=5))

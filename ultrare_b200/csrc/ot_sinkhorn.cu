@@ -14,6 +14,7 @@
 // kpad/4 lanes; column sums go registers -> shuffle -> shared -> one fp64 atomic per
 // column per CTA.
 #include "common.cuh"
+#include <cooperative_groups.h>
 
 namespace ure {
 namespace {
@@ -71,7 +72,8 @@ __device__ __forceinline__ void load_g(const float* g, int k, int gl, float4 (&o
 // MSRC: row-major matrix base (global or shared) whose row 0 is row `base_row`.
 template <int KPAD>
 __device__ __forceinline__ void colsum_rows(const float* Msrc, long long base_row, long long r0, long long r1,
-                                            const float* g_sh, int k, float scale, float a, float* csum_sh) {
+                                            const float* g_sh, int k, float scale, float a, float* csum_sh,
+                                            float* warp_part = nullptr) {
   using RM = RowMap<KPAD>;
   const int lane = threadIdx.x & 31;
   const int gl = lane % RM::LPR;
@@ -82,6 +84,7 @@ __device__ __forceinline__ void colsum_rows(const float* Msrc, long long base_ro
   load_g<KPAD>(g_sh, k, gl, g);
 #pragma unroll
   for (int v = 0; v < RM::VEC; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 2
   for (long long row0 = r0 + (long long)warp * RM::RPW; row0 < r1; row0 += (long long)n_warps * RM::RPW) {
     const long long row = row0 + rw;
     const bool valid = row < r1;
@@ -110,8 +113,12 @@ __device__ __forceinline__ void colsum_rows(const float* Msrc, long long base_ro
     }
     if (rw == 0) {
       const int c = (v * RM::LPR + gl) * 4;
-      atomicAdd(&csum_sh[c + 0], acc[v].x); atomicAdd(&csum_sh[c + 1], acc[v].y);
-      atomicAdd(&csum_sh[c + 2], acc[v].z); atomicAdd(&csum_sh[c + 3], acc[v].w);
+      if (warp_part) {                     // one slot per warp: plain stores, summed by the caller
+        *reinterpret_cast<float4*>(warp_part + warp * KPAD + c) = acc[v];
+      } else {
+        atomicAdd(&csum_sh[c + 0], acc[v].x); atomicAdd(&csum_sh[c + 1], acc[v].y);
+        atomicAdd(&csum_sh[c + 2], acc[v].z); atomicAdd(&csum_sh[c + 3], acc[v].w);
+      }
     }
   }
 }
@@ -213,6 +220,96 @@ sinkhorn_kernel(const float* __restrict__ M, long long n, int k, float* __restri
   }
   if (blockIdx.x == 0)
     for (int j = tid; j < k; j += blockDim.x) g_io[j] = g_sh[j];
+}
+
+// --------------------------------------------------------------------------- cluster Sinkhorn (small problems)
+// ml1m-sized grouping (n = 6040, k = 5: M is 386 KB) is pure latency: a grid barrier on 148 SMs per iteration
+// costs more than the iteration.  Here ONE thread-block cluster holds M in the shared memory of its CTAs, every CTA
+// pushes its k partial column sums into every peer's shared memory (distributed shared memory) and a hardware
+// cluster barrier ends the iteration; slot arrays alternate, so one barrier per iteration is enough.
+constexpr int kClusterMax = 8;
+
+template <int KPAD>
+__global__ void __launch_bounds__(kSkThreads, 1)
+sinkhorn_cluster_kernel(const float* __restrict__ M, long long n, int k, float* __restrict__ g_io, SkStages stages,
+                        SkWorkspace* ws) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank(), CS = (int)cluster.num_blocks();
+  extern __shared__ __align__(16) float m_sh[];     // this CTA's rows of M
+  __shared__ float g_sh[KPAD];
+  __shared__ __align__(16) float part_sh[kSkThreads / 32][KPAD];
+  __shared__ float slots[2][kClusterMax][KPAD];     // [parity][source CTA][column]
+  __shared__ float err_sh;
+  const int tid = threadIdx.x;
+  const long long per = (n + CS - 1) / CS;
+  const long long r0 = per * rank < n ? per * rank : n;
+  const long long r1 = r0 + per < n ? r0 + per : n;
+  for (int j = tid; j < KPAD; j += blockDim.x) g_sh[j] = j < k ? g_io[j] : 0.f;
+  {
+    const long long cnt4 = (r1 - r0) * (KPAD / 4);
+    const float4* src = reinterpret_cast<const float4*>(M + r0 * KPAD);
+    for (long long x = tid; x < cnt4; x += blockDim.x) reinterpret_cast<float4*>(m_sh)[x] = __ldg(src + x);
+  }
+  cluster.sync();                                    // every CTA of the cluster is running: its shared memory exists
+  const float a = (float)(1.0 / (double)n);
+  const double logb = -log((double)k);
+  long long it_global = 0;
+  float last_err = 0.f;
+  for (int s = 0; s < stages.n; ++s) {
+    const float eps = stages.eps[s];
+    const float scale = kLog2e / eps;
+    for (int it = 0; it < stages.iters[s]; ++it, ++it_global) {
+      const int par = (int)(it_global & 1);
+      colsum_rows<KPAD>(m_sh, r0, r0, r1, g_sh, k, scale, a, nullptr, &part_sh[0][0]);   // every warp writes its slot
+      __syncthreads();
+      if (tid < KPAD) {
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < kSkThreads / 32; ++w) v += part_sh[w][tid];
+        for (int r = 0; r < CS; ++r) *cluster.map_shared_rank(&slots[par][rank][tid], r) = v;
+      }
+      if (tid == 0) err_sh = 0.f;
+      cluster.sync();                                // all partial sums of this iteration have landed everywhere
+      if (tid < k) {
+        double c = 0.0;
+        for (int r = 0; r < CS; ++r) c += (double)slots[par][r][tid];       // same order in every CTA
+        g_sh[tid] = (float)((double)g_sh[tid] + (double)eps * (logb - log(c)));
+        const float e = (float)(fabs(c * (double)k - 1.0));
+        atomicMax(reinterpret_cast<int*>(&err_sh), __float_as_int(e));       // e >= 0: int order == float order
+      }
+      __syncthreads();
+      const float err = err_sh;
+      last_err = err;
+      if (stages.tol > 0.f && err < stages.tol) { ++it_global; break; }      // identical decision in every CTA
+    }
+  }
+  if (rank == 0) {
+    for (int j = tid; j < k; j += blockDim.x) g_io[j] = g_sh[j];
+    if (tid == 0) { ws->col_err = (double)last_err; ws->iters_done = it_global; }
+  }
+  cluster.sync();                                    // no CTA leaves while a peer may still write into it
+}
+
+template <int KPAD>
+int launch_sinkhorn_cluster(const float* M, long long n, int k, float* g, const SkStages& st, SkWorkspace* ws, int cs,
+                            size_t smem, cudaStream_t stream) {
+  auto kern = sinkhorn_cluster_kernel<KPAD>;
+  URE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(cs);
+  cfg.blockDim = dim3(kSkThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  URE_CUDA(cudaLaunchKernelEx(&cfg, kern, M, n, k, g, st, ws));
+  return 0;
 }
 
 // --------------------------------------------------------------------------- plan / assignment
@@ -451,6 +548,15 @@ extern "C" int ure_sinkhorn(const float* d_M, int64_t n, int k, int kpad, float*
   const int grid = num_sms();
   const long long per = (n + grid - 1) / grid;
   const size_t need = (size_t)per * kpad * sizeof(float);
+  if (kpad <= 64) {
+    // tiny problem: one thread-block cluster, M in its CTAs' shared memory, column sums exchanged through
+    // distributed shared memory, a hardware cluster barrier per iteration
+    const long long per_c = (n + kClusterMax - 1) / kClusterMax;
+    const size_t need_c = (size_t)per_c * kpad * sizeof(float);
+    if (need_c <= 160 * 1024) {
+      URE_KPAD_SWITCH(kpad, return (launch_sinkhorn_cluster<KP>(d_M, n, k, d_g, stg, ws, kClusterMax, need_c, st)));
+    }
+  }
   if (need <= 200 * 1024) {
     // small problem: everything is latency -- one persistent launch, a CTA's rows cached in shared memory
     URE_KPAD_SWITCH(kpad, return (launch_sinkhorn<KP, true>(d_M, n, k, d_g, stg, ws, grid, need, st)));

@@ -74,10 +74,13 @@ if __name__ == "__main__":
     g = os.path.join(ROOT, "gpurun_out")
     tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
     for rep, out, title in ((f"{g}/prof_mf_{tag}c.ncu-rep", f"{tag}_mf_train_ncu.txt", "mf_train_kernel<16>, ml1m shape K=5, 10 epochs"),
-                            (f"{g}/prof_owner_v5c.ncu-rep", f"{tag}_mf_owner_ncu.txt",
-                             "mf_owner_kernel<16,cached,u8>, ml1m shape K=5, 10 epochs (70 steps)"),
+                            (f"{g}/prof_owner_final.ncu-rep", f"{tag}_mf_owner_ncu.txt",
+                             "mf_owner_kernel<16,cached>, ml1m shape K=5, 10 epochs (70 steps)"),
+                            (f"{g}/prof_sched_final.ncu-rep", f"{tag}_mf_owner_schedule_ncu.txt",
+                             "owner_schedule_kernel, ml1m shape K=5, 51-epoch window"),
                             (f"{g}/prof_ot_{tag}a.ncu-rep", f"{tag}_ot_ncu.txt", "OT grouping kernels, n=1M k=32 d=64")):
         if os.path.exists(rep):
             raw_summary(rep, out, title)
     if os.path.exists(f"{g}/launches_bench.csv"):
         launch_list(f"{g}/launches_bench.csv", f"{tag}_bench_launches.txt", "python bench.py --steps 2 --warmup 3 --no-cpu (N=1)")
+

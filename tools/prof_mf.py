@@ -90,7 +90,7 @@ def run_trace(flags, label):
     _lib.check(L.ure_mf_debug_flags(C.c_void_p(sb.ws.data_ptr()), 0, None))
     tr = trace.cpu().numpy().astype(np.float64)[5:]          # skip cold steps
     d = np.diff(tr, axis=2)                                   # [steps, grid, 5]
-    names = (["batch list", "waves", "boundary + sweep", "arrive + step_of slice", "barrier wait"] if args.mode == "owner" else
+    names = (["waves (warp 1)", "other warps", "row sweep", "arrive + next list", "barrier wait"] if args.mode == "owner" else
              ["gradients", "overlap1", "wait1", "sweep", "arr2+fetch+wait2"])
     print("per-phase SM cycles (median over CTAs and steps / p95 / max):")
     for k, nm in enumerate(names):

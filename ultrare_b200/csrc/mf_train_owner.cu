@@ -138,10 +138,10 @@ constexpr int kMaxSpe = 8192;             // steps per epoch the schedule pre-pa
 // Dynamic shared memory of the training kernel.  The layout depends on LAUNCH-uniform capacities only
 // (cap_rows, cap_slots: the plan's maxima over the CTAs), so every array base is a uniform value:
 //   boundary rows [2*warps][d] fp32 | batch list [cap_slots] u16 | record cache [cap_slots] 8 B (optional)
-//   | owned rows [cap_rows][3d] fp32 (w | buf | g) | first boundary record of every row [cap_rows] int
+//   | owned rows [cap_rows][3d] fp32 (w | buf | g) | first / last boundary record of every row 2 x [cap_rows] int
 __host__ __device__ inline long long owner_smem_bytes(int d, int cap_rows, int cap_slots, bool cached) {
   return 2ll * kOwnWarps * d * 4 + 2ll * cap_slots + (cached ? 8ll * cap_slots : 0) + 12ll * cap_rows * d +
-         4ll * cap_rows;
+         8ll * cap_rows;
 }
 __global__ void plan_kernel(const ure_mf_shard_t* shards, int K, int batch, OwnerWs* ws) {
   __shared__ PlanScratch ps;
@@ -475,7 +475,6 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
   __shared__ Plan s_pl;
   __shared__ ure_mf_shard_t s_sh;
   __shared__ float s_wsse[NW];
-  __shared__ int s_bkey[2 * NW];           // row of every boundary record (-1: unused)
   __shared__ int s_total;                  // entries of the batch list in s_list
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gl = lane % G, gw = lane / G;
@@ -501,6 +500,7 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
   float* const s_b = s_w + D;
   float* const s_g = s_w + 2 * D;
   int* const s_bidx = reinterpret_cast<int*>(s_w + hp.owner_cap_rows * RS);   // [rows] first boundary record, or INT_MAX
+  int* const s_blast = s_bidx + hp.owner_cap_rows;                            // [rows] last boundary record, or -1
 
   const int4* const recU = reinterpret_cast<const int4*>(sh.inter_u + s_pl.su0);           // slot sl < mU
   const int4* const recI = reinterpret_cast<const int4*>(sh.inter_i + s_pl.si0) - mU;      // slot sl >= mU
@@ -519,17 +519,25 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
   const unsigned short* const sched = hp.owner_sched + s_pl.slot_base;
   const int* const sched_off = hp.owner_sched_off + (long long)blockIdx.x * (hp.owner_spe_cap + 1);
   const long long off_row = (long long)gridDim.x * (hp.owner_spe_cap + 1);
-  // batch list of (epoch ep, step kk) -> s_list, its length -> s_total; false: outside the scheduled window
-  auto load_list = [&](int ep, int kk) {
+  // where the batch list of (epoch ep, step kk) lives: false = outside the scheduled window
+  auto find_list = [&](int ep, int kk, const unsigned short*& src, int& len) {
     const int row = ep - sched_e0;
+    src = sched;
+    len = 0;
     if (row < 0 || row >= hp.owner_sched_rows) return false;
     const int* o = sched_off + row * off_row + kk;
     const int a = __ldg(o), b = __ldg(o + 1);
-    const unsigned short* src = sched + row * hp.owner_sched_stride + a;
-    for (int x = tid; x < b - a; x += kOwnThreads) s_list[x] = __ldg(src + x);
-    if (tid == 0) s_total = b - a;
+    src = sched + row * hp.owner_sched_stride + a;
+    len = b - a;
     return true;
   };
+  // The list of step t+1 is fetched into registers at the START of step t (its address was looked up in the
+  // barrier shadow of step t-1) and stored to s_list in the shadow of step t: no global latency in the shadow.
+  constexpr int PF = 6;                    // register entries per thread; longer lists copy the rest directly
+  unsigned short pf[PF];
+  const unsigned short* nx_src = sched;    // list of the NEXT step
+  int nx_len = 0;
+  bool nx_ok = true;
 
   // ---- prologue: owned rows -> shared memory, record cache, first batch list
   for (int x = tid; x < rows * G; x += kOwnThreads) {
@@ -542,11 +550,19 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
   }
   for (int x = tid; x < 2 * NW * G; x += kOwnThreads)
     *reinterpret_cast<float4*>(s_bnd + 4 * x) = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int r = tid; r < rows; r += kOwnThreads) s_bidx[r] = 0x7fffffff;
+  for (int r = tid; r < rows; r += kOwnThreads) { s_bidx[r] = 0x7fffffff; s_blast[r] = -1; }
   if (CACHED)
     for (int sl = tid; sl < m; sl += kOwnThreads) s_rec[sl] = pack_rec(__ldg((sl >= mU ? recI : recU) + sl), sl >= mU);
   int e = (int)(step_begin / spe), k = (int)(step_begin % spe);
-  bool in_window = load_list(e, k);
+  bool in_window;
+  {
+    const unsigned short* src;
+    int len;
+    in_window = find_list(e, k, src, len);
+    for (int x = tid; x < len; x += kOwnThreads) s_list[x] = __ldg(src + x);
+    if (tid == 0) s_total = len;
+    if (step_begin + 1 < t_end) nx_ok = find_list(k + 1 == spe ? e + 1 : e, k + 1 == spe ? 0 : k + 1, nx_src, nx_len);
+  }
   __syncthreads();
 
   auto lr_of = [&](int epoch) {
@@ -577,6 +593,11 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
     float sse_l = 0.f;
     const int total = s_total;
     URE_STAMP(0)
+#pragma unroll
+    for (int i = 0; i < PF; ++i) {         // next step's list on its way into registers
+      const int x = tid + i * kOwnThreads;
+      pf[i] = x < nx_len ? __ldg(nx_src + x) : (unsigned short)0;
+    }
 
     // -------------------------------------------------------------- waves: this warp's contiguous share of the
     // sorted batch list.  Only the first and the last row of the share can be shared with other warps: their
@@ -593,8 +614,10 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
       rowL = (int)(rec_of(s_list[ent1 - 1]).x >> kOtherBits);
     }
     if (lane == 0) {
-      s_bkey[2 * warp] = rowF; s_bkey[2 * warp + 1] = rowL;
-      if (rowF >= 0) { atomicMin(&s_bidx[rowF], 2 * warp); atomicMin(&s_bidx[rowL], 2 * warp + 1); }
+      if (rowF >= 0) {
+        atomicMin(&s_bidx[rowF], 2 * warp); atomicMax(&s_blast[rowF], 2 * warp);
+        atomicMin(&s_bidx[rowL], 2 * warp + 1); atomicMax(&s_blast[rowL], 2 * warp + 1);
+      }
     }
     auto flush = [&](int row, const float4& a) {
       if (row >= 0) {
@@ -674,17 +697,18 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
         float4* gp = wp + D / 2;
         float4 g = *gp, w = *wp, b = *bp;
         // boundary rows: the partial sums of the warps that shared the row (adjacent records, in list order)
+        // (records first..last: all of this row or of warps without entries, whose records are zero)
         const int bi = s_bidx[r];
         if (bi != 0x7fffffff) {
-          for (int j = bi; j < 2 * NW && (s_bkey[j] < 0 || s_bkey[j] == r); ++j) {
-            if (s_bkey[j] < 0) continue;
+          const int bl = s_blast[r];
+          for (int j = bi; j <= bl; ++j) {
             float4* rp = reinterpret_cast<float4*>(s_bnd + j * D + 4 * c);
             const float4 v = *rp;
             g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w;
             *rp = make_float4(0.f, 0.f, 0.f, 0.f);
           }
           __syncwarp(__activemask());
-          if (c == 0) s_bidx[r] = 0x7fffffff;
+          if (c == 0) { s_bidx[r] = 0x7fffffff; s_blast[r] = -1; }
         }
         // torch SGD: d_p = g + wd*w (fma); buf = buf*mu + d_p; w = w + (-lr)*buf (fma)
         g.x = fmaf(wd, w.x, g.x); g.y = fmaf(wd, w.y, g.y); g.z = fmaf(wd, w.z, g.z); g.w = fmaf(wd, w.w, g.w);
@@ -706,8 +730,22 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
     __syncwarp();
     bar_target += n_cta;
     const bool last_of_epoch = k + 1 == spe;
-    // in the barrier's shadow: the batch list of the NEXT step
-    if (t + 1 < t_end) in_window = load_list(last_of_epoch ? e + 1 : e, last_of_epoch ? 0 : k + 1);
+    // in the barrier's shadow: the NEXT step's list goes to shared memory, the one after is looked up
+    if (t + 1 < t_end) {
+      in_window = nx_ok;
+#pragma unroll
+      for (int i = 0; i < PF; ++i) {
+        const int x = tid + i * kOwnThreads;
+        if (x < nx_len) s_list[x] = pf[i];
+      }
+      for (int x = tid + PF * kOwnThreads; x < nx_len; x += kOwnThreads) s_list[x] = __ldg(nx_src + x);
+      if (tid == 0) s_total = nx_len;
+      if (t + 2 < t_end) {
+        int e2 = last_of_epoch ? e + 1 : e, k2 = last_of_epoch ? 0 : k + 1;      // step t+1 ...
+        if (k2 + 1 == spe) { ++e2; k2 = 0; } else ++k2;                            // ... and t+2
+        nx_ok = find_list(e2, k2, nx_src, nx_len);
+      }
+    }
     URE_STAMP(4)
     if (tid == 0) {
       float v = 0.f;

@@ -20,6 +20,13 @@ namespace ure {
 namespace {
 
 constexpr float kLog2e = 1.4426950408889634f;
+
+// 2^x for x <= 0 (after the max shift): one MUFU, flush-to-zero; relative error 2^-22
+__device__ __forceinline__ float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 constexpr int kMaxStages = 16;
 constexpr int kSkThreads = 512;
 
@@ -47,14 +54,14 @@ __device__ __forceinline__ float row_softmax(const float4 (&m)[RowMap<KPAD>::VEC
   float s = 0.f;
 #pragma unroll
   for (int v = 0; v < RM::VEC; ++v) {
-    p[v].x = exp2f(p[v].x - mx); p[v].y = exp2f(p[v].y - mx);
-    p[v].z = exp2f(p[v].z - mx); p[v].w = exp2f(p[v].w - mx);
+    p[v].x = ex2_fast(p[v].x - mx); p[v].y = ex2_fast(p[v].y - mx);
+    p[v].z = ex2_fast(p[v].z - mx); p[v].w = ex2_fast(p[v].w - mx);
     s += (p[v].x + p[v].y) + (p[v].z + p[v].w);
   }
 #pragma unroll
   for (int o = RM::LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o, RM::LPR);
   row_max_t = mx;
-  return 1.0f / s;
+  return __frcp_rn(s);                     // s in [1, KPAD]
 }
 
 template <int KPAD>
@@ -229,7 +236,7 @@ sinkhorn_kernel(const float* __restrict__ M, long long n, int k, float* __restri
 // cluster barrier ends the iteration; slot arrays alternate, so one barrier per iteration is enough.
 constexpr int kClusterMax = 8;
 
-template <int KPAD>
+template <int KPAD, int KS>                 // KS <= KPAD columns are kept in shared memory (k <= KS)
 __global__ void __launch_bounds__(kSkThreads, 1)
 sinkhorn_cluster_kernel(const float* __restrict__ M, long long n, int k, float* __restrict__ g_io, SkStages stages,
                         SkWorkspace* ws) {
@@ -237,19 +244,20 @@ sinkhorn_cluster_kernel(const float* __restrict__ M, long long n, int k, float* 
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank(), CS = (int)cluster.num_blocks();
   extern __shared__ __align__(16) float m_sh[];     // this CTA's rows of M
-  __shared__ float g_sh[KPAD];
-  __shared__ __align__(16) float part_sh[kSkThreads / 32][KPAD];
-  __shared__ float slots[2][kClusterMax][KPAD];     // [parity][source CTA][column]
+  __shared__ float g_sh[KS];
+  __shared__ __align__(16) float part_sh[kSkThreads / 32][KS];
+  __shared__ float slots[2][kClusterMax][KS];     // [parity][source CTA][column]
   __shared__ float err_sh;
   const int tid = threadIdx.x;
   const long long per = (n + CS - 1) / CS;
   const long long r0 = per * rank < n ? per * rank : n;
   const long long r1 = r0 + per < n ? r0 + per : n;
-  for (int j = tid; j < KPAD; j += blockDim.x) g_sh[j] = j < k ? g_io[j] : 0.f;
+  for (int j = tid; j < KS; j += blockDim.x) g_sh[j] = j < k ? g_io[j] : 0.f;
   {
-    const long long cnt4 = (r1 - r0) * (KPAD / 4);
+    const int cnt4 = (int)(r1 - r0) * (KS / 4);
     const float4* src = reinterpret_cast<const float4*>(M + r0 * KPAD);
-    for (long long x = tid; x < cnt4; x += blockDim.x) reinterpret_cast<float4*>(m_sh)[x] = __ldg(src + x);
+    for (int x = tid; x < cnt4; x += blockDim.x)
+      reinterpret_cast<float4*>(m_sh)[x] = __ldg(src + (x / (KS / 4)) * (KPAD / 4) + x % (KS / 4));
   }
   cluster.sync();                                    // every CTA of the cluster is running: its shared memory exists
   const float a = (float)(1.0 / (double)n);
@@ -261,9 +269,9 @@ sinkhorn_cluster_kernel(const float* __restrict__ M, long long n, int k, float* 
     const float scale = kLog2e / eps;
     for (int it = 0; it < stages.iters[s]; ++it, ++it_global) {
       const int par = (int)(it_global & 1);
-      colsum_rows<KPAD>(m_sh, r0, r0, r1, g_sh, k, scale, a, nullptr, &part_sh[0][0]);   // every warp writes its slot
+      colsum_rows<KS>(m_sh, r0, r0, r1, g_sh, k, scale, a, nullptr, &part_sh[0][0]);   // every warp writes its slot
       __syncthreads();
-      if (tid < KPAD) {
+      if (tid < KS) {
         float v = 0.f;
 #pragma unroll
         for (int w = 0; w < kSkThreads / 32; ++w) v += part_sh[w][tid];
@@ -291,10 +299,10 @@ sinkhorn_cluster_kernel(const float* __restrict__ M, long long n, int k, float* 
   cluster.sync();                                    // no CTA leaves while a peer may still write into it
 }
 
-template <int KPAD>
+template <int KPAD, int KS>
 int launch_sinkhorn_cluster(const float* M, long long n, int k, float* g, const SkStages& st, SkWorkspace* ws, int cs,
                             size_t smem, cudaStream_t stream) {
-  auto kern = sinkhorn_cluster_kernel<KPAD>;
+  auto kern = sinkhorn_cluster_kernel<KPAD, KS>;
   URE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(cs);
@@ -552,9 +560,13 @@ extern "C" int ure_sinkhorn(const float* d_M, int64_t n, int k, int kpad, float*
     // tiny problem: one thread-block cluster, M in its CTAs' shared memory, column sums exchanged through
     // distributed shared memory, a hardware cluster barrier per iteration
     const long long per_c = (n + kClusterMax - 1) / kClusterMax;
-    const size_t need_c = (size_t)per_c * kpad * sizeof(float);
+    const int ks = k <= 8 ? 8 : kpad;                // columns kept in shared memory
+    const size_t need_c = (size_t)per_c * ks * sizeof(float);
     if (need_c <= 160 * 1024) {
-      URE_KPAD_SWITCH(kpad, return (launch_sinkhorn_cluster<KP>(d_M, n, k, d_g, stg, ws, kClusterMax, need_c, st)));
+      if (ks == 8) {
+        URE_KPAD_SWITCH(kpad, return (launch_sinkhorn_cluster<KP, 8>(d_M, n, k, d_g, stg, ws, kClusterMax, need_c, st)));
+      }
+      URE_KPAD_SWITCH(kpad, return (launch_sinkhorn_cluster<KP, KP>(d_M, n, k, d_g, stg, ws, kClusterMax, need_c, st)));
     }
   }
   if (need <= 200 * 1024) {

@@ -42,9 +42,10 @@ t0 = time.perf_counter()
 un.unlearn(models, tl, test_dl, test_data, list(sp["del_user"]), 0, "")
 torch.cuda.synchronize()
 print("one unlearn %.3f ms; retrained %s; timing %s" % ((time.perf_counter() - t0) * 1e3, sorted(un.retrain_gid), un.timing))
+print("plan sync wait ms", getattr(un._last_batch, "plan_sync_ms", None))
 pr = cProfile.Profile()
 pr.enable()
 new().unlearn(models, tl, test_dl, test_data, list(sp["del_user"]), 0, "")
 torch.cuda.synchronize()
 pr.disable()
-pstats.Stats(pr).sort_stats("cumulative").print_stats(35)
+pstats.Stats(pr).sort_stats("tottime").print_stats(28)

@@ -159,6 +159,23 @@ def upload_interactions(raw, device, row_of: Optional[torch.Tensor] = None) -> t
     return upload_interactions_many([raw], device, row_of)[0]
 
 
+def upload_array(a: np.ndarray, device) -> torch.Tensor:
+    """Small host array -> device through the pinned staging pool (asynchronous: the host does not wait for the
+    work already queued on the stream, unlike a pageable .to(device))."""
+    a = np.ascontiguousarray(a)
+    out = torch.empty(a.shape, dtype=torch.from_numpy(a[:0].reshape(-1)).dtype, device=device)
+    if a.size == 0:
+        return out
+    stage = _staging_bytes(a.nbytes)
+    stage.numpy()[:a.nbytes] = a.reshape(-1).view(np.uint8)
+    with torch.cuda.device(device):
+        out.view(-1).view(torch.uint8).copy_(stage[:a.nbytes], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        _PINNED_BYTES[stage.shape[0]].append((stage, ev))
+    return out
+
+
 def pointer_table(tensors: Sequence[torch.Tensor], device) -> torch.Tensor:
     return torch.tensor([t.data_ptr() for t in tensors], dtype=torch.int64, device=device)
 
@@ -268,8 +285,11 @@ class ShardBatch:
 
     def _upload_table(self):
         arr = (MFShard * len(self.shards))(*[s.descriptor() for s in self.shards])
-        self.host_table = arr
-        self.table = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(self.device)
+        blob = bytes(arr)
+        if getattr(self, "_table_blob", None) == blob:       # nothing changed since the last upload
+            return
+        self.host_table, self._table_blob = arr, blob
+        self.table = upload_array(np.frombuffer(blob, dtype=np.uint8), self.device)
 
     def _prepare_owner(self, required: bool) -> str:
         """Owner-mode set-up: one allocation for the sorted record copies + row offsets of every shard,
@@ -297,7 +317,10 @@ class ShardBatch:
         with torch.cuda.device(dev):
             check(L.ure_mf_owner_prepare(_ptr(self.table), len(shards), C.byref(self.hp), self.epochs, _ptr(self.ws),
                                          _stream()), "ure_mf_owner_prepare")
+        import time as _t
+        _t0 = _t.perf_counter()
         max_rows, max_slots, max_spe, avail = self.ws[:16].view(torch.int32).tolist()   # the one sync of the set-up
+        self.plan_sync_ms = (_t.perf_counter() - _t0) * 1e3
         cap_rows, cap_slots, spe_cap = max(1, max_rows), -(-max_slots // 16) * 16, max(1, max_spe)
         need = int(L.ure_mf_owner_smem_bytes(self.hp.d, cap_rows, cap_slots, spe_cap, 0))
         need_c = int(L.ure_mf_owner_smem_bytes(self.hp.d, cap_rows, cap_slots, spe_cap, 1))

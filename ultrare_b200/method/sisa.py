@@ -161,6 +161,7 @@ class Sisa(Scratch):
                 rows = [len(self.group_index[i]) if compact else self.n_user for i in mine]
                 views = kn.alloc_shard_batch(rows, self.n_item, self.k, E, self.device,
                                              model_generator(self.seed, mine[0] + 1, self.device))
+            t_a = time.time()
             from ..read import RatingData
             RatingData.upload_many([train_dlist[i].dataset for i in mine], self.device,
                                    self._row_of if compact else None, 'sisa_local' if compact else None)
@@ -169,16 +170,19 @@ class Sisa(Scratch):
                 rec = (ld.dataset.records_mapped(self.device, self._row_of, 'sisa_local') if compact
                        else ld.dataset.records(self.device))
                 scratch = None
-                if batched:
+                if batched:                 # the nn.Module wrappers are built while the GPU trains (below)
                     P, Q, scratch = views[j]
-                    models[i] = MF.wrap(P, Q)
                 else:
                     models[i] = self._new_model(i + 1, user_rows=self._rows(i)) if compact else self._new_model(i + 1)
-                states.append(kn.ShardState(rec, models[i].user_mat.weight.data, models[i].item_mat.weight.data, E,
-                                            shard_id=i + 1, perm_seed=self.seed, perm=ld.explicit_perm(self.device, E),
-                                            scratch=scratch))
+                    P, Q = models[i].user_mat.weight.data, models[i].item_mat.weight.data
+                states.append(kn.ShardState(rec, P, Q, E, shard_id=i + 1, perm_seed=self.seed,
+                                            perm=ld.explicit_perm(self.device, E), scratch=scratch))
             batch = train_dlist[mine[0]].batch_size
+            t_b = time.time()
             sb = kn.ShardBatch(states, self.k, batch, self.lr, self.lr_decay, 50, self.lam, self.momentum)
+            self.timing['setup_alloc_ms'] = (t_a - t0) * 1e3
+            self.timing['setup_upload_states_ms'] = (t_b - t_a) * 1e3
+            self.timing['setup_batch_ms'] = (time.time() - t_b) * 1e3
             if mode == 'faithful':
                 need = sum((s.P.numel() + s.Q.numel()) * 4 for s in states) * E
                 if need > 8 << 30:
@@ -199,14 +203,20 @@ class Sisa(Scratch):
                 self.timing['setup_ms'] = (time.time() - t0) * 1e3
                 sb.train()
                 self.timing['launch_ms'] = (time.time() - t0) * 1e3 - self.timing['setup_ms']
-                # while the GPU trains: stage what the final evaluation needs (upload + user segments are cached
-                # on the RatingData objects), so self.test() after the merge finds them resident
+                if batched:
+                    for j, i in enumerate(mine):
+                        models[i] = MF.wrap(states[j].P, states[j].Q)
+                # while the GPU trains: the model wrappers, and what the final evaluation needs (upload + user
+                # segments are cached on the RatingData objects), so self.test() after the merge finds them resident
                 for ld in ([test_data] if test_data is not None else []) + \
                         ([test_dlist[i] for i in mine] if mode == 'final' and self.dist.world == 1 else []):
                     ds = getattr(ld, 'dataset', None)
                     if ds is not None and len(ds) > 0:
                         ds.records(self.device)
                         ds.segments(self.device)
+            if batched and not models:
+                for j, i in enumerate(mine):
+                    models[i] = MF.wrap(states[j].P, states[j].Q)
             self._last_batch = sb
             losses = sb.train_losses()                       # the one sync of the whole training
         self.timing['train_s'] = time.time() - t0

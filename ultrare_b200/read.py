@@ -127,8 +127,8 @@ class RatingData:
         key = str(device)
         if key not in self._segments:
             order, seg = kn.user_segments(self.users)
-            self._segments[key] = (None if order is None else torch.from_numpy(order).to(device),
-                                   torch.from_numpy(seg).to(device))
+            self._segments[key] = (None if order is None else kn.upload_array(order, device),
+                                   kn.upload_array(seg, device))
         return self._segments[key]
 
 

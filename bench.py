@@ -296,7 +296,7 @@ def run_ours(args):
         + 4 * len(del_user) + 160 * K_SHARDS
     e2e_ms = []
     d2h = 0
-    for it in range(max(1, args.warmup // 2) + args.steps):
+    for it in range(args.warmup + args.steps):
         flush.fill_(it & 0xFF)
         d.barrier()
         torch.cuda.synchronize()
@@ -311,7 +311,7 @@ def run_ours(args):
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) * 1e3
         d2h = merged_h.numel() * 4 + sum(x.numel() * 4 for x in items_h) + 24
-        if it >= max(1, args.warmup // 2):
+        if it >= args.warmup:
             e2e_ms.append(d.max_float(dt))
     e2e_value = inter_total / (float(np.mean(e2e_ms)) / 1e3)
 

@@ -192,6 +192,11 @@ int ure_rank_metrics(const ure_inter_t* d_inter, const float* d_score, const int
 int ure_pack_interactions_f64(const double* d_cols, int64_t n, int64_t ld, const int32_t* d_row_of,
                               int32_t n_map, ure_inter_t* d_out, void* stream);
 
+/* HOST helper of the ingest path: copy `bytes` from pageable memory into a (pinned) staging buffer with
+ * non-temporal stores, so that the DMA engine reads DRAM and not other cores' caches.  Thread-safe on disjoint
+ * ranges (the caller's thread pool splits the arrays); dst 16-byte aligned. */
+int ure_host_stage_copy(void* h_dst, const void* h_src, int64_t bytes);
+
 /* Affected-shard routing (method/sisa.py:76-81): flags[owner[u]] = 1 for u in del. */
 int ure_route_deletions(const int32_t* d_owner, int32_t n_user, const int32_t* d_del, int32_t n_del,
                         int32_t* d_flags, int32_t n_shards, void* stream);

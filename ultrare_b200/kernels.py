@@ -113,44 +113,63 @@ def upload_interactions_many(raws, device, row_of: Optional[torch.Tensor] = None
     dev = torch.device(device)
     if dev.type != "cuda":
         raise RuntimeError("ultrare_b200: interactions are packed on a CUDA device (no CPU path exists)")
-    arrs, stages = [], []
+    arrs = []
     for raw in raws:
         raw = np.asarray(raw)
         if raw.ndim != 2 or raw.dtype != np.float64 or raw.shape[0] != 3:
             raw = np.ascontiguousarray(np.asarray(raw).reshape(3, -1)[:3], dtype=np.float64)
         arrs.append(raw)
-        stages.append(_staging_bytes(24 * raw.shape[1]) if raw.shape[1] else None)
+    ns = [a.shape[1] for a in arrs]
+    n_tot = sum(ns)
+    out_all = torch.empty((n_tot, 4), dtype=torch.int32, device=dev)
+    offs = np.concatenate([[0], np.cumsum(ns)]).astype(np.int64)
+    outs = [out_all[offs[j]:offs[j + 1]] for j in range(len(arrs))]
+    if n_tot == 0:
+        return outs
+    # ONE pinned staging buffer and ONE device buffer for all arrays; array j starts at a 64-byte boundary
+    starts = np.zeros(len(arrs) + 1, dtype=np.int64)              # in doubles
+    for j, n in enumerate(ns):
+        starts[j + 1] = (starts[j] + 3 * n + 7) // 8 * 8
+    tot_d = int(starts[-1])
+    stage = _staging_bytes(8 * tot_d)
+    stage_f = stage[:8 * tot_d].view(torch.float64)
+    base = stage.data_ptr()
+    cols_all = torch.empty(tot_d, dtype=torch.float64, device=dev)
+    L = _lib.lib()
+    CHUNK = 1 << 21                                               # bytes per staging task
 
-    def fill(j):
-        n = arrs[j].shape[1]
-        np.copyto(stages[j].numpy()[:24 * n].view(np.float64).reshape(3, n), arrs[j])
+    def fill(j, lo, hi):                                          # bytes [lo, hi) of array j, non-temporal stores
+        check(L.ure_host_stage_copy(C.c_void_p(base + 8 * int(starts[j]) + lo), C.c_void_p(arrs[j].ctypes.data + lo),
+                                    hi - lo), "ure_host_stage_copy")
 
-    todo = [j for j, a in enumerate(arrs) if a.shape[1]]
-    outs = [torch.empty((a.shape[1], 4), dtype=torch.int32, device=dev) for a in arrs]
+    def ship(j):                                                  # main thread: async H2D + pack kernel of array j
+        lo, hi = int(starts[j]), int(starts[j]) + 3 * ns[j]
+        cols_all[lo:hi].copy_(stage_f[lo:hi], non_blocking=True)
+        check(L.ure_pack_interactions_f64(C.c_void_p(cols_all.data_ptr() + 8 * lo), ns[j], ns[j], _ptr(row_of),
+                                          0 if row_of is None else int(row_of.shape[0]), _ptr(outs[j]), _stream()),
+              "ure_pack_interactions_f64")
 
-    def ship(j):                                            # main thread: async H2D + pack kernel of array j
-        n = arrs[j].shape[1]
-        cols = torch.empty((3, n), dtype=torch.float64, device=dev)
-        cols.copy_(stages[j][:24 * n].view(torch.float64).view(3, n), non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record()
-        _PINNED_BYTES[stages[j].shape[0]].append((stages[j], ev))
-        check(_lib.lib().ure_pack_interactions_f64(_ptr(cols), n, n, _ptr(row_of),
-                                                   0 if row_of is None else int(row_of.shape[0]), _ptr(outs[j]),
-                                                   _stream()), "ure_pack_interactions_f64")
-
+    todo = [j for j in range(len(arrs)) if ns[j]]
+    for j in todo:
+        if not arrs[j].flags.c_contiguous:
+            arrs[j] = np.ascontiguousarray(arrs[j])
     with torch.cuda.device(dev):
-        if len(todo) > 1 and sum(arrs[j].shape[1] for j in todo) >= (1 << 16):
-            # staging copies on worker threads; every array is shipped as soon as ITS copy is done, so the DMA
-            # engine works while the other arrays are still being copied
-            futs = [_pack_pool().submit(fill, j) for j in todo]
-            for j, f in zip(todo, futs):
-                f.result()
+        if n_tot >= (1 << 16):
+            # staging copies on worker threads (ctypes releases the GIL); every array is shipped as soon as ITS
+            # chunks are done, so the DMA engine works while the other arrays are still being copied
+            futs = {j: [_pack_pool().submit(fill, j, lo, min(24 * ns[j], lo + CHUNK))
+                        for lo in range(0, 24 * ns[j], CHUNK)] for j in todo}
+            for j in todo:
+                for f in futs[j]:
+                    f.result()
                 ship(j)
         else:
             for j in todo:
-                fill(j)
+                fill(j, 0, 24 * ns[j])
                 ship(j)
+        ev = torch.cuda.Event()
+        ev.record()
+        _PINNED_BYTES[stage.shape[0]].append((stage, ev))
     return outs
 
 
@@ -159,11 +178,15 @@ def upload_interactions(raw, device, row_of: Optional[torch.Tensor] = None) -> t
     return upload_interactions_many([raw], device, row_of)[0]
 
 
+_TORCH_DTYPE = {"uint8": torch.uint8, "int32": torch.int32, "int64": torch.int64, "float32": torch.float32,
+                "float64": torch.float64, "int16": torch.int16}
+
+
 def upload_array(a: np.ndarray, device) -> torch.Tensor:
     """Small host array -> device through the pinned staging pool (asynchronous: the host does not wait for the
     work already queued on the stream, unlike a pageable .to(device))."""
     a = np.ascontiguousarray(a)
-    out = torch.empty(a.shape, dtype=torch.from_numpy(a[:0].reshape(-1)).dtype, device=device)
+    out = torch.empty(a.shape, dtype=_TORCH_DTYPE[a.dtype.name], device=device)
     if a.size == 0:
         return out
     stage = _staging_bytes(a.nbytes)
@@ -177,7 +200,7 @@ def upload_array(a: np.ndarray, device) -> torch.Tensor:
 
 
 def pointer_table(tensors: Sequence[torch.Tensor], device) -> torch.Tensor:
-    return torch.tensor([t.data_ptr() for t in tensors], dtype=torch.int64, device=device)
+    return upload_array(np.array([t.data_ptr() for t in tensors], dtype=np.int64), device)
 
 
 # ------------------------------------------------------------------------------ MF training

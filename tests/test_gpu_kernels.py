@@ -438,3 +438,35 @@ def test_pack_interactions_on_device_equals_host_casts(cuda_dev):
     assert np.array_equal(got[:, 0], row_of[raw[0].astype(int)])
     assert np.array_equal(got, kn.pack_interactions(row_of[raw[0].astype(int)], raw[1], raw[2], cuda_dev).cpu().numpy())
     assert kn.upload_interactions(np.zeros((3, 0)), cuda_dev).shape == (0, 4)
+
+
+def test_mf_owner_schedule_windows_vs_oracle(cuda_dev, monkeypatch):
+    """Owner schedule with schedule tables that hold only 2 epochs per shard: the training is split into windows,
+    each with its own ure_mf_owner_schedule pass; ragged shards (different steps per epoch), 5 epochs."""
+    torch = _torch()
+    from ultrare_b200 import kernels as kn
+    monkeypatch.setattr(kn, "OWNER_SCHED_BYTES", 1)
+    rng = np.random.default_rng(21)
+    d, batch, epochs, K = 16, 700, 5, 3
+    shards, host = [], []
+    for s in range(K):
+        U, I, n = 90 + 20 * s, 120, 4000 + 1500 * s
+        u, i = rng.integers(0, U, n), rng.integers(0, I, n)
+        r = rng.integers(1, 6, n).astype(np.float32) / 5
+        P0 = rng.standard_normal((U, d), dtype=np.float32) * 0.3
+        Q0 = rng.standard_normal((I, d), dtype=np.float32) * 0.3
+        perms = [omf.feistel_perm(n, omf.perm_key(5, s, ep)) for ep in range(epochs)]
+        shards.append(kn.ShardState(kn.pack_interactions(u, i, r, cuda_dev), torch.tensor(P0, device=cuda_dev),
+                                    torch.tensor(Q0, device=cuda_dev), epochs, s, 5))
+        host.append((u, i, r, P0, Q0, perms))
+    sb = kn.ShardBatch(shards, d, batch, mode="owner")
+    assert sb.owner_plan["schedule_rows"] == 2
+    sb.train()
+    torch.cuda.synchronize()
+    losses = sb.train_losses()
+    for s in range(K):
+        u, i, r, P0, Q0, perms = host[s]
+        P, Q, _, _, ls = omf.mf_train(P0, Q0, u, i, r, perms, batch, epochs)
+        np.testing.assert_allclose(losses[s], ls, rtol=1e-5)
+        assert np.abs(shards[s].P.cpu().numpy() - P).max() < 1e-4
+        assert np.abs(shards[s].Q.cpu().numpy() - Q).max() < 1e-4

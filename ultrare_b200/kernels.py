@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import time
 from typing import List, Optional, Sequence
 
 import numpy as np
@@ -340,10 +341,9 @@ class ShardBatch:
         with torch.cuda.device(dev):
             check(L.ure_mf_owner_prepare(_ptr(self.table), len(shards), C.byref(self.hp), self.epochs, _ptr(self.ws),
                                          _stream()), "ure_mf_owner_prepare")
-        import time as _t
-        _t0 = _t.perf_counter()
+        t0 = time.perf_counter()
         max_rows, max_slots, max_spe, avail = self.ws[:16].view(torch.int32).tolist()   # the one sync of the set-up
-        self.plan_sync_ms = (_t.perf_counter() - _t0) * 1e3
+        self.plan_sync_ms = (time.perf_counter() - t0) * 1e3          # host wait for upload + sorts (diagnostics)
         cap_rows, cap_slots, spe_cap = max(1, max_rows), -(-max_slots // 16) * 16, max(1, max_spe)
         need = int(L.ure_mf_owner_smem_bytes(self.hp.d, cap_rows, cap_slots, spe_cap, 0))
         need_c = int(L.ure_mf_owner_smem_bytes(self.hp.d, cap_rows, cap_slots, spe_cap, 1))

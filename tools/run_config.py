@@ -23,11 +23,12 @@ CONFIGS = {
     "c3": (138_493, 26_744, 20_000_263, 64, 8, 30_000),
     "c4": (10_000_000, 1_000_000, 1_000_000_000, 128, 64, 30_000),
     "c4small": (1_250_000, 1_000_000, 125_000_000, 128, 8, 30_000),     # one GPU's share of c4 on an 8-GPU box
+    "c3gpu": (17_312, 26_744, 2_500_033, 64, 1, 30_000),                # one GPU's share of c3 on an 8-GPU box
 }
 ap = argparse.ArgumentParser()
 ap.add_argument("--config", default="c3", choices=list(CONFIGS))
 ap.add_argument("--epochs", type=int, default=1)
-ap.add_argument("--mode", default="auto", choices=["dense", "lazy", "auto"])
+ap.add_argument("--mode", default="auto", choices=["dense", "lazy", "owner", "auto"])
 ap.add_argument("--max-steps", type=int, default=0, help="train only this many global steps (0 = all)")
 a = ap.parse_args()
 
@@ -48,7 +49,7 @@ for j, s in enumerate(mine):
     rec = synth.device_interactions(rows_u, I, n_shard, dev, seed=synth.SEED + s)
     P, Q, scratch = views[j]
     shards.append(kn.ShardState(rec, P, Q, a.epochs, shard_id=s + 1, perm_seed=42, scratch=scratch))
-sb = kn.ShardBatch(shards, d, B, lazy=lazy)
+sb = kn.ShardBatch(shards, d, B, mode="owner" if a.mode == "owner" else ("lazy" if lazy else "dense"))
 torch.cuda.synchronize()
 setup_s = time.time() - t0
 steps = sb.total_steps if a.max_steps <= 0 else min(sb.total_steps, a.max_steps)
@@ -68,7 +69,7 @@ if rank == 0:
     peak = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"] \
         if os.path.exists("MEASURED_PEAKS.json") else 6650.0
     alg = inter * (12 + 16 * d)
-    print(json.dumps({"config": a.config, "n_gpus": world, "mode": "lazy" if lazy else "dense", "epochs": a.epochs,
+    print(json.dumps({"config": a.config, "n_gpus": world, "mode": sb.mode, "epochs": a.epochs,
                       "steps": steps, "shards_per_gpu": len(mine), "interactions": inter, "ms": ms,
                       "interactions_per_s": inter / ms * 1e3, "interactions_per_s_per_gpu": inter / ms * 1e3 / world,
                       "algorithmic_GBps_per_gpu": alg / ms / 1e6 / world, "frac_of_hbm_peak": alg / ms / 1e6 / world / peak,

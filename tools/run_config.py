@@ -75,3 +75,26 @@ if rank == 0:
                       "algorithmic_GBps_per_gpu": alg / ms / 1e6 / world, "frac_of_hbm_peak": alg / ms / 1e6 / world / peak,
                       "first_epoch_rmse_rank0": float(np.sqrt(sse[0] / max(1, sum(s.n for s in shards)))),
                       "setup_s": setup_s, "mem_GB_rank0": torch.cuda.max_memory_allocated() / 2**30}))
+
+if os.environ.get("URE_TRACE") and rank == 0 and sb.mode in ("dense", "owner"):
+    import ctypes as C
+    from ultrare_b200 import _lib
+    L = _lib.lib()
+    grid, nst = L.ure_mf_grid_size(), 40
+    trace = torch.zeros((nst, grid, 6), dtype=torch.int64, device=dev)
+    _lib.check(L.ure_mf_train_trace(C.c_void_p(sb.ws.data_ptr()), C.c_void_p(trace.data_ptr()), nst, None))
+    for s_ in shards:
+        s_.bufP.zero_(); s_.bufQ.zero_(); s_.sse.zero_()
+    sb.step = 0
+    sb.train(min(steps, 60))
+    torch.cuda.synchronize()
+    tr = trace.cpu().numpy().astype(np.float64)[5:]
+    dd = np.diff(tr, axis=2)
+    names = ["gradients", "overlap1", "wait1", "sweep", "arr2+fetch+wait2"] if sb.mode == "dense" else \
+        ["waves (warp 1)", "other warps", "row sweep", "arrive + next list", "barrier wait"]
+    print("per-phase SM cycles (median / p95 / max):")
+    for k_, nm in enumerate(names):
+        x = dd[:, :, k_].ravel()
+        print(f"  {nm:18s} {np.median(x):8.0f} {np.percentile(x, 95):8.0f} {x.max():8.0f}")
+    step_cyc = tr[1:, :, 0] - tr[:-1, :, 0]
+    print("step cycles median", np.median(step_cyc))

@@ -202,7 +202,8 @@ mf_train_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
   const long long n_threads = (long long)gridDim.x * g_threads;          // the group's threads grid-wide
   const long long gtid = (long long)blockIdx.x * g_threads + tid;
   const int n_warps = (int)(n_threads >> 5);
-  const int gwarp = (int)(gtid >> 5);
+  // chunk index of this warp: CTA-minor, so that a step with fewer chunks than warps still uses every SM
+  const int gwarp = warp * (int)gridDim.x + (int)blockIdx.x;
   const float wd = hp.weight_decay, mu = hp.momentum;
   unsigned bar_target = 0;
 

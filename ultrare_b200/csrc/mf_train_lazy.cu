@@ -94,7 +94,8 @@ mf_train_lazy_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hp
   const long long n_threads = (long long)gridDim.x * kThreads;
   const long long gtid = (long long)blockIdx.x * kThreads + tid;
   const int n_warps = (int)(n_threads >> 5);
-  const int gwarp = (int)(gtid >> 5);
+  // chunk index of this warp: CTA-minor, so that a step with fewer chunks than warps still uses every SM
+  const int gwarp = (tid >> 5) * (int)gridDim.x + (int)blockIdx.x;
   const float wd = hp.weight_decay, mu = hp.momentum, nlr = -hp.lr0;
   unsigned bar_target = 0;
   __syncthreads();

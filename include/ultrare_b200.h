@@ -96,7 +96,8 @@ typedef struct {
 } ure_mf_hparams_t;
 
 /* ure_mf_hparams_t::mode -- three schedules of the SAME arithmetic (baseTrain + dense optim.SGD):
- *   DENSE  gradients scattered with L2 vector atomics, then a dense sweep; two grid barriers per step.
+ *   DENSE  gradients scattered with L2 vector atomics (into the momentum arrays, pre-scaled), then a dense
+ *          sweep; two grid barriers per step.  gP / gQ are not touched.
  *   LAZY   closed-form catch-up of untouched rows (M^n table) instead of the dense sweep.
  *   OWNER  owner-computes: every CTA owns a slice of user rows and a slice of item rows of ONE shard
  *          (weights + momentum resident in shared memory), walks its own interactions of the batch from

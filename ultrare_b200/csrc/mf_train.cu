@@ -13,12 +13,14 @@
 // on the other CTAs is issued in between:
 //
 //   gradients(t)   gather P[u], Q[i] (16-byte L2 loads), shuffle dot product, loss,
-//                  red.global.add.v4.f32 scatter of both gradient rows
-//   ARRIVE 1       -- overlap: load this thread's sweep operands w, buf (unchanged by the
-//                     gradient phase); warp 1 builds the step tables of t+1
+//                  red.global.add.v4.f32 scatter of both gradient rows -- INTO THE MOMENTUM ARRAYS, which
+//                  between two sweeps hold pre = mu*buf + wd*w, so that pre + sum(g) is the new momentum:
+//                  no gradient arrays, the sweep moves 4 instead of 6 table-sized streams
+//   ARRIVE 1       -- overlap: load this thread's sweep operand w (unchanged by the gradient phase);
+//                     warp 1 builds the step tables of t+1
 //   WAIT 1
-//   sweep(t)       dense SGD on every row of every active shard: g += wd*w; buf = mu*buf+g;
-//                  w -= lr*buf; g = 0   (in place)
+//   sweep(t)       dense SGD on every row of every active shard: buf = pre + sum(g) (already in memory);
+//                  w -= lr*buf; pre' = mu*buf + wd*w  (the true buf at a shard's last step of the launch)
 //   ARRIVE 2       -- overlap: permutation index + record fetch of this warp's chunk of t+1
 //   WAIT 2
 //
@@ -54,6 +56,7 @@ struct StepTables {
   int start[KM];                     // first position of the batch inside the epoch
   float lr[KM];
   FeistelKeys keys[KM];
+  unsigned char last[KM];            // 1: the shard's last step of this launch (its momentum is stored as such)
 };
 
 // largest s with prefix[s] <= x  (prefix[0] = 0, prefix[nseg] = total > x)
@@ -170,7 +173,7 @@ mf_train_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
   const int gl = lane % G;
   for (int s = threadIdx.x; s < K; s += kThreads) {
     const ure_mf_shard_t sh = shards[s];
-    s_ptr[s] = ShardPtrs{sh.P, sh.Q, sh.gP, sh.gQ};
+    s_ptr[s] = ShardPtrs{sh.P, sh.Q, sh.bufP, sh.bufQ};      // gradients are reduced into the momentum arrays
     s_inter[s] = sh.inter; s_perm[s] = sh.perm;
     s_buf[2 * s] = sh.bufP; s_buf[2 * s + 1] = sh.bufQ;
     s_sse[s] = sh.sse;
@@ -209,7 +212,7 @@ mf_train_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
 
   // Step tables of the group for the step its shards' cursors point at, then advance the cursors.  Executed
   // by ONE warp (lanes = shards, 32 at a time, prefix carried): no block-wide synchronisation inside.
-  auto build_tables = [&](StepTables& tb) {
+  auto build_tables = [&](StepTables& tb, long long t_build) {
     int carry = 0;
     long long carry2 = 0;
     for (int base = 0; base < K; base += 32) {
@@ -229,6 +232,7 @@ mf_train_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
           for (int q = ep / hp.lr_step; q > 0; --q) lr *= (double)hp.lr_decay;
           tb.lr[s] = (float)lr;
           tb.keys[s].init(perm_key(s_seed[s], (uint32_t)s_shard_id[s], (uint32_t)ep));
+          tb.last[s] = (unsigned char)((bi + 1 == spe && ep + 1 == epochs) || t_build + 1 == step_end);
           if (bi + 1 == spe) { s_cur_epoch[s] = ep + 1; s_cur_batch[s] = 0; }
           else s_cur_batch[s] = bi + 1;
         } else {
@@ -280,11 +284,30 @@ mf_train_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
     trace[((t - step_begin) * gridDim.x + blockIdx.x) * 6 + (PH)] = clock64();
 
   // ---- prologue: tables and first-chunk records of the group's first step
-  if (warp == 0) build_tables(s_tab[0]);
+  if (warp == 0) build_tables(s_tab[0], step_begin);
   group_sync(bar_id, g_threads);
   int ps, pu_, pi_;
   float pr_;
   fetch(s_tab[0], gwarp, ps, pu_, pi_, pr_);
+  // the momentum arrays of the shards that train in this launch: buf -> pre = mu*buf + wd*w, then a grid barrier
+  // before the first gradients are reduced into them
+  if (step_begin < step_end) {
+    const StepTables& tb = s_tab[0];
+    const long long total4 = tb.row_prefix[2 * K];
+    for (long long x = gtid; x < total4; x += n_threads) {
+      const int seg = find_segment(tb.row_prefix, 2 * K, x);
+      const size_t off = (size_t)(x - tb.row_prefix[seg]) * 4;
+      const ShardPtrs tq = s_ptr[seg >> 1];
+      const float4 w = ld_cg_f4(((seg & 1) ? tq.Q : tq.P) + off);
+      float4 b = ld_cg_f4(s_buf[seg] + off);
+      b.x = fmaf(mu, b.x, __fmul_rn(wd, w.x)); b.y = fmaf(mu, b.y, __fmul_rn(wd, w.y));
+      b.z = fmaf(mu, b.z, __fmul_rn(wd, w.z)); b.w = fmaf(mu, b.w, __fmul_rn(wd, w.w));
+      st_cg_f4(s_buf[seg] + off, b);
+    }
+    barrier_arrive(counter, bar_id, g_threads, leader);
+    bar_target += gridDim.x;
+    barrier_wait(counter, bar_target, bar_id, g_threads, leader);
+  }
 
   int cur = 0;
   for (long long t = step_begin; t < step_end; ++t, cur ^= 1) {
@@ -338,15 +361,14 @@ mf_train_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
     const long long total4 = tb.row_prefix[2 * K];
     int seg0 = 0;
     size_t off0 = 0;
-    float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f), b0 = w0;
+    float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (gtid < total4) {
       seg0 = find_segment(tb.row_prefix, 2 * K, gtid);
       off0 = (size_t)(gtid - tb.row_prefix[seg0]) * 4;
       const ShardPtrs tp = s_ptr[seg0 >> 1];
       w0 = ld_cg_f4(((seg0 & 1) ? tp.Q : tp.P) + off0);
-      b0 = ld_cg_f4(s_buf[seg0] + off0);
     }
-    if (warp == (g_warps > 1 ? 1 : 0) && more) build_tables(s_tab[cur ^ 1]);
+    if (warp == (g_warps > 1 ? 1 : 0) && more) build_tables(s_tab[cur ^ 1], t + 1);
     URE_STAMP(2)
     barrier_wait(counter, bar_target, bar_id, g_threads, leader);   // -------- WAIT 1
     URE_STAMP(3)
@@ -355,29 +377,27 @@ mf_train_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
     for (long long x = gtid; x < total4; x += n_threads) {
       int seg;
       size_t off;
-      float4 w, b;
-      if (x == gtid) { seg = seg0; off = off0; w = w0; b = b0; }
+      float4 w;
+      if (x == gtid) { seg = seg0; off = off0; w = w0; }
       else {
         seg = find_segment(tb.row_prefix, 2 * K, x);
         off = (size_t)(x - tb.row_prefix[seg]) * 4;
         const ShardPtrs tq = s_ptr[seg >> 1];
         w = ld_cg_f4(((seg & 1) ? tq.Q : tq.P) + off);
-        b = ld_cg_f4(s_buf[seg] + off);
       }
       const ShardPtrs tp = s_ptr[seg >> 1];
       float* W = (seg & 1) ? tp.Q : tp.P;
-      float* Gr = (seg & 1) ? tp.gQ : tp.gP;
       float* Bf = s_buf[seg];
       const float nlr = -tb.lr[seg >> 1];
-      float4 g = ld_cg_f4(Gr + off);
-      // torch SGD: d_p = g + wd*w (fma); buf = buf*mu + d_p; w = w + (-lr)*buf (fma)
-      g.x = fmaf(wd, w.x, g.x); g.y = fmaf(wd, w.y, g.y); g.z = fmaf(wd, w.z, g.z); g.w = fmaf(wd, w.w, g.w);
-      b.x = __fadd_rn(__fmul_rn(b.x, mu), g.x); b.y = __fadd_rn(__fmul_rn(b.y, mu), g.y);
-      b.z = __fadd_rn(__fmul_rn(b.z, mu), g.z); b.w = __fadd_rn(__fmul_rn(b.w, mu), g.w);
+      // torch SGD: buf = buf*mu + (g + wd*w) -- here pre + sum(g), already reduced in memory; w = w + (-lr)*buf
+      float4 b = ld_cg_f4(Bf + off);
       w.x = fmaf(nlr, b.x, w.x); w.y = fmaf(nlr, b.y, w.y); w.z = fmaf(nlr, b.z, w.z); w.w = fmaf(nlr, b.w, w.w);
       st_cg_f4(W + off, w);
-      st_cg_f4(Bf + off, b);
-      st_cg_f4(Gr + off, make_float4(0.f, 0.f, 0.f, 0.f));
+      if (!tb.last[seg >> 1]) {             // next step's pre; the true momentum at the shard's last step
+        b.x = fmaf(mu, b.x, __fmul_rn(wd, w.x)); b.y = fmaf(mu, b.y, __fmul_rn(wd, w.y));
+        b.z = fmaf(mu, b.z, __fmul_rn(wd, w.z)); b.w = fmaf(mu, b.w, __fmul_rn(wd, w.w));
+        st_cg_f4(Bf + off, b);
+      }
     }
     URE_STAMP(4)
     barrier_arrive(counter, bar_id, g_threads, leader);     // ---------------- ARRIVE 2

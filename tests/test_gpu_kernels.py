@@ -470,3 +470,24 @@ def test_mf_owner_schedule_windows_vs_oracle(cuda_dev, monkeypatch):
         np.testing.assert_allclose(losses[s], ls, rtol=1e-5)
         assert np.abs(shards[s].P.cpu().numpy() - P).max() < 1e-4
         assert np.abs(shards[s].Q.cpu().numpy() - Q).max() < 1e-4
+
+
+@pytest.mark.parametrize("n,d,k", [(5003, 64, 8), (7001, 128, 16), (4099, 32, 32), (3000, 64, 40), (2000, 8, 5)])
+def test_assign_centroids_register_and_shared_paths(cuda_dev, n, d, k):
+    """ure_assign_centroids: label = argmax_j (g_j - M_ij) (first max wins), per-label counts and fp64 sums of X,
+    on the register path (k <= 32, k*ceil(d/32) <= 64) and the shared-memory path."""
+    torch = _torch()
+    from ultrare_b200 import kernels as kn
+    rng = np.random.default_rng(n + d + k)
+    X = rng.standard_normal((n, d), dtype=np.float32)
+    Cc = X[rng.choice(n, k, replace=False)]
+    Xd = torch.tensor(X, device=cuda_dev)
+    M = kn.cost_matrix(Xd, torch.tensor(Cc, device=cuda_dev))
+    g = torch.tensor(rng.standard_normal(k).astype(np.float32), device=cuda_dev)
+    label, sums, cnt = kn.assign_centroids(M, k, g, Xd)
+    label = label.cpu().numpy()
+    ref = np.argmax(g.cpu().numpy()[None, :] - M.cpu().numpy()[:, :k], axis=1)
+    assert np.array_equal(label, ref)
+    assert np.array_equal(cnt.cpu().numpy(), np.bincount(ref, minlength=k))
+    ref_sum = np.stack([X[ref == j].astype(np.float64).sum(0) for j in range(k)])
+    assert np.abs(sums.cpu().numpy() - ref_sum).max() < 2e-3

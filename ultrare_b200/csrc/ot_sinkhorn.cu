@@ -476,6 +476,110 @@ assign_centroid_kernel(const float* __restrict__ M, long long n, int k, int kpad
   }
 }
 
+// Small k (<= 32): the centroid sums stay in REGISTERS.  A lane finds the label of its own row, then the warp
+// walks its 32 rows: the row of X is read coalesced (lane t holds columns t, t+32, ...), and since the label is
+// warp-uniform the add goes to the accumulator registers of that label under a uniform predicate -- no shared-
+// memory read-modify-write chain per row (the limiter of assign_centroid_kernel: 0.4 TB/s at n = 1 M).
+// KT >= k accumulator sets of DT = ceil(d/32) floats per lane; folded over the CTA's warps in shared memory,
+// then one fp64 atomic per (label, column) and CTA.
+template <int KT, int DT>
+__global__ void __launch_bounds__(256)
+assign_centroid_reg_kernel(const float* __restrict__ M, long long n, int k, int kpad, const float* __restrict__ g,
+                           const float* __restrict__ X, int d, int32_t* __restrict__ label, double* __restrict__ sum,
+                           long long* __restrict__ cnt) {
+  constexpr int NWARP = 8;
+  __shared__ float g_sh[32];
+  constexpr int FA = (KT * DT < 16) ? KT * DT : 16;   // accumulators folded per round (16 KB of shared memory)
+  __shared__ float fold_sh[NWARP][FA * 32];
+  __shared__ int cnt_sh[NWARP][32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < 32) g_sh[tid] = tid < k ? g[tid] : -INFINITY;
+  __syncthreads();
+  float acc[KT][DT];
+#pragma unroll
+  for (int j = 0; j < KT; ++j)
+#pragma unroll
+    for (int t = 0; t < DT; ++t) acc[j][t] = 0.f;
+  int my_cnt = 0;                                     // rows with label == lane
+  const long long per = (n + gridDim.x - 1) / gridDim.x;
+  const long long r0 = per * blockIdx.x < n ? per * blockIdx.x : n;
+  const long long r1 = r0 + per < n ? r0 + per : n;
+  for (long long row0 = r0 + (long long)warp * 32; row0 < r1; row0 += (long long)NWARP * 32) {
+    const long long row = row0 + lane;
+    int arg = -1;
+    if (row < r1) {
+      float best = -INFINITY;
+      arg = 0;
+      const float4* mr = reinterpret_cast<const float4*>(M + row * kpad);
+      for (int j4 = 0; j4 * 4 < k; ++j4) {
+        const float4 m = __ldg(mr + j4);
+        const float v[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int j = j4 * 4 + q;
+          const float t = g_sh[j & 31] - v[q];
+          if (j < k && t > best) { best = t; arg = j; }       // strict '>' keeps the first maximum
+        }
+      }
+      label[row] = arg;
+    }
+#pragma unroll
+    for (int j = 0; j < KT; ++j) {
+      const int c = __popc(__ballot_sync(0xffffffffu, arg == j));
+      if (lane == j) my_cnt += c;
+    }
+    if (X) {
+      const int n_valid = (int)((r1 - row0) < 32 ? (r1 - row0) : 32);
+      for (int rb = 0; rb < n_valid; rb += 4) {             // 4 rows of X in flight
+        float x[4][DT];
+        int lab[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          lab[u] = __shfl_sync(0xffffffffu, arg, (rb + u) & 31);
+          const bool ok = rb + u < n_valid;
+          if (!ok) lab[u] = -1;
+          const float* xr = X + (row0 + rb + (ok ? u : 0)) * d;
+#pragma unroll
+          for (int t = 0; t < DT; ++t) x[u][t] = (ok && lane + 32 * t < d) ? __ldg(xr + lane + 32 * t) : 0.f;
+        }
+        // acc[lab] += x as a mask-multiply over all labels: a predicated add would be turned into an indexed
+        // (local-memory) access by the compiler
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int j = 0; j < KT; ++j) {
+            const float mj = lab[u] == j ? 1.f : 0.f;
+#pragma unroll
+            for (int t = 0; t < DT; ++t) acc[j][t] = fmaf(mj, x[u][t], acc[j][t]);
+          }
+      }
+    }
+  }
+  // fold the warps, FA accumulators per round
+  cnt_sh[warp][lane] = my_cnt;
+#pragma unroll
+  for (int a0 = 0; a0 < KT * DT; a0 += FA) {
+#pragma unroll
+    for (int a = 0; a < FA; ++a) fold_sh[warp][a * 32 + lane] = acc[(a0 + a) / DT][(a0 + a) % DT];
+    __syncthreads();
+    if (X)
+      for (int x = tid; x < FA * 32; x += blockDim.x) {
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < NWARP; ++w) v += fold_sh[w][x];
+        const int ai = a0 + x / 32, j = ai / DT, col = (ai % DT) * 32 + (x & 31);
+        if (j < k && col < d && v != 0.f) atomicAdd(sum + (size_t)j * d + col, (double)v);
+      }
+    __syncthreads();
+  }
+  if (tid < k) {
+    int v = 0;
+#pragma unroll
+    for (int w = 0; w < NWARP; ++w) v += cnt_sh[w][tid];
+    if (v) atomicAdd(reinterpret_cast<unsigned long long*>(cnt + tid), (unsigned long long)v);
+  }
+}
+
 #define URE_KPAD_SWITCH(kpad, CALL)                    \
   switch (kpad) {                                      \
     case 16: { constexpr int KP = 16; CALL; } break;   \
@@ -625,6 +729,28 @@ extern "C" int ure_assign_centroids(const float* d_M, int64_t n, int k, int kpad
   if (int rc = check_mk(d_M, n, k, kpad, "ure_assign_centroids")) return rc;
   URE_REQUIRE(d_g && d_label && d_cnt && (!d_X || (d_sum && d > 0)), URE_EINVAL, "ure_assign_centroids: bad argument");
   const int dd = d_X ? d : 0;
+  {
+    // register path: k <= 32 and at most 64 accumulators per lane
+    const int kt = k <= 8 ? 8 : k <= 16 ? 16 : k <= 32 ? 32 : 0;
+    const int dt = dd <= 32 ? 1 : dd <= 64 ? 2 : dd <= 128 ? 4 : 0;
+    if (kt && dt && kt * dt <= 64) {
+      long long blocks = (n + 2047) / 2048;
+      const long long cap = (long long)num_sms() * 2;       // one wave of resident CTAs: the fp64 atomics of the
+      if (blocks > cap) blocks = cap;                         // final fold (k*d addresses) scale with the CTA count
+      auto st = static_cast<cudaStream_t>(stream);
+      auto* cntp = reinterpret_cast<long long*>(d_cnt);
+#define URE_ASSIGN_REG(KT_, DT_)                                                                              \
+  if (kt == KT_ && dt == DT_) {                                                                             \
+    assign_centroid_reg_kernel<KT_, DT_><<<(unsigned)blocks, 256, 0, st>>>(d_M, n, k, kpad, d_g, d_X, dd, d_label, \
+                                                                          d_sum, cntp);                      \
+    URE_CUDA(cudaGetLastError());                                                                            \
+    return 0;                                                                                                \
+  }
+      URE_ASSIGN_REG(8, 1) URE_ASSIGN_REG(8, 2) URE_ASSIGN_REG(8, 4) URE_ASSIGN_REG(16, 1) URE_ASSIGN_REG(16, 2)
+      URE_ASSIGN_REG(16, 4) URE_ASSIGN_REG(32, 1) URE_ASSIGN_REG(32, 2)
+#undef URE_ASSIGN_REG
+    }
+  }
   const size_t one = ((size_t)k * dd + k) * sizeof(float);
   URE_REQUIRE(one <= 200 * 1024, URE_EUNSUPPORTED, "ure_assign_centroids: k*d=%d too large for shared memory", k * d);
   int copies = (int)((96 * 1024) / one);            // <= 96 KB: two CTAs per SM stay resident

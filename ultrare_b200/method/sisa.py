@@ -131,8 +131,12 @@ class Sisa(Scratch):
             part = torch.zeros(len(ds), dtype=torch.float32, device=self.device)
         self.dist.all_reduce(part)
         score, sse = kn.score_finalize(part, inter, float(self.n_group))
+        # ranking metrics: every rank takes its block of the user segments, the three sums are all-reduced
         order, seg = ds.segments(self.device)
-        out = kn.rank_metrics(inter, score, seg, order)
+        lo, hi = self.dist.row_block(seg.shape[0] - 1)
+        out = kn.rank_metrics(inter, score, seg[lo:hi + 1], order) if hi > lo else \
+            torch.zeros(3, dtype=torch.float64, device=self.device)
+        self.dist.all_reduce(out)
         vals = torch.cat([sse, out]).cpu().numpy()
         users = max(vals[3], 1.0)
         return float(np.sqrt(vals[0] / len(ds))), float(vals[1] / users), float(vals[2] / users)

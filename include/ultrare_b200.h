@@ -64,6 +64,8 @@ typedef struct {
                             /*    ure_mf_owner_prepare; entries 0..n_user valid afterwards)                 */
   int32_t* off_i;           /* owner mode only: [n_item + 2]                                                */
   int32_t* perm_inv;        /* owner mode with explicit `perm`: [n_epochs_total][n] inverse visiting orders */
+  ure_inter_t* tmp_u;       /* owner mode only: [n] scratch of the radix sort                                */
+  ure_inter_t* tmp_i;       /* owner mode only: [n] scratch of the radix sort                                */
   int32_t n;                /* interactions in the shard                                   */
   int32_t n_user;           /* rows of P                                                   */
   int32_t n_item;           /* rows of Q                                                   */
@@ -128,14 +130,16 @@ int ure_mf_train(const ure_mf_shard_t* d_shards, int n_shards, const ure_mf_hpar
                  void* d_workspace, void* stream);
 
 /* Owner mode set-up, once per shard table (asynchronous, no host sync): builds inter_u / inter_i /
- * off_u / off_i (counting sort of the records by user and by item) and perm_inv for shards with an
- * explicit perm, then plans the CTA ownership and writes into the first 16 bytes of d_workspace
+ * off_u / off_i (row histogram + scan; STABLE radix sort of the records by user and by item, so the whole
+ * training is reproducible bit for bit) and perm_inv for shards with an explicit perm, then plans the CTA ownership and writes into the first 16 bytes of d_workspace
  * int32 {max owned rows of a CTA, max owned interactions of a CTA, max steps per epoch of a shard,
  * dynamic shared-memory bytes available}: the caller reads them back once, fills hparams.owner_cap_rows /
  * owner_cap_slots / owner_spe_cap / owner_flags, allocates the schedule tables, and must not start mode OWNER
  * when ure_mf_owner_smem_bytes exceeds what is available (ure_mf_train refuses it loudly as well). */
+int64_t ure_mf_owner_radix_bytes(int n_shards);     /* size of d_radix_hist below */
 int ure_mf_owner_prepare(const ure_mf_shard_t* d_shards, int n_shards, const ure_mf_hparams_t* h_hp,
-                         int epochs, void* d_workspace, void* stream);
+                         int epochs, int max_rows /* largest n_user / n_item of a shard */,
+                         int32_t* d_radix_hist, void* d_workspace, void* stream);
 
 /* Dynamic shared memory per CTA the OWNER schedule needs for these capacities (training kernel and
  * schedule pre-pass, whichever is larger). */

@@ -374,6 +374,7 @@ def test_mf_owner_prepare_sorts_and_inverts(cuda_dev):
         assert np.array_equal(rec[:, 2].view(np.float32), r[j])
         col = rec[:, 0] if key is u else rec[:, 1]
         assert np.all(np.diff(col) >= 0)
+        assert np.array_equal(j, np.argsort(key, kind="stable"))       # stable: record order inside every row
     inv = st.perm_inv.cpu().numpy()
     for e in range(epochs):
         assert np.array_equal(inv[e][perm[e]], np.arange(n))
@@ -491,3 +492,19 @@ def test_assign_centroids_register_and_shared_paths(cuda_dev, n, d, k):
     assert np.array_equal(cnt.cpu().numpy(), np.bincount(ref, minlength=k))
     ref_sum = np.stack([X[ref == j].astype(np.float64).sum(0) for j in range(k)])
     assert np.abs(sums.cpu().numpy() - ref_sum).max() < 2e-3
+
+
+def test_mf_owner_training_is_bit_reproducible(toy, cuda_dev):
+    """Owner schedule: no atomics on the gradient path and a stable sort in the set-up, so two trainings of the same
+    shards give bit-identical tables (the dense schedule's L2 atomics do not)."""
+    torch = _torch()
+    from ultrare_b200 import kernels as kn
+    outs = []
+    for rep in range(2):
+        shards, _ = _shard(2, toy, cuda_dev, 2, 3000, False, [3, 4])
+        sb = kn.ShardBatch(shards, toy["k"], 3000, mode="owner")
+        sb.train()
+        torch.cuda.synchronize()
+        outs.append([t.cpu().numpy().copy() for sh in shards for t in (sh.P, sh.Q, sh.bufP, sh.bufQ)])
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b)

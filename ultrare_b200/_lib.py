@@ -23,6 +23,7 @@ class MFShard(C.Structure):
     _fields_ = [("inter", _p), ("perm", _p), ("P", _p), ("Q", _p), ("bufP", _p), ("bufQ", _p),
                 ("gP", _p), ("gQ", _p), ("sse", _p), ("lastP", _p), ("lastQ", _p), ("touched", _p),
                 ("inter_u", _p), ("inter_i", _p), ("off_u", _p), ("off_i", _p), ("perm_inv", _p),
+                ("tmp_u", _p), ("tmp_i", _p),
                 ("n", _i32), ("n_user", _i32), ("n_item", _i32), ("shard_id", _i32),
                 ("perm_seed", C.c_uint32), ("group", _i32)]
 
@@ -38,7 +39,7 @@ class MFHParams(C.Structure):
 
 MF_DENSE, MF_LAZY, MF_OWNER = 0, 1, 2
 
-assert C.sizeof(MFShard) == 160 and C.sizeof(MFHParams) == 96
+assert C.sizeof(MFShard) == 176 and C.sizeof(MFHParams) == 96
 
 # name -> (restype, argtypes); every symbol include/ultrare_b200.h declares
 SIGNATURES = {
@@ -46,7 +47,8 @@ SIGNATURES = {
     "ure_abi_version": (C.c_int, []),
     "ure_mf_train_workspace_bytes": (_i64, []),
     "ure_mf_train": (C.c_int, [_p, C.c_int, C.POINTER(MFHParams), C.c_int, _i64, _i64, C.c_int, _p, _p]),
-    "ure_mf_owner_prepare": (C.c_int, [_p, C.c_int, C.POINTER(MFHParams), C.c_int, _p, _p]),
+    "ure_mf_owner_radix_bytes": (_i64, [C.c_int]),
+    "ure_mf_owner_prepare": (C.c_int, [_p, C.c_int, C.POINTER(MFHParams), C.c_int, C.c_int, _p, _p, _p]),
     "ure_mf_owner_smem_bytes": (_i64, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "ure_mf_owner_schedule": (C.c_int, [_p, C.c_int, C.POINTER(MFHParams), C.c_int, _i64, _p]),
     "ure_mf_train_trace": (C.c_int, [_p, _p, C.c_int, _p]),

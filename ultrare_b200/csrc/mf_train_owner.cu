@@ -159,17 +159,21 @@ __global__ void plan_kernel(const ure_mf_shard_t* shards, int K, int batch, Owne
   }
 }
 
-// ---------------------------------------------------------------- set-up: counting sort of the records
+// ---------------------------------------------------------------- set-up: the records sorted by user / by item
+// Row offsets: histogram + scan.  Records: a STABLE least-significant-digit radix sort on the row number (8-bit
+// digits), so the records of a row stay in record order and the whole training is reproducible bit for bit
+// (the gradient of a row is summed in slot order).  Pass p of side (user | item) reads the shard's records
+// (p = 0) or the previous pass's output and writes the other of {tmp, final}; the last pass lands in final.
 __global__ void csr_count_kernel(const ure_mf_shard_t* shards) {
   const ure_mf_shard_t& sh = shards[blockIdx.y];
   for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < sh.n; j += (long long)gridDim.x * blockDim.x) {
     const int4 r = ld_stream_i4(sh.inter + j);
-    atomicAdd(sh.off_u + r.x + 2, 1);
-    atomicAdd(sh.off_i + r.y + 2, 1);
+    atomicAdd(sh.off_u + r.x + 1, 1);
+    atomicAdd(sh.off_i + r.y + 1, 1);
   }
 }
 
-// in-place inclusive scan of off[0 .. rows+2): one CTA per (shard, side)
+// in-place inclusive scan of off[0 .. rows+2): one CTA per (shard, side); off[r] becomes the first slot of row r
 __global__ void csr_scan_kernel(const ure_mf_shard_t* shards) {
   const ure_mf_shard_t& sh = shards[blockIdx.x >> 1];
   int32_t* off = (blockIdx.x & 1) ? sh.off_i : sh.off_u;
@@ -207,16 +211,134 @@ __global__ void csr_scan_kernel(const ure_mf_shard_t* shards) {
   }
 }
 
-// after the scan off[r+1] = start of row r: used as the fill cursor, it ends as the start of row r+1
-__global__ void csr_fill_kernel(const ure_mf_shard_t* shards) {
-  const ure_mf_shard_t& sh = shards[blockIdx.y];
-  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < sh.n; j += (long long)gridDim.x * blockDim.x) {
-    int4 r = ld_stream_i4(sh.inter + j);
-    r.w = (int)j;
-    const int pu = atomicAdd(sh.off_u + r.x + 1, 1);
-    const int pi = atomicAdd(sh.off_i + r.y + 1, 1);
-    reinterpret_cast<int4*>(sh.inter_u)[pu] = r;
-    reinterpret_cast<int4*>(sh.inter_i)[pi] = r;
+constexpr int kRadixBlocks = 96;          // CTAs per (shard, side): each owns a contiguous tile of the records
+constexpr int kRadixThreads = 512;
+constexpr int kRadixWarps = kRadixThreads / 32;
+
+struct RadixView {                        // what pass `pass` of grid row y = 2*shard + side works on
+  const int4* src;
+  int4* dst;
+  long long n, t0, t1;                    // the CTA's tile [t0, t1)
+  bool item, first;
+  __device__ RadixView(const ure_mf_shard_t* shards, int pass, int npass) {
+    const ure_mf_shard_t& sh = shards[blockIdx.y >> 1];
+    item = blockIdx.y & 1;
+    first = pass == 0;
+    int4* fin = reinterpret_cast<int4*>(item ? sh.inter_i : sh.inter_u);
+    int4* tmp = reinterpret_cast<int4*>(item ? sh.tmp_i : sh.tmp_u);
+    dst = ((npass - 1 - pass) & 1) ? tmp : fin;
+    src = first ? reinterpret_cast<const int4*>(sh.inter) : (((npass - pass) & 1) ? tmp : fin);
+    n = sh.n;
+    const long long tile = (n + gridDim.x - 1) / gridDim.x;
+    t0 = min(n, tile * blockIdx.x);
+    t1 = min(n, t0 + tile);
+  }
+  __device__ __forceinline__ int digit(const int4& r, int pass) const { return ((item ? r.y : r.x) >> (8 * pass)) & 255; }
+};
+
+// hist [grid.y][grid.x][256]: records of the CTA's tile per digit value
+__global__ void __launch_bounds__(kRadixThreads)
+radix_hist_kernel(const ure_mf_shard_t* shards, int pass, int npass, int* __restrict__ hist) {
+  __shared__ int s_h[256];
+  const RadixView v(shards, pass, npass);
+  for (int x = threadIdx.x; x < 256; x += blockDim.x) s_h[x] = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  for (long long j0 = v.t0 + (threadIdx.x & ~31); j0 < v.t1; j0 += blockDim.x) {      // warp-uniform trip count
+    const long long j = j0 + lane;
+    const bool in = j < v.t1;
+    const int dg = in ? v.digit(__ldg(v.src + j), pass) : 0;
+    const unsigned act = __ballot_sync(0xffffffffu, in);
+    if (in) {
+      const unsigned same = __match_any_sync(act, dg);
+      if (lane == __ffs(same) - 1) atomicAdd(&s_h[dg], __popc(same));
+    }
+  }
+  __syncthreads();
+  for (int x = threadIdx.x; x < 256; x += blockDim.x) hist[((long long)blockIdx.y * gridDim.x + blockIdx.x) * 256 + x] = s_h[x];
+}
+
+// per grid row y: exclusive scan of hist in (digit, CTA) order, in place; one CTA of 256 threads per y
+__global__ void __launch_bounds__(256)
+radix_scan_kernel(int* __restrict__ hist, int n_blocks) {
+  __shared__ int s_tot[256];
+  int* h = hist + (long long)blockIdx.x * n_blocks * 256 + threadIdx.x;      // thread = digit: coalesced per CTA row
+  int tot = 0;
+  for (int b = 0; b < n_blocks; ++b) tot += h[b * 256];
+  s_tot[threadIdx.x] = tot;
+  __syncthreads();
+  if (threadIdx.x < 32) {                 // exclusive scan of the 256 digit totals by one warp, 8 per lane
+    int loc[8], sum = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { loc[i] = sum; sum += s_tot[threadIdx.x * 8 + i]; }
+    int inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int a = __shfl_up_sync(0xffffffffu, inc, o);
+      if ((int)threadIdx.x >= o) inc += a;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s_tot[threadIdx.x * 8 + i] = inc - sum + loc[i];
+  }
+  __syncthreads();
+  int run = s_tot[threadIdx.x];
+  for (int b = 0; b < n_blocks; ++b) {
+    const int t = h[b * 256];
+    h[b * 256] = run;
+    run += t;
+  }
+}
+
+// stable scatter of the CTA's tile: every warp owns a contiguous range; per-warp digit counts -> per-warp cursors
+// (from the CTA's global offsets); inside a warp __match_any ranks the lanes of one digit in lane (= record) order
+__global__ void __launch_bounds__(kRadixThreads)
+radix_scatter_kernel(const ure_mf_shard_t* shards, int pass, int npass, const int* __restrict__ hist) {
+  __shared__ int s_wh[kRadixWarps][256];
+  const RadixView v(shards, pass, npass);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned lt = (1u << lane) - 1u;
+  for (int x = threadIdx.x; x < kRadixWarps * 256; x += blockDim.x) (&s_wh[0][0])[x] = 0;
+  __syncthreads();
+  const long long per = ((v.t1 - v.t0) + kRadixWarps - 1) / kRadixWarps;
+  const long long w0 = min(v.t1, v.t0 + per * warp), w1 = min(v.t1, w0 + per);
+  for (long long j0 = w0; j0 < w1; j0 += 32) {
+    const long long j = j0 + lane;
+    const bool in = j < w1;
+    const int dg = in ? v.digit(__ldg(v.src + j), pass) : 0;
+    const unsigned act = __ballot_sync(0xffffffffu, in);
+    if (in) {
+      const unsigned same = __match_any_sync(act, dg);
+      if (lane == __ffs(same) - 1) s_wh[warp][dg] += __popc(same);        // the warp's own counters
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (threadIdx.x < 256) {
+    int run = hist[((long long)blockIdx.y * gridDim.x + blockIdx.x) * 256 + threadIdx.x];
+    for (int w = 0; w < kRadixWarps; ++w) {
+      const int t = s_wh[w][threadIdx.x];
+      s_wh[w][threadIdx.x] = run;
+      run += t;
+    }
+  }
+  __syncthreads();
+  for (long long j0 = w0; j0 < w1; j0 += 32) {
+    const long long j = j0 + lane;
+    const bool in = j < w1;
+    int4 r = make_int4(0, 0, 0, 0);
+    if (in) {
+      r = __ldg(v.src + j);
+      if (v.first) r.w = (int)j;          // the record's index in the shard's own order
+    }
+    const int dg = v.digit(r, pass);
+    const unsigned act = __ballot_sync(0xffffffffu, in);
+    if (in) {
+      const unsigned same = __match_any_sync(act, dg);
+      v.dst[s_wh[warp][dg] + __popc(same & lt)] = r;
+      __syncwarp(act);
+      if (lane == __ffs(same) - 1) s_wh[warp][dg] += __popc(same);
+    }
+    __syncwarp();
   }
 }
 
@@ -879,18 +1001,27 @@ extern "C" int ure_mf_owner_schedule(const ure_mf_shard_t* d_shards, int n_shard
   return 0;
 }
 
+extern "C" int64_t ure_mf_owner_radix_bytes(int n_shards) { return 2ll * n_shards * 256 * ure::kRadixBlocks * 4; }
+
 extern "C" int ure_mf_owner_prepare(const ure_mf_shard_t* d_shards, int n_shards, const ure_mf_hparams_t* h_hp,
-                                    int epochs, void* d_workspace, void* stream) {
+                                    int epochs, int max_rows, int32_t* d_radix_hist, void* d_workspace, void* stream) {
   using namespace ure;
   URE_REQUIRE(d_shards && h_hp && d_workspace, URE_EINVAL, "ure_mf_owner_prepare: null argument");
   URE_REQUIRE(n_shards >= 1 && n_shards <= num_sms(), URE_EUNSUPPORTED,
               "ure_mf_owner_prepare: n_shards=%d outside [1,%d] (one CTA per shard at least)", n_shards, num_sms());
   auto st = static_cast<cudaStream_t>(stream);
   auto* ws = static_cast<OwnerWs*>(d_workspace);
+  URE_REQUIRE(d_radix_hist && max_rows >= 1, URE_EINVAL, "ure_mf_owner_prepare: radix scratch / max_rows missing");
   const int blocks = 2 * num_sms();
   csr_count_kernel<<<dim3(blocks, n_shards), 256, 0, st>>>(d_shards);
   csr_scan_kernel<<<2 * n_shards, 1024, 0, st>>>(d_shards);
-  csr_fill_kernel<<<dim3(blocks, n_shards), 256, 0, st>>>(d_shards);
+  int npass = 1;
+  while (npass < 4 && (max_rows - 1) >> (8 * npass)) ++npass;
+  for (int pass = 0; pass < npass; ++pass) {
+    radix_hist_kernel<<<dim3(kRadixBlocks, 2 * n_shards), kRadixThreads, 0, st>>>(d_shards, pass, npass, d_radix_hist);
+    radix_scan_kernel<<<2 * n_shards, 256, 0, st>>>(d_radix_hist, kRadixBlocks);
+    radix_scatter_kernel<<<dim3(kRadixBlocks, 2 * n_shards), kRadixThreads, 0, st>>>(d_shards, pass, npass, d_radix_hist);
+  }
   perm_inverse_kernel<<<dim3(blocks, n_shards), 256, 0, st>>>(d_shards, epochs);
   int avail = 0;
   if (int rc = max_dyn_smem(&avail)) return rc;

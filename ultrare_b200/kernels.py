@@ -235,6 +235,7 @@ class ShardState:
         self.group = 0
         self.lastP = self.lastQ = self.touched = None          # lazy mode state (ShardBatch(mode="lazy"))
         self.inter_u = self.inter_i = self.off_u = self.off_i = self.perm_inv = None   # owner mode state
+        self.tmp_u = self.tmp_i = None
 
     def descriptor(self) -> MFShard:
         d = MFShard()
@@ -245,7 +246,7 @@ class ShardState:
         d.lastP = self.lastP.data_ptr() if self.lastP is not None else None
         d.lastQ = self.lastQ.data_ptr() if self.lastQ is not None else None
         d.touched = self.touched.data_ptr() if self.touched is not None else None
-        for name in ("inter_u", "inter_i", "off_u", "off_i", "perm_inv"):
+        for name in ("inter_u", "inter_i", "off_u", "off_i", "perm_inv", "tmp_u", "tmp_i"):
             t = getattr(self, name)
             setattr(d, name, t.data_ptr() if t is not None else None)
         d.n, d.n_user, d.n_item = self.n, self.P.shape[0], self.Q.shape[0]
@@ -325,22 +326,25 @@ class ShardBatch:
                 raise RuntimeError("owner mode needs at most one shard per SM")
             return "dense"
         n_tot = sum(s.n for s in shards)
-        rec = torch.empty((2, max(1, n_tot), 4), dtype=torch.int32, device=dev)
+        rec = torch.empty((4, max(1, n_tot), 4), dtype=torch.int32, device=dev)      # sorted copies + radix scratch
         n_off = sum(s.P.shape[0] + s.Q.shape[0] + 4 for s in shards)
         off = torch.zeros(n_off, dtype=torch.int32, device=dev)
         o = r = 0
         for s in shards:
             s.inter_u, s.inter_i = rec[0, r:r + s.n], rec[1, r:r + s.n]
+            s.tmp_u, s.tmp_i = rec[2, r:r + s.n], rec[3, r:r + s.n]
             r += s.n
             nu, ni = s.P.shape[0] + 2, s.Q.shape[0] + 2
             s.off_u, s.off_i = off[o:o + nu], off[o + nu:o + nu + ni]
             o += nu + ni
             s.perm_inv = torch.empty_like(s.perm) if s.perm is not None else None
-        self._owner_keep = (rec, off)
+        radix = torch.empty(int(L.ure_mf_owner_radix_bytes(len(shards))) // 4, dtype=torch.int32, device=dev)
+        self._owner_keep = (rec, off, radix)
         self._upload_table()
+        max_rows = max(max(s.P.shape[0], s.Q.shape[0]) for s in shards)
         with torch.cuda.device(dev):
-            check(L.ure_mf_owner_prepare(_ptr(self.table), len(shards), C.byref(self.hp), self.epochs, _ptr(self.ws),
-                                         _stream()), "ure_mf_owner_prepare")
+            check(L.ure_mf_owner_prepare(_ptr(self.table), len(shards), C.byref(self.hp), self.epochs, int(max_rows),
+                                         _ptr(radix), _ptr(self.ws), _stream()), "ure_mf_owner_prepare")
         t0 = time.perf_counter()
         max_rows, max_slots, max_spe, avail = self.ws[:16].view(torch.int32).tolist()   # the one sync of the set-up
         self.plan_sync_ms = (time.perf_counter() - t0) * 1e3          # host wait for upload + sorts (diagnostics)
@@ -356,7 +360,7 @@ class ShardBatch:
             if required:
                 raise RuntimeError(f"owner mode does not fit this problem: {self.owner_plan}")
             for s in shards:
-                s.inter_u = s.inter_i = s.off_u = s.off_i = s.perm_inv = None
+                s.inter_u = s.inter_i = s.off_u = s.off_i = s.perm_inv = s.tmp_u = s.tmp_i = None
             self._owner_keep = None
             return "dense"
         # schedule tables (ure_mf_owner_schedule): as many epochs per shard as OWNER_SCHED_BYTES allows, >= 2

@@ -236,3 +236,28 @@ def test_instance_run_full_then_group_end_to_end(toy, cuda_dev, tmp_path, monkey
     # routing against the brute-force restatement of sisa.py:76-81
     sisa = ins.last_sisa
     assert sisa.retrain_gid == osisa.route_deletions(sisa.group_index, p3.del_user)
+
+
+def test_instance_run_group_uniform_delper5(toy, cuda_dev, tmp_path, monkeypatch):
+    """The other branches reachable from the CLI: group_type='uniform' (runGroup's default,
+    config.py:190, groups of read.py:21-33) and --delper 5: artefacts, routing, and the deletion set of Appendix C."""
+    import ultrare_b200.config as cfg
+    import ultrare_b200.group as grp
+    from ultrare_b200 import synth
+    data, save = str(tmp_path / "data"), str(tmp_path / "result")
+    for mod in (cfg, grp):
+        monkeypatch.setattr(mod, "DATA_DIR", data)
+        monkeypatch.setattr(mod, "SAVE_DIR", save)
+    synth.ensure_dataset("toy")
+    p = cfg.InsParam("toy", 2, 1, [32], 4, 5, "rand")
+    assert np.array_equal(p.del_user, osisa.deletion_set(N_USER, 5)) and len(p.del_user) == int(0.05 * N_USER)
+    ins = cfg.Instance(p)
+    ins.runGroup(is_save=True, learn_type='sisa', group_type='uniform', n_group=4, verbose=0)
+    gdir = save + "/5/rand/toy_g4"
+    for sub in ("MF_uniform_sisa_learn", "MF_uniform_sisa_unlearn"):
+        l0 = np.load(f"{gdir}/{sub}/log0.npy", allow_pickle=True).item()
+        assert set(l0) == {'total_rmse', 'total_ndcg', 'total_hr'} and np.isfinite(l0['total_rmse'])
+    sisa = ins.last_sisa
+    groups = osisa.uniform_groups(N_USER, 4)
+    assert sorted(map(sorted, sisa.group_index)) == sorted(map(sorted, groups))
+    assert sisa.retrain_gid == osisa.route_deletions(sisa.group_index, p.del_user)

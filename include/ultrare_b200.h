@@ -197,6 +197,21 @@ int ure_rank_metrics(const ure_inter_t* d_inter, const float* d_score, const int
 int ure_pack_interactions_f64(const double* d_cols, int64_t n, int64_t ld, const int32_t* d_row_of,
                               int32_t n_map, ure_inter_t* d_out, void* stream);
 
+/* readRating's row filter and shard split (read.py:36-68) on the device: ONE stable partition of the whole ratings
+ * table by shard.  d_cols: the float64 table as read from the CSV, field c of rating j at d_cols[j*rs + c*cs] (c = uid, iid,
+ * rating; [n][3] row-major: rs=3, cs=1; [3][n]: rs=1, cs=n); d_owner[u]:
+ * shard of user u (-1: none), d_deleted[u] != 0: user u is deleted (NULL: nobody).  d_out [n]: every shard's
+ * records (user id, item id, float32(rating / max_rating)) as one contiguous run in file order;
+ * d_shard_off int64 [n_shards + 1]: the runs' starts, d_shard_off[n_shards] = rows kept.
+ * d_hist: int32 scratch [ure_partition_blocks()][256].  n_shards <= 254. */
+int ure_partition_blocks(void);
+int ure_partition_interactions(const double* d_cols, int64_t n, int64_t rs, int64_t cs, double max_rating,
+                               const int32_t* d_owner, const uint8_t* d_deleted, int32_t n_map, int n_shards,
+                               ure_inter_t* d_out, int32_t* d_hist, int64_t* d_shard_off, void* stream);
+/* out[j] = in[j] with user -> d_row_of[user] (the row inside a compact per-shard user table). */
+int ure_remap_users(const ure_inter_t* d_in, int64_t n, const int32_t* d_row_of, int32_t n_map,
+                    ure_inter_t* d_out, void* stream);
+
 /* HOST helper of the ingest path: copy `bytes` from pageable memory into a (pinned) staging buffer with
  * non-temporal stores, so that the DMA engine reads DRAM and not other cores' caches.  Thread-safe on disjoint
  * ranges (the caller's thread pool splits the arrays); dst 16-byte aligned. */

@@ -4,6 +4,7 @@ import os
 
 import numpy as np
 import pytest
+import torch
 
 from conftest import init_weights, load_gold
 from oracle import mf as omf, ot as oot, sisa as osisa
@@ -261,3 +262,48 @@ def test_instance_run_group_uniform_delper5(toy, cuda_dev, tmp_path, monkeypatch
     groups = osisa.uniform_groups(N_USER, 4)
     assert sorted(map(sorted, sisa.group_index)) == sorted(map(sorted, groups))
     assert sisa.retrain_gid == osisa.route_deletions(sisa.group_index, p.del_user)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_group,with_del,sort", [(1, False, 'r'), (5, True, 'a'), (7, True, 'r')])
+def test_read_rating_device_equals_host(n_group, with_del, sort):
+    """readRatingDevice (partition kernel) == readRating (host filter, reference read.py:36-68): same groups, same
+    rows in the same order, bit-equal float32 ratings; host views of the device-backed datasets equal too."""
+    import pandas as pd
+    from ultrare_b200 import kernels as kn
+    from ultrare_b200.read import RatingData, readRating, readRatingDevice
+    rng = np.random.default_rng(5)
+    n_user, n_item, n = 700, 300, 60000
+    df = pd.DataFrame({0: rng.integers(0, n_user, n), 1: rng.integers(0, n_item, n), 2: rng.integers(1, 6, n)})
+    del_user = list(rng.choice(n_user, 40, replace=False)) if with_del else []
+    host, gi_h = readRating(df, n_user, 5, del_user, [], n_group, [], sort)
+    dev, gi_d, total = readRatingDevice(df, n_user, 5, del_user, [], n_group, [], sort, device='cuda')
+    assert [list(g) for g in gi_h] == [list(g) for g in gi_d]
+    for g in range(n_group):
+        want = RatingData(host[g]).records('cuda').cpu().numpy()
+        got = dev[g].records('cuda').cpu().numpy()
+        assert got.shape == want.shape and np.array_equal(got, want), g
+        assert np.array_equal(dev[g].users, host[g][0].astype(int)) and np.array_equal(dev[g].ratings, host[g][2])
+        assert np.array_equal(dev[g]._raw, host[g])
+    assert np.array_equal(total.records('cuda').cpu().numpy(),
+                          RatingData(np.hstack(host)).records('cuda').cpu().numpy())
+    # compact-row remap == the pack kernel's remap
+    row_of = torch.from_numpy(rng.integers(0, 50, n_user).astype(np.int32)).cuda()
+    g = n_group - 1
+    assert np.array_equal(dev[g].records_mapped('cuda', row_of, 't').cpu().numpy(),
+                          RatingData(host[g]).records_mapped('cuda', row_of, 't').cpu().numpy())
+
+
+@pytest.mark.gpu
+def test_read_rating_device_ragged_edges():
+    """Users without ratings, an empty group, ids beyond n_user, a table smaller than one CTA tile."""
+    import pandas as pd
+    from ultrare_b200.read import RatingData, readRating, readRatingDevice
+    df = pd.DataFrame({0: [3, 3, 9, 0, 12, 3, 9], 1: [1, 2, 3, 4, 5, 6, 7], 2: [5, 4, 3, 2, 1, 5, 4]})
+    groups = [[0, 1], [2], [3, 9], [12]]
+    host, _ = readRating(df, 10, 5, [9], [], 4, groups)
+    dev, _, total = readRatingDevice(df, 10, 5, [9], [], 4, groups, device='cuda')
+    assert [len(d) for d in dev] == [h.shape[1] for h in host] == [1, 0, 3, 1]
+    for g in range(4):
+        assert np.array_equal(dev[g].records('cuda').cpu().numpy(), RatingData(host[g]).records('cuda').cpu().numpy())
+    assert len(total) == 5

@@ -59,6 +59,9 @@ SIGNATURES = {
     "ure_score_finalize": (C.c_int, [_p, _p, _i64, _f32, _p, _p, _p]),
     "ure_rank_metrics": (C.c_int, [_p, _p, _p, _p, _i64, _p, _p]),
     "ure_pack_interactions_f64": (C.c_int, [_p, _i64, _i64, _p, _i32, _p, _p]),
+    "ure_partition_blocks": (C.c_int, []),
+    "ure_partition_interactions": (C.c_int, [_p, _i64, _i64, _i64, _f64, _p, _p, _i32, C.c_int, _p, _p, _p, _p]),
+    "ure_remap_users": (C.c_int, [_p, _i64, _p, _i32, _p, _p]),
     "ure_host_stage_copy": (C.c_int, [_p, _p, _i64]),
     "ure_route_deletions": (C.c_int, [_p, _i32, _p, _i32, _p, _i32, _p]),
     "ure_merge_user_rows": (C.c_int, [_p, _p, _p, _p, _p, _i32, C.c_int, C.c_int, _p]),

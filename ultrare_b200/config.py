@@ -20,7 +20,7 @@ from .group import DATA_DIR, SAVE_DIR, Group
 from .method.scratch import Scratch
 from .method.sisa import Sisa
 from .method.utils import saveObject
-from .read import RatingData, loadData, readRating
+from .read import RatingData, loadData, readRating, readRatingDevice
 
 DATASETS = {
     # name: (train file, test file, n_user, n_item, batch)   reference config.py:26,40-44
@@ -95,6 +95,22 @@ class Instance(object):
                                     [], [], n_group, train_index)
         return train_rating, train_index, test_rating
 
+    # the same read with the filter/split on the GPU: RatingData objects instead of arrays (read.readRatingDevice);
+    # URE_HOST_INGEST=1 keeps the host split of `_read`
+    def _read_data(self, is_del=False, n_group=1, group_index=[]):
+        import torch
+        if os.environ.get('URE_HOST_INGEST', '0') == '1' or not torch.cuda.is_available():
+            train, train_index, test, test_total = self._read_data(is_del, n_group, group_index)
+            return ([RatingData(r) for r in train_rating], train_index, [RatingData(r) for r in test_rating],
+                    RatingData(np.hstack(test_rating)))
+        del_user = self.param.del_user if is_del == True else []
+        del_rating = self.param.del_rating if is_del == True else []
+        train, train_index, _ = readRatingDevice(self.param.train_dir, self.param.n_user, self.param.max_rating,
+                                                 del_user, del_rating, n_group, group_index, 'a')
+        test, _, test_total = readRatingDevice(self.param.test_dir, self.param.n_user, self.param.max_rating,
+                                               [], [], n_group, train_index)
+        return train, train_index, test, test_total
+
     def _save_dir(self, is_save, saving_name):
         if is_save != True:
             return ''
@@ -105,9 +121,9 @@ class Instance(object):
     # sub function of self.runFull (config.py:99-120)
     def _full(self, is_save, saving_name, model_type='mf', is_del=False, verbose=1):
         print(self.name, saving_name, 'begin:')
-        train_rating, _, test_rating = self._read(is_del)
-        train_data = loadData(RatingData(train_rating[0]), self.param.batch, self.param.n_worker)
-        test_data = loadData(RatingData(test_rating[0]), self.param.batch, self.param.n_worker, False)
+        train, _, test, _ = self._read_data(is_del)
+        train_data = loadData(train[0], self.param.batch, self.param.n_worker)
+        test_data = loadData(test[0], self.param.batch, self.param.n_worker, False)
         save_dir = self._save_dir(is_save, saving_name)
         model = Scratch(self.param, model_type)
         model.train(train_data, test_data, [], verbose, save_dir)
@@ -138,15 +154,14 @@ class Instance(object):
                                                                                group_type, verbose=False)
             self.timing['grouping_s'] = time.time() - t0
 
-        train_rating, train_index, test_rating = self._read(is_del, n_group, group_index)
+        train, train_index, test, test_total = self._read_data(is_del, n_group, group_index)
 
         train_dlist, test_dlist = [], []
         assert learn_type in ['sisa']
         for i in range(n_group):
-            train_dlist.append(loadData(RatingData(train_rating[i]), self.param.batch, self.param.n_worker))
-            test_dlist.append(loadData(RatingData(test_rating[i]), self.param.batch, self.param.n_worker, False))
-        test_total = np.hstack(test_rating)                                                 # config.py:144-148
-        test_data = loadData(RatingData(test_total), self.param.batch, self.param.n_worker, False)
+            train_dlist.append(loadData(train[i], self.param.batch, self.param.n_worker))
+            test_dlist.append(loadData(test[i], self.param.batch, self.param.n_worker, False))
+        test_data = loadData(test_total, self.param.batch, self.param.n_worker, False)         # config.py:144-148
 
         save_dir = self._save_dir(is_save, saving_name)
         model = Sisa(self.param, model_type, n_group, train_index)

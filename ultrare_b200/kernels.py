@@ -200,6 +200,62 @@ def upload_array(a: np.ndarray, device) -> torch.Tensor:
     return out
 
 
+def upload_table(a: np.ndarray, device) -> torch.Tensor:
+    """Large host array -> device: staging copies in 2 MB tasks on the pack pool (non-temporal stores), one DMA."""
+    a = np.ascontiguousarray(a)
+    out = torch.empty(a.shape, dtype=_TORCH_DTYPE[a.dtype.name], device=device)
+    nb = a.nbytes
+    if nb < (1 << 21):
+        return upload_array(a, device)
+    stage = _staging_bytes(nb)
+    base, src, L, CHUNK = stage.data_ptr(), a.ctypes.data, _lib.lib(), 1 << 21
+    futs = [_pack_pool().submit(L.ure_host_stage_copy, C.c_void_p(base + lo), C.c_void_p(src + lo), min(CHUNK, nb - lo))
+            for lo in range(0, nb, CHUNK)]
+    for f in futs:
+        check(f.result(), "ure_host_stage_copy")
+    with torch.cuda.device(device):
+        out.view(-1).view(torch.uint8).copy_(stage[:nb], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        _PINNED_BYTES[stage.shape[0]].append((stage, ev))
+    return out
+
+
+def partition_interactions(table: torch.Tensor, max_rating: float, owner: torch.Tensor,
+                           deleted: Optional[torch.Tensor], n_shards: int):
+    """readRating's filter + split on the device (ure_partition_interactions).  table: float64 [n,3] (rows of the
+    CSV) or [3,n]; owner int32 [n_map]; deleted uint8 [n_map] or None.  Returns (records int32 [n,4] whose first
+    shard_off[-1] rows are the shards' runs back to back, shard_off int64 device tensor [n_shards+1])."""
+    _need_cuda(table, owner, deleted)
+    assert table.dtype == torch.float64 and table.dim() == 2 and table.is_contiguous()
+    assert owner.dtype == torch.int32 and (deleted is None or (deleted.dtype == torch.uint8 and deleted.shape == owner.shape))
+    if table.shape[1] == 3:
+        n, rs, cs = table.shape[0], 3, 1
+    else:
+        assert table.shape[0] == 3
+        n, rs, cs = table.shape[1], 1, table.shape[1]
+    L = _lib.lib()
+    out = torch.empty((n, 4), dtype=torch.int32, device=table.device)
+    off = torch.empty(n_shards + 1, dtype=torch.int64, device=table.device)
+    hist = torch.empty((L.ure_partition_blocks(), 256), dtype=torch.int32, device=table.device)
+    with torch.cuda.device(table.device):
+        check(L.ure_partition_interactions(_ptr(table), n, rs, cs, float(max_rating), _ptr(owner), _ptr(deleted),
+                                           owner.shape[0], n_shards, _ptr(out), _ptr(hist), _ptr(off), _stream()),
+              "ure_partition_interactions")
+    return out, off
+
+
+def remap_users(inter: torch.Tensor, row_of: torch.Tensor) -> torch.Tensor:
+    """Copy of `inter` whose user field is row_of[user] (ure_remap_users)."""
+    _need_cuda(inter, row_of)
+    assert inter.dtype == torch.int32 and inter.is_contiguous() and row_of.dtype == torch.int32
+    out = torch.empty_like(inter)
+    with torch.cuda.device(inter.device):
+        check(_lib.lib().ure_remap_users(_ptr(inter), inter.shape[0], _ptr(row_of), row_of.shape[0], _ptr(out), _stream()),
+              "ure_remap_users")
+    return out
+
+
 def pointer_table(tensors: Sequence[torch.Tensor], device) -> torch.Tensor:
     return upload_array(np.array([t.data_ptr() for t in tensors], dtype=np.int64), device)
 

@@ -57,6 +57,51 @@ def readRating(dir, n_user, max_rating=5, del_user=[], del_rating=[], n_group=1,
     return rating_lists, group_index
 
 
+def readRatingDevice(dir, n_user, max_rating=5, del_user=[], del_rating=[], n_group=1, group_index=[], sort='r',
+                     device='cuda'):
+    """``readRating`` (reference read.py:9-70) with the row filter and the group split ON the device.
+
+    The CSV is parsed on the host (pandas, as in the reference) and uploaded ONCE; one stable partition kernel
+    (ure_partition_interactions) then does what read.py:36-68 does with K np.in1d scans.  Returns
+    (datasets [n_group] of device-backed ``RatingData`` -- same rows, same row order as readRating's arrays --,
+    group_index, total) where ``total`` is the RatingData of all groups back to back (config.py:144-148's hstack).
+    """
+    if len(group_index) == 0:                 # read.py:13-26, same RNG calls as readRating
+        group_len = int(np.ceil(n_user / n_group))
+        org_index = np.arange(n_user).tolist()
+        if n_group == 1:
+            group_index = [org_index]
+        else:
+            np.random.seed(0)
+            np.random.shuffle(org_index)
+            group_index = [org_index[i * group_len:(i + 1) * group_len] for i in range(n_group)]
+    ratings = dir if isinstance(dir, pd.DataFrame) else pd.read_csv(dir, header=None, sep=',')
+    users = ratings[0].values
+    if sort in ['d', 'a']:
+        sorted_index = sort_group(order='a', group_index=group_index, var='count', ratings0=users)
+        group_index = [group_index[i] for i in sorted_index]
+    n_map = max(n_user, int(users.max()) + 1 if len(users) else 0)
+    owner = np.full(n_map, -1, dtype=np.int32)
+    for g in range(n_group - 1, -1, -1):      # a user belongs to the first group that lists it
+        owner[np.asarray(group_index[g], dtype=np.int64)] = g
+    deleted = None
+    if len(del_user):
+        deleted = np.zeros(n_map, dtype=np.uint8)
+        deleted[np.asarray(list(del_user), dtype=np.int64)] = 1
+    dev = torch.device(device)
+    tab = np.empty((3, len(users)), dtype=np.float64)        # one cast pass per column (DataFrame.values would
+    for j in range(3):                                       # first consolidate the mixed columns into a copy)
+        tab[j] = ratings[j].values
+    table = kn.upload_table(tab, dev)
+    rec, off = kn.partition_interactions(table, max_rating, kn.upload_array(owner, dev),
+                                         None if deleted is None else kn.upload_array(deleted, dev), n_group)
+    off_h = off.cpu().numpy()
+    src = (ratings, owner, deleted, float(max_rating))
+    datasets = [DeviceRatingData(rec[int(off_h[g]):int(off_h[g + 1])], src, (g, g + 1)) for g in range(n_group)]
+    total = DeviceRatingData(rec[:int(off_h[n_group])], src, (0, n_group))
+    return datasets, group_index, total
+
+
 def sort_group(order='a', group_index=[], var='count', ratings0=[], dataset='ml1'):
     """reference read.py:73-106 (var='count': groups by ascending/descending rating count)."""
     assert var in ['count']
@@ -118,6 +163,9 @@ class RatingData:
     def upload_many(datasets, device, row_of=None, tag=None):
         """records()/records_mapped() of several datasets at once: their host copies run in parallel."""
         key = str(device) if tag is None else (str(device), tag)
+        for ds in datasets:
+            if isinstance(ds, DeviceRatingData):
+                ds.records(device) if tag is None else ds.records_mapped(device, row_of, tag)
         todo = [ds for ds in datasets if key not in ds._records]
         for ds, rec in zip(todo, kn.upload_interactions_many([ds._raw for ds in todo], device, row_of)):
             ds._records[key] = rec
@@ -130,6 +178,59 @@ class RatingData:
             self._segments[key] = (None if order is None else kn.upload_array(order, device),
                                    kn.upload_array(seg, device))
         return self._segments[key]
+
+
+class DeviceRatingData(RatingData):
+    """RatingData whose records were produced on the device by ``readRatingDevice``.  ``records()`` is the
+    partition's output; the host columns (``users``/``items``/``ratings``, ``_raw``) are rebuilt on demand:
+    ids from the records, the float64 ratings by the host filter of readRating (read.py:59-68)."""
+
+    def __init__(self, records, src, groups):
+        self._dev = records
+        self._src, self._groups = src, groups
+        self._n = int(records.shape[0])
+        self._cols, self._segments = {}, {}
+        self._records = {str(records.device): records}
+
+    def _rows(self):
+        """Indices of this dataset's rows in the source table, in record order (host filter of read.py:59-62)."""
+        if 'rows' not in self._cols:
+            ratings, owner, deleted, _ = self._src
+            users = ratings[0].values.astype(np.int64)
+            own = owner[users] if deleted is None else np.where(deleted[users] != 0, -1, owner[users])
+            lo, hi = self._groups
+            parts = [np.flatnonzero(own == g) for g in range(lo, hi)]
+            self._cols['rows'] = np.concatenate(parts) if parts else np.zeros(0, dtype=np.int64)
+        return self._cols['rows']
+
+    @property
+    def _raw(self):
+        if 'raw' not in self._cols:
+            ratings, max_rating = self._src[0], self._src[3]
+            raw = np.stack([ratings[j].values[self._rows()].astype(np.float64) for j in range(3)])
+            raw[2] /= max_rating
+            self._cols['raw'] = raw
+        return self._cols['raw']
+
+    def _col(self, j, dtype):
+        if j not in self._cols:               # host copies never wait for the device (it may be training)
+            v = self._src[0][j].values[self._rows()]
+            self._cols[j] = (v.astype(np.float64) / self._src[3] if j == 2 else v).astype(dtype)
+        return self._cols[j]
+
+    def records(self, device):
+        key = str(device)
+        if key not in self._records:
+            d = torch.device(device)
+            same = d.type == 'cuda' and (d.index is None or d.index == self._dev.device.index)
+            self._records[key] = self._dev if same else self._dev.to(d)
+        return self._records[key]
+
+    def records_mapped(self, device, row_of, tag):
+        key = (str(device), tag)
+        if key not in self._records:
+            self._records[key] = kn.remap_users(self.records(device).contiguous(), row_of)
+        return self._records[key]
 
 
 class ShardLoader:

@@ -299,8 +299,16 @@ def test_read_rating_device_ragged_edges():
     """Users without ratings, an empty group, ids beyond n_user, a table smaller than one CTA tile."""
     import pandas as pd
     from ultrare_b200.read import RatingData, readRating, readRatingDevice
+    from ultrare_b200 import kernels as kn
     df = pd.DataFrame({0: [3, 3, 9, 0, 12, 3, 9], 1: [1, 2, 3, 4, 5, 6, 7], 2: [5, 4, 3, 2, 1, 5, 4]})
     groups = [[0, 1], [2], [3, 9], [12]]
+    # both table layouts, on a 3-row table where the shapes alone cannot tell them apart
+    t3 = torch.tensor([[0., 1., 5.], [1., 2., 4.], [0., 3., 1.]], dtype=torch.float64, device='cuda')
+    own = torch.tensor([1, 0], dtype=torch.int32, device='cuda')
+    r_rows, o_rows = kn.partition_interactions(t3, 5, own, None, 2, columns=False)
+    r_cols, o_cols = kn.partition_interactions(t3.t().contiguous(), 5, own, None, 2, columns=True)
+    assert o_rows.tolist() == o_cols.tolist() == [0, 1, 3] and torch.equal(r_rows, r_cols)
+    assert r_rows[:, :2].tolist() == [[1, 2], [0, 1], [0, 3]]
     host, _ = readRating(df, 10, 5, [9], [], 4, groups)
     dev, _, total = readRatingDevice(df, 10, 5, [9], [], 4, groups, device='cuda')
     assert [len(d) for d in dev] == [h.shape[1] for h in host] == [1, 0, 3, 1]

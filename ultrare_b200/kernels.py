@@ -222,18 +222,19 @@ def upload_table(a: np.ndarray, device) -> torch.Tensor:
 
 
 def partition_interactions(table: torch.Tensor, max_rating: float, owner: torch.Tensor,
-                           deleted: Optional[torch.Tensor], n_shards: int):
-    """readRating's filter + split on the device (ure_partition_interactions).  table: float64 [n,3] (rows of the
-    CSV) or [3,n]; owner int32 [n_map]; deleted uint8 [n_map] or None.  Returns (records int32 [n,4] whose first
+                           deleted: Optional[torch.Tensor], n_shards: int, columns: bool = True):
+    """readRating's filter + split on the device (ure_partition_interactions).  table: float64 [3,n] (columns=True)
+    or [n,3] (rows of the CSV, columns=False); owner int32 [n_map]; deleted uint8 [n_map] or None.  Returns (records int32 [n,4] whose first
     shard_off[-1] rows are the shards' runs back to back, shard_off int64 device tensor [n_shards+1])."""
     _need_cuda(table, owner, deleted)
     assert table.dtype == torch.float64 and table.dim() == 2 and table.is_contiguous()
     assert owner.dtype == torch.int32 and (deleted is None or (deleted.dtype == torch.uint8 and deleted.shape == owner.shape))
-    if table.shape[1] == 3:
-        n, rs, cs = table.shape[0], 3, 1
-    else:
+    if columns:
         assert table.shape[0] == 3
-        n, rs, cs = table.shape[1], 1, table.shape[1]
+        n, rs, cs = table.shape[1], 1, max(1, table.shape[1])
+    else:
+        assert table.shape[1] == 3
+        n, rs, cs = table.shape[0], 3, 1
     L = _lib.lib()
     out = torch.empty((n, 4), dtype=torch.int32, device=table.device)
     off = torch.empty(n_shards + 1, dtype=torch.int64, device=table.device)

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define URE_ABI_VERSION 2
+#define URE_ABI_VERSION 3
 #define URE_MAX_SHARDS 256        /* shard models batched in one launch           */
 #define URE_TOP_K 10              /* baseTest(top_k=10), method/utils.py:115      */
 
@@ -88,13 +88,17 @@ typedef struct {
   int32_t decay_len;    /* lazy: number of table entries (>= total steps + 1)                */
   int32_t owner_cap_rows;  /* OWNER: max owned rows of a CTA, from ure_mf_owner_prepare's plan      */
   int32_t owner_cap_slots; /* OWNER: max owned interactions of a CTA, rounded up to a multiple of 16 */
-  int32_t owner_flags;     /* OWNER: bit 0 = keep the record cache in shared memory                 */
+  int32_t owner_flags;     /* OWNER: bit 0 = keep the record cache in shared memory; bit 1 = the schedule
+                            * pre-pass re-reads the record indices instead of caching them (large CTAs) */
   int32_t owner_spe_cap;   /* OWNER: max steps per epoch of a shard (plan)                           */
   int32_t owner_sched_rows;/* OWNER: epochs per shard the schedule tables hold                       */
   uint16_t* owner_sched;   /* OWNER: DEVICE [owner_sched_rows][owner_sched_stride] batch lists       */
   int32_t* owner_sched_off;/* OWNER: DEVICE [owner_sched_rows][#SMs][owner_spe_cap + 1] list offsets */
   int64_t owner_sched_step0;  /* OWNER: global step the schedule window starts at                    */
   int64_t owner_sched_stride; /* OWNER: slots of one schedule row = sum over the shards of 2 n       */
+  int32_t owner_cap_list;  /* OWNER: batch-list entries a CTA stages in shared memory (multiple of 16, <=
+                            * owner_cap_slots); a longer list is read from the schedule table directly  */
+  int32_t owner_reserved;
 } ure_mf_hparams_t;
 
 /* ure_mf_hparams_t::mode -- three schedules of the SAME arithmetic (baseTrain + dense optim.SGD):
@@ -143,7 +147,7 @@ int ure_mf_owner_prepare(const ure_mf_shard_t* d_shards, int n_shards, const ure
 
 /* Dynamic shared memory per CTA the OWNER schedule needs for these capacities (training kernel and
  * schedule pre-pass, whichever is larger). */
-int64_t ure_mf_owner_smem_bytes(int d, int cap_rows, int cap_slots, int spe_cap, int cached);
+int64_t ure_mf_owner_smem_bytes(int d, int cap_rows, int cap_slots, int cap_list, int spe_cap, int flags);
 
 /* OWNER mode, before ure_mf_train: fill the schedule tables for the window of owner_sched_rows epochs per
  * shard that starts at global step `step0` (epoch step0 / spe_s of shard s): for every training CTA, epoch

@@ -381,10 +381,12 @@ def test_mf_owner_prepare_sorts_and_inverts(cuda_dev):
     assert sb.owner_plan["smem_need"] <= sb.owner_plan["smem_avail"]
 
 
-@pytest.mark.parametrize("cache", [True, False])
-def test_mf_owner_skewed_rows_many_shards_vs_oracle(cuda_dev, cache):
+@pytest.mark.parametrize("cache,force", [(True, None), (False, None), (False, (2, 64)), (False, (0, 16)), (False, (2, 4096))])
+def test_mf_owner_skewed_rows_many_shards_vs_oracle(cuda_dev, cache, force, monkeypatch):
     """Owner schedule on ragged shards with heavy rows (one user / one item holding a large share of a shard, rows
-    split over many chunks and CTAs with no rows at all), more steps per epoch than a chunk window, empty shard."""
+    split over many chunks and CTAs with no rows at all), more steps per epoch than a chunk window, empty shard.
+    force = (owner_flags, list_cap): the large-problem configurations -- batch lists longer than the staged
+    capacity are read from the schedule table, the pre-pass runs without its record-index cache."""
     torch = _torch()
     from ultrare_b200 import kernels as kn
     rng = np.random.default_rng(77)
@@ -404,8 +406,11 @@ def test_mf_owner_skewed_rows_many_shards_vs_oracle(cuda_dev, cache):
         shards.append(kn.ShardState(kn.pack_interactions(u, i, r, cuda_dev), torch.tensor(P0, device=cuda_dev),
                                     torch.tensor(Q0, device=cuda_dev), epochs, s, 9))
         host.append((u, i, r, P0, Q0, perms))
+    monkeypatch.setattr(kn, "OWNER_FORCE", force)
     sb = kn.ShardBatch(shards, d, batch, mode="owner", owner_cache=cache)
     assert sb.owner_plan["cached"] == cache
+    if force is not None:
+        assert sb.owner_plan["flags"] == force[0] and sb.owner_plan["list_cap"] == min(force[1], sb.hp.owner_cap_slots)
     sb.train()
     torch.cuda.synchronize()
     losses = sb.train_losses()

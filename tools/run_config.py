@@ -51,20 +51,34 @@ for j, s in enumerate(mine):
     shards.append(kn.ShardState(rec, P, Q, a.epochs, shard_id=s + 1, perm_seed=42, scratch=scratch))
 sb = kn.ShardBatch(shards, d, B, mode="owner" if a.mode == "owner" else ("lazy" if lazy else "dense"))
 torch.cuda.synchronize()
+if rank == 0 and sb.owner_plan:
+    print("owner plan", sb.owner_plan, file=sys.stderr)
 setup_s = time.time() - t0
 steps = sb.total_steps if a.max_steps <= 0 else min(sb.total_steps, a.max_steps)
-d_.barrier()
-torch.cuda.synchronize()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record()
-sb.train(steps)
-sb.flush()
-e1.record()
-torch.cuda.synchronize()
-ms = d_.max_float(e0.elapsed_time(e1))
+ms_runs, sse_first = [], None
+for rep in range(1 if sb.lazy else 2):   # rep 0 pays the first-launch costs (module load, attribute calls)
+    for s_ in shards:
+        s_.bufP.zero_(); s_.bufQ.zero_()
+        if rep:
+            s_.sse.zero_()
+    sb.step = 0
+    if sb.mode == "owner":
+        sb._sched_cover = (0, 0)          # time the schedule pre-pass as well
+    d_.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    sb.train(steps)
+    sb.flush()
+    e1.record()
+    torch.cuda.synchronize()
+    ms_runs.append(d_.max_float(e0.elapsed_time(e1)))
+    if rep == 0:
+        sse_first = torch.stack([s_.sse for s_ in shards]).sum(0).cpu().numpy()
+ms = ms_runs[-1]
 inter_local = sum(min(steps * B, s.n * a.epochs) for s in shards)
 inter = d_.sum_int(inter_local)
-sse = torch.stack([s.sse for s in shards]).sum(0).cpu().numpy()
+sse = sse_first
 if rank == 0:
     peak = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"] \
         if os.path.exists("MEASURED_PEAKS.json") else 6650.0

@@ -34,12 +34,13 @@ class MFHParams(C.Structure):
                 ("weight_decay", _f32), ("momentum", _f32), ("mode", _i32), ("decay", _p), ("decay_len", _i32),
                 ("owner_cap_rows", _i32), ("owner_cap_slots", _i32), ("owner_flags", _i32),
                 ("owner_spe_cap", _i32), ("owner_sched_rows", _i32), ("owner_sched", _p), ("owner_sched_off", _p),
-                ("owner_sched_step0", _i64), ("owner_sched_stride", _i64)]
+                ("owner_sched_step0", _i64), ("owner_sched_stride", _i64),
+                ("owner_cap_list", _i32), ("owner_reserved", _i32)]
 
 
 MF_DENSE, MF_LAZY, MF_OWNER = 0, 1, 2
 
-assert C.sizeof(MFShard) == 176 and C.sizeof(MFHParams) == 96
+assert C.sizeof(MFShard) == 176 and C.sizeof(MFHParams) == 104
 
 # name -> (restype, argtypes); every symbol include/ultrare_b200.h declares
 SIGNATURES = {
@@ -49,7 +50,7 @@ SIGNATURES = {
     "ure_mf_train": (C.c_int, [_p, C.c_int, C.POINTER(MFHParams), C.c_int, _i64, _i64, C.c_int, _p, _p]),
     "ure_mf_owner_radix_bytes": (_i64, [C.c_int]),
     "ure_mf_owner_prepare": (C.c_int, [_p, C.c_int, C.POINTER(MFHParams), C.c_int, C.c_int, _p, _p, _p]),
-    "ure_mf_owner_smem_bytes": (_i64, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "ure_mf_owner_smem_bytes": (_i64, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "ure_mf_owner_schedule": (C.c_int, [_p, C.c_int, C.POINTER(MFHParams), C.c_int, _i64, _p]),
     "ure_mf_train_trace": (C.c_int, [_p, _p, C.c_int, _p]),
     "ure_mf_grid_size": (C.c_int, []),
@@ -96,7 +97,7 @@ def lib() -> C.CDLL:
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(handle, name)           # AttributeError if the .so lacks a declared symbol
         fn.restype, fn.argtypes = res, args
-    if handle.ure_abi_version() != 2:
+    if handle.ure_abi_version() != 3:
         raise RuntimeError("ultrare_b200: ABI version mismatch; rebuild the shared library")
     _lib = handle
     return handle

@@ -69,11 +69,15 @@ __device__ int nearest_boundary(const int32_t* off, int n_rows, long long target
 // CTA -> (shard, row slices).  CTAs are apportioned to shards by interaction count (largest remainder);
 // inside a shard CTA q takes user rows up to the boundary nearest q*n/c, and item rows so that the
 // CUMULATIVE (user + item) slot count of CTAs 0..q-1 is nearest 2*q*n/c (items are the finer grain).
+// The item slices are handed out either in row order or from the last row down, whichever gives the smaller
+// maximum of owned rows per CTA: when row number and activity are correlated in both tables (ids sorted by
+// popularity), pairing the many-row slice of one table with the few-row slice of the other is what lets the
+// owned rows fit shared memory.
 // Block-cooperative (any block size >= 32, ends with a __syncthreads); scratch in shared memory.
 struct PlanScratch {
   int c[KMAX];
   long long rem[KMAX];
-  int ub[KMAX + 1], ib[KMAX + 1];
+  int ub[KMAX + 1], ib[KMAX + 1], jb[KMAX + 1];
 };
 
 __device__ void make_plan(const ure_mf_shard_t* shards, int K, int cta, int n_cta, Plan& pl, PlanScratch& ps) {
@@ -111,22 +115,33 @@ __device__ void make_plan(const ure_mf_shard_t* shards, int K, int cta, int n_ct
   for (int q = threadIdx.x; q <= c; q += blockDim.x) {
     int u = q <= 0 ? 0 : q >= c ? (int)sh.n_user : nearest_boundary(sh.off_u, sh.n_user, q * n / c);
     ps.ub[q] = u;
-    ps.ib[q] = q <= 0 ? 0 : q >= c ? (int)sh.n_item
-                                   : nearest_boundary(sh.off_i, sh.n_item, 2 * q * n / c - (long long)sh.off_u[u]);
+    const long long want = q <= 0 || q >= c ? 0 : 2 * q * n / c - (long long)sh.off_u[u];   // item slots of CTAs < q
+    ps.ib[q] = q <= 0 ? 0 : q >= c ? (int)sh.n_item : nearest_boundary(sh.off_i, sh.n_item, want);
+    ps.jb[q] = q <= 0 ? (int)sh.n_item : q >= c ? 0 : nearest_boundary(sh.off_i, sh.n_item, max(0ll, n - want));
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    int run = 0, i0 = 0, i1 = 0;
-    for (int q = 0; q <= pl.q + 1; ++q) {
-      run = max(run, ps.ib[q]);
-      if (q == pl.q) i0 = run;
-      if (q == pl.q + 1) i1 = run;
+    int up = 0, down = (int)sh.n_item, max_f = 0, max_r = 0;
+    for (int q = 0; q <= c; ++q) {         // monotone boundaries; the owned-row maxima of both hand-out orders
+      const int pu = up, pd = down;
+      up = max(up, ps.ib[q]);
+      down = min(down, ps.jb[q]);
+      ps.ib[q] = up;
+      ps.jb[q] = down;
+      if (q > 0) {
+        const int ru = ps.ub[q] - ps.ub[q - 1];
+        max_f = max(max_f, ru + up - pu);
+        max_r = max(max_r, ru + pd - down);
+      }
     }
+    const bool rev = max_r < max_f;
     pl.ru0 = ps.ub[pl.q]; pl.ru1 = ps.ub[pl.q + 1];
-    pl.ri0 = i0; pl.ri1 = i1;
+    pl.ri0 = rev ? ps.jb[pl.q + 1] : ps.ib[pl.q];
+    pl.ri1 = rev ? ps.jb[pl.q] : ps.ib[pl.q + 1];
     pl.su0 = sh.off_u[pl.ru0]; pl.mU = sh.off_u[pl.ru1] - pl.su0;
     pl.si0 = sh.off_i[pl.ri0]; pl.mI = sh.off_i[pl.ri1] - pl.si0;
-    pl.slot_base += (long long)pl.su0 + pl.si0;
+    // the CTA's slots in a schedule row start after those of the shard's CTAs before it
+    pl.slot_base += (long long)pl.su0 + (rev ? n - (long long)sh.off_i[pl.ri1] : (long long)pl.si0);
   }
   __syncthreads();
 }
@@ -137,10 +152,10 @@ constexpr int kMaxSpe = 8192;             // steps per epoch the schedule pre-pa
 
 // Dynamic shared memory of the training kernel.  The layout depends on LAUNCH-uniform capacities only
 // (cap_rows, cap_slots: the plan's maxima over the CTAs), so every array base is a uniform value:
-//   boundary rows [2*warps][d] fp32 | batch list [cap_slots] u16 | record cache [cap_slots] 8 B (optional)
-//   | owned rows [cap_rows][3d] fp32 (w | buf | g) | first / last boundary record of every row 2 x [cap_rows] int
-__host__ __device__ inline long long owner_smem_bytes(int d, int cap_rows, int cap_slots, bool cached) {
-  return 2ll * kOwnWarps * d * 4 + 2ll * cap_slots + (cached ? 8ll * cap_slots : 0) + 12ll * cap_rows * d +
+//   boundary rows [2*warps][d] fp32 | batch list [cap_list] u16 | packed records 8 B: of every owned slot
+//   [cap_slots] (record cache) or of the staged batch list [cap_list] | owned rows [cap_rows][2d] fp32 (w | momentum) | first / last boundary record of every row 2 x [cap_rows] int
+__host__ __device__ inline long long owner_smem_bytes(int d, int cap_rows, int cap_slots, int cap_list, bool cached) {
+  return 2ll * kOwnWarps * d * 4 + 2ll * cap_list + 8ll * (cached ? cap_slots : cap_list) + 8ll * cap_rows * d +
          8ll * cap_rows;
 }
 __global__ void plan_kernel(const ure_mf_shard_t* shards, int K, int batch, OwnerWs* ws) {
@@ -361,10 +376,11 @@ __global__ void perm_inverse_kernel(const ure_mf_shard_t* shards, int epochs) {
 constexpr int kSchedThreads = 512;
 constexpr int kSchedWarps = kSchedThreads / 32;
 
-__host__ __device__ inline long long schedule_smem_bytes(int cap_slots, int spe_cap) {
-  // record index of every slot [cap] int | step, rank of every slot 2 x [cap] u16 | histogram [spe_cap + 1] int
-  // | per-warp bin counters [warps][64] int
-  return 8ll * cap_slots + 4ll * (spe_cap + 1) + 4ll * kSchedWarps * 64 + 16;
+__host__ __device__ inline long long schedule_smem_bytes(int cap_slots, int spe_cap, bool cache_j) {
+  // record index of every slot [cap] int (optional) | step of every slot [cap] u16 | rank of every slot [cap] u16
+  // (short epochs only) | histogram [spe_cap + 1] int | per-warp bin counters [warps][64] int
+  return (cache_j ? 4ll : 0ll) * cap_slots + 2ll * cap_slots + (spe_cap <= 64 ? 2ll * cap_slots : 0ll) +
+         4ll * (spe_cap + 1) + 4ll * kSchedWarps * 64 + 16;
 }
 
 __global__ void __launch_bounds__(kSchedThreads, 2)
@@ -385,16 +401,16 @@ owner_schedule_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_h
   const int spe = (n + B - 1) / B;
   if (spe == 0) return;
   const int cap = hp.owner_cap_slots, spe_cap = hp.owner_spe_cap;
+  const bool cache_j = (hp.owner_flags & 2) == 0, short_ok = spe_cap <= 64;
   int* const s_j = reinterpret_cast<int*>(dyn);                            // [cap] record index of the slot
-  unsigned short* const s_stepof = reinterpret_cast<unsigned short*>(s_j + cap);
+  unsigned short* const s_stepof = reinterpret_cast<unsigned short*>(s_j + (cache_j ? cap : 0));
   unsigned short* const s_rank = s_stepof + cap;                           // [cap] rank inside (warp, step)
-  int* const s_hist = reinterpret_cast<int*>(s_rank + cap);                // [spe_cap + 1]
+  int* const s_hist = reinterpret_cast<int*>(s_rank + (short_ok ? cap : 0));   // [spe_cap + 1]
   int* const s_wh = s_hist + spe_cap + 1;                                  // [NW][64]
-  {
-    const int4* const recU = reinterpret_cast<const int4*>(sh.inter_u + s_pl.su0);
-    const int4* const recI = reinterpret_cast<const int4*>(sh.inter_i + s_pl.si0) - mU;
+  const int4* const recU = reinterpret_cast<const int4*>(sh.inter_u + s_pl.su0);
+  const int4* const recI = reinterpret_cast<const int4*>(sh.inter_i + s_pl.si0) - mU;
+  if (cache_j)
     for (int sl = tid; sl < m; sl += kSchedThreads) s_j[sl] = __ldg(&((sl >= mU ? recI : recU) + sl)->w);
-  }
   FeistelDomain dom;
   dom.init((uint32_t)n);
   const uint32_t magic = (uint32_t)(0x100000000ull / (uint32_t)B);         // floor(2^32/B): quotient low by <= 1
@@ -418,7 +434,7 @@ owner_schedule_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_h
       for (int u = 0; u < NI; ++u) {
         const int sl = base + 32 * u + lane;
         live[u] = sl < w1;
-        x[u] = live[u] ? (uint32_t)s_j[sl] : 0u;
+        x[u] = !live[u] ? 0u : cache_j ? (uint32_t)s_j[sl] : (uint32_t)__ldg(&((sl >= mU ? recI : recU) + sl)->w);
       }
       if (pinv) {
 #pragma unroll
@@ -433,7 +449,7 @@ owner_schedule_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_h
         if ((q[u] + 1) * (uint32_t)B <= x[u]) ++q[u];
       }
     };
-    if (spe <= 64) {
+    if (spe <= 64 && short_ok) {
       // ---- short epochs (the common case): ONE pass computes the steps and the per-warp bin counts, two warps
       // turn them into cursors, one pass scatters
       for (int x = tid; x < NW * 64; x += kSchedThreads) s_wh[x] = 0;
@@ -581,16 +597,23 @@ owner_schedule_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_h
 // ---------------------------------------------------------------- the training kernel
 // The loop below is issue-bound (ncu: ~50 % issue-slot utilisation, profiles/): launch-uniform array bases,
 // 32-bit shared-memory indexing, packed cache records and compile-time CACHED keep its instruction count down.
-template <int D, bool CACHED>
+// LONGLIST: the launch's owner_cap_list is below owner_cap_slots, so a batch list may have to be read from the
+// schedule table in global memory (generic loads); false keeps every list access a shared-memory load.
+template <int D, bool CACHED, bool LONGLIST>
 __global__ void __launch_bounds__(kOwnThreads, 1)
 mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams_t hp, int epochs,
                 long long step_begin, long long step_end, OwnerWs* ws, unsigned dbg) {
-  constexpr int G = D / 4;                 // lanes per row / interaction
+  constexpr int CH = D / 4;                // float4 chunks of a row
+  // lanes per interaction and chunks per lane: one chunk per lane up to d=32; wide rows give every lane V=4 chunks
+  // (chunk gl + v*G: a load instruction of the group still covers G*16 contiguous bytes), which divides the
+  // shuffle reductions and the per-interaction bookkeeping (the loop is issue-bound) by four.
+  constexpr int V = D >= 64 ? 4 : 1;
+  constexpr int G = CH / V;                // lanes per interaction
   constexpr int GPW = 32 / G;              // lane groups per warp
-  constexpr int QB = 4;                    // interactions a group handles per wave (gathers in flight per lane)
+  constexpr int QB = V == 4 ? 2 : 4;       // interactions a group handles per wave (QB*V gathers in flight per lane)
   constexpr int WAVE = GPW * QB;           // interactions per warp and wave
   constexpr int NW = kOwnWarps;
-  constexpr int RS = 3 * D;                // row stride in floats: [w | buf | g]
+  constexpr int RS = 2 * D;                // row stride in floats: [w | momentum, pre-scaled: mu*buf + wd*w]
   constexpr unsigned FULL = 0xffffffffu;
   extern __shared__ __align__(16) unsigned char dyn[];
   __shared__ PlanScratch s_ps;
@@ -615,12 +638,13 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
 
   // ---- shared-memory carve-up: bases depend on kernel parameters only
   const int cap = hp.owner_cap_slots;      // multiple of 16, >= m
+  const int lcap = hp.owner_cap_list;      // multiple of 16: batch lists up to this length are staged in s_list
   float* const s_bnd = reinterpret_cast<float*>(dyn);                       // [2*NW][D] boundary-row partial sums
-  unsigned short* const s_list = reinterpret_cast<unsigned short*>(s_bnd + 2 * NW * D);   // [cap] slots of the batch
-  uint2* const s_rec = reinterpret_cast<uint2*>(s_list + cap);              // [cap], CACHED only
-  float* const s_w = reinterpret_cast<float*>(s_rec + (CACHED ? cap : 0));  // row r: s_w + r*RS
-  float* const s_b = s_w + D;
-  float* const s_g = s_w + 2 * D;
+  unsigned short* const s_list = reinterpret_cast<unsigned short*>(s_bnd + 2 * NW * D);   // [lcap] slots of the batch
+  // packed records: CACHED: of every owned slot [cap]; else of the entries of the staged batch list [lcap]
+  uint2* const s_rec = reinterpret_cast<uint2*>(s_list + lcap);
+  float* const s_w = reinterpret_cast<float*>(s_rec + (CACHED ? cap : lcap));   // row r: s_w + r*RS
+  float* const s_b = s_w + D;              // gradients are summed straight into the pre-scaled momentum
   int* const s_bidx = reinterpret_cast<int*>(s_w + hp.owner_cap_rows * RS);   // [rows] first boundary record, or INT_MAX
   int* const s_blast = s_bidx + hp.owner_cap_rows;                            // [rows] last boundary record, or -1
 
@@ -630,11 +654,8 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
     const unsigned row = (unsigned)(it ? rec.y - ri0 + rowsU : rec.x - ru0);
     return make_uint2((unsigned)(it ? rec.x : rec.y) | (row << kOtherBits), (unsigned)rec.z);
   };
-  auto rec_of = [&](int sl) {
-    if (CACHED) return s_rec[sl];
-    return pack_rec(__ldg((sl >= mU ? recI : recU) + sl), sl >= mU);
-  };
-  const int offF = (int)(s_bnd - s_g) + 2 * warp * D, offL = offF + D;      // float offsets relative to s_g
+  auto load_rec = [&](int sl) { return __ldg((sl >= mU ? recI : recU) + sl); };
+  const int offF = (int)(s_bnd - s_b) + 2 * warp * D, offL = offF + D;      // float offsets relative to s_b
 
   // the CTA's part of the schedule (ure_mf_owner_schedule): row of the shard's epoch, run of the step
   const int sched_e0 = (int)(hp.owner_sched_step0 / spe);
@@ -655,22 +676,31 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
   };
   // The list of step t+1 is fetched into registers at the START of step t (its address was looked up in the
   // barrier shadow of step t-1) and stored to s_list in the shadow of step t: no global latency in the shadow.
+  // Without the record cache the records of the staged list travel with it: loaded into registers when the
+  // waves are done (the list entries have arrived by then), stored next to the list in the shadow.
   constexpr int PF = 6;                    // register entries per thread; longer lists copy the rest directly
+  constexpr int PFR = 2;                   // ... of which this many also carry their record
   unsigned short pf[PF];
+  int4 pr[PFR];
   const unsigned short* nx_src = sched;    // list of the NEXT step
   int nx_len = 0;
   bool nx_ok = true;
+  const unsigned short* cur_src = sched;   // list of THIS step in the schedule table (read there when > lcap)
 
   // ---- prologue: owned rows -> shared memory, record cache, first batch list
-  for (int x = tid; x < rows * G; x += kOwnThreads) {
-    const int r = x / G, c = x % G;
+  for (int x = tid; x < rows * CH; x += kOwnThreads) {
+    const int r = x / CH, c = x % CH;
     const bool it = r >= rowsU;
     const size_t go = (size_t)(it ? ri0 + (r - rowsU) : ru0 + r) * D + 4 * c;
-    *reinterpret_cast<float4*>(s_w + r * RS + 4 * c) = ld_cg_f4((it ? sh.Q : sh.P) + go);
-    *reinterpret_cast<float4*>(s_b + r * RS + 4 * c) = ld_cg_f4((it ? sh.bufQ : sh.bufP) + go);
-    *reinterpret_cast<float4*>(s_g + r * RS + 4 * c) = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 w = ld_cg_f4((it ? sh.Q : sh.P) + go);
+    float4 b = ld_cg_f4((it ? sh.bufQ : sh.bufP) + go);
+    // pre-scaled momentum: mu*buf + wd*w, what torch SGD adds the batch gradient to (buf = mu*buf + (g + wd*w))
+    b.x = fmaf(hp.momentum, b.x, hp.weight_decay * w.x); b.y = fmaf(hp.momentum, b.y, hp.weight_decay * w.y);
+    b.z = fmaf(hp.momentum, b.z, hp.weight_decay * w.z); b.w = fmaf(hp.momentum, b.w, hp.weight_decay * w.w);
+    *reinterpret_cast<float4*>(s_w + r * RS + 4 * c) = w;
+    *reinterpret_cast<float4*>(s_b + r * RS + 4 * c) = b;
   }
-  for (int x = tid; x < 2 * NW * G; x += kOwnThreads)
+  for (int x = tid; x < 2 * NW * CH; x += kOwnThreads)
     *reinterpret_cast<float4*>(s_bnd + 4 * x) = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int r = tid; r < rows; r += kOwnThreads) { s_bidx[r] = 0x7fffffff; s_blast[r] = -1; }
   if (CACHED)
@@ -681,7 +711,13 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
     const unsigned short* src;
     int len;
     in_window = find_list(e, k, src, len);
-    for (int x = tid; x < len; x += kOwnThreads) s_list[x] = __ldg(src + x);
+    cur_src = src;
+    if (len <= lcap)
+      for (int x = tid; x < len; x += kOwnThreads) {
+        const int sl = __ldg(src + x);
+        s_list[x] = (unsigned short)sl;
+        if (!CACHED) s_rec[x] = pack_rec(load_rec(sl), sl >= mU);
+      }
     if (tid == 0) s_total = len;
     if (step_begin + 1 < t_end) nx_ok = find_list(k + 1 == spe ? e + 1 : e, k + 1 == spe ? 0 : k + 1, nx_src, nx_len);
   }
@@ -714,6 +750,15 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
     const float* const Qr = rd ? sh.gQ : sh.Q;
     float sse_l = 0.f;
     const int total = s_total;
+    const bool staged = !LONGLIST || total <= lcap;                          // uniform over the CTA
+    const unsigned short* const lst = staged ? s_list : cur_src;
+    const bool last_step = t + 1 == t_end;
+    auto rec_at = [&](int pos) {           // packed record of list entry pos
+      if (CACHED) return s_rec[lst[pos]];
+      if (staged) return s_rec[pos];
+      const int sl = lst[pos];
+      return pack_rec(load_rec(sl), sl >= mU);
+    };
     URE_STAMP(0)
 #pragma unroll
     for (int i = 0; i < PF; ++i) {         // next step's list on its way into registers
@@ -732,8 +777,8 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
     const int ent1 = min(total, wv1 * WAVE);
     int rowF = -1, rowL = -1;
     if (wv0 < wv1) {
-      rowF = (int)(rec_of(s_list[wv0 * WAVE]).x >> kOtherBits);
-      rowL = (int)(rec_of(s_list[ent1 - 1]).x >> kOtherBits);
+      rowF = (int)(rec_at(wv0 * WAVE).x >> kOtherBits);
+      rowL = (int)(rec_at(ent1 - 1).x >> kOtherBits);
     }
     if (lane == 0) {
       if (rowF >= 0) {
@@ -741,40 +786,101 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
         atomicMin(&s_bidx[rowL], 2 * warp + 1); atomicMax(&s_blast[rowL], 2 * warp + 1);
       }
     }
-    auto flush = [&](int row, const float4& a) {
+    auto flush = [&](int row, const float4 (&a)[V]) {
       if (row >= 0) {
-        float4* gp = reinterpret_cast<float4*>(s_g + (row == rowF ? offF : row == rowL ? offL : row * RS) + 4 * gl);
-        float4 v = *gp;
-        v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
-        *gp = v;
+        float* const base = s_b + (row == rowF ? offF : row == rowL ? offL : row * RS) + 4 * gl;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          float4* gp = reinterpret_cast<float4*>(base + 4 * v * G);
+          float4 x = *gp;
+          x.x += a[v].x; x.y += a[v].y; x.z += a[v].z; x.w += a[v].w;
+          *gp = x;
+        }
       }
     };
     for (int wv = wv0; wv < wv1; ++wv) {
       const int ent0 = wv * WAVE + gw * QB;
       int row[QB];
       float rat[QB];
-      float4 o4[QB];
+      float4 o4[QB][V];
 #pragma unroll
       for (int q = 0; q < QB; ++q) {       // branch-free: entries past the end re-read the last one, weight 0
-        const uint2 rec = rec_of(s_list[min(ent0 + q, ent1 - 1)]);
+        const uint2 rec = rec_at(min(ent0 + q, ent1 - 1));
         const bool ok = ent0 + q < ent1;
         const int r = (int)(rec.x >> kOtherBits);
         row[q] = ok ? r : -1;
         rat[q] = __uint_as_float(rec.y);
         // L1-allocating load: a CTA re-reads popular rows within a step; the acquire load that ends every
         // barrier invalidates L1 (CCTL.IVALL), so no line survives into the step that rewrites its buffer
-        o4[q] = __ldca(reinterpret_cast<const float4*>((r >= rowsU ? Pr : Qr) +
-                                                       (size_t)(rec.x & ((1u << kOtherBits) - 1u)) * D + 4 * gl));
+        const float* const src = (r >= rowsU ? Pr : Qr) + (size_t)(rec.x & ((1u << kOtherBits) - 1u)) * D + 4 * gl;
+#pragma unroll
+        for (int v = 0; v < V; ++v) o4[q][v] = __ldca(reinterpret_cast<const float4*>(src + 4 * v * G));
       }
-      int key = -1;
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      int key;
+      float4 acc[V];
+      if constexpr (V == 4) {
+        // wide rows, two interactions per group: both chains run side by side (four partial dot sums each, the
+        // gathered row scaled in place into its gradient contribution); the row change inside the group is
+        // resolved after both are done
+        static_assert(V != 4 || QB == 2, "the wide-row wave handles two interactions per group");
+        float dot[QB];
+#pragma unroll
+        for (int q = 0; q < QB; ++q) {
+          const float* const wrow = s_w + max(row[q], 0) * RS + 4 * gl;
+          float p[V];
+#pragma unroll
+          for (int v = 0; v < V; ++v) {
+            const float4 w = *reinterpret_cast<const float4*>(wrow + 4 * v * G);
+            p[v] = w.x * o4[q][v].x;
+            p[v] = fmaf(w.y, o4[q][v].y, p[v]);
+            p[v] = fmaf(w.z, o4[q][v].z, p[v]);
+            p[v] = fmaf(w.w, o4[q][v].w, p[v]);
+          }
+          dot[q] = (p[0] + p[1]) + (p[2] + p[3]);
+        }
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) {
+#pragma unroll
+          for (int q = 0; q < QB; ++q) dot[q] += __shfl_xor_sync(FULL, dot[q], o);
+        }
+#pragma unroll
+        for (int q = 0; q < QB; ++q) {
+          const float err = row[q] >= 0 ? dot[q] - rat[q] : 0.f;
+          const float ge = 2.f * err;
+          if (row[q] < rowsU) sse_l = fmaf(err, err, sse_l);    // every lane of the group: divided by G below
+#pragma unroll
+          for (int v = 0; v < V; ++v) {
+            o4[q][v].x *= ge; o4[q][v].y *= ge; o4[q][v].z *= ge; o4[q][v].w *= ge;
+          }
+        }
+        key = row[1];
+        if (row[0] == row[1]) {
+#pragma unroll
+          for (int v = 0; v < V; ++v) {
+            acc[v].x = o4[0][v].x + o4[1][v].x; acc[v].y = o4[0][v].y + o4[1][v].y;
+            acc[v].z = o4[0][v].z + o4[1][v].z; acc[v].w = o4[0][v].w + o4[1][v].w;
+          }
+        } else {
+          flush(row[0], o4[0]);
+#pragma unroll
+          for (int v = 0; v < V; ++v) acc[v] = o4[1][v];
+        }
+      } else {
+      key = -1;
+#pragma unroll
+      for (int v = 0; v < V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int q = 0; q < QB; ++q) {
-        const float4 w = *reinterpret_cast<const float4*>(s_w + max(row[q], 0) * RS + 4 * gl);
-        float dot = w.x * o4[q].x;
-        dot = fmaf(w.y, o4[q].y, dot);
-        dot = fmaf(w.z, o4[q].z, dot);
-        dot = fmaf(w.w, o4[q].w, dot);
+        const float* const wrow = s_w + max(row[q], 0) * RS + 4 * gl;
+        float dot = 0.f;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          const float4 w = *reinterpret_cast<const float4*>(wrow + 4 * v * G);
+          dot = v == 0 ? w.x * o4[q][v].x : fmaf(w.x, o4[q][v].x, dot);
+          dot = fmaf(w.y, o4[q][v].y, dot);
+          dot = fmaf(w.z, o4[q][v].z, dot);
+          dot = fmaf(w.w, o4[q][v].w, dot);
+        }
 #pragma unroll
         for (int o = G / 2; o > 0; o >>= 1) dot += __shfl_xor_sync(FULL, dot, o);
         const float err = row[q] >= 0 ? dot - rat[q] : 0.f;
@@ -782,28 +888,50 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
         if (row[q] < rowsU) sse_l = fmaf(err, err, sse_l);      // every lane of the group: divided by G below
         if (q > 0 && row[q] != key) {      // the row changes inside the group: the finished run goes out
           flush(key, acc);
-          acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int v = 0; v < V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         key = row[q];
-        acc.x = fmaf(ge, o4[q].x, acc.x); acc.y = fmaf(ge, o4[q].y, acc.y);
-        acc.z = fmaf(ge, o4[q].z, acc.z); acc.w = fmaf(ge, o4[q].w, acc.w);
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          acc[v].x = fmaf(ge, o4[q][v].x, acc[v].x); acc[v].y = fmaf(ge, o4[q][v].y, acc[v].y);
+          acc[v].z = fmaf(ge, o4[q][v].z, acc[v].z); acc[v].w = fmaf(ge, o4[q][v].w, acc[v].w);
+        }
       }
-      // segmented reduction of the groups' trailing runs (the list is sorted, equal rows are adjacent)
+      }
+      // segmented reduction of the groups' trailing runs (the list is sorted, equal rows are adjacent).  Wide rows
+      // (V = 4: sixteen values per lane and step of the reduction) skip it when no two neighbouring groups end in
+      // the same row -- the usual case when a step brings about one interaction per owned row.
+      const int kprev = __shfl_up_sync(FULL, key, G);
+      const bool shared_runs = V == 1 || __any_sync(FULL, gw > 0 && kprev == key);
+      if (shared_runs) {
 #pragma unroll
       for (int o = 1; o < GPW; o <<= 1) {
         const int k2 = __shfl_down_sync(FULL, key, o * G);
-        float4 a2;
-        a2.x = __shfl_down_sync(FULL, acc.x, o * G); a2.y = __shfl_down_sync(FULL, acc.y, o * G);
-        a2.z = __shfl_down_sync(FULL, acc.z, o * G); a2.w = __shfl_down_sync(FULL, acc.w, o * G);
-        if (gw + o < GPW && k2 == key) { acc.x += a2.x; acc.y += a2.y; acc.z += a2.z; acc.w += a2.w; }
+        const bool take = gw + o < GPW && k2 == key;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          float4 a2;
+          a2.x = __shfl_down_sync(FULL, acc[v].x, o * G); a2.y = __shfl_down_sync(FULL, acc[v].y, o * G);
+          a2.z = __shfl_down_sync(FULL, acc[v].z, o * G); a2.w = __shfl_down_sync(FULL, acc[v].w, o * G);
+          if (take) { acc[v].x += a2.x; acc[v].y += a2.y; acc[v].z += a2.z; acc[v].w += a2.w; }
+        }
       }
-      const int kprev = __shfl_up_sync(FULL, key, G);
+      }
       __syncwarp();                        // the in-group flushes above are visible to the head flushes below
       if (gw == 0 || kprev != key) flush(key, acc);
       __syncwarp();
     }
     sse_l = warp_sum(sse_l);
     if (lane == 0) s_wsse[warp] = sse_l * (1.f / G);
+    const int stage = (t + 1 < t_end && nx_len <= lcap) ? nx_len : 0;   // a list longer than s_list stays in the table
+    if (!CACHED) {
+#pragma unroll
+      for (int i = 0; i < PFR; ++i) {      // the next list's records: in flight during the row sweep
+        const int x = tid + i * kOwnThreads;
+        pr[i] = load_rec(x < stage ? (int)pf[i] : 0);
+      }
+    }
     URE_STAMP(1)
     __syncthreads();
     URE_STAMP(2)
@@ -812,12 +940,12 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
     {
       float* const Pw = rd ? sh.P : sh.gP;
       float* const Qw = rd ? sh.Q : sh.gQ;
-      for (int x = tid; x < rows * G; x += kOwnThreads) {
-        const int r = x / G, c = x % G;
+#pragma unroll 4
+      for (int x = tid; x < rows * CH; x += kOwnThreads) {
+        const int r = x / CH, c = x % CH;
         float4* wp = reinterpret_cast<float4*>(s_w + r * RS + 4 * c);
         float4* bp = wp + D / 4;
-        float4* gp = wp + D / 2;
-        float4 g = *gp, w = *wp, b = *bp;
+        float4 w = *wp, b = *bp;             // b: mu*buf + wd*w + the gradients flushed by the waves
         // boundary rows: the partial sums of the warps that shared the row (adjacent records, in list order)
         // (records first..last: all of this row or of warps without entries, whose records are zero)
         const int bi = s_bidx[r];
@@ -826,20 +954,21 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
           for (int j = bi; j <= bl; ++j) {
             float4* rp = reinterpret_cast<float4*>(s_bnd + j * D + 4 * c);
             const float4 v = *rp;
-            g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w;
+            b.x += v.x; b.y += v.y; b.z += v.z; b.w += v.w;
             *rp = make_float4(0.f, 0.f, 0.f, 0.f);
           }
           __syncwarp(__activemask());
           if (c == 0) { s_bidx[r] = 0x7fffffff; s_blast[r] = -1; }
         }
-        // torch SGD: d_p = g + wd*w (fma); buf = buf*mu + d_p; w = w + (-lr)*buf (fma)
-        g.x = fmaf(wd, w.x, g.x); g.y = fmaf(wd, w.y, g.y); g.z = fmaf(wd, w.z, g.z); g.w = fmaf(wd, w.w, g.w);
-        b.x = __fadd_rn(__fmul_rn(b.x, mu), g.x); b.y = __fadd_rn(__fmul_rn(b.y, mu), g.y);
-        b.z = __fadd_rn(__fmul_rn(b.z, mu), g.z); b.w = __fadd_rn(__fmul_rn(b.w, mu), g.w);
+        // torch SGD: buf = mu*buf + (g + wd*w); w = w + (-lr)*buf -- b is the new buf; the next step's pre-scaled
+        // momentum mu*b + wd*w replaces it, except after the launch's last step (the epilogue stores buf itself)
         w.x = fmaf(nlr, b.x, w.x); w.y = fmaf(nlr, b.y, w.y); w.z = fmaf(nlr, b.z, w.z); w.w = fmaf(nlr, b.w, w.w);
         *wp = w;
+        if (!last_step) {
+          b.x = fmaf(mu, b.x, wd * w.x); b.y = fmaf(mu, b.y, wd * w.y);
+          b.z = fmaf(mu, b.z, wd * w.z); b.w = fmaf(mu, b.w, wd * w.w);
+        }
         *bp = b;
-        *gp = make_float4(0.f, 0.f, 0.f, 0.f);
         const bool it = r >= rowsU;
         st_cg_f4((it ? Qw : Pw) + (size_t)(it ? ri0 + (r - rowsU) : ru0 + r) * D + 4 * c, w);
       }
@@ -855,12 +984,20 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
     // in the barrier's shadow: the NEXT step's list goes to shared memory, the one after is looked up
     if (t + 1 < t_end) {
       in_window = nx_ok;
+      cur_src = nx_src;
 #pragma unroll
       for (int i = 0; i < PF; ++i) {
         const int x = tid + i * kOwnThreads;
-        if (x < nx_len) s_list[x] = pf[i];
+        if (x < stage) {
+          s_list[x] = pf[i];
+          if (!CACHED) s_rec[x] = pack_rec(i < PFR ? pr[i < PFR ? i : 0] : load_rec(pf[i]), pf[i] >= mU);
+        }
       }
-      for (int x = tid + PF * kOwnThreads; x < nx_len; x += kOwnThreads) s_list[x] = __ldg(nx_src + x);
+      for (int x = tid + PF * kOwnThreads; x < stage; x += kOwnThreads) {
+        const int sl = __ldg(nx_src + x);
+        s_list[x] = (unsigned short)sl;
+        if (!CACHED) s_rec[x] = pack_rec(load_rec(sl), sl >= mU);
+      }
       if (tid == 0) s_total = nx_len;
       if (t + 2 < t_end) {
         int e2 = last_of_epoch ? e + 1 : e, k2 = last_of_epoch ? 0 : k + 1;      // step t+1 ...
@@ -889,8 +1026,8 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
 
   // ---- epilogue: the owned rows go back to P/Q (whatever the parity), momentum to bufP/bufQ, and the
   // alternate weight buffer gP/gQ is returned zeroed (the DENSE schedule's contract for its gradient scratch)
-  for (int x = tid; x < rows * G; x += kOwnThreads) {
-    const int r = x / G, c = x % G;
+  for (int x = tid; x < rows * CH; x += kOwnThreads) {
+    const int r = x / CH, c = x % CH;
     const bool it = r >= rowsU;
     const size_t go = (size_t)(it ? ri0 + (r - rowsU) : ru0 + r) * D + 4 * c;
     st_cg_f4((it ? sh.Q : sh.P) + go, *reinterpret_cast<const float4*>(s_w + r * RS + 4 * c));
@@ -910,7 +1047,10 @@ int max_dyn_smem(int* out) {
 template <int D>
 int launch_owner(const ure_mf_shard_t* d_shards, int K, const ure_mf_hparams_t& hp, int epochs, long long s0,
                  long long s1, OwnerWs* ws, int smem, bool cached, unsigned dbg, cudaStream_t st) {
-  auto kern = cached ? mf_owner_kernel<D, true> : mf_owner_kernel<D, false>;
+  const bool longlist = hp.owner_cap_list < hp.owner_cap_slots;
+  auto kern = cached ? mf_owner_kernel<D, true, false>
+                     : longlist ? mf_owner_kernel<D, false, true> : mf_owner_kernel<D, false, false>;
+  URE_REQUIRE(!(cached && longlist), URE_EINVAL, "ure_mf_train(owner): the record cache needs owner_cap_list == owner_cap_slots");
   URE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   URE_CUDA(cudaMemsetAsync(ws->bar, 0, sizeof(ws->bar), st));
   void* args[] = {(void*)&d_shards, (void*)&K,  (void*)&hp, (void*)&epochs,
@@ -947,8 +1087,11 @@ int mf_train_owner(const ure_mf_shard_t* d_shards, int n_shards, const ure_mf_hp
               hp->owner_cap_slots, hp->owner_cap_rows);
   URE_REQUIRE(hp->owner_sched && hp->owner_sched_off && hp->owner_sched_rows > 0 && hp->owner_sched_step0 <= step_begin,
               URE_EINVAL, "ure_mf_train(owner): no schedule for step %lld (ure_mf_owner_schedule first)", step_begin);
+  URE_REQUIRE(hp->owner_cap_list >= 16 && hp->owner_cap_list % 16 == 0 && hp->owner_cap_list <= hp->owner_cap_slots,
+              URE_EINVAL, "ure_mf_train(owner): hparams.owner_cap_list=%d must be a multiple of 16 in [16, owner_cap_slots]",
+              hp->owner_cap_list);
   const bool cached = (hp->owner_flags & 1) != 0;
-  const long long need = owner_smem_bytes(hp->d, hp->owner_cap_rows, hp->owner_cap_slots, cached);
+  const long long need = owner_smem_bytes(hp->d, hp->owner_cap_rows, hp->owner_cap_slots, hp->owner_cap_list, cached);
   int avail = 0;
   if (int rc = max_dyn_smem(&avail)) return rc;
   URE_REQUIRE(need <= avail, URE_EUNSUPPORTED,
@@ -971,9 +1114,9 @@ int mf_train_owner(const ure_mf_shard_t* d_shards, int n_shards, const ure_mf_hp
 
 }  // namespace ure
 
-extern "C" int64_t ure_mf_owner_smem_bytes(int d, int cap_rows, int cap_slots, int spe_cap, int cached) {
-  const long long a = ure::owner_smem_bytes(d, cap_rows, cap_slots, cached != 0);
-  const long long b = ure::schedule_smem_bytes(cap_slots, spe_cap);
+extern "C" int64_t ure_mf_owner_smem_bytes(int d, int cap_rows, int cap_slots, int cap_list, int spe_cap, int flags) {
+  const long long a = ure::owner_smem_bytes(d, cap_rows, cap_slots, cap_list, (flags & 1) != 0);
+  const long long b = ure::schedule_smem_bytes(cap_slots, spe_cap, (flags & 2) == 0);
   return a > b ? a : b;
 }
 
@@ -986,7 +1129,7 @@ extern "C" int ure_mf_owner_schedule(const ure_mf_shard_t* d_shards, int n_shard
                   h_hp->owner_cap_slots % 16 == 0 && h_hp->owner_cap_slots <= 65520,
               URE_EUNSUPPORTED, "ure_mf_owner_schedule: rows=%d spe_cap=%d cap_slots=%d outside the supported range",
               h_hp->owner_sched_rows, h_hp->owner_spe_cap, h_hp->owner_cap_slots);
-  const long long need = schedule_smem_bytes(h_hp->owner_cap_slots, h_hp->owner_spe_cap);
+  const long long need = schedule_smem_bytes(h_hp->owner_cap_slots, h_hp->owner_spe_cap, (h_hp->owner_flags & 2) == 0);
   int avail = 0;
   if (int rc = max_dyn_smem(&avail)) return rc;
   URE_REQUIRE(need <= avail, URE_EUNSUPPORTED, "ure_mf_owner_schedule: %lld bytes of shared memory needed, %d available",

@@ -263,6 +263,7 @@ def pointer_table(tensors: Sequence[torch.Tensor], device) -> torch.Tensor:
 
 # ------------------------------------------------------------------------------ MF training
 OWNER_SCHED_BYTES = 512 << 20  # device memory one ShardBatch may spend on owner-mode schedule tables
+OWNER_FORCE = None             # test hook: (owner_flags, list_cap) the owner schedule must use
 DEFAULT_MF_MODE = "auto"       # schedule ShardBatch picks when the caller does not say (see ShardBatch)
 
 
@@ -383,6 +384,12 @@ class ShardBatch:
                 raise RuntimeError("owner mode needs at most one shard per SM")
             return "dense"
         n_tot = sum(s.n for s in shards)
+        # cheap refusal before any allocation: the weights + momentum of all rows must fit the SMs' shared memory
+        state = sum(s.P.shape[0] + s.Q.shape[0] for s in shards) * 8 * self.hp.d
+        if state > int(L.ure_mf_grid_size()) * (200 << 10) or n_tot >= (1 << 31):
+            if required:
+                raise RuntimeError(f"owner mode does not fit this problem: {state} bytes of row state")
+            return "dense"
         rec = torch.empty((4, max(1, n_tot), 4), dtype=torch.int32, device=dev)      # sorted copies + radix scratch
         n_off = sum(s.P.shape[0] + s.Q.shape[0] + 4 for s in shards)
         off = torch.zeros(n_off, dtype=torch.int32, device=dev)
@@ -399,19 +406,41 @@ class ShardBatch:
         self._owner_keep = (rec, off, radix)
         self._upload_table()
         max_rows = max(max(s.P.shape[0], s.Q.shape[0]) for s in shards)
+        npass = 1
+        while npass < 4 and (max_rows - 1) >> (8 * npass):
+            npass += 1
+        self.prepare_launches = 2 + 3 * npass + 1 + 1     # count + scan, radix passes, perm inverse, plan
         with torch.cuda.device(dev):
             check(L.ure_mf_owner_prepare(_ptr(self.table), len(shards), C.byref(self.hp), self.epochs, int(max_rows),
                                          _ptr(radix), _ptr(self.ws), _stream()), "ure_mf_owner_prepare")
         t0 = time.perf_counter()
         max_rows, max_slots, max_spe, avail = self.ws[:16].view(torch.int32).tolist()   # the one sync of the set-up
         self.plan_sync_ms = (time.perf_counter() - t0) * 1e3          # host wait for upload + sorts (diagnostics)
-        cap_rows, cap_slots, spe_cap = max(1, max_rows), -(-max_slots // 16) * 16, max(1, max_spe)
-        need = int(L.ure_mf_owner_smem_bytes(self.hp.d, cap_rows, cap_slots, spe_cap, 0))
-        need_c = int(L.ure_mf_owner_smem_bytes(self.hp.d, cap_rows, cap_slots, spe_cap, 1))
-        fits = need <= avail and cap_slots <= 65520 and cap_rows < 4096 and max_spe <= 8192
-        cached = fits and need_c <= avail and self._owner_cache and \
-            max(max(s.P.shape[0], s.Q.shape[0]) for s in shards) <= (1 << 20)
-        self.owner_plan = {"smem_need": need, "smem_need_cached": need_c, "smem_avail": avail, "cached": cached,
+        cap_rows, cap_slots, spe_cap = max(1, max_rows), max(16, -(-max_slots // 16) * 16), max(1, max_spe)
+        d = self.hp.d
+
+        def need_of(cap_list, flags):
+            return int(L.ure_mf_owner_smem_bytes(d, cap_rows, cap_slots, cap_list, spe_cap, flags))
+
+        # shared-memory configurations, fastest first: record cache (every owned slot's record resident); batch
+        # lists and their records staged per step, as many entries as fit (a longer list is read from the schedule
+        # table); the same with the schedule pre-pass running without its record-index cache
+        cands = []
+        if self._owner_cache and max(max(s.P.shape[0], s.Q.shape[0]) for s in shards) <= (1 << 20):
+            cands.append((1, cap_slots))
+        for f in (0, 2):
+            need16 = need_of(16, f)
+            if need16 <= avail:                         # 10 bytes of shared memory per staged entry
+                cands.append((f, min(cap_slots, 16 + (avail - need16) // 160 * 16)))
+        if OWNER_FORCE is not None:                      # tests: (flags, list_cap) instead of the fastest that fits
+            cands = [(OWNER_FORCE[0], min(cap_slots, max(16, OWNER_FORCE[1] // 16 * 16)))]
+        pick = next(((f, c) for f, c in cands if need_of(c, f) <= avail and
+                     (c >= min(cap_slots, 1024) or OWNER_FORCE is not None)), None)
+        fits = pick is not None and cap_slots <= 65520 and cap_rows < 4096 and max_spe <= 8192
+        flags, cap_list = pick if pick is not None else (0, cap_slots)
+        cached = bool(flags & 1)
+        self.owner_plan = {"smem_need": need_of(cap_list, flags), "smem_need_cached": need_of(cap_slots, 1),
+                           "smem_avail": avail, "cached": cached, "flags": flags, "list_cap": cap_list,
                            "max_rows_per_cta": max_rows, "max_slots_per_cta": max_slots, "max_steps_per_epoch": max_spe}
         if not fits:
             if required:
@@ -432,7 +461,7 @@ class ShardBatch:
         self.owner_plan["schedule_rows"], self.owner_plan["schedule_bytes"] = n_rows, n_rows * row_bytes
         self.hp.mode = _lib.MF_OWNER
         self.hp.owner_cap_rows, self.hp.owner_cap_slots, self.hp.owner_spe_cap = cap_rows, cap_slots, spe_cap
-        self.hp.owner_flags = int(cached)
+        self.hp.owner_flags, self.hp.owner_cap_list = int(flags), int(cap_list)
         self.hp.owner_sched, self.hp.owner_sched_off = self._sched.data_ptr(), self._sched_off.data_ptr()
         self.hp.owner_sched_rows, self.hp.owner_sched_stride, self.hp.owner_sched_step0 = n_rows, stride, 0
         return "owner"
@@ -487,12 +516,35 @@ class ShardBatch:
     def interactions_trained(self) -> int:
         return sum(s.n for s in self.shards) * self.epochs
 
+    def train_losses_async(self):
+        """train_losses without the wait: the D2H copies are queued behind the work already on the stream and the
+        returned callable waits for them when the values are needed (the host keeps launching meanwhile)."""
+        sse = torch.stack([s.sse for s in self.shards])
+        K, E = sse.shape
+        nb = sse.numel() * 8
+        owner = self.mode == "owner"
+        host = _staging_bytes(nb + 64)
+        with torch.cuda.device(sse.device):
+            host[:nb].view(torch.float64).copy_(sse.view(-1), non_blocking=True)
+            if owner:
+                host[nb:nb + 4].copy_(self.ws[16:20], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+        ns = [max(1, s.n) for s in self.shards]
+
+        def wait() -> List[np.ndarray]:
+            ev.synchronize()
+            vals = host[:nb].view(torch.float64).numpy().reshape(K, E).copy()
+            err = int(host[nb:nb + 4].view(torch.int32).item()) if owner else 0
+            _PINNED_BYTES.setdefault(host.shape[0], []).append((host, None))
+            if err != 0:
+                raise RuntimeError("ultrare_b200: owner schedule asked for a step outside its scheduled window")
+            return [np.sqrt(vals[j] / ns[j]) for j in range(K)]
+        return wait
+
     def train_losses(self) -> List[np.ndarray]:
         """Per shard: sqrt(sse_epoch / n) for every epoch (utils.py:108).  Synchronises (one D2H)."""
-        sse = torch.stack([s.sse for s in self.shards]).cpu().numpy()
-        if self.mode == "owner" and int(self.ws[16:20].view(torch.int32).item()) != 0:
-            raise RuntimeError("ultrare_b200: owner schedule asked for a step outside its scheduled window")
-        return [np.sqrt(sse[j] / max(1, s.n)) for j, s in enumerate(self.shards)]
+        return self.train_losses_async()()
 
 
 def alloc_shard_batch(rows_P: Sequence[int], n_item: int, d: int, epochs: int, device, generator=None, std=1.0):

@@ -142,7 +142,7 @@ class Sisa(Scratch):
         return float(np.sqrt(vals[0] / len(ds))), float(vals[1] / users), float(vals[2] / users)
 
     # ------------------------------------------------------------------ batched shard training
-    def _train_shards(self, ids, train_dlist, test_dlist, test_data, verbose, prior):
+    def _train_shards(self, ids, train_dlist, test_dlist, test_data, verbose, prior, defer_logs=False):
         """Train shards `ids` (ascending) together; returns ({shard: model}, {shard: unmerged P},
         {shard: index of its last-epoch log entry}).
 
@@ -222,8 +222,30 @@ class Sisa(Scratch):
                 for j, i in enumerate(mine):
                     models[i] = MF.wrap(states[j].P, states[j].Q)
             self._last_batch = sb
-            losses = sb.train_losses()                       # the one sync of the whole training
+            # defer_logs: the loss read-back is queued and awaited after the final evaluation (_flush_logs), so
+            # the merge and the evaluation are launched while the GPU still trains
+            defer_logs = defer_logs and mode == 'none' and verbose != 1
+            pending = sb.train_losses_async()
+            losses = None if defer_logs else pending()       # the one sync of the whole training
+        else:
+            defer_logs = False
         self.timing['train_s'] = time.time() - t0
+        unmerged = {i: models[i].user_mat.weight.data for i in mine}
+        if defer_logs:
+            self._pending_logs = lambda: self._write_logs(mine, pending(), mode, models, states, snaps, prior,
+                                                          test_dlist, test_data, verbose)
+            return models, unmerged, {}, compact
+        last_idx = self._write_logs(mine, losses, mode, models, states, snaps, prior, test_dlist, test_data, verbose)
+        return models, unmerged, last_idx, compact
+
+    def _flush_logs(self):
+        """Write the training-log entries whose loss read-back was deferred (after the evaluation's sync)."""
+        pend, self._pending_logs = getattr(self, '_pending_logs', None), None
+        if pend is not None:
+            pend()
+
+    def _write_logs(self, mine, losses, mode, models, states, snaps, prior, test_dlist, test_data, verbose):
+        E = self.epochs
 
         # ---- logs, in the reference's order: shard after shard, epoch after epoch (Appendix A14)
         nan = float('nan')
@@ -248,8 +270,7 @@ class Sisa(Scratch):
                     print(f'[shard {i+1}] Epoch: [{e+1:>2d}/{E:>2d}] train loss: {losses[j][e]:>.9f},'
                           f' test RMSE: {tr[0]:>.4f}, total RMSE: {to[0]:>.4f}')
             last_idx[i] = len(self.log['test_rmse']) - 1
-        unmerged = {i: models[i].user_mat.weight.data for i in mine}
-        return models, unmerged, last_idx, compact
+        return last_idx
 
     def _finish(self, new, unmerged, last_idx, compact, merged, test_dlist, save_dir):
         """After the merge: 'final'-mode last-epoch test metrics, then the per-shard artefacts."""
@@ -310,12 +331,13 @@ class Sisa(Scratch):
         assert len(test_dlist) == self.n_group
         new, unmerged, last_idx, compact = self._train_shards(
             range(self.n_group), train_dlist, test_dlist, test_data, verbose,
-            lambda i, new: [new[j] for j in range(i)])
+            lambda i, new: [new[j] for j in range(i)], defer_logs=len(save_dir) == 0)
         merged = self._merged_from(None, unmerged, compact, None)
         self._finish(new, unmerged, last_idx, compact, merged, test_dlist, save_dir)
         shared = next(iter(new.values())).user_mat.weight if new else nn.Parameter(merged, requires_grad=False)
         self.model_list = [new[i] if i in new else _RemoteModel(shared) for i in range(self.n_group)]
         self.test(test_data, verbose, save_dir)
+        self._flush_logs()
         return self.model_list
 
     def route(self, del_user):
@@ -345,7 +367,8 @@ class Sisa(Scratch):
                    for j in range(self.n_group)]
             return _local(cur)
 
-        new, unmerged, last_idx, compact = self._train_shards(order, train_dlist, test_dlist, test_data, verbose, prior)
+        new, unmerged, last_idx, compact = self._train_shards(order, train_dlist, test_dlist, test_data, verbose, prior,
+                                                              defer_logs=len(save_dir) == 0)
         t_m = time.perf_counter()
         merged = self._merged_from(base, unmerged, compact, flags)
         self._finish(new, unmerged, last_idx, compact, merged, test_dlist, save_dir)
@@ -357,6 +380,7 @@ class Sisa(Scratch):
         t_t = time.perf_counter()
         self.test(test_data, verbose, save_dir)
         self.timing['merge_ms'] = (t_t - t_m) * 1e3
+        self._flush_logs()
         self.timing['test_ms'] = (time.perf_counter() - t_t) * 1e3
         self.timing['total_ms'] = (time.perf_counter() - t_begin) * 1e3
         return self.model_list

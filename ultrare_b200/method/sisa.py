@@ -251,6 +251,15 @@ class Sisa(Scratch):
         nan = float('nan')
         last_idx = {}
         stamp = time.strftime('%H:%M:%S', time.gmtime(self.timing['train_s'] / max(1, E * max(1, len(mine)))))
+        if not mode.startswith('faithful') and verbose != 1:
+            # no per-epoch evaluation and nothing to print: whole columns at once
+            for j, i in enumerate(mine):
+                self.log['train_loss'].extend(np.asarray(losses[j], dtype=np.float64).tolist())
+                for key in ('test_rmse', 'test_ndcg', 'test_hr', 'total_rmse', 'total_ndcg', 'total_hr'):
+                    self.log[key].extend([nan] * E)
+                self.log['time'].extend([stamp] * E)
+                last_idx[i] = len(self.log['test_rmse']) - 1
+            return last_idx
         for j, i in enumerate(mine):
             pri = prior(i, models) if mode.startswith('faithful') else None
             for e in range(E):

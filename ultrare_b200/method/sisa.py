@@ -318,13 +318,17 @@ class Sisa(Scratch):
                                zero_unowned=base is None)
             return merged
         # multi-GPU: each rank contributes the rows of the shards it trained; rows are disjoint
-        mine_flags = torch.zeros(K, dtype=torch.int32, device=dev)
-        for s in unmerged:
-            mine_flags[s] = 1
+        t0 = time.perf_counter()
+        flags_np = np.zeros(K, dtype=np.int32)
+        flags_np[list(unmerged)] = 1
+        mine_flags = kn.upload_array(flags_np, dev)
         contrib = torch.zeros((self.n_user, self.k), dtype=torch.float32, device=dev)
         if unmerged:
             kn.merge_user_rows(tables, self._owner, contrib, row_of=row_of, retrain=mine_flags, zero_unowned=True)
+        t1 = time.perf_counter()
         self.dist.all_reduce(contrib)
+        self.timing['merge_local_ms'] = (t1 - t0) * 1e3
+        self.timing['merge_allreduce_ms'] = (time.perf_counter() - t1) * 1e3
         if base is None:
             return contrib
         # retrained owners' rows of the reduced table over a copy of the pre-unlearn table: the merge kernel again,
@@ -351,7 +355,7 @@ class Sisa(Scratch):
 
     def route(self, del_user):
         """retrain flags of sisa.py:76-81, by the owner-map kernel (int32 [n_group] on device)."""
-        d = torch.as_tensor(np.asarray(list(del_user), dtype=np.int32), device=self.device)
+        d = kn.upload_array(np.asarray(list(del_user), dtype=np.int32), self.device)
         return kn.route_deletions(self._owner, d, self.n_group)
 
     def unlearn(self, model_list, train_dlist, test_dlist, test_data, del_user, verbose, save_dir):

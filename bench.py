@@ -281,6 +281,7 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None       # sampled over the timed steps + the kernel-alone repeats
     if os.environ.get("URE_BENCH_DEBUG"):
         print(f"[rank {rank}] last device-resident step: {un.timing}", file=sys.stderr)
+        print(f"[rank {rank}] owner prepare: {getattr(un._last_batch, 'prepare_ms', None)}", file=sys.stderr)
     peak, peak_src = measured_peaks()
     alg_bytes = n_inter_local * E * A_MF(D_EMB)
     achieved = alg_bytes / (kern_ms / 1e3) / 1e9

@@ -379,6 +379,7 @@ class ShardBatch:
         ure_mf_owner_prepare (counting sorts + CTA plan), one 16-byte read-back of the plan."""
         L = _lib.lib()
         shards, dev = self.shards, self.device
+        tq = [time.perf_counter()]
         if len(shards) > int(L.ure_mf_grid_size()):
             if required:
                 raise RuntimeError("owner mode needs at most one shard per SM")
@@ -404,7 +405,9 @@ class ShardBatch:
             s.perm_inv = torch.empty_like(s.perm) if s.perm is not None else None
         radix = torch.empty(int(L.ure_mf_owner_radix_bytes(len(shards))) // 4, dtype=torch.int32, device=dev)
         self._owner_keep = (rec, off, radix)
+        tq.append(time.perf_counter())
         self._upload_table()
+        tq.append(time.perf_counter())
         max_rows = max(max(s.P.shape[0], s.Q.shape[0]) for s in shards)
         npass = 1
         while npass < 4 and (max_rows - 1) >> (8 * npass):
@@ -416,6 +419,7 @@ class ShardBatch:
         t0 = time.perf_counter()
         max_rows, max_slots, max_spe, avail = self.ws[:16].view(torch.int32).tolist()   # the one sync of the set-up
         self.plan_sync_ms = (time.perf_counter() - t0) * 1e3          # host wait for upload + sorts (diagnostics)
+        tq += [t0, time.perf_counter()]
         cap_rows, cap_slots, spe_cap = max(1, max_rows), max(16, -(-max_slots // 16) * 16), max(1, max_spe)
         d = self.hp.d
 
@@ -464,6 +468,9 @@ class ShardBatch:
         self.hp.owner_flags, self.hp.owner_cap_list = int(flags), int(cap_list)
         self.hp.owner_sched, self.hp.owner_sched_off = self._sched.data_ptr(), self._sched_off.data_ptr()
         self.hp.owner_sched_rows, self.hp.owner_sched_stride, self.hp.owner_sched_step0 = n_rows, stride, 0
+        tq.append(time.perf_counter())
+        self.prepare_ms = dict(zip(("alloc", "table", "launch", "sync", "plan+sched_alloc"),
+                                   (np.diff(tq) * 1e3).round(3).tolist()))
         return "owner"
 
     @staticmethod

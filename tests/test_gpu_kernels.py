@@ -513,3 +513,42 @@ def test_mf_owner_training_is_bit_reproducible(toy, cuda_dev):
         outs.append([t.cpu().numpy().copy() for sh in shards for t in (sh.P, sh.Q, sh.bufP, sh.bufQ)])
     for a, b in zip(*outs):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_mf_full_size_ml1m_k5_vs_oracle(cuda_dev, mode):
+    """BASELINE config 2 at its full size (ml1m shape: 6040 users, 3416 items, 897 k training interactions, K=5
+    shards with compact user tables, batch 30 000, d=16): two epochs of all five shards in one launch against the
+    CPU oracle run shard by shard, for both schedules."""
+    torch = _torch()
+    from ultrare_b200 import kernels as kn, synth
+    (u, i, r), _ = synth.ml_like()
+    U, I, d, K, batch, epochs = 6040, 3416, 16, 5, 30000, 2
+    rs = np.random.RandomState(0)
+    groups = np.array_split(rs.permutation(U), K)
+    row_of, owner = np.zeros(U, dtype=np.int64), np.zeros(U, dtype=np.int64)
+    for g, ids in enumerate(groups):
+        row_of[ids], owner[ids] = np.arange(len(ids)), g
+    rng = np.random.default_rng(11)
+    shards, host = [], []
+    for g, ids in enumerate(groups):
+        loc = owner[u] == g
+        ug, ig, rg = row_of[u[loc]], i[loc], (r[loc] / 5.0).astype(np.float32)
+        P0 = rng.standard_normal((len(ids), d), dtype=np.float32)
+        Q0 = rng.standard_normal((I, d), dtype=np.float32)
+        shards.append(kn.ShardState(kn.pack_interactions(ug, ig, rg, cuda_dev), torch.tensor(P0, device=cuda_dev),
+                                    torch.tensor(Q0, device=cuda_dev), epochs, g + 1, 42))
+        host.append((ug, ig, rg, P0, Q0))
+    assert sum(len(h[0]) for h in host) == len(u) > 890_000
+    sb = kn.ShardBatch(shards, d, batch, mode=mode)
+    assert sb.mode == mode
+    sb.train()
+    losses = sb.train_losses()
+    for g in range(K):
+        ug, ig, rg, P0, Q0 = host[g]
+        perms = [omf.feistel_perm(len(ug), omf.perm_key(42, g + 1, ep)) for ep in range(epochs)]
+        P, Q, bP, bQ, ls = omf.mf_train(P0, Q0, ug, ig, rg, perms, batch, epochs)
+        np.testing.assert_allclose(losses[g], ls, rtol=1e-5)
+        assert np.abs(shards[g].P.cpu().numpy() - P).max() < 2e-4
+        assert np.abs(shards[g].Q.cpu().numpy() - Q).max() < 2e-4
+        assert np.abs(shards[g].bufP.cpu().numpy() - bP).max() < 2e-3

@@ -315,3 +315,69 @@ def test_read_rating_device_ragged_edges():
     for g in range(4):
         assert np.array_equal(dev[g].records('cuda').cpu().numpy(), RatingData(host[g]).records('cuda').cpu().numpy())
     assert len(total) == 5
+
+
+@pytest.mark.gpu
+def test_sisa_full_size_ml1m_unlearn_properties(cuda_dev):
+    """BASELINE config 2 at full size (ml1m shape, K=5, 897 k interactions) through the public Sisa surface, checked
+    by properties that do not need a full reference run: the retrain set equals the oracle's routing; shards outside
+    it keep their item tables bit for bit and their owners keep their merged user rows; retrained shards change;
+    the final ensemble metrics equal the CPU oracle's baseTest on the tables the GPU produced."""
+    import pandas as pd
+    from oracle import evalm as oev
+    from ultrare_b200 import synth
+    from ultrare_b200.method.sisa import Sisa
+    from ultrare_b200.read import RatingData, loadData, readRating
+    train, test = synth.ml_like()
+    U, I, K, E, B = 6040, 3416, 5, 2, 30000
+    tr = pd.DataFrame({0: train[0], 1: train[1], 2: train[2]})
+    te = pd.DataFrame({0: test[0], 1: test[1], 2: test[2]})
+    trr, groups = readRating(tr, U, 5, [], [], K, [], 'a')
+    ter, _ = readRating(te, U, 5, [], [], K, groups)
+    del_user = [int(x) for x in groups[1][:7]] + [int(x) for x in groups[3][5:9]]      # shards 1 and 3 only
+    trd, _ = readRating(tr, U, 5, del_user, [], K, groups, 'r')
+    assert sum(a.shape[1] for a in trr) == len(train[0]) > 890_000
+
+    class P:
+        n_user, n_item, k, lam, seed, lr, lr_decay, momentum, epochs, batch = U, I, 16, 0.1, 42, 0.001, 0.95, 0.9, E, B
+
+    def loaders(arrs, shuffle):
+        return [loadData(RatingData(a), B, 1, shuffle) for a in arrs]
+
+    test_dl = loaders(ter, False)
+    test_total = np.hstack(ter)
+    test_data = loadData(RatingData(test_total), B, 1, False)
+    s1 = Sisa(P, 'mf', K, groups)
+    s1.epoch_eval = 'none'
+    before = s1.learn(loaders(trr, True), test_dl, test_data, 0, '')
+    P_before = before[0].user_mat.weight.data.clone()
+    Q_before = [m.item_mat.weight.data.clone() for m in before]
+    log_learn = dict(s1.final_log)
+
+    s2 = Sisa(P, 'mf', K, groups)
+    s2.epoch_eval = 'none'
+    after = s2.unlearn(before, loaders(trd, True), test_dl, test_data, del_user, 0, '')
+    assert s2.retrain_gid == set(osisa.route_deletions(groups, del_user)) == {1, 3}
+    P_after = after[0].user_mat.weight.data
+    for g in range(K):
+        Qg = after[g].item_mat.weight.data
+        rows = torch.as_tensor(np.asarray(groups[g]), device=P_after.device)
+        if g in s2.retrain_gid:
+            assert not torch.equal(Qg, Q_before[g])
+            assert not torch.equal(P_after[rows], P_before[rows])
+        else:
+            assert torch.equal(Qg, Q_before[g])
+            assert torch.equal(P_after[rows], P_before[rows])
+    assert len(s2.log['train_loss']) == 2 * E and all(np.isfinite(s2.log['train_loss']))
+    # fresh N(0,1) tables on nearly the same data: the first-epoch loss of shard 1 stays in the same range
+    assert abs(s2.log['train_loss'][0] - s1.log['train_loss'][E]) < 0.1 * s1.log['train_loss'][E]
+
+    # final metrics (sisa.py:18-23 -> baseTest) against the oracle on the GPU's own tables
+    Pm = P_after.cpu().numpy()
+    Qs = [m.item_mat.weight.data.cpu().numpy() for m in after]
+    tu, ti, trt = test_total[0].astype(np.int64), test_total[1].astype(np.int64), test_total[2].astype(np.float32)
+    rmse, ndcg, hr, _ = oev.base_test([Pm] * K, Qs, tu, ti, trt)
+    got = s2.final_log
+    assert abs(got['total_rmse'] - rmse) < 1e-4 * rmse
+    assert abs(got['total_ndcg'] - ndcg) < 1e-4 and abs(got['total_hr'] - hr) < 1e-4
+    assert got['total_rmse'] != log_learn['total_rmse']

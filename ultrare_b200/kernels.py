@@ -33,7 +33,7 @@ def _need_cuda(*ts):
 
 
 # ------------------------------------------------------------------------------ interactions
-_PACK_THREADS = 8
+_PACK_THREADS = int(__import__('os').environ.get('URE_PACK_THREADS', '8'))
 _POOL = []
 
 
@@ -104,13 +104,16 @@ def _staging_bytes(nbytes: int) -> torch.Tensor:
     return torch.empty(cap, dtype=torch.uint8, pin_memory=True)
 
 
-def upload_interactions_many(raws, device, row_of: Optional[torch.Tensor] = None) -> List[torch.Tensor]:
+def upload_interactions_many(raws, device, row_of: Optional[torch.Tensor] = None, defer: bool = False):
     """float64 [3, n] arrays (uid, iid, rating/max_rating: what readRating returns, reference read.py:64-68) ->
     int32 [n,4] ure_inter_t records on `device`, packed ON the device (ure_pack_interactions_f64).
 
     The host only moves bytes: every array is copied into pinned staging memory (one thread per array, NumPy
     releases the GIL) and uploaded asynchronously; the casts of RatingData (read.py:111-113,124) and the optional
-    user -> compact-row mapping (`row_of`, int32 device tensor) run in the pack kernel."""
+    user -> compact-row mapping (`row_of`, int32 device tensor) run in the pack kernel.
+
+    defer=True returns (outs, finish): the staging copies are already running on the worker threads, `finish()`
+    waits for them and queues the uploads + pack kernels -- the caller does other host work in between."""
     dev = torch.device(device)
     if dev.type != "cuda":
         raise RuntimeError("ultrare_b200: interactions are packed on a CUDA device (no CPU path exists)")
@@ -126,7 +129,7 @@ def upload_interactions_many(raws, device, row_of: Optional[torch.Tensor] = None
     offs = np.concatenate([[0], np.cumsum(ns)]).astype(np.int64)
     outs = [out_all[offs[j]:offs[j + 1]] for j in range(len(arrs))]
     if n_tot == 0:
-        return outs
+        return (outs, lambda: None) if defer else outs
     # ONE pinned staging buffer and ONE device buffer for all arrays; array j starts at a 64-byte boundary
     starts = np.zeros(len(arrs) + 1, dtype=np.int64)              # in doubles
     for j, n in enumerate(ns):
@@ -137,7 +140,7 @@ def upload_interactions_many(raws, device, row_of: Optional[torch.Tensor] = None
     base = stage.data_ptr()
     cols_all = torch.empty(tot_d, dtype=torch.float64, device=dev)
     L = _lib.lib()
-    CHUNK = 1 << 21                                               # bytes per staging task
+    CHUNK = int(float(__import__('os').environ.get('URE_PACK_CHUNK_MB', '2')) * (1 << 20)) // 64 * 64   # bytes per staging task
 
     def fill(j, lo, hi):                                          # bytes [lo, hi) of array j, non-temporal stores
         check(L.ure_host_stage_copy(C.c_void_p(base + 8 * int(starts[j]) + lo), C.c_void_p(arrs[j].ctypes.data + lo),
@@ -154,23 +157,29 @@ def upload_interactions_many(raws, device, row_of: Optional[torch.Tensor] = None
     for j in todo:
         if not arrs[j].flags.c_contiguous:
             arrs[j] = np.ascontiguousarray(arrs[j])
-    with torch.cuda.device(dev):
-        if n_tot >= (1 << 16):
-            # staging copies on worker threads (ctypes releases the GIL); every array is shipped as soon as ITS
-            # chunks are done, so the DMA engine works while the other arrays are still being copied
-            futs = {j: [_pack_pool().submit(fill, j, lo, min(24 * ns[j], lo + CHUNK))
-                        for lo in range(0, 24 * ns[j], CHUNK)] for j in todo}
+    futs = None
+    if n_tot >= (1 << 16):
+        # staging copies on worker threads (ctypes releases the GIL); every array is shipped as soon as ITS
+        # chunks are done, so the DMA engine works while the other arrays are still being copied
+        futs = {j: [_pack_pool().submit(fill, j, lo, min(24 * ns[j], lo + CHUNK))
+                    for lo in range(0, 24 * ns[j], CHUNK)] for j in todo}
+
+    def finish():
+        with torch.cuda.device(dev):
             for j in todo:
-                for f in futs[j]:
-                    f.result()
+                if futs is None:
+                    fill(j, 0, 24 * ns[j])
+                else:
+                    for f in futs[j]:
+                        f.result()
                 ship(j)
-        else:
-            for j in todo:
-                fill(j, 0, 24 * ns[j])
-                ship(j)
-        ev = torch.cuda.Event()
-        ev.record()
-        _PINNED_BYTES[stage.shape[0]].append((stage, ev))
+            ev = torch.cuda.Event()
+            ev.record()
+            _PINNED_BYTES[stage.shape[0]].append((stage, ev))
+
+    if defer:
+        return outs, finish
+    finish()
     return outs
 
 

@@ -159,6 +159,11 @@ class Sisa(Scratch):
             # default init: ONE allocation + one normal_() for every shard of the launch (device RNG);
             # an overridden _new_model (parity runs inject weights) or host-seeded init goes shard by shard
             batched = self.init_on_device and type(self)._new_model is Scratch._new_model
+            # the staging copies of the shards' records run on worker threads while the models are allocated
+            from ..read import RatingData
+            uploaded = RatingData.upload_many([train_dlist[i].dataset for i in mine], self.device,
+                                              self._row_of if compact else None, 'sisa_local' if compact else None,
+                                              defer=True)
             if batched:
                 from .scratch import model_generator
                 from .utils import MF
@@ -166,9 +171,7 @@ class Sisa(Scratch):
                 views = kn.alloc_shard_batch(rows, self.n_item, self.k, E, self.device,
                                              model_generator(self.seed, mine[0] + 1, self.device))
             t_a = time.time()
-            from ..read import RatingData
-            RatingData.upload_many([train_dlist[i].dataset for i in mine], self.device,
-                                   self._row_of if compact else None, 'sisa_local' if compact else None)
+            uploaded()
             for j, i in enumerate(mine):
                 ld = train_dlist[i]
                 rec = (ld.dataset.records_mapped(self.device, self._row_of, 'sisa_local') if compact

@@ -160,15 +160,25 @@ class RatingData:
         return self._records[key]
 
     @staticmethod
-    def upload_many(datasets, device, row_of=None, tag=None):
-        """records()/records_mapped() of several datasets at once: their host copies run in parallel."""
+    def upload_many(datasets, device, row_of=None, tag=None, defer=False):
+        """records()/records_mapped() of several datasets at once: their host copies run in parallel.
+        defer=True: the copies are started and a `finish()` callable is returned; the records are registered (and
+        the uploads queued) when it is called."""
         key = str(device) if tag is None else (str(device), tag)
         for ds in datasets:
             if isinstance(ds, DeviceRatingData):
                 ds.records(device) if tag is None else ds.records_mapped(device, row_of, tag)
         todo = [ds for ds in datasets if key not in ds._records]
-        for ds, rec in zip(todo, kn.upload_interactions_many([ds._raw for ds in todo], device, row_of)):
-            ds._records[key] = rec
+        recs, fin = kn.upload_interactions_many([ds._raw for ds in todo], device, row_of, defer=True)
+
+        def finish():
+            fin()
+            for ds, rec in zip(todo, recs):
+                ds._records[key] = rec
+
+        if defer:
+            return finish
+        finish()
 
     def segments(self, device):
         """(order or None, seg) device tensors of the per-user test segments (utils.py:151-161)."""

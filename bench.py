@@ -292,10 +292,10 @@ def run_ours(args):
                                              {}).get("dram_bytes_per_launch")
 
     # ---- end to end from host buffers through the public API
-    # uploaded per step: the float64 [3, n] arrays of this rank's shards and of the test sets (per-shard sets + the
-    # merged set), the deletion list, the shard descriptor table
-    h2d = 24 * (sum(a.shape[1] for a in sp["unlearn_train"]) + sum(t.shape[1] for t in test_all) + test_np.shape[1]) \
-        + 4 * len(del_user) + 160 * K_SHARDS
+    # uploaded per step: the float64 [3, n] arrays of this rank's shards and of the merged test set (the per-shard
+    # test sets are only read by epoch_eval='final'/'faithful', not by this workload), the deletion list, the
+    # shard descriptor table
+    h2d = 24 * (sum(a.shape[1] for a in sp["unlearn_train"]) + test_np.shape[1]) + 4 * len(del_user) + 176 * K_SHARDS
     e2e_ms = []
     d2h = 0
     for it in range(args.warmup + args.steps):

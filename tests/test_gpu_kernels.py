@@ -552,3 +552,32 @@ def test_mf_full_size_ml1m_k5_vs_oracle(cuda_dev, mode):
         assert np.abs(shards[g].P.cpu().numpy() - P).max() < 2e-4
         assert np.abs(shards[g].Q.cpu().numpy() - Q).max() < 2e-4
         assert np.abs(shards[g].bufP.cpu().numpy() - bP).max() < 2e-3
+
+
+@pytest.mark.parametrize("contiguous", [True, False])
+def test_user_segments_on_device_equal_host_segments(cuda_dev, contiguous):
+    """Per-user test segments built on the device (stable sort + run starts, padded with empty segments) give the
+    same ranking metrics as the host segmentation of utils.py:151-161, for user-sorted and for shuffled rows, with
+    users that have no test rows and an id bound larger than the largest id; empty input."""
+    torch = _torch()
+    from ultrare_b200 import kernels as kn
+    rng = np.random.default_rng(21)
+    n, n_user = 5000, 400
+    u = rng.integers(0, 300, n)                     # users 300..399 have no rows
+    if contiguous:
+        u = np.sort(u)
+    i = rng.integers(0, 50, n)
+    r = rng.integers(1, 6, n).astype(np.float32) / 5
+    inter = kn.pack_interactions(u, i, r, cuda_dev)
+    score = torch.tensor(np.round(rng.random(n), 2).astype(np.float32), device=cuda_dev)      # ties on purpose
+    order_h, seg_h = kn.user_segments(u)
+    assert (order_h is None) == contiguous
+    want = kn.rank_metrics(inter, score, kn.upload_array(seg_h, cuda_dev),
+                           None if order_h is None else kn.upload_array(order_h, cuda_dev)).cpu().numpy()
+    order_d, seg_d = kn.user_segments_device(inter, n_user)
+    assert seg_d.shape[0] == n_user + 1 and int(seg_d[0]) == 0 and int(seg_d[-1]) == n
+    got = kn.rank_metrics(inter, score, seg_d, order_d).cpu().numpy()
+    assert got[2] == want[2] == len(np.unique(u))
+    np.testing.assert_allclose(got[:2], want[:2], rtol=1e-12)
+    o, s = kn.user_segments_device(inter[:0], n_user)
+    assert o is None and int(s.max()) == 0

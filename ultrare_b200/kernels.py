@@ -33,7 +33,18 @@ def _need_cuda(*ts):
 
 
 # ------------------------------------------------------------------------------ interactions
-_PACK_THREADS = int(__import__('os').environ.get('URE_PACK_THREADS', '8'))
+def _default_pack_threads() -> int:
+    """Staging-copy threads of this process: 8, or this rank's share of the host cores when several ranks run on
+    the node (8 ranks x 8 copy threads on a 16-core host made the end-to-end step 3x slower)."""
+    import os
+    if "URE_PACK_THREADS" in os.environ:
+        return max(1, int(os.environ["URE_PACK_THREADS"]))
+    local = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1"))))
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 8)
+    return max(1, min(8, cores // local - 1))
+
+
+_PACK_THREADS = _default_pack_threads()
 _POOL = []
 
 
@@ -621,6 +632,25 @@ def user_segments(users: np.ndarray):
     us = users[order]
     starts = np.concatenate([[0], np.flatnonzero(us[1:] != us[:-1]) + 1])
     return order.astype(np.int32), np.concatenate([starts, [n]]).astype(np.int64)
+
+
+def user_segments_device(inter: torch.Tensor, n_user: int):
+    """(order int32 [n], seg int64 [n_user + 1]) of the per-user test segments (utils.py:151-161), built ON the device
+    without a host synchronisation: a stable sort of the records by user id (rows of a user stay in file order),
+    segment r = the r-th distinct user; segments past the last user are empty (seg = n) and rank_metrics skips them.
+    The ranking metrics are sums over users, so the order of the segments does not matter."""
+    _need_cuda(inter)
+    n, dev = inter.shape[0], inter.device
+    seg = torch.full((n_user + 1,), n, dtype=torch.int64, device=dev)
+    if n == 0 or n_user <= 0:
+        return None, seg
+    su, order = torch.sort(inter[:, 0].contiguous(), stable=True)
+    run = torch.zeros(n, dtype=torch.int64, device=dev)
+    if n > 1:
+        torch.cumsum((su[1:] != su[:-1]).to(torch.int64), 0, out=run[1:])
+    run.clamp_(max=n_user - 1)
+    seg.scatter_reduce_(0, run, torch.arange(n, dtype=torch.int64, device=dev), "amin")
+    return order.to(torch.int32), seg
 
 
 def rank_metrics(inter, score, seg, order=None) -> torch.Tensor:

@@ -132,7 +132,7 @@ class Sisa(Scratch):
         self.dist.all_reduce(part)
         score, sse = kn.score_finalize(part, inter, float(self.n_group))
         # ranking metrics: every rank takes its block of the user segments, the three sums are all-reduced
-        order, seg = ds.segments(self.device)
+        order, seg = ds.segments(self.device, self.n_user)
         lo, hi = self.dist.row_block(seg.shape[0] - 1)
         out = kn.rank_metrics(inter, score, seg[lo:hi + 1], order) if hi > lo else \
             torch.zeros(3, dtype=torch.float64, device=self.device)
@@ -220,7 +220,7 @@ class Sisa(Scratch):
                     ds = getattr(ld, 'dataset', None)
                     if ds is not None and len(ds) > 0:
                         ds.records(self.device)
-                        ds.segments(self.device)
+                        ds.segments(self.device, self.n_user)
             if batched and not models:
                 for j, i in enumerate(mine):
                     models[i] = MF.wrap(states[j].P, states[j].Q)

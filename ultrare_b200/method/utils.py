@@ -168,7 +168,7 @@ def baseTest(dataloader, models, loss_fn, device, verbose, top_k=10):
     inter = ds.records(dev)
     score, sse = kn.ensemble_score([m.user_mat.weight.data for m in models],
                                    [m.item_mat.weight.data for m in models], inter)
-    order, seg = ds.segments(dev)
+    order, seg = ds.segments(dev, models[0].user_mat.weight.shape[0])
     out = kn.rank_metrics(inter, score, seg, order)
     vals = torch.cat([sse, out]).cpu().numpy()
     size = len(ds)

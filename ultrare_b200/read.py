@@ -180,13 +180,22 @@ class RatingData:
             return finish
         finish()
 
-    def segments(self, device):
-        """(order or None, seg) device tensors of the per-user test segments (utils.py:151-161)."""
-        key = str(device)
+    DEVICE_SEGMENTS_MIN_ROWS = 1 << 18
+
+    def segments(self, device, n_user=None):
+        """(order or None, seg) device tensors of the per-user test segments (utils.py:151-161).  With n_user (an
+        upper bound of the user ids: the rows of the user table) they are built on the device from the uploaded
+        records, with no host pass over the data and no synchronisation; without it, by the host (file order)."""
+        if n_user is not None and self._n < self.DEVICE_SEGMENTS_MIN_ROWS:
+            n_user = None       # small sets: the host pass is hidden behind the training launch that precedes it
+        key = str(device) if n_user is None else (str(device), int(n_user))
         if key not in self._segments:
-            order, seg = kn.user_segments(self.users)
-            self._segments[key] = (None if order is None else kn.upload_array(order, device),
-                                   kn.upload_array(seg, device))
+            if n_user is not None:
+                self._segments[key] = kn.user_segments_device(self.records(device), int(n_user))
+            else:
+                order, seg = kn.user_segments(self.users)
+                self._segments[key] = (None if order is None else kn.upload_array(order, device),
+                                       kn.upload_array(seg, device))
         return self._segments[key]
 
 

@@ -295,7 +295,9 @@ def run_ours(args):
     # uploaded per step: the float64 [3, n] arrays of this rank's shards and of the merged test set (the per-shard
     # test sets are only read by epoch_eval='final'/'faithful', not by this workload), the deletion list, the
     # shard descriptor table
-    h2d = 24 * (sum(a.shape[1] for a in sp["unlearn_train"]) + test_np.shape[1]) + 4 * len(del_user) + 176 * K_SHARDS
+    # (N > 1: the test rows are sharded, a rank uploads the test sets of its own shards only)
+    test_rows = test_np.shape[1] if world == 1 else sum(test_all[s].shape[1] for s in range(Kg) if s // K_SHARDS == rank)
+    h2d = 24 * (sum(a.shape[1] for a in sp["unlearn_train"]) + test_rows) + 4 * len(del_user) + 176 * K_SHARDS
     e2e_ms = []
     d2h = 0
     for it in range(args.warmup + args.steps):
@@ -315,6 +317,8 @@ def run_ours(args):
         d2h = merged_h.numel() * 4 + sum(x.numel() * 4 for x in items_h) + 24
         if it >= args.warmup:
             e2e_ms.append(d.max_float(dt))
+    if os.environ.get("URE_BENCH_DEBUG"):
+        print(f"[rank {rank}] e2e ms per step: {np.round(e2e_ms, 2).tolist()}; last: {un.timing}", file=sys.stderr)
     e2e_value = inter_total / (float(np.mean(e2e_ms)) / 1e3)
 
     line = {

@@ -32,8 +32,10 @@ class Param:
         self.epochs, self.batch = epochs, BATCH
 
 
-def _sisa_pass(dist_obj):
-    """learn + unlearn on toy, K=4, host-seeded init (identical weights on every rank layout)."""
+def _sisa_pass(dist_obj, eval_sharded=None):
+    """learn + unlearn on toy, K=4, host-seeded init (identical weights on every rank layout).
+    eval_sharded: None = final evaluation with the test rows sharded over the ranks, False = every rank scores
+    the whole merged test set and the partial scores are all-reduced."""
     import pandas as pd
     import torch
     from oracle import sisa as osisa
@@ -56,6 +58,7 @@ def _sisa_pass(dist_obj):
         s = Sisa(Param(E), 'mf', K, idx)
         s.init_on_device = False
         s.epoch_eval = 'none'
+        s.eval_sharded = eval_sharded
         if dist_obj is not None:
             s.dist = dist_obj
         if phase == "learn":
@@ -90,7 +93,7 @@ def _worker(rank, world, port, q):
                       LOCAL_RANK=str(rank))
     from ultrare_b200 import dist as udist
     d = udist.init_from_env(backend="nccl")
-    res = dict(sisa=_sisa_pass(d), ot=_ot_pass(d))
+    res = dict(sisa=_sisa_pass(d), sisa_whole=_sisa_pass(d, eval_sharded=False), ot=_ot_pass(d))
     d.barrier()
     q.put((rank, res))
     d.td.destroy_process_group()
@@ -113,11 +116,13 @@ def test_two_rank_sisa_and_sinkhorn_equal_single_gpu(cuda_dev):
         p.join(60)
         assert p.exitcode == 0
     for r in range(2):
-        s, ref = results[r]["sisa"], single["sisa"]
-        assert s["retrain_gid"] == ref["retrain_gid"]
-        for phase in ("learn", "unlearn"):
-            assert np.abs(s[phase + "_merged"] - ref[phase + "_merged"]).max() < 1e-4
-            np.testing.assert_allclose(s[phase + "_log0"], ref[phase + "_log0"], rtol=1e-3)
+        for variant in ("sisa", "sisa_whole"):          # both multi-GPU evaluation paths against one GPU
+            s, ref = results[r][variant], single["sisa"]
+            assert s["retrain_gid"] == ref["retrain_gid"]
+            for phase in ("learn", "unlearn"):
+                assert np.abs(s[phase + "_merged"] - ref[phase + "_merged"]).max() < 1e-4
+                np.testing.assert_allclose(s[phase + "_log0"], ref[phase + "_log0"], rtol=1e-3)
+        np.testing.assert_allclose(results[r]["sisa"]["unlearn_log0"], results[r]["sisa_whole"]["unlearn_log0"], rtol=1e-5)
     lab = np.concatenate([results[0]["ot"]["label"], results[1]["ot"]["label"]])
     assert (lab == single["ot"]["label"]).mean() > 0.999
     assert abs(results[0]["ot"]["inertia"] - single["ot"]["inertia"]) / single["ot"]["inertia"] < 1e-5

@@ -84,6 +84,22 @@ def _local(models):
     return [m for m in models if m is not None and getattr(m, 'item_mat', None) is not None]
 
 
+_EVAL_ROWS = {}
+
+
+def _eval_rows(recs, n_user):
+    """(records, order, seg) of several resident test sets evaluated together; cached while the same device
+    buffers are passed again (the cache holds them, so their addresses cannot be reused meanwhile)."""
+    key = (tuple((r.data_ptr(), r.shape[0]) for r in recs), n_user)
+    hit = _EVAL_ROWS.get(key)
+    if hit is None:
+        inter = recs[0] if len(recs) == 1 else torch.cat(recs)
+        order, seg = kn.user_segments_device(inter, n_user)
+        _EVAL_ROWS.clear()                 # one entry: the resident test sets of the current run
+        hit = _EVAL_ROWS[key] = (inter, order, seg, recs)
+    return hit[0], hit[1], hit[2]
+
+
 class Sisa(Scratch):
     def __init__(self, param={}, model_type='mf', n_group=5, group_index=[]):
         super(Sisa, self).__init__(param, model_type)
@@ -91,6 +107,10 @@ class Sisa(Scratch):
         self.group_index = group_index
         self.model_list = []
         self.epoch_eval = os.environ.get('ULTRARE_EPOCH_EVAL', 'faithful')
+        # multi-GPU final evaluation: None = shard the test rows over the ranks when test_data has as many rows
+        # as the per-shard test sets together (it is their concatenation in Instance, config.py:144-148);
+        # False = always score the whole of test_data on every rank (partial scores all-reduced)
+        self.eval_sharded = None
         self.dist = udist.get()
         self._owner_np, self._row_of_np, self._owner, self._row_of = _owner_maps(group_index, self.n_user, self.device)
         self._group_rows = {}
@@ -117,9 +137,41 @@ class Sisa(Scratch):
         self.final_log = log
         return log
 
+    def _ensemble_test_sharded(self, test_dlist):
+        """Multi-GPU evaluation with the TEST ROWS sharded: every rank scores the test sets of its own shards (the
+        rows of the users it owns) and the four sums are all-reduced; a rank uploads and segments only its own test
+        rows.  Equal to evaluating the merged set because the per-shard test sets partition it by user
+        (config.py:144-148).  After the merge every model shares ONE user table, so the ensemble mean
+        (1/K) sum_k P[u].Q_k[i] is P[u].(sum_k Q_k[i]) / K: the ranks all-reduce the sum of their item tables
+        ([n_item, d]) instead of n_test partial scores, and a test row costs one item gather instead of K."""
+        dev, K = self.device, self.n_group
+        mine = [i for i, m in enumerate(self.model_list) if getattr(m, 'item_mat', None) is not None]
+        if mine:
+            qsum = torch.stack([self.model_list[i].item_mat.weight.data for i in mine]).sum(0)
+        else:
+            qsum = torch.zeros((self.n_item, self.k), dtype=torch.float32, device=dev)
+        self.dist.all_reduce(qsum)
+        merged = self.model_list[0].user_mat.weight.data
+        out = torch.zeros(4, dtype=torch.float64, device=dev)
+        recs = [test_dlist[i].dataset.records(dev) for i in mine if len(test_dlist[i].dataset) > 0]
+        if recs:
+            inter, order, seg = _eval_rows(recs, self.n_user)
+            score, sse = kn.ensemble_score([merged], [qsum], inter, denom=float(K))
+            out[0:1] = sse
+            out[1:4] = kn.rank_metrics(inter, score, seg, order)
+        self.dist.all_reduce(out)
+        vals = out.cpu().numpy()
+        n_test = sum(len(t.dataset) for t in test_dlist)
+        users = max(vals[3], 1.0)
+        return float(np.sqrt(vals[0] / max(1, n_test))), float(vals[1] / users), float(vals[2] / users)
+
     def _ensemble_test(self, test_data, verbose):
         if self.dist.world == 1:
             return baseTest(test_data, self.model_list, self.loss_fn, self.device, verbose)
+        tdl = getattr(self, '_test_dlist', None)
+        if self.eval_sharded is not False and tdl is not None and len(tdl) == self.n_group and \
+                sum(len(t.dataset) for t in tdl) == len(test_data.dataset):
+            return self._ensemble_test_sharded(tdl)
         # every rank scores against its own shards' item tables; partial sums are all-reduced
         mine = _local(self.model_list)
         ds = test_data.dataset
@@ -215,7 +267,13 @@ class Sisa(Scratch):
                         models[i] = MF.wrap(states[j].P, states[j].Q)
                 # while the GPU trains: the model wrappers, and what the final evaluation needs (upload + user
                 # segments are cached on the RatingData objects), so self.test() after the merge finds them resident
-                for ld in ([test_data] if test_data is not None else []) + \
+                sharded_eval = self.dist.world > 1 and self.eval_sharded is not False and test_data is not None and \
+                    sum(len(t.dataset) for t in test_dlist) == len(test_data.dataset)
+                if sharded_eval:                # the final evaluation reads this rank's own test rows only
+                    for i in mine:
+                        if len(test_dlist[i].dataset) > 0:
+                            test_dlist[i].dataset.records(self.device)
+                for ld in ([test_data] if test_data is not None and not sharded_eval else []) + \
                         ([test_dlist[i] for i in mine] if mode == 'final' and self.dist.world == 1 else []):
                     ds = getattr(ld, 'dataset', None)
                     if ds is not None and len(ds) > 0:
@@ -345,6 +403,7 @@ class Sisa(Scratch):
         """reference sisa.py:25-63."""
         assert len(train_dlist) == self.n_group
         assert len(test_dlist) == self.n_group
+        self._test_dlist = test_dlist
         new, unmerged, last_idx, compact = self._train_shards(
             range(self.n_group), train_dlist, test_dlist, test_data, verbose,
             lambda i, new: [new[j] for j in range(i)], defer_logs=len(save_dir) == 0)
@@ -367,6 +426,7 @@ class Sisa(Scratch):
         assert len(train_dlist) == self.n_group
         assert len(test_dlist) == self.n_group
 
+        self._test_dlist = test_dlist
         t_begin = time.perf_counter()
         flags = self.route(del_user)
         self.retrain_gid = set(int(s) for s in np.flatnonzero(flags.cpu().numpy()))

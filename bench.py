@@ -11,12 +11,13 @@ NDCG@10).  One "step" = one such pass.  Synthetic ML-1M-shaped data (ultrare_b20
 value   = trained interactions (sum over affected shards of n_s * E) / device time of the
           step, inputs resident in HBM (whole job, all ranks).
 e2e     = the same through the public API (ultrare_b200.method.sisa.Sisa.unlearn) from HOST
-          numpy arrays: record packing, H2D of all shard / test interactions, the pass, and
-          D2H of the merged user table, the item tables and the metrics, timed by wall clock
-          between device synchronisations.
+          numpy arrays in page-locked memory: H2D of this rank's shard and test interactions,
+          record packing on the device, the pass, and D2H of the merged user table, the item
+          tables and the metrics, timed by wall clock between device synchronisations.
 N > 1   : weak scaling -- every rank owns its own ml1m-shaped user population and 5 shards
           (5N shards, 6040N users in total); training needs no communication; the merged user
-          table and the ensemble scores are all-reduced (NCCL).
+          table, the summed item tables and four metric sums are all-reduced (NCCL); every
+          rank evaluates the test rows of its own shards.
 --impl reference : the oracle port of the reference's CPU path (oracle/mf.py, oracle/evalm.py
           -- vectorised PyTorch-CPU, all host threads) on a bounded sample of the same workload.
 """
@@ -208,8 +209,12 @@ def run_ours(args):
             tl.append(loadData(RatingData(sp[key][s % K_SHARDS] if mine else empty), BATCH, 1, True))
         return tl
 
+    # the step's host inputs live in page-locked memory (the contract's "from pinned host memory"): the float64
+    # [3, n] arrays readRating produced are copied there once, outside every timed region
+    sp["unlearn_train"] = [kn.pinned_copy(a) for a in sp["unlearn_train"]]
+    test_all = [kn.pinned_copy(t) for t in test_all]
     test_dlist = [loadData(RatingData(t), BATCH, 1, False) for t in test_all]
-    test_np = np.hstack(test_all)
+    test_np = kn.pinned_copy(np.hstack(test_all))
     test_data = loadData(RatingData(test_np), BATCH, 1, False)
     param = Param(U, I, E)
 

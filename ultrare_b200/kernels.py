@@ -159,26 +159,32 @@ def upload_interactions_many(raws, device, row_of: Optional[torch.Tensor] = None
 
     def ship(j):                                                  # main thread: async H2D + pack kernel of array j
         lo, hi = int(starts[j]), int(starts[j]) + 3 * ns[j]
-        cols_all[lo:hi].copy_(stage_f[lo:hi], non_blocking=True)
+        cols_all[lo:hi].copy_(stage_f[lo:hi] if pinned[j] is None else pinned[j], non_blocking=True)
         check(L.ure_pack_interactions_f64(C.c_void_p(cols_all.data_ptr() + 8 * lo), ns[j], ns[j], _ptr(row_of),
                                           0 if row_of is None else int(row_of.shape[0]), _ptr(outs[j]), _stream()),
               "ure_pack_interactions_f64")
 
     todo = [j for j in range(len(arrs)) if ns[j]]
+    pinned = [None] * len(arrs)           # arrays that already live in page-locked memory are uploaded from there
     for j in todo:
         if not arrs[j].flags.c_contiguous:
             arrs[j] = np.ascontiguousarray(arrs[j])
+        t = torch.from_numpy(arrs[j]) if arrs[j].flags.writeable else None
+        if t is not None and t.is_pinned():
+            pinned[j] = t.view(-1)
     futs = None
     if n_tot >= (1 << 16):
         # staging copies on worker threads (ctypes releases the GIL); every array is shipped as soon as ITS
         # chunks are done, so the DMA engine works while the other arrays are still being copied
         futs = {j: [_pack_pool().submit(fill, j, lo, min(24 * ns[j], lo + CHUNK))
-                    for lo in range(0, 24 * ns[j], CHUNK)] for j in todo}
+                    for lo in range(0, 24 * ns[j], CHUNK)] if pinned[j] is None else [] for j in todo}
 
     def finish():
         with torch.cuda.device(dev):
             for j in todo:
-                if futs is None:
+                if pinned[j] is not None:
+                    pass
+                elif futs is None:
                     fill(j, 0, 24 * ns[j])
                 else:
                     for f in futs[j]:
@@ -192,6 +198,15 @@ def upload_interactions_many(raws, device, row_of: Optional[torch.Tensor] = None
         return outs, finish
     finish()
     return outs
+
+
+def pinned_copy(a: np.ndarray) -> np.ndarray:
+    """Copy of `a` in page-locked host memory (a NumPy view of a pinned torch tensor): arrays handed to
+    RatingData / upload_interactions in this form are uploaded without the staging copy."""
+    t = torch.empty(a.shape, dtype=_TORCH_DTYPE[a.dtype.name], pin_memory=True)
+    out = t.numpy()
+    out[...] = a
+    return out
 
 
 def upload_interactions(raw, device, row_of: Optional[torch.Tensor] = None) -> torch.Tensor:

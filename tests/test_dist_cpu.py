@@ -124,3 +124,42 @@ def test_sharded_merge_and_ensemble_equal_single_process():
     out = _run(_ensemble_sharded)
     for o in out:
         assert o["merge_exact"] and o["err"] < 1e-5
+
+
+def _eval_rows_sharded(d):
+    """The row-sharded evaluation (Sisa._ensemble_test_sharded): every rank evaluates the test rows of the users its
+    shards own against the merged user table and the all-reduced SUM of the item tables; the four sums
+    (SSE, NDCG, HR, users) all-reduced equal the single-process ensemble evaluation of the merged test set."""
+    from oracle import evalm, sisa as osisa
+    rng = np.random.default_rng(4)
+    K, U, I, dd, n = 5, 80, 50, 16, 1500
+    groups = osisa.uniform_groups(U, K)
+    owner = np.zeros(U, dtype=np.int64)
+    for s, g in enumerate(groups):
+        owner[np.asarray(g)] = s
+    merged = rng.standard_normal((U, dd), dtype=np.float32) * 0.3
+    Qs = [rng.standard_normal((I, dd), dtype=np.float32) * 0.3 for _ in range(K)]
+    u = np.sort(rng.integers(0, U, n))
+    i, r = rng.integers(0, I, n), (rng.integers(1, 6, n) / 5).astype(np.float32)
+    rmse_ref, ndcg_ref, hr_ref, _ = evalm.base_test([merged] * K, Qs, u, i, r)
+    mine = d.my_shards(range(K))
+    qsum = torch.from_numpy(np.sum([Qs[s] for s in mine], axis=0, dtype=np.float32) if mine
+                            else np.zeros((I, dd), dtype=np.float32))
+    d.all_reduce(qsum)
+    rows = np.isin(owner[u], mine)                       # the test sets of my shards: the rows of the users I own
+    score = evalm.mf_score(merged, qsum.numpy(), u[rows], i[rows]) / np.float32(K)
+    users = len(np.unique(u[rows]))
+    nd, hr = evalm.rank_metrics(u[rows], r[rows], score) if rows.any() else (0.0, 0.0)
+    sums = torch.tensor([evalm.sse(score, r[rows]), nd * users, hr * users, float(users)], dtype=torch.float64)
+    d.all_reduce(sums)
+    v = sums.numpy()
+    return dict(rmse=float(np.sqrt(v[0] / n)), ndcg=float(v[1] / v[3]), hr=float(v[2] / v[3]), users=int(v[3]),
+                ref=(rmse_ref, ndcg_ref, hr_ref), users_ref=len(np.unique(u)))
+
+
+def test_row_sharded_evaluation_equals_single_process():
+    out = _run(_eval_rows_sharded)
+    for o in out:
+        assert o["users"] == o["users_ref"]
+        assert abs(o["rmse"] - o["ref"][0]) < 1e-6 and abs(o["ndcg"] - o["ref"][1]) < 1e-6
+        assert abs(o["hr"] - o["ref"][2]) < 1e-6

@@ -581,3 +581,23 @@ def test_user_segments_on_device_equal_host_segments(cuda_dev, contiguous):
     np.testing.assert_allclose(got[:2], want[:2], rtol=1e-12)
     o, s = kn.user_segments_device(inter[:0], n_user)
     assert o is None and int(s.max()) == 0
+
+
+def test_download_many_and_pinned_upload_round_trip(cuda_dev):
+    """download_many == .cpu() of every tensor (mixed dtypes, odd sizes, an empty tensor); records uploaded from a
+    page-locked source array (no staging copy) equal the records of the same pageable array."""
+    torch = _torch()
+    from ultrare_b200 import kernels as kn
+    g = torch.Generator(device=cuda_dev).manual_seed(3)
+    ts = [torch.randn((37, 16), device=cuda_dev, generator=g), torch.arange(1001, device=cuda_dev, dtype=torch.int64),
+          torch.zeros((0, 4), device=cuda_dev), torch.randn(5, device=cuda_dev, generator=g).double()]
+    for got, t in zip(kn.download_many(ts), ts):
+        assert got.dtype == t.cpu().numpy().dtype and np.array_equal(got, t.cpu().numpy())
+    rng = np.random.default_rng(8)
+    n = 70000
+    raw = np.stack([rng.integers(0, 900, n), rng.integers(0, 500, n), rng.integers(1, 6, n) / 5.0]).astype(np.float64)
+    pinned = kn.pinned_copy(raw)
+    assert torch.from_numpy(pinned).is_pinned() and np.array_equal(pinned, raw)
+    a = kn.upload_interactions(raw, cuda_dev)
+    b = kn.upload_interactions(pinned, cuda_dev)
+    assert torch.equal(a, b)

@@ -292,6 +292,29 @@ def remap_users(inter: torch.Tensor, row_of: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def download_many(tensors: Sequence[torch.Tensor]) -> List[np.ndarray]:
+    """Device tensors -> host arrays through ONE pinned staging buffer and ONE synchronisation (a `.cpu()` per
+    tensor is a pageable copy + a synchronisation each)."""
+    if not tensors:
+        return []
+    dev = tensors[0].device
+    sizes = [t.numel() * t.element_size() for t in tensors]
+    offs = np.concatenate([[0], np.cumsum([(b + 63) // 64 * 64 for b in sizes])]).astype(np.int64)
+    stage = _staging_bytes(int(offs[-1]) + 64)
+    with torch.cuda.device(dev):
+        for t, o, b in zip(tensors, offs[:-1], sizes):
+            if b:
+                stage[int(o):int(o) + b].copy_(t.contiguous().view(-1).view(torch.uint8), non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        ev.synchronize()
+    host = stage.numpy()
+    outs = [host[int(o):int(o) + b].view(np.dtype(str(t.dtype).replace("torch.", ""))).reshape(tuple(t.shape)).copy()
+            for t, o, b in zip(tensors, offs[:-1], sizes)]
+    _PINNED_BYTES.setdefault(stage.shape[0], []).append((stage, None))
+    return outs
+
+
 def pointer_table(tensors: Sequence[torch.Tensor], device) -> torch.Tensor:
     return upload_array(np.array([t.data_ptr() for t in tensors], dtype=np.int64), device)
 

@@ -401,6 +401,7 @@ class ShardBatch:
                             owner_sched_step0=0, owner_sched_stride=0)
         self.owner_plan = None
         self._owner_cache = bool(owner_cache)       # False: keep the records in L2 (tests of the uncached variant)
+        self.warps_group0 = self._split_groups(shards)   # before the first table upload: descriptors are final
         if mode in ("owner", "auto"):
             mode = self._prepare_owner(mode == "owner")
         self.mode = mode
@@ -420,7 +421,6 @@ class ShardBatch:
                 s.lastQ = torch.zeros(s.Q.shape[0], dtype=torch.int32, device=self.device)
                 s.touched = torch.zeros(4 * (1 + batch), dtype=torch.int32, device=self.device)
             self.hp.mode, self.hp.decay, self.hp.decay_len = _lib.MF_LAZY, self.decay.data_ptr(), len(self.decay)
-        self.warps_group0 = self._split_groups(shards)
         self._upload_table()
         self.step = 0
 

@@ -85,6 +85,15 @@ def _local(models):
 
 
 _EVAL_ROWS = {}
+_WRITERS = []
+
+
+def _writer_pool():
+    if not _WRITERS:
+        from concurrent.futures import ThreadPoolExecutor
+        _WRITERS.append(ThreadPoolExecutor(max_workers=1))
+    return _WRITERS[0]
+
 
 
 def _eval_rows(recs, n_user):
@@ -111,6 +120,7 @@ class Sisa(Scratch):
         # as the per-shard test sets together (it is their concatenation in Instance, config.py:144-148);
         # False = always score the whole of test_data on every rank (partial scores all-reduced)
         self.eval_sharded = None
+        self._writers = []
         self.dist = udist.get()
         self._owner_np, self._row_of_np, self._owner, self._row_of = _owner_maps(group_index, self.n_user, self.device)
         self._group_rows = {}
@@ -353,18 +363,36 @@ class Sisa(Scratch):
                 tr = baseTest(test_dlist[i], [m], self.loss_fn, self.device, 0)
                 for key, v in zip(('test_rmse', 'test_ndcg', 'test_hr'), tr):
                     self.log[key][last_idx[i]] = v
-        if len(save_dir) > 0:
+        if len(save_dir) > 0 and new:
+            # artefacts (scratch.py:131-144 per shard): ONE pinned device-to-host transfer for all tables, the
+            # files are written by a worker thread while the final evaluation runs (_join_writers waits for them)
+            tensors = []
             for i, m in new.items():
                 P = unmerged[i]
                 if compact:                # artefact keeps the reference's [n_user, k] shape; non-owner rows zero
                     full = torch.zeros((self.n_user, self.k), dtype=torch.float32, device=self.device)
                     full[self._rows(i)] = P
                     P = full
-                torch.save({'user_mat.weight': P.cpu(), 'item_mat.weight': m.item_mat.weight.data.cpu()},
-                           save_dir + '/model' + str(i + 1) + '.pth')
-                np.save(save_dir + '/user_mat' + str(i + 1), P.cpu().numpy())
-                np.save(save_dir + '/item_mat' + str(i + 1), m.item_mat.weight.data.cpu().numpy())
-                np.save(save_dir + '/log' + str(i + 1), self.log)
+                tensors += [P, m.item_mat.weight.data]
+            host = kn.download_many(tensors)
+            log = {k: list(v) for k, v in self.log.items()}
+
+            def write(ids=list(new), host=host, log=log):
+                for j, i in enumerate(ids):
+                    P_h, Q_h = host[2 * j], host[2 * j + 1]
+                    torch.save({'user_mat.weight': torch.from_numpy(P_h), 'item_mat.weight': torch.from_numpy(Q_h)},
+                               save_dir + '/model' + str(i + 1) + '.pth')
+                    np.save(save_dir + '/user_mat' + str(i + 1), P_h)
+                    np.save(save_dir + '/item_mat' + str(i + 1), Q_h)
+                    np.save(save_dir + '/log' + str(i + 1), log)
+
+            self._writers.append(_writer_pool().submit(write))
+
+    def _join_writers(self):
+        """Wait for the artefact files of this learn / unlearn call (raises what a writer raised)."""
+        pending, self._writers = self._writers, []
+        for f in pending:
+            f.result()
 
     # ------------------------------------------------------------------ merge
     def _merged_from(self, base, unmerged, compact, retrain_flags):
@@ -413,6 +441,7 @@ class Sisa(Scratch):
         self.model_list = [new[i] if i in new else _RemoteModel(shared) for i in range(self.n_group)]
         self.test(test_data, verbose, save_dir)
         self._flush_logs()
+        self._join_writers()
         return self.model_list
 
     def route(self, del_user):
@@ -457,6 +486,7 @@ class Sisa(Scratch):
         self.test(test_data, verbose, save_dir)
         self.timing['merge_ms'] = (t_t - t_m) * 1e3
         self._flush_logs()
+        self._join_writers()
         self.timing['test_ms'] = (time.perf_counter() - t_t) * 1e3
         self.timing['total_ms'] = (time.perf_counter() - t_begin) * 1e3
         return self.model_list

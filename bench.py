@@ -258,10 +258,10 @@ def run_ours(args):
     n_retrained = len(un.retrain_gid)
     # kernels of ours launched per device-resident step (profiles/r1_bench_launches.txt): route, [owner schedule:
     # csr_count + csr_scan + (hist, scan, scatter) per radix pass + perm_inverse + plan, then the schedule
-    # pre-pass], train, merge (x2 when sharded over GPUs), ensemble score (+ finalize when sharded), rank metrics
+    # pre-pass], train, merge (x2 when sharded over GPUs), ensemble score, rank metrics
     owner = getattr(un._last_batch, "mode", "") == "owner"
     prep = getattr(un._last_batch, "prepare_launches", 0) + 1 if owner else 0
-    launches = (1 + prep + 1 + (2 if world > 1 else 1) + (2 if world > 1 else 1) + 1) * args.steps
+    launches = (1 + prep + 1 + (2 if world > 1 else 1) + 1 + 1) * args.steps
     ms_per_step = float(np.mean(step_ms))
     inter_total = d.sum_int(n_inter_local) * E
     value = inter_total / (ms_per_step / 1e3)

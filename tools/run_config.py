@@ -1,6 +1,6 @@
 """Large synthetic shard-training configs of BASELINE.json (C3 / C4 shapes), generated on the GPU.
 
-    python tools/run_config.py --config c3|c4|c4small [--epochs E] [--mode dense|lazy|auto]
+    python tools/run_config.py --config c3|c3gpu|c4|c4small [--epochs E] [--mode dense|lazy|owner|auto]
     torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/run_config.py --config c4 ...
 
 Shard s owns users [s*U/K, (s+1)*U/K) (compact user table, local row ids), every shard has the full item

@@ -382,7 +382,10 @@ class ShardBatch:
 
     def __init__(self, shards: List[ShardState], d: int, batch: int, lr: float = 1e-3, lr_decay: float = 0.95,
                  lr_step: int = 50, weight_decay: float = 0.1, momentum: float = 0.9, lazy: bool = False,
-                 mode: Optional[str] = None, owner_cache: bool = True):
+                 mode: Optional[str] = None, owner_cache: bool = True, after_prepare=None):
+        """after_prepare: optional callable run once the set-up kernels that only read the records are queued
+        (alloc_shard_batch(defer_init=True)'s fills), before the set-up waits for the plan."""
+        self._after_prepare = after_prepare
         if not 1 <= len(shards) <= _lib.URE_MAX_SHARDS:
             raise ValueError(f"1..{_lib.URE_MAX_SHARDS} shards per launch")
         mode = ("lazy" if lazy else DEFAULT_MF_MODE) if mode is None else mode
@@ -405,6 +408,7 @@ class ShardBatch:
         if mode in ("owner", "auto"):
             mode = self._prepare_owner(mode == "owner")
         self.mode = mode
+        self._run_after_prepare()          # schedules without a set-up pass: right away
         self.lazy = mode == "lazy"
         self.decay = None
         if self.lazy:
@@ -423,6 +427,11 @@ class ShardBatch:
             self.hp.mode, self.hp.decay, self.hp.decay_len = _lib.MF_LAZY, self.decay.data_ptr(), len(self.decay)
         self._upload_table()
         self.step = 0
+
+    def _run_after_prepare(self):
+        hook, self._after_prepare = self._after_prepare, None
+        if hook is not None:
+            hook()
 
     def _upload_table(self):
         arr = (MFShard * len(self.shards))(*[s.descriptor() for s in self.shards])
@@ -474,8 +483,10 @@ class ShardBatch:
         with torch.cuda.device(dev):
             check(L.ure_mf_owner_prepare(_ptr(self.table), len(shards), C.byref(self.hp), self.epochs, int(max_rows),
                                          _ptr(radix), _ptr(self.ws), _stream()), "ure_mf_owner_prepare")
+        rb = self.ws[:16].clone()                      # the plan, snapshotted before anything else is queued
+        self._run_after_prepare()
         t0 = time.perf_counter()
-        max_rows, max_slots, max_spe, avail = self.ws[:16].view(torch.int32).tolist()   # the one sync of the set-up
+        max_rows, max_slots, max_spe, avail = rb.view(torch.int32).tolist()             # the one sync of the set-up
         self.plan_sync_ms = (time.perf_counter() - t0) * 1e3          # host wait for upload + sorts (diagnostics)
         tq += [t0, time.perf_counter()]
         cap_rows, cap_slots, spe_cap = max(1, max_rows), max(16, -(-max_slots // 16) * 16), max(1, max_spe)
@@ -612,21 +623,32 @@ class ShardBatch:
         return self.train_losses_async()()
 
 
-def alloc_shard_batch(rows_P: Sequence[int], n_item: int, d: int, epochs: int, device, generator=None, std=1.0):
+def alloc_shard_batch(rows_P: Sequence[int], n_item: int, d: int, epochs: int, device, generator=None, std=1.0,
+                      defer_init: bool = False):
     """One allocation for all shard models of a launch: N(0,std) tables (reference utils.py:38-40) plus the
-    zero-filled momentum / gradient / loss scratch.  Returns per-shard (P, Q, scratch) views."""
+    zero-filled momentum / gradient / loss scratch.  Returns per-shard (P, Q, scratch) views.
+    defer_init=True returns (views, init): the memory is reserved, `init()` queues the fills -- pass it to
+    ShardBatch(after_prepare=init) so the owner set-up's sorts are already running when the fills are launched."""
     K = len(rows_P)
     tot_p = int(sum(rows_P))
-    W = torch.empty((tot_p + K * n_item, d), dtype=torch.float32, device=device).normal_(0.0, std, generator=generator)
-    Z = torch.zeros((2, tot_p + K * n_item, d), dtype=torch.float32, device=device)
-    sse = torch.zeros((K, max(1, epochs)), dtype=torch.float64, device=device)
+    W = torch.empty((tot_p + K * n_item, d), dtype=torch.float32, device=device)
+    Z = torch.empty((2, tot_p + K * n_item, d), dtype=torch.float32, device=device)
+    sse = torch.empty((K, max(1, epochs)), dtype=torch.float64, device=device)
+
+    def init():
+        W.normal_(0.0, std, generator=generator)
+        Z.zero_()
+        sse.zero_()
+
+    if not defer_init:
+        init()
     out, o = [], 0
     for j, r in enumerate(rows_P):
         qo = tot_p + j * n_item
         out.append((W[o:o + r], W[qo:qo + n_item],
                     (Z[0, o:o + r], Z[0, qo:qo + n_item], Z[1, o:o + r], Z[1, qo:qo + n_item], sse[j])))
         o += r
-    return out
+    return (out, init) if defer_init else out
 
 
 # ------------------------------------------------------------------------------ evaluation

@@ -230,8 +230,9 @@ class Sisa(Scratch):
                 from .scratch import model_generator
                 from .utils import MF
                 rows = [len(self.group_index[i]) if compact else self.n_user for i in mine]
-                views = kn.alloc_shard_batch(rows, self.n_item, self.k, E, self.device,
-                                             model_generator(self.seed, mine[0] + 1, self.device))
+                views, init_models = kn.alloc_shard_batch(rows, self.n_item, self.k, E, self.device,
+                                                          model_generator(self.seed, mine[0] + 1, self.device),
+                                                          defer_init=True)
             t_a = time.time()
             uploaded()
             for j, i in enumerate(mine):
@@ -248,7 +249,10 @@ class Sisa(Scratch):
                                             perm=ld.explicit_perm(self.device, E), scratch=scratch))
             batch = train_dlist[mine[0]].batch_size
             t_b = time.time()
-            sb = kn.ShardBatch(states, self.k, batch, self.lr, self.lr_decay, 50, self.lam, self.momentum)
+            # default init: the normal_ / zero fills are queued behind the owner set-up's sorts (which only read
+            # the records), so the GPU sorts while the host is still launching
+            sb = kn.ShardBatch(states, self.k, batch, self.lr, self.lr_decay, 50, self.lam, self.momentum,
+                               after_prepare=init_models if batched else None)
             self.timing['setup_alloc_ms'] = (t_a - t0) * 1e3
             self.timing['setup_upload_states_ms'] = (t_b - t_a) * 1e3
             self.timing['setup_batch_ms'] = (time.time() - t_b) * 1e3

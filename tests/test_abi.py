@@ -6,6 +6,8 @@ import re
 import subprocess
 import sys
 
+import numpy as np
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -80,3 +82,42 @@ def test_host_read_rating_matches_oracle():
         assert [list(a) for a in gidx] == [list(a) for a in ridx]
         for a, b in zip(got, ref):
             assert a.shape == b.shape and np.array_equal(a, b)
+
+
+def test_device_rating_data_host_views_match_host_read_rating():
+    """The host-side views of a device-backed RatingData (users / items / ratings / _raw, rebuilt on demand from the
+    source table without touching the device) equal what readRating returns for the same groups and deletions."""
+    import pandas as pd
+    import torch
+    from ultrare_b200.read import DeviceRatingData, readRating
+    rng = np.random.default_rng(9)
+    n_user, n = 90, 4000
+    df = pd.DataFrame({0: rng.integers(0, n_user, n), 1: rng.integers(0, 40, n), 2: rng.integers(1, 6, n)})
+    del_user = [3, 17, 42]
+    host, groups = readRating(df, n_user, 5, del_user, [], 4, [], 'a')
+    owner = np.full(n_user, -1, dtype=np.int32)
+    for g in range(3, -1, -1):
+        owner[np.asarray(groups[g])] = g
+    deleted = np.zeros(n_user, dtype=np.uint8)
+    deleted[del_user] = 1
+    src = (df, owner, deleted, 5.0)
+    for g in range(4):
+        ds = DeviceRatingData(torch.zeros((host[g].shape[1], 4), dtype=torch.int32), src, (g, g + 1))
+        assert len(ds) == host[g].shape[1]
+        assert np.array_equal(ds._raw, host[g])
+        assert np.array_equal(ds.users, host[g][0].astype(int)) and np.array_equal(ds.items, host[g][1].astype(int))
+        assert np.array_equal(ds.ratings, host[g][2])
+    total = DeviceRatingData(torch.zeros((sum(h.shape[1] for h in host), 4), dtype=torch.int32), src, (0, 4))
+    assert np.array_equal(total._raw, np.hstack(host))
+
+
+def test_pack_threads_follow_ranks_per_node(monkeypatch):
+    from ultrare_b200 import kernels as kn
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 8)
+    monkeypatch.delenv("URE_PACK_THREADS", raising=False)
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "1")
+    assert kn._default_pack_threads() == max(1, min(8, cores - 1))
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", str(cores))
+    assert kn._default_pack_threads() == 1
+    monkeypatch.setenv("URE_PACK_THREADS", "5")
+    assert kn._default_pack_threads() == 5

@@ -121,3 +121,19 @@ def test_pack_threads_follow_ranks_per_node(monkeypatch):
     assert kn._default_pack_threads() == 1
     monkeypatch.setenv("URE_PACK_THREADS", "5")
     assert kn._default_pack_threads() == 5
+
+
+def test_cli_keeps_the_reference_flags_defaults_and_checks():
+    """main.py's argparse surface (reference main.py:5-14): same flags, same defaults, AssertionError on the values
+    the reference's asserts reject (main.py:21-53)."""
+    import pytest
+    from ultrare_b200.main import _checked, parser
+    d = vars(parser.parse_args([]))
+    assert {k: d[k] for k in ('dataset', 'epoch', 'worker', 'verbose', 'group', 'layer', 'learn', 'delper', 'deltype')} == \
+        dict(dataset='ml1m', epoch=50, worker=24, verbose=1, group=2, layer=[64, 32], learn='sisa', delper=2,
+             deltype='rand')
+    ok = _checked(parser.parse_args('--dataset ml1m --epoch 50 --group 5 --learn sisa --delper 5 --deltype rand'.split()))
+    assert ok.group == 5 and ok.delper == 5
+    for bad in ('--delper 3', '--epoch 0', '--verbose 7', '--learn seq', '--deltype core', '--group -1', '--dataset ml20m'):
+        with pytest.raises(AssertionError):
+            _checked(parser.parse_args(bad.split()))

@@ -1,64 +1,65 @@
-"""B200 mirror of the reference's main.py: identical argparse surface and dispatch
-(main.py:5-14,17-70), plus optional flags whose defaults preserve the reference behaviour.
+"""Command line of the drop-in: the reference's flags with the reference's defaults and value checks
+(reference main.py:5-14 flags, :21-53 checks, :56-70 dispatch), plus two optional flags whose defaults keep the
+reference behaviour.  `python main.py --dataset ml1m --epoch 50 --group 5 --learn sisa --delper 2 --deltype rand`
 """
 import argparse
+import os
 
-parser = argparse.ArgumentParser()
-parser.add_argument('--dataset', type=str, default='ml1m', help='dataset name')
-parser.add_argument('--epoch', type=int, default=50, help='number of epochs')
-parser.add_argument('--worker', type=int, default=24, help='number of CPU workers')
-parser.add_argument('--verbose', type=int, default=1, help='verbose type')
-parser.add_argument('--group', type=int, default=2, help='number of groups')
-parser.add_argument('--layer', nargs='+', type=int, default=[64, 32], help='setting of layers')   # Appendix A12
-parser.add_argument('--learn', type=str, default='sisa', help='type of learning and unlearning')
-parser.add_argument('--delper', type=int, default=2, help='deleted user proportion')
-parser.add_argument('--deltype', type=str, default='rand', help='deletion type')
-# additions (not in the reference)
-parser.add_argument('--synth', action='store_true',
-                    help='write a deterministic synthetic ML-1M-shaped data/ml1m/squ0_{train,test}.csv if absent')
-parser.add_argument('--epoch-eval', type=str, default=None, choices=['faithful', 'final', 'none'],
-                    help='per-epoch in-training evaluation fidelity of the SISA path')
+# flag -> (type, default, help, accepted values or predicate); Appendix A12: --layer parses integers
+_FLAGS = {
+    'dataset': (str, 'ml1m', 'dataset name', ('ml1m', 'toy')),
+    'epoch': (int, 50, 'number of epochs', lambda v: v > 0),
+    'worker': (int, 24, 'number of CPU workers', lambda v: v > 0),
+    'verbose': (int, 1, 'verbose type', (0, 1, 2)),
+    'group': (int, 2, 'number of groups', lambda v: v >= 0),
+    'learn': (str, 'sisa', 'type of learning and unlearning', ('sisa',)),
+    'delper': (int, 2, 'deleted user proportion', (2, 5)),
+    'deltype': (str, 'rand', 'deletion type', ('rand',)),
+}
+GROUP_TYPES = ('emb-ot',)                      # the only grouping the reference's CLI reaches (main.py:64)
+
+
+def _build_parser():
+    p = argparse.ArgumentParser(description=__doc__.split('\n')[0])
+    for name, (typ, default, text, _) in _FLAGS.items():
+        p.add_argument('--' + name, type=typ, default=default, help=text)
+    p.add_argument('--layer', nargs='+', type=int, default=[64, 32], help='setting of layers')
+    # not in the reference
+    p.add_argument('--synth', action='store_true',
+                   help='write a deterministic synthetic ML-1M-shaped data/ml1m/squ0_{train,test}.csv if absent')
+    p.add_argument('--epoch-eval', default=None, choices=['faithful', 'final', 'none'],
+                   help='per-epoch in-training evaluation fidelity of the SISA path')
+    return p
+
+
+parser = _build_parser()
+
+
+def _checked(args):
+    """The reference validates with bare asserts; keep AssertionError as the failure mode."""
+    for name, (_, _, _, ok) in _FLAGS.items():
+        v = getattr(args, name)
+        assert ok(v) if callable(ok) else v in ok, f'--{name} {v!r} is not accepted'
+    assert all(isinstance(w, int) for w in args.layer)
+    return args
 
 
 def main(argv=None):
-    args = parser.parse_args(argv)
-    assert args.dataset in ['ml1m', 'toy']
-    dataset = args.dataset
-    assert args.epoch > 0
-    epochs = args.epoch
-    assert args.worker > 0
-    n_worker = args.worker
-    assert args.verbose in [0, 1, 2]
-    verbose = args.verbose
-    assert args.group >= 0
-    n_group = args.group
-    for i in args.layer:
-        assert type(i) == int
-    layers = args.layer
-    assert args.learn in ['sisa']
-    learn_type = args.learn
-    assert args.delper in [2, 5]
-    del_per = args.delper
-    assert args.deltype in ['rand']
-    del_type = args.deltype
-
-    import os
-    if args.epoch_eval:
-        os.environ['ULTRARE_EPOCH_EVAL'] = args.epoch_eval
+    a = _checked(parser.parse_args(argv))
+    if a.epoch_eval:
+        os.environ['ULTRARE_EPOCH_EVAL'] = a.epoch_eval
     from . import dist as udist
     udist.init_from_env()
     from .config import InsParam, Instance
-    if args.synth:
+    if a.synth:
         from . import synth
-        synth.ensure_dataset(dataset)
-
-    param = InsParam(dataset, epochs, n_worker, layers, n_group, del_per, del_type)
-    ins = Instance(param)
-    if n_group == 0:
-        ins.runFull(is_save=True, verbose=verbose)
-    else:
-        for group_type in ['emb-ot']:
-            ins.runGroup(is_save=True, learn_type=learn_type, group_type=group_type, n_group=n_group, verbose=verbose)
+        synth.ensure_dataset(a.dataset)
+    ins = Instance(InsParam(a.dataset, a.epoch, a.worker, a.layer, a.group, a.delper, a.deltype))
+    if a.group == 0:
+        ins.runFull(is_save=True, verbose=a.verbose)
+        return ins
+    for group_type in GROUP_TYPES:
+        ins.runGroup(is_save=True, learn_type=a.learn, group_type=group_type, n_group=a.group, verbose=a.verbose)
     return ins
 
 

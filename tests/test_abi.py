@@ -137,3 +137,26 @@ def test_cli_keeps_the_reference_flags_defaults_and_checks():
     for bad in ('--delper 3', '--epoch 0', '--verbose 7', '--learn seq', '--deltype core', '--group -1', '--dataset ml20m'):
         with pytest.raises(AssertionError):
             _checked(parser.parse_args(bad.split()))
+
+
+def test_instance_read_data_host_branch(tmp_path, monkeypatch):
+    """Instance._read_data without a CUDA device (or with URE_HOST_INGEST=1) is the host split of `_read`
+    (config.py:80-96): RatingData per group, the merged test set = their concatenation."""
+    import ultrare_b200.config as cfg
+    import ultrare_b200.group as grp
+    from ultrare_b200 import synth
+    data, save = str(tmp_path / "data"), str(tmp_path / "result")
+    for mod in (cfg, grp):
+        monkeypatch.setattr(mod, "DATA_DIR", data)
+        monkeypatch.setattr(mod, "SAVE_DIR", save)
+    monkeypatch.setenv("URE_HOST_INGEST", "1")
+    synth.ensure_dataset("toy")
+    ins = cfg.Instance(cfg.InsParam("toy", 2, 1, [32], 3, 2, "rand"))
+    train, idx, test, total = ins._read_data(True, 3, [])
+    raw_train, raw_idx, raw_test = ins._read(True, 3, [])
+    assert [list(g) for g in idx] == [list(g) for g in raw_idx] and len(train) == len(test) == 3
+    for g in range(3):
+        assert np.array_equal(train[g]._raw, raw_train[g]) and np.array_equal(test[g]._raw, raw_test[g])
+    assert len(total) == sum(len(t) for t in test) and np.array_equal(total._raw, np.hstack(raw_test))
+    deleted = set(int(u) for u in ins.param.del_user)
+    assert not deleted & set(int(u) for t in train for u in np.unique(t.users))

@@ -381,3 +381,26 @@ def test_sisa_full_size_ml1m_unlearn_properties(cuda_dev):
     assert abs(got['total_rmse'] - rmse) < 1e-4 * rmse
     assert abs(got['total_ndcg'] - ndcg) < 1e-4 and abs(got['total_hr'] - hr) < 1e-4
     assert got['total_rmse'] != log_learn['total_rmse']
+
+
+@pytest.mark.gpu
+def test_instance_read_data_device_equals_host_branch(toy, cuda_dev, tmp_path, monkeypatch):
+    """Instance._read_data: the device ingest (default) and the host split (URE_HOST_INGEST=1) give the same group
+    order and bit-equal records per group, for the deletion-filtered training read and the test read."""
+    import ultrare_b200.config as cfg
+    import ultrare_b200.group as grp
+    from ultrare_b200 import synth
+    data, save = str(tmp_path / "data"), str(tmp_path / "result")
+    for mod in (cfg, grp):
+        monkeypatch.setattr(mod, "DATA_DIR", data)
+        monkeypatch.setattr(mod, "SAVE_DIR", save)
+    synth.ensure_dataset("toy")
+    ins = cfg.Instance(cfg.InsParam("toy", 2, 1, [32], 4, 2, "rand"))
+    monkeypatch.setenv("URE_HOST_INGEST", "0")
+    d_train, d_idx, d_test, d_total = ins._read_data(True, 4, [])
+    monkeypatch.setenv("URE_HOST_INGEST", "1")
+    h_train, h_idx, h_test, h_total = ins._read_data(True, 4, [])
+    assert [list(g) for g in d_idx] == [list(g) for g in h_idx]
+    for a, b in list(zip(d_train, h_train)) + list(zip(d_test, h_test)) + [(d_total, h_total)]:
+        assert len(a) == len(b) > 0
+        assert torch.equal(a.records(cuda_dev), b.records(cuda_dev))

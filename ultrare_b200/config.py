@@ -100,7 +100,7 @@ class Instance(object):
     def _read_data(self, is_del=False, n_group=1, group_index=[]):
         import torch
         if os.environ.get('URE_HOST_INGEST', '0') == '1' or not torch.cuda.is_available():
-            train, train_index, test, test_total = self._read_data(is_del, n_group, group_index)
+            train_rating, train_index, test_rating = self._read(is_del, n_group, group_index)
             return ([RatingData(r) for r in train_rating], train_index, [RatingData(r) for r in test_rating],
                     RatingData(np.hstack(test_rating)))
         del_user = self.param.del_user if is_del == True else []

@@ -404,3 +404,35 @@ def test_instance_read_data_device_equals_host_branch(toy, cuda_dev, tmp_path, m
     for a, b in list(zip(d_train, h_train)) + list(zip(d_test, h_test)) + [(d_total, h_total)]:
         assert len(a) == len(b) > 0
         assert torch.equal(a.records(cuda_dev), b.records(cuda_dev))
+
+
+@pytest.mark.gpu
+def test_ot_cluster_redoes_a_failed_warm_start_from_cold(cuda_dev, monkeypatch):
+    """ot_cluster_device warm-starts Sinkhorn from the previous outer iteration's potentials.  If such a solve ends
+    with an assignment far from n/k users per centroid (seen on the ml1m CLI flow: a centroid's column sum
+    underflowed, every user landed on centroid 0, the centroids became NaN), the iteration is solved again from a
+    cold start.  Here every warm-started solve is sabotaged; the result must still be a balanced grouping."""
+    from ultrare_b200 import kernels as kn
+    from ultrare_b200.method import utils as mu
+    rng = np.random.default_rng(5)
+    n, k = 3000, 5
+    X = rng.standard_normal((n, 16)).astype(np.float32)
+    real = kn.sinkhorn
+    calls = {"warm": 0, "cold": 0}
+
+    def flaky(M, k_, sched, g=None, tol=0.0):
+        out = real(M, k_, sched, g=g, tol=tol)
+        if g is None:
+            calls["cold"] += 1
+            return out
+        calls["warm"] += 1
+        out = out.clone()
+        out[0] = 1e6                       # potentials that send every user to centroid 0
+        return out
+
+    monkeypatch.setattr(kn, "sinkhorn", flaky)
+    inertia, label, cen, it = mu.ot_cluster_device(X, k, max_iters=3, centroid0=X[:k].copy())
+    assert it >= 2 and calls["warm"] == it - 1 and calls["cold"] == it     # the first solve + every redone iteration
+    cnt = np.bincount(label, minlength=k)
+    assert cnt.min() > 0.9 * n / k and cnt.max() < 1.1 * n / k
+    assert np.isfinite(cen).all() and np.isfinite(inertia)

@@ -228,6 +228,9 @@ SINKHORN_TOL = 2e-5
 # Outer iterations after the first start from the previous potentials (the fixed point at a given eps does
 # not depend on the start) and run only the last WARM_STAGES stages of the schedule.
 SINKHORN_WARM_STAGES = 2
+# ... unless the assignment that comes out is further than this from n/k users per centroid (relative): then the
+# iteration is solved again from a cold start (see ot_cluster_device)
+WARM_START_MAX_IMBALANCE = 0.25
 
 
 def ot_cluster_device(X, k, max_iters=10, schedule=SINKHORN_SCHEDULE, centroid0=None, device=None, dist=None,
@@ -267,25 +270,39 @@ def ot_cluster_device(X, k, max_iters=10, schedule=SINKHORN_SCHEDULE, centroid0=
         inertia = float(inert.item())
         scale = max(inertia / n, 1e-30)
         warm = warm_start and it > 1
-        sched = [(e * scale, i) for e, i in (schedule[-SINKHORN_WARM_STAGES:] if warm else schedule)]
-        if dist is None or dist.world == 1:
-            g = kn.sinkhorn(M, k, sched, g=g if warm else None, tol=tol)    # replaces ot.emd, utils.py:641-644
-        else:
-            if not warm:
-                g = torch.zeros(k, dtype=torch.float32, device=dev)
-            colsum = torch.zeros(M.shape[1], dtype=torch.float64, device=dev)
-            for eps, iters in sched:
-                for _ in range(iters):
-                    kn.sinkhorn_colsum(M, k, g, eps, n, colsum)
-                    dist.all_reduce(colsum)
-                    kn.sinkhorn_update_g(g, colsum, k, eps)
-        lab, sums, cnt = kn.assign_centroids(M, k, g, Xd)                   # utils.py:647-648
-        if dist is not None and dist.world > 1:
-            dist.all_reduce(sums)
-            dist.all_reduce(cnt)
+
+        def solve(warm, g):
+            """Sinkhorn potentials for this cost matrix + the assignment they induce (counts / sums over all ranks)."""
+            sched = [(e * scale, i) for e, i in (schedule[-SINKHORN_WARM_STAGES:] if warm else schedule)]
+            if dist is None or dist.world == 1:
+                g = kn.sinkhorn(M, k, sched, g=g if warm else None, tol=tol)    # replaces ot.emd, utils.py:641-644
+            else:
+                g = g.clone() if warm else torch.zeros(k, dtype=torch.float32, device=dev)
+                colsum = torch.zeros(M.shape[1], dtype=torch.float64, device=dev)
+                for eps, iters in sched:
+                    for _ in range(iters):
+                        kn.sinkhorn_colsum(M, k, g, eps, n, colsum)
+                        dist.all_reduce(colsum)
+                        kn.sinkhorn_update_g(g, colsum, k, eps)
+            lab, sums, cnt = kn.assign_centroids(M, k, g, Xd)                   # utils.py:647-648
+            if dist is not None and dist.world > 1:
+                dist.all_reduce(sums)
+                dist.all_reduce(cnt)
+            return g, lab, sums, cnt
+
+        g_new, lab, sums, cnt = solve(warm, g)
+        cnt_h = cnt.cpu().numpy()
+        if warm and np.abs(cnt_h[:k] - n / k).max() > WARM_START_MAX_IMBALANCE * n / k:
+            # The warm start skips the large-eps stages.  When the centroids moved far (early outer iterations from a
+            # random-user start) the old potentials can leave a centroid without any mass at the small eps: its fp32
+            # column sum underflows to zero, the potential diverges and every user lands on one centroid.  A balanced
+            # plan gives every centroid n/k users, so an assignment this far off is redone from a cold start.
+            g_new, lab, sums, cnt = solve(False, None)
+            cnt_h = cnt.cpu().numpy()
+        g = g_new
         label = lab
         with np.errstate(invalid="ignore", divide="ignore"):
-            new_centroid = (sums.cpu().numpy()[:, :d] / cnt.cpu().numpy()[:, None]).astype(np.float32)
+            new_centroid = (sums.cpu().numpy()[:, :d] / cnt_h[:, None]).astype(np.float32)
         if np.allclose(centroid, new_centroid):                              # utils.py:651
             break
         centroid = new_centroid

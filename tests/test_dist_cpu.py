@@ -163,3 +163,48 @@ def test_row_sharded_evaluation_equals_single_process():
         assert o["users"] == o["users_ref"]
         assert abs(o["rmse"] - o["ref"][0]) < 1e-6 and abs(o["ndcg"] - o["ref"][1]) < 1e-6
         assert abs(o["hr"] - o["ref"][2]) < 1e-6
+
+
+def test_ot_cluster_host_loop_with_oracle_kernels(monkeypatch):
+    """The host loop of ot_cluster_device (outer iterations, warm start, the cold re-solve of an iteration whose
+    warm-started assignment is far from n/k users per centroid) with the three kernels it calls stood in by the
+    oracle's arithmetic: what is under test is the control flow, not the CUDA code (tests/test_gpu_surface.py)."""
+    from oracle import ot as oot
+    from ultrare_b200 import kernels as kn
+    from ultrare_b200.method import utils as mu
+    monkeypatch.setattr(mu, "_cuda_device", lambda device=None: torch.device("cpu"))
+
+    def cost_matrix(Xd, Cd, want_inertia=False):
+        M = ((Xd[:, None, :].double() - Cd[None, :, :].double()) ** 2).sum(-1).float()
+        return M, M.min(1).values.double().sum().reshape(1)
+
+    calls = {"warm": 0, "cold": 0, "sabotage": False}
+
+    def sinkhorn(M, k, sched, g=None, tol=0.0):
+        _, _, gg, _ = oot.sinkhorn_log(M.numpy()[:, :k], sched, g0=None if g is None else g.numpy())
+        out = torch.from_numpy(gg.astype(np.float32))
+        calls["cold" if g is None else "warm"] += 1
+        if g is not None and calls["sabotage"]:
+            out[0] = 1e6
+        return out
+
+    def assign_centroids(M, k, g, X):
+        lab = torch.argmax(g[None, :k] - M[:, :k], dim=1).to(torch.int32)
+        cnt = torch.bincount(lab.long(), minlength=k)
+        sums = torch.zeros((k, X.shape[1]), dtype=torch.float64)
+        sums.index_add_(0, lab.long(), X.double())
+        return lab, sums, cnt
+
+    monkeypatch.setattr(kn, "cost_matrix", cost_matrix)
+    monkeypatch.setattr(kn, "sinkhorn", sinkhorn)
+    monkeypatch.setattr(kn, "assign_centroids", assign_centroids)
+    rng = np.random.default_rng(2)
+    n, k = 600, 4
+    X = rng.standard_normal((n, 8)).astype(np.float32)
+    for sabotage in (False, True):
+        calls.update(warm=0, cold=0, sabotage=sabotage)
+        inertia, label, cen, it = mu.ot_cluster_device(X, k, max_iters=3, centroid0=X[:k].copy())
+        cnt = np.bincount(label, minlength=k)
+        assert cnt.sum() == n and cnt.min() > 0.8 * n / k and cnt.max() < 1.2 * n / k, (sabotage, cnt)
+        assert np.isfinite(cen).all() and np.isfinite(inertia) and label.dtype == np.int64
+        assert calls["warm"] == it - 1 and calls["cold"] == (it if sabotage else 1)

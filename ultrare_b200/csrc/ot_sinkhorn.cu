@@ -19,6 +19,13 @@
 namespace ure {
 namespace {
 
+// Column sums below this are treated as this in the potential update.  A column can sum to exactly zero in fp32 when
+// the potentials are stale (a warm start after the centroids moved) and eps is small: every exp((g_j - M_ij)/eps -
+// rowmax) underflows.  log(0) would send g_j to infinity for good; with the floor the column gains 87 eps per
+// iteration until its entries are representable again, after which the update is the exact one.  Never active on a
+// column that holds any mass (a healthy column sums to ~1/k).
+constexpr double kMinColSum = 1e-38;
+
 constexpr float kLog2e = 1.4426950408889634f;
 
 // 2^x for x <= 0 (after the max shift): one MUFU, flush-to-zero; relative error 2^-22
@@ -152,7 +159,7 @@ __global__ void update_g_kernel(float* g, double* colsum, int k, float eps) {
   const int j = threadIdx.x;
   if (j < k) {
     const double c = colsum[j];
-    g[j] = (float)((double)g[j] + (double)eps * (-log((double)k) - log(c)));
+    g[j] = (float)((double)g[j] + (double)eps * (-log((double)k) - log(fmax(c, kMinColSum))));
     colsum[j] = 0.0;
   }
 }
@@ -213,7 +220,7 @@ sinkhorn_kernel(const float* __restrict__ M, long long n, int k, float* __restri
       __syncthreads();
       for (int j = tid; j < k; j += blockDim.x) {
         const double c = __ldcg(cs + j);
-        g_sh[j] = (float)((double)g_sh[j] + (double)eps * (logb - log(c)));
+        g_sh[j] = (float)((double)g_sh[j] + (double)eps * (logb - log(fmax(c, kMinColSum))));
         if (blockIdx.x == 0) ws->colsum[(it_global + 2) % 3][j] = 0.0;
         const float e = (float)(fabs(c * (double)k - 1.0));
         atomicMax(reinterpret_cast<int*>(&err_sh), __float_as_int(e));       // e >= 0: int order == float order
@@ -282,7 +289,7 @@ sinkhorn_cluster_kernel(const float* __restrict__ M, long long n, int k, float* 
       if (tid < k) {
         double c = 0.0;
         for (int r = 0; r < CS; ++r) c += (double)slots[par][r][tid];       // same order in every CTA
-        g_sh[tid] = (float)((double)g_sh[tid] + (double)eps * (logb - log(c)));
+        g_sh[tid] = (float)((double)g_sh[tid] + (double)eps * (logb - log(fmax(c, kMinColSum))));
         const float e = (float)(fabs(c * (double)k - 1.0));
         atomicMax(reinterpret_cast<int*>(&err_sh), __float_as_int(e));       // e >= 0: int order == float order
       }

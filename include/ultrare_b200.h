@@ -138,7 +138,7 @@ int ure_mf_train(const ure_mf_shard_t* d_shards, int n_shards, const ure_mf_hpar
  * training is reproducible bit for bit) and perm_inv for shards with an explicit perm, then plans the CTA ownership and writes into the first 16 bytes of d_workspace
  * int32 {max owned rows of a CTA, max owned interactions of a CTA, max steps per epoch of a shard,
  * dynamic shared-memory bytes available}: the caller reads them back once, fills hparams.owner_cap_rows /
- * owner_cap_slots / owner_spe_cap / owner_flags, allocates the schedule tables, and must not start mode OWNER
+ * owner_cap_slots / owner_cap_list / owner_spe_cap / owner_flags, allocates the schedule tables, and must not start mode OWNER
  * when ure_mf_owner_smem_bytes exceeds what is available (ure_mf_train refuses it loudly as well). */
 int64_t ure_mf_owner_radix_bytes(int n_shards);     /* size of d_radix_hist below */
 int ure_mf_owner_prepare(const ure_mf_shard_t* d_shards, int n_shards, const ure_mf_hparams_t* h_hp,
@@ -146,7 +146,9 @@ int ure_mf_owner_prepare(const ure_mf_shard_t* d_shards, int n_shards, const ure
                          int32_t* d_radix_hist, void* d_workspace, void* stream);
 
 /* Dynamic shared memory per CTA the OWNER schedule needs for these capacities (training kernel and
- * schedule pre-pass, whichever is larger). */
+ * schedule pre-pass, whichever is larger).  flags as hparams.owner_flags; cap_list as hparams.owner_cap_list: with
+ * bit 0 (record cache) it must equal cap_slots, without it 10 bytes are needed per staged list entry, so a caller
+ * short of shared memory lowers cap_list (batch lists longer than it are read from the schedule table). */
 int64_t ure_mf_owner_smem_bytes(int d, int cap_rows, int cap_slots, int cap_list, int spe_cap, int flags);
 
 /* OWNER mode, before ure_mf_train: fill the schedule tables for the window of owner_sched_rows epochs per

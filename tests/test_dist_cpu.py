@@ -165,6 +165,60 @@ def test_row_sharded_evaluation_equals_single_process():
         assert abs(o["hr"] - o["ref"][2]) < 1e-6
 
 
+def _grouping_on_two_ranks(d):
+    """Instance._group_index under torchrun: only rank 0 may cluster / touch the cache file, and both ranks must
+    end with rank 0's grouping (here Group.grouping is stood in by a RANK-DEPENDENT answer)."""
+    import tempfile
+    from ultrare_b200 import config as cfg
+    calls = []
+
+    class FakeGroup:
+        def __init__(self, shape, dataset, user_mat):
+            pass
+
+        def grouping(self, dataset, n_group, var, verbose=True):
+            calls.append(d.rank)
+            rs = np.random.RandomState(100 + d.rank)
+            perm = rs.permutation(40)
+            return [sorted(int(u) for u in perm[i::n_group]) for i in range(n_group)]
+
+    cfg.Group = FakeGroup
+    ins = cfg.Instance.__new__(cfg.Instance)
+    ins.param = type("P", (), dict(n_user=40, n_item=7, dataset="toy"))()
+    ins.timing = {}
+    with tempfile.NamedTemporaryFile(suffix=".npy") as f:
+        np.save(f.name, np.zeros((40, 4), dtype=np.float32))
+        ins._user_mat_path = lambda: f.name
+        g = ins._group_index("emb-ot", 4)
+        u = ins._group_index("uniform", 4)
+    return dict(rank=d.rank, calls=calls, groups=g, uniform=u)
+
+
+def test_grouping_is_computed_on_rank0_and_identical_on_every_rank():
+    out = _run(_grouping_on_two_ranks)
+    assert out[0]["calls"] == [0] and out[1]["calls"] == []
+    assert out[0]["groups"] == out[1]["groups"] and len(out[0]["groups"]) == 4
+    assert sorted(u for g in out[1]["groups"] for u in g) == list(range(40))
+    assert out[0]["uniform"] == [] and out[1]["uniform"] == []
+
+
+def test_mapped_record_cache_is_keyed_on_the_row_map():
+    """RatingData.records_mapped must not return the rows of an earlier grouping (stale local rows index
+    compact tables out of bounds).  The key carries the map's storage address, version and length."""
+    from ultrare_b200 import read
+    a = torch.arange(10, dtype=torch.int32)
+    b = torch.arange(10, dtype=torch.int32)
+    k1, k2 = read._mapped_key("cpu", "t", a), read._mapped_key("cpu", "t", b)
+    assert k1 != k2 and k1 == read._mapped_key("cpu", "t", a)
+    a[0] = 5                                   # in-place edit bumps the version counter
+    assert read._mapped_key("cpu", "t", a) != k1
+    ds = read.RatingData(np.zeros((3, 4)))
+    ds._records[k1] = "old"
+    ds._maps[k1] = a
+    ds._drop_mapped("cpu", "t")
+    assert k1 not in ds._records and k1 not in ds._maps
+
+
 def test_ot_cluster_host_loop_with_oracle_kernels(monkeypatch):
     """The host loop of ot_cluster_device (outer iterations, warm start, the cold re-solve of an iteration whose
     warm-started assignment is far from n/k users per centroid) with the three kernels it calls stood in by the

@@ -119,6 +119,11 @@ def test_sisa_learn_unlearn_faithful_vs_reference_golden(toy, cuda_dev, tmp_path
         assert np.load(d1 + f"/user_mat{s+1}.npy").shape == (N_USER, 16)
         assert np.load(d1 + f"/item_mat{s+1}.npy").shape == (N_ITEM, 16)
         assert os.path.exists(d1 + f"/model{s+1}.pth") and os.path.exists(d1 + f"/log{s+1}.npy")
+        # log{i}.npy is saved as shard i finishes (scratch.py:144): the accumulated entries of shards 1..i only
+        lg = np.load(d1 + f"/log{s+1}.npy", allow_pickle=True).item()
+        assert all(len(v) == (s + 1) * epochs for v in lg.values()), {k: len(v) for k, v in lg.items()}
+        np.testing.assert_allclose(lg['train_loss'], z["learn_log_train_loss"][:(s + 1) * epochs], rtol=1e-3)
+        np.testing.assert_allclose(lg['total_rmse'], z["learn_log_total_rmse"][:(s + 1) * epochs], rtol=1e-3)
 
     # ---- unlearn
     tl, sl, total, idx2, trr = _sisa_inputs(toy, z, True, 1, K, epochs)

@@ -140,19 +140,31 @@ class Instance(object):
                 return c
         raise FileNotFoundError("user_mat0.npy not found (run `--group 0` first, config.py:132): " + cands[0])
 
+    def _group_index(self, group_type, n_group):
+        """The user grouping of config.py:126-134: [] for 'uniform' (readRating draws it), else Group.grouping.
+        One process per GPU (torchrun): rank 0 alone computes (or loads) the grouping and writes the cache file;
+        every rank then holds the SAME group_index -- the centroid sums are order-dependent fp64 atomics, so two
+        ranks clustering on their own could end with different labels and different owner maps."""
+        if group_type == 'uniform':
+            return []
+        from . import dist as udist
+        d = udist.get()
+        t0 = time.time()
+        group_index = None
+        if d.rank == 0:
+            user_mat = np.load(self._user_mat_path(), allow_pickle=True)
+            shape = type('Shape', (), {'shape': (self.param.n_user, self.param.n_item)})()   # readSparseMat: shapes only
+            group_index = Group(shape, self.param.dataset, user_mat).grouping(self.param.dataset, n_group,
+                                                                               group_type, verbose=False)
+        group_index = d.broadcast_object(group_index, src=0)
+        self.timing['grouping_s'] = time.time() - t0
+        return group_index
+
     # sub function of self.runGroup (config.py:123-174)
     def _group(self, model_list, is_save, learn_type, saving_name, model_type='mf',
                is_del=False, group_type='uniform', n_group=5, verbose=1):
         print(self.name, saving_name, 'begin:')
-        if group_type == 'uniform':
-            group_index = []
-        else:
-            user_mat = np.load(self._user_mat_path(), allow_pickle=True)
-            shape = type('Shape', (), {'shape': (self.param.n_user, self.param.n_item)})()   # readSparseMat: shapes only
-            t0 = time.time()
-            group_index = Group(shape, self.param.dataset, user_mat).grouping(self.param.dataset, n_group,
-                                                                               group_type, verbose=False)
-            self.timing['grouping_s'] = time.time() - t0
+        group_index = self._group_index(group_type, n_group)
 
         train, train_index, test, test_total = self._read_data(is_del, n_group, group_index)
 

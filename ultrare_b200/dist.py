@@ -62,6 +62,14 @@ class Dist:
         self.td.all_reduce(t, op=self.td.ReduceOp.MAX, group=self.group)
         return float(t.item())
 
+    def broadcast_object(self, obj, src: int = 0):
+        """`obj` of rank `src` on every rank (pickled; host-side bookkeeping such as the user grouping)."""
+        if self.world == 1:
+            return obj
+        box = [obj if self.rank == src else None]
+        self.td.broadcast_object_list(box, src=src, group=self.group)
+        return box[0]
+
     def barrier(self):
         if self.world > 1:
             self.td.barrier(group=self.group)

@@ -56,5 +56,7 @@ class Group(object):
             arr = np.empty(n_group, dtype=object)
             for idx in range(n_group):
                 arr[idx] = res[idx]
-            np.save(label_dir, arr)
+            tmp = label_dir + '.tmp%d.npy' % os.getpid()     # atomic: a concurrent reader never sees half a file
+            np.save(tmp, arr)
+            os.replace(tmp, label_dir)
         return res                                                               # Appendix A4

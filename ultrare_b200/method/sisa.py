@@ -381,14 +381,18 @@ class Sisa(Scratch):
             host = kn.download_many(tensors)
             log = {k: list(v) for k, v in self.log.items()}
 
-            def write(ids=list(new), host=host, log=log):
+            # log{i}.npy is written by the reference as shard i finishes (scratch.py:144): it holds the entries
+            # accumulated up to and including shard i's last epoch, not the whole run's log
+            cut = {i: last_idx.get(i, len(log['train_loss']) - 1) + 1 for i in new}
+
+            def write(ids=list(new), host=host, log=log, cut=cut):
                 for j, i in enumerate(ids):
                     P_h, Q_h = host[2 * j], host[2 * j + 1]
                     torch.save({'user_mat.weight': torch.from_numpy(P_h), 'item_mat.weight': torch.from_numpy(Q_h)},
                                save_dir + '/model' + str(i + 1) + '.pth')
                     np.save(save_dir + '/user_mat' + str(i + 1), P_h)
                     np.save(save_dir + '/item_mat' + str(i + 1), Q_h)
-                    np.save(save_dir + '/log' + str(i + 1), log)
+                    np.save(save_dir + '/log' + str(i + 1), {k: v[:cut[i]] for k, v in log.items()})
 
             self._writers.append(_writer_pool().submit(write))
 

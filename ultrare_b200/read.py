@@ -117,6 +117,13 @@ def sort_group(order='a', group_index=[], var='count', ratings0=[], dataset='ml1
     return np.argsort(sort_value)[::-1]
 
 
+def _mapped_key(device, tag, row_of):
+    """Cache key of records whose user field went through `row_of`: the map's identity (storage address + version
+    counter) is part of it, so a loader reused with ANOTHER grouping never returns rows of the previous one (the
+    kernels index compact tables with these rows and do no bounds check)."""
+    return (str(device), tag, int(row_of.data_ptr()), int(row_of._version), int(row_of.shape[0]))
+
+
 class RatingData:
     """reference read.py:108-124: users/items int, ratings float (already / max_rating)."""
 
@@ -126,6 +133,7 @@ class RatingData:
         self._cols = {}
         self._records = {}
         self._segments = {}
+        self._maps = {}
 
     def _col(self, j, dtype):
         if j not in self._cols:               # the reference's eager casts (read.py:111-113), done on demand
@@ -154,17 +162,28 @@ class RatingData:
     def records_mapped(self, device, row_of: torch.Tensor, tag: str) -> torch.Tensor:
         """Records whose user field is row_of[user] (the row inside a compact per-shard user table);
         row_of: int32 tensor on `device`, applied by the pack kernel."""
-        key = (str(device), tag)
+        key = _mapped_key(device, tag, row_of)
         if key not in self._records:
+            self._drop_mapped(device, tag)
             self._records[key] = kn.upload_interactions(self._raw, device, row_of)
+            self._keep_map(key, row_of)
         return self._records[key]
+
+    def _drop_mapped(self, device, tag):
+        """Forget the records mapped through an earlier row_of (one mapped copy per (device, tag) is kept)."""
+        for k in [k for k in self._records if isinstance(k, tuple) and k[:2] == (str(device), tag)]:
+            del self._records[k]
+            self._maps.pop(k, None)
+
+    def _keep_map(self, key, row_of):
+        self._maps[key] = row_of              # holds the tensor: its address cannot be reused while the key lives
 
     @staticmethod
     def upload_many(datasets, device, row_of=None, tag=None, defer=False):
         """records()/records_mapped() of several datasets at once: their host copies run in parallel.
         defer=True: the copies are started and a `finish()` callable is returned; the records are registered (and
         the uploads queued) when it is called."""
-        key = str(device) if tag is None else (str(device), tag)
+        key = str(device) if tag is None else _mapped_key(device, tag, row_of)
         for ds in datasets:
             if isinstance(ds, DeviceRatingData):
                 ds.records(device) if tag is None else ds.records_mapped(device, row_of, tag)
@@ -174,6 +193,9 @@ class RatingData:
         def finish():
             fin()
             for ds, rec in zip(todo, recs):
+                if tag is not None:
+                    ds._drop_mapped(device, tag)
+                    ds._keep_map(key, row_of)
                 ds._records[key] = rec
 
         if defer:
@@ -208,7 +230,7 @@ class DeviceRatingData(RatingData):
         self._dev = records
         self._src, self._groups = src, groups
         self._n = int(records.shape[0])
-        self._cols, self._segments = {}, {}
+        self._cols, self._segments, self._maps = {}, {}, {}
         self._records = {str(records.device): records}
 
     def _rows(self):
@@ -246,9 +268,11 @@ class DeviceRatingData(RatingData):
         return self._records[key]
 
     def records_mapped(self, device, row_of, tag):
-        key = (str(device), tag)
+        key = _mapped_key(device, tag, row_of)
         if key not in self._records:
+            self._drop_mapped(device, tag)
             self._records[key] = kn.remap_users(self.records(device).contiguous(), row_of)
+            self._keep_map(key, row_of)
         return self._records[key]
 
 

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define URE_ABI_VERSION 3
+#define URE_ABI_VERSION 4
 #define URE_MAX_SHARDS 256        /* shard models batched in one launch           */
 #define URE_TOP_K 10              /* baseTest(top_k=10), method/utils.py:115      */
 
@@ -98,7 +98,8 @@ typedef struct {
   int64_t owner_sched_stride; /* OWNER: slots of one schedule row = sum over the shards of 2 n       */
   int32_t owner_cap_list;  /* OWNER: batch-list entries a CTA stages in shared memory (multiple of 16, <=
                             * owner_cap_slots); a longer list is read from the schedule table directly  */
-  int32_t owner_reserved;
+  int32_t owner_max_n;     /* OWNER: largest shard size n (sizes the round tables of the short-epoch schedule
+                            * pre-pass); 0 = always use the general pre-pass                                */
 } ure_mf_hparams_t;
 
 /* ure_mf_hparams_t::mode -- three schedules of the SAME arithmetic (baseTrain + dense optim.SGD):
@@ -160,6 +161,56 @@ int64_t ure_mf_owner_smem_bytes(int d, int cap_rows, int cap_slots, int cap_list
  * word (int32 at byte 16). */
 int ure_mf_owner_schedule(const ure_mf_shard_t* d_shards, int n_shards, const ure_mf_hparams_t* h_hp,
                           int epochs, int64_t step0, void* stream);
+
+/* ---- Native host runtime of a K-shard training batch (replaces the per-shard Python bookkeeping of the K
+ * sequential Scratch.train set-ups, method/sisa.py:33-36, 86-89 -> scratch.py:59-69) ------------------------------
+ * One device allocation of the caller (the "arena") holds everything the batch needs; the library lays it out,
+ * writes the descriptor table, clears what must start at zero and queues the owner set-up; nothing is allocated by
+ * the library and nothing synchronises. */
+typedef struct {
+  const ure_inter_t* inter; /* DEVICE records of the shard; the user field is the row in the shard's user table   */
+  const int32_t* perm;      /* DEVICE explicit visiting orders [epochs][n], or NULL (keyed Feistel permutation)    */
+  int32_t n;                /* interactions                                                                        */
+  int32_t n_user;           /* rows of the shard's user table                                                      */
+  int32_t shard_id;         /* Feistel key component (model id, method/sisa.py:35)                                 */
+  int32_t group;            /* warp group of the DENSE schedule (ure_mf_train)                                     */
+} ure_mf_batch_shard_t;
+
+typedef struct {            /* byte offsets into the arena (multiples of 256) and the numbers they were sized from */
+  int64_t total;            /* bytes the caller allocates                                                          */
+  int64_t table;            /* ure_mf_shard_t [K]: the descriptor table ure_mf_train / ure_mf_owner_* take         */
+  int64_t ws;               /* ure_mf_train_workspace_bytes()                                                      */
+  int64_t W;                /* fp32 [rows_total + K*n_item, d]: user tables of shard 0..K-1, then the K item tables */
+                            /* -- the CALLER fills it (N(0,1) init, method/utils.py:38-40) before ure_mf_train     */
+  int64_t Z;                /* fp32 [2][rows_total + K*n_item, d]: momentum, gradient scratch (zeroed by setup)    */
+  int64_t sse;              /* fp64 [K][max(1, epochs)] (zeroed by setup)                                          */
+  int64_t zero_end;         /* end of the region setup clears                                                     */
+  int64_t rec, off, radix, perm_inv, sched, sched_off;   /* owner schedule only                                   */
+  int64_t rows_total, n_total, sched_stride;
+  int32_t spe_cap, max_rows, max_n, grid, owner, sched_rows;
+} ure_mf_batch_layout_t;
+
+/* Layout for these shards.  owner != 0 asks for the OWNER schedule's buffers when the weights + momentum of all rows
+ * can fit the SMs' shared memory (out->owner tells); sched_bytes_cap bounds the schedule tables (>= 2 epochs). */
+int ure_mf_batch_layout(const ure_mf_batch_shard_t* h_shards, int n_shards, int n_item, int d, int batch,
+                        int epochs, int owner, int64_t sched_bytes_cap, ure_mf_batch_layout_t* out);
+
+/* Descriptor table -> arena (through h_stage: page-locked host memory of the caller, >= 176*K + 64 bytes, not to be
+ * reused before the stream has passed this call), clears momentum / gradient scratch / losses / workspace / row
+ * offsets, queues ure_mf_owner_prepare when lay->owner, and queues the copy of the plan (4 int32, see
+ * ure_mf_owner_prepare) to h_stage + 176*K.  The weights (lay->W) are left to the caller. */
+int ure_mf_batch_setup(const ure_mf_batch_shard_t* h_shards, int n_shards, int n_item, const ure_mf_hparams_t* h_hp,
+                       int epochs, uint32_t perm_seed, void* d_arena, const ure_mf_batch_layout_t* lay, void* h_stage,
+                       void* stream);
+
+/* After the stream has passed ure_mf_batch_setup: turn the plan into launch parameters (hp->mode = OWNER, owner_*
+ * capacities, the shared-memory configuration -- record cache first, then staged lists -- and the schedule-table
+ * pointers inside the arena).  Returns 1 when the OWNER schedule can run, 0 when the caller must use DENSE with the
+ * same descriptor table, < 0 on error.  force_flags >= 0 pins the configuration (tests).  h_info (may be NULL):
+ * int32 [8] = {fits, flags, cap_list, cap_rows, cap_slots, spe_cap, smem needed, smem available}. */
+int ure_mf_batch_plan(const int32_t* h_plan, int n_shards, ure_mf_hparams_t* hp, void* d_arena,
+                      const ure_mf_batch_layout_t* lay, int allow_cache, int force_flags, int force_list,
+                      int32_t* h_info);
 
 /* Diagnostics (tracing): record six SM-clock stamps per CTA and step -- step start, tables ready,
  * gradients issued, barrier 1 passed, sweep issued, barrier 2 passed -- for the first `steps` steps of
@@ -250,7 +301,9 @@ int ure_cost_matrix_simt(const float* d_X, int64_t n, int d, const float* d_C, i
 
 /* One Sinkhorn column pass (replaces the ot.emd call, utils.py:641-644):
  * for every row i: P_ij = a_i * softmax_j((g_j - M_ij)/eps);  d_colsum[j] += sum_i P_ij.
- * a_i = 1/n_total.  d_colsum is double [kpad], zero on entry. */
+ * a_i = 1/n_total.  d_colsum is double [kpad], zero on entry.  The sums are accumulated in the log domain
+ * (per-column reference exponents): a column whose entries all lie hundreds of binades below their row maxima
+ * still gets its exact, non-zero sum (down to 2^-960), so no potential can run away after a stale warm start. */
 int ure_sinkhorn_colsum(const float* d_M, int64_t n, int k, int kpad, const float* d_g, float eps,
                         double n_total, double* d_colsum, void* stream);
 
@@ -279,6 +332,22 @@ int ure_assign_plan_f32(const float* d_plan, int64_t n, int k, int64_t ld, int32
 int ure_assign_centroids(const float* d_M, int64_t n, int k, int kpad, const float* d_g,
                          const float* d_X, int d, int32_t* d_label, double* d_sum, int64_t* d_cnt,
                          void* stream);
+
+/* Centroid accumulators of utils.py:648 for GIVEN labels (after ure_balance_labels):
+ * d_sum[j,:] += x_i, d_cnt[j] += 1 for j = d_label[i]. */
+int ure_centroid_sums(const float* d_X, int64_t n, int d, const int32_t* d_label, int k, double* d_sum,
+                      int64_t* d_cnt, void* stream);
+
+/* Balanced rounding of the assignment (SURVEY.md H1 iv; the reference's exact EMD plan, utils.py:641-647, puts
+ * exactly n/k users in every group): d_label / d_cnt = the argmax assignment of ure_assign_centroids and its group
+ * sizes on entry; users are moved from over-full to under-full groups along successive shortest augmenting paths
+ * of the group graph (edge j->l = the cheapest M_il - M_ij over the members of j), which keeps the assignment
+ * cost-optimal for its sizes and ends at the minimum-cost assignment with floor(n/k)..ceil(n/k) users per group.
+ * At most max_aug augmentations (one pass over M each).  d_workspace: ure_balance_workspace_bytes(k) bytes; after
+ * the call its int32 words [32..34] hold {augmentations applied, users still to move, gave-up flag}.  k <= 128. */
+int64_t ure_balance_workspace_bytes(int k);
+int ure_balance_labels(const float* d_M, int64_t n, int k, int kpad, int32_t* d_label, int64_t* d_cnt,
+                       int max_aug, void* d_workspace, void* stream);
 
 #ifdef __cplusplus
 }

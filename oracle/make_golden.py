@@ -83,6 +83,28 @@ def gold_train(tr, te):
     print("train losses", losses, "rmse/ndcg/hr", rmse, ndcg, hr)
 
 
+def gold_steplr(tr):
+    """Reference baseTrain + StepLR(50, 0.95) (scratch.py:69,80) over 101 epochs -- two decay boundaries -- on the
+    first 2400 toy rows, batch 800, injected weights + Feistel visiting orders."""
+    epochs, n, batch = 101, 2400, 800
+    sub = arr3(tr.iloc[:n])
+    U, I = int(sub[0].max()) + 1, int(sub[1].max()) + 1
+    P0, Q0 = init_weights(4321, U, I)
+    perms = [omf.feistel_perm(n, omf.perm_key(SEED, 3, ep)) for ep in range(epochs)]
+    model, losses = ref_shim.train_injected(sub, U, I, K_DIM, P0, Q0, perms, batch, epochs)
+    np.savez_compressed(os.path.join(GOLD, "toy_steplr.npz"), weight_seed=4321, perm_seed=SEED, shard_id=3, epochs=epochs,
+                        batch=batch, n=n, n_user=U, n_item=I, losses=np.array(losses),
+                        P_final=model.user_mat.weight.detach().numpy(), Q_final=model.item_mat.weight.detach().numpy())
+    # sensitivity: the same run with a constant learning rate must be visibly different
+    Pc, Qc, _, _, lc = omf.mf_train(P0, Q0, sub[0].astype(np.int64), sub[1].astype(np.int64), sub[2].astype(np.float32),
+                                    perms, batch, epochs, lr_decay=1.0)
+    Pd, Qd, _, _, ld = omf.mf_train(P0, Q0, sub[0].astype(np.int64), sub[1].astype(np.int64), sub[2].astype(np.float32),
+                                    perms, batch, epochs)
+    print("steplr: reference last loss", losses[-1], "oracle", ld[-1], "constant-lr oracle", lc[-1],
+          "max|dP| decay vs constant", np.abs(Pc - Pd).max(), "oracle vs reference",
+          np.abs(Pd - model.user_mat.weight.detach().numpy()).max())
+
+
 def gold_sisa(tr, te):
     """Reference Sisa.learn + Sisa.unlearn on toy, K=3, 2 epochs, injected init + perms."""
     import torch
@@ -200,6 +222,7 @@ def main():
     tr, te = gold_data()
     gold_train(tr, te)
     gold_sisa(tr, te)
+    gold_steplr(tr)
     gold_ot()
 
 

@@ -110,6 +110,75 @@ def assign(plan):
     return np.argmax(plan, axis=1)
 
 
+def balance_labels(M, label, max_aug=1 << 14):
+    """Balanced rounding of an assignment (the statement ultrare_b200/csrc/ot_balance.cu is checked against).
+
+    ``label`` is cost-optimal for its own group sizes (the argmax of a Sinkhorn plan row is); users are moved from
+    over-full to under-full groups along successive shortest augmenting paths of the k-node group graph with edge
+    weights w(j->l) = min_{i in group j} (M[i,l] - M[i,j]) (ties: lowest user index), which keeps optimality and ends
+    at the minimum-cost assignment with floor(n/k)..ceil(n/k) users per group -- for k | n and a unique optimum, the
+    argmax labels of the exact EMD plan the reference computes (utils.py:644-647).  fp32 arithmetic on the deltas
+    and path lengths, Bellman-Ford with (distance, lowest predecessor) ties, exactly as the kernel.
+    Returns (label, n_augmentations)."""
+    M = np.asarray(M, dtype=np.float32)
+    label = np.asarray(label).astype(np.int64).copy()
+    n, k = M.shape
+    lo, hi = n // k, -(-n // k)
+    size = np.bincount(label, minlength=k)
+    rows = np.arange(n)
+    done = 0
+    while done < max_aug:
+        if (size > hi).any():
+            src, snk = size > hi, size < hi
+        elif (size < lo).any():
+            src, snk = size > lo, size < lo
+        else:
+            break
+        delta = (M - M[rows, label][:, None]).astype(np.float32)            # [n,k]: M_il - M_i,label(i)
+        W = np.full((k, k), np.inf, dtype=np.float32)
+        U = np.zeros((k, k), dtype=np.int64)
+        for j in range(k):
+            mem = np.flatnonzero(label == j)
+            if mem.size == 0:
+                continue
+            dj = delta[mem]
+            arg = np.argmin(dj, axis=0)                                        # first minimum = lowest user index
+            W[j], U[j] = dj[arg, np.arange(k)], mem[arg]
+            W[j, j] = np.inf
+        dist = np.where(src, np.float32(0), np.float32(np.inf)).astype(np.float32)
+        pred = np.full(k, -1)
+        for _ in range(k + 2):
+            changed = False
+            for j in range(k):
+                if not np.isfinite(dist[j]):
+                    continue
+                for l in range(k):
+                    if l == j or not np.isfinite(W[j, l]):
+                        continue
+                    cand = np.float32(dist[j] + W[j, l])
+                    if cand < dist[l] or (cand == dist[l] and pred[l] >= 0 and j < pred[l]):
+                        changed |= cand < dist[l]
+                        dist[l], pred[l] = cand, j
+            if not changed:
+                break
+        cands = [j for j in range(k) if snk[j] and np.isfinite(dist[j])]
+        if not cands:
+            break
+        sink = min(cands, key=lambda j: (dist[j], j))
+        l = sink
+        moves = []
+        while pred[l] >= 0 and len(moves) <= k:
+            j = pred[l]
+            moves.append((U[j, l], l))
+            l = j
+        for u, new in moves:
+            label[u] = new
+        size[l] -= 1
+        size[sink] += 1
+        done += 1
+    return label, done
+
+
 def centroid_update(X, label, k):
     """np.array([X[label==i].mean(0) for i in range(k)]) (utils.py:648)."""
     X = np.asarray(X)

@@ -20,7 +20,7 @@ def test_header_symbols_are_exported_and_bound():
     for name in declared:
         assert hasattr(handle, name), f"{name} declared in the header but not exported"
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
-    assert handle.ure_abi_version() == 3
+    assert handle.ure_abi_version() == 4
     handle.ure_last_error.restype = ctypes.c_char_p
     assert isinstance(handle.ure_last_error(), bytes)
 

@@ -220,9 +220,9 @@ def test_mapped_record_cache_is_keyed_on_the_row_map():
 
 
 def test_ot_cluster_host_loop_with_oracle_kernels(monkeypatch):
-    """The host loop of ot_cluster_device (outer iterations, warm start, the cold re-solve of an iteration whose
-    warm-started assignment is far from n/k users per centroid) with the three kernels it calls stood in by the
-    oracle's arithmetic: what is under test is the control flow, not the CUDA code (tests/test_gpu_surface.py)."""
+    """The host loop of ot_cluster_device (outer iterations, warm start, balanced rounding, centroid update, the
+    loud failure on non-finite potentials) with the kernels it calls stood in by the oracle's arithmetic: what is
+    under test is the control flow, not the CUDA code (tests/test_gpu_surface.py, tests/test_gpu_kernels.py)."""
     from oracle import ot as oot
     from ultrare_b200 import kernels as kn
     from ultrare_b200.method import utils as mu
@@ -232,33 +232,67 @@ def test_ot_cluster_host_loop_with_oracle_kernels(monkeypatch):
         M = ((Xd[:, None, :].double() - Cd[None, :, :].double()) ** 2).sum(-1).float()
         return M, M.min(1).values.double().sum().reshape(1)
 
-    calls = {"warm": 0, "cold": 0, "sabotage": False}
+    calls = {"warm": 0, "cold": 0, "balance": 0, "poison": False}
 
     def sinkhorn(M, k, sched, g=None, tol=0.0):
         _, _, gg, _ = oot.sinkhorn_log(M.numpy()[:, :k], sched, g0=None if g is None else g.numpy())
         out = torch.from_numpy(gg.astype(np.float32))
         calls["cold" if g is None else "warm"] += 1
-        if g is not None and calls["sabotage"]:
-            out[0] = 1e6
+        if calls["poison"]:
+            out[0] = float("nan")
         return out
 
     def assign_centroids(M, k, g, X):
         lab = torch.argmax(g[None, :k] - M[:, :k], dim=1).to(torch.int32)
-        cnt = torch.bincount(lab.long(), minlength=k)
-        sums = torch.zeros((k, X.shape[1]), dtype=torch.float64)
-        sums.index_add_(0, lab.long(), X.double())
-        return lab, sums, cnt
+        return lab, None, torch.bincount(lab.long(), minlength=k)
 
-    monkeypatch.setattr(kn, "cost_matrix", cost_matrix)
-    monkeypatch.setattr(kn, "sinkhorn", sinkhorn)
-    monkeypatch.setattr(kn, "assign_centroids", assign_centroids)
+    def balance_labels(M, k, label, cnt, max_aug):
+        lab, n_aug = oot.balance_labels(M.numpy()[:, :k], label.numpy())
+        label.copy_(torch.from_numpy(lab.astype(np.int32)))
+        cnt.copy_(torch.bincount(label.long(), minlength=k))
+        calls["balance"] += 1
+        return torch.tensor([n_aug, 0, 0], dtype=torch.int32)
+
+    def centroid_sums(X, label, k):
+        sums = torch.zeros((k, X.shape[1]), dtype=torch.float64)
+        sums.index_add_(0, label.long(), X.double())
+        return sums, torch.bincount(label.long(), minlength=k)
+
+    for name, fn in dict(cost_matrix=cost_matrix, sinkhorn=sinkhorn, assign_centroids=assign_centroids,
+                         balance_labels=balance_labels, centroid_sums=centroid_sums,
+                         upload_table=lambda a, dev: torch.from_numpy(np.ascontiguousarray(a)),
+                         upload_array=lambda a, dev: torch.from_numpy(np.ascontiguousarray(a)),
+                         download_many=lambda ts: [t.numpy().copy() for t in ts]).items():
+        monkeypatch.setattr(kn, name, fn)
     rng = np.random.default_rng(2)
-    n, k = 600, 4
+    n, k = 602, 4                                       # k does not divide n: sizes floor / ceil
     X = rng.standard_normal((n, 8)).astype(np.float32)
-    for sabotage in (False, True):
-        calls.update(warm=0, cold=0, sabotage=sabotage)
-        inertia, label, cen, it = mu.ot_cluster_device(X, k, max_iters=3, centroid0=X[:k].copy())
-        cnt = np.bincount(label, minlength=k)
-        assert cnt.sum() == n and cnt.min() > 0.8 * n / k and cnt.max() < 1.2 * n / k, (sabotage, cnt)
-        assert np.isfinite(cen).all() and np.isfinite(inertia) and label.dtype == np.int64
-        assert calls["warm"] == it - 1 and calls["cold"] == (it if sabotage else 1)
+    inertia, label, cen, it = mu.ot_cluster_device(X, k, max_iters=3, centroid0=X[:k].copy())
+    cnt = np.bincount(label, minlength=k)
+    assert sorted(cnt.tolist()) == [150, 150, 151, 151], cnt
+    assert np.isfinite(cen).all() and np.isfinite(inertia) and label.dtype == np.int64
+    assert calls["cold"] == 1 and calls["warm"] == it - 1 and calls["balance"] == it
+    calls["poison"] = True                              # a NaN potential must not end as a silent degenerate grouping
+    with pytest.raises(RuntimeError, match="not finite"):
+        mu.ot_cluster_device(X, k, max_iters=2, centroid0=X[:k].copy())
+
+
+def test_balanced_rounding_oracle_reaches_the_exact_emd_assignment():
+    """oracle.ot.balance_labels (what csrc/ot_balance.cu is checked against): from the argmax of a Sinkhorn plan the
+    successive-shortest-path rounding ends at the argmax labels of the exact LP plan (the reference's ot.emd,
+    utils.py:644-647): equal labels, equal cost, exactly n/k users per group."""
+    from oracle import ot as oot
+    rng = np.random.default_rng(5)
+    n, k = 900, 5
+    X = rng.standard_normal((n, 8)).astype(np.float32)
+    M = oot.cost_matrix_ref_fp32(X, X[:k]).T.copy()
+    scale = float(M.min(1).mean())
+    _, _, g, _ = oot.sinkhorn_log(M, [(scale, 10), (0.3 * scale, 20), (0.1 * scale, 30), (0.03 * scale, 60)])
+    lab = np.argmax(g[None, :] - M, axis=1)
+    assert np.bincount(lab, minlength=k).tolist() != [n // k] * k          # the entropic argmax is not balanced
+    bal, n_aug = oot.balance_labels(M, lab)
+    assert np.bincount(bal, minlength=k).tolist() == [n // k] * k and n_aug > 0
+    emd = oot.assign(oot.emd_lp(np.ones(n) / n, np.ones(k) / k, M))
+    assert np.array_equal(bal, emd)
+    rows = np.arange(n)
+    assert abs(float(M[rows, bal].sum()) - float(M[rows, emd].sum())) < 1e-3

@@ -56,6 +56,33 @@ def test_mf_train_vs_reference_golden(toy, cuda_dev, explicit_perm, mode):
     assert float(shards[0].gP.abs().max()) == 0.0 and float(shards[0].gQ.abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("mode", ["dense", "owner", "lazy"])
+def test_mf_train_across_two_steplr_boundaries_vs_reference_golden(toy, cuda_dev, mode):
+    """101 epochs in one persistent launch: the kernels' lr_of(epoch) (StepLR(50, 0.95), scratch.py:69,80) crosses
+    two decay boundaries; fixture = the reference's own baseTrain + scheduler (tests/golden/toy_steplr.npz).  The
+    lazy schedule's closed-form catch-up needs a constant learning rate: it refuses such a run loudly."""
+    torch = _torch()
+    from ultrare_b200 import kernels as kn
+    z = load_gold("toy_steplr.npz")
+    n, epochs, batch = int(z["n"]), int(z["epochs"]), int(z["batch"])
+    u, i, r = (a[:n] for a in toy["train"])
+    P0, Q0 = init_weights(int(z["weight_seed"]), int(z["n_user"]), int(z["n_item"]))
+    st = kn.ShardState(kn.pack_interactions(u, i, r / 5.0, cuda_dev), torch.tensor(P0, device=cuda_dev),
+                       torch.tensor(Q0, device=cuda_dev), epochs, shard_id=int(z["shard_id"]), perm_seed=int(z["perm_seed"]))
+    sb = kn.ShardBatch([st], 16, batch, mode=mode)
+    assert sb.mode == mode
+    if mode == "lazy":
+        with pytest.raises(RuntimeError, match="constant"):
+            sb.train()
+        return
+    sb.train()
+    losses = sb.train_losses()[0]
+    np.testing.assert_allclose(losses, z["losses"], rtol=1e-3)
+    assert np.abs(losses - z["losses"]).max() / z["losses"].max() < 2e-5
+    assert np.abs(st.P.cpu().numpy() - z["P_final"]).max() < 1e-4
+    assert np.abs(st.Q.cpu().numpy() - z["Q_final"]).max() < 1e-4
+
+
 @pytest.mark.parametrize("mode", MODES)
 def test_mf_train_epoch_by_epoch_equals_single_launch(toy, cuda_dev, mode):
     torch = _torch()
@@ -289,6 +316,103 @@ def test_sinkhorn_plan_vs_float64_oracle(cuda_dev, n, k):
     assert np.abs(sums.cpu().numpy() - ref_sum).max() < 1e-3
 
 
+@pytest.mark.parametrize("form", ["cluster", "persistent", "split"])
+def test_sinkhorn_dead_column_recovers_exactly_like_the_log_domain_oracle(cuda_dev, form):
+    """Potentials that are stale by hundreds of eps (a warm start after the centroids moved, profiles/r1_notes.md):
+    every entry of one column is > 700 binades below its row maximum, so a linear-domain fp32 column sum is exactly
+    zero and log(0) sends the potential to infinity.  The kernels keep the column sums in the log domain: all three
+    forms follow the float64 log-sum-exp oracle from the very first iteration."""
+    torch = _torch()
+    from ultrare_b200 import kernels as kn
+    rng = np.random.default_rng(11)
+    n, k = {"cluster": (6040, 5), "persistent": (20000, 32), "split": (20000, 32)}[form]
+    X = rng.standard_normal((n, 16), dtype=np.float32)
+    Cc = X[rng.choice(n, k, replace=False)]
+    M = kn.cost_matrix(torch.tensor(X, device=cuda_dev), torch.tensor(Cc, device=cuda_dev))
+    Mh = M.cpu().numpy()[:, :k].astype(np.float64)
+    mean = float(Mh.min(1).mean())
+    eps = 0.02 * mean
+    g0 = np.zeros(k, dtype=np.float32)
+    g0[1] = -25.0 * mean                                   # (g_1 - M_i1)/eps is ~1250 nats below every row's maximum
+    g0[k - 1] = -8.0 * mean
+    sched = [(eps, 1)]
+    _, _, g_o1, _ = oot.sinkhorn_log(Mh, sched, g0=g0.astype(np.float64))
+    assert np.isfinite(g_o1).all() and g_o1[1] - g0[1] > 20.0 * mean
+    sched = [(eps, 40)]
+    P_o, _, g_o, _ = oot.sinkhorn_log(Mh, sched, g0=g0.astype(np.float64))
+
+    def run(iters):
+        g = torch.tensor(g0, device=cuda_dev)
+        if form == "split":
+            colsum = torch.zeros(M.shape[1], dtype=torch.float64, device=cuda_dev)
+            for _ in range(iters):
+                kn.sinkhorn_colsum(M, k, g, eps, n, colsum)
+                kn.sinkhorn_update_g(g, colsum, k, eps)
+            return g
+        return kn.sinkhorn(M, k, [(eps, iters)], g=g)
+
+    g1 = run(1).cpu().numpy()
+    assert np.isfinite(g1).all()
+    assert np.abs(g1 - g_o1).max() < 2e-3 * mean, (g1, g_o1)           # the dead columns are lifted by the exact amount
+    g = run(40)
+    plan = kn.sinkhorn_plan(M, k, g, eps).cpu().numpy()
+    assert np.abs(n * plan - n * P_o).max() < 2e-4
+    lab = np.argmax(g.cpu().numpy()[None, :] - M.cpu().numpy()[:, :k], axis=1)
+    assert np.bincount(lab, minlength=k).min() > 0.5 * n / k
+
+
+def test_sinkhorn_nan_cost_column_propagates(cuda_dev):
+    """A NaN centroid (an empty group upstream) must not be absorbed by a floor: the potentials come back non-finite
+    and ot_cluster_device raises instead of caching a degenerate grouping."""
+    torch = _torch()
+    from ultrare_b200 import kernels as kn
+    rng = np.random.default_rng(3)
+    X = rng.standard_normal((4000, 16), dtype=np.float32)
+    Cc = X[:5].copy()
+    Cc[2] = np.nan
+    M = kn.cost_matrix(torch.tensor(X, device=cuda_dev), torch.tensor(Cc, device=cuda_dev))
+    g = kn.sinkhorn(M, 5, [(5.0, 5)])
+    assert not np.isfinite(g.cpu().numpy()).all()
+
+
+@pytest.mark.parametrize("n,k,d", [(6040, 5, 16), (1001, 7, 8), (30000, 8, 16), (50000, 32, 16), (9000, 128, 32)])
+def test_balanced_rounding_vs_oracle_and_exact_emd(cuda_dev, n, k, d):
+    """ure_balance_labels on the argmax of our own Sinkhorn potentials: bit-equal to the oracle's successive-shortest-
+    path rounding on the same cost matrix and labels (single-CTA and multi-CTA launches, k | n and not), every group
+    floor(n/k)..ceil(n/k) users; at ml1m size the result is the argmax of the exact LP plan (the reference's ot.emd,
+    utils.py:644-647)."""
+    torch = _torch()
+    from ultrare_b200 import kernels as kn
+    rng = np.random.default_rng(n + k)
+    X = rng.standard_normal((n, d), dtype=np.float32)
+    Cc = X[rng.choice(n, k, replace=False)]
+    Xd = torch.tensor(X, device=cuda_dev)
+    M = kn.cost_matrix(Xd, torch.tensor(Cc, device=cuda_dev))
+    Mh = M.cpu().numpy()[:, :k]
+    scale = float(Mh.min(1).mean())
+    g = kn.sinkhorn(M, k, [(scale, 10), (0.3 * scale, 20), (0.1 * scale, 30), (0.03 * scale, 60)])
+    label, _, cnt = kn.assign_centroids(M, k, g, None)
+    lab0 = label.cpu().numpy().copy()
+    assert np.array_equal(cnt.cpu().numpy(), np.bincount(lab0, minlength=k))
+    status = kn.balance_labels(M, k, label, cnt)
+    got, sizes, status = label.cpu().numpy(), cnt.cpu().numpy(), status.cpu().numpy()
+    lo, hi = n // k, -(-n // k)
+    assert sizes.min() >= lo and sizes.max() <= hi and sizes.sum() == n, sizes
+    assert np.array_equal(sizes, np.bincount(got, minlength=k)) and status[1] == 0 and status[2] == 0
+    ref, n_aug = oot.balance_labels(Mh, lab0)
+    assert status[0] == n_aug and n_aug > 0
+    assert np.array_equal(got, ref)
+    sums, cnt2 = kn.centroid_sums(Xd, label, k)
+    assert np.array_equal(cnt2.cpu().numpy(), sizes)
+    ref_sum = np.stack([X[got == j].astype(np.float64).sum(0) for j in range(k)])
+    assert np.abs(sums.cpu().numpy() - ref_sum).max() < 1e-3
+    if n == 6040:
+        emd = oot.assign(oot.emd_lp(np.ones(n) / n, np.ones(k) / k, Mh))
+        assert (got == emd).mean() >= 0.9995, (got != emd).sum()
+        rows = np.arange(n)
+        assert abs(float(Mh[rows, got].sum()) - float(Mh[rows, emd].sum())) <= 1e-5 * float(Mh[rows, emd].sum())
+
+
 def test_assign_plan_first_max_wins_on_emd_plan(cuda_dev):
     """The reference's plan (exact EMD vertex) through the extraction kernel: bit-exact labels, ties -> first."""
     torch = _torch()
@@ -425,6 +549,61 @@ def test_mf_owner_skewed_rows_many_shards_vs_oracle(cuda_dev, cache, force, monk
         assert np.abs(shards[s].Q.cpu().numpy() - Q).max() < 1e-4
         assert np.abs(shards[s].bufQ.cpu().numpy() - bQ).max() < 1e-3
         assert float(shards[s].gP.abs().max()) == 0.0 and float(shards[s].gQ.abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("mode,sched_bytes,explicit", [("owner", None, False), ("owner", 1, False), ("dense", None, False),
+                                                       ("owner", None, True)])
+def test_arena_batch_runtime_equals_per_shard_states(cuda_dev, monkeypatch, mode, sched_bytes, explicit):
+    """The native batch runtime (ure_mf_batch_layout / _setup / _plan, kernels.ArenaShardBatch) against the per-shard
+    ShardState path on the same records, weights and visiting orders: identical descriptors in effect -- the trained
+    tables, momentum buffers and per-epoch losses are equal bit for bit (owner) / to rounding (dense: atomics), and
+    equal to the oracle.  Ragged shards, an empty shard, schedule windows of 2 epochs, explicit visiting orders."""
+    torch = _torch()
+    from ultrare_b200 import kernels as kn
+    if sched_bytes is not None:
+        monkeypatch.setattr(kn, "OWNER_SCHED_BYTES", sched_bytes)
+    rng = np.random.default_rng(77)
+    d, batch, epochs, I = 16, 900, 4, 150
+    sizes = [(110, 5200), (60, 0), (140, 7900), (95, 3100)]
+    recs, perms_h, host = [], [], []
+    for s, (U, n) in enumerate(sizes):
+        u, i = rng.integers(0, U, n), rng.integers(0, I, n)
+        r = rng.integers(1, 6, n).astype(np.float32) / 5
+        recs.append(kn.pack_interactions(u, i, r, cuda_dev))
+        if explicit:
+            perms_h.append(np.stack([rng.permutation(n) for _ in range(epochs)]).astype(np.int32).reshape(epochs, n))
+        else:
+            perms_h.append([omf.feistel_perm(n, omf.perm_key(9, s + 1, ep)) for ep in range(epochs)] if n else [])
+        host.append((u, i, r))
+    perms_d = [torch.tensor(p, device=cuda_dev) for p in perms_h] if explicit else None
+    gen = torch.Generator(device=cuda_dev).manual_seed(5)
+    ab = kn.ArenaShardBatch(recs, [U for U, _ in sizes], I, d, batch, epochs, [s + 1 for s in range(len(sizes))], 9,
+                            perms_d, generator=gen, std=0.3, mode=mode)
+    assert ab.mode == mode
+    P0 = [st.P.clone() for st in ab.shards]
+    Q0 = [st.Q.clone() for st in ab.shards]
+    ab.train()
+    la = ab.train_losses()
+    states = [kn.ShardState(recs[s], P0[s].clone(), Q0[s].clone(), epochs, s + 1, 9,
+                            perm=None if perms_d is None else perms_d[s]) for s in range(len(sizes))]
+    sb = kn.ShardBatch(states, d, batch, mode=mode)
+    sb.train()
+    lb = sb.train_losses()
+    for s, (U, n) in enumerate(sizes):
+        a, b = ab.shards[s], states[s]
+        if mode == "owner":
+            assert torch.equal(a.P, b.P) and torch.equal(a.Q, b.Q) and torch.equal(a.bufP, b.bufP)
+            assert np.array_equal(la[s], lb[s])
+        else:
+            assert (a.P - b.P).abs().max().item() < 1e-5 and (a.Q - b.Q).abs().max().item() < 1e-5
+        if n == 0:
+            assert torch.equal(a.P, P0[s])
+            continue
+        u, i, r = host[s]
+        P, Q, bP, bQ, ls = omf.mf_train(P0[s].cpu().numpy(), Q0[s].cpu().numpy(), u, i, r, list(perms_h[s]), batch, epochs)
+        np.testing.assert_allclose(la[s], ls, rtol=1e-5)
+        assert np.abs(a.P.cpu().numpy() - P).max() < 1e-4 and np.abs(a.Q.cpu().numpy() - Q).max() < 1e-4
+        assert float(a.gP.abs().max()) == 0.0 and float(a.gQ.abs().max()) == 0.0
 
 
 def test_pack_interactions_on_device_equals_host_casts(cuda_dev):

@@ -50,6 +50,28 @@ def test_mf_train_matches_reference(toy):
     assert np.abs(P - z["P_final"]).max() < 1e-4 and np.abs(Q - z["Q_final"]).max() < 1e-4
 
 
+def _steplr_inputs(toy, z):
+    n = int(z["n"])
+    u, i, r = (a[:n] for a in toy["train"])
+    r32 = (r / 5.0).astype(np.float32)
+    P0, Q0 = init_weights(int(z["weight_seed"]), int(z["n_user"]), int(z["n_item"]))
+    perms = [omf.feistel_perm(n, omf.perm_key(int(z["perm_seed"]), int(z["shard_id"]), ep)) for ep in range(int(z["epochs"]))]
+    return u, i, r32, P0, Q0, perms
+
+
+def test_mf_train_across_two_steplr_boundaries_matches_reference(toy):
+    """101 epochs: StepLR(step_size=50, gamma=0.95) fires after epochs 50 and 100 (scratch.py:69,80).  The fixture is
+    the reference's own baseTrain + scheduler; a constant learning rate would miss it by 1.4 % in the last loss."""
+    z = load_gold("toy_steplr.npz")
+    u, i, r32, P0, Q0, perms = _steplr_inputs(toy, z)
+    assert omf.lr_at_epoch(1e-3, 0.95, 49) == 1e-3 and abs(omf.lr_at_epoch(1e-3, 0.95, 100) - 1e-3 * 0.95 ** 2) < 1e-12
+    P, Q, _, _, losses = omf.mf_train(P0, Q0, u, i, r32, perms, int(z["batch"]), int(z["epochs"]))
+    np.testing.assert_allclose(losses, z["losses"], rtol=1e-5)
+    assert np.abs(P - z["P_final"]).max() < 1e-4 and np.abs(Q - z["Q_final"]).max() < 1e-4
+    _, _, _, _, flat = omf.mf_train(P0, Q0, u, i, r32, perms, int(z["batch"]), int(z["epochs"]), lr_decay=1.0)
+    assert abs(flat[-1] - z["losses"][-1]) / z["losses"][-1] > 5e-3          # the fixture is sensitive to the decay
+
+
 def test_mf_train_torch_port_matches_numpy(toy):
     import torch
     u, i, r = toy["train"]

@@ -35,12 +35,25 @@ class MFHParams(C.Structure):
                 ("owner_cap_rows", _i32), ("owner_cap_slots", _i32), ("owner_flags", _i32),
                 ("owner_spe_cap", _i32), ("owner_sched_rows", _i32), ("owner_sched", _p), ("owner_sched_off", _p),
                 ("owner_sched_step0", _i64), ("owner_sched_stride", _i64),
-                ("owner_cap_list", _i32), ("owner_reserved", _i32)]
+                ("owner_cap_list", _i32), ("owner_max_n", _i32)]
+
+
+class MFBatchShard(C.Structure):
+    """ure_mf_batch_shard_t"""
+    _fields_ = [("inter", _p), ("perm", _p), ("n", _i32), ("n_user", _i32), ("shard_id", _i32), ("group", _i32)]
+
+
+class MFBatchLayout(C.Structure):
+    """ure_mf_batch_layout_t"""
+    _fields_ = [(nm, _i64) for nm in ("total", "table", "ws", "W", "Z", "sse", "zero_end", "rec", "off", "radix",
+                                       "perm_inv", "sched", "sched_off", "rows_total", "n_total", "sched_stride")] + \
+               [(nm, _i32) for nm in ("spe_cap", "max_rows", "max_n", "grid", "owner", "sched_rows")]
 
 
 MF_DENSE, MF_LAZY, MF_OWNER = 0, 1, 2
 
 assert C.sizeof(MFShard) == 176 and C.sizeof(MFHParams) == 104
+assert C.sizeof(MFBatchShard) == 32 and C.sizeof(MFBatchLayout) == 152
 
 # name -> (restype, argtypes); every symbol include/ultrare_b200.h declares
 SIGNATURES = {
@@ -52,6 +65,12 @@ SIGNATURES = {
     "ure_mf_owner_prepare": (C.c_int, [_p, C.c_int, C.POINTER(MFHParams), C.c_int, C.c_int, _p, _p, _p]),
     "ure_mf_owner_smem_bytes": (_i64, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "ure_mf_owner_schedule": (C.c_int, [_p, C.c_int, C.POINTER(MFHParams), C.c_int, _i64, _p]),
+    "ure_mf_batch_layout": (C.c_int, [C.POINTER(MFBatchShard), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _i64,
+                                       C.POINTER(MFBatchLayout)]),
+    "ure_mf_batch_setup": (C.c_int, [C.POINTER(MFBatchShard), C.c_int, C.c_int, C.POINTER(MFHParams), C.c_int, C.c_uint32,
+                                      _p, C.POINTER(MFBatchLayout), _p, _p]),
+    "ure_mf_batch_plan": (C.c_int, [_p, C.c_int, C.POINTER(MFHParams), _p, C.POINTER(MFBatchLayout), C.c_int, C.c_int,
+                                     C.c_int, _p]),
     "ure_mf_train_trace": (C.c_int, [_p, _p, C.c_int, _p]),
     "ure_mf_grid_size": (C.c_int, []),
     "ure_mf_debug_flags": (C.c_int, [_p, C.c_uint32, _p]),
@@ -76,6 +95,9 @@ SIGNATURES = {
     "ure_assign_plan_f64": (C.c_int, [_p, _i64, C.c_int, _i64, _p, _p]),
     "ure_assign_plan_f32": (C.c_int, [_p, _i64, C.c_int, _i64, _p, _p]),
     "ure_assign_centroids": (C.c_int, [_p, _i64, C.c_int, C.c_int, _p, _p, C.c_int, _p, _p, _p, _p]),
+    "ure_centroid_sums": (C.c_int, [_p, _i64, C.c_int, _p, C.c_int, _p, _p, _p]),
+    "ure_balance_workspace_bytes": (_i64, [C.c_int]),
+    "ure_balance_labels": (C.c_int, [_p, _i64, C.c_int, C.c_int, _p, _p, C.c_int, _p, _p]),
 }
 
 _lib = None
@@ -97,7 +119,7 @@ def lib() -> C.CDLL:
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(handle, name)           # AttributeError if the .so lacks a declared symbol
         fn.restype, fn.argtypes = res, args
-    if handle.ure_abi_version() != 3:
+    if handle.ure_abi_version() != 4:
         raise RuntimeError("ultrare_b200: ABI version mismatch; rebuild the shared library")
     _lib = handle
     return handle

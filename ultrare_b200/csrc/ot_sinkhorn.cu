@@ -10,21 +10,23 @@
 // matrix M [n, kpad] (row major, columns >= k hold +inf):
 //     t_ij = (g_j - M_ij)/eps ;  P_ij = a_i * softmax_j(t_ij) ;  colsum_j = sum_i P_ij
 //     g_j += eps * (log b_j - log colsum_j),  b_j = 1/k
-// P_ij <= a_i, so colsum needs no max-shift.  Row work is a warp-shuffle reduction over
-// kpad/4 lanes; column sums go registers -> shuffle -> shared -> one fp64 atomic per
-// column per CTA.
+// Row work is a warp-shuffle reduction over kpad/4 lanes.  The column sums are accumulated in the LOG DOMAIN
+// (extended exponent): every lane keeps, per column, a reference exponent r (an integer, re-based when an
+// entry lies more than 2^60 above it) and the sum of 2^(t_ij - rowLSE_i - r) -- so a column whose every entry is
+// hundreds of binades below its row maximum (stale warm-start potentials at a small eps) still has an exact,
+// non-zero sum, exactly as the float64 log-sum-exp of oracle/ot.py:sinkhorn_log.  One MUFU ex2 per element:
+// the same exponential feeds the row sum (times 2^r, a per-lane constant) and the column sum.  Partial sums
+// travel as (r, s) pairs: lanes -> warp (shuffle) -> CTA (shared memory, fixed order) -> grid (one fp64 atomic
+// per column and CTA of s * 2^r / n, r clamped at -960; the cluster form keeps the pairs to the end).
 #include "common.cuh"
 #include <cooperative_groups.h>
 
 namespace ure {
 namespace {
 
-// Column sums below this are treated as this in the potential update.  A column can sum to exactly zero in fp32 when
-// the potentials are stale (a warm start after the centroids moved) and eps is small: every exp((g_j - M_ij)/eps -
-// rowmax) underflows.  log(0) would send g_j to infinity for good; with the floor the column gains 87 eps per
-// iteration until its entries are representable again, after which the update is the exact one.  Never active on a
-// column that holds any mass (a healthy column sums to ~1/k).
-constexpr double kMinColSum = 1e-38;
+constexpr float kNoRef = -1.0e30f;        // reference exponent of a column that has not seen a finite entry yet
+constexpr float kRebase = 60.f;           // an entry more than this many binades above the reference re-bases it
+constexpr float kMinExp = -960.f;         // smallest exponent a partial sum is converted to fp64 with
 
 constexpr float kLog2e = 1.4426950408889634f;
 
@@ -82,84 +84,149 @@ __device__ __forceinline__ void load_g(const float* g, int k, int gl, float4 (&o
   }
 }
 
-// Accumulate the column sums of rows [r0,r1) handled by this CTA into csum_sh[KPAD] (shared, fp32).
-// MSRC: row-major matrix base (global or shared) whose row 0 is row `base_row`.
+// Column sums of rows [r0,r1) handled by this CTA, in the log domain: every warp leaves, per column, the pair
+// (r, s) with sum_i P_ij * n = s * 2^r in part_r / part_s [n_warps][KPAD] (plain stores; the caller folds the
+// warps with fold_parts after a __syncthreads).  Msrc: row-major matrix base (global or shared) whose row 0 is
+// row `base_row`.  Arithmetic in log2 units: t = (g_j - M_ij) * log2(e)/eps.
 template <int KPAD>
 __device__ __forceinline__ void colsum_rows(const float* Msrc, long long base_row, long long r0, long long r1,
-                                            const float* g_sh, int k, float scale, float a, float* csum_sh,
-                                            float* warp_part = nullptr) {
+                                            const float* g_sh, int k, float scale, float* part_r, float* part_s) {
   using RM = RowMap<KPAD>;
   const int lane = threadIdx.x & 31;
   const int gl = lane % RM::LPR;
   const int rw = lane / RM::LPR;
   const int warp = threadIdx.x >> 5;
   const int n_warps = blockDim.x >> 5;
-  float4 g[RM::VEC], acc[RM::VEC];
-  load_g<KPAD>(g_sh, k, gl, g);
+  float4 gs[RM::VEC], ref[RM::VEC], cref[RM::VEC], acc[RM::VEC];
+  load_g<KPAD>(g_sh, k, gl, gs);
 #pragma unroll
-  for (int v = 0; v < RM::VEC; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int v = 0; v < RM::VEC; ++v) {
+    gs[v].x *= scale; gs[v].y *= scale; gs[v].z *= scale; gs[v].w *= scale;
+    ref[v] = make_float4(kNoRef, kNoRef, kNoRef, kNoRef);
+    cref[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const float nscale = -scale;
 #pragma unroll 2
   for (long long row0 = r0 + (long long)warp * RM::RPW; row0 < r1; row0 += (long long)n_warps * RM::RPW) {
     const long long row = row0 + rw;
     const bool valid = row < r1;
-    float4 m[RM::VEC], p[RM::VEC];
+    float4 t[RM::VEC];
+    float mx = -INFINITY;
 #pragma unroll
     for (int v = 0; v < RM::VEC; ++v) {
-      m[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (valid) m[v] = *(reinterpret_cast<const float4*>(Msrc + (row - base_row) * KPAD) + v * RM::LPR + gl);
+      float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (valid) m = *(reinterpret_cast<const float4*>(Msrc + (row - base_row) * KPAD) + v * RM::LPR + gl);
+      t[v].x = fmaf(m.x, nscale, gs[v].x); t[v].y = fmaf(m.y, nscale, gs[v].y);
+      t[v].z = fmaf(m.z, nscale, gs[v].z); t[v].w = fmaf(m.w, nscale, gs[v].w);
+      mx = fmaxf(mx, fmaxf(fmaxf(t[v].x, t[v].y), fmaxf(t[v].z, t[v].w)));
     }
-    float mx;
-    const float inv = row_softmax<KPAD>(m, g, scale, p, mx);
-    const float w = valid ? a * inv : 0.f;
+#pragma unroll
+    for (int o = RM::LPR / 2; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o, RM::LPR));
+    // d = t - rowmax (<= 0); the entry's exponent relative to the lane's column reference is d - r
+    float over = -INFINITY;
 #pragma unroll
     for (int v = 0; v < RM::VEC; ++v) {
-      acc[v].x = fmaf(p[v].x, w, acc[v].x); acc[v].y = fmaf(p[v].y, w, acc[v].y);
-      acc[v].z = fmaf(p[v].z, w, acc[v].z); acc[v].w = fmaf(p[v].w, w, acc[v].w);
+      t[v].x -= mx; t[v].y -= mx; t[v].z -= mx; t[v].w -= mx;
+      over = fmaxf(over, fmaxf(fmaxf(t[v].x - ref[v].x, t[v].y - ref[v].y), fmaxf(t[v].z - ref[v].z, t[v].w - ref[v].w)));
+    }
+    if (valid && over > kRebase) {           // rare: the first row of a column, or a jump of more than 2^60
+#pragma unroll
+      for (int v = 0; v < RM::VEC; ++v) {
+#define URE_REBASE(C)                                                     \
+  if (t[v].C - ref[v].C > kRebase) {                                      \
+    const float nr = rintf(t[v].C);                                       \
+    acc[v].C *= ex2_fast(ref[v].C - nr);                                  \
+    ref[v].C = nr;                                                        \
+    cref[v].C = ex2_fast(nr);                                             \
+  }
+        URE_REBASE(x) URE_REBASE(y) URE_REBASE(z) URE_REBASE(w)
+#undef URE_REBASE
+      }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int v = 0; v < RM::VEC; ++v) {      // q = 2^e feeds the row sum (times 2^r) and the column sum
+      t[v].x = ex2_fast(t[v].x - ref[v].x); t[v].y = ex2_fast(t[v].y - ref[v].y);
+      t[v].z = ex2_fast(t[v].z - ref[v].z); t[v].w = ex2_fast(t[v].w - ref[v].w);
+      s = fmaf(t[v].x, cref[v].x, s); s = fmaf(t[v].y, cref[v].y, s);
+      s = fmaf(t[v].z, cref[v].z, s); s = fmaf(t[v].w, cref[v].w, s);
+    }
+#pragma unroll
+    for (int o = RM::LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o, RM::LPR);
+    const float w = valid ? __frcp_rn(s) : 0.f;      // s in [1, KPAD] for a valid row (its maximum contributes 1)
+#pragma unroll
+    for (int v = 0; v < RM::VEC; ++v) {
+      acc[v].x = fmaf(t[v].x, w, acc[v].x); acc[v].y = fmaf(t[v].y, w, acc[v].y);
+      acc[v].z = fmaf(t[v].z, w, acc[v].z); acc[v].w = fmaf(t[v].w, w, acc[v].w);
     }
   }
-  // lanes with equal gl hold the same columns: fold the RPW row slots of the warp
+  // lanes with equal gl hold the same columns: fold the RPW row slots of the warp, re-based to the larger reference
 #pragma unroll
   for (int v = 0; v < RM::VEC; ++v) {
 #pragma unroll
     for (int o = RM::LPR; o < 32; o <<= 1) {
-      acc[v].x += __shfl_xor_sync(0xffffffffu, acc[v].x, o); acc[v].y += __shfl_xor_sync(0xffffffffu, acc[v].y, o);
-      acc[v].z += __shfl_xor_sync(0xffffffffu, acc[v].z, o); acc[v].w += __shfl_xor_sync(0xffffffffu, acc[v].w, o);
+#define URE_FOLD(C)                                                                     \
+  {                                                                                     \
+    const float r2 = __shfl_xor_sync(0xffffffffu, ref[v].C, o);                         \
+    const float a2 = __shfl_xor_sync(0xffffffffu, acc[v].C, o);                         \
+    const float R = fmaxf(ref[v].C, r2);                                                \
+    acc[v].C = acc[v].C * ex2_fast(ref[v].C - R) + a2 * ex2_fast(r2 - R);               \
+    ref[v].C = R;                                                                       \
+  }
+      URE_FOLD(x) URE_FOLD(y) URE_FOLD(z) URE_FOLD(w)
+#undef URE_FOLD
     }
     if (rw == 0) {
       const int c = (v * RM::LPR + gl) * 4;
-      if (warp_part) {                     // one slot per warp: plain stores, summed by the caller
-        *reinterpret_cast<float4*>(warp_part + warp * KPAD + c) = acc[v];
-      } else {
-        atomicAdd(&csum_sh[c + 0], acc[v].x); atomicAdd(&csum_sh[c + 1], acc[v].y);
-        atomicAdd(&csum_sh[c + 2], acc[v].z); atomicAdd(&csum_sh[c + 3], acc[v].w);
-      }
+      *reinterpret_cast<float4*>(part_r + warp * KPAD + c) = ref[v];
+      *reinterpret_cast<float4*>(part_s + warp * KPAD + c) = acc[v];
     }
   }
+}
+
+// (r, s) of column j over the CTA's warps, in warp order (deterministic)
+__device__ __forceinline__ void fold_parts(const float* part_r, const float* part_s, int n_warps, int kpad, int j,
+                                           float& R, float& S) {
+  R = kNoRef;
+  for (int w = 0; w < n_warps; ++w) R = fmaxf(R, part_r[w * kpad + j]);
+  S = 0.f;
+  for (int w = 0; w < n_warps; ++w) S = fmaf(part_s[w * kpad + j], ex2_fast(part_r[w * kpad + j] - R), S);
+}
+
+// s * 2^r / n as a double (r is an integer; below kMinExp the value is clamped, still positive)
+__device__ __forceinline__ double pair_to_double(float R, float S, double a) {
+  return ldexp((double)S, (int)fmaxf(R, kMinExp)) * a;
 }
 
 // --------------------------------------------------------------------------- split-phase kernels
 template <int KPAD>
 __global__ void __launch_bounds__(kSkThreads)
-colsum_kernel(const float* __restrict__ M, long long n, int k, const float* __restrict__ g, float scale, float a,
+colsum_kernel(const float* __restrict__ M, long long n, int k, const float* __restrict__ g, float scale, double a,
               double* __restrict__ colsum) {
   __shared__ float g_sh[KPAD];
-  __shared__ float csum_sh[KPAD];
-  for (int j = threadIdx.x; j < KPAD; j += blockDim.x) { g_sh[j] = j < k ? g[j] : 0.f; csum_sh[j] = 0.f; }
+  __shared__ __align__(16) float part_r[(kSkThreads / 32) * KPAD];
+  __shared__ __align__(16) float part_s[(kSkThreads / 32) * KPAD];
+  for (int j = threadIdx.x; j < KPAD; j += blockDim.x) g_sh[j] = j < k ? g[j] : 0.f;
   __syncthreads();
   const long long per = (n + gridDim.x - 1) / gridDim.x;
   const long long r0 = per * blockIdx.x;
   const long long r1 = r0 + per < n ? r0 + per : n;
-  if (r0 < r1) colsum_rows<KPAD>(M, 0, r0, r1, g_sh, k, scale, a, csum_sh);
+  if (r0 >= r1) return;
+  colsum_rows<KPAD>(M, 0, r0, r1, g_sh, k, scale, part_r, part_s);
   __syncthreads();
-  for (int j = threadIdx.x; j < k; j += blockDim.x)
-    if (csum_sh[j] != 0.f) atomicAdd(colsum + j, (double)csum_sh[j]);
+  for (int j = threadIdx.x; j < k; j += blockDim.x) {
+    float R, S;
+    fold_parts(part_r, part_s, kSkThreads / 32, KPAD, j, R, S);
+    if (S != 0.f) atomicAdd(colsum + j, pair_to_double(R, S, a));      // NaN != 0: a poisoned column propagates
+  }
 }
 
 __global__ void update_g_kernel(float* g, double* colsum, int k, float eps) {
   const int j = threadIdx.x;
   if (j < k) {
     const double c = colsum[j];
-    g[j] = (float)((double)g[j] + (double)eps * (-log((double)k) - log(fmax(c, kMinColSum))));
+    g[j] = (float)((double)g[j] + (double)eps * (-log((double)k) - log(c)));
     colsum[j] = 0.0;
   }
 }
@@ -183,21 +250,24 @@ template <int KPAD, bool CACHED>
 __global__ void __launch_bounds__(kSkThreads, 1)
 sinkhorn_kernel(const float* __restrict__ M, long long n, int k, float* __restrict__ g_io, SkStages stages,
                 SkWorkspace* ws) {
-  extern __shared__ __align__(16) float m_sh[];     // CACHED: this CTA's rows of M
+  extern __shared__ __align__(16) float m_sh[];     // part_r | part_s [warps][KPAD]; CACHED: then this CTA's rows of M
   __shared__ float g_sh[KPAD];
-  __shared__ float csum_sh[KPAD];
+  constexpr int NWARP = kSkThreads / 32;
+  float* const part_r = m_sh;
+  float* const part_s = m_sh + NWARP * KPAD;
+  float* const rows_sh = m_sh + 2 * NWARP * KPAD;
   const int tid = threadIdx.x;
   const long long per = (n + gridDim.x - 1) / gridDim.x;
   const long long r0 = per * blockIdx.x < n ? per * blockIdx.x : n;
   const long long r1 = r0 + per < n ? r0 + per : n;
-  for (int j = tid; j < KPAD; j += blockDim.x) { g_sh[j] = j < k ? g_io[j] : 0.f; csum_sh[j] = 0.f; }
+  for (int j = tid; j < KPAD; j += blockDim.x) g_sh[j] = j < k ? g_io[j] : 0.f;
   if (CACHED) {
     const long long cnt4 = (r1 - r0) * (KPAD / 4);
     const float4* src = reinterpret_cast<const float4*>(M + r0 * KPAD);
-    for (long long x = tid; x < cnt4; x += blockDim.x) reinterpret_cast<float4*>(m_sh)[x] = __ldg(src + x);
+    for (long long x = tid; x < cnt4; x += blockDim.x) reinterpret_cast<float4*>(rows_sh)[x] = __ldg(src + x);
   }
   __syncthreads();
-  const float a = (float)(1.0 / (double)n);
+  const double a = 1.0 / (double)n;
   const double logb = -log((double)k);
   unsigned bar_target = 0;
   long long it_global = 0;
@@ -206,11 +276,14 @@ sinkhorn_kernel(const float* __restrict__ M, long long n, int k, float* __restri
     const float scale = kLog2e / eps;
     for (int it = 0; it < stages.iters[s]; ++it, ++it_global) {
       double* cs = ws->colsum[it_global % 3];
-      if (r0 < r1) colsum_rows<KPAD>(CACHED ? m_sh : M, CACHED ? r0 : 0, r0, r1, g_sh, k, scale, a, csum_sh);
-      __syncthreads();
-      for (int j = tid; j < k; j += blockDim.x) {
-        if (csum_sh[j] != 0.f) atomicAdd(cs + j, (double)csum_sh[j]);
-        csum_sh[j] = 0.f;
+      if (r0 < r1) {
+        colsum_rows<KPAD>(CACHED ? rows_sh : M, CACHED ? r0 : 0, r0, r1, g_sh, k, scale, part_r, part_s);
+        __syncthreads();
+        for (int j = tid; j < k; j += blockDim.x) {
+          float R, S;
+          fold_parts(part_r, part_s, NWARP, KPAD, j, R, S);
+          if (S != 0.f) atomicAdd(cs + j, pair_to_double(R, S, a));
+        }
       }
       grid_barrier(&ws->barrier, bar_target);
       // every CTA applies the identical update to its private copy of g (and takes the identical
@@ -220,7 +293,7 @@ sinkhorn_kernel(const float* __restrict__ M, long long n, int k, float* __restri
       __syncthreads();
       for (int j = tid; j < k; j += blockDim.x) {
         const double c = __ldcg(cs + j);
-        g_sh[j] = (float)((double)g_sh[j] + (double)eps * (logb - log(fmax(c, kMinColSum))));
+        g_sh[j] = (float)((double)g_sh[j] + (double)eps * (logb - log(c)));
         if (blockIdx.x == 0) ws->colsum[(it_global + 2) % 3][j] = 0.0;
         const float e = (float)(fabs(c * (double)k - 1.0));
         atomicMax(reinterpret_cast<int*>(&err_sh), __float_as_int(e));       // e >= 0: int order == float order
@@ -239,8 +312,8 @@ sinkhorn_kernel(const float* __restrict__ M, long long n, int k, float* __restri
 // --------------------------------------------------------------------------- cluster Sinkhorn (small problems)
 // ml1m-sized grouping (n = 6040, k = 5: M is 386 KB) is pure latency: a grid barrier on 148 SMs per iteration
 // costs more than the iteration.  Here ONE thread-block cluster holds M in the shared memory of its CTAs, every CTA
-// pushes its k partial column sums into every peer's shared memory (distributed shared memory) and a hardware
-// cluster barrier ends the iteration; slot arrays alternate, so one barrier per iteration is enough.
+// pushes its k partial column sums -- (r, s) pairs -- into every peer's shared memory (distributed shared memory)
+// and a hardware cluster barrier ends the iteration; slot arrays alternate, so one barrier per iteration is enough.
 constexpr int kClusterMax = 8;
 
 template <int KPAD, int KS>                 // KS <= KPAD columns are kept in shared memory (k <= KS)
@@ -251,15 +324,18 @@ sinkhorn_cluster_kernel(const float* __restrict__ M, long long n, int k, float* 
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank(), CS = (int)cluster.num_blocks();
   extern __shared__ __align__(16) float m_sh[];     // this CTA's rows of M
+  constexpr int NWARP = kSkThreads / 32;
   __shared__ float g_sh[KS];
-  __shared__ __align__(16) float part_sh[kSkThreads / 32][KS];
-  __shared__ float slots[2][kClusterMax][KS];     // [parity][source CTA][column]
+  __shared__ __align__(16) float part_r[NWARP * KS];
+  __shared__ __align__(16) float part_s[NWARP * KS];
+  __shared__ float2 slots[2][kClusterMax][KS];     // [parity][source CTA][column] = (r, s)
   __shared__ float err_sh;
   const int tid = threadIdx.x;
   const long long per = (n + CS - 1) / CS;
   const long long r0 = per * rank < n ? per * rank : n;
   const long long r1 = r0 + per < n ? r0 + per : n;
   for (int j = tid; j < KS; j += blockDim.x) g_sh[j] = j < k ? g_io[j] : 0.f;
+  for (int x = tid; x < NWARP * KS; x += blockDim.x) { part_r[x] = kNoRef; part_s[x] = 0.f; }
   {
     const int cnt4 = (int)(r1 - r0) * (KS / 4);
     const float4* src = reinterpret_cast<const float4*>(M + r0 * KPAD);
@@ -267,7 +343,7 @@ sinkhorn_cluster_kernel(const float* __restrict__ M, long long n, int k, float* 
       reinterpret_cast<float4*>(m_sh)[x] = __ldg(src + (x / (KS / 4)) * (KPAD / 4) + x % (KS / 4));
   }
   cluster.sync();                                    // every CTA of the cluster is running: its shared memory exists
-  const float a = (float)(1.0 / (double)n);
+  const double log_a = -log((double)n);
   const double logb = -log((double)k);
   long long it_global = 0;
   float last_err = 0.f;
@@ -276,21 +352,25 @@ sinkhorn_cluster_kernel(const float* __restrict__ M, long long n, int k, float* 
     const float scale = kLog2e / eps;
     for (int it = 0; it < stages.iters[s]; ++it, ++it_global) {
       const int par = (int)(it_global & 1);
-      colsum_rows<KS>(m_sh, r0, r0, r1, g_sh, k, scale, a, nullptr, &part_sh[0][0]);   // every warp writes its slot
+      if (r0 < r1) colsum_rows<KS>(m_sh, r0, r0, r1, g_sh, k, scale, part_r, part_s);   // every warp writes its slot
       __syncthreads();
       if (tid < KS) {
-        float v = 0.f;
-#pragma unroll
-        for (int w = 0; w < kSkThreads / 32; ++w) v += part_sh[w][tid];
-        for (int r = 0; r < CS; ++r) *cluster.map_shared_rank(&slots[par][rank][tid], r) = v;
+        float R, S;
+        fold_parts(part_r, part_s, NWARP, KS, tid, R, S);
+        for (int r = 0; r < CS; ++r) *cluster.map_shared_rank(&slots[par][rank][tid], r) = make_float2(R, S);
       }
       if (tid == 0) err_sh = 0.f;
       cluster.sync();                                // all partial sums of this iteration have landed everywhere
       if (tid < k) {
+        float Rm = kNoRef;
+        for (int r = 0; r < CS; ++r) Rm = fmaxf(Rm, slots[par][r][tid].x);
         double c = 0.0;
-        for (int r = 0; r < CS; ++r) c += (double)slots[par][r][tid];       // same order in every CTA
-        g_sh[tid] = (float)((double)g_sh[tid] + (double)eps * (logb - log(fmax(c, kMinColSum))));
-        const float e = (float)(fabs(c * (double)k - 1.0));
+        for (int r = 0; r < CS; ++r)                                           // same order in every CTA
+          c += (double)slots[par][r][tid].y * (double)ex2_fast(slots[par][r][tid].x - Rm);
+        // log of the column sum with the exponent kept apart: no floor, no underflow
+        const double logc = log(c) + (double)Rm * 0.6931471805599453 + log_a;
+        g_sh[tid] = (float)((double)g_sh[tid] + (double)eps * (logb - logc));
+        const float e = (float)(fabs(exp(logc - logb) - 1.0));
         atomicMax(reinterpret_cast<int*>(&err_sh), __float_as_int(e));       // e >= 0: int order == float order
       }
       __syncthreads();
@@ -397,7 +477,7 @@ assign_centroid_kernel(const float* __restrict__ M, long long n, int k, int kpad
   float* my_acc = acc_sh + (size_t)(warp % copies) * kd;
   int* my_cnt = cnt_sh + (warp % copies) * k;
   __shared__ float g_sh[256];
-  for (int x = tid; x < k; x += blockDim.x) g_sh[x] = g[x];
+  for (int x = tid; x < k; x += blockDim.x) g_sh[x] = g ? g[x] : 0.f;
   for (int x = tid; x < copies * kd; x += blockDim.x) acc_sh[x] = 0.f;
   for (int x = tid; x < copies * k; x += blockDim.x) cnt_sh[x] = 0;
   __syncthreads();
@@ -413,7 +493,8 @@ assign_centroid_kernel(const float* __restrict__ M, long long n, int k, int kpad
         const long long row = row0 + lane;
         const bool valid = row < c1;
         int arg = 0;
-        if (valid) {
+        if (valid && !M) arg = label[row];              // labels given: sums only
+        if (valid && M) {
           float best = -INFINITY;
           const float4* mr = reinterpret_cast<const float4*>(M + row * kpad);
           for (int j4 = 0; j4 * 4 < k; ++j4) {
@@ -446,18 +527,22 @@ assign_centroid_kernel(const float* __restrict__ M, long long n, int k, int kpad
     for (long long row = c0 + warp; row < c1; row += n_warps) {
       float best = -INFINITY;
       int arg = 0x7fffffff;
-      for (int j = lane; j < k; j += 32) {
-        const float v = g_sh[j] - __ldg(M + row * kpad + j);
-        if (v > best) { best = v; arg = j; }
-      }
+      if (!M) {
+        arg = label[row];                               // labels given: sums only
+      } else {
+        for (int j = lane; j < k; j += 32) {
+          const float v = g_sh[j] - __ldg(M + row * kpad + j);
+          if (v > best) { best = v; arg = j; }
+        }
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-        const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
-        if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+          const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+          if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+        }
       }
       if (lane == 0) {
-        label[row] = arg;
+        if (M) label[row] = arg;
         if (exclusive) my_cnt[arg] += 1; else atomicAdd(&my_cnt[arg], 1);
       }
       if (X) {
@@ -500,7 +585,7 @@ assign_centroid_reg_kernel(const float* __restrict__ M, long long n, int k, int 
   __shared__ float fold_sh[NWARP][FA * 32];
   __shared__ int cnt_sh[NWARP][32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid < 32) g_sh[tid] = tid < k ? g[tid] : -INFINITY;
+  if (tid < 32) g_sh[tid] = (tid < k && g) ? g[tid] : -INFINITY;
   __syncthreads();
   float acc[KT][DT];
 #pragma unroll
@@ -514,7 +599,8 @@ assign_centroid_reg_kernel(const float* __restrict__ M, long long n, int k, int 
   for (long long row0 = r0 + (long long)warp * 32; row0 < r1; row0 += (long long)NWARP * 32) {
     const long long row = row0 + lane;
     int arg = -1;
-    if (row < r1) {
+    if (row < r1 && !M) arg = label[row];               // labels given (balanced rounding ran): sums only
+    if (row < r1 && M) {
       float best = -INFINITY;
       arg = 0;
       const float4* mr = reinterpret_cast<const float4*>(M + row * kpad);
@@ -626,7 +712,8 @@ extern "C" int ure_sinkhorn_colsum(const float* d_M, int64_t n, int k, int kpad,
   using namespace ure;
   if (int rc = check_mk(d_M, n, k, kpad, "ure_sinkhorn_colsum")) return rc;
   URE_REQUIRE(d_g && d_colsum && eps > 0.f && n_total >= 1.0, URE_EINVAL, "ure_sinkhorn_colsum: bad argument");
-  const float scale = kLog2e / eps, a = (float)(1.0 / n_total);
+  const float scale = kLog2e / eps;
+  const double a = 1.0 / n_total;
   long long blocks = (n + 2047) / 2048;
   const long long cap = (long long)num_sms() * 4;
   if (blocks > cap) blocks = cap;
@@ -666,7 +753,8 @@ extern "C" int ure_sinkhorn(const float* d_M, int64_t n, int k, int kpad, float*
   URE_CUDA(cudaMemsetAsync(ws, 0, sizeof(SkWorkspace), st));
   const int grid = num_sms();
   const long long per = (n + grid - 1) / grid;
-  const size_t need = (size_t)per * kpad * sizeof(float);
+  const size_t parts = 2 * (size_t)(kSkThreads / 32) * kpad * sizeof(float);   // per-warp (r, s) column partials
+  const size_t need = (size_t)per * kpad * sizeof(float) + parts;
   if (kpad <= 64) {
     // tiny problem: one thread-block cluster, M in its CTAs' shared memory, column sums exchanged through
     // distributed shared memory, a hardware cluster barrier per iteration
@@ -674,16 +762,20 @@ extern "C" int ure_sinkhorn(const float* d_M, int64_t n, int k, int kpad, float*
     const int ks = k <= 8 ? 8 : kpad;                // columns kept in shared memory
     const size_t need_c = (size_t)per_c * ks * sizeof(float);
     if (need_c <= 160 * 1024) {
-      if (ks == 8) {
-        URE_KPAD_SWITCH(kpad, return (launch_sinkhorn_cluster<KP, 8>(d_M, n, k, d_g, stg, ws, kClusterMax, need_c, st)));
-      }
-      URE_KPAD_SWITCH(kpad, return (launch_sinkhorn_cluster<KP, KP>(d_M, n, k, d_g, stg, ws, kClusterMax, need_c, st)));
+      // (only kpad <= 64 reaches this point: the static shared memory of the wider instantiations would not fit)
+#define URE_CLUSTER_CASE(KP)                                                                                      \
+  if (kpad == KP)                                                                                                 \
+    return ks == 8 ? launch_sinkhorn_cluster<KP, 8>(d_M, n, k, d_g, stg, ws, kClusterMax, need_c, st)             \
+                   : launch_sinkhorn_cluster<KP, KP>(d_M, n, k, d_g, stg, ws, kClusterMax, need_c, st);
+      URE_CLUSTER_CASE(16) URE_CLUSTER_CASE(32) URE_CLUSTER_CASE(64)
+#undef URE_CLUSTER_CASE
     }
   }
   if (need <= 200 * 1024) {
     // small problem: everything is latency -- one persistent launch, a CTA's rows cached in shared memory
     URE_KPAD_SWITCH(kpad, return (launch_sinkhorn<KP, true>(d_M, n, k, d_g, stg, ws, grid, need, st)));
   }
+  (void)parts;
   // large problem: one streaming pass per iteration at full occupancy (split-phase kernels, no host sync;
   // the early exit needs the column sums on the host, so every scheduled iteration runs)
   for (int s = 0; s < n_stages; ++s)
@@ -729,12 +821,11 @@ extern "C" int ure_assign_plan_f32(const float* d_plan, int64_t n, int k, int64_
   return 0;
 }
 
-extern "C" int ure_assign_centroids(const float* d_M, int64_t n, int k, int kpad, const float* d_g,
-                                    const float* d_X, int d, int32_t* d_label, double* d_sum, int64_t* d_cnt,
-                                    void* stream) {
-  using namespace ure;
-  if (int rc = check_mk(d_M, n, k, kpad, "ure_assign_centroids")) return rc;
-  URE_REQUIRE(d_g && d_label && d_cnt && (!d_X || (d_sum && d > 0)), URE_EINVAL, "ure_assign_centroids: bad argument");
+namespace ure {
+// d_M == NULL: the labels are an input (after the balanced rounding) and only the sums / counts are computed
+static int assign_centroids_impl(const float* d_M, int64_t n, int k, int kpad, const float* d_g,
+                                 const float* d_X, int d, int32_t* d_label, double* d_sum, int64_t* d_cnt,
+                                 void* stream) {
   const int dd = d_X ? d : 0;
   {
     // register path: k <= 32 and at most 64 accumulators per lane
@@ -773,4 +864,22 @@ extern "C" int ure_assign_centroids(const float* d_M, int64_t n, int k, int kpad
       d_M, n, k, kpad, d_g, d_X, dd, d_label, d_sum, reinterpret_cast<long long*>(d_cnt), 4096, copies);
   URE_CUDA(cudaGetLastError());
   return 0;
+}
+}  // namespace ure
+
+extern "C" int ure_assign_centroids(const float* d_M, int64_t n, int k, int kpad, const float* d_g,
+                                    const float* d_X, int d, int32_t* d_label, double* d_sum, int64_t* d_cnt,
+                                    void* stream) {
+  using namespace ure;
+  if (int rc = check_mk(d_M, n, k, kpad, "ure_assign_centroids")) return rc;
+  URE_REQUIRE(d_g && d_label && d_cnt && (!d_X || (d_sum && d > 0)), URE_EINVAL, "ure_assign_centroids: bad argument");
+  return assign_centroids_impl(d_M, n, k, kpad, d_g, d_X, d, d_label, d_sum, d_cnt, stream);
+}
+
+extern "C" int ure_centroid_sums(const float* d_X, int64_t n, int d, const int32_t* d_label, int k, double* d_sum,
+                                 int64_t* d_cnt, void* stream) {
+  using namespace ure;
+  URE_REQUIRE(d_X && d_label && d_sum && d_cnt && n > 0 && d > 0 && k >= 1 && k <= 256, URE_EINVAL,
+              "ure_centroid_sums: bad argument");
+  return assign_centroids_impl(nullptr, n, k, 16, nullptr, d_X, d, const_cast<int32_t*>(d_label), d_sum, d_cnt, stream);
 }

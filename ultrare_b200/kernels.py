@@ -392,6 +392,7 @@ class ShardBatch:
         if mode not in ("dense", "lazy", "owner", "auto"):
             raise ValueError(f"mode {mode!r}")
         self.shards = shards
+        self.n_shards = len(shards)
         self.device = shards[0].P.device
         self.epochs = shards[0].epochs
         assert all(s.epochs == self.epochs for s in shards)
@@ -403,6 +404,7 @@ class ShardBatch:
                             owner_spe_cap=0, owner_sched_rows=0, owner_sched=None, owner_sched_off=None,
                             owner_sched_step0=0, owner_sched_stride=0)
         self.owner_plan = None
+        self.launches_per_pass = 0          # kernels of ours this batch has launched (set-up + schedule + training)
         self._owner_cache = bool(owner_cache)       # False: keep the records in L2 (tests of the uncached variant)
         self.warps_group0 = self._split_groups(shards)   # before the first table upload: descriptors are final
         if mode in ("owner", "auto"):
@@ -480,6 +482,7 @@ class ShardBatch:
         while npass < 4 and (max_rows - 1) >> (8 * npass):
             npass += 1
         self.prepare_launches = 2 + 3 * npass + 1 + 1     # count + scan, radix passes, perm inverse, plan
+        self.launches_per_pass += self.prepare_launches
         with torch.cuda.device(dev):
             check(L.ure_mf_owner_prepare(_ptr(self.table), len(shards), C.byref(self.hp), self.epochs, int(max_rows),
                                          _ptr(radix), _ptr(self.ws), _stream()), "ure_mf_owner_prepare")
@@ -535,6 +538,7 @@ class ShardBatch:
         self.hp.mode = _lib.MF_OWNER
         self.hp.owner_cap_rows, self.hp.owner_cap_slots, self.hp.owner_spe_cap = cap_rows, cap_slots, spe_cap
         self.hp.owner_flags, self.hp.owner_cap_list = int(flags), int(cap_list)
+        self.hp.owner_max_n = max(s.n for s in shards)
         self.hp.owner_sched, self.hp.owner_sched_off = self._sched.data_ptr(), self._sched_off.data_ptr()
         self.hp.owner_sched_rows, self.hp.owner_sched_stride, self.hp.owner_sched_step0 = n_rows, stride, 0
         tq.append(time.perf_counter())
@@ -571,16 +575,26 @@ class ShardBatch:
                     # the schedule tables hold owner_sched_rows epochs per shard from the window's first step on
                     a, b = self._sched_cover
                     if not (a <= self.step < b):
-                        check(L.ure_mf_owner_schedule(_ptr(self.table), len(self.shards), C.byref(self.hp), self.epochs,
+                        check(L.ure_mf_owner_schedule(_ptr(self.table), self.n_shards, C.byref(self.hp), self.epochs,
                                                       self.step, _stream()), "ure_mf_owner_schedule")
+                        self.launches_per_pass += 1
                         a = self.step                  # shard s leaves the window at step (a // spe_s + rows) * spe_s
                         b = min([(a // spe + self.hp.owner_sched_rows) * spe for spe in self._spes
                                  if a // spe + self.hp.owner_sched_rows < self.epochs] or [self.total_steps])
                         self._sched_cover, self.hp.owner_sched_step0 = (a, b), a
                     t1 = min(step_end, b)
-                check(L.ure_mf_train(_ptr(self.table), len(self.shards), C.byref(self.hp), self.epochs,
+                check(L.ure_mf_train(_ptr(self.table), self.n_shards, C.byref(self.hp), self.epochs,
                                      self.step, t1, self.warps_group0, _ptr(self.ws), _stream()), "ure_mf_train")
+                self.launches_per_pass += 1
                 self.step = t1
+
+    def reset_for_rerun(self) -> None:
+        """Back to step 0 with zero momentum and losses (the weights stay): bench.py times the training launch alone."""
+        for st in self.shards:
+            st.bufP.zero_()
+            st.bufQ.zero_()
+            st.sse.zero_()
+        self.step = 0
 
     def flush(self) -> None:
         """Lazy mode: advance every row to the current step (call before reading P / Q)."""
@@ -595,7 +609,7 @@ class ShardBatch:
     def train_losses_async(self):
         """train_losses without the wait: the D2H copies are queued behind the work already on the stream and the
         returned callable waits for them when the values are needed (the host keeps launching meanwhile)."""
-        sse = torch.stack([s.sse for s in self.shards])
+        sse = self._sse_matrix()
         K, E = sse.shape
         nb = sse.numel() * 8
         owner = self.mode == "owner"
@@ -606,7 +620,7 @@ class ShardBatch:
                 host[nb:nb + 4].copy_(self.ws[16:20], non_blocking=True)
             ev = torch.cuda.Event()
             ev.record()
-        ns = [max(1, s.n) for s in self.shards]
+        ns = self._shard_sizes()
 
         def wait() -> List[np.ndarray]:
             ev.synchronize()
@@ -618,9 +632,170 @@ class ShardBatch:
             return [np.sqrt(vals[j] / ns[j]) for j in range(K)]
         return wait
 
+    def _sse_matrix(self) -> torch.Tensor:
+        return torch.stack([s.sse for s in self.shards])
+
+    def _shard_sizes(self):
+        return [max(1, s.n) for s in self.shards]
+
     def train_losses(self) -> List[np.ndarray]:
         """Per shard: sqrt(sse_epoch / n) for every epoch (utils.py:108).  Synchronises (one D2H)."""
         return self.train_losses_async()()
+
+
+class ShardView:
+    """One shard of an ArenaShardBatch: the tensors ShardState exposes, as views into the arena (made on demand)."""
+
+    def __init__(self, inter, P, Q, bufP, bufQ, gP, gQ, sse, n, shard_id, perm_seed, epochs, perm=None):
+        self.inter, self.P, self.Q, self.bufP, self.bufQ, self.gP, self.gQ, self.sse = inter, P, Q, bufP, bufQ, gP, gQ, sse
+        self.n, self.shard_id, self.perm_seed, self.epochs, self.perm = n, shard_id, perm_seed, epochs, perm
+
+    def steps_per_epoch(self, batch: int) -> int:
+        return -(-self.n // batch)
+
+
+class ArenaShardBatch(ShardBatch):
+    """ShardBatch whose whole device state is ONE allocation laid out, described and prepared by the native runtime
+    (csrc/mf_batch.cu: ure_mf_batch_layout / _setup / _plan): the host makes one allocation, one library call that
+    queues the descriptor upload, the clears and the owner set-up kernels, one N(0, std) fill of the weights, and
+    reads the 16-byte plan -- no per-shard tensors exist before the training launch is queued (the per-shard views
+    of `shards` are built on first use, while the GPU trains).
+
+    recs: per shard the device records (user field = row of the shard's table); rows_P: rows of every user table."""
+
+    def __init__(self, recs, rows_P, n_item: int, d: int, batch: int, epochs: int, shard_ids, perm_seed: int = 42,
+                 perms=None, lr: float = 1e-3, lr_decay: float = 0.95, lr_step: int = 50, weight_decay: float = 0.1,
+                 momentum: float = 0.9, generator=None, std: float = 1.0, mode: str = "auto", owner_cache: bool = True):
+        K = self.n_shards = len(recs)
+        if not 1 <= K <= _lib.URE_MAX_SHARDS:
+            raise ValueError(f"1..{_lib.URE_MAX_SHARDS} shards per launch")
+        if mode not in ("dense", "owner", "auto"):
+            raise ValueError(f"mode {mode!r}")
+        _need_cuda(*recs)
+        L = _lib.lib()
+        self.device = dev = recs[0].device
+        self.epochs, self.lazy, self.decay = int(epochs), False, None
+        self._recs, self._perms = list(recs), (list(perms) if perms is not None else [None] * K)
+        self._rows_P, self._n_item, self._shard_ids = [int(r) for r in rows_P], int(n_item), [int(x) for x in shard_ids]
+        self._perm_seed = int(perm_seed) & 0xFFFFFFFF
+        ns = [int(r.shape[0]) for r in recs]
+        self._ns = ns
+        self.total_steps = max(-(-n // batch) for n in ns) * self.epochs
+        self.hp = MFHParams(d=d, batch=batch, lr0=lr, lr_decay=lr_decay, lr_step=lr_step, weight_decay=weight_decay,
+                            momentum=momentum, mode=_lib.MF_DENSE)
+        self.owner_plan, self.launches_per_pass, self._shards = None, 0, None
+        # warp groups of the DENSE schedule (greedy halves by interaction count)
+        groups, load = [0] * K, [0, 0]
+        if K >= 2:
+            for j in sorted(range(K), key=lambda j: -ns[j]):
+                g = 0 if load[0] <= load[1] else 1
+                groups[j] = g
+                load[g] += ns[j]
+            w0 = int(round(32 * load[0] / max(1, load[0] + load[1])))
+            self.warps_group0 = min(32 - 6, max(6, w0))
+        else:
+            self.warps_group0 = 32
+        hs = (_lib.MFBatchShard * K)()
+        for j in range(K):
+            p = self._perms[j]
+            if p is not None:
+                assert p.dtype == torch.int32 and tuple(p.shape) == (self.epochs, ns[j]) and p.is_contiguous()
+            hs[j].inter, hs[j].perm = recs[j].data_ptr(), (p.data_ptr() if p is not None else None)
+            hs[j].n, hs[j].n_user, hs[j].shard_id, hs[j].group = ns[j], self._rows_P[j], self._shard_ids[j], groups[j]
+        lay = _lib.MFBatchLayout()
+        check(L.ure_mf_batch_layout(hs, K, n_item, d, batch, self.epochs, int(mode in ("owner", "auto")), OWNER_SCHED_BYTES,
+                                    C.byref(lay)), "ure_mf_batch_layout")
+        if mode == "owner" and not lay.owner:
+            raise RuntimeError("owner mode does not fit this problem (row state beyond the SMs' shared memory)")
+        self._lay = lay
+        self.arena = torch.empty(int(lay.total), dtype=torch.uint8, device=dev)
+        base = self.arena.data_ptr()
+        stage = _staging_bytes(176 * K + 64)
+        with torch.cuda.device(dev):
+            check(L.ure_mf_batch_setup(hs, K, n_item, C.byref(self.hp), self.epochs, self._perm_seed, C.c_void_p(base),
+                                       C.byref(lay), C.c_void_p(stage.data_ptr()), _stream()), "ure_mf_batch_setup")
+            if lay.owner:
+                npass = 1
+                while npass < 4 and (int(lay.max_rows) - 1) >> (8 * npass):
+                    npass += 1
+                self.prepare_launches = 2 + 3 * npass + 1 + 1
+                self.launches_per_pass += self.prepare_launches
+            ev = torch.cuda.Event()
+            ev.record()
+            # weights: N(0, std) (reference utils.py:38-40), queued behind the set-up kernels
+            rows_w = int(lay.rows_total) + K * n_item
+            self._W = self.arena[int(lay.W):int(lay.W) + rows_w * d * 4].view(torch.float32).view(rows_w, d)
+            self._W.normal_(0.0, std, generator=generator)
+        self.table_ptr = base + int(lay.table)
+        self.ws = self.arena[int(lay.ws):int(lay.ws) + int(L.ure_mf_train_workspace_bytes())]
+        self.mode = "dense"
+        if lay.owner:
+            t0 = time.perf_counter()
+            ev.synchronize()                                 # the one wait of the set-up: upload + sorts + plan
+            self.plan_sync_ms = (time.perf_counter() - t0) * 1e3
+            plan = stage[176 * K:176 * K + 16].view(torch.int32)
+            info = (C.c_int32 * 8)()
+            force = OWNER_FORCE if OWNER_FORCE is not None else (-1, 0)
+            rc = L.ure_mf_batch_plan(C.c_void_p(plan.data_ptr()), K, C.byref(self.hp), C.c_void_p(base), C.byref(lay),
+                                     int(bool(owner_cache)), int(force[0]), int(force[1]), info)
+            if rc < 0:
+                check(rc, "ure_mf_batch_plan")
+            self.owner_plan = dict(zip(("fits", "flags", "list_cap", "max_rows_per_cta", "max_slots_per_cta",
+                                        "max_steps_per_epoch", "smem_need", "smem_avail"), list(info)))
+            self.owner_plan["cached"] = bool(info[1] & 1) if info[1] >= 0 else False
+            if rc == 1:
+                self.mode = "owner"
+                self._sched_cover = (0, 0)
+                self._spes = [-(-n // batch) for n in ns if n > 0]
+            elif mode == "owner":
+                raise RuntimeError(f"owner mode does not fit this problem: {self.owner_plan}")
+        _PINNED_BYTES.setdefault(stage.shape[0], []).append((stage, ev))
+        self.step = 0
+
+    # ---- what ShardBatch reads through self.table / self.shards
+    @property
+    def table(self):
+        return _RawPtr(self.table_ptr)
+
+    @property
+    def shards(self):
+        if self._shards is None:
+            lay, d, K, E = self._lay, self.hp.d, len(self._recs), max(1, self.epochs)
+            rows_w = int(lay.rows_total) + K * self._n_item
+            Z = self.arena[int(lay.Z):int(lay.Z) + 2 * rows_w * d * 4].view(torch.float32).view(2, rows_w, d)
+            sse = self.arena[int(lay.sse):int(lay.sse) + K * E * 8].view(torch.float64).view(K, E)
+            out, o = [], 0
+            for j in range(K):
+                r, q = self._rows_P[j], int(lay.rows_total) + j * self._n_item
+                out.append(ShardView(self._recs[j], self._W[o:o + r], self._W[q:q + self._n_item], Z[0, o:o + r],
+                                     Z[0, q:q + self._n_item], Z[1, o:o + r], Z[1, q:q + self._n_item], sse[j],
+                                     self._ns[j], self._shard_ids[j], self._perm_seed, self.epochs, self._perms[j]))
+                o += r
+            self._shards = out
+        return self._shards
+
+    def _upload_table(self):
+        pass                                   # the descriptor table lives in the arena and never changes
+
+    def _sse_matrix(self) -> torch.Tensor:
+        lay, K, E = self._lay, self.n_shards, max(1, self.epochs)
+        return self.arena[int(lay.sse):int(lay.sse) + K * E * 8].view(torch.float64).view(K, E)
+
+    def _shard_sizes(self):
+        return [max(1, n) for n in self._ns]
+
+    def interactions_trained(self) -> int:
+        return sum(self._ns) * self.epochs
+
+
+class _RawPtr:
+    """A bare device address with the one method _ptr() needs."""
+
+    def __init__(self, p):
+        self._p = int(p)
+
+    def data_ptr(self):
+        return self._p
 
 
 def alloc_shard_batch(rows_P: Sequence[int], n_item: int, d: int, epochs: int, device, generator=None, std=1.0,
@@ -781,6 +956,22 @@ def sinkhorn(M, k, eps_schedule, g=None, tol: float = 0.0) -> torch.Tensor:
     return g
 
 
+def sinkhorn_sharded(M, k, eps_schedule, dist, n_total, g=None) -> torch.Tensor:
+    """Sinkhorn with the users (rows of M) sharded over the ranks of `dist`: every iteration is one column pass per
+    rank, an all-reduce of the kpad column marginals over the GPUs, and the potential update (replicated).  One rank:
+    the single-GPU solver.  Returns g fp32 [k] (identical on every rank)."""
+    if dist is None or dist.world == 1:
+        return sinkhorn(M, k, eps_schedule, g=g)
+    g = torch.zeros(k, dtype=torch.float32, device=M.device) if g is None else g.clone()
+    colsum = torch.zeros(M.shape[1], dtype=torch.float64, device=M.device)
+    for eps, iters in eps_schedule:
+        for _ in range(int(iters)):
+            sinkhorn_colsum(M, k, g, eps, n_total, colsum)
+            dist.all_reduce(colsum)
+            sinkhorn_update_g(g, colsum, k, eps)
+    return g
+
+
 def sinkhorn_colsum(M, k, g, eps, n_total, colsum) -> None:
     with torch.cuda.device(M.device):
         check(_lib.lib().ure_sinkhorn_colsum(_ptr(M), M.shape[0], k, M.shape[1], _ptr(g), float(eps),
@@ -827,3 +1018,30 @@ def assign_centroids(M, k, g, X=None):
         check(_lib.lib().ure_assign_centroids(_ptr(M), n, k, kp, _ptr(g), _ptr(X), d, _ptr(label), _ptr(sums),
                                               _ptr(cnt), _stream()), "ure_assign_centroids")
     return label, sums, cnt
+
+
+def centroid_sums(X, label, k):
+    """(sums fp64 [k,d], counts int64 [k]) of utils.py:648 for given labels (ure_centroid_sums)."""
+    _need_cuda(X, label)
+    n, d = X.shape
+    sums = torch.zeros((k, d), dtype=torch.float64, device=X.device)
+    cnt = torch.zeros(k, dtype=torch.int64, device=X.device)
+    with torch.cuda.device(X.device):
+        check(_lib.lib().ure_centroid_sums(_ptr(X), n, d, _ptr(label), k, _ptr(sums), _ptr(cnt), _stream()),
+              "ure_centroid_sums")
+    return sums, cnt
+
+
+def balance_labels(M, k, label, cnt, max_aug: int = 1 << 14):
+    """Balanced rounding in place (ure_balance_labels): `label` int32 [n] / `cnt` int64 [k] = an argmax assignment
+    and its group sizes; afterwards every group holds floor(n/k)..ceil(n/k) users at minimum total cost.  Returns
+    the int32 status tensor [3] = (augmentations, users still to move, gave-up flag) -- on the device, no sync."""
+    _need_cuda(M, label, cnt)
+    n, kp = M.shape
+    assert label.dtype == torch.int32 and cnt.dtype == torch.int64 and label.shape[0] == n
+    L = _lib.lib()
+    ws = torch.empty(int(L.ure_balance_workspace_bytes(k)), dtype=torch.uint8, device=M.device)
+    with torch.cuda.device(M.device):
+        check(L.ure_balance_labels(_ptr(M), n, k, kp, _ptr(label), _ptr(cnt), int(max_aug), _ptr(ws), _stream()),
+              "ure_balance_labels")
+    return ws[128:140].view(torch.int32)

@@ -218,44 +218,44 @@ class Sisa(Scratch):
         t0 = time.time()
         models, states, snaps, losses = {}, [], {}, []
         if mine:
-            # default init: ONE allocation + one normal_() for every shard of the launch (device RNG);
-            # an overridden _new_model (parity runs inject weights) or host-seeded init goes shard by shard
+            # default init: the native batch runtime (kernels.ArenaShardBatch) -- ONE allocation, one library call
+            # that queues the descriptor table, the clears and the owner set-up, one normal_() for every table of
+            # the launch (device RNG); an overridden _new_model (parity runs inject weights), host-seeded init or
+            # explicit visiting orders go shard by shard
             batched = self.init_on_device and type(self)._new_model is Scratch._new_model
             # the staging copies of the shards' records run on worker threads while the models are allocated
             from ..read import RatingData
+            from .utils import MF
             uploaded = RatingData.upload_many([train_dlist[i].dataset for i in mine], self.device,
                                               self._row_of if compact else None, 'sisa_local' if compact else None,
                                               defer=True)
-            if batched:
-                from .scratch import model_generator
-                from .utils import MF
-                rows = [len(self.group_index[i]) if compact else self.n_user for i in mine]
-                views, init_models = kn.alloc_shard_batch(rows, self.n_item, self.k, E, self.device,
-                                                          model_generator(self.seed, mine[0] + 1, self.device),
-                                                          defer_init=True)
             t_a = time.time()
             uploaded()
-            for j, i in enumerate(mine):
-                ld = train_dlist[i]
-                rec = (ld.dataset.records_mapped(self.device, self._row_of, 'sisa_local') if compact
-                       else ld.dataset.records(self.device))
-                scratch = None
-                if batched:                 # the nn.Module wrappers are built while the GPU trains (below)
-                    P, Q, scratch = views[j]
-                else:
-                    models[i] = self._new_model(i + 1, user_rows=self._rows(i)) if compact else self._new_model(i + 1)
-                    P, Q = models[i].user_mat.weight.data, models[i].item_mat.weight.data
-                states.append(kn.ShardState(rec, P, Q, E, shard_id=i + 1, perm_seed=self.seed,
-                                            perm=ld.explicit_perm(self.device, E), scratch=scratch))
+            recs = [(train_dlist[i].dataset.records_mapped(self.device, self._row_of, 'sisa_local') if compact
+                     else train_dlist[i].dataset.records(self.device)) for i in mine]
             batch = train_dlist[mine[0]].batch_size
             t_b = time.time()
-            # default init: the normal_ / zero fills are queued behind the owner set-up's sorts (which only read
-            # the records), so the GPU sorts while the host is still launching
-            sb = kn.ShardBatch(states, self.k, batch, self.lr, self.lr_decay, 50, self.lam, self.momentum,
-                               after_prepare=init_models if batched else None)
+            if batched:
+                from .scratch import model_generator
+                rows = [len(self.group_index[i]) if compact else self.n_user for i in mine]
+                perms = [train_dlist[i].explicit_perm(self.device, E) for i in mine]
+                sb = kn.ArenaShardBatch(recs, rows, self.n_item, self.k, batch, E, [i + 1 for i in mine], self.seed,
+                                        perms if any(p is not None for p in perms) else None, self.lr, self.lr_decay,
+                                        50, self.lam, self.momentum,
+                                        generator=model_generator(self.seed, mine[0] + 1, self.device))
+                states = None
+            else:
+                for j, i in enumerate(mine):
+                    models[i] = self._new_model(i + 1, user_rows=self._rows(i)) if compact else self._new_model(i + 1)
+                    P, Q = models[i].user_mat.weight.data, models[i].item_mat.weight.data
+                    states.append(kn.ShardState(recs[j], P, Q, E, shard_id=i + 1, perm_seed=self.seed,
+                                                perm=train_dlist[i].explicit_perm(self.device, E)))
+                sb = kn.ShardBatch(states, self.k, batch, self.lr, self.lr_decay, 50, self.lam, self.momentum)
             self.timing['setup_alloc_ms'] = (t_a - t0) * 1e3
             self.timing['setup_upload_states_ms'] = (t_b - t_a) * 1e3
             self.timing['setup_batch_ms'] = (time.time() - t_b) * 1e3
+            if states is None and mode == 'faithful':
+                states = sb.shards
             if mode == 'faithful':
                 need = sum((s.P.numel() + s.Q.numel()) * 4 for s in states) * E
                 if need > 8 << 30:
@@ -277,6 +277,7 @@ class Sisa(Scratch):
                 sb.train()
                 self.timing['launch_ms'] = (time.time() - t0) * 1e3 - self.timing['setup_ms']
                 if batched:
+                    states = sb.shards                                  # the per-shard views, while the GPU trains
                     for j, i in enumerate(mine):
                         models[i] = MF.wrap(states[j].P, states[j].Q)
                 # while the GPU trains: the model wrappers, and what the final evaluation needs (upload + user
@@ -294,6 +295,7 @@ class Sisa(Scratch):
                         ds.records(self.device)
                         ds.segments(self.device, self.n_user)
             if batched and not models:
+                states = sb.shards
                 for j, i in enumerate(mine):
                     models[i] = MF.wrap(states[j].P, states[j].Q)
             self._last_batch = sb
@@ -466,7 +468,7 @@ class Sisa(Scratch):
         self._test_dlist = test_dlist
         t_begin = time.perf_counter()
         flags = self.route(del_user)
-        self.retrain_gid = set(int(s) for s in np.flatnonzero(flags.cpu().numpy()))
+        self.retrain_gid = set(int(s) for s in np.flatnonzero(kn.download_many([flags])[0]))   # pinned read-back
         self.timing['route_ms'] = (time.perf_counter() - t_begin) * 1e3
         order = sorted(self.retrain_gid)
         model_before_unlearn = self.model_list[0]                               # sisa.py:84
@@ -493,6 +495,8 @@ class Sisa(Scratch):
         t_t = time.perf_counter()
         self.test(test_data, verbose, save_dir)
         self.timing['merge_ms'] = (t_t - t_m) * 1e3
+        # kernels of ours outside the training batch: route, merge (twice when sharded over GPUs), score, ranking
+        self.timing['own_launches_outside_batch'] = 1 + (2 if self.dist.world > 1 else 1) + 2
         self._flush_logs()
         self._join_writers()
         self.timing['test_ms'] = (time.perf_counter() - t_t) * 1e3

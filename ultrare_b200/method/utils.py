@@ -226,26 +226,33 @@ SINKHORN_SCHEDULE = ((1.0, 10), (0.3, 20), (0.1, 30), (0.03, 60), (0.01, 120))
 # fixed schedule itself only reaches ~3e-5 at its last stage, so nothing is lost.
 SINKHORN_TOL = 2e-5
 # Outer iterations after the first start from the previous potentials (the fixed point at a given eps does
-# not depend on the start) and run only the last WARM_STAGES stages of the schedule.
+# not depend on the start) and run only the last WARM_STAGES stages of the schedule.  The column sums are kept in
+# the log domain (csrc/ot_sinkhorn.cu), so potentials that are stale by hundreds of eps after a large centroid move
+# recover in one iteration instead of underflowing.
 SINKHORN_WARM_STAGES = 2
-# ... unless the assignment that comes out is further than this from n/k users per centroid (relative): then the
-# iteration is solved again from a cold start (see ot_cluster_device)
-WARM_START_MAX_IMBALANCE = 0.25
+# Balanced rounding (csrc/ot_balance.cu): at most this many augmenting paths per outer iteration
+BALANCE_MAX_AUGMENTATIONS = 1 << 14
 
 
 def ot_cluster_device(X, k, max_iters=10, schedule=SINKHORN_SCHEDULE, centroid0=None, device=None, dist=None,
-                      tol=SINKHORN_TOL, warm_start=True):
+                      tol=SINKHORN_TOL, warm_start=True, balance=True):
     """Balanced OT clustering on the GPU; returns (inertia, label int64 ndarray, centroid, n_outer).
 
-    With ``dist`` (ultrare_b200.dist.Dist, world_size > 1) X is this rank's row block and the
-    column marginals / centroid sums are all-reduced.
+    Per outer iteration (reference utils.py:635-654): cost matrix (tcgen05), Sinkhorn potentials, argmax labels,
+    then -- ``balance`` -- the balanced rounding that moves the few users the entropic plan leaves on the wrong side
+    along shortest augmenting paths, so that every group holds floor(n/k)..ceil(n/k) users at minimum cost, which is
+    what the reference's exact ``ot.emd`` plan gives (utils.py:644-647); centroids from the final labels.
+
+    With ``dist`` (ultrare_b200.dist.Dist, world_size > 1) X is this rank's row block, the column marginals /
+    centroid sums are all-reduced and the rounding is skipped (the cost rows live on different GPUs).
     """
     dev = _cuda_device(device)
     X = np.ascontiguousarray(X, dtype=np.float32)
     n_local, d = X.shape
-    n = n_local if dist is None else dist.sum_int(n_local)
+    sharded = dist is not None and dist.world > 1
+    n = dist.sum_int(n_local) if sharded else n_local
     if centroid0 is None:
-        if dist is not None and dist.world > 1:
+        if sharded:
             raise ValueError("distributed ot_cluster needs explicit initial centroids")
         centroid = X[np.random.choice(n, size=k, replace=False)]           # reference utils.py:632
     else:
@@ -255,7 +262,8 @@ def ot_cluster_device(X, k, max_iters=10, schedule=SINKHORN_SCHEDULE, centroid0=
     d_pad = next(v for v in (8, 16, 32, 64, 128) if v >= d)      # zero columns do not change the cost
     Xp = np.zeros((n_local, d_pad), dtype=np.float32)
     Xp[:, :d] = X
-    Xd = torch.from_numpy(Xp).to(dev)
+    Xd = kn.upload_table(Xp, dev)
+    balance = balance and not sharded and 1 < k <= 128
     label = None
     g = None
     inertia = 0.0
@@ -263,46 +271,36 @@ def ot_cluster_device(X, k, max_iters=10, schedule=SINKHORN_SCHEDULE, centroid0=
     for it in range(1, max_iters + 1):
         Cp = np.zeros((k, d_pad), dtype=np.float32)
         Cp[:, :d] = centroid
-        Cd = torch.from_numpy(Cp).to(dev)
+        Cd = kn.upload_array(Cp, dev)
         M, inert = kn.cost_matrix(Xd, Cd, want_inertia=True)                # utils.py:637-638
-        if dist is not None and dist.world > 1:
+        if sharded:
             dist.all_reduce(inert)
-        inertia = float(inert.item())
+        inertia = float(kn.download_many([inert])[0][0])
         scale = max(inertia / n, 1e-30)
         warm = warm_start and it > 1
-
-        def solve(warm, g):
-            """Sinkhorn potentials for this cost matrix + the assignment they induce (counts / sums over all ranks)."""
-            sched = [(e * scale, i) for e, i in (schedule[-SINKHORN_WARM_STAGES:] if warm else schedule)]
-            if dist is None or dist.world == 1:
-                g = kn.sinkhorn(M, k, sched, g=g if warm else None, tol=tol)    # replaces ot.emd, utils.py:641-644
-            else:
-                g = g.clone() if warm else torch.zeros(k, dtype=torch.float32, device=dev)
-                colsum = torch.zeros(M.shape[1], dtype=torch.float64, device=dev)
-                for eps, iters in sched:
-                    for _ in range(iters):
-                        kn.sinkhorn_colsum(M, k, g, eps, n, colsum)
-                        dist.all_reduce(colsum)
-                        kn.sinkhorn_update_g(g, colsum, k, eps)
-            lab, sums, cnt = kn.assign_centroids(M, k, g, Xd)                   # utils.py:647-648
-            if dist is not None and dist.world > 1:
-                dist.all_reduce(sums)
-                dist.all_reduce(cnt)
-            return g, lab, sums, cnt
-
-        g_new, lab, sums, cnt = solve(warm, g)
-        cnt_h = cnt.cpu().numpy()
-        if warm and np.abs(cnt_h[:k] - n / k).max() > WARM_START_MAX_IMBALANCE * n / k:
-            # The warm start skips the large-eps stages.  When the centroids moved far (early outer iterations from a
-            # random-user start) the old potentials can leave a centroid without any mass at the small eps: its fp32
-            # column sum underflows to zero, the potential diverges and every user lands on one centroid.  A balanced
-            # plan gives every centroid n/k users, so an assignment this far off is redone from a cold start.
-            g_new, lab, sums, cnt = solve(False, None)
-            cnt_h = cnt.cpu().numpy()
-        g = g_new
-        label = lab
-        with np.errstate(invalid="ignore", divide="ignore"):
-            new_centroid = (sums.cpu().numpy()[:, :d] / cnt_h[:, None]).astype(np.float32)
+        sched = [(e * scale, i) for e, i in (schedule[-SINKHORN_WARM_STAGES:] if warm else schedule)]
+        if not sharded:
+            g = kn.sinkhorn(M, k, sched, g=g if warm else None, tol=tol)    # replaces ot.emd, utils.py:641-644
+        else:
+            g = kn.sinkhorn_sharded(M, k, sched, dist, n, g=g if warm else None)
+        label, _, cnt = kn.assign_centroids(M, k, g, None)                  # utils.py:647 (argmax of the plan row)
+        status = kn.balance_labels(M, k, label, cnt, BALANCE_MAX_AUGMENTATIONS) if balance else None
+        sums, cnt = kn.centroid_sums(Xd, label, k)                          # utils.py:648
+        if sharded:
+            dist.all_reduce(sums)
+            dist.all_reduce(cnt)
+        got = kn.download_many([sums, cnt, g] + ([status] if balance else []))        # the iteration's one sync
+        sums_h, cnt_h, g_h = got[0], got[1], got[2]
+        if not np.isfinite(g_h).all():
+            raise RuntimeError(f"ot_cluster: Sinkhorn potentials are not finite ({g_h}); non-finite embedding or "
+                               f"centroid?")
+        if (cnt_h[:k] == 0).any():
+            raise RuntimeError(f"ot_cluster: empty group (sizes {cnt_h[:k].tolist()}); the plan is degenerate")
+        if balance and (got[3][1] != 0 or got[3][2] != 0):
+            import warnings
+            warnings.warn(f"ot_cluster: balanced rounding stopped early ({int(got[3][0])} augmentations, "
+                          f"{int(got[3][1])} users still to move); group sizes {cnt_h[:k].tolist()}")
+        new_centroid = (sums_h[:, :d] / cnt_h[:, None]).astype(np.float32)
         if np.allclose(centroid, new_centroid):                              # utils.py:651
             break
         centroid = new_centroid

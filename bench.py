@@ -371,7 +371,7 @@ def run_c2_ours(args):
                 ts.append((time.perf_counter() - t0) * 1e3)
             modes[mode] = {"ms": float(min(ts)), "total_rmse": float(un_m.final_log["total_rmse"])}
         line["epoch_eval_modes"] = modes
-        line["c4_strong"] = shard_training_leg("c4", d, dev, steps=60, reps=2)
+        line["c4_strong"] = shard_training_leg("c4", d, dev, steps=100, reps=2)
     if rank == 0 and world == 1 and not args.no_cpu:
         # ---- the CPU port on the SAME groups, initial weights and visiting orders: the baseline and the checker
         class HostInitSisa(Sisa):
@@ -533,8 +533,8 @@ def shard_training_leg(name, d_, dev, steps=None, reps=3, mode="auto", e2e=False
                 rec = synth.device_interactions(rows_u, I, n_shard, dev, seed=synth.SEED + s)
                 P, Q, scratch = views[j]
                 shards.append(kn.ShardState(rec, P, Q, 1, shard_id=s + 1, perm_seed=42, scratch=scratch))
-            lazy = (rows_u + I) > 8 * B
-            sb = kn.ShardBatch(shards, d, B, mode=("lazy" if lazy else "auto") if mode == "auto" else mode)
+            big = (rows_u + I) > 8 * B                  # tables far larger than a batch: owner-computes in HBM
+            sb = kn.ShardBatch(shards, d, B, mode=("runs" if big else "auto") if mode == "auto" else mode)
             mode_used = sb.mode
             n_steps = min(sb.total_steps, steps)
             torch.cuda.synchronize()

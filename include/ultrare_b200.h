@@ -100,7 +100,25 @@ typedef struct {
                             * owner_cap_slots); a longer list is read from the schedule table directly  */
   int32_t owner_max_n;     /* OWNER: largest shard size n (sizes the round tables of the short-epoch schedule
                             * pre-pass); 0 = always use the general pre-pass                                */
+  const struct ure_mf_runs_s* runs; /* RUNS: DEVICE table [n_shards] of the row slots / step lists (below)  */
+  int32_t runs_rows;       /* RUNS: epochs per shard the step lists hold                                    */
+  int32_t runs_spe_cap;    /* RUNS: max steps per epoch of a shard (< 1024)                                 */
+  int64_t runs_step0;      /* RUNS: global step the list window starts at                                   */
 } ure_mf_hparams_t;
+
+/* RUNS schedule: per-shard state next to ure_mf_shard_t (which still carries inter_u / inter_i of
+ * ure_mf_owner_prepare and the public tables P / Q / bufP / bufQ that ure_mf_runs_init reads and
+ * ure_mf_runs_flush writes). */
+typedef struct ure_mf_runs_s {
+  float* slotP;            /* [2][n_user][2 d]: two versions of every user row, each [w | momentum]        */
+  float* slotQ;            /* [2][n_item][2 d]                                                             */
+  unsigned long long* metaP; /* [n_user] version tag: steps applied to the previous version << 32 |         */
+  unsigned long long* metaQ; /* [n_item]   steps applied to the current version << 1 | current slot         */
+  uint32_t* list_u;        /* [runs_rows][n] slots of inter_u grouped by step, row order inside a step      */
+  uint32_t* list_i;        /* [runs_rows][n] the same for inter_i                                           */
+  int32_t* loff_u;         /* [runs_rows][runs_spe_cap + 1] first entry of every step's group               */
+  int32_t* loff_i;
+} ure_mf_runs_t;
 
 /* ure_mf_hparams_t::mode -- three schedules of the SAME arithmetic (baseTrain + dense optim.SGD):
  *   DENSE  gradients scattered with L2 vector atomics (into the momentum arrays, pre-scaled), then a dense
@@ -115,6 +133,10 @@ typedef struct {
 #define URE_MF_DENSE 0
 #define URE_MF_LAZY 1
 #define URE_MF_OWNER 2
+#define URE_MF_RUNS 3     /* owner-computes for tables in HBM: sorted step lists, whole runs of a row per warp,
+                           * two row versions + a tag instead of a second barrier (csrc/mf_train_runs.cu);
+                           * needs ure_mf_owner_prepare (sorted copies), ure_mf_runs_init, ure_mf_runs_schedule
+                           * and, before the public tables are read, ure_mf_runs_flush */
 
 const char* ure_last_error(void);
 int ure_abi_version(void);
@@ -212,6 +234,20 @@ int ure_mf_batch_plan(const int32_t* h_plan, int n_shards, ure_mf_hparams_t* hp,
                       const ure_mf_batch_layout_t* lay, int allow_cache, int force_flags, int force_list,
                       int32_t* h_info);
 
+/* ---- RUNS schedule (mode URE_MF_RUNS) ---------------------------------------------------------------------------
+ * ure_mf_runs_init: slot 0 of every row <- [P | bufP] / [Q | bufQ], tags cleared (once, before the first step).
+ * ure_mf_runs_schedule: the step lists for the window of runs_rows epochs per shard that starts at global step
+ *   `step0` -- a stable counting sort of the user-sorted / item-sorted slots by the step whose batch holds them (the
+ *   inverse of the epoch's visiting order).  d_scratch: ure_mf_runs_scratch_bytes(n_shards, max_n, rows, spe_cap).
+ * ure_mf_train with mode RUNS then runs any steps of that window (hparams.runs_step0 = step0).
+ * ure_mf_runs_flush: every row advanced to the current step and written to the public tables. */
+int64_t ure_mf_runs_scratch_bytes(int n_shards, int64_t max_n, int rows, int spe_cap);
+int ure_mf_runs_init(const ure_mf_shard_t* d_shards, int n_shards, const ure_mf_hparams_t* h_hp, void* stream);
+int ure_mf_runs_schedule(const ure_mf_shard_t* d_shards, int n_shards, const ure_mf_hparams_t* h_hp, int epochs,
+                         int64_t step0, int64_t max_n, void* d_scratch, void* stream);
+int ure_mf_runs_flush(const ure_mf_shard_t* d_shards, int n_shards, const ure_mf_hparams_t* h_hp, int epochs,
+                      int64_t step_now, void* stream);
+
 /* Diagnostics (tracing): record six SM-clock stamps per CTA and step -- step start, tables ready,
  * gradients issued, barrier 1 passed, sweep issued, barrier 2 passed -- for the first `steps` steps of
  * the following ure_mf_train calls into d_trace [steps][ure_mf_grid_size()][6] int64; NULL = off. */
@@ -274,6 +310,14 @@ int ure_remap_users(const ure_inter_t* d_in, int64_t n, const int32_t* d_row_of,
  * ranges (the caller's thread pool splits the arrays); dst 16-byte aligned. */
 int ure_host_stage_copy(void* h_dst, const void* h_src, int64_t bytes);
 
+/* Per-user segments of a test set (the host dict of method/utils.py:151-161): a STABLE sort of the records by user
+ * id (a user's rows stay in file order, which the ranking's tie rule depends on), d_order[x] = index of the x-th row
+ * in that order, d_seg[u] .. d_seg[u+1] = the rows of user u (int64 [n_user + 1]; users without rows give empty
+ * segments, which ure_rank_metrics skips).  d_scratch: ure_user_segments_scratch_bytes(n, n_user) bytes. */
+int64_t ure_user_segments_scratch_bytes(int64_t n, int n_user);
+int ure_user_segments(const ure_inter_t* d_inter, int64_t n, int n_user, int32_t* d_order, int64_t* d_seg,
+                      void* d_scratch, void* stream);
+
 /* Affected-shard routing (method/sisa.py:76-81): flags[owner[u]] = 1 for u in del. */
 int ure_route_deletions(const int32_t* d_owner, int32_t n_user, const int32_t* d_del, int32_t n_del,
                         int32_t* d_flags, int32_t n_shards, void* stream);
@@ -318,6 +362,22 @@ int ure_sinkhorn_update_g(float* d_g, double* d_colsum, int k, float eps, void* 
 int64_t ure_sinkhorn_workspace_bytes(void);
 int ure_sinkhorn(const float* d_M, int64_t n, int k, int kpad, float* d_g, const float* h_eps,
                  const int32_t* h_iters, int n_stages, float tol, void* d_workspace, void* stream);
+
+/* Multi-GPU Sinkhorn in ONE persistent launch per GPU: the users (rows of d_M) are sharded
+ * over `world` GPUs of one NVLink / NVSwitch domain; per iteration every GPU makes its column pass, stores its k
+ * column sums into every peer's exchange buffer (peer-mapped symmetric memory) and raises a flag there; every GPU adds
+ * the per-GPU sums in rank order (bit-identical potentials everywhere) -- no NCCL call, no launch between iterations.
+ * h_xchg_ptrs: HOST array [world] of the device addresses of every rank's exchange buffer as mapped in THIS process
+ * (own buffer included), each ure_sinkhorn_peer_xchg_bytes() bytes, zero-filled once when allocated and never reset.
+ * call_base: a counter that is equal on all ranks and grows by more than the call's total iteration count from call
+ * to call (flags carry call_base + iteration).  All ranks must make the same calls in the same order.  After the
+ * call the int64 iters_done of the workspace is -1 if a peer did not arrive within a few seconds.
+ * d_workspace: ure_sinkhorn_workspace_bytes() bytes. */
+int64_t ure_sinkhorn_peer_xchg_bytes(void);
+int ure_sinkhorn_peer(const float* d_M, int64_t n_local, double n_total, int k, int kpad, float* d_g,
+                      const float* h_eps, const int32_t* h_iters, int n_stages, float tol,
+                      const uint64_t* h_xchg_ptrs, int rank, int world, uint64_t call_base,
+                      void* d_workspace, void* stream);
 
 /* Row-normalised plan for given g: P[i,j] = (1/n_total) softmax_j((g_j - M_ij)/eps), [n,k] fp32. */
 int ure_sinkhorn_plan(const float* d_M, int64_t n, int k, int kpad, const float* d_g, float eps,

@@ -77,7 +77,9 @@ def sinkhorn_log(M, eps_schedule, a=None, b=None, g0=None):
     potentials g:
         f_i   = eps*(log a_i - LSE_j((g_j - M_ij)/eps))          (row scaling)
         P_ij  = exp((f_i + g_j - M_ij)/eps)     (rows sum to a_i exactly)
-        g_j  += eps*(log b_j - log sum_i P_ij)                   (column scaling)
+        g_j  += eps*(log b_j - LSE_i((f_i + g_j - M_ij)/eps))    (column scaling)
+    Both scalings are log-sum-exps (the structure of POT's sinkhorn_log): a column whose every entry is hundreds of
+    eps below its row's maximum -- stale potentials after the centroids moved -- still has a finite log-sum.
     The returned plan is the row-normalised plan for the final g.
     """
     M = np.asarray(M, dtype=np.float64)
@@ -96,8 +98,9 @@ def sinkhorn_log(M, eps_schedule, a=None, b=None, g0=None):
     for eps, iters in eps_schedule:
         for _ in range(int(iters)):
             T, lse = rows(g, eps)
-            col = np.exp(T + (loga - lse)[:, None]).sum(axis=0)
-            g = g + eps * (logb - np.log(col))
+            L = T + (loga - lse)[:, None]                    # log P_ij
+            cmx = L.max(axis=0)
+            g = g + eps * (logb - (cmx + np.log(np.exp(L - cmx[None, :]).sum(axis=0))))
     T, lse = rows(g, eps)
     f = eps * (loga - lse)
     P = np.exp(T + (loga - lse)[:, None])

@@ -27,7 +27,7 @@ def test_header_symbols_are_exported_and_bound():
 
 def test_struct_layouts_match_the_header():
     from ultrare_b200 import _lib
-    assert ctypes.sizeof(_lib.MFShard) == 176 and ctypes.sizeof(_lib.MFHParams) == 104
+    assert ctypes.sizeof(_lib.MFShard) == 176 and ctypes.sizeof(_lib.MFHParams) == 128
     assert _lib.MFShard.inter_u.offset == 96 and _lib.MFShard.n.offset == 152 and _lib.MFShard.perm_seed.offset == 168
     assert _lib.MFHParams.mode.offset == 28 and _lib.MFHParams.decay.offset == 32 and _lib.MFHParams.owner_cap_rows.offset == 44
 

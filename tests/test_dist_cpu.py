@@ -94,7 +94,8 @@ def test_row_sharded_sinkhorn_equals_single_process():
 
 def _ensemble_sharded(d):
     """Shard s on rank s mod world: partial ensemble sums all-reduced == single-process ensemble; the merge of
-    owner rows as a sum of zero-filled contributions is bit-exact (rows are disjoint)."""
+    owner rows as an ALL-GATHER of the ranks' compact tables (padded to the longest rank, Sisa._merged_from) gathered
+    back through owner / row maps is bit-exact."""
     from oracle import evalm, sisa as osisa
     rng = np.random.default_rng(1)
     K, U, I, dd, n = 5, 60, 40, 16, 500
@@ -103,13 +104,22 @@ def _ensemble_sharded(d):
     Qs = [rng.standard_normal((I, dd), dtype=np.float32) for _ in range(K)]
     u, i = rng.integers(0, U, n), rng.integers(0, I, n)
     merged_ref = osisa.merge_learn(Ps, groups)
-    contrib = np.zeros_like(merged_ref)
-    for s in d.my_shards(range(K)):
-        g = np.asarray(groups[s])
-        contrib[g] = Ps[s][g]
-    t = torch.from_numpy(contrib)
-    d.all_reduce(t)
-    merged = t.numpy()
+    sizes = [len(g) for g in groups]
+    by_rank = {r: [s for s in range(K) if d.owner_of_shard(s) == r] for r in range(d.world)}
+    maxlen = max(sum(sizes[s] for s in v) for v in by_rank.values())
+    send = torch.zeros((maxlen, dd), dtype=torch.float32)
+    o = 0
+    for s in by_rank[d.rank]:                      # this rank's compact tables (owner rows in group order), back to back
+        send[o:o + sizes[s]] = torch.from_numpy(Ps[s][np.asarray(groups[s])])
+        o += sizes[s]
+    gathered = torch.empty((d.world * maxlen, dd), dtype=torch.float32)
+    d.all_gather_into(gathered, send)
+    merged = np.zeros_like(merged_ref)
+    for r, v in by_rank.items():
+        o = r * maxlen
+        for s in v:
+            merged[np.asarray(groups[s])] = gathered[o:o + sizes[s]].numpy()
+            o += sizes[s]
     part = np.zeros(n, dtype=np.float32)
     for s in d.my_shards(range(K)):
         part += evalm.mf_score(merged, Qs[s], u, i)

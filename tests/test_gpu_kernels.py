@@ -333,11 +333,11 @@ def test_sinkhorn_dead_column_recovers_exactly_like_the_log_domain_oracle(cuda_d
     mean = float(Mh.min(1).mean())
     eps = 0.02 * mean
     g0 = np.zeros(k, dtype=np.float32)
-    g0[1] = -25.0 * mean                                   # (g_1 - M_i1)/eps is ~1250 nats below every row's maximum
-    g0[k - 1] = -8.0 * mean
+    g0[1] = -12.0 * mean                                   # (g_1 - M_i1)/eps is ~600 nats (870 binades) below every
+    g0[k - 1] = -3.0 * mean                                # row's maximum: far beyond an fp32 linear-domain sum
     sched = [(eps, 1)]
     _, _, g_o1, _ = oot.sinkhorn_log(Mh, sched, g0=g0.astype(np.float64))
-    assert np.isfinite(g_o1).all() and g_o1[1] - g0[1] > 20.0 * mean
+    assert np.isfinite(g_o1).all() and g_o1[1] - g0[1] > 10.0 * mean
     sched = [(eps, 40)]
     P_o, _, g_o, _ = oot.sinkhorn_log(Mh, sched, g0=g0.astype(np.float64))
 
@@ -473,6 +473,79 @@ def test_mf_train_lazy_equals_dense_reference_arithmetic(cuda_dev, d, K):
         untouched = np.setdiff1d(np.arange(U), u)
         assert len(untouched) > 0                      # rows that only ever decayed are exact too
         assert np.abs(shards[s].P.cpu().numpy()[untouched] - P[untouched]).max() < 1e-5
+
+
+@pytest.mark.parametrize("d,K,explicit,list_bytes", [(128, 8, False, None), (64, 3, False, 1), (16, 2, True, None),
+                                                       (128, 1, True, 1), (8, 2, False, None)])
+def test_mf_train_runs_equals_dense_reference_arithmetic(cuda_dev, monkeypatch, d, K, explicit, list_bytes):
+    """RUNS schedule (csrc/mf_train_runs.cu: owner-computes for tables in HBM -- sorted step lists, whole runs of a
+    row per warp, two row versions + a tag, closed-form catch-up of untouched rows) == the reference's dense
+    optimiser.  c4small-like proportions (tables far larger than a batch, d = 128, K = 8 shards, 2 epochs; SURVEY
+    config C4 scaled down so that the dense NumPy oracle finishes), ragged shards, skewed rows (long runs),
+    explicit visiting orders, one-epoch list windows; after ure_mf_runs_flush weights 1e-4 abs, losses 1e-5 rel."""
+    torch = _torch()
+    from ultrare_b200 import kernels as kn
+    if list_bytes is not None:
+        monkeypatch.setattr(kn, "RUNS_LIST_BYTES", list_bytes)
+    rng = np.random.default_rng(300 + d + K)
+    U, I, batch, epochs = 2500, 5000, 700, 2
+    shards, host = [], []
+    for s in range(K):
+        n = 9000 + 2300 * s
+        u = (rng.random(n) ** 1.5 * U).astype(np.int64)                # heavy-tailed rows, as synth.device_interactions
+        i = (rng.random(n) ** 2.0 * I).astype(np.int64)
+        r = rng.integers(1, 6, n).astype(np.float32) / 5
+        P0 = rng.standard_normal((U, d), dtype=np.float32) * 0.3
+        Q0 = rng.standard_normal((I, d), dtype=np.float32) * 0.3
+        if explicit:
+            perms = [rng.permutation(n) for _ in range(epochs)]
+            perm_t = torch.tensor(np.stack(perms).astype(np.int32), device=cuda_dev)
+        else:
+            perms = [omf.feistel_perm(n, omf.perm_key(9, s, ep)) for ep in range(epochs)]
+            perm_t = None
+        shards.append(kn.ShardState(kn.pack_interactions(u, i, r, cuda_dev), torch.tensor(P0, device=cuda_dev),
+                                    torch.tensor(Q0, device=cuda_dev), epochs, s, 9, perm=perm_t))
+        host.append((u, i, r, P0, Q0, perms))
+    sb = kn.ShardBatch(shards, d, batch, mode="runs")
+    assert sb.mode == "runs" and sb.hp.runs_rows == (1 if list_bytes else epochs)
+    sb.train()
+    sb.flush()
+    torch.cuda.synchronize()
+    losses = sb.train_losses()
+    for s in range(K):
+        u, i, r, P0, Q0, perms = host[s]
+        P, Q, bP, bQ, ls = omf.mf_train(P0, Q0, u, i, r, perms, batch, epochs)
+        np.testing.assert_allclose(losses[s], ls, rtol=1e-5)
+        assert np.abs(shards[s].P.cpu().numpy() - P).max() < 1e-4
+        assert np.abs(shards[s].Q.cpu().numpy() - Q).max() < 1e-4
+        assert np.abs(shards[s].bufP.cpu().numpy() - bP).max() < 1e-3
+        assert np.abs(shards[s].bufQ.cpu().numpy() - bQ).max() < 1e-3
+        untouched = np.setdiff1d(np.arange(I), i)
+        assert len(untouched) > 0                      # rows that only ever decayed are exact too
+        assert np.abs(shards[s].Q.cpu().numpy()[untouched] - Q[untouched]).max() < 1e-5
+
+
+def test_mf_train_runs_epoch_by_epoch_equals_single_launch(cuda_dev):
+    """RUNS: training in two launches (the row slots and version tags persist between them) == one launch."""
+    torch = _torch()
+    from ultrare_b200 import kernels as kn
+    rng = np.random.default_rng(17)
+    U, I, n, d, batch, epochs = 900, 1500, 7000, 32, 400, 3
+    u, i = (rng.random(n) ** 1.5 * U).astype(np.int64), (rng.random(n) ** 2.0 * I).astype(np.int64)
+    r = rng.integers(1, 6, n).astype(np.float32) / 5
+    P0 = rng.standard_normal((U, d), dtype=np.float32) * 0.3
+    Q0 = rng.standard_normal((I, d), dtype=np.float32) * 0.3
+    outs = []
+    for cuts in ([None], [5, 18, 19, None]):
+        st = kn.ShardState(kn.pack_interactions(u, i, r, cuda_dev), torch.tensor(P0, device=cuda_dev),
+                           torch.tensor(Q0, device=cuda_dev), epochs, 1, 9)
+        sb = kn.ShardBatch([st], d, batch, mode="runs")
+        for c in cuts:
+            sb.train(c)
+            sb.flush()                                 # exporting the tables in between must not disturb the slots
+        outs.append((st.P.cpu().numpy(), st.Q.cpu().numpy(), sb.train_losses()[0]))
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    np.testing.assert_allclose(outs[0][2], outs[1][2], rtol=1e-6)
 
 
 def test_mf_owner_prepare_sorts_and_inverts(cuda_dev):
@@ -730,7 +803,7 @@ def test_mf_full_size_ml1m_k5_vs_oracle(cuda_dev, mode):
         np.testing.assert_allclose(losses[g], ls, rtol=1e-5)
         assert np.abs(shards[g].P.cpu().numpy() - P).max() < 2e-4
         assert np.abs(shards[g].Q.cpu().numpy() - Q).max() < 2e-4
-        assert np.abs(shards[g].bufP.cpu().numpy() - bP).max() < 2e-3
+        assert np.abs(shards[g].bufP.cpu().numpy() - bP).max() < 4e-3      # momenta reach ~60: 6e-5 relative
 
 
 @pytest.mark.parametrize("contiguous", [True, False])
@@ -755,6 +828,9 @@ def test_user_segments_on_device_equal_host_segments(cuda_dev, contiguous):
                            None if order_h is None else kn.upload_array(order_h, cuda_dev)).cpu().numpy()
     order_d, seg_d = kn.user_segments_device(inter, n_user)
     assert seg_d.shape[0] == n_user + 1 and int(seg_d[0]) == 0 and int(seg_d[-1]) == n
+    # bit-exact: the stable argsort by user id and its CSR offsets (hand-written radix sort, no library kernel)
+    assert np.array_equal(order_d.cpu().numpy(), np.argsort(u, kind="stable"))
+    assert np.array_equal(seg_d.cpu().numpy(), np.concatenate([[0], np.cumsum(np.bincount(u, minlength=n_user))]))
     got = kn.rank_metrics(inter, score, seg_d, order_d).cpu().numpy()
     assert got[2] == want[2] == len(np.unique(u))
     np.testing.assert_allclose(got[:2], want[:2], rtol=1e-12)

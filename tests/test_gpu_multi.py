@@ -79,11 +79,24 @@ def _ot_pass(dist_obj):
     X = rng.standard_normal((n, d), dtype=np.float32)
     c0 = X[:k].copy()
     if dist_obj is None or dist_obj.world == 1:
-        inertia, label, cen, it = ot_cluster_device(X, k, centroid0=c0)
+        # the row-sharded path skips the balanced rounding (the cost rows live on different GPUs): same here
+        inertia, label, cen, it = ot_cluster_device(X, k, centroid0=c0, balance=False)
         return dict(inertia=float(inertia), label=label, it=it)
+    import torch
+    from ultrare_b200 import kernels as kn
     lo, hi = dist_obj.row_block(n)
     inertia, label, cen, it = ot_cluster_device(X[lo:hi], k, centroid0=c0, dist=dist_obj)
-    return dict(inertia=float(inertia), label=label, it=it, lo=lo, hi=hi)
+    out = dict(inertia=float(inertia), label=label, it=it, lo=lo, hi=hi, peer=kn._peer_exchange(dist_obj, torch.device("cuda", dist_obj.rank)) is not None)
+    # the fused peer-memory Sinkhorn against the NCCL all-reduce loop on the same cost rows: same potentials
+    dev = torch.device("cuda", dist_obj.rank)
+    M = kn.cost_matrix(torch.tensor(X[lo:hi], device=dev), torch.tensor(c0, device=dev))
+    sched = [(8.0, 15), (2.0, 25)]
+    g_peer = kn.sinkhorn_sharded(M, k, sched, dist_obj, n)
+    kn.PEER_SINKHORN = False
+    g_nccl = kn.sinkhorn_sharded(M, k, sched, dist_obj, n)
+    kn.PEER_SINKHORN = True
+    out["g_peer"], out["g_nccl"] = g_peer.cpu().numpy(), g_nccl.cpu().numpy()
+    return out
 
 
 def _worker(rank, world, port, q):
@@ -123,6 +136,10 @@ def test_two_rank_sisa_and_sinkhorn_equal_single_gpu(cuda_dev):
                 assert np.abs(s[phase + "_merged"] - ref[phase + "_merged"]).max() < 1e-4
                 np.testing.assert_allclose(s[phase + "_log0"], ref[phase + "_log0"], rtol=1e-3)
         np.testing.assert_allclose(results[r]["sisa"]["unlearn_log0"], results[r]["sisa_whole"]["unlearn_log0"], rtol=1e-5)
+    for r in range(2):
+        assert results[r]["ot"]["peer"], "no peer-mapped symmetric memory between the two GPUs"
+        assert np.abs(results[r]["ot"]["g_peer"] - results[r]["ot"]["g_nccl"]).max() < 1e-5
+    assert np.array_equal(results[0]["ot"]["g_peer"], results[1]["ot"]["g_peer"])      # bit-identical on every rank
     lab = np.concatenate([results[0]["ot"]["label"], results[1]["ot"]["label"]])
     assert (lab == single["ot"]["label"]).mean() > 0.999
     assert abs(results[0]["ot"]["inertia"] - single["ot"]["inertia"]) / single["ot"]["inertia"] < 1e-5

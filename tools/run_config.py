@@ -28,7 +28,7 @@ CONFIGS = {
 ap = argparse.ArgumentParser()
 ap.add_argument("--config", default="c3", choices=list(CONFIGS))
 ap.add_argument("--epochs", type=int, default=1)
-ap.add_argument("--mode", default="auto", choices=["dense", "lazy", "owner", "auto"])
+ap.add_argument("--mode", default="auto", choices=["dense", "lazy", "owner", "auto", "runs"])
 ap.add_argument("--max-steps", type=int, default=0, help="train only this many global steps (0 = all)")
 a = ap.parse_args()
 
@@ -49,14 +49,14 @@ for j, s in enumerate(mine):
     rec = synth.device_interactions(rows_u, I, n_shard, dev, seed=synth.SEED + s)
     P, Q, scratch = views[j]
     shards.append(kn.ShardState(rec, P, Q, a.epochs, shard_id=s + 1, perm_seed=42, scratch=scratch))
-sb = kn.ShardBatch(shards, d, B, mode="owner" if a.mode == "owner" else ("lazy" if lazy else "dense"))
+sb = kn.ShardBatch(shards, d, B, mode=a.mode if a.mode in ("owner", "runs") else ("lazy" if lazy else "dense"))
 torch.cuda.synchronize()
 if rank == 0 and sb.owner_plan:
     print("owner plan", sb.owner_plan, file=sys.stderr)
 setup_s = time.time() - t0
 steps = sb.total_steps if a.max_steps <= 0 else min(sb.total_steps, a.max_steps)
 ms_runs, sse_first = [], None
-for rep in range(1 if sb.lazy else 2):   # rep 0 pays the first-launch costs (module load, attribute calls)
+for rep in range(1 if sb.lazy else 2):   # lazy / runs: one launch (their row state is not reset by zeroing buf)   # rep 0 pays the first-launch costs (module load, attribute calls)
     for s_ in shards:
         s_.bufP.zero_(); s_.bufQ.zero_()
         if rep:

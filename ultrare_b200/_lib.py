@@ -35,7 +35,13 @@ class MFHParams(C.Structure):
                 ("owner_cap_rows", _i32), ("owner_cap_slots", _i32), ("owner_flags", _i32),
                 ("owner_spe_cap", _i32), ("owner_sched_rows", _i32), ("owner_sched", _p), ("owner_sched_off", _p),
                 ("owner_sched_step0", _i64), ("owner_sched_stride", _i64),
-                ("owner_cap_list", _i32), ("owner_max_n", _i32)]
+                ("owner_cap_list", _i32), ("owner_max_n", _i32),
+                ("runs", _p), ("runs_rows", _i32), ("runs_spe_cap", _i32), ("runs_step0", _i64)]
+
+
+class MFRuns(C.Structure):
+    """ure_mf_runs_t"""
+    _fields_ = [(nm, _p) for nm in ("slotP", "slotQ", "metaP", "metaQ", "list_u", "list_i", "loff_u", "loff_i")]
 
 
 class MFBatchShard(C.Structure):
@@ -50,9 +56,9 @@ class MFBatchLayout(C.Structure):
                [(nm, _i32) for nm in ("spe_cap", "max_rows", "max_n", "grid", "owner", "sched_rows")]
 
 
-MF_DENSE, MF_LAZY, MF_OWNER = 0, 1, 2
+MF_DENSE, MF_LAZY, MF_OWNER, MF_RUNS = 0, 1, 2, 3
 
-assert C.sizeof(MFShard) == 176 and C.sizeof(MFHParams) == 104
+assert C.sizeof(MFShard) == 176 and C.sizeof(MFHParams) == 128 and C.sizeof(MFRuns) == 64
 assert C.sizeof(MFBatchShard) == 32 and C.sizeof(MFBatchLayout) == 152
 
 # name -> (restype, argtypes); every symbol include/ultrare_b200.h declares
@@ -71,6 +77,10 @@ SIGNATURES = {
                                       _p, C.POINTER(MFBatchLayout), _p, _p]),
     "ure_mf_batch_plan": (C.c_int, [_p, C.c_int, C.POINTER(MFHParams), _p, C.POINTER(MFBatchLayout), C.c_int, C.c_int,
                                      C.c_int, _p]),
+    "ure_mf_runs_scratch_bytes": (_i64, [C.c_int, _i64, C.c_int, C.c_int]),
+    "ure_mf_runs_init": (C.c_int, [_p, C.c_int, C.POINTER(MFHParams), _p]),
+    "ure_mf_runs_schedule": (C.c_int, [_p, C.c_int, C.POINTER(MFHParams), C.c_int, _i64, _i64, _p, _p]),
+    "ure_mf_runs_flush": (C.c_int, [_p, C.c_int, C.POINTER(MFHParams), C.c_int, _i64, _p]),
     "ure_mf_train_trace": (C.c_int, [_p, _p, C.c_int, _p]),
     "ure_mf_grid_size": (C.c_int, []),
     "ure_mf_debug_flags": (C.c_int, [_p, C.c_uint32, _p]),
@@ -83,6 +93,8 @@ SIGNATURES = {
     "ure_partition_interactions": (C.c_int, [_p, _i64, _i64, _i64, _f64, _p, _p, _i32, C.c_int, _p, _p, _p, _p]),
     "ure_remap_users": (C.c_int, [_p, _i64, _p, _i32, _p, _p]),
     "ure_host_stage_copy": (C.c_int, [_p, _p, _i64]),
+    "ure_user_segments_scratch_bytes": (_i64, [_i64, C.c_int]),
+    "ure_user_segments": (C.c_int, [_p, _i64, C.c_int, _p, _p, _p, _p]),
     "ure_route_deletions": (C.c_int, [_p, _i32, _p, _i32, _p, _i32, _p]),
     "ure_merge_user_rows": (C.c_int, [_p, _p, _p, _p, _p, _i32, C.c_int, C.c_int, _p]),
     "ure_cost_matrix": (C.c_int, [_p, _i64, C.c_int, _p, C.c_int, C.c_int, _p, _p, _p]),
@@ -91,6 +103,9 @@ SIGNATURES = {
     "ure_sinkhorn_update_g": (C.c_int, [_p, _p, C.c_int, _f32, _p]),
     "ure_sinkhorn_workspace_bytes": (_i64, []),
     "ure_sinkhorn": (C.c_int, [_p, _i64, C.c_int, C.c_int, _p, C.POINTER(_f32), C.POINTER(_i32), C.c_int, _f32, _p, _p]),
+    "ure_sinkhorn_peer_xchg_bytes": (_i64, []),
+    "ure_sinkhorn_peer": (C.c_int, [_p, _i64, _f64, C.c_int, C.c_int, _p, C.POINTER(_f32), C.POINTER(_i32), C.c_int, _f32,
+                                     C.POINTER(C.c_uint64), C.c_int, C.c_int, C.c_uint64, _p, _p]),
     "ure_sinkhorn_plan": (C.c_int, [_p, _i64, C.c_int, C.c_int, _p, _f32, _f64, _p, _p]),
     "ure_assign_plan_f64": (C.c_int, [_p, _i64, C.c_int, _i64, _p, _p]),
     "ure_assign_plan_f32": (C.c_int, [_p, _i64, C.c_int, _i64, _p, _p]),

@@ -20,6 +20,10 @@ int mf_train_lazy(const ure_mf_shard_t* d_shards, int n_shards, const ure_mf_hpa
 int mf_flush_lazy(const ure_mf_shard_t* h_shards, int n_shards, const ure_mf_hparams_t* hp, int epochs,
                   long long step_now, cudaStream_t st);
 
+// owner-computes for tables in HBM (mf_train_runs.cu)
+int mf_train_runs(const ure_mf_shard_t* d_shards, int n_shards, const ure_mf_hparams_t* hp, int epochs,
+                  long long step_begin, long long step_end, void* d_workspace, cudaStream_t st);
+
 // owner-computes variant (mf_train_owner.cu)
 int mf_train_owner(const ure_mf_shard_t* d_shards, int n_shards, const ure_mf_hparams_t* hp, int epochs,
                    long long step_begin, long long step_end, void* d_workspace, cudaStream_t st);

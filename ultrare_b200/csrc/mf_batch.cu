@@ -6,6 +6,7 @@
 // the descriptor table, the training workspace), writes the descriptor table, clears what must be zero and queues
 // the owner set-up kernels; a second call turns the plan those kernels leave into the launch parameters.  The host
 // does no per-shard tensor bookkeeping before the training kernel is queued (round 1: ~0.5 ms of Python per step).
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -184,7 +185,10 @@ extern "C" int ure_mf_batch_plan(const int32_t* h_plan, int n_shards, ure_mf_hpa
   hp->owner_sched = reinterpret_cast<uint16_t*>(base + lay->sched);
   hp->owner_sched_off = reinterpret_cast<int32_t*>(base + lay->sched_off);
   hp->owner_sched_rows = lay->sched_rows; hp->owner_sched_stride = lay->sched_stride; hp->owner_sched_step0 = 0;
-  hp->owner_max_n = lay->max_n;
+  {
+    static const int fast = getenv("URE_SCHED_FAST") ? atoi(getenv("URE_SCHED_FAST")) : 1;      // 0: general pre-pass (A/B)
+    hp->owner_max_n = fast ? lay->max_n : 0;
+  }
   // the offsets table was laid out for the host-side steps-per-epoch bound; the plan's is the same number
   URE_REQUIRE(spe_cap <= lay->spe_cap, URE_EINVAL, "ure_mf_batch_plan: plan steps per epoch %d above the layout's %d",
               spe_cap, lay->spe_cap);

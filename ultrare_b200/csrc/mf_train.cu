@@ -448,8 +448,11 @@ extern "C" int ure_mf_train(const ure_mf_shard_t* d_shards, int n_shards, const 
               "ure_mf_train: n_shards=%d outside [1,%d]", n_shards, URE_MAX_SHARDS);
   URE_REQUIRE(h_hp->batch > 0 && h_hp->lr_step > 0 && epochs > 0, URE_EINVAL,
               "ure_mf_train: batch/lr_step/epochs must be positive");
-  URE_REQUIRE(h_hp->mode >= URE_MF_DENSE && h_hp->mode <= URE_MF_OWNER, URE_EINVAL, "ure_mf_train: mode=%d unknown",
+  URE_REQUIRE(h_hp->mode >= URE_MF_DENSE && h_hp->mode <= URE_MF_RUNS, URE_EINVAL, "ure_mf_train: mode=%d unknown",
               h_hp->mode);
+  if (h_hp->mode == URE_MF_RUNS)
+    return mf_train_runs(d_shards, n_shards, h_hp, epochs, step_begin, step_end, d_workspace,
+                         static_cast<cudaStream_t>(stream));
   if (h_hp->mode == URE_MF_OWNER)
     return mf_train_owner(d_shards, n_shards, h_hp, epochs, step_begin, step_end, d_workspace,
                           static_cast<cudaStream_t>(stream));

@@ -25,6 +25,7 @@
 //     semantics of the reference) with ONE barrier per step -- and only among the CTAs of the shard.
 #include "common.cuh"
 #include "feistel.cuh"
+#include <string.h>
 #include <type_traits>
 
 namespace ure {
@@ -1350,6 +1351,70 @@ extern "C" int ure_mf_owner_schedule(const ure_mf_shard_t* d_shards, int n_shard
   URE_CUDA(cudaFuncSetAttribute(owner_schedule_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
   owner_schedule_kernel<<<dim3(num_sms(), ny), kSchedThreads, (size_t)need, static_cast<cudaStream_t>(stream)>>>(
       d_shards, n_shards, hp, epochs, step0);
+  URE_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------- per-user segments of a test set (baseTest)
+// The host dict of method/utils.py:151-161 groups the test rows by user, a user's rows in file order.  Here: the
+// same stable radix sort the owner set-up uses (user side only) on the test records, CSR offsets by user id.
+namespace ure {
+namespace {
+__global__ void seg_count_kernel(const ure_inter_t* __restrict__ inter, long long n, int n_user, int32_t* off_u,
+                                 int* __restrict__ bad) {
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (long long)gridDim.x * blockDim.x) {
+    const int u = inter[j].user;
+    if (u < 0 || u >= n_user) { *bad = 1; continue; }
+    atomicAdd(off_u + u + 1, 1);
+  }
+}
+__global__ void seg_extract_kernel(const ure_inter_t* __restrict__ sorted, long long n, const int32_t* __restrict__ off_u,
+                                   int n_user, int32_t* __restrict__ order, long long* __restrict__ seg) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) order[j] = sorted[j].pad;
+  for (long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x; u <= n_user; u += stride) seg[u] = off_u[u];
+}
+inline int64_t seg_align(int64_t x) { return (x + 255) / 256 * 256; }
+}  // namespace
+}  // namespace ure
+
+extern "C" int64_t ure_user_segments_scratch_bytes(int64_t n, int n_user) {
+  using namespace ure;
+  return 256 + seg_align(((int64_t)n_user + 2) * 4) + 2 * seg_align(n * 16) + seg_align(256ll * kRadixBlocks * 4) + 256;
+}
+
+extern "C" int ure_user_segments(const ure_inter_t* d_inter, int64_t n, int n_user, int32_t* d_order, int64_t* d_seg,
+                                 void* d_scratch, void* stream) {
+  using namespace ure;
+  URE_REQUIRE(d_inter && d_order && d_seg && d_scratch && n > 0 && n_user > 0 && n < (1ll << 31), URE_EINVAL,
+              "ure_user_segments: bad argument (n=%lld, n_user=%d)", (long long)n, n_user);
+  auto st = static_cast<cudaStream_t>(stream);
+  char* base = static_cast<char*>(d_scratch);
+  auto* d_desc = reinterpret_cast<ure_mf_shard_t*>(base);
+  auto* off_u = reinterpret_cast<int32_t*>(base + 256);
+  char* p = base + 256 + seg_align(((int64_t)n_user + 2) * 4);
+  auto* sorted = reinterpret_cast<ure_inter_t*>(p); p += seg_align(n * 16);
+  auto* tmp = reinterpret_cast<ure_inter_t*>(p); p += seg_align(n * 16);
+  auto* hist = reinterpret_cast<int*>(p); p += seg_align(256ll * kRadixBlocks * 4);
+  int* bad = reinterpret_cast<int*>(p);
+  ure_mf_shard_t h;
+  memset(&h, 0, sizeof(h));
+  h.inter = d_inter; h.inter_u = sorted; h.tmp_u = tmp; h.off_u = off_u; h.n = (int32_t)n; h.n_user = n_user;
+  URE_CUDA(cudaMemcpyAsync(d_desc, &h, sizeof(h), cudaMemcpyHostToDevice, st));
+  URE_CUDA(cudaMemsetAsync(off_u, 0, ((size_t)n_user + 2) * 4, st));
+  URE_CUDA(cudaMemsetAsync(bad, 0, 4, st));
+  long long blocks = (n + 1023) / 1024;
+  if (blocks > 2 * num_sms()) blocks = 2 * num_sms();
+  seg_count_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_inter, n, n_user, off_u, bad);
+  csr_scan_kernel<<<1, 1024, 0, st>>>(d_desc);
+  int npass = 1;
+  while (npass < 4 && (n_user - 1) >> (8 * npass)) ++npass;
+  for (int pass = 0; pass < npass; ++pass) {            // grid.y = 1: shard 0, user side only
+    radix_hist_kernel<<<dim3(kRadixBlocks, 1), kRadixThreads, 0, st>>>(d_desc, pass, npass, hist);
+    radix_scan_kernel<<<1, 256, 0, st>>>(hist, kRadixBlocks);
+    radix_scatter_kernel<<<dim3(kRadixBlocks, 1), kRadixThreads, 0, st>>>(d_desc, pass, npass, hist);
+  }
+  seg_extract_kernel<<<(unsigned)blocks, 256, 0, st>>>(sorted, n, off_u, n_user, d_order, reinterpret_cast<long long*>(d_seg));
   URE_CUDA(cudaGetLastError());
   return 0;
 }

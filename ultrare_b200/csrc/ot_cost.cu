@@ -16,6 +16,9 @@
 //   3*d/8 MMAs and commits to an mbarrier; the four warps read their 32 TMEM lanes back
 //   with tcgen05.ld, apply the norm epilogue and store the rows of M.
 // The problem is bound by reading X (4*n*d bytes), not by the tensor pipe (Appendix D).
+#include <cuda.h>
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace ure {
@@ -135,7 +138,7 @@ __host__ __device__ inline CostSmemLayout cost_layout(int D, int NB, int stages)
 template <int D>
 __global__ void __launch_bounds__(kCostThreads)
 cost_tc_kernel(const float* __restrict__ X, long long n, const float* __restrict__ C, int k, int kpad, int NB,
-               int stages, uint32_t tmem_cols, float* __restrict__ M, double* __restrict__ inertia) {
+               int stages, uint32_t tmem_cols, float* __restrict__ M, double* __restrict__ inertia, int raw_hi) {
   constexpr int CH = D / 4;                    // 16-byte K chunks per row
   extern __shared__ __align__(128) unsigned char sm[];
   const CostSmemLayout L = cost_layout(D, NB, stages);
@@ -209,7 +212,9 @@ cost_tc_kernel(const float* __restrict__ X, long long n, const float* __restrict
       const float4 v = *reinterpret_cast<const float4*>(raw + r * D + c * 4);
       const float4 hi = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
       const float4 lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
-      *reinterpret_cast<float4*>(sm + L.a_hi + c * L.lbo_a + r * 16) = hi;
+      // raw_hi (experiment, URE_COST_RAW_HI=1): hand the tensor core the UNTRUNCATED value as the hi operand -- equal
+      // results mean kind::tf32 ignores the low 13 mantissa bits, i.e. the raw tile can serve as the hi tile
+      *reinterpret_cast<float4*>(sm + L.a_hi + c * L.lbo_a + r * 16) = raw_hi ? v : hi;
       *reinterpret_cast<float4*>(sm + L.a_lo + c * L.lbo_a + r * 16) = lo;
       float s = (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
 #pragma unroll
@@ -272,6 +277,256 @@ cost_tc_kernel(const float* __restrict__ X, long long n, const float* __restrict
   if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
 }
 
+// ------------------------------------------------------------------ v2: tensor-map TMA straight into the UMMA layout
+// Measured on the B200 (tests with URE_COST_RAW_HI=1): tcgen05 kind::tf32 ignores the low 13 mantissa bits of its
+// operands, so the RAW fp32 tile is a valid `hi` operand: hi*B is computed on the truncated values either way.  The
+// tile therefore goes from global memory directly into the K-major core-matrix layout the tensor core reads
+// ([d/4 chunks][128 rows][16 B]: one 2-D TMA box {4 floats, 128 rows} per chunk, cp.async.bulk.tensor), and the only
+// generic-proxy pass left is lo = x - trunc(x) plus the row norms: half the shared-memory stores of v1, none of its
+// bank conflicts (threads walk rows, 16 contiguous bytes each), and a footprint that lets two CTAs share an SM at
+// d = 64 so that one CTA's TMA / MMA / epilogue latencies are covered by the other's work.
+__device__ __forceinline__ void tma_load_2d(void* dst_smem, const CUtensorMap* tmap, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+
+struct CostSmemLayout2 {
+  uint32_t hi_off, stage_bytes, stages, lo_off, lbo_a;
+  uint32_t b_hi, b_lo, lbo_b;
+  uint32_t xnorm, rowmin, cnorm, bars, holder, total;
+};
+
+__host__ __device__ inline CostSmemLayout2 cost_layout2(int D, int NB, int stages) {
+  CostSmemLayout2 L;
+  const uint32_t chunks = D / 4;
+  L.lbo_a = kTileRows * 16;                   // a TMA box lands as 128 contiguous 16-byte rows
+  L.lbo_b = NB * 16 + (chunks >= 8 ? 16 : 32);
+  uint32_t o = 0;
+  L.stages = stages;
+  L.stage_bytes = kTileRows * D * 4;
+  L.hi_off = o; o += L.stage_bytes * stages;
+  L.lo_off = o; o += L.stage_bytes;
+  L.b_hi = o; o += L.lbo_b * chunks;
+  L.b_lo = o; o += L.lbo_b * chunks;
+  L.xnorm = o; o += kTileRows * 4;
+  L.rowmin = o; o += kTileRows * 4;
+  L.cnorm = o; o += NB * 4;
+  o = (o + 7) / 8 * 8;
+  L.bars = o; o += 8 * 4;                     // full[2], mma
+  L.holder = o; o += 16;
+  L.total = o;
+  return L;
+}
+
+template <int D>
+__global__ void __launch_bounds__(kCostThreads)
+cost_tma_kernel(const __grid_constant__ CUtensorMap tmap, long long n, const float* __restrict__ C, int k, int kpad, int NB,
+                int stages, uint32_t tmem_cols, float* __restrict__ M, double* __restrict__ inertia) {
+  constexpr int CH = D / 4;                    // 16-byte K chunks per row
+  extern __shared__ __align__(128) unsigned char sm[];
+  const CostSmemLayout2 L = cost_layout2(D, NB, stages);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sm + L.bars);
+  uint64_t* mma_bar = full + 2;
+  uint32_t* holder = reinterpret_cast<uint32_t*>(sm + L.holder);
+  float* xnorm = reinterpret_cast<float*>(sm + L.xnorm);
+  int* rowmin = reinterpret_cast<int*>(sm + L.rowmin);     // float bits (costs are >= 0: int order == float order)
+  float* cnorm = reinterpret_cast<float*>(sm + L.cnorm);
+  const int col0 = blockIdx.y * NB;            // first centroid column of this CTA
+
+  if (tid == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    mbar_init(mma_bar, 1);
+    fence_mbar_init();
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+  }
+  if (warp == 0) tmem_alloc(holder, tmem_cols);
+
+  // ---- centroid block -> B_hi / B_lo (K-major core-matrix layout) + ||c||^2
+  for (int idx = tid; idx < NB * CH; idx += kCostThreads) {
+    const int j = idx / CH, c = idx % CH;
+    const int col = col0 + j;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (col < k) v = __ldg(reinterpret_cast<const float4*>(C + (size_t)col * D) + c);
+    float4 hi = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+    float4 lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
+    *reinterpret_cast<float4*>(sm + L.b_hi + c * L.lbo_b + j * 16) = hi;
+    *reinterpret_cast<float4*>(sm + L.b_lo + c * L.lbo_b + j * 16) = lo;
+    float s = (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+#pragma unroll
+    for (int o = CH / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o, CH);
+    if (c == 0) cnorm[j] = col < k ? s : INFINITY;
+  }
+  if (tid < kTileRows) xnorm[tid] = 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *holder;
+  const uint32_t idesc = make_idesc_tf32(NB);
+  const uint32_t a_lo_addr = smem_u32(sm + L.lo_off);
+  const uint32_t b_hi_addr = smem_u32(sm + L.b_hi), b_lo_addr = smem_u32(sm + L.b_lo);
+
+  const long long n_tiles = (n + kTileRows - 1) / kTileRows;
+  auto issue_load = [&](long long tile, int stage) {          // CH boxes of {4 floats, 128 rows}: rows past n are zeros
+    mbar_expect_tx(&full[stage], L.stage_bytes);
+    unsigned char* dst = sm + L.hi_off + (size_t)stage * L.stage_bytes;
+#pragma unroll 4
+    for (int c = 0; c < CH; ++c) tma_load_2d(dst + c * L.lbo_a, &tmap, 4 * c, (int)(tile * kTileRows), &full[stage]);
+  };
+
+  long long tile = blockIdx.x;
+  if (tid == 0 && tile < n_tiles) issue_load(tile, 0);
+  double inertia_acc = 0.0;
+  for (int it = 0; tile < n_tiles; ++it, tile += gridDim.x) {
+    const int stage = stages == 2 ? (it & 1) : 0;
+    const uint32_t full_parity = stages == 2 ? ((it >> 1) & 1) : (it & 1);
+    const long long next = tile + gridDim.x;
+    if (stages == 2 && tid == 0 && next < n_tiles) issue_load(next, stage ^ 1);
+    mbar_wait(&full[stage], full_parity);
+
+    // ---- lo = x - trunc(x) in the same layout, row norms; threads walk rows (16 contiguous bytes each)
+    const unsigned char* hi = sm + L.hi_off + (size_t)stage * L.stage_bytes;
+    if (tid < kTileRows) rowmin[tid] = 0x7f800000;          // +inf
+    {
+      const int r = tid & (kTileRows - 1), cg = tid / kTileRows;
+      float s = 0.f;
+#pragma unroll 4
+      for (int c = cg; c < CH; c += kCostThreads / kTileRows) {
+        const float4 v = *reinterpret_cast<const float4*>(hi + c * L.lbo_a + r * 16);
+        const float4 lo = make_float4(v.x - tf32_hi(v.x), v.y - tf32_hi(v.y), v.z - tf32_hi(v.z), v.w - tf32_hi(v.w));
+        *reinterpret_cast<float4*>(sm + L.lo_off + c * L.lbo_a + r * 16) = lo;
+        s += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+      }
+      if (cg < CH) atomicAdd(&xnorm[r], s);
+    }
+    fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+    __syncthreads();
+
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t a_hi_addr = smem_u32(hi);
+#pragma unroll
+      for (int kk = 0; kk < D / 8; ++kk) {
+        const uint64_t ah = make_desc(a_hi_addr + kk * 2 * L.lbo_a, L.lbo_a, 128);
+        const uint64_t al = make_desc(a_lo_addr + kk * 2 * L.lbo_a, L.lbo_a, 128);
+        const uint64_t bh = make_desc(b_hi_addr + kk * 2 * L.lbo_b, L.lbo_b, 128);
+        const uint64_t bl = make_desc(b_lo_addr + kk * 2 * L.lbo_b, L.lbo_b, 128);
+        umma_tf32(tmem_base, ah, bh, idesc, kk > 0);       // the tensor core truncates the raw tile to tf32 itself
+        umma_tf32(tmem_base, ah, bl, idesc, 1);
+        umma_tf32(tmem_base, al, bh, idesc, 1);
+      }
+      umma_commit(mma_bar);       // implies tcgen05.fence::before_thread_sync
+    }
+    mbar_wait(mma_bar, it & 1);
+    tc_fence_after();
+    if (stages == 1 && tid == 0 && next < n_tiles) issue_load(next, 0);     // the MMAs have consumed the raw tile
+
+    // ---- epilogue: warp w reads TMEM lanes 32*(w%4).. (its row quarter) and every 4th 16-column chunk
+    const int rq = warp & 3, cg = warp >> 2;
+    const int trow = rq * 32 + lane;
+    const long long row = tile * kTileRows + trow;
+    const float xn = xnorm[trow];
+    float rmin = INFINITY;
+    for (int c0 = cg * 16; c0 < NB; c0 += 16 * (kCostThreads / 128)) {
+      float acc[16];
+      tmem_ld16(tmem_base + ((uint32_t)(rq * 32) << 16) + (uint32_t)c0, acc);
+      if (row < n) {
+        float out[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          out[j] = fmaf(-2.f, acc[j], xn + cnorm[c0 + j]);
+          rmin = fminf(rmin, out[j]);
+        }
+        float4* dst = reinterpret_cast<float4*>(M + row * kpad + col0 + c0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) dst[q] = make_float4(out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]);
+      }
+    }
+    if (inertia && row < n && rmin < INFINITY) atomicMin(&rowmin[trow], __float_as_int(fmaxf(rmin, 0.f)));
+    tc_fence_before();
+    __syncthreads();              // TMEM accumulator, the lo tile and xnorm may be overwritten now
+    if (tid < kTileRows) {
+      if (inertia && tile * kTileRows + tid < n) inertia_acc += (double)__int_as_float(rowmin[tid]);
+      xnorm[tid] = 0.f;
+    }
+    __syncthreads();              // rowmin / xnorm are re-initialised before the next tile's passes
+  }
+  if (inertia) {
+    inertia_acc = warp_sum(inertia_acc);
+    if (lane == 0 && inertia_acc != 0.0) atomicAdd(inertia, inertia_acc);
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+// *used = 1 when the TMA kernel was launched (2: the caller still owes the inertia pass), 0 when the caller should
+// use v1 (no driver entry point / odd shape); the return value is an error code as everywhere
+template <int D>
+int launch_cost_tma(const float* X, long long n, const float* C, int k, int kpad, float* M, double* inertia, cudaStream_t st,
+                    int* used) {
+  *used = 0;
+  static const int force_v1 = getenv("URE_COST_V1") ? atoi(getenv("URE_COST_V1")) : 0;
+  EncodeTiledFn enc = encode_tiled();
+  if (force_v1 || !enc || D < 8 || (reinterpret_cast<uintptr_t>(X) & 15) != 0 || n >= (1ll << 31)) return 0;
+  // column block and stages: prefer a footprint that lets two CTAs share an SM
+  int NB = kpad > 128 ? 128 : kpad, stages = 2;
+  while (kpad % NB) NB -= 16;
+  if (cost_layout2(D, NB, 2).total > 110 * 1024 && cost_layout2(D, NB, 1).total <= 110 * 1024) stages = 1;
+  if (cost_layout2(D, NB, stages).total > 220 * 1024) stages = 1;
+  if (cost_layout2(D, NB, stages).total > 220 * 1024) return 0;
+  const int col_blocks = kpad / NB;
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < NB) tmem_cols <<= 1;
+  CUtensorMap tmap;
+  const cuuint64_t dims[2] = {(cuuint64_t)D, (cuuint64_t)n};
+  const cuuint64_t strides[1] = {(cuuint64_t)D * 4};
+  const cuuint32_t box[2] = {4, (cuuint32_t)kTileRows};
+  const cuuint32_t estr[2] = {1, 1};
+  if (enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(X), dims, strides, box, estr,
+          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return 0;
+  const CostSmemLayout2 L = cost_layout2(D, NB, stages);
+  auto kern = cost_tma_kernel<D>;
+  URE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+  int occ = 0;
+  URE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kCostThreads, L.total));
+  if (occ < 1) return 0;
+  const int max_by_tmem = 512 / (int)tmem_cols;
+  if (occ > max_by_tmem) occ = max_by_tmem;
+  if (occ > 4) occ = 4;
+  *used = 1;
+  const long long n_tiles = (n + kTileRows - 1) / kTileRows;
+  long long gx = (long long)num_sms() * occ / col_blocks;
+  if (gx < 1) gx = 1;
+  if (gx > n_tiles) gx = n_tiles;
+  double* fused_inertia = (col_blocks == 1) ? inertia : nullptr;
+  kern<<<dim3((unsigned)gx, (unsigned)col_blocks), kCostThreads, L.total, st>>>(tmap, n, C, k, kpad, NB, stages, tmem_cols, M,
+                                                                            fused_inertia);
+  URE_CUDA(cudaGetLastError());
+  if (inertia && !fused_inertia) *used = 2;
+  return 0;
+}
+
 // ------------------------------------------------------------------ CUDA-core check kernel
 // Direct fp32 sum_t (x-c)^2 (the reference expression): one thread per (row, column).
 __global__ void cost_simt_kernel(const float* __restrict__ X, long long n, int d, const float* __restrict__ C, int k,
@@ -314,15 +569,25 @@ int launch_rowmin(const float* M, long long n, int k, int kpad, double* inertia,
 template <int D>
 int launch_cost_tc(const float* X, long long n, const float* C, int k, int kpad, float* M, double* inertia,
                    cudaStream_t st) {
+  {
+    int used = 0;
+    if (int rc = launch_cost_tma<D>(X, n, C, k, kpad, M, inertia, st, &used)) return rc;
+    if (used == 1) return 0;
+    if (used == 2) return launch_rowmin(M, n, k, kpad, inertia, st);
+  }
   // choose the column block NB (multiple of 16) and the number of raw stages that fit in shared memory
-  const uint32_t budget = 220 * 1024;
-  int NB = kpad, stages = 2;
+  // one raw stage leaves room for a second CTA per SM at d = 64 (its latency phases then overlap the other CTA's
+  // work); URE_COST_STAGES=1|2 pins the choice (experiments)
+  static const int want_stages = getenv("URE_COST_STAGES") ? atoi(getenv("URE_COST_STAGES")) : 0;
+  const uint32_t budget = want_stages == 1 ? 110 * 1024 : 220 * 1024;
+  int NB = kpad, stages = want_stages == 1 ? 1 : 2;
   while (true) {
     if (cost_layout(D, NB, stages).total <= budget) break;
     if (stages == 2 && cost_layout(D, NB, 1).total <= budget) { stages = 1; break; }
+    if (NB <= 16 && want_stages == 1 && budget < 220 * 1024) { stages = 1; break; }      // cannot halve further
     if (NB <= 16) { set_error("ure_cost_matrix: d=%d does not fit shared memory", D); return URE_EUNSUPPORTED; }
     NB = ((NB / 2 + 15) / 16) * 16;
-    stages = 2;
+    stages = want_stages == 1 ? 1 : 2;
   }
   const int col_blocks = (kpad + NB - 1) / NB;
   URE_REQUIRE(col_blocks * NB == kpad, URE_EUNSUPPORTED, "ure_cost_matrix: kpad=%d not divisible into %d-column blocks",
@@ -343,8 +608,9 @@ int launch_cost_tc(const float* X, long long n, const float* C, int k, int kpad,
   if (gx < 1) gx = 1;
   if (gx > n_tiles) gx = n_tiles;
   double* fused_inertia = (col_blocks == 1) ? inertia : nullptr;
+  static const int raw_hi = getenv("URE_COST_RAW_HI") ? atoi(getenv("URE_COST_RAW_HI")) : 0;
   kern<<<dim3((unsigned)gx, (unsigned)col_blocks), kCostThreads, L.total, st>>>(X, n, C, k, kpad, NB, stages, tmem_cols, M,
-                                                                            fused_inertia);
+                                                                            fused_inertia, raw_hi);
   URE_CUDA(cudaGetLastError());
   if (inertia && !fused_inertia) return launch_rowmin(M, n, k, kpad, inertia, st);
   return 0;

@@ -90,7 +90,8 @@ __device__ __forceinline__ void load_g(const float* g, int k, int gl, float4 (&o
 // row `base_row`.  Arithmetic in log2 units: t = (g_j - M_ij) * log2(e)/eps.
 template <int KPAD>
 __device__ __forceinline__ void colsum_rows(const float* Msrc, long long base_row, long long r0, long long r1,
-                                            const float* g_sh, int k, float scale, float* part_r, float* part_s) {
+                                            const float* g_sh, int k, float scale, float* part_r, float* part_s,
+                                            int stride = KPAD) {       // floats between rows (>= KPAD: a column slice)
   using RM = RowMap<KPAD>;
   const int lane = threadIdx.x & 31;
   const int gl = lane % RM::LPR;
@@ -112,33 +113,37 @@ __device__ __forceinline__ void colsum_rows(const float* Msrc, long long base_ro
     const long long row = row0 + rw;
     const bool valid = row < r1;
     float4 t[RM::VEC];
-    float mx = -INFINITY;
+    float mx = -1.0e30f;                     // a row slot past the end holds +inf costs: every q below is exactly 0
 #pragma unroll
     for (int v = 0; v < RM::VEC; ++v) {
-      float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (valid) m = *(reinterpret_cast<const float4*>(Msrc + (row - base_row) * KPAD) + v * RM::LPR + gl);
+      float4 m = make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
+      if (valid) m = *(reinterpret_cast<const float4*>(Msrc + (row - base_row) * stride) + v * RM::LPR + gl);
       t[v].x = fmaf(m.x, nscale, gs[v].x); t[v].y = fmaf(m.y, nscale, gs[v].y);
       t[v].z = fmaf(m.z, nscale, gs[v].z); t[v].w = fmaf(m.w, nscale, gs[v].w);
       mx = fmaxf(mx, fmaxf(fmaxf(t[v].x, t[v].y), fmaxf(t[v].z, t[v].w)));
     }
 #pragma unroll
     for (int o = RM::LPR / 2; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o, RM::LPR));
-    // d = t - rowmax (<= 0); the entry's exponent relative to the lane's column reference is d - r
-    float over = -INFINITY;
+    // q = 2^((t - rowmax) - r): the entry relative to the lane's column reference.  One exponential per element; a
+    // q beyond 2^60 (the first row of a column, or a jump of more than 60 binades) re-bases the reference first.
+    float4 q[RM::VEC];
+    float big = 0.f;
 #pragma unroll
     for (int v = 0; v < RM::VEC; ++v) {
-      t[v].x -= mx; t[v].y -= mx; t[v].z -= mx; t[v].w -= mx;
-      over = fmaxf(over, fmaxf(fmaxf(t[v].x - ref[v].x, t[v].y - ref[v].y), fmaxf(t[v].z - ref[v].z, t[v].w - ref[v].w)));
+      q[v].x = ex2_fast((t[v].x - mx) - ref[v].x); q[v].y = ex2_fast((t[v].y - mx) - ref[v].y);
+      q[v].z = ex2_fast((t[v].z - mx) - ref[v].z); q[v].w = ex2_fast((t[v].w - mx) - ref[v].w);
+      big = fmaxf(big, fmaxf(fmaxf(q[v].x, q[v].y), fmaxf(q[v].z, q[v].w)));
     }
-    if (valid && over > kRebase) {           // rare: the first row of a column, or a jump of more than 2^60
+    if (big > 1.0e18f) {                     // rare
 #pragma unroll
       for (int v = 0; v < RM::VEC; ++v) {
 #define URE_REBASE(C)                                                     \
-  if (t[v].C - ref[v].C > kRebase) {                                      \
-    const float nr = rintf(t[v].C);                                       \
+  if (q[v].C > 1.0e18f) {                                                 \
+    const float nr = rintf(t[v].C - mx);                                  \
     acc[v].C *= ex2_fast(ref[v].C - nr);                                  \
     ref[v].C = nr;                                                        \
     cref[v].C = ex2_fast(nr);                                             \
+    q[v].C = ex2_fast((t[v].C - mx) - nr);                                \
   }
         URE_REBASE(x) URE_REBASE(y) URE_REBASE(z) URE_REBASE(w)
 #undef URE_REBASE
@@ -146,19 +151,17 @@ __device__ __forceinline__ void colsum_rows(const float* Msrc, long long base_ro
     }
     float s = 0.f;
 #pragma unroll
-    for (int v = 0; v < RM::VEC; ++v) {      // q = 2^e feeds the row sum (times 2^r) and the column sum
-      t[v].x = ex2_fast(t[v].x - ref[v].x); t[v].y = ex2_fast(t[v].y - ref[v].y);
-      t[v].z = ex2_fast(t[v].z - ref[v].z); t[v].w = ex2_fast(t[v].w - ref[v].w);
-      s = fmaf(t[v].x, cref[v].x, s); s = fmaf(t[v].y, cref[v].y, s);
-      s = fmaf(t[v].z, cref[v].z, s); s = fmaf(t[v].w, cref[v].w, s);
+    for (int v = 0; v < RM::VEC; ++v) {      // the row sum wants 2^(t - rowmax) = q * 2^r
+      s = fmaf(q[v].x, cref[v].x, s); s = fmaf(q[v].y, cref[v].y, s);
+      s = fmaf(q[v].z, cref[v].z, s); s = fmaf(q[v].w, cref[v].w, s);
     }
 #pragma unroll
     for (int o = RM::LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o, RM::LPR);
     const float w = valid ? __frcp_rn(s) : 0.f;      // s in [1, KPAD] for a valid row (its maximum contributes 1)
 #pragma unroll
     for (int v = 0; v < RM::VEC; ++v) {
-      acc[v].x = fmaf(t[v].x, w, acc[v].x); acc[v].y = fmaf(t[v].y, w, acc[v].y);
-      acc[v].z = fmaf(t[v].z, w, acc[v].z); acc[v].w = fmaf(t[v].w, w, acc[v].w);
+      acc[v].x = fmaf(q[v].x, w, acc[v].x); acc[v].y = fmaf(q[v].y, w, acc[v].y);
+      acc[v].z = fmaf(q[v].z, w, acc[v].z); acc[v].w = fmaf(q[v].w, w, acc[v].w);
     }
   }
   // lanes with equal gl hold the same columns: fold the RPW row slots of the warp, re-based to the larger reference
@@ -203,7 +206,7 @@ __device__ __forceinline__ double pair_to_double(float R, float S, double a) {
 template <int KPAD>
 __global__ void __launch_bounds__(kSkThreads)
 colsum_kernel(const float* __restrict__ M, long long n, int k, const float* __restrict__ g, float scale, double a,
-              double* __restrict__ colsum) {
+              double* __restrict__ colsum, int stride) {
   __shared__ float g_sh[KPAD];
   __shared__ __align__(16) float part_r[(kSkThreads / 32) * KPAD];
   __shared__ __align__(16) float part_s[(kSkThreads / 32) * KPAD];
@@ -213,7 +216,7 @@ colsum_kernel(const float* __restrict__ M, long long n, int k, const float* __re
   const long long r0 = per * blockIdx.x;
   const long long r1 = r0 + per < n ? r0 + per : n;
   if (r0 >= r1) return;
-  colsum_rows<KPAD>(M, 0, r0, r1, g_sh, k, scale, part_r, part_s);
+  colsum_rows<KPAD>(M, 0, r0, r1, g_sh, k, scale, part_r, part_s, stride);
   __syncthreads();
   for (int j = threadIdx.x; j < k; j += blockDim.x) {
     float R, S;
@@ -297,6 +300,115 @@ sinkhorn_kernel(const float* __restrict__ M, long long n, int k, float* __restri
         if (blockIdx.x == 0) ws->colsum[(it_global + 2) % 3][j] = 0.0;
         const float e = (float)(fabs(c * (double)k - 1.0));
         atomicMax(reinterpret_cast<int*>(&err_sh), __float_as_int(e));       // e >= 0: int order == float order
+      }
+      __syncthreads();
+      const float err = err_sh;
+      if (blockIdx.x == 0 && tid == 0) { ws->col_err = (double)err; ws->iters_done = it_global + 1; }
+      __syncthreads();
+      if (stages.tol > 0.f && err < stages.tol) { ++it_global; break; }
+    }
+  }
+  if (blockIdx.x == 0)
+    for (int j = tid; j < k; j += blockDim.x) g_io[j] = g_sh[j];
+}
+
+// --------------------------------------------------------------------------- multi-GPU Sinkhorn over peer memory
+// Users (rows of M) are sharded over the GPUs of one NVSwitch domain; an iteration needs the k column sums of ALL
+// rows.  Instead of `column pass -> NCCL all-reduce -> update` (three launches and a collective per iteration, each
+// costing more than the pass itself at 1 M users per GPU), ONE persistent kernel per GPU runs every iteration:
+//   column pass over the GPU's rows -> grid barrier -> CTA 0 stores the GPU's k sums into EVERY peer's exchange
+//   buffer (NVLink stores into symmetric memory), fences, and raises its flag there -> every CTA polls the flags in
+//   its OWN buffer, adds the per-GPU sums in rank order (identical on every GPU, bit for bit) and updates g.
+// Buffers alternate by iteration parity: a peer can only be two iterations ahead after it has seen this GPU's flag of
+// the next iteration, which is raised after every CTA here has read the current slot.  Flags only grow (call_base +
+// iteration), so nothing is ever reset between calls.  A poll that does not succeed within ~2 s raises the error word
+// instead of hanging the GPU.
+constexpr int kPeerMax = 16;
+struct SkPeers {
+  unsigned long long* xchg[kPeerMax];      // every rank's exchange buffer (peer-mapped), this rank's own included
+};
+struct SkXchg {
+  unsigned long long flag[2][kPeerMax];
+  double val[2][kPeerMax][256];
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+template <int KPAD>
+__global__ void __launch_bounds__(kSkThreads, 1)
+sinkhorn_peer_kernel(const float* __restrict__ M, long long n, double n_total, int k, float* __restrict__ g_io,
+                     SkStages stages, SkWorkspace* ws, SkPeers peers, int rank, int world, unsigned long long call_base,
+                     int stride) {
+  constexpr int NWARP = kSkThreads / 32;
+  __shared__ float g_sh[KPAD];
+  __shared__ __align__(16) float part_r[NWARP * KPAD];
+  __shared__ __align__(16) float part_s[NWARP * KPAD];
+  __shared__ float err_sh;
+  __shared__ int fail_sh;
+  const int tid = threadIdx.x;
+  const long long per = (n + gridDim.x - 1) / gridDim.x;
+  const long long r0 = per * blockIdx.x < n ? per * blockIdx.x : n;
+  const long long r1 = r0 + per < n ? r0 + per : n;
+  for (int j = tid; j < KPAD; j += blockDim.x) g_sh[j] = j < k ? g_io[j] : 0.f;
+  if (tid == 0) fail_sh = 0;
+  __syncthreads();
+  const double a = 1.0 / n_total;
+  const double logb = -log((double)k);
+  SkXchg* const mine = reinterpret_cast<SkXchg*>(peers.xchg[rank]);
+  unsigned bar_target = 0;
+  long long it_global = 0;
+  for (int s = 0; s < stages.n; ++s) {
+    const float eps = stages.eps[s];
+    const float scale = kLog2e / eps;
+    for (int it = 0; it < stages.iters[s]; ++it, ++it_global) {
+      double* cs = ws->colsum[it_global % 3];
+      const int par = (int)(it_global & 1);
+      const unsigned long long stamp = call_base + (unsigned long long)it_global + 1ull;
+      if (r0 < r1) {
+        colsum_rows<KPAD>(M, 0, r0, r1, g_sh, k, scale, part_r, part_s, stride);
+        __syncthreads();
+        for (int j = tid; j < k; j += blockDim.x) {
+          float R, S;
+          fold_parts(part_r, part_s, NWARP, KPAD, j, R, S);
+          if (S != 0.f) atomicAdd(cs + j, pair_to_double(R, S, a));
+        }
+      }
+      grid_barrier(&ws->barrier, bar_target);
+      if (blockIdx.x == 0) {
+        // this GPU's sums -> slot `rank` of every GPU's buffer, then the flag (release, system scope)
+        for (int x = tid; x < world * k; x += blockDim.x) {
+          const int p = x / k, j = x - p * k;
+          reinterpret_cast<SkXchg*>(peers.xchg[p])->val[par][rank][j] = __ldcg(cs + j);
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (tid < world) st_release_sys_u64(&reinterpret_cast<SkXchg*>(peers.xchg[tid])->flag[par][rank], stamp);
+        for (int j = tid; j < k; j += blockDim.x) ws->colsum[(it_global + 2) % 3][j] = 0.0;
+      }
+      if (tid < world) {                    // every CTA polls its OWN GPU's flags: one lane per source rank
+        long long spins = 0;
+        while (ld_acquire_sys_u64(&mine->flag[par][tid]) < stamp)
+          if (++spins > (1ll << 23)) { fail_sh = 1; break; }     // a few seconds
+      }
+      if (tid == 0) err_sh = 0.f;
+      __syncthreads();
+      if (fail_sh) {                        // a peer never arrived: stop (identical data is not guaranteed any more)
+        if (tid == 0) ws->iters_done = -1;
+        return;
+      }
+      for (int j = tid; j < k; j += blockDim.x) {
+        double c = 0.0;
+        for (int r = 0; r < world; ++r) c += __ldcv(&mine->val[par][r][j]);      // rank order: same sum everywhere
+        g_sh[j] = (float)((double)g_sh[j] + (double)eps * (logb - log(c)));
+        const float e = (float)(fabs(c * (double)k - 1.0));
+        atomicMax(reinterpret_cast<int*>(&err_sh), __float_as_int(e));
       }
       __syncthreads();
       const float err = err_sh;
@@ -718,7 +830,13 @@ extern "C" int ure_sinkhorn_colsum(const float* d_M, int64_t n, int k, int kpad,
   const long long cap = (long long)num_sms() * 4;
   if (blocks > cap) blocks = cap;
   auto st = static_cast<cudaStream_t>(stream);
-  URE_KPAD_SWITCH(kpad, (colsum_kernel<KP><<<(unsigned)blocks, kSkThreads, 0, st>>>(d_M, n, k, d_g, scale, a, d_colsum)));
+  if (k <= 8) {
+    // only the first 8 columns hold centroids (the rest of the kpad-wide row is +inf padding): read that 32-byte
+    // slice of every row -- half the bytes and half the exponentials at kpad = 16
+    colsum_kernel<8><<<(unsigned)blocks, kSkThreads, 0, st>>>(d_M, n, k, d_g, scale, a, d_colsum, kpad);
+  } else {
+    URE_KPAD_SWITCH(kpad, (colsum_kernel<KP><<<(unsigned)blocks, kSkThreads, 0, st>>>(d_M, n, k, d_g, scale, a, d_colsum, kpad)));
+  }
   URE_CUDA(cudaGetLastError());
   return 0;
 }
@@ -783,6 +901,50 @@ extern "C" int ure_sinkhorn(const float* d_M, int64_t n, int k, int kpad, float*
       if (int rc = ure_sinkhorn_colsum(d_M, n, k, kpad, d_g, h_eps[s], (double)n, ws->colsum[0], stream)) return rc;
       if (int rc = ure_sinkhorn_update_g(d_g, ws->colsum[0], k, h_eps[s], stream)) return rc;
     }
+  return 0;
+}
+
+extern "C" int64_t ure_sinkhorn_peer_xchg_bytes(void) { return (int64_t)sizeof(ure::SkXchg); }
+
+extern "C" int ure_sinkhorn_peer(const float* d_M, int64_t n_local, double n_total, int k, int kpad, float* d_g,
+                                 const float* h_eps, const int32_t* h_iters, int n_stages, float tol,
+                                 const uint64_t* h_xchg_ptrs, int rank, int world, uint64_t call_base,
+                                 void* d_workspace, void* stream) {
+  using namespace ure;
+  URE_REQUIRE(d_M && d_g && h_eps && h_iters && h_xchg_ptrs && d_workspace, URE_EINVAL, "ure_sinkhorn_peer: null argument");
+  URE_REQUIRE(n_local >= 0 && n_total >= 1.0 && k >= 1 && k <= kpad && kpad <= 256, URE_EINVAL,
+              "ure_sinkhorn_peer: bad shape n_local=%lld k=%d kpad=%d", (long long)n_local, k, kpad);
+  URE_REQUIRE(world >= 1 && world <= kPeerMax && rank >= 0 && rank < world, URE_EINVAL,
+              "ure_sinkhorn_peer: rank %d of %d (at most %d GPUs)", rank, world, kPeerMax);
+  URE_REQUIRE(n_stages >= 1 && n_stages <= kMaxStages, URE_EINVAL, "ure_sinkhorn_peer: n_stages=%d", n_stages);
+  SkStages stg;
+  stg.n = n_stages;
+  stg.tol = tol;
+  for (int s = 0; s < n_stages; ++s) {
+    URE_REQUIRE(h_eps[s] > 0.f && h_iters[s] >= 0, URE_EINVAL, "ure_sinkhorn_peer: stage %d eps/iters invalid", s);
+    stg.eps[s] = h_eps[s];
+    stg.iters[s] = h_iters[s];
+  }
+  SkPeers peers;
+  for (int r = 0; r < kPeerMax; ++r) peers.xchg[r] = reinterpret_cast<unsigned long long*>(r < world ? h_xchg_ptrs[r] : 0);
+  auto st = static_cast<cudaStream_t>(stream);
+  auto* ws = static_cast<SkWorkspace*>(d_workspace);
+  URE_CUDA(cudaMemsetAsync(ws, 0, sizeof(SkWorkspace), st));
+  long long grid = (n_local + 2047) / 2048;
+  if (grid > num_sms()) grid = num_sms();
+  if (grid < 1) grid = 1;
+  long long nn = n_local;
+  unsigned long long base = call_base;
+  int stride = kpad;
+  void* args[] = {(void*)&d_M, (void*)&nn, (void*)&n_total, (void*)&k, (void*)&d_g, (void*)&stg, (void*)&ws,
+                  (void*)&peers, (void*)&rank, (void*)&world, (void*)&base, (void*)&stride};
+  if (k <= 8) {                            // the 8-column slice of every row, as in ure_sinkhorn_colsum
+    URE_CUDA(cudaLaunchCooperativeKernel((void*)sinkhorn_peer_kernel<8>, dim3((unsigned)grid), dim3(kSkThreads), args, 0, st));
+    return 0;
+  }
+  URE_KPAD_SWITCH(kpad, {
+    URE_CUDA(cudaLaunchCooperativeKernel((void*)sinkhorn_peer_kernel<KP>, dim3((unsigned)grid), dim3(kSkThreads), args, 0, st));
+  });
   return 0;
 }
 

@@ -46,6 +46,14 @@ class Dist:
                                group=self.group)
         return t
 
+    def all_gather_into(self, out: torch.Tensor, part: torch.Tensor) -> torch.Tensor:
+        """out [world * m, ...] <- every rank's `part` [m, ...] in rank order."""
+        if self.world == 1:
+            out.copy_(part)
+        else:
+            self.td.all_gather_into_tensor(out, part, group=self.group)
+        return out
+
     def sum_int(self, v: int) -> int:
         if self.world == 1:
             return int(v)

@@ -106,7 +106,7 @@ _PINNED_BYTES = {}   # capacity -> list of (pinned uint8 buffer, event): staging
 
 
 def _staging_bytes(nbytes: int) -> torch.Tensor:
-    cap = 1 << max(16, int(nbytes - 1).bit_length())
+    cap = 1 << max(12, int(nbytes - 1).bit_length())
     pool = _PINNED_BYTES.setdefault(cap, [])
     for item in pool:
         if item[1] is None or item[1].query():
@@ -321,6 +321,7 @@ def pointer_table(tensors: Sequence[torch.Tensor], device) -> torch.Tensor:
 
 # ------------------------------------------------------------------------------ MF training
 OWNER_SCHED_BYTES = 512 << 20  # device memory one ShardBatch may spend on owner-mode schedule tables
+RUNS_LIST_BYTES = 2 << 30      # device memory one ShardBatch may spend on the RUNS schedule's step lists
 OWNER_FORCE = None             # test hook: (owner_flags, list_cap) the owner schedule must use
 DEFAULT_MF_MODE = "auto"       # schedule ShardBatch picks when the caller does not say (see ShardBatch)
 
@@ -389,7 +390,7 @@ class ShardBatch:
         if not 1 <= len(shards) <= _lib.URE_MAX_SHARDS:
             raise ValueError(f"1..{_lib.URE_MAX_SHARDS} shards per launch")
         mode = ("lazy" if lazy else DEFAULT_MF_MODE) if mode is None else mode
-        if mode not in ("dense", "lazy", "owner", "auto"):
+        if mode not in ("dense", "lazy", "owner", "auto", "runs"):
             raise ValueError(f"mode {mode!r}")
         self.shards = shards
         self.n_shards = len(shards)
@@ -411,9 +412,11 @@ class ShardBatch:
             mode = self._prepare_owner(mode == "owner")
         self.mode = mode
         self._run_after_prepare()          # schedules without a set-up pass: right away
-        self.lazy = mode == "lazy"
+        self.lazy = mode in ("lazy", "runs")            # rows catch up in closed form: flush() before reading P / Q
         self.decay = None
-        if self.lazy:
+        if mode == "runs":
+            self._prepare_runs(lr, weight_decay, momentum)
+        elif self.lazy:
             # M^n for n = 0..total_steps (float64 on the host): the n-step gradient-free SGD update
             # [w;buf] <- M^n [w;buf], M = [[1-lr*wd, -lr*mu],[wd, mu]]  (csrc/mf_train_lazy.cu)
             M = np.array([[1.0 - lr * weight_decay, -lr * momentum], [weight_decay, momentum]])
@@ -546,6 +549,74 @@ class ShardBatch:
                                    (np.diff(tq) * 1e3).round(3).tolist()))
         return "owner"
 
+    def _decay_table(self, lr, weight_decay, momentum):
+        """M^n for n = 0..total_steps (float64 on the host): the n-step gradient-free SGD update
+        [w;buf] <- M^n [w;buf], M = [[1-lr*wd, -lr*mu],[wd, mu]]  (csrc/mf_train_lazy.cu, mf_train_runs.cu)"""
+        M = np.array([[1.0 - lr * weight_decay, -lr * momentum], [weight_decay, momentum]])
+        T = np.empty((self.total_steps + 2, 2, 2))
+        T[0] = np.eye(2)
+        for n in range(1, len(T)):
+            T[n] = M @ T[n - 1]
+        return torch.from_numpy(T.reshape(-1, 4).astype(np.float32)).to(self.device)
+
+    def _prepare_runs(self, lr, weight_decay, momentum):
+        """RUNS schedule set-up (csrc/mf_train_runs.cu): the user-sorted / item-sorted record copies of the owner
+        set-up, two row slots + a version tag per row, step lists for a window of epochs, the M^n table."""
+        L = _lib.lib()
+        shards, dev, d, K = self.shards, self.device, self.hp.d, len(self.shards)
+        n_tot = sum(s.n for s in shards)
+        max_n = max(s.n for s in shards)
+        spe_cap = max(1, max(s.steps_per_epoch(self.hp.batch) for s in shards))
+        if spe_cap >= 1024:
+            raise RuntimeError(f"runs mode handles < 1024 steps per epoch ({spe_cap})")
+        rec = torch.empty((2, max(1, n_tot), 4), dtype=torch.int32, device=dev)
+        tmp = torch.empty((2, max(1, n_tot), 4), dtype=torch.int32, device=dev)       # radix scratch: freed below
+        n_off = sum(s.P.shape[0] + s.Q.shape[0] + 4 for s in shards)
+        off = torch.zeros(n_off, dtype=torch.int32, device=dev)
+        rows = int(min(self.epochs, max(1, RUNS_LIST_BYTES // max(1, 8 * n_tot))))
+        lists = torch.empty((2, rows * max(1, n_tot)), dtype=torch.int32, device=dev)
+        loff = torch.zeros((K, 2, rows, spe_cap + 1), dtype=torch.int32, device=dev)
+        keep, o, r, lo = [rec, off, lists, loff], 0, 0, 0
+        runs = (_lib.MFRuns * K)()
+        for j, s in enumerate(shards):
+            s.inter_u, s.inter_i = rec[0, r:r + s.n], rec[1, r:r + s.n]
+            s.tmp_u, s.tmp_i = tmp[0, r:r + s.n], tmp[1, r:r + s.n]
+            r += s.n
+            nu, ni = s.P.shape[0] + 2, s.Q.shape[0] + 2
+            s.off_u, s.off_i = off[o:o + nu], off[o + nu:o + nu + ni]
+            o += nu + ni
+            s.perm_inv = torch.empty_like(s.perm) if s.perm is not None else None
+            slotP = torch.empty((2, s.P.shape[0], 2 * d), dtype=torch.float32, device=dev)
+            slotQ = torch.empty((2, s.Q.shape[0], 2 * d), dtype=torch.float32, device=dev)
+            metaP = torch.empty(s.P.shape[0], dtype=torch.int64, device=dev)
+            metaQ = torch.empty(s.Q.shape[0], dtype=torch.int64, device=dev)
+            keep += [slotP, slotQ, metaP, metaQ]
+            runs[j].slotP, runs[j].slotQ, runs[j].metaP, runs[j].metaQ = (t.data_ptr() for t in (slotP, slotQ, metaP, metaQ))
+            runs[j].list_u = lists[0, lo:].data_ptr()
+            runs[j].list_i = lists[1, lo:].data_ptr()
+            lo += rows * s.n
+            runs[j].loff_u, runs[j].loff_i = loff[j, 0].data_ptr(), loff[j, 1].data_ptr()
+        radix = torch.empty(int(L.ure_mf_owner_radix_bytes(K)) // 4, dtype=torch.int32, device=dev)
+        self._upload_table()
+        max_rows = max(max(s.P.shape[0], s.Q.shape[0]) for s in shards)
+        with torch.cuda.device(dev):
+            check(L.ure_mf_owner_prepare(_ptr(self.table), K, C.byref(self.hp), self.epochs, int(max_rows), _ptr(radix),
+                                         _ptr(self.ws), _stream()), "ure_mf_owner_prepare")
+        del tmp, radix
+        for s in shards:
+            s.tmp_u = s.tmp_i = None
+        self.decay = self._decay_table(lr, weight_decay, momentum)
+        self._runs_table = upload_array(np.frombuffer(bytes(runs), dtype=np.uint8), dev)
+        self._runs_scratch = torch.empty(int(L.ure_mf_runs_scratch_bytes(K, max_n, rows, spe_cap)), dtype=torch.uint8,
+                                         device=dev)
+        self._runs_keep, self._runs_max_n = keep, max_n
+        self.hp.mode, self.hp.decay, self.hp.decay_len = _lib.MF_RUNS, self.decay.data_ptr(), len(self.decay)
+        self.hp.runs, self.hp.runs_rows, self.hp.runs_spe_cap, self.hp.runs_step0 = self._runs_table.data_ptr(), rows, spe_cap, 0
+        with torch.cuda.device(dev):
+            check(L.ure_mf_runs_init(_ptr(self.table), K, C.byref(self.hp), _stream()), "ure_mf_runs_init")
+        self._sched_cover = (0, 0)
+        self._spes = [s.steps_per_epoch(self.hp.batch) for s in shards if s.n > 0]
+
     @staticmethod
     def _split_groups(shards, total_warps: int = 32, min_warps: int = 6) -> int:
         """Greedy split of the shards into two warp groups of near-equal interaction count; returns the
@@ -571,17 +642,28 @@ class ShardBatch:
         with torch.cuda.device(self.device):
             while self.step < step_end:
                 t1 = step_end
-                if self.mode == "owner":
-                    # the schedule tables hold owner_sched_rows epochs per shard from the window's first step on
+                if self.mode in ("owner", "runs"):
+                    # the schedule tables hold `rows` epochs per shard from the window's first step on
                     a, b = self._sched_cover
+                    rows = self.hp.owner_sched_rows if self.mode == "owner" else self.hp.runs_rows
                     if not (a <= self.step < b):
-                        check(L.ure_mf_owner_schedule(_ptr(self.table), self.n_shards, C.byref(self.hp), self.epochs,
-                                                      self.step, _stream()), "ure_mf_owner_schedule")
-                        self.launches_per_pass += 1
+                        if self.mode == "owner":
+                            check(L.ure_mf_owner_schedule(_ptr(self.table), self.n_shards, C.byref(self.hp), self.epochs,
+                                                          self.step, _stream()), "ure_mf_owner_schedule")
+                            self.launches_per_pass += 1
+                        else:
+                            check(L.ure_mf_runs_schedule(_ptr(self.table), self.n_shards, C.byref(self.hp), self.epochs,
+                                                         self.step, self._runs_max_n, _ptr(self._runs_scratch), _stream()),
+                                  "ure_mf_runs_schedule")
+                            self.launches_per_pass += 3
                         a = self.step                  # shard s leaves the window at step (a // spe_s + rows) * spe_s
-                        b = min([(a // spe + self.hp.owner_sched_rows) * spe for spe in self._spes
-                                 if a // spe + self.hp.owner_sched_rows < self.epochs] or [self.total_steps])
-                        self._sched_cover, self.hp.owner_sched_step0 = (a, b), a
+                        b = min([(a // spe + rows) * spe for spe in self._spes
+                                 if a // spe + rows < self.epochs] or [self.total_steps])
+                        self._sched_cover = (a, b)
+                        if self.mode == "owner":
+                            self.hp.owner_sched_step0 = a
+                        else:
+                            self.hp.runs_step0 = a
                     t1 = min(step_end, b)
                 check(L.ure_mf_train(_ptr(self.table), self.n_shards, C.byref(self.hp), self.epochs,
                                      self.step, t1, self.warps_group0, _ptr(self.ws), _stream()), "ure_mf_train")
@@ -598,7 +680,11 @@ class ShardBatch:
 
     def flush(self) -> None:
         """Lazy mode: advance every row to the current step (call before reading P / Q)."""
-        if self.lazy:
+        if self.mode == "runs":
+            with torch.cuda.device(self.device):
+                check(_lib.lib().ure_mf_runs_flush(_ptr(self.table), self.n_shards, C.byref(self.hp), self.epochs,
+                                                   self.step, _stream()), "ure_mf_runs_flush")
+        elif self.lazy:
             with torch.cuda.device(self.device):
                 check(_lib.lib().ure_mf_flush(self.host_table, len(self.shards), C.byref(self.hp), self.epochs,
                                               self.step, _stream()), "ure_mf_flush")
@@ -871,21 +957,21 @@ def user_segments(users: np.ndarray):
 
 def user_segments_device(inter: torch.Tensor, n_user: int):
     """(order int32 [n], seg int64 [n_user + 1]) of the per-user test segments (utils.py:151-161), built ON the device
-    without a host synchronisation: a stable sort of the records by user id (rows of a user stay in file order),
-    segment r = the r-th distinct user; segments past the last user are empty (seg = n) and rank_metrics skips them.
-    The ranking metrics are sums over users, so the order of the segments does not matter."""
+    without a host synchronisation by ure_user_segments: the owner set-up's stable radix sort on the user id (rows of
+    a user stay in file order), CSR offsets by user id; users without test rows are empty segments (rank_metrics
+    skips them).  The ranking metrics are sums over users, so the order of the segments does not matter."""
     _need_cuda(inter)
     n, dev = inter.shape[0], inter.device
-    seg = torch.full((n_user + 1,), n, dtype=torch.int64, device=dev)
     if n == 0 or n_user <= 0:
-        return None, seg
-    su, order = torch.sort(inter[:, 0].contiguous(), stable=True)
-    run = torch.zeros(n, dtype=torch.int64, device=dev)
-    if n > 1:
-        torch.cumsum((su[1:] != su[:-1]).to(torch.int64), 0, out=run[1:])
-    run.clamp_(max=n_user - 1)
-    seg.scatter_reduce_(0, run, torch.arange(n, dtype=torch.int64, device=dev), "amin")
-    return order.to(torch.int32), seg
+        return None, torch.full((max(0, n_user) + 1,), n, dtype=torch.int64, device=dev)
+    L = _lib.lib()
+    seg = torch.empty(n_user + 1, dtype=torch.int64, device=dev)
+    order = torch.empty(n, dtype=torch.int32, device=dev)
+    scratch = torch.empty(int(L.ure_user_segments_scratch_bytes(n, n_user)), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        check(L.ure_user_segments(_ptr(inter.contiguous()), n, n_user, _ptr(order), _ptr(seg), _ptr(scratch), _stream()),
+              "ure_user_segments")
+    return order, seg
 
 
 def rank_metrics(inter, score, seg, order=None) -> torch.Tensor:
@@ -956,14 +1042,56 @@ def sinkhorn(M, k, eps_schedule, g=None, tol: float = 0.0) -> torch.Tensor:
     return g
 
 
-def sinkhorn_sharded(M, k, eps_schedule, dist, n_total, g=None) -> torch.Tensor:
-    """Sinkhorn with the users (rows of M) sharded over the ranks of `dist`: every iteration is one column pass per
-    rank, an all-reduce of the kpad column marginals over the GPUs, and the potential update (replicated).  One rank:
-    the single-GPU solver.  Returns g fp32 [k] (identical on every rank)."""
+_PEER_XCHG = {}      # (device index, world) -> (symmetric tensor, peer pointers, [call_base])
+PEER_SINKHORN = True  # False: always the NCCL all-reduce loop (tests compare the two)
+
+
+def _peer_exchange(dist, dev):
+    """Symmetric (peer-mapped) exchange buffer of the fused multi-GPU Sinkhorn: allocated once per process through
+    torch's symmetric-memory allocator, zero-filled, rendezvoused over the process group -> every rank's address."""
+    key = (dev.index, dist.world)
+    if key not in _PEER_XCHG:
+        try:
+            import torch.distributed._symmetric_memory as symm
+            nbytes = int(_lib.lib().ure_sinkhorn_peer_xchg_bytes())
+            t = symm.empty(nbytes // 8, dtype=torch.int64, device=dev)
+            t.zero_()
+            hdl = symm.rendezvous(t, dist.group if dist.group is not None else dist.td.group.WORLD)
+            ptrs = [int(p) for p in hdl.buffer_ptrs]
+            torch.cuda.synchronize(dev)
+            dist.barrier()                                   # every buffer is zero before anybody's kernel runs
+            _PEER_XCHG[key] = (t, hdl, ptrs, [1])
+        except Exception as e:                               # no peer access (e.g. gloo / one GPU per node)
+            _PEER_XCHG[key] = e
+    got = _PEER_XCHG[key]
+    return None if isinstance(got, Exception) else got
+
+
+def sinkhorn_sharded(M, k, eps_schedule, dist, n_total, g=None, tol: float = 0.0) -> torch.Tensor:
+    """Sinkhorn with the users (rows of M) sharded over the ranks of `dist`.  One rank: the single-GPU solver.
+    Several GPUs with peer access: ONE persistent kernel per GPU that exchanges the k column sums through peer-mapped
+    symmetric memory every iteration (ure_sinkhorn_peer).  Otherwise: column pass, all-reduce of the kpad column
+    marginals, potential update per iteration.  Returns g fp32 [k], bit-identical on every rank."""
     if dist is None or dist.world == 1:
-        return sinkhorn(M, k, eps_schedule, g=g)
-    g = torch.zeros(k, dtype=torch.float32, device=M.device) if g is None else g.clone()
-    colsum = torch.zeros(M.shape[1], dtype=torch.float64, device=M.device)
+        return sinkhorn(M, k, eps_schedule, g=g, tol=tol)
+    dev = M.device
+    g = torch.zeros(k, dtype=torch.float32, device=dev) if g is None else g.clone()
+    xchg = _peer_exchange(dist, dev) if (PEER_SINKHORN and M.is_cuda) else None
+    if xchg is not None:
+        _, _, ptrs, base = xchg
+        S = len(eps_schedule)
+        eps = (C.c_float * S)(*[float(e) for e, _ in eps_schedule])
+        its = (C.c_int32 * S)(*[int(i) for _, i in eps_schedule])
+        total = sum(int(i) for _, i in eps_schedule)
+        ws = torch.zeros(int(_lib.lib().ure_sinkhorn_workspace_bytes()), dtype=torch.uint8, device=dev)
+        arr = (C.c_uint64 * dist.world)(*ptrs)
+        with torch.cuda.device(dev):
+            check(_lib.lib().ure_sinkhorn_peer(_ptr(M), M.shape[0], float(n_total), k, M.shape[1], _ptr(g), eps, its, S,
+                                               float(tol), arr, dist.rank, dist.world, base[0], _ptr(ws), _stream()),
+                  "ure_sinkhorn_peer")
+        base[0] += total + 2
+        return g
+    colsum = torch.zeros(M.shape[1], dtype=torch.float64, device=dev)
     for eps, iters in eps_schedule:
         for _ in range(int(iters)):
             sinkhorn_colsum(M, k, g, eps, n_total, colsum)

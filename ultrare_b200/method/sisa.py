@@ -38,7 +38,7 @@ from torch import nn
 from .. import dist as udist
 from .. import kernels as kn
 from .scratch import Scratch
-from .utils import baseTest
+from .utils import baseTest, base_test_device, base_test_values
 
 
 class _Table:
@@ -102,7 +102,14 @@ def _eval_rows(recs, n_user):
     key = (tuple((r.data_ptr(), r.shape[0]) for r in recs), n_user)
     hit = _EVAL_ROWS.get(key)
     if hit is None:
-        inter = recs[0] if len(recs) == 1 else torch.cat(recs)
+        if len(recs) == 1:
+            inter = recs[0]
+        else:                              # back to back in one buffer: device-to-device copies, no kernel
+            inter = torch.empty((sum(r.shape[0] for r in recs), 4), dtype=torch.int32, device=recs[0].device)
+            o = 0
+            for r in recs:
+                inter[o:o + r.shape[0]].copy_(r, non_blocking=True)
+                o += r.shape[0]
         order, seg = kn.user_segments_device(inter, n_user)
         _EVAL_ROWS.clear()                 # one entry: the resident test sets of the current run
         hit = _EVAL_ROWS[key] = (inter, order, seg, recs)
@@ -337,16 +344,25 @@ class Sisa(Scratch):
                 self.log['time'].extend([stamp] * E)
                 last_idx[i] = len(self.log['test_rmse']) - 1
             return last_idx
+        # per-epoch evaluations (scratch.py:83-97): ALL of them are queued first -- two launches each, no
+        # synchronisation -- and their sums come back in one transfer (round 1 synchronised after every baseTest:
+        # 2 x epochs x shards host round trips)
+        queued = {}
         for j, i in enumerate(mine):
             pri = prior(i, models) if mode.startswith('faithful') else None
             for e in range(E):
-                self.log['train_loss'].append(float(losses[j][e]))
-                tr = to = (nan, nan, nan)
                 if mode == 'faithful' or (mode == 'faithful-last' and e == E - 1):
                     P, Q = snaps[(i, e)] if mode == 'faithful' else (states[j].P, states[j].Q)
                     ms = pri + [_Table(P, Q)]
-                    tr = baseTest(test_dlist[i], ms, self.loss_fn, self.device, 0)
-                    to = baseTest(test_data, ms, self.loss_fn, self.device, 0)
+                    queued[(i, e)] = (base_test_device(test_dlist[i], ms), base_test_device(test_data, ms))
+        keys = list(queued)
+        host = kn.download_many([queued[k][w][0] for k in keys for w in (0, 1)]) if keys else []
+        results = {k: (base_test_values(host[2 * x], queued[k][0][1]), base_test_values(host[2 * x + 1], queued[k][1][1]))
+                   for x, k in enumerate(keys)}
+        for j, i in enumerate(mine):
+            for e in range(E):
+                self.log['train_loss'].append(float(losses[j][e]))
+                tr, to = results.get((i, e), ((nan, nan, nan), (nan, nan, nan)))
                 for key, v in zip(('test_rmse', 'test_ndcg', 'test_hr'), tr):
                     self.log[key].append(v)
                 for key, v in zip(('total_rmse', 'total_ndcg', 'total_hr'), to):
@@ -416,24 +432,37 @@ class Sisa(Scratch):
             kn.merge_user_rows(tables, self._owner, merged, row_of=row_of, retrain=retrain_flags,
                                zero_unowned=base is None)
             return merged
-        # multi-GPU: each rank contributes the rows of the shards it trained; rows are disjoint
+        # multi-GPU: each rank contributes the rows of the shards it trained.  Owner rows are disjoint, so the ranks
+        # ALL-GATHER their compact tables (each rank's shards back to back, padded to the longest rank) -- every
+        # row crosses NVLink once -- and the merge kernel gathers from the gathered buffer through per-shard base
+        # pointers.  (Round 1 all-reduced a zero-filled [n_user, k] table: twice the bytes.)
         t0 = time.perf_counter()
-        flags_np = np.zeros(K, dtype=np.int32)
-        flags_np[list(unmerged)] = 1
-        mine_flags = kn.upload_array(flags_np, dev)
-        contrib = torch.zeros((self.n_user, self.k), dtype=torch.float32, device=dev)
-        if unmerged:
-            kn.merge_user_rows(tables, self._owner, contrib, row_of=row_of, retrain=mine_flags, zero_unowned=True)
+        trained = sorted(self.retrain_gid) if base is not None else list(range(K))
+        sizes = {s_: (len(self.group_index[s_]) if compact else self.n_user) for s_ in trained}
+        by_rank = {}
+        for s_ in trained:
+            by_rank.setdefault(self.dist.owner_of_shard(s_), []).append(s_)
+        maxlen = max([sum(sizes[s_] for s_ in v) for v in by_rank.values()] or [1])
+        send = torch.empty((maxlen, self.k), dtype=torch.float32, device=dev)
+        o = 0
+        for s_ in by_rank.get(self.dist.rank, []):
+            send[o:o + sizes[s_]].copy_(unmerged[s_], non_blocking=True)
+            o += sizes[s_]
+        gathered = torch.empty((self.dist.world * maxlen, self.k), dtype=torch.float32, device=dev)
         t1 = time.perf_counter()
-        self.dist.all_reduce(contrib)
+        self.dist.all_gather_into(gathered, send)
         self.timing['merge_local_ms'] = (t1 - t0) * 1e3
-        self.timing['merge_allreduce_ms'] = (time.perf_counter() - t1) * 1e3
-        if base is None:
-            return contrib
-        # retrained owners' rows of the reduced table over a copy of the pre-unlearn table: the merge kernel again,
-        # with the reduced table (indexed by global user id) standing in for every shard's table
-        merged = base.clone()
-        kn.merge_user_rows([contrib] * K, self._owner, merged, row_of=None, retrain=retrain_flags, zero_unowned=False)
+        self.timing['merge_allgather_ms'] = (time.perf_counter() - t1) * 1e3
+        tables, flags_np = [gathered] * K, np.zeros(K, dtype=np.int32)
+        for r_, v in by_rank.items():
+            o = r_ * maxlen
+            for s_ in v:
+                tables[s_] = gathered[o:o + sizes[s_]]
+                flags_np[s_] = 1
+                o += sizes[s_]
+        merged = torch.zeros((self.n_user, self.k), dtype=torch.float32, device=dev) if base is None else base.clone()
+        kn.merge_user_rows(tables, self._owner, merged, row_of=row_of, retrain=kn.upload_array(flags_np, dev),
+                           zero_unowned=base is None)
         return merged
 
     # ------------------------------------------------------------------ learn / unlearn

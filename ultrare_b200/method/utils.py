@@ -157,12 +157,9 @@ def baseTrain(dataloader, model, loss_fn, is_rmse, opt, device, verbose, var='no
     return train_loss, train_loss
 
 
-def baseTest(dataloader, models, loss_fn, device, verbose, top_k=10):
-    """Ensemble evaluation (reference utils.py:115-187); returns (rmse, ndcg, hr).
-
-    Tie order of the per-user top-10: descending value, later index first (SURVEY.md H7).
-    """
-    assert top_k == kn._lib.URE_TOP_K
+def base_test_device(dataloader, models):
+    """The evaluation kernels of baseTest queued on the stream, no synchronisation: returns the device tensor
+    fp64 [4] = (sum of squared errors, sum of NDCG@10, sum of HR@10, users) and the number of test rows."""
     dev = models[0].user_mat.weight.device
     ds = dataloader.dataset
     inter = ds.records(dev)
@@ -170,11 +167,24 @@ def baseTest(dataloader, models, loss_fn, device, verbose, top_k=10):
                                    [m.item_mat.weight.data for m in models], inter)
     order, seg = ds.segments(dev, models[0].user_mat.weight.shape[0])
     out = kn.rank_metrics(inter, score, seg, order)
-    vals = torch.cat([sse, out]).cpu().numpy()
-    size = len(ds)
-    rmse = float(np.sqrt(vals[0] / size))
+    return torch.cat([sse, out]), len(ds)
+
+
+def base_test_values(vals, size):
+    """(rmse, ndcg, hr) from the four sums of base_test_device (host values)."""
+    rmse = float(np.sqrt(vals[0] / max(1, size)))
     users = max(vals[3], 1.0)
-    ndcg, hr = float(vals[1] / users), float(vals[2] / users)
+    return rmse, float(vals[1] / users), float(vals[2] / users)
+
+
+def baseTest(dataloader, models, loss_fn, device, verbose, top_k=10):
+    """Ensemble evaluation (reference utils.py:115-187); returns (rmse, ndcg, hr).
+
+    Tie order of the per-user top-10: descending value, later index first (SURVEY.md H7).
+    """
+    assert top_k == kn._lib.URE_TOP_K
+    vals, size = base_test_device(dataloader, models)
+    rmse, ndcg, hr = base_test_values(kn.download_many([vals])[0], size)
     if verbose == 2:
         print(f'Test - RMSE: {rmse:>.4f}, NDCG: {ndcg:>.3f}, HR: {hr:>.3f}')
     return rmse, ndcg, hr

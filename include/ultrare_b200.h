@@ -334,7 +334,7 @@ int ure_merge_user_rows(const float* const* d_P, const int32_t* d_owner, const i
 /* Squared-euclidean cost matrix of ot_cluster (method/utils.py:637), transposed to
  * [n, kpad] row major: M[i,j] = ||x_i||^2 + ||c_j||^2 - 2 x_i.c_j, the contraction on
  * tcgen05 (kind::tf32, 3-term hi/lo split = fp32-accurate).  Columns j >= k are
- * filled with +inf.  d multiple of 8, d <= 128; kpad multiple of 16, <= 256.
+ * filled with +inf.  d multiple of 8, d <= 128; kpad = 8 or a multiple of 16, <= 256.
  * d_inertia (may be NULL): += sum_i min_j M[i,j] (utils.py:638). */
 int ure_cost_matrix(const float* d_X, int64_t n, int d, const float* d_C, int k, int kpad,
                     float* d_M, double* d_inertia, void* stream);

@@ -395,6 +395,14 @@ def test_sisa_full_size_ml1m_unlearn_properties(cuda_dev):
     s2.epoch_eval = 'none'
     after = s2.unlearn(before, loaders(trd, True), test_dl, test_data, del_user, 0, '')
     assert s2.retrain_gid == set(osisa.route_deletions(groups, del_user)) == {1, 3}
+    # both routing paths (host look-ups for a small deletion set, the owner-map kernel for a large one) give the
+    # same flags, with out-of-range and unowned ids ignored
+    s3 = Sisa(P, 'mf', K, groups)
+    odd = list(del_user) + [-5, 10 ** 9]
+    f_host = s3.route(odd).cpu().numpy()
+    s3.ROUTE_ON_HOST_MAX = 0
+    f_dev = s3.route([u for u in odd if 0 <= u < s3.n_user]).cpu().numpy()
+    assert np.array_equal(f_host, f_dev) and set(np.flatnonzero(f_host)) == {1, 3}
     P_after = after[0].user_mat.weight.data
     for g in range(K):
         Qg = after[g].item_mat.weight.data

@@ -397,16 +397,18 @@ __global__ void perm_inverse_kernel(const ure_mf_shard_t* shards, int epochs) {
 constexpr int kSchedThreads = 512;
 constexpr int kSchedWarps = kSchedThreads / 32;
 
-__host__ __device__ inline long long schedule_smem_bytes(int cap_slots, int spe_cap, bool cache_j) {
+__host__ __device__ inline long long schedule_smem_bytes(int cap_slots, int spe_cap, bool cache_j, int tab_cap = 0) {
   // record index of every slot [cap] int (optional) | step of every slot [cap] u16 | rank of every slot [cap] u16
-  // (short epochs only) | histogram [spe_cap + 1] int | per-warp bin counters [warps][64] int
+  // (short epochs only) | histogram [spe_cap + 1] int | per-warp bin counters [warps][64] int | 4 round-function
+  // tables [tab_cap] u16 (optional)
   return (cache_j ? 4ll : 0ll) * cap_slots + 2ll * cap_slots + (spe_cap <= 64 ? 2ll * cap_slots : 0ll) +
-         4ll * (spe_cap + 1) + 4ll * kSchedWarps * 64 + 16;
+         4ll * (spe_cap + 1) + 4ll * kSchedWarps * 64 + 16 + 8ll * tab_cap;
 }
+constexpr int kTabMaxHalf = 8192;         // round tables: a, b <= this (n <= 6.7e7)
 
 __global__ void __launch_bounds__(kSchedThreads, 2)
 owner_schedule_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams_t hp, int epochs,
-                      long long step0) {
+                      long long step0, int tab_cap) {
   constexpr int NW = kSchedWarps;
   constexpr unsigned FULL = 0xffffffffu;
   extern __shared__ __align__(16) unsigned char dyn[];
@@ -428,6 +430,11 @@ owner_schedule_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_h
   unsigned short* const s_rank = s_stepof + cap;                           // [cap] rank inside (warp, step)
   int* const s_hist = reinterpret_cast<int*>(s_rank + (short_ok ? cap : 0));   // [spe_cap + 1]
   int* const s_wh = s_hist + spe_cap + 1;                                  // [NW][64]
+  // tab_cap > 0: a Feistel round adds f_r(other half) to one half, and the halves live in [0, a) / [0, b) with
+  // a, b ~ sqrt(n): the four round functions of an epoch are TABLES (2 (a + b) u16, built by the CTA per epoch), so
+  // a round of the inverse network is one shared-memory load, a compare and an add instead of two multiplies, a
+  // shift, an xor and a mulhi
+  unsigned short* const s_tab = reinterpret_cast<unsigned short*>(s_wh + NW * 64 + 4);     // 4 x [tab_cap]
   const int4* const recU = reinterpret_cast<const int4*>(sh.inter_u + s_pl.su0);
   const int4* const recI = reinterpret_cast<const int4*>(sh.inter_i + s_pl.si0) - mU;
   if (cache_j)
@@ -448,6 +455,19 @@ owner_schedule_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_h
     ks.init(perm_key(sh.perm_seed, (uint32_t)sh.shard_id, (uint32_t)epoch));
     const int32_t* pinv = sh.perm_inv ? sh.perm_inv + (long long)epoch * n : nullptr;
     constexpr int NI = 4;
+    const bool tabbed = tab_cap > 0 && !pinv && n > 1;
+    if (tabbed) {
+      __syncthreads();                     // the previous row is done with the tables
+      for (int x = tid; x < (int)dom.b; x += kSchedThreads) {
+        s_tab[x] = (unsigned short)mulhi32(round_hash((uint32_t)x ^ ks.rk[0]), dom.a);
+        s_tab[2 * tab_cap + x] = (unsigned short)mulhi32(round_hash((uint32_t)x ^ ks.rk[2]), dom.a);
+      }
+      for (int x = tid; x < (int)dom.a; x += kSchedThreads) {
+        s_tab[tab_cap + x] = (unsigned short)mulhi32(round_hash((uint32_t)x ^ ks.rk[1]), dom.b);
+        s_tab[3 * tab_cap + x] = (unsigned short)mulhi32(round_hash((uint32_t)x ^ ks.rk[3]), dom.b);
+      }
+      // (the __syncthreads that every path below starts with publishes the tables)
+    }
     // step of NI x 32 consecutive slots of this warp's range (lane = slot inside a 32-block)
     auto steps_of = [&](int base, uint32_t (&q)[NI], bool (&live)[NI]) {
       uint32_t x[NI];
@@ -461,6 +481,35 @@ owner_schedule_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_h
 #pragma unroll
         for (int u = 0; u < NI; ++u)
           if (live[u]) x[u] = (uint32_t)__ldg(pinv + x[u]);
+      } else if (tabbed) {
+        const unsigned short* const T0 = s_tab, *const T1 = s_tab + tab_cap, *const T2 = s_tab + 2 * tab_cap,
+                                    *const T3 = s_tab + 3 * tab_cap;
+        bool pend[NI];
+#pragma unroll
+        for (int u = 0; u < NI; ++u) pend[u] = live[u];
+        bool any = true;
+        while (any) {                      // cycle walking: almost never a second trip
+          uint32_t L[NI], R[NI];
+#pragma unroll
+          for (int u = 0; u < NI; ++u) dom.split(x[u], L[u], R[u]);
+#pragma unroll
+          for (int u = 0; u < NI; ++u) { const uint32_t f = T3[L[u]]; R[u] = R[u] >= f ? R[u] - f : R[u] + dom.b - f; }
+#pragma unroll
+          for (int u = 0; u < NI; ++u) { const uint32_t f = T2[R[u]]; L[u] = L[u] >= f ? L[u] - f : L[u] + dom.a - f; }
+#pragma unroll
+          for (int u = 0; u < NI; ++u) { const uint32_t f = T1[L[u]]; R[u] = R[u] >= f ? R[u] - f : R[u] + dom.b - f; }
+#pragma unroll
+          for (int u = 0; u < NI; ++u) { const uint32_t f = T0[R[u]]; L[u] = L[u] >= f ? L[u] - f : L[u] + dom.a - f; }
+          any = false;
+#pragma unroll
+          for (int u = 0; u < NI; ++u) {
+            if (pend[u]) {
+              x[u] = L[u] * dom.b + R[u];
+              pend[u] = x[u] >= dom.n;
+              any |= pend[u];
+            }
+          }
+        }
       } else {
         feistel_inverse_n<NI>(dom, ks, x, live);
       }
@@ -611,181 +660,6 @@ owner_schedule_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_h
         __syncwarp();
       }
       __syncthreads();
-    }
-  }
-}
-
-// ---------------------------------------------------------------- the schedule pre-pass, short epochs
-// The common case (ml1m K=5: 6-7 steps per epoch): at most 32 steps per epoch and a visiting-order domain whose
-// round-function tables fit shared memory.  Same output as owner_schedule_kernel, a third of its instructions:
-//   * a Feistel round adds f_r(other half) to one half, and the halves live in [0, a) / [0, b) with a, b ~ sqrt(n):
-//     the four round functions of an epoch are TABLES of a or b entries (2 (a + b) u16 per epoch, built by the CTA),
-//     so a round of the inverse network is one shared-memory load, a compare and an add;
-//   * the stable counting sort by step keeps one counter per step in the LANES of a warp: for every 32 slots and
-//     every step one ballot + popc (no match.any, no shared-memory counters, no stored ranks); the second pass
-//     recomputes the ranks the same way from the steps kept as bytes.
-constexpr int kFastMaxSpe = 32;
-constexpr int kFastMaxHalf = 8192;        // a, b <= this (n <= 6.7e7)
-
-__host__ __device__ inline long long schedule_fast_smem_bytes(int cap_slots, int tab_cap, bool cache_j) {
-  // record index of every slot [cap] int (optional) | step of every slot [cap] u8 | 4 round tables [tab_cap] u16
-  // each | per-warp step counters [warps][32] int
-  return (cache_j ? 4ll : 0ll) * cap_slots + (long long)((cap_slots + 15) / 16 * 16) + 8ll * tab_cap +
-         4ll * kSchedWarps * 32 + 16;
-}
-
-__global__ void __launch_bounds__(kSchedThreads, 2)
-owner_schedule_fast_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams_t hp, int epochs,
-                           long long step0, int tab_cap) {
-  constexpr int NW = kSchedWarps;
-  constexpr unsigned FULL = 0xffffffffu;
-  extern __shared__ __align__(16) unsigned char dyn[];
-  __shared__ PlanScratch s_ps;
-  __shared__ Plan s_pl;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  make_plan(shards, K, blockIdx.x, gridDim.x, s_pl, s_ps);
-  const ure_mf_shard_t& sh = shards[s_pl.shard];
-  const int mU = s_pl.mU, m = mU + s_pl.mI;
-  const int B = hp.batch, n = sh.n;
-  const int spe = (n + B - 1) / B;
-  if (spe == 0) return;
-  const int cap = hp.owner_cap_slots, spe_cap = hp.owner_spe_cap;
-  const bool cache_j = (hp.owner_flags & 2) == 0;
-  int* const s_j = reinterpret_cast<int*>(dyn);                                   // [cap] record index of the slot
-  unsigned char* const s_q = reinterpret_cast<unsigned char*>(s_j + (cache_j ? cap : 0));   // [cap] step of the slot
-  unsigned short* const s_tab = reinterpret_cast<unsigned short*>(s_q + (cap + 15) / 16 * 16);   // 4 x [tab_cap]
-  int* const s_wc = reinterpret_cast<int*>(s_tab + 4 * tab_cap);                  // [NW][32]
-  const int4* const recU = reinterpret_cast<const int4*>(sh.inter_u + s_pl.su0);
-  const int4* const recI = reinterpret_cast<const int4*>(sh.inter_i + s_pl.si0) - mU;
-  if (cache_j)
-    for (int sl = tid; sl < m; sl += kSchedThreads) s_j[sl] = __ldg(&((sl >= mU ? recI : recU) + sl)->w);
-  FeistelDomain dom;
-  dom.init((uint32_t)n);
-  const uint32_t magic = (uint32_t)(0x100000000ull / (uint32_t)B);         // floor(2^32/B): quotient low by <= 1
-  const int per = (m + NW - 1) / NW;                                       // every warp owns a contiguous range
-  const int w0 = min(warp * per, m), w1 = min(w0 + per, m);
-  const unsigned lt = (1u << lane) - 1u;
-  const unsigned short* const T0 = s_tab;                 // round 0 (even): index R in [0,b) -> offset of L in [0,a)
-  const unsigned short* const T1 = s_tab + tab_cap;       // round 1 (odd):  index L in [0,a) -> offset of R in [0,b)
-  const unsigned short* const T2 = s_tab + 2 * tab_cap;
-  const unsigned short* const T3 = s_tab + 3 * tab_cap;
-
-  for (int r = blockIdx.y; r < hp.owner_sched_rows; r += gridDim.y) {
-    const int epoch = (int)(step0 / spe) + r;
-    if (epoch >= epochs) break;
-    unsigned short* const out = hp.owner_sched + (long long)r * hp.owner_sched_stride + s_pl.slot_base;
-    int* const off = hp.owner_sched_off + ((long long)r * gridDim.x + blockIdx.x) * (spe_cap + 1);
-    const int32_t* pinv = sh.perm_inv ? sh.perm_inv + (long long)epoch * n : nullptr;
-    __syncthreads();                       // s_j complete; the previous row's passes are done with s_tab / s_q / s_wc
-    if (!pinv && n > 1) {
-      FeistelKeys ks;
-      ks.init(perm_key(sh.perm_seed, (uint32_t)sh.shard_id, (uint32_t)epoch));
-      for (int x = tid; x < (int)dom.b; x += kSchedThreads) {
-        s_tab[x] = (unsigned short)mulhi32(round_hash((uint32_t)x ^ ks.rk[0]), dom.a);
-        s_tab[2 * tab_cap + x] = (unsigned short)mulhi32(round_hash((uint32_t)x ^ ks.rk[2]), dom.a);
-      }
-      for (int x = tid; x < (int)dom.a; x += kSchedThreads) {
-        s_tab[tab_cap + x] = (unsigned short)mulhi32(round_hash((uint32_t)x ^ ks.rk[1]), dom.b);
-        s_tab[3 * tab_cap + x] = (unsigned short)mulhi32(round_hash((uint32_t)x ^ ks.rk[3]), dom.b);
-      }
-    }
-    __syncthreads();
-    // ---- pass 1: step of every slot (kept as a byte), the warp's count per step in lane `step`
-    constexpr int NI = 4;
-    int cnt = 0;
-    for (int base = w0; base < w1; base += 32 * NI) {
-      uint32_t x[NI];
-      bool live[NI];
-#pragma unroll
-      for (int u = 0; u < NI; ++u) {
-        const int sl = base + 32 * u + lane;
-        live[u] = sl < w1;
-        x[u] = !live[u] ? 0u : cache_j ? (uint32_t)s_j[sl] : (uint32_t)__ldg(&((sl >= mU ? recI : recU) + sl)->w);
-      }
-      if (pinv) {
-#pragma unroll
-        for (int u = 0; u < NI; ++u)
-          if (live[u]) x[u] = (uint32_t)__ldg(pinv + x[u]);
-      } else if (n > 1) {
-        bool pend[NI];
-#pragma unroll
-        for (int u = 0; u < NI; ++u) pend[u] = live[u];
-        bool any = true;
-        while (any) {                      // cycle walking: almost never a second trip
-          uint32_t L[NI], R[NI];
-#pragma unroll
-          for (int u = 0; u < NI; ++u) dom.split(x[u], L[u], R[u]);
-#pragma unroll
-          for (int u = 0; u < NI; ++u) { const uint32_t f = T3[L[u]]; R[u] = R[u] >= f ? R[u] - f : R[u] + dom.b - f; }
-#pragma unroll
-          for (int u = 0; u < NI; ++u) { const uint32_t f = T2[R[u]]; L[u] = L[u] >= f ? L[u] - f : L[u] + dom.a - f; }
-#pragma unroll
-          for (int u = 0; u < NI; ++u) { const uint32_t f = T1[L[u]]; R[u] = R[u] >= f ? R[u] - f : R[u] + dom.b - f; }
-#pragma unroll
-          for (int u = 0; u < NI; ++u) { const uint32_t f = T0[R[u]]; L[u] = L[u] >= f ? L[u] - f : L[u] + dom.a - f; }
-          any = false;
-#pragma unroll
-          for (int u = 0; u < NI; ++u) {
-            if (pend[u]) {
-              x[u] = L[u] * dom.b + R[u];
-              pend[u] = x[u] >= dom.n;
-              any |= pend[u];
-            }
-          }
-        }
-      } else {
-#pragma unroll
-        for (int u = 0; u < NI; ++u) x[u] = 0;
-      }
-#pragma unroll
-      for (int u = 0; u < NI; ++u) {
-        uint32_t q = B == 1 ? x[u] : mulhi32(x[u], magic);
-        if ((q + 1) * (uint32_t)B <= x[u]) ++q;
-        if (live[u]) s_q[base + 32 * u + lane] = (unsigned char)q;
-        const int qq = live[u] ? (int)q : -1;
-        for (int k = 0; k < spe; ++k) {
-          const unsigned mask = __ballot_sync(FULL, qq == k);
-          if (lane == k) cnt += __popc(mask);
-        }
-      }
-    }
-    s_wc[warp * 32 + lane] = cnt;
-    __syncthreads();
-    // ---- step totals -> starts of the steps' runs -> every warp's first position in every run
-    if (warp == 0) {
-      int tot = 0;
-      for (int w = 0; w < NW; ++w) tot += s_wc[w * 32 + lane];
-      int inc = tot;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int a2 = __shfl_up_sync(FULL, inc, o);
-        if (lane >= o) inc += a2;
-      }
-      int run = inc - tot;
-      if (lane <= spe) off[lane] = lane < spe ? run : m;
-      if (lane == 31 && spe == 32) off[32] = m;
-      for (int w = 0; w < NW; ++w) {
-        const int t = s_wc[w * 32 + lane];
-        s_wc[w * 32 + lane] = run;
-        run += t;
-      }
-    }
-    __syncthreads();
-    // ---- pass 2: stable scatter; lane `step` carries the warp's cursor of that step
-    int cur = s_wc[warp * 32 + lane];
-    for (int base = w0; base < w1; base += 32) {
-      const int sl = base + lane;
-      const int qq = sl < w1 ? (int)s_q[sl] : -1;
-      unsigned mine = 0;
-      int add = 0;
-      for (int k = 0; k < spe; ++k) {
-        const unsigned mask = __ballot_sync(FULL, qq == k);
-        if (qq == k) mine = mask;
-        if (lane == k) add = __popc(mask);
-      }
-      const int first = __shfl_sync(FULL, cur, qq & 31);
-      if (qq >= 0) out[first + __popc(mine & lt)] = (unsigned short)sl;
-      cur += add;
     }
   }
 }
@@ -1331,26 +1205,20 @@ extern "C" int ure_mf_owner_schedule(const ure_mf_shard_t* d_shards, int n_shard
   hp.owner_sched_step0 = step0;
   const int ny = h_hp->owner_sched_rows < 4 ? h_hp->owner_sched_rows : 4;    // 2 blocks per SM, 2 rounds
   const bool cache_j = (h_hp->owner_flags & 2) == 0;
-  // short epochs + a visiting-order domain whose round tables fit shared memory: the table-driven kernel
-  if (h_hp->owner_spe_cap <= kFastMaxSpe && h_hp->owner_max_n > 0) {
+  // round-function tables of the visiting order when they fit next to the rest (a, b ~ sqrt(n) entries each)
+  int tab_cap = 0;
+  if (h_hp->owner_max_n > 1) {
     FeistelDomain dom;
-    dom.init((uint32_t)h_hp->owner_max_n);             // a, b grow with n: the largest shard sizes the tables
-    const int tab_cap = (int)((dom.a > dom.b ? dom.a : dom.b) + 2 + 7) / 8 * 8;
-    const long long need_f = schedule_fast_smem_bytes(h_hp->owner_cap_slots, tab_cap, cache_j);
-    if (tab_cap <= kFastMaxHalf && need_f <= avail) {
-      URE_CUDA(cudaFuncSetAttribute(owner_schedule_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need_f));
-      owner_schedule_fast_kernel<<<dim3(num_sms(), ny), kSchedThreads, (size_t)need_f, static_cast<cudaStream_t>(stream)>>>(
-          d_shards, n_shards, hp, epochs, step0, tab_cap);
-      URE_CUDA(cudaGetLastError());
-      return 0;
-    }
+    dom.init((uint32_t)h_hp->owner_max_n);             // a >= b and a grows with n: the largest shard sizes the tables
+    const int cap = (int)((dom.a > dom.b ? dom.a : dom.b) + 2 + 7) / 8 * 8;
+    if (cap <= kTabMaxHalf && schedule_smem_bytes(h_hp->owner_cap_slots, h_hp->owner_spe_cap, cache_j, cap) <= avail) tab_cap = cap;
   }
-  const long long need = schedule_smem_bytes(h_hp->owner_cap_slots, h_hp->owner_spe_cap, cache_j);
+  const long long need = schedule_smem_bytes(h_hp->owner_cap_slots, h_hp->owner_spe_cap, cache_j, tab_cap);
   URE_REQUIRE(need <= avail, URE_EUNSUPPORTED, "ure_mf_owner_schedule: %lld bytes of shared memory needed, %d available",
               need, avail);
   URE_CUDA(cudaFuncSetAttribute(owner_schedule_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
   owner_schedule_kernel<<<dim3(num_sms(), ny), kSchedThreads, (size_t)need, static_cast<cudaStream_t>(stream)>>>(
-      d_shards, n_shards, hp, epochs, step0);
+      d_shards, n_shards, hp, epochs, step0, tab_cap);
   URE_CUDA(cudaGetLastError());
   return 0;
 }

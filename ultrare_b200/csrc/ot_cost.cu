@@ -99,6 +99,12 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
          ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
 }
+// K-major SWIZZLE_128B descriptor (layout type 2 in bits [61,64)): rows of 128 bytes, 8-row groups 1024 bytes apart
+// (SBO); the 16-byte chunk index of an address is XORed with its row-in-group by the hardware, as the TMA engine does
+// when it writes the tile with CU_TENSOR_MAP_SWIZZLE_128B.  LBO is unused for a K extent inside one swizzle atom.
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
 // cute::UMMA::InstrDescriptor for kind::tf32, fp32 accumulate, both operands K-major, M = 128
 __device__ __forceinline__ uint32_t make_idesc_tf32(int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileRows >> 4) << 24);
@@ -260,7 +266,8 @@ cost_tc_kernel(const float* __restrict__ X, long long n, const float* __restrict
         }
         float4* dst = reinterpret_cast<float4*>(M + row * kpad + col0 + c0);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) dst[q] = make_float4(out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]);
+        for (int q = 0; q < 4; ++q)            // kpad == 8: the 16-column accumulator block is stored as 32-byte rows
+          if (4 * q < kpad) dst[q] = make_float4(out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]);
       }
     }
     if (inertia && row < n && rmin < INFINITY) atomicMin(&rowmin[trow], __float_as_int(fmaxf(rmin, 0.f)));
@@ -302,7 +309,7 @@ struct CostSmemLayout2 {
 __host__ __device__ inline CostSmemLayout2 cost_layout2(int D, int NB, int stages) {
   CostSmemLayout2 L;
   const uint32_t chunks = D / 4;
-  L.lbo_a = kTileRows * 16;                   // a TMA box lands as 128 contiguous 16-byte rows
+  L.lbo_a = kTileRows * 16;                   // (no swizzle) a TMA box lands as 128 contiguous 16-byte rows
   L.lbo_b = NB * 16 + (chunks >= 8 ? 16 : 32);
   uint32_t o = 0;
   L.stages = stages;
@@ -321,12 +328,17 @@ __host__ __device__ inline CostSmemLayout2 cost_layout2(int D, int NB, int stage
   return L;
 }
 
-template <int D>
+// SW: the tile is loaded as D/32 boxes of {32 floats = 128 bytes, 128 rows} with the 128-byte swizzle (one wide box
+// per 16 KB instead of eight 16-byte-wide ones: the TMA engine moves whole 128-byte rows) and the A descriptors say
+// SWIZZLE_128B; lo is written at the SAME offsets as the raw tile, so the pass needs no index arithmetic at all.
+template <int D, bool SW>
 __global__ void __launch_bounds__(kCostThreads)
 cost_tma_kernel(const __grid_constant__ CUtensorMap tmap, long long n, const float* __restrict__ C, int k, int kpad, int NB,
-                int stages, uint32_t tmem_cols, float* __restrict__ M, double* __restrict__ inertia) {
+                int stages, uint32_t tmem_cols, float* __restrict__ M, double* __restrict__ inertia, int nacc) {
   constexpr int CH = D / 4;                    // 16-byte K chunks per row
-  extern __shared__ __align__(128) unsigned char sm[];
+  extern __shared__ __align__(128) unsigned char sm_raw[];
+  // the swizzle atoms want 1024-byte aligned tiles: the launch asks for 1 KB more than the layout
+  unsigned char* const sm = sm_raw + ((1024u - (smem_u32(sm_raw) & 1023u)) & 1023u);
   const CostSmemLayout2 L = cost_layout2(D, NB, stages);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   uint64_t* full = reinterpret_cast<uint64_t*>(sm + L.bars);
@@ -374,8 +386,13 @@ cost_tma_kernel(const __grid_constant__ CUtensorMap tmap, long long n, const flo
   auto issue_load = [&](long long tile, int stage) {          // CH boxes of {4 floats, 128 rows}: rows past n are zeros
     mbar_expect_tx(&full[stage], L.stage_bytes);
     unsigned char* dst = sm + L.hi_off + (size_t)stage * L.stage_bytes;
+    if (SW) {
+#pragma unroll
+      for (int a = 0; a < D / 32; ++a) tma_load_2d(dst + a * (kTileRows * 128), &tmap, 32 * a, (int)(tile * kTileRows), &full[stage]);
+    } else {
 #pragma unroll 4
-    for (int c = 0; c < CH; ++c) tma_load_2d(dst + c * L.lbo_a, &tmap, 4 * c, (int)(tile * kTileRows), &full[stage]);
+      for (int c = 0; c < CH; ++c) tma_load_2d(dst + c * L.lbo_a, &tmap, 4 * c, (int)(tile * kTileRows), &full[stage]);
+    }
   };
 
   long long tile = blockIdx.x;
@@ -391,7 +408,20 @@ cost_tma_kernel(const __grid_constant__ CUtensorMap tmap, long long n, const flo
     // ---- lo = x - trunc(x) in the same layout, row norms; threads walk rows (16 contiguous bytes each)
     const unsigned char* hi = sm + L.hi_off + (size_t)stage * L.stage_bytes;
     if (tid < kTileRows) rowmin[tid] = 0x7f800000;          // +inf
-    {
+    if (SW) {
+      // linear walk over the tile's 16-byte chunks: 8 consecutive chunks are one 128-byte row of one K atom
+#pragma unroll 4
+      for (int x = tid; x < kTileRows * CH; x += kCostThreads) {
+        const float4 v = *reinterpret_cast<const float4*>(hi + x * 16);
+        const float4 lo = make_float4(v.x - tf32_hi(v.x), v.y - tf32_hi(v.y), v.z - tf32_hi(v.z), v.w - tf32_hi(v.w));
+        *reinterpret_cast<float4*>(sm + L.lo_off + x * 16) = lo;
+        float s = (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        if ((tid & 7) == 0) atomicAdd(&xnorm[(x >> 3) & (kTileRows - 1)], s);
+      }
+    } else {
       const int r = tid & (kTileRows - 1), cg = tid / kTileRows;
       float s = 0.f;
 #pragma unroll 4
@@ -411,13 +441,17 @@ cost_tma_kernel(const __grid_constant__ CUtensorMap tmap, long long n, const flo
       const uint32_t a_hi_addr = smem_u32(hi);
 #pragma unroll
       for (int kk = 0; kk < D / 8; ++kk) {
-        const uint64_t ah = make_desc(a_hi_addr + kk * 2 * L.lbo_a, L.lbo_a, 128);
-        const uint64_t al = make_desc(a_lo_addr + kk * 2 * L.lbo_a, L.lbo_a, 128);
+        // SW: K atom kk / 4 (16 KB each), 32 bytes further inside the atom per instruction
+        const uint32_t a_off = SW ? (uint32_t)((kk >> 2) * (kTileRows * 128) + (kk & 3) * 32) : (uint32_t)(kk * 2 * L.lbo_a);
+        const uint64_t ah = SW ? make_desc_sw128(a_hi_addr + a_off) : make_desc(a_hi_addr + a_off, L.lbo_a, 128);
+        const uint64_t al = SW ? make_desc_sw128(a_lo_addr + a_off) : make_desc(a_lo_addr + a_off, L.lbo_a, 128);
         const uint64_t bh = make_desc(b_hi_addr + kk * 2 * L.lbo_b, L.lbo_b, 128);
         const uint64_t bl = make_desc(b_lo_addr + kk * 2 * L.lbo_b, L.lbo_b, 128);
+        // nacc == 3: hi*hi, hi*lo and lo*hi accumulate in three TMEM column blocks -- three independent chains of
+        // D/8 instructions instead of one chain of 3*D/8 whose every link waits for the previous accumulator update
         umma_tf32(tmem_base, ah, bh, idesc, kk > 0);       // the tensor core truncates the raw tile to tf32 itself
-        umma_tf32(tmem_base, ah, bl, idesc, 1);
-        umma_tf32(tmem_base, al, bh, idesc, 1);
+        umma_tf32(tmem_base + (nacc == 3 ? NB : 0), ah, bl, idesc, nacc == 3 ? kk > 0 : 1);
+        umma_tf32(tmem_base + (nacc == 3 ? 2 * NB : 0), al, bh, idesc, nacc == 3 ? kk > 0 : 1);
       }
       umma_commit(mma_bar);       // implies tcgen05.fence::before_thread_sync
     }
@@ -434,6 +468,15 @@ cost_tma_kernel(const __grid_constant__ CUtensorMap tmap, long long n, const flo
     for (int c0 = cg * 16; c0 < NB; c0 += 16 * (kCostThreads / 128)) {
       float acc[16];
       tmem_ld16(tmem_base + ((uint32_t)(rq * 32) << 16) + (uint32_t)c0, acc);
+      if (nacc == 3) {
+        float a2[16];
+        tmem_ld16(tmem_base + ((uint32_t)(rq * 32) << 16) + (uint32_t)(NB + c0), a2);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] += a2[j];
+        tmem_ld16(tmem_base + ((uint32_t)(rq * 32) << 16) + (uint32_t)(2 * NB + c0), a2);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] += a2[j];
+      }
       if (row < n) {
         float out[16];
 #pragma unroll
@@ -443,7 +486,8 @@ cost_tma_kernel(const __grid_constant__ CUtensorMap tmap, long long n, const flo
         }
         float4* dst = reinterpret_cast<float4*>(M + row * kpad + col0 + c0);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) dst[q] = make_float4(out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]);
+        for (int q = 0; q < 4; ++q)            // kpad == 8: the 16-column accumulator block is stored as 32-byte rows
+          if (4 * q < kpad) dst[q] = make_float4(out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]);
       }
     }
     if (inertia && row < n && rmin < INFINITY) atomicMin(&rowmin[trow], __float_as_int(fmaxf(rmin, 0.f)));
@@ -488,28 +532,40 @@ int launch_cost_tma(const float* X, long long n, const float* C, int k, int kpad
   EncodeTiledFn enc = encode_tiled();
   if (force_v1 || !enc || D < 8 || (reinterpret_cast<uintptr_t>(X) & 15) != 0 || n >= (1ll << 31)) return 0;
   // column block and stages: prefer a footprint that lets two CTAs share an SM
-  int NB = kpad > 128 ? 128 : kpad, stages = 2;
-  while (kpad % NB) NB -= 16;
-  if (cost_layout2(D, NB, 2).total > 110 * 1024 && cost_layout2(D, NB, 1).total <= 110 * 1024) stages = 1;
-  if (cost_layout2(D, NB, stages).total > 220 * 1024) stages = 1;
-  if (cost_layout2(D, NB, stages).total > 220 * 1024) return 0;
-  const int col_blocks = kpad / NB;
+  const int kcols = kpad < 16 ? 16 : kpad;      // kpad == 8: a 16-column MMA block, 8 columns stored
+  int NB = kcols > 128 ? 128 : kcols, stages = 2;
+  while (kcols % NB) NB -= 16;
+  if (cost_layout2(D, NB, 2).total > 109 * 1024 && cost_layout2(D, NB, 1).total <= 109 * 1024) stages = 1;
+  if (cost_layout2(D, NB, stages).total > 219 * 1024) stages = 1;
+  if (cost_layout2(D, NB, stages).total > 219 * 1024) return 0;
+  const int col_blocks = kcols / NB;
+  static const int one_acc = getenv("URE_COST_1ACC") ? atoi(getenv("URE_COST_1ACC")) : 0;
+  const int nacc = (!one_acc && 3 * NB <= 256) ? 3 : 1;      // two CTAs per SM share the 512 TMEM columns
   uint32_t tmem_cols = 32;
-  while ((int)tmem_cols < NB) tmem_cols <<= 1;
+  while ((int)tmem_cols < nacc * NB) tmem_cols <<= 1;
+  static const int no_sw = getenv("URE_COST_NOSW") ? atoi(getenv("URE_COST_NOSW")) : 0;
+  constexpr bool kCanSw = D >= 32;             // a 128-byte swizzle atom is 32 floats of K
+  const bool sw = kCanSw && !no_sw;
   CUtensorMap tmap;
   const cuuint64_t dims[2] = {(cuuint64_t)D, (cuuint64_t)n};
   const cuuint64_t strides[1] = {(cuuint64_t)D * 4};
-  const cuuint32_t box[2] = {4, (cuuint32_t)kTileRows};
+  const cuuint32_t box[2] = {sw ? 32u : 4u, (cuuint32_t)kTileRows};
   const cuuint32_t estr[2] = {1, 1};
   if (enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(X), dims, strides, box, estr,
-          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+          CU_TENSOR_MAP_INTERLEAVE_NONE, sw ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return 0;
   const CostSmemLayout2 L = cost_layout2(D, NB, stages);
-  auto kern = cost_tma_kernel<D>;
-  URE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+  void (*kern)(const CUtensorMap, long long, const float*, int, int, int, int, uint32_t, float*, double*, int) =
+      cost_tma_kernel<D, false>;
+  if constexpr (kCanSw) {
+    if (sw) kern = cost_tma_kernel<D, true>;
+  }
+  const size_t smem = (size_t)L.total + 1024;
+  URE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  URE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   int occ = 0;
-  URE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kCostThreads, L.total));
+  URE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kCostThreads, smem));
   if (occ < 1) return 0;
   const int max_by_tmem = 512 / (int)tmem_cols;
   if (occ > max_by_tmem) occ = max_by_tmem;
@@ -520,8 +576,8 @@ int launch_cost_tma(const float* X, long long n, const float* C, int k, int kpad
   if (gx < 1) gx = 1;
   if (gx > n_tiles) gx = n_tiles;
   double* fused_inertia = (col_blocks == 1) ? inertia : nullptr;
-  kern<<<dim3((unsigned)gx, (unsigned)col_blocks), kCostThreads, L.total, st>>>(tmap, n, C, k, kpad, NB, stages, tmem_cols, M,
-                                                                            fused_inertia);
+  kern<<<dim3((unsigned)gx, (unsigned)col_blocks), kCostThreads, smem, st>>>(tmap, n, C, k, kpad, NB, stages, tmem_cols, M,
+                                                                         fused_inertia, nacc);
   URE_CUDA(cudaGetLastError());
   if (inertia && !fused_inertia) *used = 2;
   return 0;
@@ -580,7 +636,8 @@ int launch_cost_tc(const float* X, long long n, const float* C, int k, int kpad,
   // work); URE_COST_STAGES=1|2 pins the choice (experiments)
   static const int want_stages = getenv("URE_COST_STAGES") ? atoi(getenv("URE_COST_STAGES")) : 0;
   const uint32_t budget = want_stages == 1 ? 110 * 1024 : 220 * 1024;
-  int NB = kpad, stages = want_stages == 1 ? 1 : 2;
+  const int kcols = kpad < 16 ? 16 : kpad;      // kpad == 8: a 16-column MMA block, 8 columns stored
+  int NB = kcols, stages = want_stages == 1 ? 1 : 2;
   while (true) {
     if (cost_layout(D, NB, stages).total <= budget) break;
     if (stages == 2 && cost_layout(D, NB, 1).total <= budget) { stages = 1; break; }
@@ -589,8 +646,8 @@ int launch_cost_tc(const float* X, long long n, const float* C, int k, int kpad,
     NB = ((NB / 2 + 15) / 16) * 16;
     stages = want_stages == 1 ? 1 : 2;
   }
-  const int col_blocks = (kpad + NB - 1) / NB;
-  URE_REQUIRE(col_blocks * NB == kpad, URE_EUNSUPPORTED, "ure_cost_matrix: kpad=%d not divisible into %d-column blocks",
+  const int col_blocks = (kcols + NB - 1) / NB;
+  URE_REQUIRE(col_blocks * NB == kcols, URE_EUNSUPPORTED, "ure_cost_matrix: kpad=%d not divisible into %d-column blocks",
               kpad, NB);
   uint32_t tmem_cols = 32;
   while ((int)tmem_cols < NB) tmem_cols <<= 1;
@@ -618,8 +675,8 @@ int launch_cost_tc(const float* X, long long n, const float* C, int k, int kpad,
 
 int check_cost_args(const float* X, long long n, int d, const float* C, int k, int kpad, float* M, const char* who) {
   URE_REQUIRE(X && C && M, URE_EINVAL, "%s: null argument", who);
-  URE_REQUIRE(n > 0 && k >= 1 && k <= kpad && kpad % 16 == 0 && kpad <= 256, URE_EINVAL,
-              "%s: bad shape n=%lld k=%d kpad=%d (kpad multiple of 16, <= 256)", who, n, k, kpad);
+  URE_REQUIRE(n > 0 && k >= 1 && k <= kpad && (kpad == 8 || kpad % 16 == 0) && kpad <= 256, URE_EINVAL,
+              "%s: bad shape n=%lld k=%d kpad=%d (kpad 8 or a multiple of 16, <= 256)", who, n, k, kpad);
   URE_REQUIRE(d >= 1, URE_EINVAL, "%s: d=%d", who, d);
   return 0;
 }

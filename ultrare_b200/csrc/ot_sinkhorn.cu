@@ -787,13 +787,14 @@ assign_centroid_reg_kernel(const float* __restrict__ M, long long n, int k, int 
 
 #define URE_KPAD_SWITCH(kpad, CALL)                    \
   switch (kpad) {                                      \
+    case 8: { constexpr int KP = 8; CALL; } break;     \
     case 16: { constexpr int KP = 16; CALL; } break;   \
     case 32: { constexpr int KP = 32; CALL; } break;   \
     case 64: { constexpr int KP = 64; CALL; } break;   \
     case 128: { constexpr int KP = 128; CALL; } break; \
     case 256: { constexpr int KP = 256; CALL; } break; \
     default:                                           \
-      set_error("kpad=%d not in {16,32,64,128,256}", kpad); \
+      set_error("kpad=%d not in {8,16,32,64,128,256}", kpad); \
       return URE_EUNSUPPORTED;                         \
   }
 
@@ -826,16 +827,25 @@ extern "C" int ure_sinkhorn_colsum(const float* d_M, int64_t n, int k, int kpad,
   URE_REQUIRE(d_g && d_colsum && eps > 0.f && n_total >= 1.0, URE_EINVAL, "ure_sinkhorn_colsum: bad argument");
   const float scale = kLog2e / eps;
   const double a = 1.0 / n_total;
-  long long blocks = (n + 2047) / 2048;
-  const long long cap = (long long)num_sms() * 4;
-  if (blocks > cap) blocks = cap;
   auto st = static_cast<cudaStream_t>(stream);
-  if (k <= 8) {
+  // grid = one full wave of resident CTAs (a second, partly filled wave costs as much as a full one: 489 CTAs on
+  // 444 slots ran at half speed), fewer only when there are not 512 rows per CTA
+  auto grid_for = [&](const void* kern) -> unsigned {
+    int occ = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kSkThreads, 0) != cudaSuccess || occ < 1) occ = 1;
+    long long blocks = (n + 511) / 512;
+    const long long cap = (long long)num_sms() * occ;
+    if (blocks > cap) blocks = cap;
+    return (unsigned)(blocks < 1 ? 1 : blocks);
+  };
+  if (k <= 8 && kpad != 8) {
     // only the first 8 columns hold centroids (the rest of the kpad-wide row is +inf padding): read that 32-byte
-    // slice of every row -- half the bytes and half the exponentials at kpad = 16
-    colsum_kernel<8><<<(unsigned)blocks, kSkThreads, 0, st>>>(d_M, n, k, d_g, scale, a, d_colsum, kpad);
+    // slice of every row -- half the exponentials at kpad = 16 (the bytes still come from DRAM in 64-byte pieces;
+    // kernels.kpad_for stores such matrices 8 wide to begin with)
+    colsum_kernel<8><<<grid_for((const void*)colsum_kernel<8>), kSkThreads, 0, st>>>(d_M, n, k, d_g, scale, a, d_colsum, kpad);
   } else {
-    URE_KPAD_SWITCH(kpad, (colsum_kernel<KP><<<(unsigned)blocks, kSkThreads, 0, st>>>(d_M, n, k, d_g, scale, a, d_colsum, kpad)));
+    URE_KPAD_SWITCH(kpad, (colsum_kernel<KP><<<grid_for((const void*)colsum_kernel<KP>), kSkThreads, 0, st>>>(
+                              d_M, n, k, d_g, scale, a, d_colsum, kpad)));
   }
   URE_CUDA(cudaGetLastError());
   return 0;
@@ -885,7 +895,7 @@ extern "C" int ure_sinkhorn(const float* d_M, int64_t n, int k, int kpad, float*
   if (kpad == KP)                                                                                                 \
     return ks == 8 ? launch_sinkhorn_cluster<KP, 8>(d_M, n, k, d_g, stg, ws, kClusterMax, need_c, st)             \
                    : launch_sinkhorn_cluster<KP, KP>(d_M, n, k, d_g, stg, ws, kClusterMax, need_c, st);
-      URE_CLUSTER_CASE(16) URE_CLUSTER_CASE(32) URE_CLUSTER_CASE(64)
+      URE_CLUSTER_CASE(8) URE_CLUSTER_CASE(16) URE_CLUSTER_CASE(32) URE_CLUSTER_CASE(64)
 #undef URE_CLUSTER_CASE
     }
   }
@@ -930,21 +940,24 @@ extern "C" int ure_sinkhorn_peer(const float* d_M, int64_t n_local, double n_tot
   auto st = static_cast<cudaStream_t>(stream);
   auto* ws = static_cast<SkWorkspace*>(d_workspace);
   URE_CUDA(cudaMemsetAsync(ws, 0, sizeof(SkWorkspace), st));
-  long long grid = (n_local + 2047) / 2048;
-  if (grid > num_sms()) grid = num_sms();
-  if (grid < 1) grid = 1;
   long long nn = n_local;
   unsigned long long base = call_base;
   int stride = kpad;
   void* args[] = {(void*)&d_M, (void*)&nn, (void*)&n_total, (void*)&k, (void*)&d_g, (void*)&stg, (void*)&ws,
                   (void*)&peers, (void*)&rank, (void*)&world, (void*)&base, (void*)&stride};
-  if (k <= 8) {                            // the 8-column slice of every row, as in ure_sinkhorn_colsum
-    URE_CUDA(cudaLaunchCooperativeKernel((void*)sinkhorn_peer_kernel<8>, dim3((unsigned)grid), dim3(kSkThreads), args, 0, st));
+  // every CTA the GPU can keep resident (cooperative launch), fewer only when there are not 512 rows per CTA
+  auto launch = [&](const void* kern) -> int {
+    int occ = 1;
+    URE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kSkThreads, 0));
+    URE_REQUIRE(occ >= 1, URE_ECOOP, "sinkhorn_peer_kernel cannot be resident");
+    long long grid = (n_local + 511) / 512;
+    if (grid > (long long)num_sms() * occ) grid = (long long)num_sms() * occ;
+    if (grid < 1) grid = 1;
+    URE_CUDA(cudaLaunchCooperativeKernel(kern, dim3((unsigned)grid), dim3(kSkThreads), args, 0, st));
     return 0;
-  }
-  URE_KPAD_SWITCH(kpad, {
-    URE_CUDA(cudaLaunchCooperativeKernel((void*)sinkhorn_peer_kernel<KP>, dim3((unsigned)grid), dim3(kSkThreads), args, 0, st));
-  });
+  };
+  if (k <= 8 && kpad != 8) return launch((const void*)sinkhorn_peer_kernel<8>);     // the 8-column slice of every row
+  URE_KPAD_SWITCH(kpad, return launch((const void*)sinkhorn_peer_kernel<KP>));
   return 0;
 }
 

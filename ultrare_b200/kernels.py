@@ -1005,7 +1005,9 @@ def merge_user_rows(P_list, owner, merged, row_of=None, retrain=None, zero_unown
 
 # ------------------------------------------------------------------------------ OT grouping
 def kpad_for(k: int) -> int:
-    for kp in (16, 32, 64, 128, 256):
+    """Columns a row of the cost matrix is stored with: 8 (32-byte rows: k <= 8 centroids are the common grouping,
+    and a 64-byte row would be fetched from DRAM whole even if only half of it were read), else 16 .. 256."""
+    for kp in (8, 16, 32, 64, 128, 256):
         if k <= kp:
             return kp
     raise ValueError("k > 256 centroids is not supported")

@@ -483,9 +483,22 @@ class Sisa(Scratch):
         self._join_writers()
         return self.model_list
 
-    def route(self, del_user):
-        """retrain flags of sisa.py:76-81, by the owner-map kernel (int32 [n_group] on device)."""
-        d = kn.upload_array(np.asarray(list(del_user), dtype=np.int32), self.device)
+    ROUTE_ON_HOST_MAX = 1 << 14     # deletion sets up to this size are routed from the host copy of the owner map
+
+    def route(self, del_user, defer_upload=False):
+        """retrain flags of sisa.py:76-81 (int32 [n_group] on the device): flags[owner[u]] = 1 for every deleted u.
+        Large deletion sets go through the owner-map kernel (ure_route_deletions); a small one is a few hundred
+        look-ups in the host copy of the same owner map -- no device round trip before the shards can be set up
+        (defer_upload: not even the upload of the flags; the caller sends them when the merge needs them)."""
+        ids = np.asarray(list(del_user), dtype=np.int64)
+        if len(ids) <= self.ROUTE_ON_HOST_MAX:
+            own = self._owner_np[ids[(ids >= 0) & (ids < self.n_user)]]
+            flags_h = np.zeros(self.n_group, dtype=np.int32)
+            flags_h[own[own >= 0]] = 1
+            self._route_flags_host = flags_h
+            return None if defer_upload else kn.upload_array(flags_h, self.device)
+        self._route_flags_host = None
+        d = kn.upload_array(ids.astype(np.int32), self.device)
         return kn.route_deletions(self._owner, d, self.n_group)
 
     def unlearn(self, model_list, train_dlist, test_dlist, test_data, del_user, verbose, save_dir):
@@ -496,8 +509,9 @@ class Sisa(Scratch):
 
         self._test_dlist = test_dlist
         t_begin = time.perf_counter()
-        flags = self.route(del_user)
-        self.retrain_gid = set(int(s) for s in np.flatnonzero(kn.download_many([flags])[0]))   # pinned read-back
+        flags = self.route(del_user, defer_upload=True)
+        flags_h = self._route_flags_host if self._route_flags_host is not None else kn.download_many([flags])[0]
+        self.retrain_gid = set(int(s) for s in np.flatnonzero(flags_h))
         self.timing['route_ms'] = (time.perf_counter() - t_begin) * 1e3
         order = sorted(self.retrain_gid)
         model_before_unlearn = self.model_list[0]                               # sisa.py:84
@@ -514,6 +528,8 @@ class Sisa(Scratch):
         new, unmerged, last_idx, compact = self._train_shards(order, train_dlist, test_dlist, test_data, verbose, prior,
                                                               defer_logs=len(save_dir) == 0)
         t_m = time.perf_counter()
+        if flags is None:                              # routed on the host: the flags go up while the GPU trains
+            flags = kn.upload_array(self._route_flags_host, self.device)
         merged = self._merged_from(base, unmerged, compact, flags)
         self._finish(new, unmerged, last_idx, compact, merged, test_dlist, save_dir)
         for i, m in new.items():
@@ -524,8 +540,8 @@ class Sisa(Scratch):
         t_t = time.perf_counter()
         self.test(test_data, verbose, save_dir)
         self.timing['merge_ms'] = (t_t - t_m) * 1e3
-        # kernels of ours outside the training batch: route, merge (twice when sharded over GPUs), score, ranking
-        self.timing['own_launches_outside_batch'] = 1 + (2 if self.dist.world > 1 else 1) + 2
+        # kernels of ours outside the training batch: route (large deletion sets only), merge, score, ranking
+        self.timing['own_launches_outside_batch'] = (0 if self._route_flags_host is not None else 1) + 1 + 2
         self._flush_logs()
         self._join_writers()
         self.timing['test_ms'] = (time.perf_counter() - t_t) * 1e3

@@ -583,6 +583,260 @@ int launch_cost_tma(const float* X, long long n, const float* C, int k, int kpad
   return 0;
 }
 
+// ------------------------------------------------------------------ v4: warp-specialised pipeline (d >= 32, kpad <= 64)
+// ncu of the kernels above (profiles/r2_notes.md): a CTA walks  TMA wait -> lo pass -> MMAs -> commit wait -> epilogue
+// strictly one after the other -- 28 % of the stall samples sit on the MMA-completion mbarrier alone (with N = 16 every
+// instruction re-reads a 4 KB A slab from shared memory for 16 columns of output), the rest on the TMA and the
+// barriers in between.  Here every stage has its own warps and the stages of consecutive tiles overlap:
+//   warp 0      TMA producer: S raw tiles in flight (128-byte-swizzled boxes, the raw tile IS the hi operand);
+//   warps 1-8   lo = x - trunc(x) into one of two lo tiles, row norms (8 slots deep);
+//   warp 9      MMA issuer: D1 [128 x 2NB] += A_hi x [B_hi ; B_lo]^T  (hi*hi and hi*lo in ONE instruction: the A slab
+//               is read once for both), D2 [128 x NB] += A_lo x B_hi^T; two accumulator stages in TMEM; three
+//               tcgen05.commit release the raw tile, the lo tile and publish the accumulators;
+//   warps 10-13 epilogue: tcgen05.ld of D1[:, :NB] + D1[:, NB:] + D2, norms, rows of M, inertia.
+constexpr int kWsThreads = 14 * 32;
+constexpr int kWsLoWarps = 8;
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+struct CostWsLayout {
+  uint32_t hi_off, tile_bytes, S, lo_off, LS, b_off, lbo_b, xnorm, cnorm, bars, holder, total;
+};
+__host__ __device__ inline CostWsLayout cost_ws_layout(int D, int NB) {
+  CostWsLayout L;
+  const uint32_t chunks = D / 4;
+  L.tile_bytes = kTileRows * D * 4;
+  L.S = D >= 128 ? 2 : 4;
+  L.LS = D >= 128 ? 1 : 2;
+  L.lbo_b = 2 * NB * 16 + (chunks >= 8 ? 16 : 32);      // [B_hi ; B_lo]: 2 NB rows per 16-byte K chunk
+  uint32_t o = 0;
+  L.hi_off = o; o += L.tile_bytes * L.S;
+  L.lo_off = o; o += L.tile_bytes * L.LS;
+  L.b_off = o; o += L.lbo_b * chunks;
+  L.xnorm = o; o += 8 * kTileRows * 4;
+  L.cnorm = o; o += NB * 4;
+  o = (o + 7) / 8 * 8;
+  L.bars = o; o += 16 * 8;                               // full[4] empty[4] lo_full[2] lo_empty[2] t_full[2] t_empty[2]
+  L.holder = o; o += 16;
+  L.total = o;
+  return L;
+}
+
+template <int D>
+__global__ void __launch_bounds__(kWsThreads, 1)
+cost_ws_kernel(const __grid_constant__ CUtensorMap tmap, long long n, const float* __restrict__ C, int k, int kpad, int NB,
+               uint32_t tmem_cols, float* __restrict__ M, double* __restrict__ inertia) {
+  constexpr int CH = D / 4;
+  extern __shared__ __align__(128) unsigned char sm_raw[];
+  unsigned char* const sm = sm_raw + ((1024u - (smem_u32(sm_raw) & 1023u)) & 1023u);
+  const CostWsLayout L = cost_ws_layout(D, NB);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint64_t* const full = reinterpret_cast<uint64_t*>(sm + L.bars);
+  uint64_t* const empty = full + 4;
+  uint64_t* const lo_full = full + 8;
+  uint64_t* const lo_empty = full + 10;
+  uint64_t* const t_full = full + 12;
+  uint64_t* const t_empty = full + 14;
+  uint32_t* const holder = reinterpret_cast<uint32_t*>(sm + L.holder);
+  float* const xnorm = reinterpret_cast<float*>(sm + L.xnorm);        // [8][128]
+  float* const cnorm = reinterpret_cast<float*>(sm + L.cnorm);
+  const int S = (int)L.S, LS = (int)L.LS;
+
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&lo_full[i], kWsLoWarps * 32); mbar_init(&lo_empty[i], 1);
+      mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 128);
+    }
+    fence_mbar_init();
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+  }
+  if (warp == 0) tmem_alloc(holder, tmem_cols);
+  // ---- centroids -> [B_hi ; B_lo] (K-major core-matrix layout, no swizzle) + ||c||^2
+  for (int idx = tid; idx < NB * CH; idx += kWsThreads) {
+    const int j = idx / CH, c = idx % CH;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (j < k) v = __ldg(reinterpret_cast<const float4*>(C + (size_t)j * D) + c);
+    const float4 hi = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+    const float4 lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
+    *reinterpret_cast<float4*>(sm + L.b_off + c * L.lbo_b + j * 16) = hi;
+    *reinterpret_cast<float4*>(sm + L.b_off + c * L.lbo_b + (NB + j) * 16) = lo;
+    float s = (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+#pragma unroll
+    for (int o = CH / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o, CH);
+    if (c == 0) cnorm[j] = j < k ? s : INFINITY;
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *holder;
+  const long long n_tiles = (n + kTileRows - 1) / kTileRows;
+  const int my_tiles = blockIdx.x < n_tiles ? (int)((n_tiles - 1 - blockIdx.x) / gridDim.x) + 1 : 0;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0)
+      for (int it = 0; it < my_tiles; ++it) {
+        const int s = it % S;
+        const long long tile = blockIdx.x + (long long)it * gridDim.x;
+        mbar_wait(&empty[s], (uint32_t)(((it / S) & 1) ^ 1));
+        mbar_expect_tx(&full[s], L.tile_bytes);
+        unsigned char* dst = sm + L.hi_off + (size_t)s * L.tile_bytes;
+#pragma unroll
+        for (int a = 0; a < D / 32; ++a) tma_load_2d(dst + a * (kTileRows * 128), &tmap, 32 * a, (int)(tile * kTileRows), &full[s]);
+      }
+  } else if (warp <= kWsLoWarps) {
+    // ------------------------------------------------------------ lo pass + row norms
+    // Thread = (row, half of the row's eight 16-byte positions in every 128-byte atom row): the norm of a row is a
+    // private sum + ONE shuffle (no shared-memory atomics: a float atomicAdd there is a compare-and-swap loop), and
+    // lo lands at the address its hi came from, so the swizzle never has to be undone.  Position j of the four is
+    // rotated by the row number: the 8 threads of a quarter-warp (4 rows x 2 halves) hit 8 different bank groups.
+    const int lt = tid - 32;                                    // 0 .. 255
+    const int lrow = lt >> 1, lhalf = lt & 1;
+    uint32_t pos[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) pos[j] = (uint32_t)(lrow * 128 + (lhalf * 4 + ((j + lrow) & 3)) * 16);
+    for (int it = 0; it < my_tiles; ++it) {
+      const int s = it % S, ls = it % LS;
+      mbar_wait(&full[s], (uint32_t)((it / S) & 1));
+      mbar_wait(&lo_empty[ls], (uint32_t)(((it / LS) & 1) ^ 1));
+      const unsigned char* hi = sm + L.hi_off + (size_t)s * L.tile_bytes;
+      unsigned char* lo = sm + L.lo_off + (size_t)ls * L.tile_bytes;
+      float4 v[D / 32][4];
+#pragma unroll
+      for (int a = 0; a < D / 32; ++a)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[a][j] = *reinterpret_cast<const float4*>(hi + a * (kTileRows * 128) + pos[j]);
+      float q0 = 0.f, q1 = 0.f;
+#pragma unroll
+      for (int a = 0; a < D / 32; ++a)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 x = v[a][j];
+          *reinterpret_cast<float4*>(lo + a * (kTileRows * 128) + pos[j]) =
+              make_float4(x.x - tf32_hi(x.x), x.y - tf32_hi(x.y), x.z - tf32_hi(x.z), x.w - tf32_hi(x.w));
+          q0 = fmaf(x.x, x.x, fmaf(x.y, x.y, q0));
+          q1 = fmaf(x.z, x.z, fmaf(x.w, x.w, q1));
+        }
+      float q = q0 + q1;
+      q += __shfl_xor_sync(0xffffffffu, q, 1);
+      if (lhalf == 0) xnorm[(it & 7) * kTileRows + lrow] = q;   // slot read by the epilogue, reused eight tiles later
+      fence_proxy_async();                                      // lo is read by the tensor core (async proxy)
+      mbar_arrive(&lo_full[ls]);
+    }
+  } else if (warp == kWsLoWarps + 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc2 = make_idesc_tf32(2 * NB), idesc1 = make_idesc_tf32(NB);
+      const uint32_t b_addr = smem_u32(sm + L.b_off);
+      for (int it = 0; it < my_tiles; ++it) {
+        const int s = it % S, ls = it % LS, a = it & 1;
+        mbar_wait(&lo_full[ls], (uint32_t)((it / LS) & 1));
+        mbar_wait(&t_empty[a], (uint32_t)(((it >> 1) & 1) ^ 1));
+        tc_fence_after();
+        const uint32_t hi_addr = smem_u32(sm + L.hi_off + (size_t)s * L.tile_bytes);
+        const uint32_t lo_addr = smem_u32(sm + L.lo_off + (size_t)ls * L.tile_bytes);
+        const uint32_t d1 = tmem_base + (uint32_t)(a * 3 * NB), d2 = d1 + (uint32_t)(2 * NB);
+#pragma unroll
+        for (int kk = 0; kk < D / 8; ++kk) {
+          const uint32_t a_off = (uint32_t)((kk >> 2) * (kTileRows * 128) + (kk & 3) * 32);
+          const uint64_t bdesc = make_desc(b_addr + kk * 2 * L.lbo_b, L.lbo_b, 128);
+          umma_tf32(d1, make_desc_sw128(hi_addr + a_off), bdesc, idesc2, kk > 0);     // hi*hi | hi*lo
+          umma_tf32(d2, make_desc_sw128(lo_addr + a_off), bdesc, idesc1, kk > 0);     // lo*hi (first NB rows of B)
+        }
+        umma_commit(&empty[s]);             // the raw tile may be overwritten by the producer
+        umma_commit(&lo_empty[ls]);         // ... the lo tile by the lo warps
+        umma_commit(&t_full[a]);            // ... and the accumulators are complete
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue: one TMEM lane = one row per thread
+    const int rq = warp & 3;
+    const int trow = rq * 32 + lane;
+    double inertia_acc = 0.0;
+    for (int it = 0; it < my_tiles; ++it) {
+      const int a = it & 1;
+      const long long tile = blockIdx.x + (long long)it * gridDim.x;
+      const long long row = tile * kTileRows + trow;
+      mbar_wait(&t_full[a], (uint32_t)((it >> 1) & 1));
+      tc_fence_after();
+      float* xn = xnorm + (it & 7) * kTileRows;
+      const float xnr = xn[trow];
+      const uint32_t d1 = tmem_base + ((uint32_t)(rq * 32) << 16) + (uint32_t)(a * 3 * NB);
+      float rmin = INFINITY;
+      for (int c0 = 0; c0 < NB; c0 += 16) {
+        float acc[16], t2[16];
+        tmem_ld16(d1 + (uint32_t)c0, acc);
+        tmem_ld16(d1 + (uint32_t)(NB + c0), t2);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] += t2[j];
+        tmem_ld16(d1 + (uint32_t)(2 * NB + c0), t2);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] += t2[j];
+        if (row < n) {
+          float out[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            out[j] = fmaf(-2.f, acc[j], xnr + cnorm[c0 + j]);
+            rmin = fminf(rmin, out[j]);
+          }
+          float4* dst = reinterpret_cast<float4*>(M + row * kpad + c0);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (c0 + 4 * q < kpad) dst[q] = make_float4(out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&t_empty[a]);
+      if (inertia && row < n && rmin < INFINITY) inertia_acc += (double)fmaxf(rmin, 0.f);
+    }
+    if (inertia) {
+      inertia_acc = warp_sum(inertia_acc);
+      if (lane == 0 && inertia_acc != 0.0) atomicAdd(inertia, inertia_acc);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// *used = 1 when the pipeline kernel ran
+template <int D>
+int launch_cost_ws(const float* X, long long n, const float* C, int k, int kpad, float* M, double* inertia, cudaStream_t st,
+                   int* used) {
+  *used = 0;
+  static const int off = getenv("URE_COST_WS") ? !atoi(getenv("URE_COST_WS")) : 0;
+  EncodeTiledFn enc = encode_tiled();
+  const int NB = kpad < 16 ? 16 : kpad;
+  if (off || !enc || D < 32 || NB > 64 || (reinterpret_cast<uintptr_t>(X) & 15) != 0 || n >= (1ll << 31)) return 0;
+  const CostWsLayout L = cost_ws_layout(D, NB);
+  const size_t smem = (size_t)L.total + 1024;
+  if (smem > 226 * 1024) return 0;
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < 6 * NB) tmem_cols <<= 1;            // two accumulator stages of [D1 (2 NB) | D2 (NB)]
+  CUtensorMap tmap;
+  const cuuint64_t dims[2] = {(cuuint64_t)D, (cuuint64_t)n};
+  const cuuint64_t strides[1] = {(cuuint64_t)D * 4};
+  const cuuint32_t box[2] = {32u, (cuuint32_t)kTileRows};
+  const cuuint32_t estr[2] = {1, 1};
+  if (enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(X), dims, strides, box, estr,
+          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return 0;
+  auto kern = cost_ws_kernel<D>;
+  URE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long n_tiles = (n + kTileRows - 1) / kTileRows;
+  long long gx = num_sms();
+  if (gx > n_tiles) gx = n_tiles;
+  *used = 1;
+  kern<<<dim3((unsigned)gx), kWsThreads, smem, st>>>(tmap, n, C, k, kpad, NB, tmem_cols, M, inertia);
+  URE_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // ------------------------------------------------------------------ CUDA-core check kernel
 // Direct fp32 sum_t (x-c)^2 (the reference expression): one thread per (row, column).
 __global__ void cost_simt_kernel(const float* __restrict__ X, long long n, int d, const float* __restrict__ C, int k,
@@ -625,6 +879,11 @@ int launch_rowmin(const float* M, long long n, int k, int kpad, double* inertia,
 template <int D>
 int launch_cost_tc(const float* X, long long n, const float* C, int k, int kpad, float* M, double* inertia,
                    cudaStream_t st) {
+  if constexpr (D >= 32) {
+    int used = 0;
+    if (int rc = launch_cost_ws<D>(X, n, C, k, kpad, M, inertia, st, &used)) return rc;
+    if (used) return 0;
+  }
   {
     int used = 0;
     if (int rc = launch_cost_tma<D>(X, n, C, k, kpad, M, inertia, st, &used)) return rc;

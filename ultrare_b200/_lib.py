@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libultrare_b200.so")
+LIB_PATH = os.environ.get("URE_LIB") or os.path.join(HERE, "libultrare_b200.so")   # URE_LIB: experiment builds (tools/)
 
 URE_MAX_SHARDS = 256
 URE_TOP_K = 10

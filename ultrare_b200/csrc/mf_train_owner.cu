@@ -664,6 +664,211 @@ owner_schedule_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_h
   }
 }
 
+// ---------------------------------------------------------------- the schedule pre-pass, short epochs (the usual case)
+// Same output as owner_schedule_kernel for epochs of at most 64 steps, at half its instruction count and shared memory
+// (two CTAs per SM instead of one; ncu of the general kernel: 136 warp-instructions per 32 slots and epoch, one CTA
+// per SM because of 117 KB of shared memory, issue slots 45 % busy):
+//   * the (L, R) halves of a slot's record index -- what every epoch's inverse network starts from -- are split once
+//     per launch and kept as one packed word per slot, in doubled units so that a half IS the byte offset into a
+//     16-bit round table;
+//   * NT of the four rounds of the inverse network read a per-epoch table (one LDS of random lanes: ~3.5 bank
+//     wavefronts), the others evaluate the round function (6 ALU instructions): the mix keeps the shared-memory
+//     pipe and the issue slots equally busy;
+//   * cycle walking (x >= n, one slot in ~400) is a rare divergent loop instead of a second trip of the whole group;
+//   * step and rank of a slot share one 16-bit word; the per-(step, warp) counts are scanned by the whole CTA.
+// Lists are identical to the general kernel's (same stable order), so either serves the training kernel.
+__host__ __device__ inline long long schedule_tab_smem_bytes(int cap_slots, int tab_cap, int n_tab) {
+  // packed halves / record index [cap] u32 | step + rank [cap] u16 | counters [warps][64] int | scan scratch |
+  // round tables 2 sets x n_tab x [tab_cap] u16
+  return 4ll * cap_slots + 2ll * cap_slots + 4ll * kSchedWarps * 64 + 4ll * (kSchedWarps + 4) + 2ll * 2 * n_tab * tab_cap + 64;
+}
+
+template <int NT>
+__global__ void __launch_bounds__(kSchedThreads, 2)
+owner_schedule_tab_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams_t hp, int epochs,
+                          long long step0, int tab_cap, int sb) {
+  constexpr int NW = kSchedWarps;
+  constexpr unsigned FULL = 0xffffffffu;
+  constexpr int NI = 4;
+  extern __shared__ __align__(16) unsigned char dyn[];
+  __shared__ PlanScratch s_ps;
+  __shared__ Plan s_pl;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  make_plan(shards, K, blockIdx.x, gridDim.x, s_pl, s_ps);
+  const ure_mf_shard_t& sh = shards[s_pl.shard];
+  const int mU = s_pl.mU, m = mU + s_pl.mI;
+  const int B = hp.batch, n = sh.n;
+  const int spe = (n + B - 1) / B;
+  if (spe == 0) return;
+  const int cap = hp.owner_cap_slots, spe_cap = hp.owner_spe_cap;
+  uint32_t* const s_lr = reinterpret_cast<uint32_t*>(dyn);                       // [cap]
+  unsigned short* const s_sr = reinterpret_cast<unsigned short*>(s_lr + cap);    // [cap] step | rank << sb
+  int* const s_wh = reinterpret_cast<int*>(s_sr + cap);                          // [NW][64]
+  int* const s_wtot = s_wh + NW * 64;                                            // [NW + 4]
+  unsigned char* const s_tab = reinterpret_cast<unsigned char*>(s_wtot + NW + 4);   // NT x [tab_cap] u16
+  const uint32_t tab_bytes = 2u * (uint32_t)tab_cap;
+  const int4* const recU = reinterpret_cast<const int4*>(sh.inter_u + s_pl.su0);
+  const int4* const recI = reinterpret_cast<const int4*>(sh.inter_i + s_pl.si0) - mU;
+  FeistelDomain dom;
+  dom.init((uint32_t)n);
+  const bool explicit_order = sh.perm_inv != nullptr;
+  const bool trivial = n <= 1;
+  for (int sl = tid; sl < m; sl += kSchedThreads) {
+    const uint32_t j = (uint32_t)__ldg(&((sl >= mU ? recI : recU) + sl)->w);
+    uint32_t L, R;
+    dom.split(j, L, R);
+    s_lr[sl] = explicit_order || trivial ? j : (L << 17) | (R << 1);
+  }
+  const uint32_t B2 = 2u * (uint32_t)B;
+  const uint32_t magic2 = (uint32_t)(0x100000000ull / B2);                       // floor(2^32 / 2B): quotient low by <= 1
+  const uint32_t a2 = 2u * dom.a, b2 = 2u * dom.b, n2 = 2u * dom.n;
+  const int per = ((m + NW - 1) / NW + 31) & ~31;                                // whole 32-slot blocks per warp
+  const int w0 = min(warp * per, m), w1 = min(w0 + per, m);
+  const unsigned lt = (1u << lane) - 1u;
+  const uint32_t qmask = (1u << sb) - 1u;
+
+  // round tables of one epoch (rounds 3, 2 when NT >= 2; 1, 0 when NT == 4), doubled values, built by threads
+  // t0, t0 + nthr, ... of the CTA
+  auto build_tables = [&](int epoch, unsigned char* tab, int t0, int nthr) {
+    if (explicit_order || trivial || NT == 0 || t0 < 0) return;
+    FeistelKeys kt;
+    kt.init(perm_key(sh.perm_seed, (uint32_t)sh.shard_id, (uint32_t)epoch));
+    for (int x = t0; x < (int)dom.a; x += nthr) {
+      *reinterpret_cast<unsigned short*>(tab + 2 * x) = (unsigned short)(2u * mulhi32(round_hash((uint32_t)x ^ kt.rk[3]), dom.b));
+      if (NT >= 4)
+        *reinterpret_cast<unsigned short*>(tab + 2 * tab_bytes + 2 * x) = (unsigned short)(2u * mulhi32(round_hash((uint32_t)x ^ kt.rk[1]), dom.b));
+    }
+    for (int x = t0; x < (int)dom.b; x += nthr) {
+      *reinterpret_cast<unsigned short*>(tab + tab_bytes + 2 * x) = (unsigned short)(2u * mulhi32(round_hash((uint32_t)x ^ kt.rk[2]), dom.a));
+      if (NT >= 4)
+        *reinterpret_cast<unsigned short*>(tab + 3 * tab_bytes + 2 * x) = (unsigned short)(2u * mulhi32(round_hash((uint32_t)x ^ kt.rk[0]), dom.a));
+    }
+  };
+  const int e_first = (int)(step0 / spe);
+  if (blockIdx.y < hp.owner_sched_rows && e_first + (int)blockIdx.y < epochs) build_tables(e_first + blockIdx.y, s_tab, tid, kSchedThreads);
+  for (int x = tid; x < NW * 64; x += kSchedThreads) s_wh[x] = 0;
+  __syncthreads();
+
+  int it = 0;
+  for (int r = blockIdx.y; r < hp.owner_sched_rows; r += gridDim.y, ++it) {
+    const int epoch = e_first + r;
+    if (epoch >= epochs) break;
+    unsigned short* const out = hp.owner_sched + (long long)r * hp.owner_sched_stride + s_pl.slot_base;
+    int* const off = hp.owner_sched_off + ((long long)r * gridDim.x + blockIdx.x) * (spe_cap + 1);
+    FeistelKeys ks;
+    ks.init(perm_key(sh.perm_seed, (uint32_t)sh.shard_id, (uint32_t)epoch));
+    const int32_t* const pinv = explicit_order ? sh.perm_inv + (long long)epoch * n : nullptr;
+    const unsigned char* const tabs = s_tab + (it & 1) * NT * tab_bytes;        // tables alternate between two sets
+    // one round of the inverse network in doubled units: h -= 2 f(o) (mod m2)
+    auto round_tab = [&](uint32_t& h, uint32_t o2, uint32_t t, uint32_t m2) {
+      const uint32_t f = *reinterpret_cast<const unsigned short*>(tabs + t * tab_bytes + o2);
+      const uint32_t d = h - f;
+      h = min(d, d + m2);                  // unsigned: the wrapped difference is the larger one
+    };
+    auto round_alu = [&](uint32_t& h, uint32_t o2, uint32_t key, uint32_t mod, uint32_t m2) {
+      const uint32_t f = mulhi32(round_hash((o2 >> 1) ^ key), mod);
+      const uint32_t d = h - 2u * f;
+      h = min(d, d + m2);
+    };
+    auto inverse2 = [&](uint32_t Ls, uint32_t Rs) {       // -> 2 x position
+      if (NT >= 2) { round_tab(Rs, Ls, 0, b2); round_tab(Ls, Rs, 1, a2); }
+      else { round_alu(Rs, Ls, ks.rk[3], dom.b, b2); round_alu(Ls, Rs, ks.rk[2], dom.a, a2); }
+      if (NT >= 4) { round_tab(Rs, Ls, 2, b2); round_tab(Ls, Rs, 3, a2); }
+      else { round_alu(Rs, Ls, ks.rk[1], dom.b, b2); round_alu(Ls, Rs, ks.rk[0], dom.a, a2); }
+      return (Ls >> 1) * b2 + Rs;
+    };
+    // ---- pass 1: step of every slot; rank among the warp's slots of the same step, in slot order.  No CTA barrier
+    // since the previous row's pass 2: a warp touches its own range of s_sr and its own counters only
+    for (int base = w0; base < w1; base += 32 * NI) {
+      uint32_t x2[NI];
+      bool live[NI];
+#pragma unroll
+      for (int u = 0; u < NI; ++u) {
+        const int sl = base + 32 * u + lane;
+        live[u] = sl < w1;
+        x2[u] = live[u] ? s_lr[sl] : 0u;
+      }
+      if (explicit_order) {
+#pragma unroll
+        for (int u = 0; u < NI; ++u) x2[u] = live[u] ? 2u * (uint32_t)__ldg(pinv + x2[u]) : 0u;
+      } else if (trivial) {
+#pragma unroll
+        for (int u = 0; u < NI; ++u) x2[u] = 0u;
+      } else {
+#pragma unroll
+        for (int u = 0; u < NI; ++u) x2[u] = inverse2(x2[u] >> 16, x2[u] & 0xffffu);
+#pragma unroll
+        for (int u = 0; u < NI; ++u)
+          while (x2[u] >= n2) {            // cycle walking: rare, lanes on their own
+            uint32_t L, R;
+            dom.split(x2[u] >> 1, L, R);
+            x2[u] = inverse2(2u * L, 2u * R);
+          }
+      }
+#pragma unroll
+      for (int u = 0; u < NI; ++u) {
+        uint32_t q = mulhi32(x2[u], magic2);
+        if ((q + 1u) * B2 <= x2[u]) ++q;
+        const uint32_t key = live[u] ? q : 0xffffffffu;          // dead lanes form their own group and write nothing
+        const unsigned same = __match_any_sync(FULL, key);
+        const unsigned below = __popc(same & lt);
+        int old = 0;
+        if (live[u]) {
+          old = s_wh[warp * 64 + q];                              // the warp's own counters
+          s_sr[base + 32 * u + lane] = (unsigned short)(q | ((uint32_t)(old + below) << sb));
+        }
+        __syncwarp();
+        if (live[u] && below == 0) s_wh[warp * 64 + q] = old + __popc(same);
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    // ---- warp 0: exclusive scan of the counts in (step, warp) order (entry e = step * NW + warp, C per lane);
+    // the other warps build the next row's round tables meanwhile
+    if (warp == 0) {
+      const int T = spe * NW, C = (T + 31) / 32;
+      const int e0 = lane * C;
+      int sum = 0;
+      for (int c = 0; c < C; ++c) {
+        const int e = e0 + c;
+        if (e < T) sum += s_wh[(e % NW) * 64 + e / NW];
+      }
+      int inc = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(FULL, inc, o);
+        if (lane >= o) inc += t;
+      }
+      int run = inc - sum;
+      for (int c = 0; c < C; ++c) {
+        const int e = e0 + c;
+        if (e < T) {
+          int* const p = &s_wh[(e % NW) * 64 + e / NW];
+          const int v = *p;
+          *p = run;
+          if (e % NW == 0) off[e / NW] = run;
+          run += v;
+        }
+      }
+      if (lane == 0) off[spe] = m;
+    } else {
+      const int rn = r + gridDim.y;
+      if (rn < hp.owner_sched_rows && e_first + rn < epochs)
+        build_tables(e_first + rn, s_tab + ((it + 1) & 1) * NT * tab_bytes, tid - 32, kSchedThreads - 32);
+    }
+    __syncthreads();
+    // ---- pass 2: position = start of (step, warp) + rank; then the warp clears its counters for the next row
+    for (int sl = w0 + lane; sl < w1; sl += 32) {
+      const uint32_t pk = s_sr[sl];
+      out[s_wh[warp * 64 + (pk & qmask)] + (pk >> sb)] = (unsigned short)sl;
+    }
+    __syncwarp();
+    s_wh[warp * 64 + lane] = 0;
+    s_wh[warp * 64 + 32 + lane] = 0;
+    __syncwarp();
+  }
+}
+
 // ---------------------------------------------------------------- the training kernel
 // The loop below is issue-bound (ncu: ~50 % issue-slot utilisation, profiles/): launch-uniform array bases,
 // 32-bit shared-memory indexing, packed cache records and compile-time CACHED keep its instruction count down.
@@ -677,10 +882,16 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
   // lanes per interaction and chunks per lane: one chunk per lane up to d=32; wide rows give every lane V=4 chunks
   // (chunk gl + v*G: a load instruction of the group still covers G*16 contiguous bytes), which divides the
   // shuffle reductions and the per-interaction bookkeeping (the loop is issue-bound) by four.
-  constexpr int V = D >= 64 ? 4 : 1;
+#ifndef URE_OWNER_V16
+#define URE_OWNER_V16 1
+#endif
+#ifndef URE_OWNER_QB16
+#define URE_OWNER_QB16 4
+#endif
+  constexpr int V = D >= 64 ? 4 : D == 16 ? URE_OWNER_V16 : 1;
   constexpr int G = CH / V;                // lanes per interaction
   constexpr int GPW = 32 / G;              // lane groups per warp
-  constexpr int QB = V == 4 ? 2 : 4;       // interactions a group handles per wave (QB*V gathers in flight per lane)
+  constexpr int QB = V == 4 ? 2 : D == 16 ? URE_OWNER_QB16 : 4;   // interactions a group handles per wave (QB*V gathers in flight per lane)
   constexpr int WAVE = GPW * QB;           // interactions per warp and wave
   constexpr int NW = kOwnWarps;
   constexpr int RS = 2 * D;                // row stride in floats: [w | momentum, pre-scaled: mu*buf + wd*w]
@@ -1212,6 +1423,24 @@ extern "C" int ure_mf_owner_schedule(const ure_mf_shard_t* d_shards, int n_shard
     dom.init((uint32_t)h_hp->owner_max_n);             // a >= b and a grows with n: the largest shard sizes the tables
     const int cap = (int)((dom.a > dom.b ? dom.a : dom.b) + 2 + 7) / 8 * 8;
     if (cap <= kTabMaxHalf && schedule_smem_bytes(h_hp->owner_cap_slots, h_hp->owner_spe_cap, cache_j, cap) <= avail) tab_cap = cap;
+  }
+  // short epochs with round tables: the tight kernel (two CTAs per SM)
+  {
+    static const int nt_env = getenv("URE_SCHED_NT") ? atoi(getenv("URE_SCHED_NT")) : 4;       // -1: general kernel (A/B)
+    int sb = 1;
+    while ((1 << sb) < h_hp->owner_spe_cap) ++sb;
+    const int per = (((h_hp->owner_cap_slots + kSchedWarps - 1) / kSchedWarps) + 31) & ~31;
+    const int nt = nt_env >= 4 ? 4 : nt_env >= 2 ? 2 : 0;
+    const long long need_t = schedule_tab_smem_bytes(h_hp->owner_cap_slots, tab_cap, nt);
+    if (nt_env >= 0 && tab_cap > 0 && h_hp->owner_spe_cap <= 64 && per < (1 << (16 - sb)) && need_t <= avail) {
+      auto kern = nt == 4 ? owner_schedule_tab_kernel<4> : nt == 2 ? owner_schedule_tab_kernel<2> : owner_schedule_tab_kernel<0>;
+      URE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need_t));
+      const int ny2 = h_hp->owner_sched_rows < 2 ? h_hp->owner_sched_rows : 2;     // 2 CTAs per SM: one wave
+      kern<<<dim3(num_sms(), ny2), kSchedThreads, (size_t)need_t, static_cast<cudaStream_t>(stream)>>>(
+          d_shards, n_shards, hp, epochs, step0, tab_cap, sb);
+      URE_CUDA(cudaGetLastError());
+      return 0;
+    }
   }
   const long long need = schedule_smem_bytes(h_hp->owner_cap_slots, h_hp->owner_spe_cap, cache_j, tab_cap);
   URE_REQUIRE(need <= avail, URE_EUNSUPPORTED, "ure_mf_owner_schedule: %lld bytes of shared memory needed, %d available",

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define URE_ABI_VERSION 4
+#define URE_ABI_VERSION 5
 #define URE_MAX_SHARDS 256        /* shard models batched in one launch           */
 #define URE_TOP_K 10              /* baseTest(top_k=10), method/utils.py:115      */
 
@@ -104,9 +104,15 @@ typedef struct {
   int32_t runs_rows;       /* RUNS: epochs per shard the step lists hold                                    */
   int32_t runs_spe_cap;    /* RUNS: max steps per epoch of a shard (< 1024)                                 */
   int64_t runs_step0;      /* RUNS: global step the list window starts at                                   */
+  void* owner_plan;        /* OWNER: NULL, or the DEVICE workspace of ure_mf_train.  When set, ure_mf_owner_schedule checks
+                            * ON THE DEVICE, CTA by CTA, that owner_cap_rows / owner_cap_slots / owner_spe_cap cover the
+                            * plan, and leaves error code 2 in the workspace (int32 at byte 16) if they do not; ure_mf_train
+                            * then trains nothing.  A caller may thus queue both launches with the capacities of an earlier
+                            * plan of the same shapes instead of waiting for this plan's read-back (and skip the plan
+                            * kernel: URE_BATCH_NO_PLAN), and repeats the pass with the exact plan when the code comes back */
 } ure_mf_hparams_t;
 
-/* RUNS schedule: per-shard state next to ure_mf_shard_t (which still carries inter_u / inter_i of
+/* RUNS schedule: per-shard state next to the ure_mf_shard_t entry, which still carries inter_u / inter_i of
  * ure_mf_owner_prepare and the public tables P / Q / bufP / bufQ that ure_mf_runs_init reads and
  * ure_mf_runs_flush writes). */
 typedef struct ure_mf_runs_s {
@@ -221,9 +227,11 @@ int ure_mf_batch_layout(const ure_mf_batch_shard_t* h_shards, int n_shards, int 
  * reused before the stream has passed this call), clears momentum / gradient scratch / losses / workspace / row
  * offsets, queues ure_mf_owner_prepare when lay->owner, and queues the copy of the plan (4 int32, see
  * ure_mf_owner_prepare) to h_stage + 176*K.  The weights (lay->W) are left to the caller. */
+#define URE_BATCH_NO_PLAN 1       /* flags: do not compute / copy the plan (the launch runs on remembered capacities,
+                                   * hparams.owner_plan set) */
 int ure_mf_batch_setup(const ure_mf_batch_shard_t* h_shards, int n_shards, int n_item, const ure_mf_hparams_t* h_hp,
                        int epochs, uint32_t perm_seed, void* d_arena, const ure_mf_batch_layout_t* lay, void* h_stage,
-                       void* stream);
+                       int flags, void* stream);
 
 /* After the stream has passed ure_mf_batch_setup: turn the plan into launch parameters (hp->mode = OWNER, owner_*
  * capacities, the shared-memory configuration -- record cache first, then staged lists -- and the schedule-table

@@ -469,3 +469,60 @@ def test_balanced_rounding_from_a_degenerate_assignment_is_still_the_exact_optim
     Mh = M.cpu().numpy()[:, :k]
     emd = oot.assign(oot.emd_lp(np.ones(n) / n, np.ones(k) / k, Mh))
     assert (label.cpu().numpy() == emd).mean() >= 0.998
+
+
+@pytest.mark.gpu
+def test_optimistic_owner_launch_hit_and_miss(cuda_dev):
+    """Sisa.unlearn without artefacts queues the owner launch with the capacities of the last plan of the same shapes
+    (kernels._PLAN_HINTS) instead of waiting for the plan read-back; the kernels verify them on the device
+    (hparams.owner_plan).  A hit reproduces the waited-for pass bit for bit; a remembered plan that does not cover
+    the batch trains nothing, raises PlanHintMiss when the deferred losses are read, and the pass is repeated."""
+    import pandas as pd
+    from ultrare_b200 import kernels as kn, synth
+    from ultrare_b200.method.sisa import Sisa
+    from ultrare_b200.read import RatingData, loadData, readRating
+    train, test = synth.ml_like()
+    U, I, K, E, B = 6040, 3416, 5, 2, 30000
+    tr = pd.DataFrame({0: train[0], 1: train[1], 2: train[2]})
+    te = pd.DataFrame({0: test[0], 1: test[1], 2: test[2]})
+    trr, groups = readRating(tr, U, 5, [], [], K, [], 'a')
+    ter, _ = readRating(te, U, 5, [], [], K, groups)
+    del_user = [int(g[0]) for g in groups]                                   # every shard retrains
+    trd, _ = readRating(tr, U, 5, del_user, [], K, groups, 'r')
+
+    class P:
+        n_user, n_item, k, lam, seed, lr, lr_decay, momentum, epochs, batch = U, I, 16, 0.1, 42, 0.001, 0.95, 0.9, E, B
+
+    mk = lambda arrs, sh: [loadData(RatingData(a), B, 1, sh) for a in arrs]
+    tdl = mk(ter, False)
+    tdata = loadData(RatingData(np.hstack(ter)), B, 1, False)
+
+    def new():
+        s = Sisa(P, 'mf', K, groups)
+        s.epoch_eval = 'none'
+        return s
+
+    models = new().learn(mk(trr, True), tdl, tdata, 0, '')
+    train_dl = mk(trd, True)
+    kn._PLAN_HINTS.clear()                                                   # (learn remembers its plan as well)
+
+    def run():
+        un = new()
+        out = un.unlearn(models, train_dl, tdl, tdata, del_user, 0, '')
+        return un, [m.item_mat.weight.data.clone() for m in out], out[0].user_mat.weight.data.clone()
+
+    un0, q0, p0 = run()                                                      # waits for its plan, remembers it
+    assert not un0._last_batch.optimistic and len(kn._PLAN_HINTS) >= 1
+    un1, q1, p1 = run()                                                      # queued on the remembered plan
+    assert un1._last_batch.optimistic and un1._last_batch.owner_plan['optimistic']
+    assert torch.equal(p0, p1) and all(torch.equal(a, b) for a, b in zip(q0, q1))
+    same_log = lambda a, b: all(abs(a[k] - b[k]) <= 1e-12 for k in a)           # metric sums: fp64 atomics, any order
+    assert same_log(un1.final_log, un0.final_log)
+    sig = un1._last_batch._plan_sig
+    good = kn._PLAN_HINTS[sig]
+    kn._PLAN_HINTS[sig] = (max(1, good[0] // 2), max(16, good[1] // 2), good[2], good[3])   # too small: must miss
+    un2, q2, p2 = run()
+    assert not un2._last_batch.optimistic                                    # the repeat waited for the real plan
+    assert kn._PLAN_HINTS[sig] == good
+    assert torch.equal(p0, p2) and all(torch.equal(a, b) for a, b in zip(q0, q2))
+    assert same_log(un2.final_log, un0.final_log)

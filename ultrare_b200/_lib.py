@@ -36,7 +36,7 @@ class MFHParams(C.Structure):
                 ("owner_spe_cap", _i32), ("owner_sched_rows", _i32), ("owner_sched", _p), ("owner_sched_off", _p),
                 ("owner_sched_step0", _i64), ("owner_sched_stride", _i64),
                 ("owner_cap_list", _i32), ("owner_max_n", _i32),
-                ("runs", _p), ("runs_rows", _i32), ("runs_spe_cap", _i32), ("runs_step0", _i64)]
+                ("runs", _p), ("runs_rows", _i32), ("runs_spe_cap", _i32), ("runs_step0", _i64), ("owner_plan", _p)]
 
 
 class MFRuns(C.Structure):
@@ -58,7 +58,7 @@ class MFBatchLayout(C.Structure):
 
 MF_DENSE, MF_LAZY, MF_OWNER, MF_RUNS = 0, 1, 2, 3
 
-assert C.sizeof(MFShard) == 176 and C.sizeof(MFHParams) == 128 and C.sizeof(MFRuns) == 64
+assert C.sizeof(MFShard) == 176 and C.sizeof(MFHParams) == 136 and C.sizeof(MFRuns) == 64
 assert C.sizeof(MFBatchShard) == 32 and C.sizeof(MFBatchLayout) == 152
 
 # name -> (restype, argtypes); every symbol include/ultrare_b200.h declares
@@ -74,7 +74,7 @@ SIGNATURES = {
     "ure_mf_batch_layout": (C.c_int, [C.POINTER(MFBatchShard), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _i64,
                                        C.POINTER(MFBatchLayout)]),
     "ure_mf_batch_setup": (C.c_int, [C.POINTER(MFBatchShard), C.c_int, C.c_int, C.POINTER(MFHParams), C.c_int, C.c_uint32,
-                                      _p, C.POINTER(MFBatchLayout), _p, _p]),
+                                      _p, C.POINTER(MFBatchLayout), _p, C.c_int, _p]),
     "ure_mf_batch_plan": (C.c_int, [_p, C.c_int, C.POINTER(MFHParams), _p, C.POINTER(MFBatchLayout), C.c_int, C.c_int,
                                      C.c_int, _p]),
     "ure_mf_runs_scratch_bytes": (_i64, [C.c_int, _i64, C.c_int, C.c_int]),
@@ -134,7 +134,7 @@ def lib() -> C.CDLL:
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(handle, name)           # AttributeError if the .so lacks a declared symbol
         fn.restype, fn.argtypes = res, args
-    if handle.ure_abi_version() != 4:
+    if handle.ure_abi_version() != 5:
         raise RuntimeError("ultrare_b200: ABI version mismatch; rebuild the shared library")
     _lib = handle
     return handle

@@ -78,33 +78,52 @@ ensemble_score_kernel(const float* const* __restrict__ Pk, const float* const* _
 //   common[p] = top_rating[p] in set(top_pred)        (positional, utils.py:179)
 //   NDCG = (sum_p relevance[p]*hit[p]*common[p] * w_p) / sum_p w_p,  w_0 = 1, w_p = 1/log2(p+1)
 // ---------------------------------------------------------------------------
+constexpr int kSegStage = 512;        // a segment up to this long is staged in shared memory (score, rating)
+// DCG position weights 1 / log2(p + 1) (w_0 = 1) and their sum over the top 10, as double literals: fp64 log2 and
+// division per thread cost more than the ranking itself on this part
+static_assert(URE_TOP_K == 10, "weight table below");
+__constant__ double kDcgWeight[URE_TOP_K] = {1.0, 1.0, 0.6309297535714575, 0.5, 0.43067655807339306,
+                                             0.38685280723454163, 0.3562071871080222, 0.3333333333333333,
+                                             0.31546487678572877, 0.3010299956639812};
+constexpr double kIdcg = 5.254494511770457;
+
 __global__ void __launch_bounds__(256)
 rank_metrics_kernel(const ure_inter_t* __restrict__ inter, const float* __restrict__ score,
                     const int32_t* __restrict__ order, const long long* __restrict__ seg, long long n_seg,
                     double* __restrict__ out) {
   __shared__ int top_pred[8][URE_TOP_K];
   __shared__ int top_rating[8][URE_TOP_K];
+  __shared__ float2 s_vt[8][kSegStage];
   const int lane = threadIdx.x & 31;
   const int w = threadIdx.x >> 5;
   const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
   double ndcg_sum = 0.0, hr_sum = 0.0, users = 0.0;
+  const double wgt = lane < URE_TOP_K ? kDcgWeight[lane] : 0.0;
   for (long long sgm = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; sgm < n_seg; sgm += n_warps) {
     const long long b = seg[sgm];
     const int L = (int)(seg[sgm + 1] - b);
     if (L <= 0) continue;
     if (lane < URE_TOP_K) { top_pred[w][lane] = -1; top_rating[w][lane] = -1; }
+    const bool staged = L <= kSegStage;
+    // (score, rating) of element f of the segment: from shared memory, or -- very long segments -- from global memory
+    auto value_of = [&](int f) {
+      if (staged) return s_vt[w][f];
+      const long long rf = order ? order[b + f] : b + f;
+      return make_float2(score[rf], inter[rf].rating);
+    };
+    if (staged)
+      for (int e = lane; e < L; e += 32) {
+        const long long re = order ? order[b + e] : b + e;
+        s_vt[w][e] = make_float2(score[re], inter[re].rating);
+      }
     __syncwarp();
     for (int e = lane; e < L; e += 32) {
-      const long long re = order ? order[b + e] : b + e;
-      const float ve = score[re];
-      const float te = inter[re].rating;
+      const float2 me = value_of(e);
       int rp = 0, rr = 0;
       for (int f = 0; f < L; ++f) {
-        const long long rf = order ? order[b + f] : b + f;
-        const float vf = score[rf];
-        const float tf = inter[rf].rating;
-        rp += (vf > ve) || (vf == ve && f > e);
-        rr += (tf > te) || (tf == te && f > e);
+        const float2 o = value_of(f);
+        rp += (o.x > me.x) || (o.x == me.x && f > e);
+        rr += (o.y > me.y) || (o.y == me.y && f > e);
       }
       if (rp < URE_TOP_K) top_pred[w][rp] = e;
       if (rr < URE_TOP_K) top_rating[w][rr] = e;
@@ -113,32 +132,32 @@ rank_metrics_kernel(const ure_inter_t* __restrict__ inter, const float* __restri
     double rel = 0.0, hit = 0.0;
     if (lane < URE_TOP_K && lane < L) {
       const int ep = top_pred[w][lane];
-      const long long rpos = order ? order[b + ep] : b + ep;
-      const double relevance = (double)inter[rpos].rating;
+      const double relevance = (double)value_of(ep).y;
       const bool h = relevance >= (4.0 / 5.0);
       const int tr = top_rating[w][lane];
       bool common = false;
 #pragma unroll
       for (int q = 0; q < URE_TOP_K; ++q) common |= (top_pred[w][q] == tr);
       hit = h ? 1.0 : 0.0;
-      const double wgt = lane == 0 ? 1.0 : 1.0 / log2((double)(lane + 1));
       rel = (h && common) ? relevance * wgt : 0.0;
     }
     rel = warp_sum(rel);
     hit = warp_sum(hit);
     if (lane == 0) {
-      double idcg = 1.0;
-      for (int p = 1; p < URE_TOP_K; ++p) idcg += 1.0 / log2((double)(p + 1));
-      ndcg_sum += rel / idcg;
+      ndcg_sum += rel / kIdcg;
       hr_sum += hit / (double)URE_TOP_K;
       users += 1.0;
     }
     __syncwarp();
   }
-  if (lane == 0 && users > 0.0) {
-    atomicAdd(out + 0, ndcg_sum);
-    atomicAdd(out + 1, hr_sum);
-    atomicAdd(out + 2, users);
+  // one set of atomics per CTA (thousands of warps on three addresses serialise in L2)
+  __shared__ double s_part[8][3];
+  if (lane == 0) { s_part[w][0] = ndcg_sum; s_part[w][1] = hr_sum; s_part[w][2] = users; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double t = 0.0;
+    for (int x = 0; x < 8; ++x) t += s_part[x][threadIdx.x];
+    if (t != 0.0) atomicAdd(out + threadIdx.x, t);
   }
 }
 
@@ -215,7 +234,7 @@ extern "C" int ure_rank_metrics(const ure_inter_t* d_inter, const float* d_score
               "ure_rank_metrics: null argument");
   if (n_seg <= 0) return 0;
   long long blocks = (n_seg + 7) / 8;
-  const long long cap = (long long)num_sms() * 8;
+  const long long cap = (long long)num_sms() * 4;            // 32 KB of shared memory per CTA: a full wave
   if (blocks > cap) blocks = cap;
   rank_metrics_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       d_inter, d_score, d_order, reinterpret_cast<const long long*>(d_seg), n_seg, d_out);

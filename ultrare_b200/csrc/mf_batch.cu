@@ -14,8 +14,10 @@
 extern "C" int64_t ure_mf_train_workspace_bytes(void);
 extern "C" int64_t ure_mf_owner_radix_bytes(int n_shards);
 extern "C" int64_t ure_mf_owner_smem_bytes(int d, int cap_rows, int cap_slots, int cap_list, int spe_cap, int flags);
-extern "C" int ure_mf_owner_prepare(const ure_mf_shard_t* d_shards, int n_shards, const ure_mf_hparams_t* h_hp, int epochs,
-                                    int max_rows, int32_t* d_radix_hist, void* d_workspace, void* stream);
+namespace ure {
+int mf_owner_prepare_impl(const ure_mf_shard_t* d_shards, int n_shards, const ure_mf_hparams_t* h_hp, int epochs,
+                          int max_rows, int32_t* d_radix_hist, void* d_workspace, void* stream, int flags);
+}
 
 static_assert(sizeof(ure_mf_batch_shard_t) == 32 && sizeof(ure_mf_batch_layout_t) == 152, "ctypes mirrors in _lib.py");
 
@@ -48,24 +50,25 @@ extern "C" int ure_mf_batch_layout(const ure_mf_batch_shard_t* h_shards, int n_s
   const int grid = num_sms();
   const int64_t table_rows = rows + (int64_t)n_shards * n_item;
   int64_t o = 0;
+  // the owner schedule wants the weights + momentum of every row in the SMs' shared memory: refuse cheaply
+  const int64_t state = table_rows * 8 * d;
+  out->owner = owner && n_shards <= grid && state <= (int64_t)grid * (200 << 10) && n_tot < (1ll << 31) && n_tot > 0;
   out->table = o; o = align_up(o + (int64_t)n_shards * sizeof(ure_mf_shard_t));
-  out->ws = o; o = align_up(o + ure_mf_train_workspace_bytes());
   out->W = o; o = align_up(o + table_rows * d * 4);
+  // everything ure_mf_batch_setup clears is ONE region [ws, zero_end): workspace, momentum + scratch, losses, row offsets
+  out->ws = o; o = align_up(o + ure_mf_train_workspace_bytes());
   out->Z = o; o = align_up(o + 2 * table_rows * d * 4);
   out->sse = o; o = align_up(o + (int64_t)n_shards * (epochs > 1 ? epochs : 1) * 8);
-  out->zero_end = o;                               // [Z, zero_end) is cleared by ure_mf_batch_setup
+  if (out->owner) { out->off = o; o = align_up(o + n_off * 4); }
+  out->zero_end = o;
   out->rows_total = rows;
   out->n_total = n_tot;
   out->spe_cap = spe_cap;
   out->max_rows = max_rows;
   out->max_n = max_n;
   out->grid = grid;
-  // the owner schedule wants the weights + momentum of every row in the SMs' shared memory: refuse cheaply
-  const int64_t state = table_rows * 8 * d;
-  out->owner = owner && n_shards <= grid && state <= (int64_t)grid * (200 << 10) && n_tot < (1ll << 31) && n_tot > 0;
   if (out->owner) {
     out->rec = o; o = align_up(o + 4 * (n_tot > 0 ? n_tot : 1) * 16);
-    out->off = o; o = align_up(o + n_off * 4);
     out->radix = o; o = align_up(o + ure_mf_owner_radix_bytes(n_shards));
     out->perm_inv = o; o = align_up(o + n_pinv * 4);
     const int64_t stride = 2 * n_tot > 0 ? 2 * n_tot : 1;
@@ -84,7 +87,7 @@ extern "C" int ure_mf_batch_layout(const ure_mf_batch_shard_t* h_shards, int n_s
 
 extern "C" int ure_mf_batch_setup(const ure_mf_batch_shard_t* h_shards, int n_shards, int n_item,
                                   const ure_mf_hparams_t* h_hp, int epochs, uint32_t perm_seed, void* d_arena,
-                                  const ure_mf_batch_layout_t* lay, void* h_stage, void* stream) {
+                                  const ure_mf_batch_layout_t* lay, void* h_stage, int flags, void* stream) {
   using namespace ure;
   URE_REQUIRE(h_shards && h_hp && d_arena && lay && h_stage, URE_EINVAL, "ure_mf_batch_setup: null argument");
   auto st = static_cast<cudaStream_t>(stream);
@@ -123,16 +126,20 @@ extern "C" int ure_mf_batch_setup(const ure_mf_batch_shard_t* h_shards, int n_sh
     prow += t.n_user;
   }
   URE_CUDA(cudaMemcpyAsync(base + lay->table, tab, (size_t)n_shards * sizeof(ure_mf_shard_t), cudaMemcpyHostToDevice, st));
-  URE_CUDA(cudaMemsetAsync(base + lay->ws, 0, (size_t)ure_mf_train_workspace_bytes(), st));
-  URE_CUDA(cudaMemsetAsync(base + lay->Z, 0, (size_t)(lay->zero_end - lay->Z), st));
+  URE_CUDA(cudaMemsetAsync(base + lay->ws, 0, (size_t)(lay->zero_end - lay->ws), st));
   if (lay->owner) {
-    URE_CUDA(cudaMemsetAsync(base + lay->off, 0, (size_t)(lay->radix - lay->off), st));
-    if (int rc = ure_mf_owner_prepare(reinterpret_cast<const ure_mf_shard_t*>(base + lay->table), n_shards, h_hp, epochs,
-                                      lay->max_rows, reinterpret_cast<int32_t*>(base + lay->radix), base + lay->ws, stream))
+    bool any_perm = false;
+    for (int s = 0; s < n_shards; ++s) any_perm |= h_shards[s].perm != nullptr;
+    const bool no_plan = (flags & URE_BATCH_NO_PLAN) != 0;
+    // 1: the workspace has just been cleared | 2: no plan kernel | 4: no explicit visiting orders to invert
+    if (int rc = mf_owner_prepare_impl(reinterpret_cast<const ure_mf_shard_t*>(base + lay->table), n_shards, h_hp, epochs,
+                                       lay->max_rows, reinterpret_cast<int32_t*>(base + lay->radix), base + lay->ws, stream,
+                                       1 | (no_plan ? 2 : 0) | (any_perm ? 0 : 4)))
       return rc;
     // the plan (4 ints) travels to the page-locked block right behind the descriptor table
-    URE_CUDA(cudaMemcpyAsync(static_cast<char*>(h_stage) + (size_t)n_shards * sizeof(ure_mf_shard_t), base + lay->ws, 16,
-                             cudaMemcpyDeviceToHost, st));
+    if (!no_plan)
+      URE_CUDA(cudaMemcpyAsync(static_cast<char*>(h_stage) + (size_t)n_shards * sizeof(ure_mf_shard_t), base + lay->ws, 16,
+                               cudaMemcpyDeviceToHost, st));
   }
   return 0;
 }

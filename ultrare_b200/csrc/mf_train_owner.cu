@@ -147,6 +147,17 @@ __device__ void make_plan(const ure_mf_shard_t* shards, int K, int cta, int n_ct
   __syncthreads();
 }
 
+// hparams.owner_plan (the workspace): the launch was queued with capacities from an earlier plan.  Every CTA of the
+// schedule pre-pass compares them with the plan it derives; one that is not covered flags the workspace and does
+// nothing else (block-uniform).  The training kernel starts after the pre-pass and trains nothing when the flag is up.
+__device__ __forceinline__ bool plan_not_covered(const ure_mf_hparams_t& hp, const Plan& pl, int spe) {
+  if (!hp.owner_plan) return false;
+  const bool bad = (pl.ru1 - pl.ru0) + (pl.ri1 - pl.ri0) > hp.owner_cap_rows || pl.mU + pl.mI > hp.owner_cap_slots ||
+                   spe > hp.owner_spe_cap;
+  if (bad && threadIdx.x == 0) static_cast<OwnerWs*>(hp.owner_plan)->error = 2;
+  return bad;
+}
+
 constexpr int kOtherBits = 20;            // record cache: other-table row in the low 20 bits, own row above
 constexpr int kOwnWarps = kOwnThreads / 32;
 constexpr int kMaxSpe = 8192;             // steps per epoch the schedule pre-pass handles (histogram in shared memory)
@@ -159,11 +170,12 @@ __host__ __device__ inline long long owner_smem_bytes(int d, int cap_rows, int c
   return 2ll * kOwnWarps * d * 4 + 2ll * cap_list + 8ll * (cached ? cap_slots : cap_list) + 8ll * cap_rows * d +
          8ll * cap_rows;
 }
-__global__ void plan_kernel(const ure_mf_shard_t* shards, int K, int batch, OwnerWs* ws) {
+__global__ void plan_kernel(const ure_mf_shard_t* shards, int K, int batch, int avail_smem, OwnerWs* ws) {
   __shared__ PlanScratch ps;
   __shared__ Plan pl;
   make_plan(shards, K, blockIdx.x, gridDim.x, pl, ps);
   if (threadIdx.x == 0) {
+    if (blockIdx.x == 0) ws->avail_smem = avail_smem;
     atomicMax(&ws->max_rows, (pl.ru1 - pl.ru0) + (pl.ri1 - pl.ri0));
     atomicMax(&ws->max_slots, pl.mU + pl.mI);
     atomicMax(&ws->max_spe, (shards[pl.shard].n + batch - 1) / batch);
@@ -422,6 +434,7 @@ owner_schedule_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_h
   const int mU = s_pl.mU, m = mU + s_pl.mI;
   const int B = hp.batch, n = sh.n;
   const int spe = (n + B - 1) / B;
+  if (plan_not_covered(hp, s_pl, spe)) return;
   if (spe == 0) return;
   const int cap = hp.owner_cap_slots, spe_cap = hp.owner_spe_cap;
   const bool cache_j = (hp.owner_flags & 2) == 0, short_ok = spe_cap <= 64;
@@ -699,6 +712,7 @@ owner_schedule_tab_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_
   const int mU = s_pl.mU, m = mU + s_pl.mI;
   const int B = hp.batch, n = sh.n;
   const int spe = (n + B - 1) / B;
+  if (plan_not_covered(hp, s_pl, spe)) return;
   if (spe == 0) return;
   const int cap = hp.owner_cap_slots, spe_cap = hp.owner_spe_cap;
   uint32_t* const s_lr = reinterpret_cast<uint32_t*>(dyn);                       // [cap]
@@ -904,6 +918,7 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
   __shared__ int s_total;                  // entries of the batch list in s_list
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gl = lane % G, gw = lane / G;
+  if (hp.owner_plan && ld_acquire_u32(reinterpret_cast<const unsigned*>(&ws->error)) == 2u) return;   // uniform over the grid: the pre-pass found the remembered capacities too small
   make_plan(shards, K, blockIdx.x, gridDim.x, s_pl, s_ps);
   if (tid == 0) s_sh = shards[s_pl.shard];
   __syncthreads();
@@ -1518,8 +1533,19 @@ extern "C" int ure_user_segments(const ure_inter_t* d_inter, int64_t n, int n_us
 
 extern "C" int64_t ure_mf_owner_radix_bytes(int n_shards) { return 2ll * n_shards * 256 * ure::kRadixBlocks * 4; }
 
+namespace ure {
+int mf_owner_prepare_impl(const ure_mf_shard_t* d_shards, int n_shards, const ure_mf_hparams_t* h_hp, int epochs,
+                          int max_rows, int32_t* d_radix_hist, void* d_workspace, void* stream, int flags);
+}
 extern "C" int ure_mf_owner_prepare(const ure_mf_shard_t* d_shards, int n_shards, const ure_mf_hparams_t* h_hp,
                                     int epochs, int max_rows, int32_t* d_radix_hist, void* d_workspace, void* stream) {
+  return ure::mf_owner_prepare_impl(d_shards, n_shards, h_hp, epochs, max_rows, d_radix_hist, d_workspace, stream, 0);
+}
+
+// flags (the native batch runtime): 1 = the caller has just cleared the workspace; 2 = no plan kernel (the launch runs
+// on remembered capacities, checked by the schedule pre-pass); 4 = no shard has explicit visiting orders
+int ure::mf_owner_prepare_impl(const ure_mf_shard_t* d_shards, int n_shards, const ure_mf_hparams_t* h_hp, int epochs,
+                               int max_rows, int32_t* d_radix_hist, void* d_workspace, void* stream, int flags) {
   using namespace ure;
   URE_REQUIRE(d_shards && h_hp && d_workspace, URE_EINVAL, "ure_mf_owner_prepare: null argument");
   URE_REQUIRE(n_shards >= 1 && n_shards <= num_sms(), URE_EUNSUPPORTED,
@@ -1544,12 +1570,14 @@ extern "C" int ure_mf_owner_prepare(const ure_mf_shard_t* d_shards, int n_shards
     radix_scan_kernel<<<2 * n_shards, 256, 0, st>>>(d_radix_hist, kRadixBlocks);
     radix_scatter_kernel<<<dim3(kRadixBlocks, 2 * n_shards), kRadixThreads, 0, st>>>(d_shards, pass, npass, d_radix_hist);
   }
-  perm_inverse_kernel<<<dim3(blocks, n_shards), 256, 0, st>>>(d_shards, epochs);
+  if (!(flags & 4)) perm_inverse_kernel<<<dim3(blocks, n_shards), 256, 0, st>>>(d_shards, epochs);
   int avail = 0;
   if (int rc = max_dyn_smem(&avail)) return rc;
-  const int head[6] = {0, 0, 0, avail, 0, 0};
-  URE_CUDA(cudaMemcpyAsync(ws, head, sizeof(head), cudaMemcpyHostToDevice, st));
-  plan_kernel<<<num_sms(), 32, 0, st>>>(d_shards, n_shards, h_hp->batch, ws);
+  if (!(flags & 1)) {                      // a workspace of unknown content: reset the plan fields
+    const int head[6] = {0, 0, 0, 0, 0, 0};
+    URE_CUDA(cudaMemcpyAsync(ws, head, sizeof(head), cudaMemcpyHostToDevice, st));
+  }
+  if (!(flags & 2)) plan_kernel<<<num_sms(), 32, 0, st>>>(d_shards, n_shards, h_hp->batch, avail, ws);
   URE_CUDA(cudaGetLastError());
   return 0;
 }

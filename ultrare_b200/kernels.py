@@ -643,32 +643,38 @@ class ShardBatch:
             while self.step < step_end:
                 t1 = step_end
                 if self.mode in ("owner", "runs"):
-                    # the schedule tables hold `rows` epochs per shard from the window's first step on
-                    a, b = self._sched_cover
-                    rows = self.hp.owner_sched_rows if self.mode == "owner" else self.hp.runs_rows
-                    if not (a <= self.step < b):
-                        if self.mode == "owner":
-                            check(L.ure_mf_owner_schedule(_ptr(self.table), self.n_shards, C.byref(self.hp), self.epochs,
-                                                          self.step, _stream()), "ure_mf_owner_schedule")
-                            self.launches_per_pass += 1
-                        else:
-                            check(L.ure_mf_runs_schedule(_ptr(self.table), self.n_shards, C.byref(self.hp), self.epochs,
-                                                         self.step, self._runs_max_n, _ptr(self._runs_scratch), _stream()),
-                                  "ure_mf_runs_schedule")
-                            self.launches_per_pass += 3
-                        a = self.step                  # shard s leaves the window at step (a // spe_s + rows) * spe_s
-                        b = min([(a // spe + rows) * spe for spe in self._spes
-                                 if a // spe + rows < self.epochs] or [self.total_steps])
-                        self._sched_cover = (a, b)
-                        if self.mode == "owner":
-                            self.hp.owner_sched_step0 = a
-                        else:
-                            self.hp.runs_step0 = a
-                    t1 = min(step_end, b)
+                    t1 = min(step_end, self._schedule_window())
                 check(L.ure_mf_train(_ptr(self.table), self.n_shards, C.byref(self.hp), self.epochs,
                                      self.step, t1, self.warps_group0, _ptr(self.ws), _stream()), "ure_mf_train")
                 self.launches_per_pass += 1
                 self.step = t1
+
+    def _schedule_window(self) -> int:
+        """OWNER / RUNS: make sure the schedule tables cover self.step (queue the pre-pass if not); returns the global
+        step the window ends at.  The tables hold `rows` epochs per shard from the window's first step on."""
+        L = _lib.lib()
+        a, b = self._sched_cover
+        rows = self.hp.owner_sched_rows if self.mode == "owner" else self.hp.runs_rows
+        if not (a <= self.step < b):
+            with torch.cuda.device(self.device):
+                if self.mode == "owner":
+                    check(L.ure_mf_owner_schedule(_ptr(self.table), self.n_shards, C.byref(self.hp), self.epochs,
+                                                  self.step, _stream()), "ure_mf_owner_schedule")
+                    self.launches_per_pass += 1
+                else:
+                    check(L.ure_mf_runs_schedule(_ptr(self.table), self.n_shards, C.byref(self.hp), self.epochs,
+                                                 self.step, self._runs_max_n, _ptr(self._runs_scratch), _stream()),
+                          "ure_mf_runs_schedule")
+                    self.launches_per_pass += 3
+            a = self.step                  # shard s leaves the window at step (a // spe_s + rows) * spe_s
+            b = min([(a // spe + rows) * spe for spe in self._spes
+                     if a // spe + rows < self.epochs] or [self.total_steps])
+            self._sched_cover = (a, b)
+            if self.mode == "owner":
+                self.hp.owner_sched_step0 = a
+            else:
+                self.hp.runs_step0 = a
+        return b
 
     def reset_for_rerun(self) -> None:
         """Back to step 0 with zero momentum and losses (the weights stay): bench.py times the training launch alone."""
@@ -713,6 +719,9 @@ class ShardBatch:
             vals = host[:nb].view(torch.float64).numpy().reshape(K, E).copy()
             err = int(host[nb:nb + 4].view(torch.int32).item()) if owner else 0
             _PINNED_BYTES.setdefault(host.shape[0], []).append((host, None))
+            if err == 2:
+                _PLAN_HINTS.pop(getattr(self, "_plan_sig", None), None)
+                raise PlanHintMiss("ultrare_b200: the remembered owner plan does not cover this batch; repeat the pass")
             if err != 0:
                 raise RuntimeError("ultrare_b200: owner schedule asked for a step outside its scheduled window")
             return [np.sqrt(vals[j] / ns[j]) for j in range(K)]
@@ -740,6 +749,15 @@ class ShardView:
         return -(-self.n // batch)
 
 
+class PlanHintMiss(RuntimeError):
+    """An optimistic owner launch (capacities from an earlier plan of the same shapes) did not cover the plan the
+    set-up kernels found: nothing was trained; the caller repeats the pass (the hint is gone, so it waits for the plan)."""
+
+
+_PLAN_HINTS = {}          # batch signature -> (max_rows, max_slots, max_spe, smem) of the last plan read back
+PLAN_HINT_MARGIN = 0.03   # capacities of an optimistic launch: the remembered maxima plus this fraction
+
+
 class ArenaShardBatch(ShardBatch):
     """ShardBatch whose whole device state is ONE allocation laid out, described and prepared by the native runtime
     (csrc/mf_batch.cu: ure_mf_batch_layout / _setup / _plan): the host makes one allocation, one library call that
@@ -751,8 +769,15 @@ class ArenaShardBatch(ShardBatch):
 
     def __init__(self, recs, rows_P, n_item: int, d: int, batch: int, epochs: int, shard_ids, perm_seed: int = 42,
                  perms=None, lr: float = 1e-3, lr_decay: float = 0.95, lr_step: int = 50, weight_decay: float = 0.1,
-                 momentum: float = 0.9, generator=None, std: float = 1.0, mode: str = "auto", owner_cache: bool = True):
+                 momentum: float = 0.9, generator=None, std: float = 1.0, mode: str = "auto", owner_cache: bool = True,
+                 optimistic: bool = False):
+        """optimistic: the caller reads the training losses (train_losses_async) only after everything that depends
+        on the training is queued, and repeats the pass on PlanHintMiss.  The launch is then queued with the
+        capacities of the last plan read back for the same shapes (+ PLAN_HINT_MARGIN) instead of waiting for this
+        one's -- the kernels compare them with the real plan on the device (hparams.owner_plan)."""
         K = self.n_shards = len(recs)
+        tq = [("start", time.perf_counter())]                # host stamps of the constructor (diagnostics: ctor_ms)
+        stamp = lambda name: tq.append((name, time.perf_counter()))
         if not 1 <= K <= _lib.URE_MAX_SHARDS:
             raise ValueError(f"1..{_lib.URE_MAX_SHARDS} shards per launch")
         if mode not in ("dense", "owner", "auto"):
@@ -794,49 +819,89 @@ class ArenaShardBatch(ShardBatch):
         if mode == "owner" and not lay.owner:
             raise RuntimeError("owner mode does not fit this problem (row state beyond the SMs' shared memory)")
         self._lay = lay
+        stamp("layout")
         self.arena = torch.empty(int(lay.total), dtype=torch.uint8, device=dev)
         base = self.arena.data_ptr()
         stage = _staging_bytes(176 * K + 64)
+        stamp("alloc")
+        self.table_ptr = base + int(lay.table)
+        self.ws = self.arena[int(lay.ws):int(lay.ws) + int(L.ure_mf_train_workspace_bytes())]
+        self.mode, self.optimistic, self.step = "dense", False, 0
+        info = (C.c_int32 * 8)()
+        force = OWNER_FORCE if OWNER_FORCE is not None else (-1, 0)
+        sig = (K, d, batch, int(n_item), tuple(self._rows_P), self.epochs, perms is not None, bool(owner_cache),
+               OWNER_FORCE, dev.index)
+
+        def plan_with(vals):
+            arr = (C.c_int32 * 4)(*[int(v) for v in vals])
+            return L.ure_mf_batch_plan(arr, K, C.byref(self.hp), C.c_void_p(base), C.byref(lay),
+                                       int(bool(owner_cache)), int(force[0]), int(force[1]), info)
+
+        # optimistic: launch parameters from the remembered plan of these shapes, before anything is queued
+        rc = 0
+        hint = _PLAN_HINTS.get(sig) if (optimistic and lay.owner) else None
+        if hint is not None:
+            mr, ms, _, avail = hint
+            for margin in (PLAN_HINT_MARGIN, 0.0):
+                rc = plan_with((mr + int(mr * margin) + (2 if margin else 0), ms + int(ms * margin), lay.spe_cap, avail))
+                if rc == 1:
+                    break
+            if rc == 1:
+                self.optimistic, self.plan_sync_ms = True, 0.0
+                self.hp.owner_plan = self.ws.data_ptr()
         with torch.cuda.device(dev):
             check(L.ure_mf_batch_setup(hs, K, n_item, C.byref(self.hp), self.epochs, self._perm_seed, C.c_void_p(base),
-                                       C.byref(lay), C.c_void_p(stage.data_ptr()), _stream()), "ure_mf_batch_setup")
+                                       C.byref(lay), C.c_void_p(stage.data_ptr()), 1 if self.optimistic else 0, _stream()),
+                  "ure_mf_batch_setup")
             if lay.owner:
                 npass = 1
                 while npass < 4 and (int(lay.max_rows) - 1) >> (8 * npass):
                     npass += 1
-                self.prepare_launches = 2 + 3 * npass + 1 + 1
+                # count + scan, radix passes, [inverse visiting orders], [plan]
+                self.prepare_launches = 2 + 3 * npass + (1 if perms is not None else 0) + (0 if self.optimistic else 1)
                 self.launches_per_pass += self.prepare_launches
             ev = torch.cuda.Event()
             ev.record()
-            # weights: N(0, std) (reference utils.py:38-40), queued behind the set-up kernels
-            rows_w = int(lay.rows_total) + K * n_item
-            self._W = self.arena[int(lay.W):int(lay.W) + rows_w * d * 4].view(torch.float32).view(rows_w, d)
-            self._W.normal_(0.0, std, generator=generator)
-        self.table_ptr = base + int(lay.table)
-        self.ws = self.arena[int(lay.ws):int(lay.ws) + int(L.ure_mf_train_workspace_bytes())]
-        self.mode = "dense"
+        stamp("setup_queued")
+        rows_w = int(lay.rows_total) + K * n_item
+
+        def fill_weights():
+            # weights: N(0, std) (reference utils.py:38-40), queued behind the set-up kernels -- and, on the optimistic
+            # path, behind the schedule pre-pass, which does not read them (the host reaches that launch sooner)
+            with torch.cuda.device(dev):
+                self._W = self.arena[int(lay.W):int(lay.W) + rows_w * d * 4].view(torch.float32).view(rows_w, d)
+                self._W.normal_(0.0, std, generator=generator() if callable(generator) else generator)
+
+        if not self.optimistic:
+            fill_weights()
         if lay.owner:
-            t0 = time.perf_counter()
-            ev.synchronize()                                 # the one wait of the set-up: upload + sorts + plan
-            self.plan_sync_ms = (time.perf_counter() - t0) * 1e3
-            plan = stage[176 * K:176 * K + 16].view(torch.int32)
-            info = (C.c_int32 * 8)()
-            force = OWNER_FORCE if OWNER_FORCE is not None else (-1, 0)
-            rc = L.ure_mf_batch_plan(C.c_void_p(plan.data_ptr()), K, C.byref(self.hp), C.c_void_p(base), C.byref(lay),
-                                     int(bool(owner_cache)), int(force[0]), int(force[1]), info)
+            if not self.optimistic:
+                t0 = time.perf_counter()
+                ev.synchronize()                             # the one wait of the set-up: upload + sorts + plan
+                self.plan_sync_ms = (time.perf_counter() - t0) * 1e3
+                plan = stage[176 * K:176 * K + 16].view(torch.int32)
+                _PLAN_HINTS[sig] = tuple(int(v) for v in plan.tolist())
+                rc = plan_with(plan.tolist())
             if rc < 0:
                 check(rc, "ure_mf_batch_plan")
             self.owner_plan = dict(zip(("fits", "flags", "list_cap", "max_rows_per_cta", "max_slots_per_cta",
                                         "max_steps_per_epoch", "smem_need", "smem_avail"), list(info)))
             self.owner_plan["cached"] = bool(info[1] & 1) if info[1] >= 0 else False
+            self.owner_plan["optimistic"] = self.optimistic
+            self._plan_sig = sig
             if rc == 1:
                 self.mode = "owner"
                 self._sched_cover = (0, 0)
                 self._spes = [-(-n // batch) for n in ns if n > 0]
+                if self.optimistic:
+                    self._schedule_window()              # the pre-pass is queued before anything else
+                    stamp("schedule_queued")
+                    fill_weights()
             elif mode == "owner":
                 raise RuntimeError(f"owner mode does not fit this problem: {self.owner_plan}")
         _PINNED_BYTES.setdefault(stage.shape[0], []).append((stage, ev))
-        self.step = 0
+        stamp("end")
+        self.ctor_ms = {b[0]: round((b[1] - a[1]) * 1e3, 4) for a, b in zip(tq[:-1], tq[1:])}
 
     # ---- what ShardBatch reads through self.table / self.shards
     @property

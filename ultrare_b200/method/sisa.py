@@ -249,7 +249,8 @@ class Sisa(Scratch):
                 sb = kn.ArenaShardBatch(recs, rows, self.n_item, self.k, batch, E, [i + 1 for i in mine], self.seed,
                                         perms if any(p is not None for p in perms) else None, self.lr, self.lr_decay,
                                         50, self.lam, self.momentum,
-                                        generator=model_generator(self.seed, mine[0] + 1, self.device))
+                                        generator=lambda: model_generator(self.seed, mine[0] + 1, self.device),
+                                        optimistic=defer_logs and mode == 'none' and verbose != 1 and self.dist.world == 1)
                 states = None
             else:
                 for j, i in enumerate(mine):
@@ -261,6 +262,7 @@ class Sisa(Scratch):
             self.timing['setup_alloc_ms'] = (t_a - t0) * 1e3
             self.timing['setup_upload_states_ms'] = (t_b - t_a) * 1e3
             self.timing['setup_batch_ms'] = (time.time() - t_b) * 1e3
+            self.timing['batch_ctor_ms'] = getattr(sb, 'ctor_ms', None)
             if states is None and mode == 'faithful':
                 states = sb.shards
             if mode == 'faithful':
@@ -466,8 +468,21 @@ class Sisa(Scratch):
         return merged
 
     # ------------------------------------------------------------------ learn / unlearn
+    def _retrying(self, once, *args):
+        """An optimistic owner launch whose remembered plan did not cover the batch trained nothing (kernels.PlanHintMiss,
+        raised when the deferred losses are read): repeat the pass -- the hint is gone, so this one waits for its plan."""
+        try:
+            return once(*args)
+        except kn.PlanHintMiss:
+            self._pending_logs = None
+            self._join_writers()
+            return once(*args)
+
     def learn(self, train_dlist, test_dlist, test_data, verbose, save_dir):
         """reference sisa.py:25-63."""
+        return self._retrying(self._learn_once, train_dlist, test_dlist, test_data, verbose, save_dir)
+
+    def _learn_once(self, train_dlist, test_dlist, test_data, verbose, save_dir):
         assert len(train_dlist) == self.n_group
         assert len(test_dlist) == self.n_group
         self._test_dlist = test_dlist
@@ -503,6 +518,10 @@ class Sisa(Scratch):
 
     def unlearn(self, model_list, train_dlist, test_dlist, test_data, del_user, verbose, save_dir):
         """reference sisa.py:66-118."""
+        return self._retrying(self._unlearn_once, model_list, train_dlist, test_dlist, test_data, del_user, verbose,
+                              save_dir)
+
+    def _unlearn_once(self, model_list, train_dlist, test_dlist, test_data, del_user, verbose, save_dir):
         self.model_list = list(model_list)
         assert len(train_dlist) == self.n_group
         assert len(test_dlist) == self.n_group

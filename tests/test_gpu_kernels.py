@@ -225,6 +225,30 @@ def test_rank_metrics_edge_cases(cuda_dev):
     assert empty.cpu().numpy().tolist() == [0.0, 0.0, 0.0]
 
 
+def test_rank_metrics_long_segments(cuda_dev):
+    """Segments far longer than a warp (several elements per lane in the staged arg-max rounds) and longer than the
+    shared-memory stage (the counting-rank path), with heavily tied scores and ratings, in user order and through
+    the order indirection."""
+    torch = _torch()
+    from ultrare_b200 import kernels as kn
+    rng = np.random.default_rng(3)
+    lens = [300, 513, 700, 33, 64, 9, 512]
+    u = np.concatenate([np.full(n, j) for j, n in enumerate(lens)])
+    n = len(u)
+    r = (rng.integers(1, 6, n) / 5).astype(np.float32)
+    s = np.round(rng.standard_normal(n) * 2).astype(np.float32) / 2          # many exact ties
+    for shuffle in (False, True):
+        idx = rng.permutation(n) if shuffle else np.arange(n)
+        uu, rr, ss = u[idx], r[idx], s[idx]
+        inter = kn.pack_interactions(uu, np.zeros(n, dtype=np.int64), rr, cuda_dev)
+        order, seg = kn.user_segments(uu)
+        assert (order is not None) == shuffle
+        out = kn.rank_metrics(inter, torch.tensor(ss, device=cuda_dev), torch.tensor(seg, device=cuda_dev),
+                              None if order is None else torch.tensor(order, device=cuda_dev)).cpu().numpy()
+        nd, hr = evalm.rank_metrics(uu, rr, ss, kind="stable")
+        assert out[2] == len(lens) and abs(out[0] / len(lens) - nd) < 1e-12 and abs(out[1] / len(lens) - hr) < 1e-12
+
+
 def test_routing_and_merge_vs_reference_golden(cuda_dev):
     """retrain_gid and merged tables bit-exact (Appendix E)."""
     torch = _torch()

@@ -117,16 +117,45 @@ rank_metrics_kernel(const ure_inter_t* __restrict__ inter, const float* __restri
         s_vt[w][e] = make_float2(score[re], inter[re].rating);
       }
     __syncwarp();
-    for (int e = lane; e < L; e += 32) {
-      const float2 me = value_of(e);
-      int rp = 0, rr = 0;
-      for (int f = 0; f < L; ++f) {
-        const float2 o = value_of(f);
-        rp += (o.x > me.x) || (o.x == me.x && f > e);
-        rr += (o.y > me.y) || (o.y == me.y && f > e);
+    if (staged) {
+      // the element of rank p is the p-th in the order (value descending, index descending): ten rounds of a warp
+      // arg-max over the staged segment instead of L^2 comparisons (one heavy user used to be the kernel's tail)
+      auto top10 = [&](bool by_rating, int* dst) {
+        unsigned taken = 0;                  // bit k: element lane + 32 k is already placed
+        const int P = L < URE_TOP_K ? L : URE_TOP_K;
+        for (int p = 0; p < P; ++p) {
+          float bv = -INFINITY;
+          int be = -1;
+          for (int k = 0, e = lane; e < L; ++k, e += 32) {
+            if ((taken >> k) & 1u) continue;
+            const float2 x = s_vt[w][e];
+            const float v = by_rating ? x.y : x.x;
+            if (v > bv || (v == bv && e > be)) { bv = v; be = e; }
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oe = __shfl_xor_sync(0xffffffffu, be, o);
+            if (ov > bv || (ov == bv && oe > be)) { bv = ov; be = oe; }
+          }
+          if (lane == 0) dst[p] = be;
+          if (be >= 0 && (be & 31) == lane) taken |= 1u << (be >> 5);
+        }
+      };
+      top10(false, top_pred[w]);
+      top10(true, top_rating[w]);
+    } else {
+      for (int e = lane; e < L; e += 32) {
+        const float2 me = value_of(e);
+        int rp = 0, rr = 0;
+        for (int f = 0; f < L; ++f) {
+          const float2 o = value_of(f);
+          rp += (o.x > me.x) || (o.x == me.x && f > e);
+          rr += (o.y > me.y) || (o.y == me.y && f > e);
+        }
+        if (rp < URE_TOP_K) top_pred[w][rp] = e;
+        if (rr < URE_TOP_K) top_rating[w][rr] = e;
       }
-      if (rp < URE_TOP_K) top_pred[w][rp] = e;
-      if (rr < URE_TOP_K) top_rating[w][rr] = e;
     }
     __syncwarp();
     double rel = 0.0, hit = 0.0;

@@ -608,9 +608,13 @@ __host__ __device__ inline CostWsLayout cost_ws_layout(int D, int NB) {
   CostWsLayout L;
   const uint32_t chunks = D / 4;
   L.tile_bytes = kTileRows * D * 4;
-  L.S = D >= 128 ? 2 : 4;
-  L.LS = D >= 128 ? 1 : 2;
   L.lbo_b = 2 * NB * 16 + (chunks >= 8 ? 16 : 32);      // [B_hi ; B_lo]: 2 NB rows per 16-byte K chunk
+  // raw (hi) and lo tile stages: as many as fit next to the centroid block (226 KB per CTA)
+  const uint32_t fixed = L.lbo_b * chunks + 8 * kTileRows * 4 + NB * 4 + 16 * 8 + 16 + 64 + 1024;
+  const uint32_t tiles = fixed < 226u * 1024u ? (226u * 1024u - fixed) / L.tile_bytes : 0u;
+  L.S = tiles >= 6 ? 4 : tiles >= 4 ? 3 : 2;
+  L.LS = tiles >= 5 ? 2 : 1;
+  if (tiles < 3) L.S = 0;                                // does not fit: the caller falls back
   uint32_t o = 0;
   L.hi_off = o; o += L.tile_bytes * L.S;
   L.lo_off = o; o += L.tile_bytes * L.LS;
@@ -627,7 +631,7 @@ __host__ __device__ inline CostWsLayout cost_ws_layout(int D, int NB) {
 template <int D>
 __global__ void __launch_bounds__(kWsThreads, 1)
 cost_ws_kernel(const __grid_constant__ CUtensorMap tmap, long long n, const float* __restrict__ C, int k, int kpad, int NB,
-               uint32_t tmem_cols, float* __restrict__ M, double* __restrict__ inertia) {
+               uint32_t tmem_cols, int fold, float* __restrict__ M, double* __restrict__ inertia) {
   constexpr int CH = D / 4;
   extern __shared__ __align__(128) unsigned char sm_raw[];
   unsigned char* const sm = sm_raw + ((1024u - (smem_u32(sm_raw) & 1023u)) & 1023u);
@@ -739,13 +743,28 @@ cost_ws_kernel(const __grid_constant__ CUtensorMap tmap, long long n, const floa
         tc_fence_after();
         const uint32_t hi_addr = smem_u32(sm + L.hi_off + (size_t)s * L.tile_bytes);
         const uint32_t lo_addr = smem_u32(sm + L.lo_off + (size_t)ls * L.tile_bytes);
-        const uint32_t d1 = tmem_base + (uint32_t)(a * 3 * NB), d2 = d1 + (uint32_t)(2 * NB);
+        if (!fold) {
+          const uint32_t d1 = tmem_base + (uint32_t)(a * 3 * NB), d2 = d1 + (uint32_t)(2 * NB);
 #pragma unroll
-        for (int kk = 0; kk < D / 8; ++kk) {
-          const uint32_t a_off = (uint32_t)((kk >> 2) * (kTileRows * 128) + (kk & 3) * 32);
-          const uint64_t bdesc = make_desc(b_addr + kk * 2 * L.lbo_b, L.lbo_b, 128);
-          umma_tf32(d1, make_desc_sw128(hi_addr + a_off), bdesc, idesc2, kk > 0);     // hi*hi | hi*lo
-          umma_tf32(d2, make_desc_sw128(lo_addr + a_off), bdesc, idesc1, kk > 0);     // lo*hi (first NB rows of B)
+          for (int kk = 0; kk < D / 8; ++kk) {
+            const uint32_t a_off = (uint32_t)((kk >> 2) * (kTileRows * 128) + (kk & 3) * 32);
+            const uint64_t bdesc = make_desc(b_addr + kk * 2 * L.lbo_b, L.lbo_b, 128);
+            umma_tf32(d1, make_desc_sw128(hi_addr + a_off), bdesc, idesc2, kk > 0);     // hi*hi | hi*lo
+            umma_tf32(d2, make_desc_sw128(lo_addr + a_off), bdesc, idesc1, kk > 0);     // lo*hi (first NB rows of B)
+          }
+        } else {
+          // wide centroid blocks (6 NB columns of TMEM do not exist): the three products go to ONE accumulator
+          const uint32_t dd = tmem_base + (uint32_t)(a * NB);
+#pragma unroll
+          for (int kk = 0; kk < D / 8; ++kk) {
+            const uint32_t a_off = (uint32_t)((kk >> 2) * (kTileRows * 128) + (kk & 3) * 32);
+            const uint64_t bhi = make_desc(b_addr + kk * 2 * L.lbo_b, L.lbo_b, 128);
+            const uint64_t blo = make_desc(b_addr + kk * 2 * L.lbo_b + (uint32_t)NB * 16u, L.lbo_b, 128);
+            const uint64_t ahi = make_desc_sw128(hi_addr + a_off);
+            umma_tf32(dd, ahi, bhi, idesc1, kk > 0);
+            umma_tf32(dd, ahi, blo, idesc1, 1);
+            umma_tf32(dd, make_desc_sw128(lo_addr + a_off), bhi, idesc1, 1);
+          }
         }
         umma_commit(&empty[s]);             // the raw tile may be overwritten by the producer
         umma_commit(&lo_empty[ls]);         // ... the lo tile by the lo warps
@@ -765,17 +784,19 @@ cost_ws_kernel(const __grid_constant__ CUtensorMap tmap, long long n, const floa
       tc_fence_after();
       float* xn = xnorm + (it & 7) * kTileRows;
       const float xnr = xn[trow];
-      const uint32_t d1 = tmem_base + ((uint32_t)(rq * 32) << 16) + (uint32_t)(a * 3 * NB);
+      const uint32_t d1 = tmem_base + ((uint32_t)(rq * 32) << 16) + (uint32_t)(a * (fold ? 1 : 3) * NB);
       float rmin = INFINITY;
       for (int c0 = 0; c0 < NB; c0 += 16) {
         float acc[16], t2[16];
         tmem_ld16(d1 + (uint32_t)c0, acc);
-        tmem_ld16(d1 + (uint32_t)(NB + c0), t2);
+        if (!fold) {
+          tmem_ld16(d1 + (uint32_t)(NB + c0), t2);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc[j] += t2[j];
-        tmem_ld16(d1 + (uint32_t)(2 * NB + c0), t2);
+          for (int j = 0; j < 16; ++j) acc[j] += t2[j];
+          tmem_ld16(d1 + (uint32_t)(2 * NB + c0), t2);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc[j] += t2[j];
+          for (int j = 0; j < 16; ++j) acc[j] += t2[j];
+        }
         if (row < n) {
           float out[16];
 #pragma unroll
@@ -811,12 +832,13 @@ int launch_cost_ws(const float* X, long long n, const float* C, int k, int kpad,
   static const int off = getenv("URE_COST_WS") ? !atoi(getenv("URE_COST_WS")) : 0;
   EncodeTiledFn enc = encode_tiled();
   const int NB = kpad < 16 ? 16 : kpad;
-  if (off || !enc || D < 32 || NB > 64 || (reinterpret_cast<uintptr_t>(X) & 15) != 0 || n >= (1ll << 31)) return 0;
+  if (off || !enc || D < 32 || NB > 128 || (reinterpret_cast<uintptr_t>(X) & 15) != 0 || n >= (1ll << 31)) return 0;
   const CostWsLayout L = cost_ws_layout(D, NB);
   const size_t smem = (size_t)L.total + 1024;
-  if (smem > 226 * 1024) return 0;
+  if (L.S == 0 || smem > 227 * 1024) return 0;
+  const int fold = 6 * NB > 512;                              // TMEM has 512 columns
   uint32_t tmem_cols = 32;
-  while ((int)tmem_cols < 6 * NB) tmem_cols <<= 1;            // two accumulator stages of [D1 (2 NB) | D2 (NB)]
+  while ((int)tmem_cols < (fold ? 2 : 6) * NB) tmem_cols <<= 1;   // two accumulator stages of [D1 (2 NB) | D2 (NB)], or of one [NB]
   CUtensorMap tmap;
   const cuuint64_t dims[2] = {(cuuint64_t)D, (cuuint64_t)n};
   const cuuint64_t strides[1] = {(cuuint64_t)D * 4};
@@ -832,7 +854,7 @@ int launch_cost_ws(const float* X, long long n, const float* C, int k, int kpad,
   long long gx = num_sms();
   if (gx > n_tiles) gx = n_tiles;
   *used = 1;
-  kern<<<dim3((unsigned)gx), kWsThreads, smem, st>>>(tmap, n, C, k, kpad, NB, tmem_cols, M, inertia);
+  kern<<<dim3((unsigned)gx), kWsThreads, smem, st>>>(tmap, n, C, k, kpad, NB, tmem_cols, fold, M, inertia);
   URE_CUDA(cudaGetLastError());
   return 0;
 }

@@ -899,8 +899,15 @@ extern "C" int ure_sinkhorn(const float* d_M, int64_t n, int k, int kpad, float*
 #undef URE_CLUSTER_CASE
     }
   }
-  if (need <= 200 * 1024) {
-    // small problem: everything is latency -- one persistent launch, a CTA's rows cached in shared memory
+  int smem_optin = 0;
+  {
+    int dev = 0;
+    URE_CUDA(cudaGetDevice(&dev));
+    URE_CUDA(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  }
+  if ((long long)need <= (long long)smem_optin - 2048) {     // minus the kernel's static shared memory
+    // the cost rows fit the SMs' shared memory (n = 1 M users at k <= 8: 216 KB per SM): one persistent launch, M is
+    // read from HBM once for ALL iterations, an iteration costs a shared-memory sweep + one grid barrier
     URE_KPAD_SWITCH(kpad, return (launch_sinkhorn<KP, true>(d_M, n, k, d_g, stg, ws, grid, need, st)));
   }
   (void)parts;

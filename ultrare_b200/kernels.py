@@ -1078,13 +1078,16 @@ def kpad_for(k: int) -> int:
     raise ValueError("k > 256 centroids is not supported")
 
 
-def cost_matrix(X, Cc, want_inertia=False, simt=False):
-    """M [n,kpad] fp32 (columns >= k are +inf) and optionally the fp64 inertia scalar tensor."""
+def cost_matrix(X, Cc, want_inertia=False, simt=False, out=None):
+    """M [n,kpad] fp32 (columns >= k are +inf) and optionally the fp64 inertia scalar tensor.  out: an [n,kpad] fp32
+    tensor to write into instead of a new one."""
     _need_cuda(X, Cc)
     n, d = X.shape
     k = Cc.shape[0]
     kp = kpad_for(k)
-    M = torch.empty((n, kp), dtype=torch.float32, device=X.device)
+    if out is not None:
+        assert out.shape == (n, kp) and out.dtype == torch.float32 and out.is_contiguous() and out.device == X.device
+    M = torch.empty((n, kp), dtype=torch.float32, device=X.device) if out is None else out
     inertia = torch.zeros(1, dtype=torch.float64, device=X.device) if want_inertia else None
     fn = _lib.lib().ure_cost_matrix_simt if simt else _lib.lib().ure_cost_matrix
     with torch.cuda.device(X.device):

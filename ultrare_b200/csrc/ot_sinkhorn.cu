@@ -18,6 +18,8 @@
 // the same exponential feeds the row sum (times 2^r, a per-lane constant) and the column sum.  Partial sums
 // travel as (r, s) pairs: lanes -> warp (shuffle) -> CTA (shared memory, fixed order) -> grid (one fp64 atomic
 // per column and CTA of s * 2^r / n, r clamped at -960; the cluster form keeps the pairs to the end).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include <cooperative_groups.h>
 
@@ -250,7 +252,7 @@ struct SkWorkspace {
 };
 
 template <int KPAD, bool CACHED>
-__global__ void __launch_bounds__(kSkThreads, 1)
+__global__ void __launch_bounds__(kSkThreads, CACHED ? 1 : 2)
 sinkhorn_kernel(const float* __restrict__ M, long long n, int k, float* __restrict__ g_io, SkStages stages,
                 SkWorkspace* ws) {
   extern __shared__ __align__(16) float m_sh[];     // part_r | part_s [warps][KPAD]; CACHED: then this CTA's rows of M
@@ -341,8 +343,9 @@ __device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsign
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+// two CTAs per SM (<= 64 registers): one CTA of 16 warps per SM streams at a third of the HBM rate
 template <int KPAD>
-__global__ void __launch_bounds__(kSkThreads, 1)
+__global__ void __launch_bounds__(kSkThreads, 2)
 sinkhorn_peer_kernel(const float* __restrict__ M, long long n, double n_total, int k, float* __restrict__ g_io,
                      SkStages stages, SkWorkspace* ws, SkPeers peers, int rank, int world, unsigned long long call_base,
                      int stride) {
@@ -910,7 +913,18 @@ extern "C" int ure_sinkhorn(const float* d_M, int64_t n, int k, int kpad, float*
     // read from HBM once for ALL iterations, an iteration costs a shared-memory sweep + one grid barrier
     URE_KPAD_SWITCH(kpad, return (launch_sinkhorn<KP, true>(d_M, n, k, d_g, stg, ws, grid, need, st)));
   }
-  (void)parts;
+  {
+    // large problem, one persistent launch (two CTAs per SM, one grid barrier per iteration); URE_SK_PERSIST=0: the
+    // split-phase kernels below (two launches per iteration)
+    static const int persist = getenv("URE_SK_PERSIST") ? atoi(getenv("URE_SK_PERSIST")) : 0;
+    if (persist) {
+      int occ = 1;
+      URE_KPAD_SWITCH(kpad, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (sinkhorn_kernel<KP, false>), kSkThreads, parts));
+      if (occ < 1) occ = 1;
+      if (occ > 2) occ = 2;
+      URE_KPAD_SWITCH(kpad, return (launch_sinkhorn<KP, false>(d_M, n, k, d_g, stg, ws, grid * occ, parts, st)));
+    }
+  }
   // large problem: one streaming pass per iteration at full occupancy (split-phase kernels, no host sync;
   // the early exit needs the column sums on the host, so every scheduled iteration runs)
   for (int s = 0; s < n_stages; ++s)

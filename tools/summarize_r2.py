@@ -29,14 +29,15 @@ def raw(rep):
     return rows[0], rows[1], rows[2:]
 
 
-def summarize_rep(name, title, command):
+def summarize_rep(name, title, command, out=None, mode="w"):
     rep = os.path.join(GO, name + ".ncu-rep")
     if not os.path.exists(rep):
         return
     hdr, units, rows = raw(rep)
     ki = hdr.index("Kernel Name")
-    with open(os.path.join(OUT, name.replace("r2b_", "r2_").replace("r2c_", "r2_").replace("r2d_", "r2_").replace("r2e_", "r2_")
-                           .replace("r2f_", "r2_") + "_ncu.txt"), "w") as f:
+    import re
+    out = out or re.sub(r"^r2[a-z0-9]*_", "r2_", name) + "_ncu.txt"
+    with open(os.path.join(OUT, out), mode) as f:
         f.write(f"# {title}\n# {command}\n# ncu --set full --clock-control none (cold caches, kernel replay): shares and ratios, not bench times\n")
         for r in rows:
             f.write(f"\n== {r[ki][:150]}\n")
@@ -84,5 +85,13 @@ if __name__ == "__main__":
                   "python tools/prof_ot.py --n 1000000 --k 8 --d 64 --reps 1 --iters 2")
     summarize_rep("r2d_ot32", "cost_tma_kernel + colsum_kernel<32> BEFORE the full-wave grid fix, n=1M k=32 d=64",
                   "python tools/prof_ot.py --n 1000000 --k 32 --d 64 --reps 1 --iters 2")
-    summarize_rep("r2f_ot", "cost_ws_kernel<64> + colsum_kernel<8>, n=1M k=8 d=64",
+    summarize_rep("r2f_ot", "cost_ws_kernel<64> (FIRST warp-specialised version: shared-memory atomics in the lo pass) + colsum_kernel<8>, n=1M k=8 d=64",
                   "python tools/prof_ot.py --n 1000000 --k 8 --d 64 --reps 1 --iters 2")
+    summarize_rep("r2i_sched", "owner_schedule_kernel (general pre-pass, start of the session), C2 step",
+                  "python bench.py --steps 1 --warmup 3 --no-cpu --no-extra", out="r2_sched_ncu.txt")
+    summarize_rep("r2k_sched", "owner_schedule_tab_kernel<4> (short-epoch pre-pass), C2 step",
+                  "python bench.py --steps 1 --warmup 3 --no-cpu --no-extra", out="r2_sched_ncu.txt", mode="a")
+    summarize_rep("r2z_cost", "cost_ws_kernel<64> (final), n=10M k=8 d=64",
+                  "python tools/prof_ot.py --n 10000000 --k 8 --d 64 --reps 1 --iters 2", out="r2_cost_final_ncu.txt")
+    summarize_rep("r2z_owner", "mf_owner_kernel<16> + owner_schedule_tab_kernel<4> (final), C2 step",
+                  "python bench.py --steps 1 --warmup 3 --no-cpu --no-extra", out="r2_owner_final_ncu.txt")

@@ -235,6 +235,11 @@ SINKHORN_SCHEDULE = ((1.0, 10), (0.3, 20), (0.1, 30), (0.03, 60), (0.01, 120))
 # A stage ends early once the relative column-marginal error max_j |colsum_j*k - 1| drops below this; the
 # fixed schedule itself only reaches ~3e-5 at its last stage, so nothing is lost.
 SINKHORN_TOL = 2e-5
+# With the balanced rounding behind it Sinkhorn only has to get the group sizes NEAR n/k: whatever the potentials, the
+# argmax labels are the minimum-cost assignment for their own sizes, and the rounding moves the surplus users along
+# shortest augmenting paths to the exact balanced optimum.  Measured at ml1m size (tools/prof_ot_small.py): the same
+# labels for every tolerance from 2e-5 to 1e-2, 8.9 -> 5.9 ms for the ten outer iterations at 1e-3.
+SINKHORN_TOL_BALANCED = 1e-3
 # Outer iterations after the first start from the previous potentials (the fixed point at a given eps does
 # not depend on the start) and run only the last WARM_STAGES stages of the schedule.  The column sums are kept in
 # the log domain (csrc/ot_sinkhorn.cu), so potentials that are stale by hundreds of eps after a large centroid move
@@ -245,7 +250,7 @@ BALANCE_MAX_AUGMENTATIONS = 1 << 14
 
 
 def ot_cluster_device(X, k, max_iters=10, schedule=SINKHORN_SCHEDULE, centroid0=None, device=None, dist=None,
-                      tol=SINKHORN_TOL, warm_start=True, balance=True):
+                      tol=None, warm_start=True, balance=True):
     """Balanced OT clustering on the GPU; returns (inertia, label int64 ndarray, centroid, n_outer).
 
     Per outer iteration (reference utils.py:635-654): cost matrix (tcgen05), Sinkhorn potentials, argmax labels,
@@ -274,6 +279,8 @@ def ot_cluster_device(X, k, max_iters=10, schedule=SINKHORN_SCHEDULE, centroid0=
     Xp[:, :d] = X
     Xd = kn.upload_table(Xp, dev)
     balance = balance and not sharded and 1 < k <= 128
+    if tol is None:
+        tol = SINKHORN_TOL_BALANCED if balance else SINKHORN_TOL
     label = None
     g = None
     inertia = 0.0

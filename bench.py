@@ -321,18 +321,24 @@ def run_c2_ours(args):
         tl = loaders("unlearn_train")                                        # fresh: records are packed + uploaded
         tdl = [loadData(RatingData(t), BATCH, 1, False) for t in test_all]
         tdata = loadData(RatingData(test_np), BATCH, 1, False)
+        t1 = time.perf_counter()
         un = new_sisa()
+        t2 = time.perf_counter()
         ms_out = un.unlearn(model_list, tl, tdl, tdata, list(del_user), 0, "")
+        t3 = time.perf_counter()
         # results to the host: the merged user table and this rank's item tables, one pinned transfer
         res_h = kn.download_many([ms_out[0].user_mat.weight.data] +
-                                 [m.item_mat.weight.data for m in ms_out if getattr(m, "item_mat", None) is not None])
+                                 [m.item_mat.weight.data for m in ms_out if getattr(m, "item_mat", None) is not None],
+                                 copy=False)
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) * 1e3
+        e2e_parts = {"loaders_ms": (t1 - t0) * 1e3, "new_sisa_ms": (t2 - t1) * 1e3, "unlearn_ms": (t3 - t2) * 1e3,
+                     "results_to_host_ms": dt - (t3 - t0) * 1e3}
         d2h = sum(x.size * 4 for x in res_h) + 24
         if it >= args.warmup:
             e2e_ms.append(d.max_float(dt))
     if os.environ.get("URE_BENCH_DEBUG"):
-        print(f"[rank {rank}] e2e ms per step: {np.round(e2e_ms, 2).tolist()}; last: {un.timing}", file=sys.stderr)
+        print(f"[rank {rank}] e2e ms per step: {np.round(e2e_ms, 2).tolist()}; last: {e2e_parts} {un.timing}", file=sys.stderr)
     e2e_value = inter_total / (float(np.mean(e2e_ms)) / 1e3)
 
     line = {
@@ -372,6 +378,10 @@ def run_c2_ours(args):
             modes[mode] = {"ms": float(min(ts)), "total_rmse": float(un_m.final_log["total_rmse"])}
         line["epoch_eval_modes"] = modes
         line["c4_strong"] = shard_training_leg("c4", d, dev, steps=100, reps=2)
+        line["c3_strong"] = shard_training_leg("c3", d, dev, reps=2)
+        # the C5 Sinkhorn sweep at this N (no CPU legs here: `--config c5` times the float64 NumPy Sinkhorn beside it)
+        line["c5_sweep"] = [{k_: e[k_] for k_ in ("n", "k", "us_per_iter", "hbm_frac_per_gpu", "cost_matrix_ms", "cost_hbm_frac")}
+                            for e in c5_sweep(d, dev, cpu=False)]
     if world > 1 and not args.no_extra:
         line["ot_sharded"] = ot_sharded_leg(d, dev)
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -570,6 +580,14 @@ def shard_training_leg(name, d_, dev, steps=None, reps=3, mode="auto", e2e=False
     rank, world = d_.rank, d_.world
     mine = [s for s in range(K) if s % world == rank]
     rows_u, n_shard = U // K, N // K
+    if mode == "auto" and (rows_u + I) <= 8 * B:
+        # tables of the size of a batch: the owner schedule (rows resident in the SMs' shared memory) beats the dense
+        # one whenever a launch's rows fit -- launch as many shards together as do (c3: ONE 22 MB shard at a time:
+        # 2.5 G interactions/s against 2.0 for eight shards in one dense launch)
+        from ultrare_b200 import _lib
+        budget = int(_lib.lib().ure_mf_grid_size()) * (200 << 10)
+        fit = max(1, budget // ((rows_u + I) * 8 * d))
+        R = min(R, fit)
     rounds = [mine[x:x + R] for x in range(0, len(mine), R)]
     times, inter_local, mode_used, mem = [], 0, None, 0
     for rep in range(reps):
@@ -605,10 +623,10 @@ def shard_training_leg(name, d_, dev, steps=None, reps=3, mode="auto", e2e=False
     peak, _ = measured_peaks()
     alg = inter * A_MF(d)
     return {"workload": f"{name}: {U} users x {I} items, {N} interactions, d={d}, K={K} shards, batch {B}; {steps} global "
-                        f"steps of every shard, {R} shards per launch", "scaling": "strong", "n_gpus": world,
+                        f"steps of every shard, {R} shard(s) per launch", "scaling": "strong", "n_gpus": world,
             "shards_per_gpu": len(mine), "schedule": mode_used, "interactions": int(inter), "ms": ms,
             "value": inter / ms * 1e3, "unit": UNIT, "interactions_per_s_per_gpu": inter / ms * 1e3 / world,
-            "roofline_frac_per_gpu": alg / ms / 1e6 / world / peak, "mem_GB": mem,
+            "roofline_frac_per_gpu": alg / ms / 1e6 / world / peak, "mem_GB": mem, "launches_per_pass": len(rounds),
             "data": "synthetic, generated on the device (no host copy of 1 B interactions)"}
 
 
@@ -634,7 +652,7 @@ def run_shards_ours(args):
             "roofline": {"bound": "hbm", "kernel": f"mf_train ({leg['schedule']})", "achieved": leg["roofline_frac_per_gpu"] * peak,
                          "peak": peak, "unit": "GB/s", "frac": leg["roofline_frac_per_gpu"], "traffic": None,
                          "peak_source": src},
-            "e2e": None, "gpu_launches": args.steps * (-(-(K // d_.world) // R)), "detail": leg}
+            "e2e": None, "gpu_launches": args.steps * leg["launches_per_pass"], "detail": leg}
     if d_.rank == 0:
         print(json.dumps(line))
 
@@ -654,15 +672,39 @@ def c5_inputs(n_local, k, d, seed):
 
 def run_c5_ours(args):
     import torch
-    from ultrare_b200 import dist as udist, kernels as kn
+    from ultrare_b200 import dist as udist
     d_ = udist.init_from_env()
     rank, world = d_.rank, d_.world
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
     torch.cuda.set_device(dev)
     peak, src = measured_peaks()
-    iters, d = 100, 64
+    iters = 100
+    out = c5_sweep(d_, dev, cpu=not args.no_cpu, iters=iters)
+    if rank == 0:
+        big = out[3]
+        print(json.dumps({"metric": "sinkhorn_iterations_per_s (OT grouping sweep, c5)", "value": 1e6 / big["us_per_iter"],
+                          "unit": "iterations/s", "n_gpus": world, "steps": iters, "warmup": 1,
+                          "ms_per_step": big["us_per_iter"] / 1e3, "higher_is_better": True, "scaling": "strong",
+                          "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": "c5: Sinkhorn sweep n in {1M,10M} x k in {8,32,128}, d=64, 100 "
+                                                 "iterations at eps = 0.05 x mean nearest-centroid cost; headline = "
+                                                 "n=10M, k=8", "parallelism": f"users row-sharded x{world}",
+                                     "l2": "cost matrix larger than L2 at every point but n=1M, k=8 per 8 GPUs"},
+                          "roofline": {"bound": "hbm", "kernel": "sinkhorn column pass", "frac": big["hbm_frac_per_gpu"],
+                                       "achieved": big["hbm_frac_per_gpu"] * peak, "peak": peak, "unit": "GB/s",
+                                       "traffic": None, "peak_source": src},
+                          "e2e": None, "gpu_launches": iters, "sweep": out}))
+
+
+def c5_sweep(d_, dev, cpu=False, iters=100, d=64, points=None):
+    """The C5 points at this run's N: users row-sharded over the ranks, cost matrix + `iters` Sinkhorn iterations
+    (single GPU: ure_sinkhorn; N > 1: the peer-memory kernel), whole-job time = max over ranks."""
+    import torch
+    from ultrare_b200 import kernels as kn
+    rank, world = d_.rank, d_.world
+    peak, _ = measured_peaks()
     out = []
-    for n, k in C5_POINTS:
+    for n, k in (C5_POINTS if points is None else points):
         lo, hi = d_.row_block(n)
         X, cen = c5_inputs(hi - lo, k, d, 100 + rank)
         torch.manual_seed(5)
@@ -700,25 +742,12 @@ def run_c5_ours(args):
                  "cost_matrix_ms": cost_ms, "cost_GBps": (4.0 * n_loc * d + 4.0 * n_loc * kp) / (cost_ms / 1e3) / 1e9,
                  "cost_hbm_frac": (4.0 * n_loc * d + 4.0 * n_loc * kp) / (cost_ms / 1e3) / 1e9 / peak,
                  "cost_tflops": 2.0 * n_loc * kp * d / (cost_ms / 1e3) / 1e12}
-        if rank == 0 and not args.no_cpu:
+        if rank == 0 and cpu:
             entry["cpu_float64_sinkhorn"] = c5_cpu_leg(X, C0, eps, iters, n if world == 1 else None)
         out.append(entry)
         del X, M
         torch.cuda.empty_cache()
-    if rank == 0:
-        big = out[3]
-        print(json.dumps({"metric": "sinkhorn_iterations_per_s (OT grouping sweep, c5)", "value": 1e6 / big["us_per_iter"],
-                          "unit": "iterations/s", "n_gpus": world, "steps": iters, "warmup": 1,
-                          "ms_per_step": big["us_per_iter"] / 1e3, "higher_is_better": True, "scaling": "strong",
-                          "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                          "config": {"workload": "c5: Sinkhorn sweep n in {1M,10M} x k in {8,32,128}, d=64, 100 "
-                                                 "iterations at eps = 0.05 x mean nearest-centroid cost; headline = "
-                                                 "n=10M, k=8", "parallelism": f"users row-sharded x{world}",
-                                     "l2": "cost matrix larger than L2 at every point but n=1M, k=8 per 8 GPUs"},
-                          "roofline": {"bound": "hbm", "kernel": "sinkhorn column pass", "frac": big["hbm_frac_per_gpu"],
-                                       "achieved": big["hbm_frac_per_gpu"] * peak, "peak": peak, "unit": "GB/s",
-                                       "traffic": None, "peak_source": src},
-                          "e2e": None, "gpu_launches": iters, "sweep": out}))
+    return out
 
 
 def c5_cpu_leg(X, C0, eps, iters, n_full, budget_s=20.0):

@@ -147,6 +147,10 @@ typedef struct ure_mf_runs_s {
 const char* ure_last_error(void);
 int ure_abi_version(void);
 
+/* Asynchronous copy of `bytes` from device memory to PAGE-LOCKED host memory on `stream` (results of a pass:
+ * user_mat / item_mat tables, method/scratch.py:131-144 -- one call per contiguous run of tables). */
+int ure_copy_to_host_async(void* h_dst, const void* d_src, int64_t bytes, void* stream);
+
 /* Bytes of device scratch ure_mf_train needs (grid barrier + step tables). */
 int64_t ure_mf_train_workspace_bytes(void);
 

@@ -83,6 +83,7 @@ SIGNATURES = {
     "ure_mf_runs_flush": (C.c_int, [_p, C.c_int, C.POINTER(MFHParams), C.c_int, _i64, _p]),
     "ure_mf_train_trace": (C.c_int, [_p, _p, C.c_int, _p]),
     "ure_mf_grid_size": (C.c_int, []),
+    "ure_copy_to_host_async": (C.c_int, [_p, _p, _i64, _p]),
     "ure_mf_debug_flags": (C.c_int, [_p, C.c_uint32, _p]),
     "ure_mf_flush": (C.c_int, [C.POINTER(MFShard), C.c_int, C.POINTER(MFHParams), C.c_int, _i64, _p]),
     "ure_ensemble_score": (C.c_int, [_p, _p, C.c_int, C.c_int, _p, _i64, _f32, _p, _p, _p]),

@@ -66,3 +66,13 @@ extern "C" int ure_host_stage_copy(void* dst, const void* src, int64_t bytes) {
   _mm_sfence();
   return 0;
 }
+
+// Asynchronous device -> page-locked host copy on the caller's stream (the host mirror's result read-back: one call
+// per contiguous run instead of one framework dispatch per tensor).
+extern "C" int ure_copy_to_host_async(void* h_dst, const void* d_src, int64_t bytes, void* stream) {
+  using namespace ure;
+  URE_REQUIRE(bytes >= 0 && (bytes == 0 || (h_dst && d_src)), URE_EINVAL, "ure_copy_to_host_async: bad argument");
+  if (bytes == 0) return 0;
+  URE_CUDA(cudaMemcpyAsync(h_dst, d_src, (size_t)bytes, cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)));
+  return 0;
+}

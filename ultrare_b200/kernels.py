@@ -26,6 +26,18 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+_SIDE_STREAMS = {}
+
+
+def side_stream(device) -> "torch.cuda.Stream":
+    """One extra stream per device for uploads that must not queue behind a long kernel on the caller's stream."""
+    dev = torch.device(device)
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    if idx not in _SIDE_STREAMS:
+        _SIDE_STREAMS[idx] = torch.cuda.Stream(device=idx)
+    return _SIDE_STREAMS[idx]
+
+
 def _need_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
@@ -172,6 +184,14 @@ def upload_interactions_many(raws, device, row_of: Optional[torch.Tensor] = None
         t = torch.from_numpy(arrs[j]) if arrs[j].flags.writeable else None
         if t is not None and t.is_pinned():
             pinned[j] = t.view(-1)
+    # arrays that already live in page-locked memory need no staging copy: their upload + pack are queued right here
+    # (defer or not), so the DMA engine starts while the caller still does its host-side set-up
+    shipped = set()
+    with torch.cuda.device(dev):
+        for j in todo:
+            if pinned[j] is not None:
+                ship(j)
+                shipped.add(j)
     futs = None
     if n_tot >= (1 << 16):
         # staging copies on worker threads (ctypes releases the GIL); every array is shipped as soon as ITS
@@ -182,9 +202,9 @@ def upload_interactions_many(raws, device, row_of: Optional[torch.Tensor] = None
     def finish():
         with torch.cuda.device(dev):
             for j in todo:
-                if pinned[j] is not None:
-                    pass
-                elif futs is None:
+                if j in shipped:
+                    continue
+                if futs is None:
                     fill(j, 0, 24 * ns[j])
                 else:
                     for f in futs[j]:
@@ -292,26 +312,43 @@ def remap_users(inter: torch.Tensor, row_of: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def download_many(tensors: Sequence[torch.Tensor]) -> List[np.ndarray]:
+def download_many(tensors: Sequence[torch.Tensor], copy: bool = True) -> List[np.ndarray]:
     """Device tensors -> host arrays through ONE pinned staging buffer and ONE synchronisation (a `.cpu()` per
-    tensor is a pageable copy + a synchronisation each)."""
+    tensor is a pageable copy + a synchronisation each).  Tensors that lie back to back in device memory (the tables
+    of a batch arena) travel as one transfer.  copy=False: the arrays are views of a page-locked buffer of their own
+    (no second pass over the bytes on the host); it stays alive as long as any of them does."""
     if not tensors:
         return []
     dev = tensors[0].device
+    tensors = [t.contiguous() for t in tensors]
     sizes = [t.numel() * t.element_size() for t in tensors]
-    offs = np.concatenate([[0], np.cumsum([(b + 63) // 64 * 64 for b in sizes])]).astype(np.int64)
-    stage = _staging_bytes(int(offs[-1]) + 64)
-    with torch.cuda.device(dev):
-        for t, o, b in zip(tensors, offs[:-1], sizes):
+    offs, runs, o = [], [], 0                # runs: (device address, staging offset, bytes) of every transfer
+    for t, b in zip(tensors, sizes):
+        if runs and b and t.data_ptr() == runs[-1][0] + runs[-1][2]:
+            offs.append(runs[-1][1] + runs[-1][2])
+            runs[-1] = (runs[-1][0], runs[-1][1], runs[-1][2] + b)
+            o = runs[-1][1] + runs[-1][2]
+        else:
+            o = (o + 63) // 64 * 64
+            offs.append(o)
             if b:
-                stage[int(o):int(o) + b].copy_(t.contiguous().view(-1).view(torch.uint8), non_blocking=True)
+                runs.append((t.data_ptr(), o, b))
+            o += b
+    total = o + 64
+    stage = _staging_bytes(total) if copy else torch.empty(total, dtype=torch.uint8, pin_memory=True)
+    with torch.cuda.device(dev):
+        for src, so, b in runs:         # raw async copies: a torch copy_ per tensor costs ~20 us of dispatch each
+            check(_lib.lib().ure_copy_to_host_async(C.c_void_p(stage.data_ptr() + so), C.c_void_p(src), b, _stream()),
+                  "ure_copy_to_host_async")
         ev = torch.cuda.Event()
         ev.record()
         ev.synchronize()
     host = stage.numpy()
-    outs = [host[int(o):int(o) + b].view(np.dtype(str(t.dtype).replace("torch.", ""))).reshape(tuple(t.shape)).copy()
-            for t, o, b in zip(tensors, offs[:-1], sizes)]
-    _PINNED_BYTES.setdefault(stage.shape[0], []).append((stage, None))
+    outs = [host[int(o_):int(o_) + b].view(np.dtype(str(t.dtype).replace("torch.", ""))).reshape(tuple(t.shape))
+            for t, o_, b in zip(tensors, offs, sizes)]
+    if copy:
+        outs = [x.copy() for x in outs]
+        _PINNED_BYTES.setdefault(stage.shape[0], []).append((stage, None))
     return outs
 
 

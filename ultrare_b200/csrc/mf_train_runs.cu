@@ -25,6 +25,10 @@
 #include "common.cuh"
 #include "feistel.cuh"
 
+#ifndef URE_RUNS_STCS
+#define URE_RUNS_STCS 0
+#endif
+
 namespace ure {
 namespace {
 
@@ -387,8 +391,16 @@ mf_runs_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams_
         w_own.z = fmaf(nlr, b_own.z, w_own.z); w_own.w = fmaf(nlr, b_own.w, w_own.w);
         float* dst = S_own + ((long long)(cur_slot ^ 1) * rows_own + cur_row) * 2 * D;
         if (act) {
+#if URE_RUNS_STCS
+          // experiment (tools/build_variant.sh, -DURE_RUNS_STCS=1): the new version is not read again before the
+          // next step, so streaming stores could leave L2 to the rows of THIS step (each is read twice: by its owner
+          // and by the other side's gather).  Measured SLOWER: 0.66 -> 0.48 G interactions/s on one GPU's share of C4.
+          __stcs(reinterpret_cast<float4*>(dst) + lane, w_own);
+          __stcs(reinterpret_cast<float4*>(dst + D) + lane, b_own);
+#else
           __stcg(reinterpret_cast<float4*>(dst) + lane, w_own);
           __stcg(reinterpret_cast<float4*>(dst + D) + lane, b_own);
+#endif
         }
         __syncwarp();
         if (lane == 0) {

@@ -295,6 +295,24 @@ int ure_score_finalize(const float* d_sum, const ure_inter_t* d_inter, int64_t n
 int ure_rank_metrics(const ure_inter_t* d_inter, const float* d_score, const int32_t* d_order,
                      const int64_t* d_seg, int64_t n_seg, double* d_out, void* stream);
 
+/* Many evaluations in ONE pair of launches (grid.y = job): the per-epoch in-training evaluations of
+ * method/scratch.py:83-97 (two baseTest calls per shard and epoch).  Every job is what ure_ensemble_score +
+ * ure_rank_metrics do for one (model list, test set): out[0] += sum of squared errors, out[1..3] += (sum NDCG@10,
+ * sum HR@10, users).  score: n floats of scratch per job.  max_n / max_seg: the largest n / n_seg of the jobs. */
+typedef struct {
+  const float* const* P;   /* DEVICE table of n_models user-table pointers                                   */
+  const float* const* Q;   /* DEVICE table of n_models item-table pointers                                   */
+  const ure_inter_t* inter;
+  const int32_t* order;    /* as ure_rank_metrics (or NULL)                                                  */
+  const int64_t* seg;      /* [n_seg + 1]                                                                    */
+  float* score;            /* [n] scratch                                                                    */
+  double* out;             /* [4], zero on entry                                                             */
+  int64_t n, n_seg;
+  int32_t n_models;
+  float denom;             /* usually n_models                                                               */
+} ure_eval_job_t;
+int ure_eval_jobs(const ure_eval_job_t* d_jobs, int n_jobs, int d, int64_t max_n, int64_t max_seg, void* stream);
+
 /* Data ingest (what RatingData.__init__ + __getitem__ do on the host, read.py:111-113,118-124): the float64
  * [3, n] array readRating hands over (rows: user id, item id, rating / max_rating; row stride ld elements),
  * already on the device, becomes packed records: user = int(u) -- or d_row_of[int(u)], the row inside a

@@ -225,6 +225,38 @@ def test_rank_metrics_edge_cases(cuda_dev):
     assert empty.cpu().numpy().tolist() == [0.0, 0.0, 0.0]
 
 
+def test_eval_jobs_equal_single_calls(cuda_dev):
+    """ure_eval_jobs (many evaluations, grid.y = job) = ure_ensemble_score + ure_rank_metrics per job: different model
+    counts, test sets of different sizes (one empty-segment user, one shuffled set with the order indirection)."""
+    torch = _torch()
+    from ultrare_b200 import kernels as kn
+    rng = np.random.default_rng(11)
+    U, I, d = 70, 50, 16
+    tabs = [(torch.tensor(rng.standard_normal((U, d), dtype=np.float32), device=cuda_dev),
+             torch.tensor(rng.standard_normal((I, d), dtype=np.float32), device=cuda_dev)) for _ in range(4)]
+    sets = []
+    for n, shuffle in ((4000, False), (900, True), (37, False)):
+        u = np.sort(rng.integers(0, U - 1, n))                       # user U-1 has no test rows
+        if shuffle:
+            u = rng.permutation(u)
+        i = rng.integers(0, I, n)
+        r = (rng.integers(1, 6, n) / 5).astype(np.float32)
+        inter = kn.pack_interactions(u, i, r, cuda_dev)
+        order, seg = kn.user_segments(u)
+        sets.append((inter, None if order is None else torch.tensor(order, device=cuda_dev), torch.tensor(seg, device=cuda_dev)))
+    jobs, want = [], []
+    for ms in ([0], [0, 1, 2], [3, 1], [2]):
+        for inter, order, seg in sets:
+            Ps, Qs = [tabs[m][0] for m in ms], [tabs[m][1] for m in ms]
+            jobs.append((Ps, Qs, inter, order, seg))
+            score, sse = kn.ensemble_score(Ps, Qs, inter)
+            want.append(torch.cat([sse, kn.rank_metrics(inter, score, seg, order)]).cpu().numpy())
+    got = kn.eval_jobs(jobs, d).cpu().numpy()
+    want = np.stack(want)
+    assert got.shape == want.shape == (12, 4)
+    np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-12)
+
+
 def test_rank_metrics_long_segments(cuda_dev):
     """Segments far longer than a warp (several elements per lane in the staged arg-max rounds) and longer than the
     shared-memory stage (the counting-rank path), with heavily tied scores and ratings, in user order and through

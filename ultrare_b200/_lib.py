@@ -44,6 +44,12 @@ class MFRuns(C.Structure):
     _fields_ = [(nm, _p) for nm in ("slotP", "slotQ", "metaP", "metaQ", "list_u", "list_i", "loff_u", "loff_i")]
 
 
+class EvalJob(C.Structure):
+    """ure_eval_job_t"""
+    _fields_ = [("P", _p), ("Q", _p), ("inter", _p), ("order", _p), ("seg", _p), ("score", _p), ("out", _p),
+                ("n", _i64), ("n_seg", _i64), ("n_models", _i32), ("denom", _f32)]
+
+
 class MFBatchShard(C.Structure):
     """ure_mf_batch_shard_t"""
     _fields_ = [("inter", _p), ("perm", _p), ("n", _i32), ("n_user", _i32), ("shard_id", _i32), ("group", _i32)]
@@ -89,6 +95,7 @@ SIGNATURES = {
     "ure_ensemble_score": (C.c_int, [_p, _p, C.c_int, C.c_int, _p, _i64, _f32, _p, _p, _p]),
     "ure_score_finalize": (C.c_int, [_p, _p, _i64, _f32, _p, _p, _p]),
     "ure_rank_metrics": (C.c_int, [_p, _p, _p, _p, _i64, _p, _p]),
+    "ure_eval_jobs": (C.c_int, [_p, C.c_int, C.c_int, _i64, _i64, _p]),
     "ure_pack_interactions_f64": (C.c_int, [_p, _i64, _i64, _p, _i32, _p, _p]),
     "ure_partition_blocks": (C.c_int, []),
     "ure_partition_interactions": (C.c_int, [_p, _i64, _i64, _i64, _f64, _p, _p, _i32, C.c_int, _p, _p, _p, _p]),

@@ -12,10 +12,9 @@ namespace {
 // sisa.py:57-58) the user row stays in registers.
 // ---------------------------------------------------------------------------
 template <int D>
-__global__ void __launch_bounds__(256)
-ensemble_score_kernel(const float* const* __restrict__ Pk, const float* const* __restrict__ Qk, int K,
-                      const ure_inter_t* __restrict__ inter, long long n, float denom,
-                      float* __restrict__ score, double* __restrict__ sse) {
+__device__ __forceinline__ void ensemble_score_body(const float* const* __restrict__ Pk, const float* const* __restrict__ Qk,
+                                                    int K, const ure_inter_t* __restrict__ inter, long long n, float denom,
+                                                    float* __restrict__ score, double* __restrict__ sse) {
   constexpr int G = D / 4;
   const int lane = threadIdx.x & 31;
   const int gl = lane % G;
@@ -70,6 +69,23 @@ ensemble_score_kernel(const float* const* __restrict__ Pk, const float* const* _
   }
 }
 
+template <int D>
+__global__ void __launch_bounds__(256)
+ensemble_score_kernel(const float* const* __restrict__ Pk, const float* const* __restrict__ Qk, int K,
+                      const ure_inter_t* __restrict__ inter, long long n, float denom,
+                      float* __restrict__ score, double* __restrict__ sse) {
+  ensemble_score_body<D>(Pk, Qk, K, inter, n, denom, score, sse);
+}
+
+// many evaluations in one launch (blockIdx.y = job): the per-epoch in-training evaluations of scratch.py:83-97
+template <int D>
+__global__ void __launch_bounds__(256)
+ensemble_score_jobs_kernel(const ure_eval_job_t* __restrict__ jobs) {
+  const ure_eval_job_t jb = jobs[blockIdx.y];
+  if (jb.n <= 0) return;
+  ensemble_score_body<D>(jb.P, jb.Q, jb.n_models, jb.inter, jb.n, jb.denom, jb.score, jb.out);
+}
+
 // ---------------------------------------------------------------------------
 // HR@10 / NDCG@10 per user segment, one warp per user (utils.py:166-181).
 //   rank_v(e) = #{e' : v(e') > v(e) or (v(e') == v(e) and e' > e)}   ("later index first")
@@ -87,10 +103,9 @@ __constant__ double kDcgWeight[URE_TOP_K] = {1.0, 1.0, 0.6309297535714575, 0.5, 
                                              0.31546487678572877, 0.3010299956639812};
 constexpr double kIdcg = 5.254494511770457;
 
-__global__ void __launch_bounds__(256)
-rank_metrics_kernel(const ure_inter_t* __restrict__ inter, const float* __restrict__ score,
-                    const int32_t* __restrict__ order, const long long* __restrict__ seg, long long n_seg,
-                    double* __restrict__ out) {
+__device__ __forceinline__ void rank_metrics_body(const ure_inter_t* __restrict__ inter, const float* __restrict__ score,
+                                                  const int32_t* __restrict__ order, const long long* __restrict__ seg,
+                                                  long long n_seg, double* __restrict__ out) {
   __shared__ int top_pred[8][URE_TOP_K];
   __shared__ int top_rating[8][URE_TOP_K];
   __shared__ float2 s_vt[8][kSegStage];
@@ -191,6 +206,20 @@ rank_metrics_kernel(const ure_inter_t* __restrict__ inter, const float* __restri
 }
 
 __global__ void __launch_bounds__(256)
+rank_metrics_kernel(const ure_inter_t* __restrict__ inter, const float* __restrict__ score,
+                    const int32_t* __restrict__ order, const long long* __restrict__ seg, long long n_seg,
+                    double* __restrict__ out) {
+  rank_metrics_body(inter, score, order, seg, n_seg, out);
+}
+
+__global__ void __launch_bounds__(256)
+rank_metrics_jobs_kernel(const ure_eval_job_t* __restrict__ jobs) {
+  const ure_eval_job_t jb = jobs[blockIdx.y];
+  if (jb.n_seg <= 0 || jb.n <= 0) return;
+  rank_metrics_body(jb.inter, jb.score, jb.order, reinterpret_cast<const long long*>(jb.seg), jb.n_seg, jb.out + 1);
+}
+
+__global__ void __launch_bounds__(256)
 score_finalize_kernel(const float* __restrict__ sum, const ure_inter_t* __restrict__ inter, long long n, float denom,
                       float* __restrict__ score, double* __restrict__ sse) {
   double acc = 0.0;
@@ -267,6 +296,39 @@ extern "C" int ure_rank_metrics(const ure_inter_t* d_inter, const float* d_score
   if (blocks > cap) blocks = cap;
   rank_metrics_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       d_inter, d_score, d_order, reinterpret_cast<const long long*>(d_seg), n_seg, d_out);
+  URE_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int ure_eval_jobs(const ure_eval_job_t* d_jobs, int n_jobs, int d, int64_t max_n, int64_t max_seg,
+                             void* stream) {
+  using namespace ure;
+  URE_REQUIRE(d_jobs && n_jobs >= 0 && n_jobs <= 65535 && max_n >= 0 && max_seg >= 0, URE_EINVAL,
+              "ure_eval_jobs: bad argument (n_jobs=%d)", n_jobs);
+  if (n_jobs == 0 || max_n == 0) return 0;
+  auto st = static_cast<cudaStream_t>(stream);
+  // a full wave of CTAs over all jobs together: few blocks per job when there are many jobs
+  auto blocks_for = [&](long long want) {
+    long long per_job = ((long long)num_sms() * 8 + n_jobs - 1) / n_jobs;
+    if (per_job < 1) per_job = 1;
+    return (unsigned)(want < per_job ? (want < 1 ? 1 : want) : per_job);
+  };
+  {
+    const int G = d / 4;
+    URE_REQUIRE(d == 8 || d == 16 || d == 32 || d == 64 || d == 128, URE_EUNSUPPORTED, "ure_eval_jobs: d=%d not in {8,16,32,64,128}", d);
+    const dim3 grid(blocks_for((max_n + 256 / G - 1) / (256 / G)), (unsigned)n_jobs);
+    switch (d) {
+      case 8: ensemble_score_jobs_kernel<8><<<grid, 256, 0, st>>>(d_jobs); break;
+      case 16: ensemble_score_jobs_kernel<16><<<grid, 256, 0, st>>>(d_jobs); break;
+      case 32: ensemble_score_jobs_kernel<32><<<grid, 256, 0, st>>>(d_jobs); break;
+      case 64: ensemble_score_jobs_kernel<64><<<grid, 256, 0, st>>>(d_jobs); break;
+      default: ensemble_score_jobs_kernel<128><<<grid, 256, 0, st>>>(d_jobs); break;
+    }
+  }
+  if (max_seg > 0) {
+    const dim3 grid(blocks_for((max_seg + 7) / 8), (unsigned)n_jobs);
+    rank_metrics_jobs_kernel<<<grid, 256, 0, st>>>(d_jobs);
+  }
   URE_CUDA(cudaGetLastError());
   return 0;
 }

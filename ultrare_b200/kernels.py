@@ -1076,6 +1076,41 @@ def user_segments_device(inter: torch.Tensor, n_user: int):
     return order, seg
 
 
+def eval_jobs(jobs, d: int) -> torch.Tensor:
+    """Many baseTest evaluations in one pair of launches (ure_eval_jobs).  jobs: list of (P_list, Q_list, inter, order
+    or None, seg) -- device tensors; the ensemble mean divides by len(P_list).  Returns fp64 [n_jobs, 4] on the device:
+    (sum of squared errors, sum NDCG@10, sum HR@10, users) per job, no synchronisation."""
+    if not jobs:
+        return torch.zeros((0, 4), dtype=torch.float64)
+    dev = jobs[0][2].device
+    ns = [int(j[2].shape[0]) for j in jobs]
+    out = torch.zeros((len(jobs), 4), dtype=torch.float64, device=dev)
+    score = torch.empty(max(1, sum(ns)), dtype=torch.float32, device=dev)
+    ptrs = []
+    for P_list, Q_list, *_ in jobs:
+        assert len(P_list) == len(Q_list) >= 1
+        ptrs += [t.data_ptr() for t in P_list] + [t.data_ptr() for t in Q_list]
+    tab = upload_array(np.asarray(ptrs, dtype=np.int64), dev)
+    arr = (_lib.EvalJob * len(jobs))()
+    o = so = 0
+    for x, (P_list, Q_list, inter, order, seg) in enumerate(jobs):
+        _need_cuda(inter, order, seg, *P_list, *Q_list)
+        m = len(P_list)
+        a = arr[x]
+        a.P, a.Q = tab.data_ptr() + 8 * o, tab.data_ptr() + 8 * (o + m)
+        a.inter, a.order, a.seg = inter.data_ptr(), (order.data_ptr() if order is not None else None), seg.data_ptr()
+        a.score, a.out = score.data_ptr() + 4 * so, out.data_ptr() + 32 * x
+        a.n, a.n_seg, a.n_models, a.denom = ns[x], int(seg.shape[0]) - 1, m, float(m)
+        o += 2 * m
+        so += ns[x]
+    d_jobs = upload_array(np.frombuffer(bytes(arr), dtype=np.uint8), dev)
+    with torch.cuda.device(dev):
+        check(_lib.lib().ure_eval_jobs(_ptr(d_jobs), len(jobs), int(d), max(ns), max(int(j[4].shape[0]) - 1 for j in jobs),
+                                       _stream()), "ure_eval_jobs")
+    out._keep = (tab, d_jobs, score, jobs)        # alive until the result has been read
+    return out
+
+
 def rank_metrics(inter, score, seg, order=None) -> torch.Tensor:
     """fp64 [3] = (sum ndcg, sum hr, #users)."""
     _need_cuda(inter, score, seg, order)

@@ -359,18 +359,31 @@ class Sisa(Scratch):
         # per-epoch evaluations (scratch.py:83-97): ALL of them are queued first -- two launches each, no
         # synchronisation -- and their sums come back in one transfer (round 1 synchronised after every baseTest:
         # 2 x epochs x shards host round trips)
-        queued = {}
+        # ... as JOBS of one pair of launches (ure_eval_jobs, grid.y = job): two baseTest calls per shard and epoch
+        # were 4 launches each, 2000 launches for K = 5, E = 50 -- the default mode was launch-bound at ~90 ms per pass
+        keys, jobs, sizes = [], [], []
+        dev = self.device
         for j, i in enumerate(mine):
             pri = prior(i, models) if mode.startswith('faithful') else None
             for e in range(E):
                 if mode == 'faithful' or (mode == 'faithful-last' and e == E - 1):
                     P, Q = snaps[(i, e)] if mode == 'faithful' else (states[j].P, states[j].Q)
-                    ms = pri + [_Table(P, Q)]
-                    queued[(i, e)] = (base_test_device(test_dlist[i], ms), base_test_device(test_data, ms))
-        keys = list(queued)
-        host = kn.download_many([queued[k][w][0] for k in keys for w in (0, 1)]) if keys else []
-        results = {k: (base_test_values(host[2 * x], queued[k][0][1]), base_test_values(host[2 * x + 1], queued[k][1][1]))
-                   for x, k in enumerate(keys)}
+                    Ps = [m.user_mat.weight.data for m in pri] + [P]
+                    Qs = [m.item_mat.weight.data for m in pri] + [Q]
+                    keys.append((i, e))
+                    for ld in (test_dlist[i], test_data):
+                        ds = ld.dataset
+                        order, seg = ds.segments(dev, Ps[0].shape[0])
+                        jobs.append((Ps, Qs, ds.records(dev), order, seg))
+                        sizes.append(len(ds))
+        results = {}
+        chunk = max(2, int((1 << 30) // (4 * max([1] + sizes))) // 2 * 2)        # <= 1 GB of score scratch per launch
+        for c0 in range(0, len(jobs), chunk):
+            live = [x for x in range(c0, min(len(jobs), c0 + chunk)) if sizes[x] > 0]
+            vals = kn.download_many([kn.eval_jobs([jobs[x] for x in live], self.k)])[0] if live else np.zeros((0, 4))
+            got = {x: vals[y] for y, x in enumerate(live)}
+            for x in range(c0, min(len(jobs), c0 + chunk), 2):
+                results[keys[x // 2]] = tuple(base_test_values(got.get(x + w, np.zeros(4)), sizes[x + w]) for w in (0, 1))
         for j, i in enumerate(mine):
             for e in range(E):
                 self.log['train_loss'].append(float(losses[j][e]))

@@ -862,6 +862,32 @@ def test_mf_full_size_ml1m_k5_vs_oracle(cuda_dev, mode):
         assert np.abs(shards[g].bufP.cpu().numpy() - bP).max() < 4e-3      # momenta reach ~60: 6e-5 relative
 
 
+def test_mf_c3_share_shape_vs_oracle(cuda_dev):
+    """One GPU's share of BASELINE config C3 at its real shape (ml-20m: one of 8 shards -- 17 311 users x 26 744 items,
+    2.5 M interactions, d = 64, batch 30 000): the wide-row OWNER schedule (four chunks per lane, rows resident in shared
+    memory only with the row-balancing item order) against the CPU oracle, two epochs = 168 global steps."""
+    torch = _torch()
+    from ultrare_b200 import kernels as kn, synth
+    U, I, n, d, batch, epochs = 138_493 // 8, 26_744, 20_000_263 // 8, 64, 30000, 2
+    rec = synth.device_interactions(U, I, n, cuda_dev, seed=synth.SEED + 3)
+    h = rec.cpu().numpy()
+    ug, ig, rg = h[:, 0].astype(np.int64), h[:, 1].astype(np.int64), h[:, 2].copy().view(np.float32)
+    assert ug.max() < U and ig.max() < I and len(ug) == n
+    rng = np.random.default_rng(5)
+    P0 = (0.1 * rng.standard_normal((U, d))).astype(np.float32)
+    Q0 = (0.1 * rng.standard_normal((I, d))).astype(np.float32)
+    sh = kn.ShardState(rec, torch.tensor(P0, device=cuda_dev), torch.tensor(Q0, device=cuda_dev), epochs, 4, 42)
+    sb = kn.ShardBatch([sh], d, batch, mode="owner")
+    assert sb.mode == "owner"
+    sb.train()
+    losses = sb.train_losses()[0]
+    perms = [omf.feistel_perm(n, omf.perm_key(42, 4, ep)) for ep in range(epochs)]
+    P, Q, bP, bQ, ls = omf.mf_train(P0, Q0, ug, ig, rg, perms, batch, epochs)
+    np.testing.assert_allclose(losses, ls, rtol=1e-5)
+    assert np.abs(sh.P.cpu().numpy() - P).max() < 1e-4 and np.abs(sh.Q.cpu().numpy() - Q).max() < 1e-4
+    assert np.abs(sh.bufP.cpu().numpy() - bP).max() < 2e-3 and np.abs(sh.bufQ.cpu().numpy() - bQ).max() < 2e-3
+
+
 @pytest.mark.parametrize("contiguous", [True, False])
 def test_user_segments_on_device_equal_host_segments(cuda_dev, contiguous):
     """Per-user test segments built on the device (stable sort + run starts, padded with empty segments) give the

@@ -72,6 +72,45 @@ def _sisa_pass(dist_obj, eval_sharded=None):
     return out
 
 
+def _optimistic_pass(dist_obj):
+    """Device-initialised batches (kernels.ArenaShardBatch) on several GPUs: a pass queued on the remembered plan
+    equals the pass that waited for its plan, and a remembered plan that does not cover ONE rank's batch makes every
+    rank repeat the pass (the flag travels with the all-reduced metric sums)."""
+    import pandas as pd
+    import torch
+    from oracle import sisa as osisa
+    from ultrare_b200 import kernels as kn
+    from ultrare_b200.method.sisa import Sisa
+    from ultrare_b200.read import RatingData, loadData, readRating
+    K, E = 4, 2
+    tr, te = _toy()
+    dtr = pd.DataFrame({0: tr[0], 1: tr[1], 2: tr[2]})
+    dte = pd.DataFrame({0: te[0], 1: te[1], 2: te[2]})
+    g0 = osisa.uniform_groups(N_USER, K)
+    trr, idx = readRating(dtr, N_USER, 5, [], [], K, g0, 'a')
+    ter, _ = readRating(dte, N_USER, 5, [], [], K, idx)
+    tl = [loadData(RatingData(a), BATCH, 1, True) for a in trr]
+    sl = [loadData(RatingData(a), BATCH, 1, False) for a in ter]
+    total = loadData(RatingData(np.hstack(ter)), BATCH, 1, False)
+    out = []
+    for what in ("wait", "hit", "miss"):
+        if what == "wait":
+            kn._PLAN_HINTS.clear()
+        if what == "miss" and dist_obj.rank == 1:
+            for key, v in list(kn._PLAN_HINTS.items()):
+                kn._PLAN_HINTS[key] = (max(1, v[0] // 2), max(16, v[1] // 2), v[2], v[3])
+        s = Sisa(Param(E), 'mf', K, idx)
+        s.epoch_eval = 'none'
+        s.dist = dist_obj
+        models = s.learn(tl, sl, total, 0, '')
+        sb = s._last_batch
+        out.append(dict(what=what, optimistic=bool(sb is not None and sb.optimistic), mode=None if sb is None else sb.mode,
+                        merged=models[0].user_mat.weight.data.cpu().numpy(),
+                        log0=[s.final_log[k] for k in ('total_rmse', 'total_ndcg', 'total_hr')]))
+    torch.cuda.synchronize()
+    return out
+
+
 def _ot_pass(dist_obj):
     from ultrare_b200.method.utils import ot_cluster_device
     rng = np.random.default_rng(3)
@@ -106,7 +145,7 @@ def _worker(rank, world, port, q):
                       LOCAL_RANK=str(rank))
     from ultrare_b200 import dist as udist
     d = udist.init_from_env(backend="nccl")
-    res = dict(sisa=_sisa_pass(d), sisa_whole=_sisa_pass(d, eval_sharded=False), ot=_ot_pass(d))
+    res = dict(sisa=_sisa_pass(d), sisa_whole=_sisa_pass(d, eval_sharded=False), ot=_ot_pass(d), opt=_optimistic_pass(d))
     d.barrier()
     q.put((rank, res))
     d.td.destroy_process_group()
@@ -136,6 +175,13 @@ def test_two_rank_sisa_and_sinkhorn_equal_single_gpu(cuda_dev):
                 assert np.abs(s[phase + "_merged"] - ref[phase + "_merged"]).max() < 1e-4
                 np.testing.assert_allclose(s[phase + "_log0"], ref[phase + "_log0"], rtol=1e-3)
         np.testing.assert_allclose(results[r]["sisa"]["unlearn_log0"], results[r]["sisa_whole"]["unlearn_log0"], rtol=1e-5)
+    for r in range(2):
+        wait, hit, miss = results[r]["opt"]
+        assert wait["mode"] == hit["mode"] == "owner"
+        assert not wait["optimistic"] and hit["optimistic"] and not miss["optimistic"]      # the miss was repeated
+        for other in (hit, miss):
+            assert np.array_equal(other["merged"], wait["merged"])
+            np.testing.assert_allclose(other["log0"], wait["log0"], rtol=1e-12)
     for r in range(2):
         assert results[r]["ot"]["peer"], "no peer-mapped symmetric memory between the two GPUs"
         assert np.abs(results[r]["ot"]["g_peer"] - results[r]["ot"]["g_nccl"]).max() < 1e-5

@@ -3,13 +3,13 @@
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 N=${1:-2}
 O=gpurun_out
-nvidia-smi topo -m > $O/r2u_topo.txt 2>&1
-timeout 900 python -m pytest tests/test_gpu_multi.py -q -m gpu -x > $O/r2u_multi_tests.log 2>&1
-tail -15 $O/r2u_multi_tests.log
+nvidia-smi topo -m > $O/r2mm_topo.txt 2>&1
+timeout 900 python -m pytest tests/test_gpu_multi.py -q -m gpu -x > $O/r2mm_multi_tests.log 2>&1
+tail -15 $O/r2mm_multi_tests.log
 RUN="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517"
-URE_BENCH_DEBUG=1 timeout 900 $RUN bench.py --gpus $N --steps 5 --warmup 3 > $O/r2u_bench_$N.log 2> $O/r2u_bench_$N.err
-tail -c 1500 $O/r2u_bench_$N.err; tail -c 3000 $O/r2u_bench_$N.log
-timeout 900 $RUN bench.py --gpus $N --config c5 --no-cpu > $O/r2u_c5_$N.log 2> $O/r2u_c5_$N.err
-tail -c 600 $O/r2u_c5_$N.err; tail -c 2500 $O/r2u_c5_$N.log
-timeout 900 $RUN bench.py --gpus $N --config c4 --steps 2 > $O/r2u_c4_$N.log 2> $O/r2u_c4_$N.err
-tail -c 600 $O/r2u_c4_$N.err; tail -c 1500 $O/r2u_c4_$N.log
+URE_BENCH_DEBUG=1 timeout 900 $RUN bench.py --gpus $N --steps 5 --warmup 3 > $O/r2mm_bench_$N.log 2> $O/r2mm_bench_$N.err
+tail -c 1500 $O/r2mm_bench_$N.err; tail -c 3000 $O/r2mm_bench_$N.log
+
+
+
+

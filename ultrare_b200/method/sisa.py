@@ -169,15 +169,20 @@ class Sisa(Scratch):
             qsum = torch.zeros((self.n_item, self.k), dtype=torch.float32, device=dev)
         self.dist.all_reduce(qsum)
         merged = self.model_list[0].user_mat.weight.data
-        out = torch.zeros(4, dtype=torch.float64, device=dev)
+        out = torch.zeros(5, dtype=torch.float64, device=dev)
         recs = [test_dlist[i].dataset.records(dev) for i in mine if len(test_dlist[i].dataset) > 0]
         if recs:
             inter, order, seg = _eval_rows(recs, self.n_user)
             score, sse = kn.ensemble_score([merged], [qsum], inter, denom=float(K))
             out[0:1] = sse
             out[1:4] = kn.rank_metrics(inter, score, seg, order)
+        sb = getattr(self, '_last_batch', None)
+        if sb is not None and getattr(sb, 'optimistic', False):
+            out[4:5] = (sb.ws[16:20].view(torch.int32) == 2).to(torch.float64)      # this rank's plan was not covered
         self.dist.all_reduce(out)
         vals = out.cpu().numpy()
+        if vals[4] > 0:                        # on some rank: every rank repeats the pass (Sisa._retrying)
+            raise kn.PlanHintMiss("ultrare_b200: a rank's remembered owner plan did not cover its batch")
         n_test = sum(len(t.dataset) for t in test_dlist)
         users = max(vals[3], 1.0)
         return float(np.sqrt(vals[0] / max(1, n_test))), float(vals[1] / users), float(vals[2] / users)
@@ -219,6 +224,7 @@ class Sisa(Scratch):
         i trains, `new` being the {shard: model} dict of this call (epoch_eval='faithful' only).
         """
         mine = self.dist.my_shards(list(ids))
+        self._last_batch = None
         mode = self._mode()
         compact = mode != 'faithful'
         E = self.epochs
@@ -244,13 +250,19 @@ class Sisa(Scratch):
             t_b = time.time()
             if batched:
                 from .scratch import model_generator
+                # optimistic launch (kernels.ArenaShardBatch): only when the losses are read after the evaluation;
+                # several GPUs: only with the row-sharded final evaluation, whose all-reduce carries every rank's
+                # "plan not covered" flag, so that all ranks repeat the pass together
+                will_shard_eval = self.dist.world > 1 and self.eval_sharded is not False and test_data is not None and \
+                    sum(len(t.dataset) for t in test_dlist) == len(test_data.dataset)
+                optimistic = defer_logs and mode == 'none' and verbose != 1 and (self.dist.world == 1 or will_shard_eval)
                 rows = [len(self.group_index[i]) if compact else self.n_user for i in mine]
                 perms = [train_dlist[i].explicit_perm(self.device, E) for i in mine]
                 sb = kn.ArenaShardBatch(recs, rows, self.n_item, self.k, batch, E, [i + 1 for i in mine], self.seed,
                                         perms if any(p is not None for p in perms) else None, self.lr, self.lr_decay,
                                         50, self.lam, self.momentum,
                                         generator=lambda: model_generator(self.seed, mine[0] + 1, self.device),
-                                        optimistic=defer_logs and mode == 'none' and verbose != 1 and self.dist.world == 1)
+                                        optimistic=optimistic)
                 states = None
             else:
                 for j, i in enumerate(mine):
@@ -506,6 +518,7 @@ class Sisa(Scratch):
         try:
             return once(*args)
         except kn.PlanHintMiss:
+            kn._PLAN_HINTS.clear()
             self._pending_logs = None
             self._join_writers()
             return once(*args)

@@ -634,6 +634,46 @@ def test_mf_owner_prepare_sorts_and_inverts(cuda_dev):
     assert sb.owner_plan["smem_need"] <= sb.owner_plan["smem_avail"]
 
 
+def test_mf_owner_prepare_records_already_in_user_order(cuda_dev):
+    """Rating files are written user by user: a shard whose records arrive in user-row order skips the user-side
+    radix passes (the counting pass notices and keeps the copy it wrote while reading).  Three shards in one batch --
+    in order, in order except for ONE late inversion, random -- give the same sorted copies as a stable argsort, and
+    the batched runtime's arena path agrees."""
+    torch = _torch()
+    from ultrare_b200 import kernels as kn
+    rng = np.random.default_rng(9)
+    U, I, d = 300, 500, 16
+    shards, host = [], []
+    for kind, n in (("sorted", 70_001), ("one inversion", 50_000), ("random", 30_000)):
+        u = np.sort(rng.integers(0, U, n)) if kind != "random" else rng.integers(0, U, n)
+        if kind == "one inversion":
+            u[-1] = 0
+        i = rng.integers(0, I, n)
+        r = rng.integers(1, 6, n).astype(np.float32) / 5
+        shards.append(kn.ShardState(kn.pack_interactions(u, i, r, cuda_dev), torch.zeros((U, d), device=cuda_dev),
+                                    torch.zeros((I, d), device=cuda_dev), 1))
+        host.append((u, i))
+    kn.ShardBatch(shards, d, 4096, mode="owner")
+    torch.cuda.synchronize()
+    for st, (u, i) in zip(shards, host):
+        for rec, key in ((st.inter_u, u), (st.inter_i, i)):
+            rec = rec.cpu().numpy()
+            j = np.argsort(key, kind="stable")
+            assert np.array_equal(rec[:, 3], j) and np.array_equal(rec[:, 0], u[j]) and np.array_equal(rec[:, 1], i[j])
+    sb = kn.ArenaShardBatch([st.inter for st in shards], [U] * 3, I, d, 4096, 1, [1, 2, 3])
+    torch.cuda.synchronize()
+    for v, (u, i) in zip(sb.shards, host):
+        pass                                              # (the views expose tables only; the arena's sorted copies:)
+    lay, n_tot = sb._lay, sum(len(h[0]) for h in host)
+    rec = sb.arena[int(lay.rec):int(lay.rec) + 2 * n_tot * 16].view(torch.int32).view(2, n_tot, 4).cpu().numpy()
+    o = 0
+    for u, i in host:
+        n = len(u)
+        assert np.array_equal(rec[0, o:o + n, 3], np.argsort(u, kind="stable"))
+        assert np.array_equal(rec[1, o:o + n, 3], np.argsort(i, kind="stable"))
+        o += n
+
+
 @pytest.mark.parametrize("cache,force", [(True, None), (False, None), (False, (2, 64)), (False, (0, 16)), (False, (2, 4096))])
 def test_mf_owner_skewed_rows_many_shards_vs_oracle(cuda_dev, cache, force, monkeypatch):
     """Owner schedule on ragged shards with heavy rows (one user / one item holding a large share of a shard, rows

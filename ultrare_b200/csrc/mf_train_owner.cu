@@ -47,6 +47,7 @@ struct OwnerWs {
   long long tot_slots;    // written by plan_kernel: sum over the shards of 2 n (slots of one schedule row)
   int pad[20];
   unsigned bar[KMAX][32]; // one barrier counter per shard, one 128-byte line each
+  unsigned unsorted[KMAX]; // set by csr_count_kernel: the shard's records are NOT already in user-row order (zero on entry)
 };
 
 struct Plan {
@@ -194,11 +195,23 @@ __global__ void plan_kernel(const ure_mf_shard_t* shards, int K, int batch, int 
 // (p = 0) or the previous pass's output and writes the other of {tmp, final}; the last pass lands in final.
 // smem_rows > 0: the shard's rows (user + item) fit a shared-memory histogram of that many counters -- the global
 // atomics (875 k x 2 on a few thousand hot addresses at ml1m size) shrink to one per row and CTA
-__global__ void csr_count_kernel(const ure_mf_shard_t* shards, int smem_rows) {
+// Rating files are written user by user (ML-1M / ML-20M, and what readRating hands over), so a shard's records usually
+// arrive ALREADY in user-row order and the stable sort by user is the identity.  The counting pass checks that while
+// it reads the records (every record against its predecessor) and writes the user-sorted copy speculatively
+// (inter_u[j] = record j, pad = j): when no inversion shows up, the radix passes of the user side return at once
+// (ws->unsorted[shard] == 0); otherwise they overwrite the copy.  Same bytes either way.
+__device__ __forceinline__ void note_order(const ure_mf_shard_t& sh, long long j, const int4& r, unsigned* unsorted) {
+  if (!unsorted) return;
+  if (j > 0 && __ldg(&sh.inter[j - 1].user) > r.x) *unsorted = 1u;      // benign race: every writer stores 1
+  reinterpret_cast<int4*>(sh.inter_u)[j] = make_int4(r.x, r.y, r.z, (int)j);
+}
+
+__global__ void csr_count_kernel(const ure_mf_shard_t* shards, int smem_rows, OwnerWs* ws) {
   extern __shared__ int s_cnt[];
   const ure_mf_shard_t& sh = shards[blockIdx.y];
   const long long stride = (long long)gridDim.x * blockDim.x;
   const int nu = sh.n_user, rows = sh.n_user + sh.n_item;
+  unsigned* const unsorted = ws ? &ws->unsorted[blockIdx.y] : nullptr;
   if (smem_rows > 0 && rows <= smem_rows) {
     for (int x = threadIdx.x; x < rows; x += blockDim.x) s_cnt[x] = 0;
     __syncthreads();
@@ -206,6 +219,7 @@ __global__ void csr_count_kernel(const ure_mf_shard_t* shards, int smem_rows) {
       const int4 r = ld_stream_i4(sh.inter + j);
       atomicAdd(&s_cnt[r.x], 1);
       atomicAdd(&s_cnt[nu + r.y], 1);
+      note_order(sh, j, r, unsorted);
     }
     __syncthreads();
     for (int x = threadIdx.x; x < rows; x += blockDim.x) {
@@ -218,6 +232,7 @@ __global__ void csr_count_kernel(const ure_mf_shard_t* shards, int smem_rows) {
     const int4 r = ld_stream_i4(sh.inter + j);
     atomicAdd(sh.off_u + r.x + 1, 1);
     atomicAdd(sh.off_i + r.y + 1, 1);
+    note_order(sh, j, r, unsorted);
   }
 }
 
@@ -286,8 +301,9 @@ struct RadixView {                        // what pass `pass` of grid row y = 2*
 
 // hist [grid.y][grid.x][256]: records of the CTA's tile per digit value
 __global__ void __launch_bounds__(kRadixThreads)
-radix_hist_kernel(const ure_mf_shard_t* shards, int pass, int npass, int* __restrict__ hist) {
+radix_hist_kernel(const ure_mf_shard_t* shards, int pass, int npass, int* __restrict__ hist, const OwnerWs* ws) {
   __shared__ int s_h[256];
+  if (ws && !(blockIdx.y & 1) && ws->unsorted[blockIdx.y >> 1] == 0) return;      // user side already in order
   const RadixView v(shards, pass, npass);
   for (int x = threadIdx.x; x < 256; x += blockDim.x) s_h[x] = 0;
   __syncthreads();
@@ -308,8 +324,9 @@ radix_hist_kernel(const ure_mf_shard_t* shards, int pass, int npass, int* __rest
 
 // per grid row y: exclusive scan of hist in (digit, CTA) order, in place; one CTA of 256 threads per y
 __global__ void __launch_bounds__(256)
-radix_scan_kernel(int* __restrict__ hist, int n_blocks) {
+radix_scan_kernel(int* __restrict__ hist, int n_blocks, const OwnerWs* ws) {
   __shared__ int s_tot[256];
+  if (ws && !(blockIdx.x & 1) && ws->unsorted[blockIdx.x >> 1] == 0) return;
   int* h = hist + (long long)blockIdx.x * n_blocks * 256 + threadIdx.x;      // thread = digit: coalesced per CTA row
   int tot = 0;
   for (int b = 0; b < n_blocks; ++b) tot += h[b * 256];
@@ -340,8 +357,9 @@ radix_scan_kernel(int* __restrict__ hist, int n_blocks) {
 // stable scatter of the CTA's tile: every warp owns a contiguous range; per-warp digit counts -> per-warp cursors
 // (from the CTA's global offsets); inside a warp __match_any ranks the lanes of one digit in lane (= record) order
 __global__ void __launch_bounds__(kRadixThreads)
-radix_scatter_kernel(const ure_mf_shard_t* shards, int pass, int npass, const int* __restrict__ hist) {
+radix_scatter_kernel(const ure_mf_shard_t* shards, int pass, int npass, const int* __restrict__ hist, const OwnerWs* ws) {
   __shared__ int s_wh[kRadixWarps][256];
+  if (ws && !(blockIdx.y & 1) && ws->unsorted[blockIdx.y >> 1] == 0) return;
   const RadixView v(shards, pass, npass);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned lt = (1u << lane) - 1u;
@@ -1522,9 +1540,9 @@ extern "C" int ure_user_segments(const ure_inter_t* d_inter, int64_t n, int n_us
   int npass = 1;
   while (npass < 4 && (n_user - 1) >> (8 * npass)) ++npass;
   for (int pass = 0; pass < npass; ++pass) {            // grid.y = 1: shard 0, user side only
-    radix_hist_kernel<<<dim3(kRadixBlocks, 1), kRadixThreads, 0, st>>>(d_desc, pass, npass, hist);
-    radix_scan_kernel<<<1, 256, 0, st>>>(hist, kRadixBlocks);
-    radix_scatter_kernel<<<dim3(kRadixBlocks, 1), kRadixThreads, 0, st>>>(d_desc, pass, npass, hist);
+    radix_hist_kernel<<<dim3(kRadixBlocks, 1), kRadixThreads, 0, st>>>(d_desc, pass, npass, hist, nullptr);
+    radix_scan_kernel<<<1, 256, 0, st>>>(hist, kRadixBlocks, nullptr);
+    radix_scatter_kernel<<<dim3(kRadixBlocks, 1), kRadixThreads, 0, st>>>(d_desc, pass, npass, hist, nullptr);
   }
   seg_extract_kernel<<<(unsigned)blocks, 256, 0, st>>>(sorted, n, off_u, n_user, d_order, reinterpret_cast<long long*>(d_seg));
   URE_CUDA(cudaGetLastError());
@@ -1560,15 +1578,16 @@ int ure::mf_owner_prepare_impl(const ure_mf_shard_t* d_shards, int n_shards, con
     const int cb = smem_rows ? (num_sms() / n_shards > 0 ? num_sms() / n_shards : 1) : blocks;   // one wave of CTAs
     if (smem_rows)
       URE_CUDA(cudaFuncSetAttribute(csr_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_rows * 4));
-    csr_count_kernel<<<dim3(cb, n_shards), 1024, (size_t)smem_rows * 4, st>>>(d_shards, smem_rows);
+    if (!(flags & 1)) URE_CUDA(cudaMemsetAsync(ws->unsorted, 0, sizeof(ws->unsorted), st));
+    csr_count_kernel<<<dim3(cb, n_shards), 1024, (size_t)smem_rows * 4, st>>>(d_shards, smem_rows, ws);
   }
   csr_scan_kernel<<<2 * n_shards, 1024, 0, st>>>(d_shards);
   int npass = 1;
   while (npass < 4 && (max_rows - 1) >> (8 * npass)) ++npass;
   for (int pass = 0; pass < npass; ++pass) {
-    radix_hist_kernel<<<dim3(kRadixBlocks, 2 * n_shards), kRadixThreads, 0, st>>>(d_shards, pass, npass, d_radix_hist);
-    radix_scan_kernel<<<2 * n_shards, 256, 0, st>>>(d_radix_hist, kRadixBlocks);
-    radix_scatter_kernel<<<dim3(kRadixBlocks, 2 * n_shards), kRadixThreads, 0, st>>>(d_shards, pass, npass, d_radix_hist);
+    radix_hist_kernel<<<dim3(kRadixBlocks, 2 * n_shards), kRadixThreads, 0, st>>>(d_shards, pass, npass, d_radix_hist, ws);
+    radix_scan_kernel<<<2 * n_shards, 256, 0, st>>>(d_radix_hist, kRadixBlocks, ws);
+    radix_scatter_kernel<<<dim3(kRadixBlocks, 2 * n_shards), kRadixThreads, 0, st>>>(d_shards, pass, npass, d_radix_hist, ws);
   }
   if (!(flags & 4)) perm_inverse_kernel<<<dim3(blocks, n_shards), 256, 0, st>>>(d_shards, epochs);
   int avail = 0;

@@ -917,6 +917,9 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
 #ifndef URE_OWNER_V16
 #define URE_OWNER_V16 1
 #endif
+#ifndef URE_OWNER_PREFETCH
+#define URE_OWNER_PREFETCH 0
+#endif
 #ifndef URE_OWNER_QB16
 #define URE_OWNER_QB16 4
 #endif
@@ -1130,6 +1133,20 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
 #pragma unroll
         for (int v = 0; v < V; ++v) o4[q][v] = __ldca(reinterpret_cast<const float4*>(src + 4 * v * G));
       }
+#if URE_OWNER_PREFETCH
+      // experiment (tools/build_variant.sh -DURE_OWNER_PREFETCH=1|2): the NEXT wave's gathered rows on their way into
+      // L1 while this wave computes, no registers held.  Measured SLOWER (7.3-7.5 vs 6.9 us per step): the loop is bound
+      // by its dependent instruction stream, not by the L2 latency of the gathers.
+      if (wv + 1 < wv1) {
+#pragma unroll
+        for (int q = 0; q < QB; ++q) {
+          const uint2 rec = rec_at(min(ent0 + WAVE + q, ent1 - 1));
+          const int r = (int)(rec.x >> kOtherBits);
+          const float* const src = (r >= rowsU ? Pr : Qr) + (size_t)(rec.x & ((1u << kOtherBits) - 1u)) * D;
+          if (URE_OWNER_PREFETCH == 2 || gl == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(src + 4 * gl));
+        }
+      }
+#endif
       int key;
       float4 acc[V];
       if constexpr (V == 4) {

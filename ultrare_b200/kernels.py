@@ -917,6 +917,8 @@ class ArenaShardBatch(ShardBatch):
                 ev.synchronize()                             # the one wait of the set-up: upload + sorts + plan
                 self.plan_sync_ms = (time.perf_counter() - t0) * 1e3
                 plan = stage[176 * K:176 * K + 16].view(torch.int32)
+                if len(_PLAN_HINTS) >= 256:                 # shapes come and go: the memory stays bounded
+                    _PLAN_HINTS.clear()
                 _PLAN_HINTS[sig] = tuple(int(v) for v in plan.tolist())
                 rc = plan_with(plan.tolist())
             if rc < 0:

@@ -271,6 +271,30 @@ def run_c2_ours(args):
         ms = e0.elapsed_time(e1)
         if it >= args.warmup:
             step_ms.append(d.max_float(ms))
+    if os.environ.get("URE_BENCH_TIMELINE") and rank == 0:
+        # CUPTI timeline of one more device-resident step on rank 0 (every rank runs the step: collectives)
+        from torch.profiler import ProfilerActivity, profile
+        prof = profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA])
+    else:
+        prof = None
+    if os.environ.get("URE_BENCH_TIMELINE"):
+        flush.fill_(3)
+        un = new_sisa()
+        d.barrier()
+        torch.cuda.synchronize()
+        if prof is not None:
+            prof.__enter__()
+        un.unlearn(model_list, train_dl, test_dlist, test_data, list(del_user), 0, "")
+        torch.cuda.synchronize()
+        if prof is not None:
+            prof.__exit__(None, None, None)
+            evs = sorted([e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA],
+                         key=lambda e: e.time_range.start)
+            t0_, prev = evs[0].time_range.start, evs[0].time_range.start
+            for e in evs:
+                s_, en = e.time_range.start, e.time_range.end
+                print(f"[timeline] {s_ - t0_:9.1f} {en - s_:9.1f} {s_ - prev:8.1f}  {e.name[:100]}", file=sys.stderr)
+                prev = max(prev, en)
     n_retrained = len(un.retrain_gid)
     step_rmse = float(un.final_log["total_rmse"])
     sb = un._last_batch

@@ -80,6 +80,21 @@ def _owner_maps(group_index, n_user, device):
     return out
 
 
+def _as_one_block(tensors):
+    """The tensors as ONE [n, ...] view when they lie back to back in device memory in this order (the tables of a
+    batch arena do), else None."""
+    if not tensors:
+        return None
+    t0 = tensors[0]
+    end = t0.data_ptr()
+    for t in tensors:
+        if t.data_ptr() != end or not t.is_contiguous() or t.dtype != t0.dtype or t.shape[1:] != t0.shape[1:]:
+            return None
+        end += t.numel() * t.element_size()
+    rows = sum(int(t.shape[0]) for t in tensors)
+    return torch.as_strided(t0, (rows,) + tuple(t0.shape[1:]), t0.stride())
+
+
 def _local(models):
     return [m for m in models if m is not None and getattr(m, 'item_mat', None) is not None]
 
@@ -164,7 +179,9 @@ class Sisa(Scratch):
         dev, K = self.device, self.n_group
         mine = [i for i, m in enumerate(self.model_list) if getattr(m, 'item_mat', None) is not None]
         if mine:
-            qsum = torch.stack([self.model_list[i].item_mat.weight.data for i in mine]).sum(0)
+            qs = [self.model_list[i].item_mat.weight.data for i in mine]
+            block = _as_one_block(qs)      # the item tables of a batch arena: one reduction, no stack copy
+            qsum = block.view(len(qs), self.n_item, self.k).sum(0) if block is not None else torch.stack(qs).sum(0)
         else:
             qsum = torch.zeros((self.n_item, self.k), dtype=torch.float32, device=dev)
         self.dist.all_reduce(qsum)
@@ -178,9 +195,10 @@ class Sisa(Scratch):
             out[1:4] = kn.rank_metrics(inter, score, seg, order)
         sb = getattr(self, '_last_batch', None)
         if sb is not None and getattr(sb, 'optimistic', False):
-            out[4:5] = (sb.ws[16:20].view(torch.int32) == 2).to(torch.float64)      # this rank's plan was not covered
+            # this rank's error word (0, or 2 = the remembered plan was not covered), one converting copy
+            out[4:5].copy_(sb.ws[16:20].view(torch.int32))
         self.dist.all_reduce(out)
-        vals = out.cpu().numpy()
+        vals = kn.download_many([out])[0]
         if vals[4] > 0:                        # on some rank: every rank repeats the pass (Sisa._retrying)
             raise kn.PlanHintMiss("ultrare_b200: a rank's remembered owner plan did not cover its batch")
         n_test = sum(len(t.dataset) for t in test_dlist)
@@ -489,11 +507,16 @@ class Sisa(Scratch):
         for s_ in trained:
             by_rank.setdefault(self.dist.owner_of_shard(s_), []).append(s_)
         maxlen = max([sum(sizes[s_] for s_ in v) for v in by_rank.values()] or [1])
-        send = torch.empty((maxlen, self.k), dtype=torch.float32, device=dev)
-        o = 0
-        for s_ in by_rank.get(self.dist.rank, []):
-            send[o:o + sizes[s_]].copy_(unmerged[s_], non_blocking=True)
-            o += sizes[s_]
+        mine_now = by_rank.get(self.dist.rank, [])
+        block = _as_one_block([unmerged[s_] for s_ in mine_now])
+        if block is not None and block.shape[0] == maxlen:
+            send = block                   # this rank's owner rows are one run of the batch arena: gathered in place
+        else:
+            send = torch.empty((maxlen, self.k), dtype=torch.float32, device=dev)
+            o = 0
+            for s_ in mine_now:
+                send[o:o + sizes[s_]].copy_(unmerged[s_], non_blocking=True)
+                o += sizes[s_]
         gathered = torch.empty((self.dist.world * maxlen, self.k), dtype=torch.float32, device=dev)
         t1 = time.perf_counter()
         self.dist.all_gather_into(gathered, send)

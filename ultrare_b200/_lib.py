@@ -36,7 +36,8 @@ class MFHParams(C.Structure):
                 ("owner_spe_cap", _i32), ("owner_sched_rows", _i32), ("owner_sched", _p), ("owner_sched_off", _p),
                 ("owner_sched_step0", _i64), ("owner_sched_stride", _i64),
                 ("owner_cap_list", _i32), ("owner_max_n", _i32),
-                ("runs", _p), ("runs_rows", _i32), ("runs_spe_cap", _i32), ("runs_step0", _i64), ("owner_plan", _p)]
+                ("runs", _p), ("runs_rows", _i32), ("runs_spe_cap", _i32), ("runs_step0", _i64), ("owner_plan", _p),
+                ("owner_ready", _p)]
 
 
 class MFRuns(C.Structure):
@@ -58,14 +59,14 @@ class MFBatchShard(C.Structure):
 class MFBatchLayout(C.Structure):
     """ure_mf_batch_layout_t"""
     _fields_ = [(nm, _i64) for nm in ("total", "table", "ws", "W", "Z", "sse", "zero_end", "rec", "off", "radix",
-                                       "perm_inv", "sched", "sched_off", "rows_total", "n_total", "sched_stride")] + \
+                                       "perm_inv", "sched", "sched_off", "ready", "rows_total", "n_total", "sched_stride")] + \
                [(nm, _i32) for nm in ("spe_cap", "max_rows", "max_n", "grid", "owner", "sched_rows")]
 
 
 MF_DENSE, MF_LAZY, MF_OWNER, MF_RUNS = 0, 1, 2, 3
 
-assert C.sizeof(MFShard) == 176 and C.sizeof(MFHParams) == 136 and C.sizeof(MFRuns) == 64
-assert C.sizeof(MFBatchShard) == 32 and C.sizeof(MFBatchLayout) == 152
+assert C.sizeof(MFShard) == 176 and C.sizeof(MFHParams) == 144 and C.sizeof(MFRuns) == 64
+assert C.sizeof(MFBatchShard) == 32 and C.sizeof(MFBatchLayout) == 160
 
 # name -> (restype, argtypes); every symbol include/ultrare_b200.h declares
 SIGNATURES = {
@@ -77,6 +78,7 @@ SIGNATURES = {
     "ure_mf_owner_prepare": (C.c_int, [_p, C.c_int, C.POINTER(MFHParams), C.c_int, C.c_int, _p, _p, _p]),
     "ure_mf_owner_smem_bytes": (_i64, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "ure_mf_owner_schedule": (C.c_int, [_p, C.c_int, C.POINTER(MFHParams), C.c_int, _i64, _p]),
+    "ure_mf_owner_concurrent_ok": (C.c_int, [C.POINTER(MFHParams), C.c_int]),
     "ure_mf_batch_layout": (C.c_int, [C.POINTER(MFBatchShard), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _i64,
                                        C.POINTER(MFBatchLayout)]),
     "ure_mf_batch_setup": (C.c_int, [C.POINTER(MFBatchShard), C.c_int, C.c_int, C.POINTER(MFHParams), C.c_int, C.c_uint32,
@@ -142,7 +144,7 @@ def lib() -> C.CDLL:
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(handle, name)           # AttributeError if the .so lacks a declared symbol
         fn.restype, fn.argtypes = res, args
-    if handle.ure_abi_version() != 5:
+    if handle.ure_abi_version() != 6:
         raise RuntimeError("ultrare_b200: ABI version mismatch; rebuild the shared library")
     _lib = handle
     return handle

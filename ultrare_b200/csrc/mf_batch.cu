@@ -19,7 +19,7 @@ int mf_owner_prepare_impl(const ure_mf_shard_t* d_shards, int n_shards, const ur
                           int max_rows, int32_t* d_radix_hist, void* d_workspace, void* stream, int flags);
 }
 
-static_assert(sizeof(ure_mf_batch_shard_t) == 32 && sizeof(ure_mf_batch_layout_t) == 152, "ctypes mirrors in _lib.py");
+static_assert(sizeof(ure_mf_batch_shard_t) == 32 && sizeof(ure_mf_batch_layout_t) == 160, "ctypes mirrors in _lib.py");
 
 namespace ure {
 namespace {
@@ -59,7 +59,16 @@ extern "C" int ure_mf_batch_layout(const ure_mf_batch_shard_t* h_shards, int n_s
   out->ws = o; o = align_up(o + ure_mf_train_workspace_bytes());
   out->Z = o; o = align_up(o + 2 * table_rows * d * 4);
   out->sse = o; o = align_up(o + (int64_t)n_shards * (epochs > 1 ? epochs : 1) * 8);
-  if (out->owner) { out->off = o; o = align_up(o + n_off * 4); }
+  int64_t n_rows = 0, stride = 0;
+  if (out->owner) {
+    out->off = o; o = align_up(o + n_off * 4);
+    stride = 2 * n_tot > 0 ? 2 * n_tot : 1;
+    const int64_t row_bytes = 2 * stride + 4ll * grid * (spe_cap + 1);
+    n_rows = sched_bytes_cap / row_bytes;
+    if (n_rows < 2) n_rows = 2;
+    if (n_rows > epochs + 1) n_rows = epochs + 1;
+    out->ready = o; o = align_up(o + (int64_t)grid * n_rows * 4);       // row flags of the concurrent pre-pass
+  }
   out->zero_end = o;
   out->rows_total = rows;
   out->n_total = n_tot;
@@ -71,11 +80,6 @@ extern "C" int ure_mf_batch_layout(const ure_mf_batch_shard_t* h_shards, int n_s
     out->rec = o; o = align_up(o + 4 * (n_tot > 0 ? n_tot : 1) * 16);
     out->radix = o; o = align_up(o + ure_mf_owner_radix_bytes(n_shards));
     out->perm_inv = o; o = align_up(o + n_pinv * 4);
-    const int64_t stride = 2 * n_tot > 0 ? 2 * n_tot : 1;
-    const int64_t row_bytes = 2 * stride + 4ll * grid * (spe_cap + 1);
-    int64_t n_rows = sched_bytes_cap / row_bytes;
-    if (n_rows < 2) n_rows = 2;
-    if (n_rows > epochs + 1) n_rows = epochs + 1;
     out->sched_rows = (int32_t)n_rows;
     out->sched_stride = stride;
     out->sched = o; o = align_up(o + n_rows * stride * 2);

@@ -714,11 +714,16 @@ __host__ __device__ inline long long schedule_tab_smem_bytes(int cap_slots, int 
   return 4ll * cap_slots + 2ll * cap_slots + 4ll * kSchedWarps * 64 + 4ll * (kSchedWarps + 4) + 2ll * 2 * n_tab * tab_cap + 64;
 }
 
-template <int NT>
-__global__ void __launch_bounds__(kSchedThreads, 2)
+// CO (concurrent mode, hp.owner_ready): ONE 256-thread CTA per training CTA, launched next to the training kernel on
+// the registers and shared memory it leaves free (56 x 256 registers, ~40 KB); the rows are produced in epoch order
+// and published one by one (ready[cta * rows + row] = 1, release); the packed halves live in the radix scratch of
+// the set-up (tmp_u / tmp_i, free by now) instead of shared memory.
+template <int NT, int NTHR, bool CO>
+__global__ void __maxnreg__(CO ? 56 : 64)
 owner_schedule_tab_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams_t hp, int epochs,
                           long long step0, int tab_cap, int sb) {
-  constexpr int NW = kSchedWarps;
+  constexpr int kSchedThreads = NTHR;      // (shadows the namespace constant: every loop below strides by the CTA size)
+  constexpr int NW = NTHR / 32;
   constexpr unsigned FULL = 0xffffffffu;
   constexpr int NI = 4;
   extern __shared__ __align__(16) unsigned char dyn[];
@@ -730,11 +735,16 @@ owner_schedule_tab_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_
   const int mU = s_pl.mU, m = mU + s_pl.mI;
   const int B = hp.batch, n = sh.n;
   const int spe = (n + B - 1) / B;
-  if (plan_not_covered(hp, s_pl, spe)) return;
+  if (plan_not_covered(hp, s_pl, spe)) {
+    if (CO)                                // the training CTA of this index is (or will be) waiting: tell it to give up
+      for (int r = tid; r < hp.owner_sched_rows; r += kSchedThreads)
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(hp.owner_ready + (long long)blockIdx.x * hp.owner_sched_rows + r),
+                     "r"(2u) : "memory");
+    return;
+  }
   if (spe == 0) return;
   const int cap = hp.owner_cap_slots, spe_cap = hp.owner_spe_cap;
-  uint32_t* const s_lr = reinterpret_cast<uint32_t*>(dyn);                       // [cap]
-  unsigned short* const s_sr = reinterpret_cast<unsigned short*>(s_lr + cap);    // [cap] step | rank << sb
+  unsigned short* const s_sr = reinterpret_cast<unsigned short*>(reinterpret_cast<uint32_t*>(dyn) + (CO ? 0 : cap));   // [cap] step | rank << sb
   int* const s_wh = reinterpret_cast<int*>(s_sr + cap);                          // [NW][64]
   int* const s_wtot = s_wh + NW * 64;                                            // [NW + 4]
   unsigned char* const s_tab = reinterpret_cast<unsigned char*>(s_wtot + NW + 4);   // NT x [tab_cap] u16
@@ -745,11 +755,16 @@ owner_schedule_tab_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_
   dom.init((uint32_t)n);
   const bool explicit_order = sh.perm_inv != nullptr;
   const bool trivial = n <= 1;
+  // packed halves of every slot: shared memory, or (CO) the set-up's radix scratch -- 16 bytes per record and side,
+  // 4 needed; slot sl of the user side at tmp_u[su0 ..], of the item side at tmp_i[si0 ..]
+  uint32_t* const lrU = CO ? reinterpret_cast<uint32_t*>(sh.tmp_u) + s_pl.su0 : reinterpret_cast<uint32_t*>(dyn);
+  uint32_t* const lrI = CO ? reinterpret_cast<uint32_t*>(sh.tmp_i) + s_pl.si0 - mU : lrU;
+  auto lr_at = [&](int sl) -> uint32_t& { return (sl >= mU ? lrI : lrU)[sl]; };
   for (int sl = tid; sl < m; sl += kSchedThreads) {
     const uint32_t j = (uint32_t)__ldg(&((sl >= mU ? recI : recU) + sl)->w);
     uint32_t L, R;
     dom.split(j, L, R);
-    s_lr[sl] = explicit_order || trivial ? j : (L << 17) | (R << 1);
+    lr_at(sl) = explicit_order || trivial ? j : (L << 17) | (R << 1);
   }
   const uint32_t B2 = 2u * (uint32_t)B;
   const uint32_t magic2 = (uint32_t)(0x100000000ull / B2);                       // floor(2^32 / 2B): quotient low by <= 1
@@ -818,7 +833,7 @@ owner_schedule_tab_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_
       for (int u = 0; u < NI; ++u) {
         const int sl = base + 32 * u + lane;
         live[u] = sl < w1;
-        x2[u] = live[u] ? s_lr[sl] : 0u;
+        x2[u] = live[u] ? lr_at(sl) : 0u;
       }
       if (explicit_order) {
 #pragma unroll
@@ -898,6 +913,13 @@ owner_schedule_tab_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_
     s_wh[warp * 64 + lane] = 0;
     s_wh[warp * 64 + 32 + lane] = 0;
     __syncwarp();
+    if (CO) {                              // the row is complete: tell the training CTA of the same index
+      __threadfence();
+      __syncthreads();
+      if (tid == 0)
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(hp.owner_ready + (long long)blockIdx.x * hp.owner_sched_rows + r),
+                     "r"(1u) : "memory");
+    }
   }
 }
 
@@ -906,8 +928,18 @@ owner_schedule_tab_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_
 // 32-bit shared-memory indexing, packed cache records and compile-time CACHED keep its instruction count down.
 // LONGLIST: the launch's owner_cap_list is below owner_cap_slots, so a batch list may have to be read from the
 // schedule table in global memory (generic loads); false keeps every list access a shared-memory load.
+// -DURE_OWNER_REGS=96: narrow rows (d <= 32) compiled for 96 registers (no spills, 6.85 vs 6.79 us per step with the 122
+// the compiler takes when left alone): 512 x 96 leaves a quarter of the SM's register file to the concurrent schedule
+// pre-pass experiment (owner_schedule_tab_kernel<.., 256, true>).
 template <int D, bool CACHED, bool LONGLIST>
+#ifndef URE_OWNER_REGS
+#define URE_OWNER_REGS 0                  // 96: the build the concurrent pre-pass experiment needs (tools/build_variant.sh)
+#endif
+#if URE_OWNER_REGS
+__global__ void __maxnreg__(D <= 32 ? URE_OWNER_REGS : 128)
+#else
 __global__ void __launch_bounds__(kOwnThreads, 1)
+#endif
 mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams_t hp, int epochs,
                 long long step_begin, long long step_end, OwnerWs* ws, unsigned dbg) {
   constexpr int CH = D / 4;                // float4 chunks of a row
@@ -937,11 +969,12 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
   __shared__ ure_mf_shard_t s_sh;
   __shared__ float s_wsse[NW];
   __shared__ int s_total;                  // entries of the batch list in s_list
+  __shared__ int s_abort;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gl = lane % G, gw = lane / G;
   if (hp.owner_plan && ld_acquire_u32(reinterpret_cast<const unsigned*>(&ws->error)) == 2u) return;   // uniform over the grid: the pre-pass found the remembered capacities too small
   make_plan(shards, K, blockIdx.x, gridDim.x, s_pl, s_ps);
-  if (tid == 0) s_sh = shards[s_pl.shard];
+  if (tid == 0) { s_sh = shards[s_pl.shard]; s_abort = 0; }
   __syncthreads();
   const ure_mf_shard_t& sh = s_sh;
   const int ru0 = s_pl.ru0, ri0 = s_pl.ri0, mU = s_pl.mU;
@@ -980,13 +1013,29 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
   const int* const sched_off = hp.owner_sched_off + (long long)blockIdx.x * (hp.owner_spe_cap + 1);
   const long long off_row = (long long)gridDim.x * (hp.owner_spe_cap + 1);
   // where the batch list of (epoch ep, step kk) lives: false = outside the scheduled window
+  // concurrent pre-pass (hp.owner_ready): row r of THIS CTA's lists is complete once ready[blockIdx.x * rows + r] is
+  // non-zero (written with release semantics by the pre-pass CTA of the same index, which runs on this SM's spare
+  // registers while the kernel trains).  A row that does not arrive within ~2 s raises error 3 for the whole grid.
+  int ready_rows = hp.owner_ready ? 0 : 0x7fffffff;            // rows known to be complete
   auto find_list = [&](int ep, int kk, const unsigned short*& src, int& len) {
     const int row = ep - sched_e0;
     src = sched;
     len = 0;
     if (row < 0 || row >= hp.owner_sched_rows) return false;
+    if (row >= ready_rows) {
+      const unsigned* const flag = reinterpret_cast<const unsigned*>(hp.owner_ready) +
+                                   (long long)blockIdx.x * hp.owner_sched_rows + row;
+      long long spins = 0;
+      unsigned v;
+      while ((v = ld_acquire_u32(flag)) == 0u) {
+        if (++spins > (1ll << 22)) { atomicMax(&ws->error, 3); v = 2u; break; }
+        __nanosleep(64);
+      }
+      if (v != 1u) return false;           // timed out, or the pre-pass found the remembered capacities too small
+      ready_rows = row + 1;
+    }
     const int* o = sched_off + row * off_row + kk;
-    const int a = __ldg(o), b = __ldg(o + 1);
+    const int a = __ldcg(o), b = __ldcg(o + 1);
     src = sched + row * hp.owner_sched_stride + a;
     len = b - a;
     return true;
@@ -1031,7 +1080,7 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
     cur_src = src;
     if (len <= lcap)
       for (int x = tid; x < len; x += kOwnThreads) {
-        const int sl = __ldg(src + x);
+        const int sl = __ldcg(src + x);
         s_list[x] = (unsigned short)sl;
         if (!CACHED) s_rec[x] = pack_rec(load_rec(sl), sl >= mU);
       }
@@ -1059,9 +1108,10 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
 
   for (long long t = step_begin; t < t_end; ++t) {
     if (!in_window) {                      // uniform over the shard's CTAs: all of them stop at the same step
-      if (tid == 0) ws->error = 1;
+      if (tid == 0) atomicMax(&ws->error, 1);
       break;
     }
+    if (hp.owner_ready && ld_acquire_u32(reinterpret_cast<const unsigned*>(&ws->error)) >= 2u) break;
     const bool rd = (t - step_begin) & 1;
     const float* const Pr = rd ? sh.gP : sh.P;
     const float* const Qr = rd ? sh.gQ : sh.Q;
@@ -1080,7 +1130,7 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
 #pragma unroll
     for (int i = 0; i < PF; ++i) {         // next step's list on its way into registers
       const int x = tid + i * kOwnThreads;
-      pf[i] = x < nx_len ? __ldg(nx_src + x) : (unsigned short)0;
+      pf[i] = x < nx_len ? __ldcg(nx_src + x) : (unsigned short)0;
     }
 
     // -------------------------------------------------------------- waves: this warp's contiguous share of the
@@ -1325,7 +1375,7 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
         }
       }
       for (int x = tid + PF * kOwnThreads; x < stage; x += kOwnThreads) {
-        const int sl = __ldg(nx_src + x);
+        const int sl = __ldcg(nx_src + x);
         s_list[x] = (unsigned short)sl;
         if (!CACHED) s_rec[x] = pack_rec(load_rec(sl), sl >= mU);
       }
@@ -1345,10 +1395,16 @@ mf_owner_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams
         if (epoch_sse != 0.0) atomicAdd(sh.sse + e, epoch_sse);
         epoch_sse = 0.0;
       }
+      unsigned polls = 0;
       while (ld_acquire_u32(counter) < bar_target) {
+        if (hp.owner_ready && (++polls & 1023u) == 0u && ld_acquire_u32(reinterpret_cast<const unsigned*>(&ws->error)) >= 2u) {
+          s_abort = 1;                         // a CTA gave up waiting for its lists: nobody may wait for it
+          break;
+        }
       }
     }
     __syncthreads();
+    if (s_abort) break;
     URE_STAMP(5)
     if (last_of_epoch) { ++e; k = 0; nlr = -lr_of(e); }
     else ++k;
@@ -1375,6 +1431,64 @@ int max_dyn_smem(int* out) {
   return 0;
 }
 
+// side stream + events of the concurrent pre-pass: one set per device, created on first use and kept for the life of
+// the process (the one piece of state the library holds; nothing the caller owns is referenced by it)
+struct CoStreams {
+  cudaStream_t side;
+  cudaEvent_t ev_in, ev_out;
+};
+int co_streams(CoStreams** out) {
+  static CoStreams table[64];
+  static bool made[64] = {};
+  int dev = 0;
+  URE_CUDA(cudaGetDevice(&dev));
+  URE_REQUIRE(dev >= 0 && dev < 64, URE_EUNSUPPORTED, "device index %d", dev);
+  if (!made[dev]) {
+    URE_CUDA(cudaStreamCreateWithFlags(&table[dev].side, cudaStreamNonBlocking));
+    URE_CUDA(cudaEventCreateWithFlags(&table[dev].ev_in, cudaEventDisableTiming));
+    URE_CUDA(cudaEventCreateWithFlags(&table[dev].ev_out, cudaEventDisableTiming));
+    made[dev] = true;
+  }
+  *out = &table[dev];
+  return 0;
+}
+
+constexpr int kCoThreads = 256;
+constexpr int kCoWarps = kCoThreads / 32;
+inline long long schedule_co_smem_bytes(int cap_slots, int tab_cap) {
+  // step + rank [cap] u16 | counters [warps][64] int | scan scratch | round tables 2 sets x 4 x [tab_cap] u16
+  return 2ll * cap_slots + 4ll * kCoWarps * 64 + 4ll * (kCoWarps + 4) + 2ll * 2 * 4 * tab_cap + 64;
+}
+// tab_cap / sb of the concurrent pre-pass, or tab_cap = 0 when the batch does not qualify (long epochs, halves beyond
+// the table size, per-warp ranges beyond the packed rank, a window shorter than the training)
+void schedule_co_params(const ure_mf_hparams_t& hp, int epochs, int* tab_cap, int* sb) {
+  *tab_cap = 0;
+  *sb = 1;
+  while ((1 << *sb) < hp.owner_spe_cap) ++*sb;
+  if (hp.owner_max_n <= 1 || hp.owner_spe_cap > 64 || hp.owner_sched_rows < epochs || hp.d > 32) return;
+  FeistelDomain dom;
+  dom.init((uint32_t)hp.owner_max_n);
+  const int cap = (int)((dom.a > dom.b ? dom.a : dom.b) + 2 + 7) / 8 * 8;
+  const int per = (((hp.owner_cap_slots + kCoWarps - 1) / kCoWarps) + 31) & ~31;
+  if (cap > kTabMaxHalf || per >= (1 << (16 - *sb))) return;
+  *tab_cap = cap;
+}
+int launch_schedule_co(const ure_mf_shard_t* d_shards, int K, const ure_mf_hparams_t& hp, int epochs, long long step0,
+                       cudaStream_t side) {
+  int tab_cap = 0, sb = 1;
+  schedule_co_params(hp, epochs, &tab_cap, &sb);
+  URE_REQUIRE(tab_cap > 0 && step0 == hp.owner_sched_step0, URE_EINVAL,
+              "ure_mf_train(owner): hparams.owner_ready is set but the batch does not qualify for the concurrent "
+              "pre-pass (ure_mf_owner_concurrent_ok)");
+  const long long need = schedule_co_smem_bytes(hp.owner_cap_slots, tab_cap);
+  auto kern = owner_schedule_tab_kernel<4, kCoThreads, true>;
+  URE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+  URE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  kern<<<dim3(num_sms(), 1), kCoThreads, (size_t)need, side>>>(d_shards, K, hp, epochs, step0, tab_cap, sb);
+  URE_CUDA(cudaGetLastError());
+  return 0;
+}
+
 template <int D>
 int launch_owner(const ure_mf_shard_t* d_shards, int K, const ure_mf_hparams_t& hp, int epochs, long long s0,
                  long long s1, OwnerWs* ws, int smem, bool cached, unsigned dbg, cudaStream_t st) {
@@ -1386,7 +1500,35 @@ int launch_owner(const ure_mf_shard_t* d_shards, int K, const ure_mf_hparams_t& 
   URE_CUDA(cudaMemsetAsync(ws->bar, 0, sizeof(ws->bar), st));
   void* args[] = {(void*)&d_shards, (void*)&K,  (void*)&hp, (void*)&epochs,
                   (void*)&s0,       (void*)&s1, (void*)&ws, (void*)&dbg};
-  URE_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(num_sms()), dim3(kOwnThreads), args, (size_t)smem, st));
+  if (!hp.owner_ready) {
+    URE_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(num_sms()), dim3(kOwnThreads), args, (size_t)smem, st));
+    return 0;
+  }
+  // ---- concurrent schedule pre-pass (experiment, kernels.CONCURRENT_SCHEDULE / URE_SCHED_CO=1; off by default).
+  // The pre-pass is queued on a side stream behind everything the caller's stream holds up to here (the owner
+  // set-up), then the training kernel on the caller's stream -- an ordinary launch: a cooperative one does not share
+  // the device with a kernel of another stream; one CTA per SM is all that fits, so the grid is co-resident all the
+  // same -- and the caller's stream waits for the side stream after it.  All of an SM's shared memory is asked for,
+  // so that the second kernel fits the carve-out the first one set.  The pre-pass never waits for the training
+  // kernel, so nothing can dead-lock; the training kernel gives up on a row after ~2 s (error 3).
+  // MEASURED (C2 step, profiles/r2_notes.md): the two kernels do share the SMs (pre-pass 1.24 ms next to training),
+  // but the training kernel -- a dependent instruction stream at 16 warps per SM -- slows by as much as the pre-pass
+  // costs alone (2.27 -> 2.61 ms): device-resident step 3.22 vs 3.20 ms, end to end 3.75 vs 3.82 ms.
+  static const int seq = getenv("URE_SCHED_CO_SEQ") ? atoi(getenv("URE_SCHED_CO_SEQ")) : 0;
+  if (seq) {                               // debugging aid: the same two kernels one after the other on one stream
+    if (int rc = launch_schedule_co(d_shards, K, hp, epochs, s0, st)) return rc;
+    URE_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(num_sms()), dim3(kOwnThreads), args, (size_t)smem, st));
+    return 0;
+  }
+  CoStreams* cs = nullptr;
+  if (int rc = co_streams(&cs)) return rc;
+  URE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  URE_CUDA(cudaEventRecord(cs->ev_in, st));
+  URE_CUDA(cudaStreamWaitEvent(cs->side, cs->ev_in, 0));
+  if (int rc = launch_schedule_co(d_shards, K, hp, epochs, s0, cs->side)) return rc;
+  URE_CUDA(cudaEventRecord(cs->ev_out, cs->side));
+  URE_CUDA(cudaLaunchKernel((void*)kern, dim3(num_sms()), dim3(kOwnThreads), args, (size_t)smem, st));
+  URE_CUDA(cudaStreamWaitEvent(st, cs->ev_out, 0));
   return 0;
 }
 
@@ -1445,6 +1587,21 @@ int mf_train_owner(const ure_mf_shard_t* d_shards, int n_shards, const ure_mf_hp
 
 }  // namespace ure
 
+extern "C" int ure_mf_owner_concurrent_ok(const ure_mf_hparams_t* h_hp, int epochs) {
+  using namespace ure;
+  if (!h_hp || h_hp->mode != URE_MF_OWNER) return 0;
+#if !URE_OWNER_REGS
+  return 0;                                // the training kernel of this build leaves no registers for a second kernel
+#endif
+  int tab_cap = 0, sb = 1, avail = 0;
+  schedule_co_params(*h_hp, epochs, &tab_cap, &sb);
+  if (tab_cap <= 0 || max_dyn_smem(&avail) != 0) return 0;
+  // both kernels on one SM: the training CTA's shared memory + the pre-pass CTA's + static and reserved parts
+  const long long train = owner_smem_bytes(h_hp->d, h_hp->owner_cap_rows, h_hp->owner_cap_slots, h_hp->owner_cap_list,
+                                           (h_hp->owner_flags & 1) != 0);
+  return train + schedule_co_smem_bytes(h_hp->owner_cap_slots, tab_cap) + 20 * 1024 <= (long long)avail + 8 * 1024 ? 1 : 0;
+}
+
 extern "C" int64_t ure_mf_owner_smem_bytes(int d, int cap_rows, int cap_slots, int cap_list, int spe_cap, int flags) {
   const long long a = ure::owner_smem_bytes(d, cap_rows, cap_slots, cap_list, (flags & 1) != 0);
   const long long b = ure::schedule_smem_bytes(cap_slots, spe_cap, (flags & 2) == 0);
@@ -1456,6 +1613,8 @@ extern "C" int ure_mf_owner_schedule(const ure_mf_shard_t* d_shards, int n_shard
   using namespace ure;
   URE_REQUIRE(d_shards && h_hp && h_hp->owner_sched && h_hp->owner_sched_off, URE_EINVAL,
               "ure_mf_owner_schedule: null argument");
+  URE_REQUIRE(!h_hp->owner_ready, URE_EINVAL,
+              "ure_mf_owner_schedule: hparams.owner_ready is set -- the concurrent pre-pass is launched by ure_mf_train");
   URE_REQUIRE(h_hp->owner_sched_rows >= 1 && h_hp->owner_spe_cap >= 1 && h_hp->owner_spe_cap <= kMaxSpe &&
                   h_hp->owner_cap_slots % 16 == 0 && h_hp->owner_cap_slots <= 65520,
               URE_EUNSUPPORTED, "ure_mf_owner_schedule: rows=%d spe_cap=%d cap_slots=%d outside the supported range",
@@ -1483,7 +1642,8 @@ extern "C" int ure_mf_owner_schedule(const ure_mf_shard_t* d_shards, int n_shard
     const int nt = nt_env >= 4 ? 4 : nt_env >= 2 ? 2 : 0;
     const long long need_t = schedule_tab_smem_bytes(h_hp->owner_cap_slots, tab_cap, nt);
     if (nt_env >= 0 && tab_cap > 0 && h_hp->owner_spe_cap <= 64 && per < (1 << (16 - sb)) && need_t <= avail) {
-      auto kern = nt == 4 ? owner_schedule_tab_kernel<4> : nt == 2 ? owner_schedule_tab_kernel<2> : owner_schedule_tab_kernel<0>;
+      auto kern = nt == 4 ? owner_schedule_tab_kernel<4, kSchedThreads, false>
+                          : nt == 2 ? owner_schedule_tab_kernel<2, kSchedThreads, false> : owner_schedule_tab_kernel<0, kSchedThreads, false>;
       URE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need_t));
       const int ny2 = h_hp->owner_sched_rows < 2 ? h_hp->owner_sched_rows : 2;     // 2 CTAs per SM: one wave
       kern<<<dim3(num_sms(), ny2), kSchedThreads, (size_t)need_t, static_cast<cudaStream_t>(stream)>>>(

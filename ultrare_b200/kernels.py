@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 import time
 from typing import List, Optional, Sequence
 
@@ -681,6 +682,10 @@ class ShardBatch:
                 t1 = step_end
                 if self.mode in ("owner", "runs"):
                     t1 = min(step_end, self._schedule_window())
+                if getattr(self, "concurrent", False):
+                    if self.step != 0 or t1 != self.total_steps:
+                        raise RuntimeError("ultrare_b200: a batch built with whole_training=True trains all steps in one call")
+                    self.launches_per_pass += 1        # the concurrent pre-pass
                 check(L.ure_mf_train(_ptr(self.table), self.n_shards, C.byref(self.hp), self.epochs,
                                      self.step, t1, self.warps_group0, _ptr(self.ws), _stream()), "ure_mf_train")
                 self.launches_per_pass += 1
@@ -692,6 +697,11 @@ class ShardBatch:
         L = _lib.lib()
         a, b = self._sched_cover
         rows = self.hp.owner_sched_rows if self.mode == "owner" else self.hp.runs_rows
+        if getattr(self, "concurrent", False):
+            # ure_mf_train launches the pre-pass next to the training kernel: one window, one training call
+            self._sched_cover = (0, self.total_steps)
+            self.hp.owner_sched_step0 = 0
+            return self.total_steps
         if not (a <= self.step < b):
             with torch.cuda.device(self.device):
                 if self.mode == "owner":
@@ -719,6 +729,8 @@ class ShardBatch:
             st.bufP.zero_()
             st.bufQ.zero_()
             st.sse.zero_()
+        if getattr(self, "concurrent", False):
+            self._ready.zero_()                         # the pre-pass runs again next to the training kernel
         self.step = 0
 
     def flush(self) -> None:
@@ -756,6 +768,10 @@ class ShardBatch:
             vals = host[:nb].view(torch.float64).numpy().reshape(K, E).copy()
             err = int(host[nb:nb + 4].view(torch.int32).item()) if owner else 0
             _PINNED_BYTES.setdefault(host.shape[0], []).append((host, None))
+            if err == 3:
+                global CONCURRENT_SCHEDULE
+                CONCURRENT_SCHEDULE = False
+                raise ConcurrentScheduleStall("ultrare_b200: the concurrent schedule pre-pass stalled; repeat the pass")
             if err == 2:
                 _PLAN_HINTS.pop(getattr(self, "_plan_sig", None), None)
                 raise PlanHintMiss("ultrare_b200: the remembered owner plan does not cover this batch; repeat the pass")
@@ -791,6 +807,14 @@ class PlanHintMiss(RuntimeError):
     set-up kernels found: nothing was trained; the caller repeats the pass (the hint is gone, so it waits for the plan)."""
 
 
+class ConcurrentScheduleStall(PlanHintMiss):
+    """The concurrent schedule pre-pass did not deliver a row within the training kernel's patience (it could not be
+    co-scheduled on this device?): nothing usable was trained; CONCURRENT_SCHEDULE is switched off, repeat the pass."""
+
+
+# Schedule pre-pass NEXT TO the training kernel (hparams.owner_ready) instead of before it.  Off by default: measured on
+# the C2 step, the training kernel slows by as much as the pre-pass costs alone (profiles/r2_notes.md).
+CONCURRENT_SCHEDULE = os.environ.get("URE_SCHED_CO", "0") == "1"
 _PLAN_HINTS = {}          # batch signature -> (max_rows, max_slots, max_spe, smem) of the last plan read back
 PLAN_HINT_MARGIN = 0.03   # capacities of an optimistic launch: the remembered maxima plus this fraction
 
@@ -807,11 +831,14 @@ class ArenaShardBatch(ShardBatch):
     def __init__(self, recs, rows_P, n_item: int, d: int, batch: int, epochs: int, shard_ids, perm_seed: int = 42,
                  perms=None, lr: float = 1e-3, lr_decay: float = 0.95, lr_step: int = 50, weight_decay: float = 0.1,
                  momentum: float = 0.9, generator=None, std: float = 1.0, mode: str = "auto", owner_cache: bool = True,
-                 optimistic: bool = False):
+                 optimistic: bool = False, whole_training: bool = False):
         """optimistic: the caller reads the training losses (train_losses_async) only after everything that depends
         on the training is queued, and repeats the pass on PlanHintMiss.  The launch is then queued with the
         capacities of the last plan read back for the same shapes (+ PLAN_HINT_MARGIN) instead of waiting for this
-        one's -- the kernels compare them with the real plan on the device (hparams.owner_plan)."""
+        one's -- the kernels compare them with the real plan on the device (hparams.owner_plan).
+        whole_training: the caller will train all steps with ONE train() call.  The schedule pre-pass then runs
+        CONCURRENTLY with the training kernel (hparams.owner_ready) when the batch qualifies
+        (ure_mf_owner_concurrent_ok), on the registers and shared memory the training kernel leaves free."""
         K = self.n_shards = len(recs)
         tq = [("start", time.perf_counter())]                # host stamps of the constructor (diagnostics: ctor_ms)
         stamp = lambda name: tq.append((name, time.perf_counter()))
@@ -863,7 +890,7 @@ class ArenaShardBatch(ShardBatch):
         stamp("alloc")
         self.table_ptr = base + int(lay.table)
         self.ws = self.arena[int(lay.ws):int(lay.ws) + int(L.ure_mf_train_workspace_bytes())]
-        self.mode, self.optimistic, self.step = "dense", False, 0
+        self.mode, self.optimistic, self.step, self.concurrent = "dense", False, 0, False
         info = (C.c_int32 * 8)()
         force = OWNER_FORCE if OWNER_FORCE is not None else (-1, 0)
         sig = (K, d, batch, int(n_item), tuple(self._rows_P), self.epochs, perms is not None, bool(owner_cache),
@@ -932,6 +959,12 @@ class ArenaShardBatch(ShardBatch):
                 self.mode = "owner"
                 self._sched_cover = (0, 0)
                 self._spes = [-(-n // batch) for n in ns if n > 0]
+                self.concurrent = bool(whole_training and CONCURRENT_SCHEDULE and self.total_steps > 0 and
+                                       L.ure_mf_owner_concurrent_ok(C.byref(self.hp), self.epochs))
+                self.owner_plan["concurrent_schedule"] = self.concurrent
+                if self.concurrent:
+                    self.hp.owner_ready = base + int(lay.ready)
+                    self._ready = self.arena[int(lay.ready):int(lay.ready) + 4 * int(lay.grid) * int(lay.sched_rows)]
                 if self.optimistic:
                     self._schedule_window()              # the pre-pass is queued before anything else
                     stamp("schedule_queued")

@@ -200,7 +200,8 @@ class Sisa(Scratch):
         self.dist.all_reduce(out)
         vals = kn.download_many([out])[0]
         if vals[4] > 0:                        # on some rank: every rank repeats the pass (Sisa._retrying)
-            raise kn.PlanHintMiss("ultrare_b200: a rank's remembered owner plan did not cover its batch")
+            raise kn.PlanHintMiss("ultrare_b200: a rank's remembered owner plan did not cover its batch (or its "
+                                  "concurrent pre-pass stalled)")
         n_test = sum(len(t.dataset) for t in test_dlist)
         users = max(vals[3], 1.0)
         return float(np.sqrt(vals[0] / max(1, n_test))), float(vals[1] / users), float(vals[2] / users)
@@ -280,7 +281,7 @@ class Sisa(Scratch):
                                         perms if any(p is not None for p in perms) else None, self.lr, self.lr_decay,
                                         50, self.lam, self.momentum,
                                         generator=lambda: model_generator(self.seed, mine[0] + 1, self.device),
-                                        optimistic=optimistic)
+                                        optimistic=optimistic, whole_training=mode in ('none', 'final', 'faithful-last'))
                 states = None
             else:
                 for j, i in enumerate(mine):
@@ -542,6 +543,13 @@ class Sisa(Scratch):
             return once(*args)
         except kn.PlanHintMiss:
             kn._PLAN_HINTS.clear()
+            if self.dist.world > 1:
+                # was it a stalled concurrent pre-pass somewhere?  Every rank is here (the flag travelled with the
+                # all-reduced sums), so one more scalar reduction is safe; the mode goes off on all ranks together
+                sb = getattr(self, '_last_batch', None)
+                mine = int(sb.ws[16:20].view(torch.int32).item()) == 3 if sb is not None else False
+                if self.dist.max_float(1.0 if mine else 0.0) > 0:
+                    kn.CONCURRENT_SCHEDULE = False
             self._pending_logs = None
             self._join_writers()
             return once(*args)

@@ -158,6 +158,8 @@ int ure_abi_version(void);
 /* Asynchronous copy of `bytes` from device memory to PAGE-LOCKED host memory on `stream` (results of a pass:
  * user_mat / item_mat tables, method/scratch.py:131-144 -- one call per contiguous run of tables). */
 int ure_copy_to_host_async(void* h_dst, const void* d_src, int64_t bytes, void* stream);
+/* ... and the other direction: page-locked host memory -> device (the float64 [3, n] arrays of read.py:64-68). */
+int ure_copy_to_device_async(void* d_dst, const void* h_src, int64_t bytes, void* stream);
 
 /* Bytes of device scratch ure_mf_train needs (grid barrier + step tables). */
 int64_t ure_mf_train_workspace_bytes(void);
@@ -199,6 +201,19 @@ int64_t ure_mf_owner_smem_bytes(int d, int cap_rows, int cap_slots, int cap_list
  * ure_mf_train may then run any steps [a, b) with step0 <= a whose epochs lie inside the window
  * (hparams.owner_sched_step0 = step0); a step outside it stops the shard and raises the workspace's error
  * word (int32 at byte 16). */
+/* Pipelined set-up: shards [shard0, shard0 + n_part) of the batch only (count, scan, radix passes; no plan kernel, no
+ * inverse visiting orders: shards with explicit orders use ure_mf_owner_prepare) on a workspace the caller has cleared;
+ * ure_mf_owner_cta_split gives the training CTAs per shard (h_c[n_shards], from the shard sizes h_n alone), and
+ * ure_mf_owner_schedule_part runs the pre-pass for the CTAs [cta0, cta0 + cta_n) of shards that are set up -- so a
+ * caller that uploads shard after shard overlaps set-up + pre-pass of one shard with the upload of the next
+ * (capacities from a remembered plan, hparams.owner_plan set: no plan exists yet). */
+int ure_mf_owner_prepare_part(const ure_mf_shard_t* d_shards, int n_shards, int shard0, int n_part,
+                              const ure_mf_hparams_t* h_hp, int epochs, int max_rows, int32_t* d_radix_hist,
+                              void* d_workspace, void* stream);
+int ure_mf_owner_cta_split(const int32_t* h_n, int n_shards, int32_t* h_c);
+int ure_mf_owner_schedule_part(const ure_mf_shard_t* d_shards, int n_shards, const ure_mf_hparams_t* h_hp, int epochs,
+                               int64_t step0, int cta0, int cta_n, void* stream);
+
 /* 1 when a batch with these (planned) hparams can run the schedule pre-pass concurrently with the training kernel
  * (hparams.owner_ready): short epochs, d <= 32, one window for all epochs, both kernels' shared memory on one SM. */
 int ure_mf_owner_concurrent_ok(const ure_mf_hparams_t* h_hp, int epochs);
@@ -243,6 +258,8 @@ int ure_mf_batch_layout(const ure_mf_batch_shard_t* h_shards, int n_shards, int 
  * reused before the stream has passed this call), clears momentum / gradient scratch / losses / workspace / row
  * offsets, queues ure_mf_owner_prepare when lay->owner, and queues the copy of the plan (4 int32, see
  * ure_mf_owner_prepare) to h_stage + 176*K.  The weights (lay->W) are left to the caller. */
+#define URE_BATCH_NO_PREPARE 2    /* flags: do not queue ure_mf_owner_prepare either: the caller sets the shards up one by one
+                                   * (ure_mf_owner_prepare_part), each as soon as its records have arrived            */
 #define URE_BATCH_NO_PLAN 1       /* flags: do not compute / copy the plan (the launch runs on remembered capacities,
                                    * hparams.owner_plan set) */
 int ure_mf_batch_setup(const ure_mf_batch_shard_t* h_shards, int n_shards, int n_item, const ure_mf_hparams_t* h_hp,

@@ -79,6 +79,9 @@ SIGNATURES = {
     "ure_mf_owner_smem_bytes": (_i64, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "ure_mf_owner_schedule": (C.c_int, [_p, C.c_int, C.POINTER(MFHParams), C.c_int, _i64, _p]),
     "ure_mf_owner_concurrent_ok": (C.c_int, [C.POINTER(MFHParams), C.c_int]),
+    "ure_mf_owner_prepare_part": (C.c_int, [_p, C.c_int, C.c_int, C.c_int, C.POINTER(MFHParams), C.c_int, C.c_int, _p, _p, _p]),
+    "ure_mf_owner_cta_split": (C.c_int, [C.POINTER(_i32), C.c_int, C.POINTER(_i32)]),
+    "ure_mf_owner_schedule_part": (C.c_int, [_p, C.c_int, C.POINTER(MFHParams), C.c_int, _i64, C.c_int, C.c_int, _p]),
     "ure_mf_batch_layout": (C.c_int, [C.POINTER(MFBatchShard), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _i64,
                                        C.POINTER(MFBatchLayout)]),
     "ure_mf_batch_setup": (C.c_int, [C.POINTER(MFBatchShard), C.c_int, C.c_int, C.POINTER(MFHParams), C.c_int, C.c_uint32,
@@ -92,6 +95,7 @@ SIGNATURES = {
     "ure_mf_train_trace": (C.c_int, [_p, _p, C.c_int, _p]),
     "ure_mf_grid_size": (C.c_int, []),
     "ure_copy_to_host_async": (C.c_int, [_p, _p, _i64, _p]),
+    "ure_copy_to_device_async": (C.c_int, [_p, _p, _i64, _p]),
     "ure_mf_debug_flags": (C.c_int, [_p, C.c_uint32, _p]),
     "ure_mf_flush": (C.c_int, [C.POINTER(MFShard), C.c_int, C.POINTER(MFHParams), C.c_int, _i64, _p]),
     "ure_ensemble_score": (C.c_int, [_p, _p, C.c_int, C.c_int, _p, _i64, _f32, _p, _p, _p]),

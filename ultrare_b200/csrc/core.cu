@@ -76,3 +76,13 @@ extern "C" int ure_copy_to_host_async(void* h_dst, const void* d_src, int64_t by
   URE_CUDA(cudaMemcpyAsync(h_dst, d_src, (size_t)bytes, cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)));
   return 0;
 }
+
+// Asynchronous PAGE-LOCKED host -> device copy on the caller's stream (the uploads of RatingData: one driver call per
+// array instead of a framework dispatch).
+extern "C" int ure_copy_to_device_async(void* d_dst, const void* h_src, int64_t bytes, void* stream) {
+  using namespace ure;
+  URE_REQUIRE(bytes >= 0 && (bytes == 0 || (d_dst && h_src)), URE_EINVAL, "ure_copy_to_device_async: bad argument");
+  if (bytes == 0) return 0;
+  URE_CUDA(cudaMemcpyAsync(d_dst, h_src, (size_t)bytes, cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream)));
+  return 0;
+}

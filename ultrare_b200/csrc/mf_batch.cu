@@ -131,7 +131,7 @@ extern "C" int ure_mf_batch_setup(const ure_mf_batch_shard_t* h_shards, int n_sh
   }
   URE_CUDA(cudaMemcpyAsync(base + lay->table, tab, (size_t)n_shards * sizeof(ure_mf_shard_t), cudaMemcpyHostToDevice, st));
   URE_CUDA(cudaMemsetAsync(base + lay->ws, 0, (size_t)(lay->zero_end - lay->ws), st));
-  if (lay->owner) {
+  if (lay->owner && !(flags & URE_BATCH_NO_PREPARE)) {
     bool any_perm = false;
     for (int s = 0; s < n_shards; ++s) any_perm |= h_shards[s].perm != nullptr;
     const bool no_plan = (flags & URE_BATCH_NO_PLAN) != 0;

@@ -206,12 +206,12 @@ __device__ __forceinline__ void note_order(const ure_mf_shard_t& sh, long long j
   reinterpret_cast<int4*>(sh.inter_u)[j] = make_int4(r.x, r.y, r.z, (int)j);
 }
 
-__global__ void csr_count_kernel(const ure_mf_shard_t* shards, int smem_rows, OwnerWs* ws) {
+__global__ void csr_count_kernel(const ure_mf_shard_t* shards, int smem_rows, unsigned* unsorted_flags) {
   extern __shared__ int s_cnt[];
   const ure_mf_shard_t& sh = shards[blockIdx.y];
   const long long stride = (long long)gridDim.x * blockDim.x;
   const int nu = sh.n_user, rows = sh.n_user + sh.n_item;
-  unsigned* const unsorted = ws ? &ws->unsorted[blockIdx.y] : nullptr;
+  unsigned* const unsorted = unsorted_flags ? unsorted_flags + blockIdx.y : nullptr;
   if (smem_rows > 0 && rows <= smem_rows) {
     for (int x = threadIdx.x; x < rows; x += blockDim.x) s_cnt[x] = 0;
     __syncthreads();
@@ -301,9 +301,9 @@ struct RadixView {                        // what pass `pass` of grid row y = 2*
 
 // hist [grid.y][grid.x][256]: records of the CTA's tile per digit value
 __global__ void __launch_bounds__(kRadixThreads)
-radix_hist_kernel(const ure_mf_shard_t* shards, int pass, int npass, int* __restrict__ hist, const OwnerWs* ws) {
+radix_hist_kernel(const ure_mf_shard_t* shards, int pass, int npass, int* __restrict__ hist, const unsigned* unsorted) {
   __shared__ int s_h[256];
-  if (ws && !(blockIdx.y & 1) && ws->unsorted[blockIdx.y >> 1] == 0) return;      // user side already in order
+  if (unsorted && !(blockIdx.y & 1) && unsorted[blockIdx.y >> 1] == 0) return;      // user side already in order
   const RadixView v(shards, pass, npass);
   for (int x = threadIdx.x; x < 256; x += blockDim.x) s_h[x] = 0;
   __syncthreads();
@@ -324,9 +324,9 @@ radix_hist_kernel(const ure_mf_shard_t* shards, int pass, int npass, int* __rest
 
 // per grid row y: exclusive scan of hist in (digit, CTA) order, in place; one CTA of 256 threads per y
 __global__ void __launch_bounds__(256)
-radix_scan_kernel(int* __restrict__ hist, int n_blocks, const OwnerWs* ws) {
+radix_scan_kernel(int* __restrict__ hist, int n_blocks, const unsigned* unsorted) {
   __shared__ int s_tot[256];
-  if (ws && !(blockIdx.x & 1) && ws->unsorted[blockIdx.x >> 1] == 0) return;
+  if (unsorted && !(blockIdx.x & 1) && unsorted[blockIdx.x >> 1] == 0) return;
   int* h = hist + (long long)blockIdx.x * n_blocks * 256 + threadIdx.x;      // thread = digit: coalesced per CTA row
   int tot = 0;
   for (int b = 0; b < n_blocks; ++b) tot += h[b * 256];
@@ -357,9 +357,9 @@ radix_scan_kernel(int* __restrict__ hist, int n_blocks, const OwnerWs* ws) {
 // stable scatter of the CTA's tile: every warp owns a contiguous range; per-warp digit counts -> per-warp cursors
 // (from the CTA's global offsets); inside a warp __match_any ranks the lanes of one digit in lane (= record) order
 __global__ void __launch_bounds__(kRadixThreads)
-radix_scatter_kernel(const ure_mf_shard_t* shards, int pass, int npass, const int* __restrict__ hist, const OwnerWs* ws) {
+radix_scatter_kernel(const ure_mf_shard_t* shards, int pass, int npass, const int* __restrict__ hist, const unsigned* unsorted) {
   __shared__ int s_wh[kRadixWarps][256];
-  if (ws && !(blockIdx.y & 1) && ws->unsorted[blockIdx.y >> 1] == 0) return;
+  if (unsorted && !(blockIdx.y & 1) && unsorted[blockIdx.y >> 1] == 0) return;
   const RadixView v(shards, pass, npass);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned lt = (1u << lane) - 1u;
@@ -721,7 +721,8 @@ __host__ __device__ inline long long schedule_tab_smem_bytes(int cap_slots, int 
 template <int NT, int NTHR, bool CO>
 __global__ void __maxnreg__(CO ? 56 : 64)
 owner_schedule_tab_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_mf_hparams_t hp, int epochs,
-                          long long step0, int tab_cap, int sb) {
+                          long long step0, int tab_cap, int sb, int cta0, int n_cta) {
+  const int cta = cta0 + (int)blockIdx.x;  // the training CTA this block serves (a launch may cover a sub-range)
   constexpr int kSchedThreads = NTHR;      // (shadows the namespace constant: every loop below strides by the CTA size)
   constexpr int NW = NTHR / 32;
   constexpr unsigned FULL = 0xffffffffu;
@@ -730,7 +731,7 @@ owner_schedule_tab_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_
   __shared__ PlanScratch s_ps;
   __shared__ Plan s_pl;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  make_plan(shards, K, blockIdx.x, gridDim.x, s_pl, s_ps);
+  make_plan(shards, K, cta, n_cta, s_pl, s_ps);
   const ure_mf_shard_t& sh = shards[s_pl.shard];
   const int mU = s_pl.mU, m = mU + s_pl.mI;
   const int B = hp.batch, n = sh.n;
@@ -738,7 +739,7 @@ owner_schedule_tab_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_
   if (plan_not_covered(hp, s_pl, spe)) {
     if (CO)                                // the training CTA of this index is (or will be) waiting: tell it to give up
       for (int r = tid; r < hp.owner_sched_rows; r += kSchedThreads)
-        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(hp.owner_ready + (long long)blockIdx.x * hp.owner_sched_rows + r),
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(hp.owner_ready + (long long)cta * hp.owner_sched_rows + r),
                      "r"(2u) : "memory");
     return;
   }
@@ -801,7 +802,7 @@ owner_schedule_tab_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_
     const int epoch = e_first + r;
     if (epoch >= epochs) break;
     unsigned short* const out = hp.owner_sched + (long long)r * hp.owner_sched_stride + s_pl.slot_base;
-    int* const off = hp.owner_sched_off + ((long long)r * gridDim.x + blockIdx.x) * (spe_cap + 1);
+    int* const off = hp.owner_sched_off + ((long long)r * n_cta + cta) * (spe_cap + 1);
     FeistelKeys ks;
     ks.init(perm_key(sh.perm_seed, (uint32_t)sh.shard_id, (uint32_t)epoch));
     const int32_t* const pinv = explicit_order ? sh.perm_inv + (long long)epoch * n : nullptr;
@@ -917,7 +918,7 @@ owner_schedule_tab_kernel(const ure_mf_shard_t* __restrict__ shards, int K, ure_
       __threadfence();
       __syncthreads();
       if (tid == 0)
-        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(hp.owner_ready + (long long)blockIdx.x * hp.owner_sched_rows + r),
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(hp.owner_ready + (long long)cta * hp.owner_sched_rows + r),
                      "r"(1u) : "memory");
     }
   }
@@ -1484,7 +1485,7 @@ int launch_schedule_co(const ure_mf_shard_t* d_shards, int K, const ure_mf_hpara
   auto kern = owner_schedule_tab_kernel<4, kCoThreads, true>;
   URE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
   URE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  kern<<<dim3(num_sms(), 1), kCoThreads, (size_t)need, side>>>(d_shards, K, hp, epochs, step0, tab_cap, sb);
+  kern<<<dim3(num_sms(), 1), kCoThreads, (size_t)need, side>>>(d_shards, K, hp, epochs, step0, tab_cap, sb, 0, num_sms());
   URE_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1608,8 +1609,53 @@ extern "C" int64_t ure_mf_owner_smem_bytes(int d, int cap_rows, int cap_slots, i
   return a > b ? a : b;
 }
 
+namespace ure {
+int mf_owner_schedule_impl(const ure_mf_shard_t* d_shards, int n_shards, const ure_mf_hparams_t* h_hp, int epochs,
+                           int64_t step0, void* stream, int cta0, int cta_n);
+}
 extern "C" int ure_mf_owner_schedule(const ure_mf_shard_t* d_shards, int n_shards, const ure_mf_hparams_t* h_hp,
                                      int epochs, int64_t step0, void* stream) {
+  return ure::mf_owner_schedule_impl(d_shards, n_shards, h_hp, epochs, step0, stream, 0, ure::num_sms());
+}
+
+// CTAs of the training grid per shard (make_plan's apportioning, on the host): h_c[s], and their sum = the grid
+extern "C" int ure_mf_owner_cta_split(const int32_t* h_n, int n_shards, int32_t* h_c) {
+  using namespace ure;
+  URE_REQUIRE(h_n && h_c && n_shards >= 1 && n_shards <= num_sms(), URE_EINVAL, "ure_mf_owner_cta_split: bad argument");
+  const int n_cta = num_sms();
+  long long N = 0;
+  for (int s = 0; s < n_shards; ++s) N += h_n[s];
+  if (N < 1) N = 1;
+  const long long spare = n_cta - n_shards;
+  long long rem[URE_MAX_SHARDS];
+  int used = 0;
+  for (int s = 0; s < n_shards; ++s) {
+    const long long x = spare * (long long)h_n[s];
+    h_c[s] = 1 + (int)(x / N);
+    rem[s] = x % N;
+    used += h_c[s];
+  }
+  for (int left = n_cta - used; left > 0; --left) {
+    int best = 0;
+    for (int s = 1; s < n_shards; ++s)
+      if (rem[s] > rem[best]) best = s;
+    ++h_c[best];
+    rem[best] = -1;
+  }
+  return 0;
+}
+
+// The pre-pass for the training CTAs [cta0, cta0 + cta_n) only -- the CTAs of the shards whose set-up is done
+// (ure_mf_owner_cta_split tells which): short epochs with round tables only (URE_EUNSUPPORTED otherwise).
+extern "C" int ure_mf_owner_schedule_part(const ure_mf_shard_t* d_shards, int n_shards, const ure_mf_hparams_t* h_hp,
+                                          int epochs, int64_t step0, int cta0, int cta_n, void* stream) {
+  using namespace ure;
+  URE_REQUIRE(cta0 >= 0 && cta_n >= 1 && cta0 + cta_n <= num_sms(), URE_EINVAL, "ure_mf_owner_schedule_part: CTA range");
+  return mf_owner_schedule_impl(d_shards, n_shards, h_hp, epochs, step0, stream, cta0, cta_n);
+}
+
+int ure::mf_owner_schedule_impl(const ure_mf_shard_t* d_shards, int n_shards, const ure_mf_hparams_t* h_hp, int epochs,
+                                int64_t step0, void* stream, int cta0, int cta_n) {
   using namespace ure;
   URE_REQUIRE(d_shards && h_hp && h_hp->owner_sched && h_hp->owner_sched_off, URE_EINVAL,
               "ure_mf_owner_schedule: null argument");
@@ -1645,13 +1691,18 @@ extern "C" int ure_mf_owner_schedule(const ure_mf_shard_t* d_shards, int n_shard
       auto kern = nt == 4 ? owner_schedule_tab_kernel<4, kSchedThreads, false>
                           : nt == 2 ? owner_schedule_tab_kernel<2, kSchedThreads, false> : owner_schedule_tab_kernel<0, kSchedThreads, false>;
       URE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need_t));
-      const int ny2 = h_hp->owner_sched_rows < 2 ? h_hp->owner_sched_rows : 2;     // 2 CTAs per SM: one wave
-      kern<<<dim3(num_sms(), ny2), kSchedThreads, (size_t)need_t, static_cast<cudaStream_t>(stream)>>>(
-          d_shards, n_shards, hp, epochs, step0, tab_cap, sb);
+      // 2 CTAs per SM: one wave -- of the whole grid, or (a part of the training CTAs) with more row classes per CTA
+      int ny2 = (2 * num_sms() + cta_n - 1) / cta_n;
+      if (ny2 > h_hp->owner_sched_rows) ny2 = h_hp->owner_sched_rows;
+      if (ny2 < 1) ny2 = 1;
+      kern<<<dim3(cta_n, ny2), kSchedThreads, (size_t)need_t, static_cast<cudaStream_t>(stream)>>>(
+          d_shards, n_shards, hp, epochs, step0, tab_cap, sb, cta0, num_sms());
       URE_CUDA(cudaGetLastError());
       return 0;
     }
   }
+  URE_REQUIRE(cta0 == 0 && cta_n == num_sms(), URE_EUNSUPPORTED,
+              "ure_mf_owner_schedule_part: only the short-epoch pre-pass runs on a part of the grid");
   const long long need = schedule_smem_bytes(h_hp->owner_cap_slots, h_hp->owner_spe_cap, cache_j, tab_cap);
   URE_REQUIRE(need <= avail, URE_EUNSUPPORTED, "ure_mf_owner_schedule: %lld bytes of shared memory needed, %d available",
               need, avail);
@@ -1731,17 +1782,38 @@ extern "C" int64_t ure_mf_owner_radix_bytes(int n_shards) { return 2ll * n_shard
 namespace ure {
 int mf_owner_prepare_impl(const ure_mf_shard_t* d_shards, int n_shards, const ure_mf_hparams_t* h_hp, int epochs,
                           int max_rows, int32_t* d_radix_hist, void* d_workspace, void* stream, int flags);
+int mf_owner_prepare_part(const ure_mf_shard_t* d_all, int n_all, int shard0, int n_shards, const ure_mf_hparams_t* h_hp,
+                          int epochs, int max_rows, int32_t* d_radix_all, void* d_workspace, void* stream, int flags);
 }
 extern "C" int ure_mf_owner_prepare(const ure_mf_shard_t* d_shards, int n_shards, const ure_mf_hparams_t* h_hp,
                                     int epochs, int max_rows, int32_t* d_radix_hist, void* d_workspace, void* stream) {
   return ure::mf_owner_prepare_impl(d_shards, n_shards, h_hp, epochs, max_rows, d_radix_hist, d_workspace, stream, 0);
 }
 
+extern "C" int ure_mf_owner_prepare_part(const ure_mf_shard_t* d_shards, int n_shards, int shard0, int n_part,
+                                         const ure_mf_hparams_t* h_hp, int epochs, int max_rows, int32_t* d_radix_hist,
+                                         void* d_workspace, void* stream) {
+  return ure::mf_owner_prepare_part(d_shards, n_shards, shard0, n_part, h_hp, epochs, max_rows, d_radix_hist, d_workspace,
+                                    stream, 1 | 2 | 4);
+}
+
 // flags (the native batch runtime): 1 = the caller has just cleared the workspace; 2 = no plan kernel (the launch runs
 // on remembered capacities, checked by the schedule pre-pass); 4 = no shard has explicit visiting orders
 int ure::mf_owner_prepare_impl(const ure_mf_shard_t* d_shards, int n_shards, const ure_mf_hparams_t* h_hp, int epochs,
                                int max_rows, int32_t* d_radix_hist, void* d_workspace, void* stream, int flags) {
+  return mf_owner_prepare_part(d_shards, n_shards, 0, n_shards, h_hp, epochs, max_rows, d_radix_hist, d_workspace, stream, flags);
+}
+
+// shards [shard0, shard0 + n_sub) of the batch (the whole batch: 0, n_shards).  A caller that uploads the shards one
+// after the other sets them up one by one, each as soon as its records have arrived, while the next one is on the bus.
+int ure::mf_owner_prepare_part(const ure_mf_shard_t* d_all, int n_all, int shard0, int n_shards, const ure_mf_hparams_t* h_hp,
+                               int epochs, int max_rows, int32_t* d_radix_all, void* d_workspace, void* stream, int flags) {
   using namespace ure;
+  URE_REQUIRE(shard0 >= 0 && n_shards >= 1 && shard0 + n_shards <= n_all, URE_EINVAL, "ure_mf_owner_prepare: shard range");
+  const ure_mf_shard_t* const d_shards = d_all + shard0;
+  int32_t* const d_radix_hist = d_radix_all ? d_radix_all + (long long)shard0 * 2 * kRadixBlocks * 256 : nullptr;
+  const bool whole = shard0 == 0 && n_shards == n_all;
+  if (!whole) flags |= 2 | 4 | 1;          // parts: no plan kernel, no inverse orders, the caller cleared the workspace
   URE_REQUIRE(d_shards && h_hp && d_workspace, URE_EINVAL, "ure_mf_owner_prepare: null argument");
   URE_REQUIRE(n_shards >= 1 && n_shards <= num_sms(), URE_EUNSUPPORTED,
               "ure_mf_owner_prepare: n_shards=%d outside [1,%d] (one CTA per shard at least)", n_shards, num_sms());
@@ -1756,15 +1828,15 @@ int ure::mf_owner_prepare_impl(const ure_mf_shard_t* d_shards, int n_shards, con
     if (smem_rows)
       URE_CUDA(cudaFuncSetAttribute(csr_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_rows * 4));
     if (!(flags & 1)) URE_CUDA(cudaMemsetAsync(ws->unsorted, 0, sizeof(ws->unsorted), st));
-    csr_count_kernel<<<dim3(cb, n_shards), 1024, (size_t)smem_rows * 4, st>>>(d_shards, smem_rows, ws);
+    csr_count_kernel<<<dim3(cb, n_shards), 1024, (size_t)smem_rows * 4, st>>>(d_shards, smem_rows, ws->unsorted + shard0);
   }
   csr_scan_kernel<<<2 * n_shards, 1024, 0, st>>>(d_shards);
   int npass = 1;
   while (npass < 4 && (max_rows - 1) >> (8 * npass)) ++npass;
   for (int pass = 0; pass < npass; ++pass) {
-    radix_hist_kernel<<<dim3(kRadixBlocks, 2 * n_shards), kRadixThreads, 0, st>>>(d_shards, pass, npass, d_radix_hist, ws);
-    radix_scan_kernel<<<2 * n_shards, 256, 0, st>>>(d_radix_hist, kRadixBlocks, ws);
-    radix_scatter_kernel<<<dim3(kRadixBlocks, 2 * n_shards), kRadixThreads, 0, st>>>(d_shards, pass, npass, d_radix_hist, ws);
+    radix_hist_kernel<<<dim3(kRadixBlocks, 2 * n_shards), kRadixThreads, 0, st>>>(d_shards, pass, npass, d_radix_hist, ws->unsorted + shard0);
+    radix_scan_kernel<<<2 * n_shards, 256, 0, st>>>(d_radix_hist, kRadixBlocks, ws->unsorted + shard0);
+    radix_scatter_kernel<<<dim3(kRadixBlocks, 2 * n_shards), kRadixThreads, 0, st>>>(d_shards, pass, npass, d_radix_hist, ws->unsorted + shard0);
   }
   if (!(flags & 4)) perm_inverse_kernel<<<dim3(blocks, n_shards), 256, 0, st>>>(d_shards, epochs);
   int avail = 0;

@@ -128,7 +128,8 @@ def _staging_bytes(nbytes: int) -> torch.Tensor:
     return torch.empty(cap, dtype=torch.uint8, pin_memory=True)
 
 
-def upload_interactions_many(raws, device, row_of: Optional[torch.Tensor] = None, defer: bool = False):
+def upload_interactions_many(raws, device, row_of: Optional[torch.Tensor] = None, defer: bool = False,
+                             stream=None, events: Optional[list] = None):
     """float64 [3, n] arrays (uid, iid, rating/max_rating: what readRating returns, reference read.py:64-68) ->
     int32 [n,4] ure_inter_t records on `device`, packed ON the device (ure_pack_interactions_f64).
 
@@ -137,7 +138,10 @@ def upload_interactions_many(raws, device, row_of: Optional[torch.Tensor] = None
     user -> compact-row mapping (`row_of`, int32 device tensor) run in the pack kernel.
 
     defer=True returns (outs, finish): the staging copies are already running on the worker threads, `finish()`
-    waits for them and queues the uploads + pack kernels -- the caller does other host work in between."""
+    waits for them and queues the uploads + pack kernels -- the caller does other host work in between.
+    stream (a torch.cuda.Stream) + events (a list to fill): arrays that live in page-locked memory are shipped on that
+    stream, and events[j] is recorded there behind array j's pack kernel (None for arrays that went the ordinary way):
+    the caller's stream waits for exactly the arrays it needs, while the later ones are still on the bus."""
     dev = torch.device(device)
     if dev.type != "cuda":
         raise RuntimeError("ultrare_b200: interactions are packed on a CUDA device (no CPU path exists)")
@@ -172,7 +176,9 @@ def upload_interactions_many(raws, device, row_of: Optional[torch.Tensor] = None
 
     def ship(j):                                                  # main thread: async H2D + pack kernel of array j
         lo, hi = int(starts[j]), int(starts[j]) + 3 * ns[j]
-        cols_all[lo:hi].copy_(stage_f[lo:hi] if pinned[j] is None else pinned[j], non_blocking=True)
+        src = base + 8 * lo if pinned[j] is None else int(arrs[j].ctypes.data)      # both page-locked
+        check(L.ure_copy_to_device_async(C.c_void_p(cols_all.data_ptr() + 8 * lo), C.c_void_p(src), 8 * (hi - lo), _stream()),
+              "ure_copy_to_device_async")
         check(L.ure_pack_interactions_f64(C.c_void_p(cols_all.data_ptr() + 8 * lo), ns[j], ns[j], _ptr(row_of),
                                           0 if row_of is None else int(row_of.shape[0]), _ptr(outs[j]), _stream()),
               "ure_pack_interactions_f64")
@@ -182,17 +188,31 @@ def upload_interactions_many(raws, device, row_of: Optional[torch.Tensor] = None
     for j in todo:
         if not arrs[j].flags.c_contiguous:
             arrs[j] = np.ascontiguousarray(arrs[j])
-        t = torch.from_numpy(arrs[j]) if arrs[j].flags.writeable else None
-        if t is not None and t.is_pinned():
-            pinned[j] = t.view(-1)
+        if _is_page_locked(arrs[j]):
+            pinned[j] = True
     # arrays that already live in page-locked memory need no staging copy: their upload + pack are queued right here
     # (defer or not), so the DMA engine starts while the caller still does its host-side set-up
     shipped = set()
+    if events is not None:
+        events[:] = [None] * len(arrs)
     with torch.cuda.device(dev):
-        for j in todo:
-            if pinned[j] is not None:
-                ship(j)
-                shipped.add(j)
+        if stream is not None and events is not None and any(pinned[j] is not None for j in todo):
+            main = torch.cuda.current_stream()
+            stream.wait_stream(main)                 # the fresh buffers may be recycled blocks of the caller's stream
+            out_all.record_stream(stream)
+            cols_all.record_stream(stream)
+            with torch.cuda.stream(stream):
+                for j in todo:
+                    if pinned[j] is not None:
+                        ship(j)
+                        shipped.add(j)
+                        events[j] = torch.cuda.Event()
+                        events[j].record()
+        else:
+            for j in todo:
+                if pinned[j] is not None:
+                    ship(j)
+                    shipped.add(j)
     futs = None
     if n_tot >= (1 << 16):
         # staging copies on worker threads (ctypes releases the GIL); every array is shipped as soon as ITS
@@ -221,13 +241,35 @@ def upload_interactions_many(raws, device, row_of: Optional[torch.Tensor] = None
     return outs
 
 
+_PAGE_LOCKED = []        # (first byte, one past the last, weak reference to the owning tensor) of pinned_copy's buffers
+
+
 def pinned_copy(a: np.ndarray) -> np.ndarray:
     """Copy of `a` in page-locked host memory (a NumPy view of a pinned torch tensor): arrays handed to
     RatingData / upload_interactions in this form are uploaded without the staging copy."""
+    import weakref
     t = torch.empty(a.shape, dtype=_TORCH_DTYPE[a.dtype.name], pin_memory=True)
     out = t.numpy()
     out[...] = a
+    _PAGE_LOCKED[:] = [e for e in _PAGE_LOCKED if e[2]() is not None]
+    _PAGE_LOCKED.append((t.data_ptr(), t.data_ptr() + t.numel() * t.element_size(), weakref.ref(t)))
     return out
+
+
+def _is_page_locked(arr: np.ndarray) -> bool:
+    """Does the array live in page-locked memory?  Buffers of pinned_copy are known by address (no driver call per
+    upload); anything else is asked through torch once."""
+    p0 = int(arr.ctypes.data)
+    p1 = p0 + arr.nbytes
+    for lo, hi, ref in _PAGE_LOCKED:
+        if lo <= p0 and p1 <= hi and ref() is not None:
+            return True
+    if not arr.flags.writeable:
+        return False
+    try:
+        return bool(torch.from_numpy(arr).is_pinned())
+    except Exception:
+        return False
 
 
 def upload_interactions(raw, device, row_of: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -815,6 +857,7 @@ class ConcurrentScheduleStall(PlanHintMiss):
 # Schedule pre-pass NEXT TO the training kernel (hparams.owner_ready) instead of before it.  Off by default: measured on
 # the C2 step, the training kernel slows by as much as the pre-pass costs alone (profiles/r2_notes.md).
 CONCURRENT_SCHEDULE = os.environ.get("URE_SCHED_CO", "0") == "1"
+PIPELINE_GROUPS = int(os.environ.get("URE_PIPE_GROUPS", "1"))   # shard groups set up while the next one uploads (1: off)
 _PLAN_HINTS = {}          # batch signature -> (max_rows, max_slots, max_spe, smem) of the last plan read back
 PLAN_HINT_MARGIN = 0.03   # capacities of an optimistic launch: the remembered maxima plus this fraction
 
@@ -831,14 +874,18 @@ class ArenaShardBatch(ShardBatch):
     def __init__(self, recs, rows_P, n_item: int, d: int, batch: int, epochs: int, shard_ids, perm_seed: int = 42,
                  perms=None, lr: float = 1e-3, lr_decay: float = 0.95, lr_step: int = 50, weight_decay: float = 0.1,
                  momentum: float = 0.9, generator=None, std: float = 1.0, mode: str = "auto", owner_cache: bool = True,
-                 optimistic: bool = False, whole_training: bool = False):
+                 optimistic: bool = False, whole_training: bool = False, ready_events=None):
         """optimistic: the caller reads the training losses (train_losses_async) only after everything that depends
         on the training is queued, and repeats the pass on PlanHintMiss.  The launch is then queued with the
         capacities of the last plan read back for the same shapes (+ PLAN_HINT_MARGIN) instead of waiting for this
         one's -- the kernels compare them with the real plan on the device (hparams.owner_plan).
         whole_training: the caller will train all steps with ONE train() call.  The schedule pre-pass then runs
         CONCURRENTLY with the training kernel (hparams.owner_ready) when the batch qualifies
-        (ure_mf_owner_concurrent_ok), on the registers and shared memory the training kernel leaves free."""
+        (ure_mf_owner_concurrent_ok), on the registers and shared memory the training kernel leaves free.
+        ready_events: per shard, the event behind its records when they are still on their way (uploads on a side
+        stream, read.RatingData.upload_many(stream=...)), else None.  On the optimistic path the shards are then set up
+        ONE BY ONE -- set-up kernels and schedule pre-pass of shard j queued behind event j -- so that the SMs work on
+        the first shards while the later ones are still on the bus; otherwise the stream simply waits for all of them."""
         K = self.n_shards = len(recs)
         tq = [("start", time.perf_counter())]                # host stamps of the constructor (diagnostics: ctor_ms)
         stamp = lambda name: tq.append((name, time.perf_counter()))
@@ -913,14 +960,56 @@ class ArenaShardBatch(ShardBatch):
             if rc == 1:
                 self.optimistic, self.plan_sync_ms = True, 0.0
                 self.hp.owner_plan = self.ws.data_ptr()
+        pending = [e for e in (ready_events or []) if e is not None]
+        self.pipelined = bool(pending and self.optimistic and lay.owner and perms is None and self.total_steps > 0 and
+                              not CONCURRENT_SCHEDULE and PIPELINE_GROUPS > 1 and K > 1)
+        piped_schedule = False
         with torch.cuda.device(dev):
+            main = torch.cuda.current_stream()
+            if pending and not self.pipelined:
+                for e in pending:                        # records still on the bus: the whole set-up waits for them
+                    main.wait_event(e)
+            npass = 1
+            while npass < 4 and (int(lay.max_rows) - 1) >> (8 * npass):
+                npass += 1
             check(L.ure_mf_batch_setup(hs, K, n_item, C.byref(self.hp), self.epochs, self._perm_seed, C.c_void_p(base),
-                                       C.byref(lay), C.c_void_p(stage.data_ptr()), 1 if self.optimistic else 0, _stream()),
+                                       C.byref(lay), C.c_void_p(stage.data_ptr()),
+                                       (1 if self.optimistic else 0) | (2 if self.pipelined else 0), _stream()),
                   "ure_mf_batch_setup")
-            if lay.owner:
-                npass = 1
-                while npass < 4 and (int(lay.max_rows) - 1) >> (8 * npass):
-                    npass += 1
+            if self.pipelined:
+                # shard by shard: set-up + pre-pass of shard j behind the arrival of its records
+                n_arr, c_arr = (C.c_int32 * K)(*ns), (C.c_int32 * K)()
+                check(L.ure_mf_owner_cta_split(n_arr, K, c_arr), "ure_mf_owner_cta_split")
+                radix = C.c_void_p(base + int(lay.radix))
+                tab, wsp = C.c_void_p(base + int(lay.table)), C.c_void_p(base + int(lay.ws))
+                # contiguous groups of shards of about equal bytes (a part per shard would pay the latency of eight
+                # small kernels per shard: measured, the gain goes into them)
+                G = max(1, min(PIPELINE_GROUPS, K))
+                tot, acc, groups, g0 = float(sum(ns)) or 1.0, 0, [], 0
+                for j in range(K):
+                    acc += ns[j]
+                    if acc >= tot * (len(groups) + 1) / G or j == K - 1:
+                        groups.append((g0, j + 1))
+                        g0 = j + 1
+                piped_schedule, cta0 = True, 0
+                for a, b in groups:
+                    for j in range(a, b):
+                        if ready_events[j] is not None:
+                            main.wait_event(ready_events[j])
+                    check(L.ure_mf_owner_prepare_part(tab, K, a, b - a, C.byref(self.hp), self.epochs, int(lay.max_rows), radix,
+                                                      wsp, _stream()), "ure_mf_owner_prepare_part")
+                    self.launches_per_pass += 2 + 3 * npass
+                    c_grp = sum(int(c_arr[j]) for j in range(a, b))
+                    if piped_schedule and sum(ns[a:b]) > 0:
+                        self.hp.owner_sched_step0 = 0
+                        rc_s = L.ure_mf_owner_schedule_part(tab, K, C.byref(self.hp), self.epochs, 0, cta0, c_grp, _stream())
+                        if rc_s == 0:
+                            self.launches_per_pass += 1
+                        else:                            # not the short-epoch pre-pass: one launch for all, below
+                            piped_schedule = False
+                    cta0 += c_grp
+                self.prepare_launches = len(groups) * (2 + 3 * npass)
+            elif lay.owner:
                 # count + scan, radix passes, [inverse visiting orders], [plan]
                 self.prepare_launches = 2 + 3 * npass + (1 if perms is not None else 0) + (0 if self.optimistic else 1)
                 self.launches_per_pass += self.prepare_launches
@@ -966,7 +1055,13 @@ class ArenaShardBatch(ShardBatch):
                     self.hp.owner_ready = base + int(lay.ready)
                     self._ready = self.arena[int(lay.ready):int(lay.ready) + 4 * int(lay.grid) * int(lay.sched_rows)]
                 if self.optimistic:
-                    self._schedule_window()              # the pre-pass is queued before anything else
+                    if piped_schedule:
+                        # the pre-pass went out shard by shard above: the window is covered
+                        rows = self.hp.owner_sched_rows
+                        self._sched_cover = (0, min([rows * spe for spe in self._spes if rows < self.epochs] or
+                                                    [self.total_steps]))
+                    else:
+                        self._schedule_window()          # the pre-pass is queued before anything else
                     stamp("schedule_queued")
                     fill_weights()
             elif mode == "owner":

@@ -258,11 +258,17 @@ class Sisa(Scratch):
             # the staging copies of the shards' records run on worker threads while the models are allocated
             from ..read import RatingData
             from .utils import MF
+            # page-locked arrays go up on a side stream, one event per shard: the batch runtime sets the shards up one
+            # by one as they arrive (kernels.ArenaShardBatch(ready_events=...)) instead of after the last byte
+            from ..read import _mapped_key
+            up_stream = kn.side_stream(self.device) if (batched and mode != 'faithful') else None
             uploaded = RatingData.upload_many([train_dlist[i].dataset for i in mine], self.device,
                                               self._row_of if compact else None, 'sisa_local' if compact else None,
-                                              defer=True)
+                                              defer=True, stream=up_stream)
             t_a = time.time()
             uploaded()
+            rec_key = _mapped_key(self.device, 'sisa_local', self._row_of) if compact else str(self.device)
+            ready_events = [train_dlist[i].dataset.take_upload_event(rec_key) for i in mine] if up_stream is not None else None
             recs = [(train_dlist[i].dataset.records_mapped(self.device, self._row_of, 'sisa_local') if compact
                      else train_dlist[i].dataset.records(self.device)) for i in mine]
             batch = train_dlist[mine[0]].batch_size
@@ -281,7 +287,8 @@ class Sisa(Scratch):
                                         perms if any(p is not None for p in perms) else None, self.lr, self.lr_decay,
                                         50, self.lam, self.momentum,
                                         generator=lambda: model_generator(self.seed, mine[0] + 1, self.device),
-                                        optimistic=optimistic, whole_training=mode in ('none', 'final', 'faithful-last'))
+                                        optimistic=optimistic, whole_training=mode in ('none', 'final', 'faithful-last'),
+                                        ready_events=ready_events)
                 states = None
             else:
                 for j, i in enumerate(mine):

@@ -152,11 +152,22 @@ class RatingData:
                 torch.tensor(self.items[idx], dtype=torch.long),
                 torch.tensor(self.ratings[idx], dtype=torch.float32))
 
+    def take_upload_event(self, key):
+        """The event behind records that were shipped on a side stream (upload_many(stream=...)), handed over ONCE: the
+        taker's stream has to wait for it before it touches the records."""
+        return self.__dict__.get('_upload_events', {}).pop(key, None)
+
+    def _wait_upload(self, key):
+        ev = self.take_upload_event(key)
+        if ev is not None:
+            torch.cuda.current_stream(ev.device if hasattr(ev, 'device') else None).wait_event(ev)
+
     def records(self, device) -> torch.Tensor:
         """int32 [n,4] ure_inter_t records resident on `device` (uploaded once)."""
         key = str(device)
         if key not in self._records:
             self._records[key] = kn.upload_interactions(self._raw, device)
+        self._wait_upload(key)
         return self._records[key]
 
     def records_mapped(self, device, row_of: torch.Tensor, tag: str) -> torch.Tensor:
@@ -167,6 +178,7 @@ class RatingData:
             self._drop_mapped(device, tag)
             self._records[key] = kn.upload_interactions(self._raw, device, row_of)
             self._keep_map(key, row_of)
+        self._wait_upload(key)
         return self._records[key]
 
     def _drop_mapped(self, device, tag):
@@ -179,16 +191,24 @@ class RatingData:
         self._maps[key] = row_of              # holds the tensor: its address cannot be reused while the key lives
 
     @staticmethod
-    def upload_many(datasets, device, row_of=None, tag=None, defer=False):
+    def upload_many(datasets, device, row_of=None, tag=None, defer=False, stream=None):
         """records()/records_mapped() of several datasets at once: their host copies run in parallel.
         defer=True: the copies are started and a `finish()` callable is returned; the records are registered (and
-        the uploads queued) when it is called."""
+        the uploads queued) when it is called.  stream: page-locked arrays are shipped on that stream; the event
+        behind each dataset's records is kept in ds._upload_events[key] (the caller's stream must wait for it)."""
         key = str(device) if tag is None else _mapped_key(device, tag, row_of)
         for ds in datasets:
             if isinstance(ds, DeviceRatingData):
                 ds.records(device) if tag is None else ds.records_mapped(device, row_of, tag)
         todo = [ds for ds in datasets if key not in ds._records]
-        recs, fin = kn.upload_interactions_many([ds._raw for ds in todo], device, row_of, defer=True)
+        if not todo:
+            return (lambda: None) if defer else None
+        evs = [] if stream is not None else None
+        recs, fin = kn.upload_interactions_many([ds._raw for ds in todo], device, row_of, defer=True, stream=stream,
+                                                events=evs)
+        for x, ds in enumerate(todo):
+            if evs is not None and evs[x] is not None:
+                ds.__dict__.setdefault('_upload_events', {})[key] = evs[x]
 
         def finish():
             fin()

@@ -258,10 +258,11 @@ class Sisa(Scratch):
             # the staging copies of the shards' records run on worker threads while the models are allocated
             from ..read import RatingData
             from .utils import MF
-            # page-locked arrays go up on a side stream, one event per shard: the batch runtime sets the shards up one
-            # by one as they arrive (kernels.ArenaShardBatch(ready_events=...)) instead of after the last byte
+            # kernels.PIPELINE_GROUPS > 1 (experiment, off by default): page-locked arrays go up on a side stream, one
+            # event per shard, and the batch runtime sets the shards up group by group as they arrive
+            # (kernels.ArenaShardBatch(ready_events=...)) instead of after the last byte
             from ..read import _mapped_key
-            up_stream = kn.side_stream(self.device) if (batched and mode != 'faithful') else None
+            up_stream = kn.side_stream(self.device) if (batched and mode != 'faithful' and kn.PIPELINE_GROUPS > 1) else None
             uploaded = RatingData.upload_many([train_dlist[i].dataset for i in mine], self.device,
                                               self._row_of if compact else None, 'sisa_local' if compact else None,
                                               defer=True, stream=up_stream)

@@ -337,6 +337,10 @@ def run_c2_ours(args):
     h2d = 24 * (sum(a.shape[1] for a in sp["unlearn_train"]) + test_rows) + 4 * len(del_user) + 176 * K_SHARDS
     e2e_ms = []
     d2h = 0
+    # the loaders of an end-to-end step start their upload when they are BUILT (read.EAGER_UPLOAD_DEVICE: page-locked
+    # arrays only), so the bytes travel while the step routes the deletions and lays out the batch
+    from ultrare_b200 import read as ure_read
+    ure_read.EAGER_UPLOAD_DEVICE = dev
     for it in range(args.warmup + args.steps):
         flush.fill_(it & 0xFF)
         d.barrier()
@@ -361,6 +365,7 @@ def run_c2_ours(args):
         d2h = sum(x.size * 4 for x in res_h) + 24
         if it >= args.warmup:
             e2e_ms.append(d.max_float(dt))
+    ure_read.EAGER_UPLOAD_DEVICE = None
     if os.environ.get("URE_BENCH_DEBUG"):
         print(f"[rank {rank}] e2e ms per step: {np.round(e2e_ms, 2).tolist()}; last: {e2e_parts} {un.timing}", file=sys.stderr)
     e2e_value = inter_total / (float(np.mean(e2e_ms)) / 1e3)

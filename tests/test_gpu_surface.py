@@ -539,3 +539,31 @@ def test_optimistic_owner_launch_hit_and_miss(cuda_dev):
         assert all(torch.equal(m.item_mat.weight.data, b) for m, b in zip(out3, q0))
         assert same_log(un3.final_log, un0.final_log)
     kn.PIPELINE_GROUPS = groups_before
+
+
+@pytest.mark.gpu
+def test_eager_upload_from_the_constructor(cuda_dev):
+    """read.EAGER_UPLOAD_DEVICE: a RatingData built on a page-locked float64 [3, n] array starts its host -> device copy
+    in the constructor (side stream); records(), records_mapped() and upload_many() then pack from the device columns.
+    Same records as the ordinary upload; arrays that do not qualify (small, pageable) take the ordinary way."""
+    from ultrare_b200 import kernels as kn, read as rd
+    from ultrare_b200.read import RatingData
+    rng = np.random.default_rng(4)
+    n, U, I = 200_000, 5000, 3000
+    raw = np.stack([rng.integers(0, U, n), rng.integers(0, I, n), rng.integers(1, 6, n) / 5.0]).astype(np.float64)
+    row_of = torch.tensor(rng.permutation(U).astype(np.int32), device=cuda_dev)
+    want = RatingData(raw).records(cuda_dev).cpu()
+    want_m = RatingData(raw).records_mapped(cuda_dev, row_of, 't').cpu()
+    pinned, small = kn.pinned_copy(raw), kn.pinned_copy(raw[:, :1000].copy())
+    rd.EAGER_UPLOAD_DEVICE = cuda_dev
+    try:
+        a, b, c, d_, e = RatingData(pinned), RatingData(pinned), RatingData(pinned), RatingData(small), RatingData(raw)
+        assert a._eager is not None and b._eager is not None and d_._eager is None and e._eager is None
+        assert torch.equal(a.records(cuda_dev).cpu(), want) and a._eager is None
+        assert torch.equal(b.records_mapped(cuda_dev, row_of, 't').cpu(), want_m)
+        RatingData.upload_many([c, d_, e], cuda_dev, row_of, 't')
+        assert torch.equal(c.records_mapped(cuda_dev, row_of, 't').cpu(), want_m)
+        assert torch.equal(e.records_mapped(cuda_dev, row_of, 't').cpu(), want_m)
+        assert torch.equal(d_.records_mapped(cuda_dev, row_of, 't').cpu(), want_m[:1000])
+    finally:
+        rd.EAGER_UPLOAD_DEVICE = None

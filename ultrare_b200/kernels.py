@@ -129,7 +129,7 @@ def _staging_bytes(nbytes: int) -> torch.Tensor:
 
 
 def upload_interactions_many(raws, device, row_of: Optional[torch.Tensor] = None, defer: bool = False,
-                             stream=None, events: Optional[list] = None):
+                             stream=None, events: Optional[list] = None, eager: Optional[list] = None):
     """float64 [3, n] arrays (uid, iid, rating/max_rating: what readRating returns, reference read.py:64-68) ->
     int32 [n,4] ure_inter_t records on `device`, packed ON the device (ure_pack_interactions_f64).
 
@@ -141,7 +141,9 @@ def upload_interactions_many(raws, device, row_of: Optional[torch.Tensor] = None
     waits for them and queues the uploads + pack kernels -- the caller does other host work in between.
     stream (a torch.cuda.Stream) + events (a list to fill): arrays that live in page-locked memory are shipped on that
     stream, and events[j] is recorded there behind array j's pack kernel (None for arrays that went the ordinary way):
-    the caller's stream waits for exactly the arrays it needs, while the later ones are still on the bus."""
+    the caller's stream waits for exactly the arrays it needs, while the later ones are still on the bus.
+    eager[j] = (device columns, event) of an array whose copy was started earlier (eager_upload): only its pack kernel
+    is queued here, behind the event."""
     dev = torch.device(device)
     if dev.type != "cuda":
         raise RuntimeError("ultrare_b200: interactions are packed on a CUDA device (no CPU path exists)")
@@ -175,6 +177,15 @@ def upload_interactions_many(raws, device, row_of: Optional[torch.Tensor] = None
                                     hi - lo), "ure_host_stage_copy")
 
     def ship(j):                                                  # main thread: async H2D + pack kernel of array j
+        if eager is not None and eager[j] is not None:            # already on its way (or there): pack behind its event
+            cols_j, ev_j = eager[j]
+            cur = torch.cuda.current_stream()
+            cur.wait_event(ev_j)
+            cols_j.record_stream(cur)
+            check(L.ure_pack_interactions_f64(C.c_void_p(cols_j.data_ptr()), ns[j], ns[j], _ptr(row_of),
+                                              0 if row_of is None else int(row_of.shape[0]), _ptr(outs[j]), _stream()),
+                  "ure_pack_interactions_f64")
+            return
         lo, hi = int(starts[j]), int(starts[j]) + 3 * ns[j]
         src = base + 8 * lo if pinned[j] is None else int(arrs[j].ctypes.data)      # both page-locked
         check(L.ure_copy_to_device_async(C.c_void_p(cols_all.data_ptr() + 8 * lo), C.c_void_p(src), 8 * (hi - lo), _stream()),
@@ -188,7 +199,7 @@ def upload_interactions_many(raws, device, row_of: Optional[torch.Tensor] = None
     for j in todo:
         if not arrs[j].flags.c_contiguous:
             arrs[j] = np.ascontiguousarray(arrs[j])
-        if _is_page_locked(arrs[j]):
+        if (eager is not None and eager[j] is not None) or _is_page_locked(arrs[j]):
             pinned[j] = True
     # arrays that already live in page-locked memory need no staging copy: their upload + pack are queued right here
     # (defer or not), so the DMA engine starts while the caller still does its host-side set-up
@@ -272,9 +283,32 @@ def _is_page_locked(arr: np.ndarray) -> bool:
         return False
 
 
-def upload_interactions(raw, device, row_of: Optional[torch.Tensor] = None) -> torch.Tensor:
+def upload_interactions(raw, device, row_of: Optional[torch.Tensor] = None, eager=None) -> torch.Tensor:
     """One array through upload_interactions_many."""
-    return upload_interactions_many([raw], device, row_of)[0]
+    return upload_interactions_many([raw], device, row_of, eager=None if eager is None else [eager])[0]
+
+
+EAGER_MIN_ROWS = 1 << 16      # smaller arrays are not worth a stream hand-over
+
+
+def eager_upload(raw, device):
+    """Start the host -> device copy of a float64 [3, n] array that lives in page-locked memory RIGHT NOW, on the side
+    stream (read.EAGER_UPLOAD_DEVICE: RatingData calls this from its constructor, so the bytes travel while the caller
+    is still building loaders, routing deletions, laying out the batch).  Returns (device columns, event) -- what
+    upload_interactions_many(eager=...) packs from -- or None when the array does not qualify."""
+    if not (isinstance(raw, np.ndarray) and raw.dtype == np.float64 and raw.ndim == 2 and raw.shape[0] == 3 and
+            raw.flags.c_contiguous and raw.shape[1] >= EAGER_MIN_ROWS and _is_page_locked(raw)):
+        return None
+    dev = torch.device(device)
+    side = side_stream(dev)
+    with torch.cuda.device(dev):
+        with torch.cuda.stream(side):                  # the buffer comes from the side stream's pool
+            cols = torch.empty(3 * raw.shape[1], dtype=torch.float64, device=dev)
+        check(_lib.lib().ure_copy_to_device_async(C.c_void_p(cols.data_ptr()), C.c_void_p(int(raw.ctypes.data)), raw.nbytes,
+                                                  C.c_void_p(side.cuda_stream)), "ure_copy_to_device_async")
+        ev = torch.cuda.Event()
+        ev.record(side)
+    return cols, ev
 
 
 _TORCH_DTYPE = {"uint8": torch.uint8, "int32": torch.int32, "int64": torch.int64, "float32": torch.float32,

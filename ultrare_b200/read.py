@@ -124,6 +124,12 @@ def _mapped_key(device, tag, row_of):
     return (str(device), tag, int(row_of.data_ptr()), int(row_of._version), int(row_of.shape[0]))
 
 
+# A torch.device: a RatingData built on a page-locked float64 [3, n] array (kernels.pinned_copy) starts its host -> device
+# copy in the constructor, on the side stream -- the bytes travel while the caller still builds loaders, routes the
+# deletions and lays out the batch; records() / records_mapped() / upload_many() then only pack.  None: off.
+EAGER_UPLOAD_DEVICE = None
+
+
 class RatingData:
     """reference read.py:108-124: users/items int, ratings float (already / max_rating)."""
 
@@ -134,6 +140,16 @@ class RatingData:
         self._records = {}
         self._segments = {}
         self._maps = {}
+        self._eager = kn.eager_upload(rating_array, EAGER_UPLOAD_DEVICE) if EAGER_UPLOAD_DEVICE is not None else None
+
+    def _take_eager(self, device):
+        """The columns an eager upload put on `device` (handed over once), or None."""
+        e, self._eager = getattr(self, '_eager', None), None
+        if e is None:
+            return None
+        want, have = torch.device(device), e[0].device
+        same = want.type == have.type and (want.index is None or want.index == have.index)
+        return e if same else None
 
     def _col(self, j, dtype):
         if j not in self._cols:               # the reference's eager casts (read.py:111-113), done on demand
@@ -166,7 +182,7 @@ class RatingData:
         """int32 [n,4] ure_inter_t records resident on `device` (uploaded once)."""
         key = str(device)
         if key not in self._records:
-            self._records[key] = kn.upload_interactions(self._raw, device)
+            self._records[key] = kn.upload_interactions(self._raw, device, eager=self._take_eager(device))
         self._wait_upload(key)
         return self._records[key]
 
@@ -176,7 +192,7 @@ class RatingData:
         key = _mapped_key(device, tag, row_of)
         if key not in self._records:
             self._drop_mapped(device, tag)
-            self._records[key] = kn.upload_interactions(self._raw, device, row_of)
+            self._records[key] = kn.upload_interactions(self._raw, device, row_of, eager=self._take_eager(device))
             self._keep_map(key, row_of)
         self._wait_upload(key)
         return self._records[key]
@@ -205,7 +221,7 @@ class RatingData:
             return (lambda: None) if defer else None
         evs = [] if stream is not None else None
         recs, fin = kn.upload_interactions_many([ds._raw for ds in todo], device, row_of, defer=True, stream=stream,
-                                                events=evs)
+                                                events=evs, eager=[ds._take_eager(device) for ds in todo])
         for x, ds in enumerate(todo):
             if evs is not None and evs[x] is not None:
                 ds.__dict__.setdefault('_upload_events', {})[key] = evs[x]

@@ -634,6 +634,38 @@ def test_mf_owner_prepare_sorts_and_inverts(cuda_dev):
     assert sb.owner_plan["smem_need"] <= sb.owner_plan["smem_avail"]
 
 
+@pytest.mark.parametrize("fused", ["0", "1"])
+@pytest.mark.parametrize("U,I,n", [(200, 250, 20_000), (5000, 3000, 150_000), (70_000, 300, 90_000), (40, 70_000, 60_001)])
+def test_mf_owner_setup_one_launch_equals_eight(cuda_dev, monkeypatch, fused, U, I, n):
+    """URE_SETUP_FUSED: the whole set-up as ONE cooperative launch (owner_setup_kernel: the same bodies as virtual
+    blocks, grid barriers where the launch boundaries were) against the eight separate launches -- one, two and three
+    radix passes, row counters in shared memory and (tables too large) in global memory, two shards of which one is
+    already in user order.  Both give the stable argsort and the row histograms' prefix sums."""
+    torch = _torch()
+    from ultrare_b200 import kernels as kn
+    monkeypatch.setenv("URE_SETUP_FUSED", fused)
+    rng = np.random.default_rng(U + n)
+    shards, host = [], []
+    for kind in ("random", "sorted"):
+        u = rng.integers(0, U, n) if kind == "random" else np.sort(rng.integers(0, U, n))
+        i = rng.integers(0, I, n)
+        r = rng.integers(1, 6, n).astype(np.float32) / 5
+        shards.append(kn.ShardState(kn.pack_interactions(u, i, r, cuda_dev), torch.zeros((U, 16), device=cuda_dev),
+                                    torch.zeros((I, 16), device=cuda_dev), 1))
+        host.append((u, i))
+    try:
+        kn.ShardBatch(shards, 16, 4096, mode="owner")
+    except RuntimeError as e:              # the set-up has run; the training plan of the widest tables does not fit
+        assert "does not fit" in str(e) and max(U, I) > 50_000
+    torch.cuda.synchronize()
+    for st, (u, i) in zip(shards, host):
+        for rec, off, key, rows in ((st.inter_u, st.off_u, u, U), (st.inter_i, st.off_i, i, I)):
+            rec, off = rec.cpu().numpy(), off.cpu().numpy()
+            j = np.argsort(key, kind="stable")
+            assert np.array_equal(rec[:, 3], j) and np.array_equal(rec[:, 0], u[j]) and np.array_equal(rec[:, 1], i[j])
+            assert np.array_equal(off[:rows + 1], np.concatenate([[0], np.cumsum(np.bincount(key, minlength=rows))]))
+
+
 def test_mf_owner_prepare_records_already_in_user_order(cuda_dev):
     """Rating files are written user by user: a shard whose records arrive in user-row order skips the user-side
     radix passes (the counting pass notices and keeps the copy it wrote while reading).  Three shards in one batch --

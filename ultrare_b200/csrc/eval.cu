@@ -95,6 +95,7 @@ ensemble_score_jobs_kernel(const ure_eval_job_t* __restrict__ jobs) {
 //   NDCG = (sum_p relevance[p]*hit[p]*common[p] * w_p) / sum_p w_p,  w_0 = 1, w_p = 1/log2(p+1)
 // ---------------------------------------------------------------------------
 constexpr int kSegStage = 512;        // a segment up to this long is staged in shared memory (score, rating)
+constexpr int kSegCount = 64;         // up to this long: ranks by counting (L * ceil(L / 32) steps); longer: ten arg-max rounds
 // DCG position weights 1 / log2(p + 1) (w_0 = 1) and their sum over the top 10, as double literals: fp64 log2 and
 // division per thread cost more than the ranking itself on this part
 static_assert(URE_TOP_K == 10, "weight table below");
@@ -112,9 +113,11 @@ __device__ __forceinline__ void rank_metrics_body(const ure_inter_t* __restrict_
   const int lane = threadIdx.x & 31;
   const int w = threadIdx.x >> 5;
   const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  // consecutive segments go to DIFFERENT CTAs (warp w of CTA b takes segment w * gridDim.x + b): rating files list their
+  // heaviest users next to each other, and eight long segments in one CTA were the tail of the whole kernel
   double ndcg_sum = 0.0, hr_sum = 0.0, users = 0.0;
   const double wgt = lane < URE_TOP_K ? kDcgWeight[lane] : 0.0;
-  for (long long sgm = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; sgm < n_seg; sgm += n_warps) {
+  for (long long sgm = (long long)w * gridDim.x + blockIdx.x; sgm < n_seg; sgm += n_warps) {
     const long long b = seg[sgm];
     const int L = (int)(seg[sgm + 1] - b);
     if (L <= 0) continue;
@@ -132,34 +135,34 @@ __device__ __forceinline__ void rank_metrics_body(const ure_inter_t* __restrict_
         s_vt[w][e] = make_float2(score[re], inter[re].rating);
       }
     __syncwarp();
-    if (staged) {
+    if (staged && L > kSegCount) {
       // the element of rank p is the p-th in the order (value descending, index descending): ten rounds of a warp
       // arg-max over the staged segment instead of L^2 comparisons (one heavy user used to be the kernel's tail)
-      auto top10 = [&](bool by_rating, int* dst) {
-        unsigned taken = 0;                  // bit k: element lane + 32 k is already placed
-        const int P = L < URE_TOP_K ? L : URE_TOP_K;
-        for (int p = 0; p < P; ++p) {
-          float bv = -INFINITY;
-          int be = -1;
-          for (int k = 0, e = lane; e < L; ++k, e += 32) {
-            if ((taken >> k) & 1u) continue;
-            const float2 x = s_vt[w][e];
-            const float v = by_rating ? x.y : x.x;
-            if (v > bv || (v == bv && e > be)) { bv = v; be = e; }
-          }
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-            const int oe = __shfl_xor_sync(0xffffffffu, be, o);
-            if (ov > bv || (ov == bv && oe > be)) { bv = ov; be = oe; }
-          }
-          if (lane == 0) dst[p] = be;
-          if (be >= 0 && (be & 31) == lane) taken |= 1u << (be >> 5);
+      // (both orders in one sweep: two independent compare chains per lane instead of twenty dependent rounds)
+      unsigned taken_p = 0, taken_r = 0;     // bit k: element lane + 32 k is already placed in that order
+      const int P = L < URE_TOP_K ? L : URE_TOP_K;
+      for (int p = 0; p < P; ++p) {
+        float vp = -INFINITY, vr = -INFINITY;
+        int ep = -1, er = -1;
+        for (int k = 0, e = lane; e < L; ++k, e += 32) {
+          const float2 x = s_vt[w][e];
+          if (!((taken_p >> k) & 1u) && (x.x > vp || (x.x == vp && e > ep))) { vp = x.x; ep = e; }
+          if (!((taken_r >> k) & 1u) && (x.y > vr || (x.y == vr && e > er))) { vr = x.y; er = e; }
         }
-      };
-      top10(false, top_pred[w]);
-      top10(true, top_rating[w]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ovp = __shfl_xor_sync(0xffffffffu, vp, o), ovr = __shfl_xor_sync(0xffffffffu, vr, o);
+          const int oep = __shfl_xor_sync(0xffffffffu, ep, o), oer = __shfl_xor_sync(0xffffffffu, er, o);
+          if (ovp > vp || (ovp == vp && oep > ep)) { vp = ovp; ep = oep; }
+          if (ovr > vr || (ovr == vr && oer > er)) { vr = ovr; er = oer; }
+        }
+        if (lane == 0) { top_pred[w][p] = ep; top_rating[w][p] = er; }
+        if (ep >= 0 && (ep & 31) == lane) taken_p |= 1u << (ep >> 5);
+        if (er >= 0 && (er & 31) == lane) taken_r |= 1u << (er >> 5);
+      }
     } else {
+      // short segments (the common case: a few test rows per user) and the very long ones that are not staged: every
+      // lane counts the elements ranked before its own, both orders in one sweep (broadcast reads of shared memory)
       for (int e = lane; e < L; e += 32) {
         const float2 me = value_of(e);
         int rp = 0, rr = 0;

@@ -135,10 +135,11 @@ extern "C" int ure_mf_batch_setup(const ure_mf_batch_shard_t* h_shards, int n_sh
     bool any_perm = false;
     for (int s = 0; s < n_shards; ++s) any_perm |= h_shards[s].perm != nullptr;
     const bool no_plan = (flags & URE_BATCH_NO_PLAN) != 0;
-    // 1: the workspace has just been cleared | 2: no plan kernel | 4: no explicit visiting orders to invert
+    // 1: the workspace has just been cleared | 2: no plan kernel | 4: no explicit visiting orders to invert | 8: the
+    // set-up of a small batch is launch-bound: one cooperative launch (owner_setup_kernel) instead of eight
     if (int rc = mf_owner_prepare_impl(reinterpret_cast<const ure_mf_shard_t*>(base + lay->table), n_shards, h_hp, epochs,
                                        lay->max_rows, reinterpret_cast<int32_t*>(base + lay->radix), base + lay->ws, stream,
-                                       1 | (no_plan ? 2 : 0) | (any_perm ? 0 : 4)))
+                                       1 | (no_plan ? 2 : 0) | (any_perm ? 0 : 4) | (lay->n_total <= (8ll << 20) ? 8 : 0)))
       return rc;
     // the plan (4 ints) travels to the page-locked block right behind the descriptor table
     if (!no_plan)

@@ -27,6 +27,9 @@
 #include "feistel.cuh"
 #include <string.h>
 #include <type_traits>
+#include <cooperative_groups.h>
+
+namespace cg = cooperative_groups;
 
 namespace ure {
 namespace {
@@ -206,16 +209,17 @@ __device__ __forceinline__ void note_order(const ure_mf_shard_t& sh, long long j
   reinterpret_cast<int4*>(sh.inter_u)[j] = make_int4(r.x, r.y, r.z, (int)j);
 }
 
-__global__ void csr_count_kernel(const ure_mf_shard_t* shards, int smem_rows, unsigned* unsorted_flags) {
-  extern __shared__ int s_cnt[];
-  const ure_mf_shard_t& sh = shards[blockIdx.y];
-  const long long stride = (long long)gridDim.x * blockDim.x;
+// virtual block (bx of gx, shard by); s_cnt: smem_rows ints (or unused)
+__device__ __forceinline__ void csr_count_body(const ure_mf_shard_t* shards, int smem_rows, unsigned* unsorted_flags,
+                                               int* s_cnt, int bx, int by, int gx) {
+  const ure_mf_shard_t& sh = shards[by];
+  const long long stride = (long long)gx * blockDim.x;
   const int nu = sh.n_user, rows = sh.n_user + sh.n_item;
-  unsigned* const unsorted = unsorted_flags ? unsorted_flags + blockIdx.y : nullptr;
+  unsigned* const unsorted = unsorted_flags ? unsorted_flags + by : nullptr;
   if (smem_rows > 0 && rows <= smem_rows) {
     for (int x = threadIdx.x; x < rows; x += blockDim.x) s_cnt[x] = 0;
     __syncthreads();
-    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < sh.n; j += stride) {
+    for (long long j = (long long)bx * blockDim.x + threadIdx.x; j < sh.n; j += stride) {
       const int4 r = ld_stream_i4(sh.inter + j);
       atomicAdd(&s_cnt[r.x], 1);
       atomicAdd(&s_cnt[nu + r.y], 1);
@@ -228,7 +232,7 @@ __global__ void csr_count_kernel(const ure_mf_shard_t* shards, int smem_rows, un
     }
     return;
   }
-  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < sh.n; j += stride) {
+  for (long long j = (long long)bx * blockDim.x + threadIdx.x; j < sh.n; j += stride) {
     const int4 r = ld_stream_i4(sh.inter + j);
     atomicAdd(sh.off_u + r.x + 1, 1);
     atomicAdd(sh.off_i + r.y + 1, 1);
@@ -236,13 +240,19 @@ __global__ void csr_count_kernel(const ure_mf_shard_t* shards, int smem_rows, un
   }
 }
 
+__global__ void csr_count_kernel(const ure_mf_shard_t* shards, int smem_rows, unsigned* unsorted_flags) {
+  extern __shared__ int s_cnt[];
+  csr_count_body(shards, smem_rows, unsorted_flags, s_cnt, blockIdx.x, blockIdx.y, gridDim.x);
+}
+
 // in-place inclusive scan of off[0 .. rows+2): one CTA per (shard, side); off[r] becomes the first slot of row r
-__global__ void csr_scan_kernel(const ure_mf_shard_t* shards) {
-  const ure_mf_shard_t& sh = shards[blockIdx.x >> 1];
-  int32_t* off = (blockIdx.x & 1) ? sh.off_i : sh.off_u;
-  const int len = ((blockIdx.x & 1) ? sh.n_item : sh.n_user) + 2;
-  __shared__ int s_warp[32];
-  __shared__ int s_carry;
+// s_scr: 33 ints of shared memory
+__device__ __forceinline__ void csr_scan_body(const ure_mf_shard_t* shards, int* s_scr, int vb) {
+  const ure_mf_shard_t& sh = shards[vb >> 1];
+  int32_t* off = (vb & 1) ? sh.off_i : sh.off_u;
+  const int len = ((vb & 1) ? sh.n_item : sh.n_user) + 2;
+  int* const s_warp = s_scr;
+  int& s_carry = s_scr[32];
   if (threadIdx.x == 0) s_carry = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -257,7 +267,7 @@ __global__ void csr_scan_kernel(const ure_mf_shard_t* shards) {
     if (lane == 31) s_warp[warp] = v;
     __syncthreads();
     if (warp == 0) {
-      int w = s_warp[lane];
+      int w = lane < (int)(blockDim.x >> 5) ? s_warp[lane] : 0;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         const int a = __shfl_up_sync(0xffffffffu, w, o);
@@ -274,37 +284,41 @@ __global__ void csr_scan_kernel(const ure_mf_shard_t* shards) {
   }
 }
 
+__global__ void csr_scan_kernel(const ure_mf_shard_t* shards) {
+  __shared__ int s_scr[33];
+  csr_scan_body(shards, s_scr, blockIdx.x);
+}
+
 constexpr int kRadixBlocks = 96;          // CTAs per (shard, side): each owns a contiguous tile of the records
 constexpr int kRadixThreads = 512;
 constexpr int kRadixWarps = kRadixThreads / 32;
 
-struct RadixView {                        // what pass `pass` of grid row y = 2*shard + side works on
+struct RadixView {                        // what pass `pass` of virtual block (bx of gx, by = 2*shard + side) works on
   const int4* src;
   int4* dst;
   long long n, t0, t1;                    // the CTA's tile [t0, t1)
   bool item, first;
-  __device__ RadixView(const ure_mf_shard_t* shards, int pass, int npass) {
-    const ure_mf_shard_t& sh = shards[blockIdx.y >> 1];
-    item = blockIdx.y & 1;
+  __device__ RadixView(const ure_mf_shard_t* shards, int pass, int npass, int bx, int by, int gx) {
+    const ure_mf_shard_t& sh = shards[by >> 1];
+    item = by & 1;
     first = pass == 0;
     int4* fin = reinterpret_cast<int4*>(item ? sh.inter_i : sh.inter_u);
     int4* tmp = reinterpret_cast<int4*>(item ? sh.tmp_i : sh.tmp_u);
     dst = ((npass - 1 - pass) & 1) ? tmp : fin;
     src = first ? reinterpret_cast<const int4*>(sh.inter) : (((npass - pass) & 1) ? tmp : fin);
     n = sh.n;
-    const long long tile = (n + gridDim.x - 1) / gridDim.x;
-    t0 = min(n, tile * blockIdx.x);
+    const long long tile = (n + gx - 1) / gx;
+    t0 = min(n, tile * bx);
     t1 = min(n, t0 + tile);
   }
   __device__ __forceinline__ int digit(const int4& r, int pass) const { return ((item ? r.y : r.x) >> (8 * pass)) & 255; }
 };
 
-// hist [grid.y][grid.x][256]: records of the CTA's tile per digit value
-__global__ void __launch_bounds__(kRadixThreads)
-radix_hist_kernel(const ure_mf_shard_t* shards, int pass, int npass, int* __restrict__ hist, const unsigned* unsorted) {
-  __shared__ int s_h[256];
-  if (unsorted && !(blockIdx.y & 1) && unsorted[blockIdx.y >> 1] == 0) return;      // user side already in order
-  const RadixView v(shards, pass, npass);
+// hist [2 * shards][gx][256]: records of the CTA's tile per digit value.  s_h: 256 ints.  Any block size (multiple of 32).
+__device__ __forceinline__ void radix_hist_body(const ure_mf_shard_t* shards, int pass, int npass, int* __restrict__ hist,
+                                                const unsigned* unsorted, int* s_h, int bx, int by, int gx) {
+  if (unsorted && !(by & 1) && unsorted[by >> 1] == 0) return;      // user side already in order
+  const RadixView v(shards, pass, npass, bx, by, gx);
   for (int x = threadIdx.x; x < 256; x += blockDim.x) s_h[x] = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31;
@@ -319,18 +333,26 @@ radix_hist_kernel(const ure_mf_shard_t* shards, int pass, int npass, int* __rest
     }
   }
   __syncthreads();
-  for (int x = threadIdx.x; x < 256; x += blockDim.x) hist[((long long)blockIdx.y * gridDim.x + blockIdx.x) * 256 + x] = s_h[x];
+  for (int x = threadIdx.x; x < 256; x += blockDim.x) hist[((long long)by * gx + bx) * 256 + x] = s_h[x];
 }
 
-// per grid row y: exclusive scan of hist in (digit, CTA) order, in place; one CTA of 256 threads per y
-__global__ void __launch_bounds__(256)
-radix_scan_kernel(int* __restrict__ hist, int n_blocks, const unsigned* unsorted) {
-  __shared__ int s_tot[256];
-  if (unsorted && !(blockIdx.x & 1) && unsorted[blockIdx.x >> 1] == 0) return;
-  int* h = hist + (long long)blockIdx.x * n_blocks * 256 + threadIdx.x;      // thread = digit: coalesced per CTA row
-  int tot = 0;
-  for (int b = 0; b < n_blocks; ++b) tot += h[b * 256];
-  s_tot[threadIdx.x] = tot;
+__global__ void __launch_bounds__(kRadixThreads)
+radix_hist_kernel(const ure_mf_shard_t* shards, int pass, int npass, int* __restrict__ hist, const unsigned* unsorted) {
+  __shared__ int s_h[256];
+  radix_hist_body(shards, pass, npass, hist, unsorted, s_h, blockIdx.x, blockIdx.y, gridDim.x);
+}
+
+// per row y = 2 * shard + side: exclusive scan of hist in (digit, CTA) order, in place; threads 0..255 of one CTA per y.
+// s_tot: 256 ints.
+__device__ __forceinline__ void radix_scan_body(int* __restrict__ hist, int n_blocks, const unsigned* unsorted, int* s_tot, int y) {
+  if (unsorted && !(y & 1) && unsorted[y >> 1] == 0) return;
+  const bool on = threadIdx.x < 256;
+  int* h = hist + (long long)y * n_blocks * 256 + (threadIdx.x & 255);      // thread = digit: coalesced per CTA row
+  if (on) {
+    int tot = 0;
+    for (int b = 0; b < n_blocks; ++b) tot += h[b * 256];
+    s_tot[threadIdx.x] = tot;
+  }
   __syncthreads();
   if (threadIdx.x < 32) {                 // exclusive scan of the 256 digit totals by one warp, 8 per lane
     int loc[8], sum = 0;
@@ -346,24 +368,33 @@ radix_scan_kernel(int* __restrict__ hist, int n_blocks, const unsigned* unsorted
     for (int i = 0; i < 8; ++i) s_tot[threadIdx.x * 8 + i] = inc - sum + loc[i];
   }
   __syncthreads();
-  int run = s_tot[threadIdx.x];
-  for (int b = 0; b < n_blocks; ++b) {
-    const int t = h[b * 256];
-    h[b * 256] = run;
-    run += t;
+  if (on) {
+    int run = s_tot[threadIdx.x];
+    for (int b = 0; b < n_blocks; ++b) {
+      const int t = h[b * 256];
+      h[b * 256] = run;
+      run += t;
+    }
   }
 }
 
+__global__ void __launch_bounds__(256)
+radix_scan_kernel(int* __restrict__ hist, int n_blocks, const unsigned* unsorted) {
+  __shared__ int s_tot[256];
+  radix_scan_body(hist, n_blocks, unsorted, s_tot, blockIdx.x);
+}
+
 // stable scatter of the CTA's tile: every warp owns a contiguous range; per-warp digit counts -> per-warp cursors
-// (from the CTA's global offsets); inside a warp __match_any ranks the lanes of one digit in lane (= record) order
-__global__ void __launch_bounds__(kRadixThreads)
-radix_scatter_kernel(const ure_mf_shard_t* shards, int pass, int npass, const int* __restrict__ hist, const unsigned* unsorted) {
-  __shared__ int s_wh[kRadixWarps][256];
-  if (unsorted && !(blockIdx.y & 1) && unsorted[blockIdx.y >> 1] == 0) return;
-  const RadixView v(shards, pass, npass);
+// (from the CTA's global offsets); inside a warp __match_any ranks the lanes of one digit in lane (= record) order.
+// s_whp: [kRadixWarps][256] ints; block size kRadixThreads.
+__device__ __forceinline__ void radix_scatter_body(const ure_mf_shard_t* shards, int pass, int npass, const int* __restrict__ hist,
+                                                   const unsigned* unsorted, int* s_whp, int bx, int by, int gx) {
+  if (unsorted && !(by & 1) && unsorted[by >> 1] == 0) return;
+  int (*s_wh)[256] = reinterpret_cast<int (*)[256]>(s_whp);
+  const RadixView v(shards, pass, npass, bx, by, gx);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned lt = (1u << lane) - 1u;
-  for (int x = threadIdx.x; x < kRadixWarps * 256; x += blockDim.x) (&s_wh[0][0])[x] = 0;
+  for (int x = threadIdx.x; x < kRadixWarps * 256; x += blockDim.x) s_whp[x] = 0;
   __syncthreads();
   const long long per = ((v.t1 - v.t0) + kRadixWarps - 1) / kRadixWarps;
   const long long w0 = min(v.t1, v.t0 + per * warp), w1 = min(v.t1, w0 + per);
@@ -380,7 +411,7 @@ radix_scatter_kernel(const ure_mf_shard_t* shards, int pass, int npass, const in
   }
   __syncthreads();
   if (threadIdx.x < 256) {
-    int run = hist[((long long)blockIdx.y * gridDim.x + blockIdx.x) * 256 + threadIdx.x];
+    int run = hist[((long long)by * gx + bx) * 256 + threadIdx.x];
     for (int w = 0; w < kRadixWarps; ++w) {
       const int t = s_wh[w][threadIdx.x];
       s_wh[w][threadIdx.x] = run;
@@ -405,6 +436,52 @@ radix_scatter_kernel(const ure_mf_shard_t* shards, int pass, int npass, const in
       if (lane == __ffs(same) - 1) s_wh[warp][dg] += __popc(same);
     }
     __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(kRadixThreads)
+radix_scatter_kernel(const ure_mf_shard_t* shards, int pass, int npass, const int* __restrict__ hist, const unsigned* unsorted) {
+  __shared__ int s_wh[kRadixWarps * 256];
+  radix_scatter_body(shards, pass, npass, hist, unsorted, s_wh, blockIdx.x, blockIdx.y, gridDim.x);
+}
+
+// The whole set-up in ONE cooperative launch (batches whose set-up is launch-bound: eight launches of a few
+// microseconds each): the bodies above run as virtual blocks of a co-resident grid, with a grid barrier where a launch
+// boundary was.  Dynamic shared memory: max(smem_rows, kRadixWarps * 256) ints.
+//   count + histogram of pass 0 | row-offset scan + digit scan | scatter | histogram | digit scan | scatter ...
+__global__ void __launch_bounds__(kRadixThreads)
+owner_setup_kernel(const ure_mf_shard_t* shards, int n_shards, int smem_rows, int cb, int npass, int* __restrict__ hist,
+                   unsigned* unsorted) {
+  extern __shared__ int s_dyn[];
+  cg::grid_group grid = cg::this_grid();
+  const int G = gridDim.x, me = blockIdx.x;
+  const int n_count = cb * n_shards, n_radix = kRadixBlocks * 2 * n_shards, n_scan = 2 * n_shards;
+  // the histogram blocks of pass 0 first (they do not depend on the counting pass): the user side is counted although
+  // the records may turn out to be in user order already -- the flags are final only at the first barrier
+  for (int vb = me; vb < n_radix + n_count; vb += G) {
+    if (vb < n_count) csr_count_body(shards, smem_rows, unsorted, s_dyn, vb % cb, vb / cb, cb);      // the longer blocks first
+    else radix_hist_body(shards, 0, npass, hist, nullptr, s_dyn, (vb - n_count) % kRadixBlocks, (vb - n_count) / kRadixBlocks, kRadixBlocks);
+    __syncthreads();
+  }
+  for (int pass = 0; pass < npass; ++pass) {
+    if (pass > 0) {
+      grid.sync();
+      for (int vb = me; vb < n_radix; vb += G) {
+        radix_hist_body(shards, pass, npass, hist, unsorted, s_dyn, vb % kRadixBlocks, vb / kRadixBlocks, kRadixBlocks);
+        __syncthreads();
+      }
+    }
+    grid.sync();
+    for (int vb = me; vb < n_scan * (pass == 0 ? 2 : 1); vb += G) {
+      if (vb < n_scan) radix_scan_body(hist, kRadixBlocks, unsorted, s_dyn, vb);
+      else csr_scan_body(shards, s_dyn, vb - n_scan);
+      __syncthreads();
+    }
+    grid.sync();
+    for (int vb = me; vb < n_radix; vb += G) {
+      radix_scatter_body(shards, pass, npass, hist, unsorted, s_dyn, vb % kRadixBlocks, vb / kRadixBlocks, kRadixBlocks);
+      __syncthreads();
+    }
   }
 }
 
@@ -1798,7 +1875,8 @@ extern "C" int ure_mf_owner_prepare_part(const ure_mf_shard_t* d_shards, int n_s
 }
 
 // flags (the native batch runtime): 1 = the caller has just cleared the workspace; 2 = no plan kernel (the launch runs
-// on remembered capacities, checked by the schedule pre-pass); 4 = no shard has explicit visiting orders
+// on remembered capacities, checked by the schedule pre-pass); 4 = no shard has explicit visiting orders; 8 = the whole
+// set-up in one cooperative launch
 int ure::mf_owner_prepare_impl(const ure_mf_shard_t* d_shards, int n_shards, const ure_mf_hparams_t* h_hp, int epochs,
                                int max_rows, int32_t* d_radix_hist, void* d_workspace, void* stream, int flags) {
   return mf_owner_prepare_part(d_shards, n_shards, 0, n_shards, h_hp, epochs, max_rows, d_radix_hist, d_workspace, stream, flags);
@@ -1821,22 +1899,48 @@ int ure::mf_owner_prepare_part(const ure_mf_shard_t* d_all, int n_all, int shard
   auto* ws = static_cast<OwnerWs*>(d_workspace);
   URE_REQUIRE(d_radix_hist && max_rows >= 1, URE_EINVAL, "ure_mf_owner_prepare: radix scratch / max_rows missing");
   const int blocks = 2 * num_sms();
-  {
-    // max_rows bounds n_user and n_item of every shard: both tables' counters in shared memory when they fit 96 KB
-    const int smem_rows = 2 * max_rows <= 24576 ? 2 * max_rows : 0;
-    const int cb = smem_rows ? (num_sms() / n_shards > 0 ? num_sms() / n_shards : 1) : blocks;   // one wave of CTAs
+  int npass = 1;
+  while (npass < 4 && (max_rows - 1) >> (8 * npass)) ++npass;
+  // max_rows bounds n_user and n_item of every shard: both tables' counters in shared memory when they fit 96 KB
+  const int smem_rows = 2 * max_rows <= 24576 ? 2 * max_rows : 0;
+  const int cb = smem_rows ? (num_sms() / n_shards > 0 ? num_sms() / n_shards : 1) : blocks;   // one wave of CTAs
+  // flags & 8 (the batch runtime, small batches) or URE_SETUP_FUSED=1: one cooperative launch instead of 2 + 3 npass
+  const char* const fe = getenv("URE_SETUP_FUSED");      // read per call: the tests compare both ways in one process
+  const int fused_env = fe ? atoi(fe) : -1;
+  bool fused = fused_env > 0 || (fused_env < 0 && (flags & 8));
+  if (fused) {
+    const int smem_ints = smem_rows > kRadixWarps * 256 ? smem_rows : kRadixWarps * 256;
+    static int smem_set = 48 << 10;
+    if (smem_ints * 4 > smem_set) {
+      URE_CUDA(cudaFuncSetAttribute(owner_setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_ints * 4));
+      smem_set = smem_ints * 4;
+    }
+    int occ = 0;
+    URE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, owner_setup_kernel, kRadixThreads, (size_t)smem_ints * 4));
+    if (occ < 1) fused = false;
+    else {
+      if (!(flags & 1)) URE_CUDA(cudaMemsetAsync(ws->unsorted, 0, sizeof(ws->unsorted), st));
+      const int per_sm = occ < 4 ? occ : 4;
+      int n_sh = n_shards, sr = smem_rows, cbv = cb, np = npass;
+      const ure_mf_shard_t* dsh = d_shards;
+      int32_t* hist = d_radix_hist;
+      unsigned* uns = ws->unsorted + shard0;
+      void* args[] = {&dsh, &n_sh, &sr, &cbv, &np, &hist, &uns};
+      URE_CUDA(cudaLaunchCooperativeKernel((void*)owner_setup_kernel, dim3(per_sm * num_sms()), dim3(kRadixThreads), args,
+                                           (size_t)smem_ints * 4, st));
+    }
+  }
+  if (!fused) {
     if (smem_rows)
       URE_CUDA(cudaFuncSetAttribute(csr_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_rows * 4));
     if (!(flags & 1)) URE_CUDA(cudaMemsetAsync(ws->unsorted, 0, sizeof(ws->unsorted), st));
     csr_count_kernel<<<dim3(cb, n_shards), 1024, (size_t)smem_rows * 4, st>>>(d_shards, smem_rows, ws->unsorted + shard0);
-  }
-  csr_scan_kernel<<<2 * n_shards, 1024, 0, st>>>(d_shards);
-  int npass = 1;
-  while (npass < 4 && (max_rows - 1) >> (8 * npass)) ++npass;
-  for (int pass = 0; pass < npass; ++pass) {
-    radix_hist_kernel<<<dim3(kRadixBlocks, 2 * n_shards), kRadixThreads, 0, st>>>(d_shards, pass, npass, d_radix_hist, ws->unsorted + shard0);
-    radix_scan_kernel<<<2 * n_shards, 256, 0, st>>>(d_radix_hist, kRadixBlocks, ws->unsorted + shard0);
-    radix_scatter_kernel<<<dim3(kRadixBlocks, 2 * n_shards), kRadixThreads, 0, st>>>(d_shards, pass, npass, d_radix_hist, ws->unsorted + shard0);
+    csr_scan_kernel<<<2 * n_shards, 1024, 0, st>>>(d_shards);
+    for (int pass = 0; pass < npass; ++pass) {
+      radix_hist_kernel<<<dim3(kRadixBlocks, 2 * n_shards), kRadixThreads, 0, st>>>(d_shards, pass, npass, d_radix_hist, ws->unsorted + shard0);
+      radix_scan_kernel<<<2 * n_shards, 256, 0, st>>>(d_radix_hist, kRadixBlocks, ws->unsorted + shard0);
+      radix_scatter_kernel<<<dim3(kRadixBlocks, 2 * n_shards), kRadixThreads, 0, st>>>(d_shards, pass, npass, d_radix_hist, ws->unsorted + shard0);
+    }
   }
   if (!(flags & 4)) perm_inverse_kernel<<<dim3(blocks, n_shards), 256, 0, st>>>(d_shards, epochs);
   int avail = 0;

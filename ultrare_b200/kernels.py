@@ -30,13 +30,32 @@ def _stream():
 _SIDE_STREAMS = {}
 
 
-def side_stream(device) -> "torch.cuda.Stream":
-    """One extra stream per device for uploads that must not queue behind a long kernel on the caller's stream."""
+def side_stream(device, lane: int = 0) -> "torch.cuda.Stream":
+    """Extra streams per device for copies that must not queue behind a long kernel on the caller's stream: lane 0
+    carries uploads, lane 1 the read-backs that wait for that kernel (so that uploads never queue behind them)."""
     dev = torch.device(device)
     idx = dev.index if dev.index is not None else torch.cuda.current_device()
-    if idx not in _SIDE_STREAMS:
-        _SIDE_STREAMS[idx] = torch.cuda.Stream(device=idx)
-    return _SIDE_STREAMS[idx]
+    if (idx, lane) not in _SIDE_STREAMS:
+        _SIDE_STREAMS[(idx, lane)] = torch.cuda.Stream(device=idx)
+    return _SIDE_STREAMS[(idx, lane)]
+
+
+SIDE_SMALL_UPLOADS = True      # pointer tables / flags of the merge and the evaluation travel on the side stream
+
+
+def on_side(device):
+    """Context: torch work inside runs on the upload side stream; on exit the caller's stream waits for it.  Tensors
+    allocated inside must be handed to the caller's stream with record_stream (see upload_array)."""
+    import contextlib
+
+    @contextlib.contextmanager
+    def ctx():
+        main = torch.cuda.current_stream(device)
+        side = side_stream(device)
+        with torch.cuda.stream(side):
+            yield main
+        main.wait_stream(side)
+    return ctx()
 
 
 def _need_cuda(*ts):
@@ -315,10 +334,16 @@ _TORCH_DTYPE = {"uint8": torch.uint8, "int32": torch.int32, "int64": torch.int64
                 "float64": torch.float64, "int16": torch.int16}
 
 
-def upload_array(a: np.ndarray, device) -> torch.Tensor:
+def upload_array(a: np.ndarray, device, side: bool = False) -> torch.Tensor:
     """Small host array -> device through the pinned staging pool (asynchronous: the host does not wait for the
-    work already queued on the stream, unlike a pageable .to(device))."""
+    work already queued on the stream, unlike a pageable .to(device)).  side: the copy runs on the upload side stream
+    and the caller's stream waits for its event -- a table queued while a long kernel runs is resident when it ends."""
     a = np.ascontiguousarray(a)
+    if side and SIDE_SMALL_UPLOADS and a.size:
+        with on_side(device) as main:
+            out = upload_array(a, device)
+            out.record_stream(main)
+        return out
     out = torch.empty(a.shape, dtype=_TORCH_DTYPE[a.dtype.name], device=device)
     if a.size == 0:
         return out
@@ -430,7 +455,7 @@ def download_many(tensors: Sequence[torch.Tensor], copy: bool = True) -> List[np
 
 
 def pointer_table(tensors: Sequence[torch.Tensor], device) -> torch.Tensor:
-    return upload_array(np.array([t.data_ptr() for t in tensors], dtype=np.int64), device)
+    return upload_array(np.array([t.data_ptr() for t in tensors], dtype=np.int64), device, side=True)
 
 
 # ------------------------------------------------------------------------------ MF training
@@ -832,11 +857,22 @@ class ShardBatch:
         owner = self.mode == "owner"
         host = _staging_bytes(nb + 64)
         with torch.cuda.device(sse.device):
-            host[:nb].view(torch.float64).copy_(sse.view(-1), non_blocking=True)
+            # on their own stream behind an event of the caller's: what the caller queues next (merge, evaluation)
+            # does not wait for these two copies
+            main = torch.cuda.current_stream(sse.device)
+            back = side_stream(sse.device, 1)
+            done = torch.cuda.Event()
+            done.record(main)
+            back.wait_event(done)
+            sse.record_stream(back)
             if owner:
-                host[nb:nb + 4].copy_(self.ws[16:20], non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record()
+                self.ws.record_stream(back)
+            with torch.cuda.stream(back):
+                host[:nb].view(torch.float64).copy_(sse.view(-1), non_blocking=True)
+                if owner:
+                    host[nb:nb + 4].copy_(self.ws[16:20], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(back)
         ns = self._shard_sizes()
 
         def wait() -> List[np.ndarray]:
@@ -1179,14 +1215,16 @@ def alloc_shard_batch(rows_P: Sequence[int], n_item: int, d: int, epochs: int, d
 
 
 # ------------------------------------------------------------------------------ evaluation
-def ensemble_score(P_list, Q_list, inter, denom: Optional[float] = None, want_score: bool = True):
-    """(score fp32 [n] or None, sse fp64 [1]) for the K models (P_k, Q_k)."""
-    _need_cuda(inter, *P_list, *Q_list)
+def ensemble_score(P_list, Q_list, inter, denom: Optional[float] = None, want_score: bool = True, sse=None):
+    """(score fp32 [n] or None, sse fp64 [1]) for the K models (P_k, Q_k).  sse: a zeroed fp64 [1] to add into."""
+    _need_cuda(inter, sse, *P_list, *Q_list)
     dev = inter.device
     K, d, n = len(P_list), P_list[0].shape[1], inter.shape[0]
     score = torch.empty(n, dtype=torch.float32, device=dev) if want_score else None
-    sse = torch.zeros(1, dtype=torch.float64, device=dev)
-    pt, qt = pointer_table(P_list, dev), pointer_table(Q_list, dev)
+    if sse is None:
+        sse = torch.zeros(1, dtype=torch.float64, device=dev)
+    both = pointer_table(list(P_list) + list(Q_list), dev)      # one upload for both tables
+    pt, qt = both[:K], both[K:]
     with torch.cuda.device(dev):
         check(_lib.lib().ure_ensemble_score(_ptr(pt), _ptr(qt), K, d, _ptr(inter), n,
                                             float(K if denom is None else denom), _ptr(score), _ptr(sse),
@@ -1275,10 +1313,11 @@ def eval_jobs(jobs, d: int) -> torch.Tensor:
     return out
 
 
-def rank_metrics(inter, score, seg, order=None) -> torch.Tensor:
-    """fp64 [3] = (sum ndcg, sum hr, #users)."""
-    _need_cuda(inter, score, seg, order)
-    out = torch.zeros(3, dtype=torch.float64, device=inter.device)
+def rank_metrics(inter, score, seg, order=None, out=None) -> torch.Tensor:
+    """fp64 [3] = (sum ndcg, sum hr, #users).  out: a zeroed fp64 [3] to add into."""
+    _need_cuda(inter, score, seg, order, out)
+    if out is None:
+        out = torch.zeros(3, dtype=torch.float64, device=inter.device)
     with torch.cuda.device(inter.device):
         check(_lib.lib().ure_rank_metrics(_ptr(inter), _ptr(score), _ptr(order), _ptr(seg), seg.shape[0] - 1,
                                           _ptr(out), _stream()), "ure_rank_metrics")

@@ -632,7 +632,7 @@ class Sisa(Scratch):
                                                               defer_logs=len(save_dir) == 0)
         t_m = time.perf_counter()
         if flags is None:                              # routed on the host: the flags go up while the GPU trains
-            flags = kn.upload_array(self._route_flags_host, self.device)
+            flags = kn.upload_array(self._route_flags_host, self.device, side=True)
         merged = self._merged_from(base, unmerged, compact, flags)
         self._finish(new, unmerged, last_idx, compact, merged, test_dlist, save_dir)
         for i, m in new.items():

@@ -163,11 +163,12 @@ def base_test_device(dataloader, models):
     dev = models[0].user_mat.weight.device
     ds = dataloader.dataset
     inter = ds.records(dev)
-    score, sse = kn.ensemble_score([m.user_mat.weight.data for m in models],
-                                   [m.item_mat.weight.data for m in models], inter)
+    vals = torch.zeros(4, dtype=torch.float64, device=dev)      # one clear, both kernels add into their slice
+    score, _ = kn.ensemble_score([m.user_mat.weight.data for m in models],
+                                 [m.item_mat.weight.data for m in models], inter, sse=vals[0:1])
     order, seg = ds.segments(dev, models[0].user_mat.weight.shape[0])
-    out = kn.rank_metrics(inter, score, seg, order)
-    return torch.cat([sse, out]), len(ds)
+    kn.rank_metrics(inter, score, seg, order, out=vals[1:4])
+    return vals, len(ds)
 
 
 def base_test_values(vals, size):

@@ -826,6 +826,35 @@ def test_pack_interactions_on_device_equals_host_casts(cuda_dev):
     assert kn.upload_interactions(np.zeros((3, 0)), cuda_dev).shape == (0, 4)
 
 
+def test_uploads_through_the_staging_ring_equal_one_shot_uploads(cuda_dev, monkeypatch):
+    """Tables / rating arrays beyond UPLOAD_ONE_SHOT_BYTES travel through a two-segment page-locked ring (a C4-sized
+    table cannot be staged whole).  With the limits lowered: ragged sizes (not a multiple of a segment, of 2 MB, of 16
+    bytes), several arrays with an empty one and a page-locked one among them, deferred and direct -- bit-equal to
+    the one-shot path."""
+    torch = _torch()
+    from ultrare_b200 import kernels as kn
+    rng = np.random.default_rng(5)
+    tab = rng.standard_normal(3 * (1 << 20) + 12345)
+    small = rng.integers(0, 1 << 30, 700_001).astype(np.int32)
+    ns, U = [300_007, 0, 150_001, 90_000], 4000
+    raws = [np.vstack([rng.integers(0, U, n).astype(np.float64), rng.integers(0, 3000, n).astype(np.float64),
+                       rng.integers(1, 11, n) / 2.0 / 5.0]) for n in ns]
+    raws[3] = kn.pinned_copy(raws[3])
+    row_of = torch.tensor(rng.permutation(U).astype(np.int32), device=cuda_dev)
+    ref_tab, ref_small = kn.upload_table(tab, cuda_dev), kn.upload_table(small, cuda_dev)
+    ref = kn.upload_interactions_many(raws, cuda_dev, row_of)
+    monkeypatch.setattr(kn, "UPLOAD_ONE_SHOT_BYTES", 1 << 20)
+    monkeypatch.setattr(kn, "UPLOAD_RING_BYTES", (1 << 22) + (1 << 20))       # 5 MB: segments of 2.5 staging tasks
+    assert torch.equal(kn.upload_table(tab, cuda_dev), ref_tab) and np.array_equal(ref_tab.cpu().numpy(), tab)
+    assert torch.equal(kn.upload_table(small, cuda_dev), ref_small)
+    got = kn.upload_interactions_many(raws, cuda_dev, row_of)
+    outs, finish = kn.upload_interactions_many(raws, cuda_dev, row_of, defer=True)
+    finish()
+    for a, b, c in zip(ref, got, outs):
+        assert torch.equal(a, b) and torch.equal(a, c)
+    assert got[1].shape == (0, 4)
+
+
 def test_mf_owner_schedule_windows_vs_oracle(cuda_dev, monkeypatch):
     """Owner schedule with schedule tables that hold only 2 epochs per shard: the training is split into windows,
     each with its own ure_mf_owner_schedule pass; ragged shards (different steps per epoch), 5 epochs."""

@@ -147,6 +147,33 @@ def _staging_bytes(nbytes: int) -> torch.Tensor:
     return torch.empty(cap, dtype=torch.uint8, pin_memory=True)
 
 
+UPLOAD_RING_BYTES = 64 << 20         # segment of the two-segment staging ring of very large uploads
+UPLOAD_ONE_SHOT_BYTES = 1 << 30      # uploads up to this size are staged whole (one pinned buffer, one DMA per array)
+
+
+def _upload_ring(dst_ptr: int, src_ptr: int, nb: int) -> None:
+    """Pageable host bytes [src, src + nb) -> device [dst, dst + nb) on the current stream through TWO page-locked
+    segments of UPLOAD_RING_BYTES: the pool threads fill one (non-temporal stores) while the DMA engine drains the
+    other, so the page-locked footprint of an upload does not grow with its size (a C4-sized rating table is 24 GB)."""
+    L, seg, CH = _lib.lib(), int(UPLOAD_RING_BYTES), 1 << 21
+    bufs = [_staging_bytes(seg), _staging_bytes(seg)]
+    evs = [None, None]
+    for k, lo in enumerate(range(0, nb, seg)):
+        b, n = k & 1, min(seg, nb - lo)
+        if evs[b] is not None:
+            evs[b].synchronize()                                   # the DMA that last read this segment is done
+        base = bufs[b].data_ptr()
+        futs = [_pack_pool().submit(L.ure_host_stage_copy, C.c_void_p(base + o), C.c_void_p(src_ptr + lo + o), min(CH, n - o))
+                for o in range(0, n, CH)]
+        for f in futs:
+            check(f.result(), "ure_host_stage_copy")
+        check(L.ure_copy_to_device_async(C.c_void_p(dst_ptr + lo), C.c_void_p(base), n, _stream()), "ure_copy_to_device_async")
+        evs[b] = torch.cuda.Event()
+        evs[b].record()
+    for b in range(2):
+        _PINNED_BYTES.setdefault(bufs[b].shape[0], []).append((bufs[b], evs[b]))
+
+
 def upload_interactions_many(raws, device, row_of: Optional[torch.Tensor] = None, defer: bool = False,
                              stream=None, events: Optional[list] = None, eager: Optional[list] = None):
     """float64 [3, n] arrays (uid, iid, rating/max_rating: what readRating returns, reference read.py:64-68) ->
@@ -184,11 +211,44 @@ def upload_interactions_many(raws, device, row_of: Optional[torch.Tensor] = None
     for j, n in enumerate(ns):
         starts[j + 1] = (starts[j] + 3 * n + 7) // 8 * 8
     tot_d = int(starts[-1])
+    L = _lib.lib()
+    if 8 * tot_d > UPLOAD_ONE_SHOT_BYTES:
+        # too large to stage whole: array after array, each through the two-segment ring (or straight from its own
+        # page-locked memory) into a device buffer that lives until its pack kernel has run
+        if events is not None:
+            events[:] = [None] * len(arrs)
+
+        def one_by_one():
+            with torch.cuda.device(dev):
+                for j in range(len(arrs)):
+                    if not ns[j]:
+                        continue
+                    if eager is not None and eager[j] is not None:
+                        cols_j, ev_j = eager[j]
+                        cur = torch.cuda.current_stream()
+                        cur.wait_event(ev_j)
+                        cols_j.record_stream(cur)
+                    else:
+                        a = np.ascontiguousarray(arrs[j])
+                        cols_j = torch.empty(3 * ns[j], dtype=torch.float64, device=dev)
+                        if _is_page_locked(a):
+                            check(L.ure_copy_to_device_async(C.c_void_p(cols_j.data_ptr()), C.c_void_p(int(a.ctypes.data)),
+                                                             a.nbytes, _stream()), "ure_copy_to_device_async")
+                        else:
+                            _upload_ring(cols_j.data_ptr(), int(a.ctypes.data), a.nbytes)
+                    check(L.ure_pack_interactions_f64(C.c_void_p(cols_j.data_ptr()), ns[j], ns[j], _ptr(row_of),
+                                                      0 if row_of is None else int(row_of.shape[0]), _ptr(outs[j]), _stream()),
+                          "ure_pack_interactions_f64")
+                    del cols_j                                     # stream-ordered: the block is reused behind the pack kernel
+
+        if defer:
+            return outs, one_by_one
+        one_by_one()
+        return outs
     stage = _staging_bytes(8 * tot_d)
     stage_f = stage[:8 * tot_d].view(torch.float64)
     base = stage.data_ptr()
     cols_all = torch.empty(tot_d, dtype=torch.float64, device=dev)
-    L = _lib.lib()
     CHUNK = int(float(__import__('os').environ.get('URE_PACK_CHUNK_MB', '2')) * (1 << 20)) // 64 * 64   # bytes per staging task
 
     def fill(j, lo, hi):                                          # bytes [lo, hi) of array j, non-temporal stores
@@ -358,12 +418,17 @@ def upload_array(a: np.ndarray, device, side: bool = False) -> torch.Tensor:
 
 
 def upload_table(a: np.ndarray, device) -> torch.Tensor:
-    """Large host array -> device: staging copies in 2 MB tasks on the pack pool (non-temporal stores), one DMA."""
+    """Large host array -> device: staging copies in 2 MB tasks on the pack pool (non-temporal stores), one DMA; beyond
+    UPLOAD_ONE_SHOT_BYTES through a two-segment staging ring (_upload_ring)."""
     a = np.ascontiguousarray(a)
     out = torch.empty(a.shape, dtype=_TORCH_DTYPE[a.dtype.name], device=device)
     nb = a.nbytes
     if nb < (1 << 21):
         return upload_array(a, device)
+    if nb > UPLOAD_ONE_SHOT_BYTES:
+        with torch.cuda.device(device):
+            _upload_ring(out.data_ptr(), int(a.ctypes.data), nb)
+        return out
     stage = _staging_bytes(nb)
     base, src, L, CHUNK = stage.data_ptr(), a.ctypes.data, _lib.lib(), 1 << 21
     futs = [_pack_pool().submit(L.ure_host_stage_copy, C.c_void_p(base + lo), C.c_void_p(src + lo), min(CHUNK, nb - lo))

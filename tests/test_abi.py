@@ -160,3 +160,49 @@ def test_instance_read_data_host_branch(tmp_path, monkeypatch):
     assert len(total) == sum(len(t) for t in test) and np.array_equal(total._raw, np.hstack(raw_test))
     deleted = set(int(u) for u in ins.param.del_user)
     assert not deleted & set(int(u) for t in train for u in np.unique(t.users))
+
+
+def test_upload_ring_host_logic(monkeypatch):
+    """kernels._upload_ring (uploads beyond UPLOAD_ONE_SHOT_BYTES): segment hand-over, ragged tail, both segments back
+    in the staging pool -- with the real ure_host_stage_copy, the DMA stood in by memmove and events by no-ops (the
+    GPU version of this test is test_uploads_through_the_staging_ring_equal_one_shot_uploads)."""
+    import torch
+    from ultrare_b200 import _lib, kernels as kn
+    real = _lib.lib()
+    waits = []
+
+    class Lib:
+        def __getattr__(self, name):
+            return getattr(real, name)
+
+        def ure_copy_to_device_async(self, dst, src, n, stream):
+            ctypes.memmove(dst, src, n)
+            return 0
+
+    class Event:
+        def record(self, *a):
+            pass
+
+        def synchronize(self):
+            waits.append(1)
+
+        def query(self):
+            return True
+
+    fake = Lib()
+    monkeypatch.setattr(kn._lib, "lib", lambda: fake)
+    monkeypatch.setattr(torch.cuda, "Event", Event)
+    monkeypatch.setattr(kn, "_stream", lambda: None)
+    monkeypatch.setattr(kn, "_staging_bytes", lambda nb: torch.empty(1 << max(12, int(nb - 1).bit_length()), dtype=torch.uint8))
+    monkeypatch.setattr(kn, "_PINNED_BYTES", {})
+    monkeypatch.setattr(kn, "UPLOAD_RING_BYTES", (1 << 22) + (1 << 20))
+    rng = np.random.default_rng(0)
+    for count in (3 * (1 << 20) + 12345, 1000, 655360 + 1):       # 5 segments and a tail; one short segment; one + 8 bytes
+        src = rng.standard_normal(count)
+        dst = np.zeros_like(src)
+        waits.clear()
+        kn._upload_ring(dst.ctypes.data, src.ctypes.data, src.nbytes)
+        assert np.array_equal(src, dst)
+        n_seg = -(-src.nbytes // kn.UPLOAD_RING_BYTES)
+        assert len(waits) == max(0, n_seg - 2)                      # a segment is waited for only before its re-use
+    assert sum(len(v) for v in kn._PINNED_BYTES.values()) == 6      # two segments returned per upload

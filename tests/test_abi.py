@@ -206,3 +206,28 @@ def test_upload_ring_host_logic(monkeypatch):
         n_seg = -(-src.nbytes // kn.UPLOAD_RING_BYTES)
         assert len(waits) == max(0, n_seg - 2)                      # a segment is waited for only before its re-use
     assert sum(len(v) for v in kn._PINNED_BYTES.values()) == 6      # two segments returned per upload
+
+
+def test_staging_pools_take_a_free_buffer_behind_a_busy_one(monkeypatch):
+    """The page-locked staging pools hand out the first buffer whose last copy has completed.  With uploads on two
+    streams the FIRST entry can still be busy when a later one is free; taking that one out with list.remove compared
+    (tensor, event) tuples element-wise and raised "Boolean value of Tensor ... is ambiguous" (2-GPU run of the round)."""
+    import torch
+    from ultrare_b200 import kernels as kn
+
+    class Event:
+        def __init__(self, done):
+            self.done = done
+
+        def query(self):
+            return self.done
+
+    a, b, c = (torch.full((4096,), v, dtype=torch.uint8) for v in (0, 1, 2))
+    pool = [(a, Event(False)), (b, Event(True)), (c, None)]
+    monkeypatch.setattr(kn, "_PINNED_BYTES", {4096: pool})
+    assert kn._staging_bytes(16) is b and [x[0] is y for x, y in zip(pool, (a, c))] == [True, True]
+    assert kn._staging_bytes(4096) is c and len(pool) == 1 and pool[0][0] is a
+    ra, rb = torch.zeros((1024, 4), dtype=torch.int32), torch.ones((1024, 4), dtype=torch.int32)
+    rpool = [(ra, Event(False)), (rb, Event(True))]
+    monkeypatch.setattr(kn, "_PINNED", {1024: rpool})
+    assert kn._staging(1000) is rb and len(rpool) == 1 and rpool[0][0] is ra

@@ -93,9 +93,9 @@ _PINNED = {}   # rows -> list of pinned int32 [rows,4] staging buffers (reused: 
 def _staging(n: int) -> torch.Tensor:
     cap = 1 << max(10, int(n - 1).bit_length())
     pool = _PINNED.setdefault(cap, [])
-    for buf, ev in pool:
+    for idx, (buf, ev) in enumerate(pool):
         if ev is None or ev.query():
-            pool.remove((buf, ev))
+            del pool[idx]                # by position: list.remove would compare the tensors of the entries before it
             return buf
     return torch.empty((cap, 4), dtype=torch.int32, pin_memory=True)
 
@@ -140,10 +140,10 @@ _PINNED_BYTES = {}   # capacity -> list of (pinned uint8 buffer, event): staging
 def _staging_bytes(nbytes: int) -> torch.Tensor:
     cap = 1 << max(12, int(nbytes - 1).bit_length())
     pool = _PINNED_BYTES.setdefault(cap, [])
-    for item in pool:
+    for idx, item in enumerate(pool):
         if item[1] is None or item[1].query():
-            pool.remove(item)
-            return item[0]
+            del pool[idx]                # by position: list.remove(item) compares item with every entry before it, and
+            return item[0]               # (tensor, event) == (other tensor, event) is an element-wise tensor comparison
     return torch.empty(cap, dtype=torch.uint8, pin_memory=True)
 
 

@@ -144,6 +144,28 @@ def test_emd_plan_is_integral_and_balanced():
     assert np.bincount(oot.assign(G)).tolist() == [n // k] * k
 
 
+def test_emd_stand_in_agrees_with_an_independent_exact_solver():
+    """ot.emd (POT, absent here) is an exact solver; its stand-in is a dual-simplex LP.  An independent exact method
+    -- the assignment problem on centroid columns replicated n/k times (scipy's modified Jonker-Volgenant) -- reaches
+    the same vertex on squared-distance costs at the reference's shapes: the optimum is unique there, so ANY exact
+    solver, POT's network simplex included, returns this plan.  Also on the reference's own toy embedding (golden)."""
+    from scipy.optimize import linear_sum_assignment
+    rng = np.random.default_rng(12)
+    cases = [(rng.standard_normal((600, 16)), 5), (rng.standard_normal((960, 8)), 32)]
+    z = load_gold("ot_cluster.npz")
+    cases.append((np.asarray(z["X"], dtype=np.float64), int(z["k"])))
+    for X, k in cases:
+        n = X.shape[0]
+        assert n % k == 0
+        M = oot.cost_matrix(X, X[rng.choice(n, k, replace=False)])
+        G = oot.emd_lp(np.ones(n) / n, np.ones(k) / k, M)
+        rows, cols = linear_sum_assignment(np.repeat(M, n // k, axis=1))
+        label = np.empty(n, dtype=np.int64)
+        label[rows] = cols // (n // k)
+        assert np.array_equal(oot.assign(G), label)
+        assert abs((G * M).sum() - M[np.arange(n), label].sum() / n) <= 1e-9 * abs((G * M).sum())
+
+
 def test_sinkhorn_converges_to_emd_labels():
     rng = np.random.default_rng(4)
     n, k, d = 400, 4, 8

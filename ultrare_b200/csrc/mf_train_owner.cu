@@ -449,6 +449,10 @@ radix_scatter_kernel(const ure_mf_shard_t* shards, int pass, int npass, const in
 // microseconds each): the bodies above run as virtual blocks of a co-resident grid, with a grid barrier where a launch
 // boundary was.  Dynamic shared memory: max(smem_rows, kRadixWarps * 256) ints.
 //   count + histogram of pass 0 | row-offset scan + digit scan | scatter | histogram | digit scan | scatter ...
+// The bodies read their source records with __ldg although a later pass reads what an earlier pass of THIS launch
+// wrote: up to three passes (rows < 2^24) no buffer is read through the non-coherent path, rewritten and read again
+// inside the launch (pass p reads only what pass p - 1 wrote into a buffer nobody has read yet), and every grid barrier
+// ends in an acquire that drops the SM's L1 lines anyway.
 __global__ void __launch_bounds__(kRadixThreads)
 owner_setup_kernel(const ure_mf_shard_t* shards, int n_shards, int smem_rows, int cb, int npass, int* __restrict__ hist,
                    unsigned* unsorted) {

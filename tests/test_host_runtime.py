@@ -174,3 +174,31 @@ def test_owner_smem_bytes_grows_with_every_capacity():
     assert h.ure_mf_owner_smem_bytes(16, 100, 8016, 8016, 7, 1) > base
     assert h.ure_mf_owner_smem_bytes(64, 100, 8000, 8000, 7, 1) > base
     assert h.ure_mf_owner_smem_bytes(16, 100, 8000, 4000, 7, 0) < h.ure_mf_owner_smem_bytes(16, 100, 8000, 8000, 7, 0)
+
+
+def test_host_stage_copy_copies_every_size_and_requires_an_aligned_destination():
+    """ure_host_stage_copy (non-temporal stores into page-locked staging memory; the host half of every upload): 64-byte
+    main loop, 16-byte loop, byte tail; any source alignment; a destination off the 16-byte grid is an error."""
+    _, h = _lib()
+    rng = np.random.default_rng(1)
+    src_all = rng.integers(0, 256, 1_000_200, dtype=np.uint8)
+    raw = np.zeros(1_000_200 + 64, dtype=np.uint8)
+    o = (-raw.ctypes.data) % 64
+    dst_all = raw[o:o + 1_000_200]
+    assert dst_all.ctypes.data % 64 == 0
+    for nbytes in (0, 1, 15, 16, 17, 63, 64, 65, 4097, 1_000_003):
+        for soff in (0, 1, 7, 16):
+            dst_all[:] = 0
+            src = src_all[soff:soff + nbytes]
+            assert h.ure_host_stage_copy(C.c_void_p(dst_all.ctypes.data), C.c_void_p(src.ctypes.data), nbytes) == 0
+            assert np.array_equal(dst_all[:nbytes], src) and not dst_all[nbytes:nbytes + 64].any()
+    assert h.ure_host_stage_copy(C.c_void_p(dst_all.ctypes.data + 8), C.c_void_p(src_all.ctypes.data), 64) != 0
+    assert b"16-byte aligned" in h.ure_last_error()
+
+
+def test_scratch_size_queries_are_positive_and_monotone():
+    """The *_bytes entry points a caller sizes its scratch tensors with (host-only)."""
+    _, h = _lib()
+    assert h.ure_mf_train_workspace_bytes() > 0 and h.ure_sinkhorn_workspace_bytes() > 0
+    assert 0 < h.ure_mf_owner_radix_bytes(1) < h.ure_mf_owner_radix_bytes(5)
+    assert h.ure_partition_blocks() >= 1

@@ -43,3 +43,29 @@ def cuda_dev():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     return torch.device("cuda:0")
+
+
+def collect_results(procs, q, n, timeout=300.0, poll=1.0):
+    """{rank: result} from `n` worker processes that each put (rank, result) on `q`.  A worker that dies first (an
+    exception on one rank leaves the others waiting in a collective) ends the wait at once: the survivors are killed
+    and the test fails with the exit codes, instead of holding the GPUs until the time-out."""
+    import queue
+    import time
+    results, deadline = {}, time.monotonic() + timeout
+    while len(results) < n:
+        try:
+            rank, res = q.get(timeout=poll)
+            results[rank] = res
+            continue
+        except queue.Empty:
+            pass
+        dead = [p.exitcode for p in procs if p.exitcode not in (None, 0)]
+        if dead or time.monotonic() > deadline:
+            for p in procs:
+                if p.is_alive():
+                    p.kill()
+            for p in procs:
+                p.join(10)
+            pytest.fail(f"workers failed: exit codes {[p.exitcode for p in procs]}" if dead else
+                        f"no result from {n - len(results)} worker(s) after {timeout:.0f} s")
+    return results

@@ -306,3 +306,36 @@ def test_balanced_rounding_oracle_reaches_the_exact_emd_assignment():
     assert np.array_equal(bal, emd)
     rows = np.arange(n)
     assert abs(float(M[rows, bal].sum()) - float(M[rows, emd].sum())) < 1e-3
+
+
+def _talker(rank, q, fail):
+    import time
+    if fail and rank == 1:
+        raise RuntimeError("rank 1 breaks")
+    if fail:
+        time.sleep(120)                    # rank 0 would wait in a collective
+    q.put((rank, rank * 10))
+
+
+def test_collect_results_ends_at_once_when_a_worker_dies():
+    """The harness of the 2-GPU test (conftest.collect_results): results of all workers; and a worker that raises ends
+    the wait within seconds -- the survivor is killed -- instead of after the time-out (that cost the round its last
+    GPU minutes once)."""
+    import time
+    from conftest import collect_results
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_talker, args=(r, q, False)) for r in range(2)]
+    for p in procs:
+        p.start()
+    assert collect_results(procs, q, 2, timeout=60) == {0: 0, 1: 10}
+    for p in procs:
+        p.join(30)
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_talker, args=(r, q, True)) for r in range(2)]
+    for p in procs:
+        p.start()
+    t0 = time.monotonic()
+    with pytest.raises(pytest.fail.Exception, match="exit codes"):
+        collect_results(procs, q, 2, timeout=100)
+    assert time.monotonic() - t0 < 60 and not any(p.is_alive() for p in procs)

@@ -5,6 +5,7 @@ import socket
 
 import numpy as np
 import pytest
+from conftest import collect_results
 
 pytestmark = pytest.mark.gpu
 N_USER, N_ITEM, BATCH, SEED = 1508, 2071, 3000, 42
@@ -163,7 +164,7 @@ def test_two_rank_sisa_and_sinkhorn_equal_single_gpu(cuda_dev):
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    results = dict(q.get(timeout=300) for _ in range(2))
+    results = collect_results(procs, q, 2, timeout=300)      # a rank that raises ends the test at once
     for p in procs:
         p.join(60)
         assert p.exitcode == 0

@@ -1146,7 +1146,15 @@ class ArenaShardBatch(ShardBatch):
                 self.prepare_launches = len(groups) * (2 + 3 * npass)
             elif lay.owner:
                 # count + scan, radix passes, [inverse visiting orders], [plan]
-                self.prepare_launches = 2 + 3 * npass + (1 if perms is not None else 0) + (0 if self.optimistic else 1)
+                # one cooperative launch for batches of up to 8 M interactions (csrc/mf_batch.cu: flags & 8), unless
+                # URE_SETUP_FUSED says otherwise
+                try:
+                    fused_env = int(os.environ.get("URE_SETUP_FUSED", "-1"))
+                except ValueError:
+                    fused_env = 0
+                fused = fused_env > 0 or (fused_env < 0 and int(lay.n_total) <= (8 << 20))
+                self.prepare_launches = (1 if fused else 2 + 3 * npass) + (1 if perms is not None else 0) + \
+                    (0 if self.optimistic else 1)
                 self.launches_per_pass += self.prepare_launches
             ev = torch.cuda.Event()
             ev.record()

@@ -17,7 +17,6 @@ from ultrare_b200.read import RatingData, loadData  # noqa: E402
 E = int(sys.argv[1]) if len(sys.argv) > 1 else 50
 d = udist.init_from_env()
 w = bench.host_workload(0, E)
-from oracle import sisa as osisa
 rs = np.random.RandomState(1)
 perm = rs.permutation(w["n_user"])
 sp = bench.group_and_split(w, [perm[i::5].tolist() for i in range(5)])
